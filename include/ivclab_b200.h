@@ -1,0 +1,157 @@
+/*
+ * ivclab_b200.h -- C ABI of the B200-native ivclab per-block coding loop.
+ *
+ * This is the drop-in boundary: a reference-side binding (ctypes from Python,
+ * see INTEGRATION.md) needs nothing but this header and libivcb200.so.
+ * Every entry point
+ *   - takes plain device pointers + sizes (no torch / numpy types),
+ *   - enqueues its kernels on the caller's stream (cudaStream_t passed as
+ *     void*; NULL = legacy default stream) on `device`, and returns without
+ *     synchronising,
+ *   - allocates nothing and keeps no mutable global state (the caller owns
+ *     inputs, outputs and workspaces),
+ *   - returns IVC_OK (0) or a negative IVC_ERR_* code; it never throws.
+ *
+ * Reference interfaces replaced (file:line under n2oblife/ivclab):
+ *   ivclab/signal/dct.py:12-46            DiscreteCosineTransform.transform / inverse_transform
+ *   ivclab/quantization/patchquant.py:39-78  PatchQuant.get_quantization_table / quantize / dequantize
+ *   ivclab/utils/shape.py:21-36           ZigZag.flatten / unflatten
+ *   ivclab/video/motion.py:8-97           MotionCompensator.compute_motion_vector / reconstruct_with_motion_vector
+ *   ivclab/image/intracodec.py:66-75,115-124   the chained calls the fused entry points replace
+ *   ivclab/video/videocodec.py:68-74      P-frame residual / reconstruction adds
+ *
+ * Layout vocabulary: a "patched" array is [n0, n1, C, 8, 8] (Patcher.patch,
+ * shape.py:45-54); a "scan" array is [n0, n1, C, 64] in zig-zag order; an
+ * image is HWC, a luma plane is HW.  Strides are in ELEMENTS.
+ */
+#ifndef IVCLAB_B200_H
+#define IVCLAB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IVC_ABI_VERSION 1
+
+/* element types */
+#define IVC_U8   0
+#define IVC_I32  1
+#define IVC_F32  2
+#define IVC_F64  3
+#define IVC_I64  4
+
+/* status codes */
+#define IVC_OK            0
+#define IVC_ERR_ARG      -1   /* null pointer / negative size / bad flag            */
+#define IVC_ERR_DTYPE    -2   /* dtype combination not supported by this entry      */
+#define IVC_ERR_SHAPE    -3   /* shape the reference would reject (e.g. H%8 != 0)   */
+#define IVC_ERR_CUDA     -4   /* a CUDA call failed; see ivc_last_cuda_error()      */
+#define IVC_ERR_WORKSPACE -5  /* workspace too small                                */
+
+/* ME kernel selection */
+#define IVC_ME_AUTO   0   /* integer kernel if both frames are integer-valued in [0,255], else exact-float */
+#define IVC_ME_EXACT  1   /* IEEE order-exact float kernel (numpy summation order, no FMA)                 */
+#define IVC_ME_INT    2   /* packed-u8 integer kernel; caller guarantees integer-valued [0,255] frames     */
+
+int         ivc_abi_version(void);
+const char *ivc_build_info(void);            /* "ivclab_b200 <ver> sm_100a nvcc <ver>" */
+const char *ivc_error_string(int status);
+int         ivc_last_cuda_error(void);       /* cudaError_t of the last failing CUDA call on this thread */
+const char *ivc_last_cuda_error_string(void);
+
+/* ---- a2/a3: 2-D 8x8 DCT-II / DCT-III, orthonormal (dct.py:12-46) -----------------------------
+ * x: patched [n0,n1,C,8,8] with arbitrary element strides (the reference feeds a strided view of
+ * the HWC image, intracodec.py:66).  out: C-contiguous [n0,n1,C,8,8].
+ * in f32 -> out f32 (float arithmetic); in u8/i32/f64 -> out f64.  Arithmetic is op-for-op the
+ * sequence scipy's ducc0 back-end executes, so results are bit-identical to scipy.fft.dct/idct. */
+int ivc_dct8x8(int device, void *stream, int inverse,
+               const void *x, int x_dtype, int64_t n0, int64_t n1, int64_t C,
+               const int64_t strides[5], void *out, int out_dtype);
+
+/* ---- a6: PatchQuant.quantize (patchquant.py:56-60) ------------------------------------------
+ * out[n0,n1,Cout,8,8] = int32(rint(x / table[c])) with numpy broadcasting of C against 3
+ * (C==1 -> Cout=3, C==3 -> Cout=3).  table: device [3,8,8] in table_dtype (F32 or F64).
+ * compute_dtype: F32 only when numpy would divide in float32 (x u8/f32 and table f32), else F64. */
+int ivc_quantize(int device, void *stream,
+                 const void *x, int x_dtype, int64_t n0, int64_t n1, int64_t C,
+                 const int64_t strides[5],
+                 const void *table, int table_dtype, int compute_dtype,
+                 int32_t *out);
+
+/* ---- a7: PatchQuant.dequantize (patchquant.py:74-78) ----------------------------------------
+ * out[n0,n1,3,8,8] = int32(trunc(q * table[c])), product in compute_dtype (F64 for int32 q). */
+int ivc_dequantize(int device, void *stream,
+                   const void *q, int q_dtype, int64_t n0, int64_t n1, int64_t C,
+                   const int64_t strides[5],
+                   const void *table, int table_dtype, int compute_dtype,
+                   int32_t *out);
+
+/* ---- a9/a10: ZigZag.flatten / unflatten (shape.py:21-36) -------------------------------------
+ * nblocks contiguous blocks of 64 elements of elem_size bytes (1,2,4,8).
+ * inverse=0: out[b][order[k]] = x[b][k];  inverse=1: out[b][k] = x[b][order[k]]. */
+int ivc_zigzag(int device, void *stream, int inverse,
+               const void *x, int elem_size, int64_t nblocks, void *out);
+
+/* ---- fused intra forward: patch -> DCT -> quantize -> flatten (intracodec.py:66-75) ----------
+ * img: n_frames HWC images, C in {1,3}, dtype F64, pixel stride C, row stride W*C,
+ * frame stride frame_stride elements.  H, W multiples of 8.
+ * out: [n_frames, H/8, W/8, 3, 64] int32. */
+int ivc_intra_forward(int device, void *stream,
+                      const void *img, int dtype, int64_t n_frames, int64_t H, int64_t W, int64_t C,
+                      int64_t frame_stride,
+                      const void *table, int table_dtype,
+                      int32_t *out);
+
+/* ---- fused intra inverse: unflatten -> dequantize -> IDCT -> un-patch (intracodec.py:115-124)
+ * zz: [n_frames, Hp, Wp, C, 64] int32, C in {1,3}.  out: [n_frames, 8*Hp, 8*Wp, 3] F64. */
+int ivc_intra_inverse(int device, void *stream,
+                      const int32_t *zz, int64_t n_frames, int64_t Hp, int64_t Wp, int64_t C,
+                      const void *table, int table_dtype,
+                      void *out, int out_dtype);
+
+/* ---- a13: MotionCompensator.compute_motion_vector (motion.py:8-58) ---------------------------
+ * ref, cur: n_frames luma planes [H,W] (dtype F32 or F64, both the same), contiguous rows.
+ * mv_out: [n_frames, H/8, W/8, 1] int64, index = (dy+sr)*(2sr+1) + (dx+sr); first minimum in
+ * (dy asc, dx asc) order over in-bounds candidates.
+ * workspace: needed for IVC_ME_AUTO / IVC_ME_INT, ivc_me_workspace_bytes() bytes (else NULL). */
+int64_t ivc_me_workspace_bytes(int64_t n_frames, int64_t H, int64_t W);
+int ivc_me_full_search(int device, void *stream,
+                       const void *ref, const void *cur, int dtype,
+                       int64_t n_frames, int64_t H, int64_t W,
+                       int64_t ref_frame_stride, int64_t cur_frame_stride,
+                       int search_range, int mode,
+                       int64_t *mv_out, void *workspace, int64_t workspace_bytes);
+
+/* ---- a14: MotionCompensator.reconstruct_with_motion_vector (motion.py:60-97) -----------------
+ * ref: [n_frames, H, W, C] of elem_size-byte elements; mv: [n_frames, H/8, W/8, 1] int64.
+ * Blocks whose source window leaves the frame are zero. */
+int ivc_mc_reconstruct(int device, void *stream,
+                       const void *ref, int elem_size, int64_t n_frames, int64_t H, int64_t W, int64_t C,
+                       const int64_t *mv, int search_range, void *out);
+
+/* ---- a15 fused: P-frame encoder half (videocodec.py:68-71 + intracodec.py:66-75) -------------
+ * pred = MC(ref, mv); residual = cur - pred; zz = flatten(quantize(dct(patch(residual)))).
+ * cur/ref: [n_frames,H,W] F64.  pred_out may be NULL.  zz_out: [n_frames,Hp,Wp,3,64] int32. */
+int ivc_pframe_forward(int device, void *stream,
+                       const void *cur, const void *ref, const int64_t *mv, int dtype,
+                       int64_t n_frames, int64_t H, int64_t W, int search_range,
+                       const void *table, int table_dtype,
+                       void *pred_out, int32_t *zz_out);
+
+/* ---- a15 fused: P-frame decoder half (intracodec.py:115-124 + videocodec.py:74) --------------
+ * recon = pred + idct(dequantize(unflatten(zz[..., 0, :])))[channel 0]  (luminance table).
+ * zz: [n_frames,Hp,Wp,Czz,64] int32 (channel 0 is used).  Either pred != NULL, or pred == NULL
+ * and (ref, mv) are given and the prediction is re-gathered.  recon_out: [n_frames,H,W] F64. */
+int ivc_pframe_inverse(int device, void *stream,
+                       const int32_t *zz, int64_t Czz,
+                       const void *pred, const void *ref, const int64_t *mv, int dtype,
+                       int64_t n_frames, int64_t H, int64_t W, int search_range,
+                       const void *table, int table_dtype,
+                       void *recon_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IVCLAB_B200_H */

@@ -1,0 +1,26 @@
+"""ivclab_b200 -- B200-native (sm_100a) implementation of ivclab's per-block coding loop.
+
+Drop-in classes with the reference's names, signatures and array conventions:
+
+    DiscreteCosineTransform   (ivclab.signal)         transform / inverse_transform
+    PatchQuant                (ivclab.quantization)   get_quantization_table / quantize / dequantize
+    ZigZag, Patcher           (ivclab.utils)          flatten / unflatten, patch / unpatch
+    MotionCompensator         (ivclab.video)          compute_motion_vector / reconstruct_with_motion_vector
+
+plus the fused coders (:class:`IntraBlockCoder`, :class:`PFrameBlockCoder`), the sharding
+helpers (:mod:`ivclab_b200.shard`) and :func:`install` / :func:`inject` to run the unmodified
+reference codecs on top.  Everything executes in hand-written CUDA kernels behind the C ABI of
+``include/ivclab_b200.h``; there is no CPU fallback -- importing this package fails if the
+extension has not been built, and calling it fails if no CUDA device is visible.
+"""
+from . import _lib  # noqa: F401  (loads libivcb200.so or raises)
+from .codec import IntraBlockCoder, PFrameBlockCoder
+from .install import inject, install
+from .quantization import PatchQuant
+from .signal import DiscreteCosineTransform
+from .utils import Patcher, ZigZag
+from .video import MotionCompensator
+
+__version__ = "0.1.0"
+__all__ = ["DiscreteCosineTransform", "PatchQuant", "ZigZag", "Patcher", "MotionCompensator",
+           "IntraBlockCoder", "PFrameBlockCoder", "install", "inject"]

@@ -1,0 +1,80 @@
+"""ctypes binding of libivcb200.so (the C ABI declared in include/ivclab_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, an
+exception is raised.  Build it with ``python -c "import __graft_entry__ as g; g.build()"``
+(or ``python build_ext.py``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_C", "libivcb200.so")
+
+# element type codes (include/ivclab_b200.h)
+U8, I32, F32, F64, I64 = 0, 1, 2, 3, 4
+ME_AUTO, ME_EXACT, ME_INT = 0, 1, 2
+OK, ERR_ARG, ERR_DTYPE, ERR_SHAPE, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4, -5
+
+_i, _i64, _p = C.c_int, C.c_int64, C.c_void_p
+_s5 = C.POINTER(C.c_int64)
+
+# name -> (restype, argtypes); kept in one table so tests can check it against the header
+SIGNATURES = {
+    "ivc_abi_version": (_i, []),
+    "ivc_build_info": (C.c_char_p, []),
+    "ivc_error_string": (C.c_char_p, [_i]),
+    "ivc_last_cuda_error": (_i, []),
+    "ivc_last_cuda_error_string": (C.c_char_p, []),
+    "ivc_dct8x8": (_i, [_i, _p, _i, _p, _i, _i64, _i64, _i64, _s5, _p, _i]),
+    "ivc_quantize": (_i, [_i, _p, _p, _i, _i64, _i64, _i64, _s5, _p, _i, _i, _p]),
+    "ivc_dequantize": (_i, [_i, _p, _p, _i, _i64, _i64, _i64, _s5, _p, _i, _i, _p]),
+    "ivc_zigzag": (_i, [_i, _p, _i, _p, _i, _i64, _p]),
+    "ivc_intra_forward": (_i, [_i, _p, _p, _i, _i64, _i64, _i64, _i64, _i64, _p, _i, _p]),
+    "ivc_intra_inverse": (_i, [_i, _p, _p, _i64, _i64, _i64, _i64, _p, _i, _p, _i]),
+    "ivc_me_workspace_bytes": (_i64, [_i64, _i64, _i64]),
+    "ivc_me_full_search": (_i, [_i, _p, _p, _p, _i, _i64, _i64, _i64, _i64, _i64, _i, _i, _p, _p, _i64]),
+    "ivc_mc_reconstruct": (_i, [_i, _p, _p, _i, _i64, _i64, _i64, _i64, _p, _i, _p]),
+    "ivc_pframe_forward": (_i, [_i, _p, _p, _p, _p, _i, _i64, _i64, _i64, _i, _p, _i, _p, _p]),
+    "ivc_pframe_inverse": (_i, [_i, _p, _p, _i64, _p, _p, _p, _i, _i64, _i64, _i64, _i, _p, _i, _p]),
+}
+
+
+class IvcError(RuntimeError):
+    """A C-ABI call returned a negative status."""
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built. ivclab_b200 has no CPU "
+            "fallback. Build it with `python -c 'import __graft_entry__ as g; g.build()'`.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)            # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ivc_abi_version() != 1:
+        raise ImportError(f"{LIB_PATH}: ABI version {lib.ivc_abi_version()} != 1 (stale build?)")
+    return lib
+
+
+lib = _load()
+
+
+def check(status: int, what: str) -> None:
+    """Map a status code to the exception the reference would have produced."""
+    if status == OK:
+        return
+    msg = f"{what}: {lib.ivc_error_string(status).decode()}"
+    if status == ERR_CUDA:
+        msg += f" [{lib.ivc_last_cuda_error_string().decode()}]"
+        raise IvcError(msg)
+    if status in (ERR_SHAPE, ERR_DTYPE):
+        raise ValueError(msg)
+    raise IvcError(msg)
+
+
+def strides5(s):
+    return (C.c_int64 * 5)(*[int(v) for v in s])

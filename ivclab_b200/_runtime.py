@@ -1,0 +1,74 @@
+"""Host-side plumbing shared by the drop-in classes: numpy <-> device tensors,
+dtype codes, current stream.  PyTorch is used for device memory and streams only."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_CODES = {torch.uint8: _lib.U8, torch.int32: _lib.I32, torch.float32: _lib.F32,
+          torch.float64: _lib.F64, torch.int64: _lib.I64}
+_NP_OK = (np.uint8, np.int8, np.int16, np.int32, np.int64, np.float16, np.float32, np.float64, np.bool_)
+
+
+def require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("ivclab_b200 runs on a CUDA device (B200, sm_100a) only; there is no CPU "
+                           "fallback and no CUDA device is visible")
+
+
+def code(dtype: torch.dtype) -> int:
+    try:
+        return _CODES[dtype]
+    except KeyError:
+        raise ValueError(f"dtype {dtype} is not supported on this path") from None
+
+
+def to_device(x, device=None):
+    """-> (cuda tensor, was_numpy).  numpy arrays (incl. strided views such as
+    Patcher.patch output) are copied H2D keeping their strides; cuda tensors pass through."""
+    require_cuda()
+    if isinstance(x, torch.Tensor):
+        if not x.is_cuda:
+            return x.to(device or "cuda"), False
+        return x, False
+    a = np.asarray(x)
+    if a.dtype.type not in _NP_OK:
+        a = a.astype(np.float64)
+    if any(s < 0 for s in a.strides):
+        a = np.ascontiguousarray(a)              # torch cannot wrap negative strides
+    with _quiet_nonwritable():                   # read-only arrays are only read
+        t = torch.from_numpy(a)
+    return t.to(device or "cuda"), True
+
+
+class _quiet_nonwritable:
+    def __enter__(self):
+        import warnings
+        self._w = warnings.catch_warnings()
+        self._w.__enter__()
+        warnings.simplefilter("ignore", UserWarning)
+
+    def __exit__(self, *a):
+        self._w.__exit__(*a)
+
+
+def to_host(t: torch.Tensor, as_numpy: bool):
+    return t.cpu().numpy() if as_numpy else t
+
+
+def stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def dev_index(t: torch.Tensor) -> int:
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def aligned16(t: torch.Tensor) -> torch.Tensor:
+    """The fused kernels move 16-byte vectors: hand them a contiguous, 16-byte aligned buffer."""
+    t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()
+    return t

@@ -1,0 +1,151 @@
+"""Fused per-block coding loop: what ``IntraCodec.image2symbols`` / ``symbols2image``
+(ivclab/image/intracodec.py:66-75, :115-124) and the P-frame branch of the video codecs
+(ivclab/video/videocodec.py:52-75; exercises/ch4/E4-1.py:257-306) chain together, as ONE kernel
+per direction.  Results are identical to calling the four drop-in classes one after another
+(and therefore to the reference); the difference is HBM traffic: each sample is read once and
+written once.  All entry points accept a single image/frame or a batch (leading axis)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._runtime import aligned16, code, dev_index, stream_ptr, to_device, to_host
+from .quantization import PatchQuant
+from .video import MotionCompensator
+
+__all__ = ["IntraBlockCoder", "PFrameBlockCoder"]
+
+
+class IntraBlockCoder:
+    """patch -> DCT -> quantize -> zig-zag (``forward``) and its inverse (``inverse``)."""
+
+    def __init__(self, quantization_scale=1.0, luminance=None, chrominance=None):
+        self.quant = PatchQuant(quantization_scale, luminance, chrominance)
+
+    @property
+    def quantization_scale(self):
+        return self.quant.quantization_scale
+
+    def forward(self, img):
+        """HWC float64 image ``[H, W, C]`` or batch ``[N, H, W, C]`` (C in {1,3}; a 2-D ``[H, W]``
+        plane is treated as C=1) -> int32 scan indices ``[(N,) H/8, W/8, 3, 64]``."""
+        t, was_np = to_device(img)
+        if t.ndim == 2:
+            t = t[..., None]
+        batched = t.ndim == 4
+        if t.ndim not in (3, 4):
+            raise ValueError(f"expected [H,W], [H,W,C] or [N,H,W,C], got shape {tuple(t.shape)}")
+        t = aligned16(t.to(torch.float64))
+        v = t if batched else t[None]
+        N, H, W, C = v.shape
+        _, dtab = self.quant._table_on(v.device)
+        out = torch.empty((N, H // 8, W // 8, 3, 64), dtype=torch.int32, device=v.device)
+        st = _lib.lib.ivc_intra_forward(dev_index(v), stream_ptr(v.device), v.data_ptr(), _lib.F64, N, H, W, C,
+                                        H * W * C, dtab.data_ptr(), code(dtab.dtype), out.data_ptr())
+        _lib.check(st, "ivc_intra_forward")
+        return to_host(out if batched else out[0], was_np)
+
+    def inverse(self, zz):
+        """int32 scan indices ``[(N,) Hp, Wp, C, 64]`` (C in {1,3}) -> float64 ``[(N,) 8Hp, 8Wp, 3]``."""
+        t, was_np = to_device(zz)
+        batched = t.ndim == 5
+        if t.ndim not in (4, 5) or t.shape[-1] != 64:
+            raise ValueError(f"expected [Hp,Wp,C,64] or [N,Hp,Wp,C,64], got shape {tuple(t.shape)}")
+        t = aligned16(t.to(torch.int32))
+        v = t if batched else t[None]
+        N, Hp, Wp, C, _ = v.shape
+        _, dtab = self.quant._table_on(v.device)
+        out = torch.empty((N, Hp * 8, Wp * 8, 3), dtype=torch.float64, device=v.device)
+        st = _lib.lib.ivc_intra_inverse(dev_index(v), stream_ptr(v.device), v.data_ptr(), N, Hp, Wp, C,
+                                        dtab.data_ptr(), code(dtab.dtype), out.data_ptr(), _lib.F64)
+        _lib.check(st, "ivc_intra_inverse")
+        return to_host(out if batched else out[0], was_np)
+
+
+class PFrameBlockCoder:
+    """Motion estimation, then MC + residual fused into the forward transform and
+    prediction + residual fused into the inverse transform (luma planes, float64)."""
+
+    def __init__(self, quantization_scale=1.0, search_range=4, me_mode="auto", luminance=None, chrominance=None):
+        self.quant = PatchQuant(quantization_scale, luminance, chrominance)
+        self.motion_comp = MotionCompensator(search_range, me_mode)
+
+    @property
+    def search_range(self):
+        return self.motion_comp.search_range
+
+    def estimate(self, ref, cur):
+        """Batched ``compute_motion_vector``: ``[(N,) H, W]`` x2 -> int64 ``[(N,) H/8, W/8, 1]``."""
+        r, was_np = to_device(ref)
+        c, _ = to_device(cur, r.device)
+        batched = r.ndim == 3
+        dt = torch.float32 if (r.dtype == torch.float32 and c.dtype == torch.float32) else torch.float64
+        r = r.to(dt).contiguous()
+        c = c.to(dt).contiguous()
+        rv, cv = (r, c) if batched else (r[None], c[None])
+        N, H, W = rv.shape
+        if H % 8 or W % 8:
+            raise IndexError(f"frame sides ({H}, {W}) must be multiples of the 8x8 block size")
+        mv = torch.empty((N, H // 8, W // 8, 1), dtype=torch.int64, device=r.device)
+        mode = {"auto": _lib.ME_AUTO, "exact": _lib.ME_EXACT, "int": _lib.ME_INT}[self.motion_comp.me_mode]
+        ws, ws_bytes = None, 0
+        if mode != _lib.ME_EXACT:
+            ws_bytes = _lib.lib.ivc_me_workspace_bytes(N, H, W)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=r.device)
+        st = _lib.lib.ivc_me_full_search(dev_index(rv), stream_ptr(rv.device), rv.data_ptr(), cv.data_ptr(), code(dt),
+                                         N, H, W, H * W, H * W, int(self.search_range), mode, mv.data_ptr(),
+                                         ws.data_ptr() if ws is not None else None, ws_bytes)
+        _lib.check(st, "ivc_me_full_search")
+        return to_host(mv if batched else mv[0], was_np)
+
+    def forward(self, cur, ref, mv, return_prediction=False):
+        """residual = cur - MC(ref, mv); -> scan indices ``[(N,) Hp, Wp, 3, 64]`` (and the prediction)."""
+        c, was_np = to_device(cur)
+        r, _ = to_device(ref, c.device)
+        m, _ = to_device(mv, c.device)
+        batched = c.ndim == 3
+        c = aligned16(c.to(torch.float64))
+        r = r.to(torch.float64).contiguous()
+        m = m.to(torch.int64).contiguous()
+        cv = c if batched else c[None]
+        N, H, W = cv.shape
+        _, dtab = self.quant._table_on(c.device)
+        zz = torch.empty((N, H // 8, W // 8, 3, 64), dtype=torch.int32, device=c.device)
+        pred = torch.empty_like(cv) if return_prediction else None
+        st = _lib.lib.ivc_pframe_forward(dev_index(c), stream_ptr(c.device), cv.data_ptr(), r.data_ptr(), m.data_ptr(),
+                                         _lib.F64, N, H, W, int(self.search_range), dtab.data_ptr(), code(dtab.dtype),
+                                         pred.data_ptr() if pred is not None else None, zz.data_ptr())
+        _lib.check(st, "ivc_pframe_forward")
+        zz = zz if batched else zz[0]
+        if return_prediction:
+            return to_host(zz, was_np), to_host(pred if batched else pred[0], was_np)
+        return to_host(zz, was_np)
+
+    def inverse(self, zz, pred=None, ref=None, mv=None):
+        """recon = prediction + idct(dequantize(unflatten(zz[..., 0, :]))) with the luminance table
+        (what ``symbols2image(...)[..., 0]`` returns, E4-1.py:284-306).  Give either ``pred`` or ``(ref, mv)``."""
+        z, was_np = to_device(zz)
+        batched = z.ndim == 5
+        z = aligned16(z.to(torch.int32))
+        zv = z if batched else z[None]
+        N, Hp, Wp, Czz, _ = zv.shape
+        H, W = Hp * 8, Wp * 8
+        _, dtab = self.quant._table_on(z.device)
+        p = r = m = None
+        if pred is not None:
+            p = aligned16(to_device(pred, z.device)[0].to(torch.float64))
+        else:
+            if ref is None or mv is None:
+                raise ValueError("give either pred, or ref and mv")
+            r = to_device(ref, z.device)[0].to(torch.float64).contiguous()
+            m = to_device(mv, z.device)[0].to(torch.int64).contiguous()
+        out = torch.empty((N, H, W), dtype=torch.float64, device=z.device)
+        st = _lib.lib.ivc_pframe_inverse(dev_index(z), stream_ptr(z.device), zv.data_ptr(), Czz,
+                                         p.data_ptr() if p is not None else None,
+                                         r.data_ptr() if r is not None else None,
+                                         m.data_ptr() if m is not None else None,
+                                         _lib.F64, N, H, W, int(self.search_range), dtab.data_ptr(), code(dtab.dtype),
+                                         out.data_ptr())
+        _lib.check(st, "ivc_pframe_inverse")
+        return to_host(out if batched else out[0], was_np)

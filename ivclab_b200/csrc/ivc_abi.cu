@@ -1,0 +1,237 @@
+// ivc_abi.cu -- the extern "C" surface declared in include/ivclab_b200.h.
+// Argument validation lives here; kernels live in ivc_transform.cu / ivc_motion.cu.
+#include "ivc_common.cuh"
+
+#ifndef IVC_VERSION
+#define IVC_VERSION "0.1.0"
+#endif
+#define IVC_STR2(x) #x
+#define IVC_STR(x) IVC_STR2(x)
+
+namespace {
+
+thread_local cudaError_t g_last_cuda = cudaSuccess;
+
+int cuda_fail(cudaError_t e) {
+    g_last_cuda = e;
+    return IVC_ERR_CUDA;
+}
+
+int enter(int device) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(e);
+    return IVC_OK;
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline bool is_float(int dt) { return dt == IVC_F32 || dt == IVC_F64; }
+inline int elem_size(int dt) {
+    switch (dt) {
+        case IVC_U8: return 1;
+        case IVC_I32: case IVC_F32: return 4;
+        case IVC_F64: case IVC_I64: return 8;
+        default: return 0;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int ivc_abi_version(void) { return IVC_ABI_VERSION; }
+
+const char *ivc_build_info(void) {
+    return "ivclab_b200 " IVC_VERSION " sm_100a nvcc " IVC_STR(__CUDACC_VER_MAJOR__) "." IVC_STR(__CUDACC_VER_MINOR__);
+}
+
+const char *ivc_error_string(int status) {
+    switch (status) {
+        case IVC_OK: return "ok";
+        case IVC_ERR_ARG: return "invalid argument (null/misaligned pointer, negative size or bad flag)";
+        case IVC_ERR_DTYPE: return "unsupported dtype combination";
+        case IVC_ERR_SHAPE: return "unsupported shape (frame sides must be multiples of 8; C must broadcast against 3)";
+        case IVC_ERR_CUDA: return "CUDA error (see ivc_last_cuda_error_string)";
+        case IVC_ERR_WORKSPACE: return "workspace missing or too small";
+        default: return "unknown status";
+    }
+}
+
+int ivc_last_cuda_error(void) { return (int)g_last_cuda; }
+const char *ivc_last_cuda_error_string(void) { return cudaGetErrorString(g_last_cuda); }
+
+int ivc_dct8x8(int device, void *stream, int inverse, const void *x, int x_dtype, int64_t n0, int64_t n1, int64_t C,
+               const int64_t strides[5], void *out, int out_dtype) {
+    if (n0 < 0 || n1 < 0 || C < 0 || !strides) return IVC_ERR_ARG;
+    if (n0 * n1 * C == 0) return IVC_OK;
+    if (!x || !out) return IVC_ERR_ARG;
+    if (x_dtype != IVC_U8 && x_dtype != IVC_I32 && x_dtype != IVC_F32 && x_dtype != IVC_F64) return IVC_ERR_DTYPE;
+    const int want = (x_dtype == IVC_F32) ? IVC_F32 : IVC_F64;          // scipy keeps f32, promotes the rest to f64
+    if (out_dtype != want) return IVC_ERR_DTYPE;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_dct(device, (cudaStream_t)stream, inverse != 0, x, x_dtype, n0, n1, C, strides, out,
+                                    want == IVC_F32);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
+static int quant_common(int device, void *stream, bool dequant, const void *x, int x_dtype, int64_t n0, int64_t n1,
+                        int64_t C, const int64_t strides[5], const void *table, int table_dtype, int compute_dtype,
+                        int32_t *out) {
+    if (n0 < 0 || n1 < 0 || !strides) return IVC_ERR_ARG;
+    if (C != 1 && C != 3) return IVC_ERR_SHAPE;                         // numpy broadcasting against [3,8,8]
+    if (!table || !is_float(table_dtype) || !is_float(compute_dtype)) return IVC_ERR_DTYPE;
+    if (n0 * n1 == 0) return IVC_OK;
+    if (!x || !out) return IVC_ERR_ARG;
+    if (compute_dtype == IVC_F32) {
+        if (table_dtype != IVC_F32) return IVC_ERR_DTYPE;
+        if (x_dtype != IVC_U8 && x_dtype != IVC_F32 && x_dtype != IVC_I32) return IVC_ERR_DTYPE;
+    } else {
+        if (elem_size(x_dtype) == 0) return IVC_ERR_DTYPE;
+    }
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_quant(device, (cudaStream_t)stream, dequant, x, x_dtype, n0, n1, C, strides, table,
+                                      table_dtype, compute_dtype == IVC_F32, out);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
+int ivc_quantize(int device, void *stream, const void *x, int x_dtype, int64_t n0, int64_t n1, int64_t C,
+                 const int64_t strides[5], const void *table, int table_dtype, int compute_dtype, int32_t *out) {
+    return quant_common(device, stream, false, x, x_dtype, n0, n1, C, strides, table, table_dtype, compute_dtype, out);
+}
+
+int ivc_dequantize(int device, void *stream, const void *q, int q_dtype, int64_t n0, int64_t n1, int64_t C,
+                   const int64_t strides[5], const void *table, int table_dtype, int compute_dtype, int32_t *out) {
+    return quant_common(device, stream, true, q, q_dtype, n0, n1, C, strides, table, table_dtype, compute_dtype, out);
+}
+
+int ivc_zigzag(int device, void *stream, int inverse, const void *x, int elem_sz, int64_t nblocks, void *out) {
+    if (nblocks < 0) return IVC_ERR_ARG;
+    if (elem_sz != 1 && elem_sz != 2 && elem_sz != 4 && elem_sz != 8) return IVC_ERR_DTYPE;
+    if (nblocks == 0) return IVC_OK;
+    if (!x || !out || x == out) return IVC_ERR_ARG;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_zigzag(device, (cudaStream_t)stream, inverse != 0, x, elem_sz, nblocks, out);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
+int ivc_intra_forward(int device, void *stream, const void *img, int dtype, int64_t n_frames, int64_t H, int64_t W,
+                      int64_t C, int64_t frame_stride, const void *table, int table_dtype, int32_t *out) {
+    if (n_frames < 0 || H < 0 || W < 0 || frame_stride < 0) return IVC_ERR_ARG;
+    if (dtype != IVC_F64 || !is_float(table_dtype)) return IVC_ERR_DTYPE;
+    if ((H & 7) || (W & 7) || (C != 1 && C != 3)) return IVC_ERR_SHAPE;
+    if (n_frames * H * W == 0) return IVC_OK;
+    if (!img || !table || !out) return IVC_ERR_ARG;
+    if (!aligned16(img) || !aligned16(out) || (frame_stride & 1)) return IVC_ERR_ARG;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_forward(device, (cudaStream_t)stream, img, n_frames, H, W, (int)C, frame_stride, table,
+                                        table_dtype, out, nullptr, nullptr, 0, nullptr, false);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
+int ivc_intra_inverse(int device, void *stream, const int32_t *zz, int64_t n_frames, int64_t Hp, int64_t Wp, int64_t C,
+                      const void *table, int table_dtype, void *out, int out_dtype) {
+    if (n_frames < 0 || Hp < 0 || Wp < 0) return IVC_ERR_ARG;
+    if (out_dtype != IVC_F64 || !is_float(table_dtype)) return IVC_ERR_DTYPE;
+    if (C != 1 && C != 3) return IVC_ERR_SHAPE;
+    if (n_frames * Hp * Wp == 0) return IVC_OK;
+    if (!zz || !table || !out) return IVC_ERR_ARG;
+    if (!aligned16(zz) || !aligned16(out)) return IVC_ERR_ARG;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_inverse(device, (cudaStream_t)stream, zz, n_frames, Hp, Wp, (int)C, table, table_dtype,
+                                        out, C == 3 ? 0 : 1, nullptr, nullptr, nullptr, 0);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
+int64_t ivc_me_workspace_bytes(int64_t n_frames, int64_t H, int64_t W) {
+    if (n_frames < 0 || H < 0 || W < 0) return -1;
+    const int64_t plane = ((n_frames * H * W + 255) / 256) * 256;
+    return 256 + 2 * plane;                    // [flag | ref8 | cur8]
+}
+
+int ivc_me_full_search(int device, void *stream, const void *ref, const void *cur, int dtype, int64_t n_frames,
+                       int64_t H, int64_t W, int64_t ref_frame_stride, int64_t cur_frame_stride, int search_range,
+                       int mode, int64_t *mv_out, void *workspace, int64_t workspace_bytes) {
+    if (n_frames < 0 || H < 0 || W < 0 || search_range < 0 || search_range > 64) return IVC_ERR_ARG;
+    if (dtype != IVC_F32 && dtype != IVC_F64) return IVC_ERR_DTYPE;
+    if ((H & 7) || (W & 7)) return IVC_ERR_SHAPE;                         // the reference raises on ragged frames
+    if (mode != IVC_ME_AUTO && mode != IVC_ME_EXACT && mode != IVC_ME_INT) return IVC_ERR_ARG;
+    if (n_frames * H * W == 0) return IVC_OK;
+    if (!ref || !cur || !mv_out) return IVC_ERR_ARG;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool f32 = dtype == IVC_F32;
+    cudaError_t e;
+    if (mode == IVC_ME_EXACT) {
+        e = ivc::launch_me_exact(device, st, ref, cur, f32, n_frames, H, W, ref_frame_stride, cur_frame_stride,
+                                 search_range, mv_out, nullptr, 0);
+        return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+    }
+    if (!workspace || workspace_bytes < ivc_me_workspace_bytes(n_frames, H, W)) return IVC_ERR_WORKSPACE;
+    const int64_t plane = ((n_frames * H * W + 255) / 256) * 256;
+    int *flag = (int *)workspace;
+    unsigned char *ref8 = (unsigned char *)workspace + 256, *cur8 = ref8 + plane;
+    e = ivc::launch_me_pack_u8(device, st, ref, cur, f32, n_frames, H, W, ref_frame_stride, cur_frame_stride, ref8, cur8, flag);
+    if (e != cudaSuccess) return cuda_fail(e);
+    // exactly one of the next two kernels does work, chosen by the device-side flag (no host sync)
+    e = ivc::launch_me_int(device, st, ref8, cur8, n_frames, H, W, search_range, mv_out, mode == IVC_ME_AUTO ? flag : nullptr);
+    if (e != cudaSuccess) return cuda_fail(e);
+    if (mode == IVC_ME_AUTO) {
+        e = ivc::launch_me_exact(device, st, ref, cur, f32, n_frames, H, W, ref_frame_stride, cur_frame_stride,
+                                 search_range, mv_out, flag, 1);
+        if (e != cudaSuccess) return cuda_fail(e);
+    }
+    return IVC_OK;
+}
+
+int ivc_mc_reconstruct(int device, void *stream, const void *ref, int elem_sz, int64_t n_frames, int64_t H, int64_t W,
+                       int64_t C, const int64_t *mv, int search_range, void *out) {
+    if (n_frames < 0 || H < 0 || W < 0 || C < 0 || search_range < 0) return IVC_ERR_ARG;
+    if (elem_sz != 1 && elem_sz != 2 && elem_sz != 4 && elem_sz != 8) return IVC_ERR_DTYPE;
+    if ((H & 7) || (W & 7)) return IVC_ERR_SHAPE;
+    if (n_frames * H * W * C == 0) return IVC_OK;
+    if (!ref || !mv || !out || ref == out) return IVC_ERR_ARG;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_mc(device, (cudaStream_t)stream, ref, elem_sz, n_frames, H, W, C, mv, search_range, out);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
+int ivc_pframe_forward(int device, void *stream, const void *cur, const void *ref, const int64_t *mv, int dtype,
+                       int64_t n_frames, int64_t H, int64_t W, int search_range, const void *table, int table_dtype,
+                       void *pred_out, int32_t *zz_out) {
+    if (n_frames < 0 || H < 0 || W < 0 || search_range < 0) return IVC_ERR_ARG;
+    if (dtype != IVC_F64 || !is_float(table_dtype)) return IVC_ERR_DTYPE;
+    if ((H & 7) || (W & 7)) return IVC_ERR_SHAPE;
+    if (n_frames * H * W == 0) return IVC_OK;
+    if (!cur || !ref || !mv || !table || !zz_out) return IVC_ERR_ARG;
+    if (!aligned16(cur) || !aligned16(zz_out) || (pred_out && !aligned16(pred_out))) return IVC_ERR_ARG;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_forward(device, (cudaStream_t)stream, cur, n_frames, H, W, 1, H * W, table, table_dtype,
+                                        zz_out, ref, mv, search_range, pred_out, true);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
+int ivc_pframe_inverse(int device, void *stream, const int32_t *zz, int64_t Czz, const void *pred, const void *ref,
+                       const int64_t *mv, int dtype, int64_t n_frames, int64_t H, int64_t W, int search_range,
+                       const void *table, int table_dtype, void *recon_out) {
+    if (n_frames < 0 || H < 0 || W < 0 || search_range < 0 || Czz < 1) return IVC_ERR_ARG;
+    if (dtype != IVC_F64 || !is_float(table_dtype)) return IVC_ERR_DTYPE;
+    if ((H & 7) || (W & 7)) return IVC_ERR_SHAPE;
+    if (n_frames * H * W == 0) return IVC_OK;
+    if (!zz || !table || !recon_out) return IVC_ERR_ARG;
+    if (!pred && (!ref || !mv)) return IVC_ERR_ARG;
+    if (!aligned16(zz) || !aligned16(recon_out) || (pred && !aligned16(pred))) return IVC_ERR_ARG;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_inverse(device, (cudaStream_t)stream, zz, n_frames, H / 8, W / 8, (int)Czz, table,
+                                        table_dtype, recon_out, 2, pred, ref, mv, search_range);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
+}  // extern "C"

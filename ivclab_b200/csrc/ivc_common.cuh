@@ -1,0 +1,35 @@
+// ivc_common.cuh -- shared declarations between the kernel translation units and the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/ivclab_b200.h"
+
+namespace ivc {
+
+// launchers implemented in ivc_transform.cu
+cudaError_t launch_forward(int device, cudaStream_t st, const void *img, int64_t n, int64_t H, int64_t W, int C,
+                           int64_t frame_stride, const void *table, int table_dtype, int32_t *out,
+                           const void *ref, const int64_t *mv, int sr, void *pred_out, bool pframe);
+cudaError_t launch_inverse(int device, cudaStream_t st, const int32_t *zz, int64_t n, int64_t Hp, int64_t Wp, int Czz,
+                           const void *table, int table_dtype, void *out, int mode,
+                           const void *pred, const void *ref, const int64_t *mv, int sr);
+cudaError_t launch_dct(int device, cudaStream_t st, bool inverse, const void *x, int x_dtype, int64_t n0, int64_t n1,
+                       int64_t C, const int64_t s[5], void *out, bool f32);
+cudaError_t launch_quant(int device, cudaStream_t st, bool dequant, const void *x, int x_dtype, int64_t n0, int64_t n1,
+                         int64_t C, const int64_t s[5], const void *table, int table_dtype, bool f32, int32_t *out);
+cudaError_t launch_zigzag(int device, cudaStream_t st, bool inverse, const void *x, int elem_size, int64_t nblocks,
+                          void *out);
+
+// launchers implemented in ivc_motion.cu
+cudaError_t launch_me_exact(int device, cudaStream_t st, const void *ref, const void *cur, bool f32, int64_t n,
+                            int64_t H, int64_t W, int64_t ref_fs, int64_t cur_fs, int sr, int64_t *mv,
+                            const int *skip_flag, int run_if_flag);
+cudaError_t launch_me_pack_u8(int device, cudaStream_t st, const void *ref, const void *cur, bool f32, int64_t n,
+                              int64_t H, int64_t W, int64_t ref_fs, int64_t cur_fs, unsigned char *ref8,
+                              unsigned char *cur8, int *flag);
+cudaError_t launch_me_int(int device, cudaStream_t st, const unsigned char *ref8, const unsigned char *cur8, int64_t n,
+                          int64_t H, int64_t W, int sr, int64_t *mv, const int *skip_flag);
+cudaError_t launch_mc(int device, cudaStream_t st, const void *ref, int elem_size, int64_t n, int64_t H, int64_t W,
+                      int64_t C, const int64_t *mv, int sr, void *out);
+
+}  // namespace ivc

@@ -1,0 +1,705 @@
+// ivc_transform.cu -- DCT / quantiser / zig-zag kernels for sm_100a.
+//
+// Work decomposition of the fused kernels (K1 forward, K2 inverse, and their P-frame variants):
+//   * a TILE is 8 pixel rows x 12 "block-channels" (12 independent 8x8 transforms):
+//       C == 3 : 4 horizontally adjacent blocks x 3 interleaved channels
+//       C == 1 : 12 horizontally adjacent luma blocks
+//     in both cases one tile row is 96 consecutive doubles (768 B) of the HWC image.
+//   * ONE WARP owns a tile end to end and never synchronises with other warps.  Lane = r + 8u:
+//     in the row pass lane (r,u) transforms pixel row r of the three block-channels (u,0..2);
+//     the 8x8 transposition goes through a warp-private shared-memory buffer; in the column pass
+//     lane (j,u) transforms column j of the same three block-channels.
+//   * global traffic is always 16-byte vector loads/stores in which consecutive lanes touch
+//     consecutive addresses; the de-interleave / zig-zag scatter happens in shared memory.
+//   * the per-warp 8 KB buffer is reused by the phases of a tile (input rows -> transposition ->
+//     output staging); phases are separated by __syncwarp().
+//   * persistent grid: every warp strides over the tile list of the whole batch.
+// HBM traffic is exactly the algorithmic bytes (each input element read once, each output written
+// once); arithmetic is FP64 (14 rounded operations per sample for the 2-D transform).
+#include "ivc_dct.cuh"
+#include "ivc_common.cuh"
+
+namespace ivc {
+
+// ------------------------------------------------------------------------------------------------
+// per-warp scratch geometry (in doubles unless stated)
+// ------------------------------------------------------------------------------------------------
+constexpr int kWarpsPerCta = 8;
+constexpr int kWarpBufBytes = 8192;
+constexpr int kRowPitch = 98;        // 96 doubles of tile row + 2 pad: 784 B == 16 (mod 128)
+constexpr int kTJ = 10;              // transposition buffer: T[u][m*8+j][r], 80-byte rows
+constexpr int kTU = 248;             // 24 rows * 10 + 8 pad: u-planes land 64 B apart (mod 128)
+constexpr int kStageU = 200;         // int32 staging: 3 chunks * 64 ints + 8 pad per u
+
+static_assert(8 * kRowPitch * 8 <= kWarpBufBytes, "row tile must fit");
+static_assert(4 * kTU * 8 <= kWarpBufBytes, "transposition buffer must fit");
+static_assert(4 * kStageU * 4 <= kWarpBufBytes, "staging must fit");
+
+struct TileGeom {
+    int64_t n_frames, H, W;          // pixels
+    int Hp, Wp;                      // blocks
+    int C;                           // channels of the image (1 or 3)
+    int tiles_per_row;               // ceil(Wp / blocks_per_tile)
+    int64_t total_tiles;
+};
+
+__device__ __forceinline__ void tile_coords(const TileGeom &g, int64_t t, int64_t &frame, int &by, int &tx) {
+    tx = (int)(t % g.tiles_per_row);
+    const int64_t q = t / g.tiles_per_row;
+    by = (int)(q % g.Hp);
+    frame = q / g.Hp;
+}
+
+__device__ __forceinline__ double2 ldg_stream(const double *p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int4 ldg_stream(const int4 *p) {
+    int4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream(double *p, double2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void stg_stream(int4 *p, int4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+// quantiser tables in shared memory, one copy per CTA:
+//   fwd: rt[ch*64+k] = fl(1/t), t[ch*64+k]                    (raster k = 8v + j)
+//   inv: tT[ch*64 + j*8 + r] = t[ch][8r + j]                  (transposed so lanes r are contiguous)
+__device__ __forceinline__ double load_table_elem(const void *table, int table_dtype, int i) {
+    return table_dtype == IVC_F32 ? (double)((const float *)table)[i] : ((const double *)table)[i];
+}
+
+// decode a motion-vector index (motion.py:83-84) and test the source window (motion.py:90-92)
+__device__ __forceinline__ void mv_decode(int64_t idx, int sr, int &dy, int &dx) {
+    const int64_t span = 2 * (int64_t)sr + 1;
+    // python floor division / modulo semantics for negative indices
+    int64_t qd = idx / span, rm = idx % span;
+    if (rm < 0) { rm += span; qd -= 1; }
+    dy = (int)(qd - sr);
+    dx = (int)(rm - sr);
+}
+
+// ================================================================================================
+// K1: fused forward  (patch -> DCT -> quantize -> zig-zag), optionally with MC + residual in front
+// ================================================================================================
+struct FwdArgs {
+    TileGeom g;
+    const double *img;               // intra: HWC image(s); pframe: current luma plane(s)
+    int64_t frame_stride;            // elements
+    const void *table;
+    int table_dtype;
+    int32_t *out;                    // [n, Hp, Wp, 3, 64]
+    // P-frame extras
+    const double *ref;
+    const int64_t *mv;
+    int sr;
+    double *pred_out;                // may be null
+};
+
+template <int C, bool PFRAME>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward(const FwdArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_rt = reinterpret_cast<double *>(smem_raw);            // [3*64]
+    double *s_t = s_rt + 192;                                        // [3*64]
+    unsigned char *s_warp = smem_raw + 2 * 192 * sizeof(double);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *buf = reinterpret_cast<double *>(s_warp + warp * kWarpBufBytes);
+    int *ibuf = reinterpret_cast<int *>(buf);
+
+    for (int i = threadIdx.x; i < 192; i += blockDim.x) {
+        const double t = load_table_elem(a.table, a.table_dtype, i);
+        s_t[i] = t;
+        s_rt[i] = __drcp_rn(t);
+    }
+    __syncthreads();
+
+    const int r = lane & 7, u = lane >> 3;       // row pass: pixel row r; column pass: column j == r
+    int zz[8];                                   // scan position of raster (v, j=r)
+#pragma unroll
+    for (int v = 0; v < 8; ++v) zz[v] = ZZ_ORDER[v * 8 + r];
+
+    const TileGeom &g = a.g;
+    constexpr int kBlocksPerTile = (C == 3) ? 4 : 12;
+    const int64_t row_elems = g.W * C;           // doubles per image row
+    const int64_t gw = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+    const int64_t nw = (int64_t)gridDim.x * kWarpsPerCta;
+
+    for (int64_t t = gw; t < g.total_tiles; t += nw) {
+        int64_t frame; int by, tx;
+        tile_coords(g, t, frame, by, tx);
+        const int b0 = tx * kBlocksPerTile;
+        const int nb = min(kBlocksPerTile, g.Wp - b0);               // valid blocks in this tile
+        const int nchunk = nb * (C == 3 ? 12 : 4);                   // valid 16-byte chunks per tile row
+        const double *src = a.img + frame * a.frame_stride + (int64_t)by * 8 * row_elems + (int64_t)tx * 96;
+
+        // ---- phase 1: coalesced 16-byte loads of the 8 x 768 B tile into padded smem rows ----
+        if (!PFRAME) {
+            double2 v[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const int id = lane + 32 * k, row = id / 48, c16 = id % 48;
+                v[k] = (c16 < nchunk) ? ldg_stream(src + row * row_elems + 2 * c16) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const int id = lane + 32 * k, row = id / 48, c16 = id % 48;
+                *reinterpret_cast<double2 *>(buf + row * kRowPitch + 2 * c16) = v[k];
+            }
+        } else {
+            // residual = cur - MC(ref, mv) (videocodec.py:68-71); 12 luma blocks per tile.
+            // lanes 0..11 decode the block vectors once, the rest fetch them by shuffle.
+            int dy = 0, dx = 0;
+            if (lane < nb) mv_decode(a.mv[(frame * g.Hp + by) * g.Wp + b0 + lane], a.sr, dy, dx);
+            const double *refp = a.ref + frame * a.frame_stride;
+            double *predp = a.pred_out ? a.pred_out + frame * a.frame_stride + (int64_t)by * 8 * row_elems + (int64_t)tx * 96
+                                       : nullptr;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const int id = lane + 32 * k, row = id / 48, c16 = id % 48;
+                const int blk = c16 >> 2;
+                const int bdy = __shfl_sync(0xffffffffu, dy, blk), bdx = __shfl_sync(0xffffffffu, dx, blk);
+                double2 res = make_double2(0.0, 0.0);
+                if (c16 < nchunk) {
+                    const double2 cur = ldg_stream(src + row * row_elems + 2 * c16);
+                    const int sy = (by + 0) * 8 + bdy, sx = (b0 + blk) * 8 + bdx;       // source window origin
+                    double2 pr = make_double2(0.0, 0.0);
+                    if (sy >= 0 && sy + 8 <= g.H && sx >= 0 && sx + 8 <= g.W) {
+                        const double *rp = refp + (int64_t)(sy + row) * row_elems + sx + ((2 * c16) & 7);
+                        pr.x = __ldg(rp);
+                        pr.y = __ldg(rp + 1);
+                    }
+                    if (predp) stg_stream(predp + row * row_elems + 2 * c16, pr);
+                    res.x = __dsub_rn(cur.x, pr.x);
+                    res.y = __dsub_rn(cur.y, pr.y);
+                }
+                *reinterpret_cast<double2 *>(buf + row * kRowPitch + 2 * c16) = res;
+            }
+        }
+        __syncwarp();
+
+        // ---- phase 2: row pass.  lane (r,u) reads its 24 consecutive doubles (conflict-free) ----
+        double x[3][8];
+        {
+            double raw[24];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const double2 v = *reinterpret_cast<const double2 *>(buf + r * kRowPitch + 24 * u + 2 * k);
+                raw[2 * k] = v.x;
+                raw[2 * k + 1] = v.y;
+            }
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+#pragma unroll
+                for (int p = 0; p < 8; ++p) x[m][p] = (C == 3) ? raw[3 * p + m] : raw[8 * m + p];
+        }
+#pragma unroll
+        for (int m = 0; m < 3; ++m) dct2_8(x[m]);
+        __syncwarp();                                   // everyone has consumed the input rows
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) buf[u * kTU + (m * 8 + j) * kTJ + r] = x[m][j];
+        __syncwarp();
+
+        // ---- phase 3: column pass.  lane (j,u), j == r ----
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double2 v = *reinterpret_cast<const double2 *>(buf + u * kTU + (m * 8 + r) * kTJ + 2 * k);
+                x[m][2 * k] = v.x;
+                x[m][2 * k + 1] = v.y;
+            }
+            dct2_8(x[m]);                               // x[m][v] = coefficient (v, j)
+        }
+        __syncwarp();                                   // transposition buffer is dead
+
+        // ---- phase 4: quantise, zig-zag scatter into staging, coalesced 16-byte stores ----
+        int32_t *outf = a.out + ((frame * g.Hp + by) * (int64_t)g.Wp) * 192;
+        if (C == 3) {
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    const int k = m * 64 + v * 8 + r;
+                    ibuf[u * kStageU + m * 64 + zz[v]] = quantize_f64(x[m][v], s_t[k], s_rt[k]);
+                }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const int id = lane + 32 * k, chunk = id >> 4, part = id & 15;   // chunk = u*3 + m
+                const int cu = chunk / 3;
+                if (cu < nb) {
+                    const int4 v = *reinterpret_cast<const int4 *>(ibuf + cu * kStageU + (chunk - cu * 3) * 64 + part * 4);
+                    stg_stream(reinterpret_cast<int4 *>(outf + (int64_t)(b0 * 3 + chunk) * 64 + part * 4), v);
+                }
+            }
+            __syncwarp();
+        } else {
+            // C == 1: numpy broadcasting quantises the single channel with all three tables
+            // (patchquant.py:59).  One round per sub-block m: 4 blocks x 3 tables = 12 chunks.
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) {
+                        const int k = ch * 64 + v * 8 + r;
+                        ibuf[u * kStageU + ch * 64 + zz[v]] = quantize_f64(x[m][v], s_t[k], s_rt[k]);
+                    }
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const int id = lane + 32 * k, chunk = id >> 4, part = id & 15;
+                    const int cu = chunk / 3, ch = chunk - cu * 3;
+                    const int blk = 3 * cu + m;
+                    if (blk < nb) {
+                        const int4 v = *reinterpret_cast<const int4 *>(ibuf + cu * kStageU + ch * 64 + part * 4);
+                        stg_stream(reinterpret_cast<int4 *>(outf + ((int64_t)(b0 + blk) * 3 + ch) * 64 + part * 4), v);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+// ================================================================================================
+// K2: fused inverse (un-zig-zag -> dequantize -> IDCT -> un-patch), optionally + prediction
+// ================================================================================================
+struct InvArgs {
+    TileGeom g;                      // g.C = channels of the scan input (1 or 3); PFRAME: luma geometry
+    const int32_t *zz;               // [n, Hp, Wp, Czz, 64]
+    int Czz;
+    const void *table;
+    int table_dtype;
+    double *out;                     // intra: [n, H, W, 3]; pframe: [n, H, W]
+    // P-frame extras
+    const double *pred;              // may be null -> gather from (ref, mv)
+    const double *ref;
+    const int64_t *mv;
+    int sr;
+};
+
+// MODE 0: intra, 3 scan channels -> 3 image channels      (tile = 4 blocks x 3 channels)
+// MODE 1: intra, 1 scan channel broadcast against 3 tables (tile = 4 blocks, m = table index)
+// MODE 2: P-frame luma: channel 0 of the scan, luminance table, + prediction (tile = 12 blocks)
+template <int MODE>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_inverse(const InvArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_tT = reinterpret_cast<double *>(smem_raw);            // [3][j*8 + r]
+    unsigned char *s_warp = smem_raw + 192 * sizeof(double);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *buf = reinterpret_cast<double *>(s_warp + warp * kWarpBufBytes);
+    int *ibuf = reinterpret_cast<int *>(buf);
+
+    for (int i = threadIdx.x; i < 192; i += blockDim.x) {
+        const int ch = i >> 6, k = i & 63, rr = k >> 3, jj = k & 7;
+        s_tT[ch * 64 + jj * 8 + rr] = load_table_elem(a.table, a.table_dtype, i);
+    }
+    __syncthreads();
+
+    const int r = lane & 7, u = lane >> 3;
+    int zr[8];                                   // scan position of raster (r, j)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) zr[j] = ZZ_ORDER[r * 8 + j];
+
+    const TileGeom &g = a.g;
+    constexpr int kBlocksPerTile = (MODE == 2) ? 12 : 4;
+    constexpr int kOutC = (MODE == 2) ? 1 : 3;
+    const int64_t row_elems = g.W * kOutC;
+    const int64_t out_frame = g.H * row_elems;
+    const int64_t gw = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+    const int64_t nw = (int64_t)gridDim.x * kWarpsPerCta;
+
+    for (int64_t t = gw; t < g.total_tiles; t += nw) {
+        int64_t frame; int by, tx;
+        tile_coords(g, t, frame, by, tx);
+        const int b0 = tx * kBlocksPerTile;
+        const int nb = min(kBlocksPerTile, g.Wp - b0);
+        const int32_t *zsrc = a.zz + ((frame * g.Hp + by) * (int64_t)g.Wp + b0) * a.Czz * 64;
+
+        // ---- phase 1: stage the scan blocks (256-byte chunks) ----
+        // staging slot s (0..11) holds block-channel (u = s/3, m = s%3)
+        if (MODE == 0) {
+            int4 v[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const int id = lane + 32 * k, chunk = id >> 4, part = id & 15;
+                v[k] = (chunk / 3 < nb) ? ldg_stream(reinterpret_cast<const int4 *>(zsrc + chunk * 64 + part * 4))
+                                        : make_int4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const int id = lane + 32 * k, chunk = id >> 4, part = id & 15;
+                const int cu = chunk / 3;
+                *reinterpret_cast<int4 *>(ibuf + cu * kStageU + (chunk - cu * 3) * 64 + part * 4) = v[k];
+            }
+        } else if (MODE == 1) {
+            // 4 blocks, one scan channel each (Czz == 1): slot (u, 0)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int id = lane + 32 * k, cu = id >> 4, part = id & 15;
+                const int4 v = (cu < nb) ? ldg_stream(reinterpret_cast<const int4 *>(zsrc + (int64_t)cu * 64 + part * 4))
+                                         : make_int4(0, 0, 0, 0);
+                *reinterpret_cast<int4 *>(ibuf + cu * kStageU + part * 4) = v;
+            }
+        } else {
+            // 12 luma blocks: slot (u, m) <- block 3u+m, scan channel 0 of Czz
+            int4 v[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const int id = lane + 32 * k, blk = id >> 4, part = id & 15;
+                v[k] = (blk < nb) ? ldg_stream(reinterpret_cast<const int4 *>(zsrc + (int64_t)blk * a.Czz * 64 + part * 4))
+                                  : make_int4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const int id = lane + 32 * k, blk = id >> 4, part = id & 15;
+                const int cu = blk / 3;
+                *reinterpret_cast<int4 *>(ibuf + cu * kStageU + (blk - cu * 3) * 64 + part * 4) = v[k];
+            }
+        }
+        __syncwarp();
+
+        // ---- phase 2: gather raster row r, dequantise, row IDCT (axis -1 first, dct.py:42) ----
+        double x[3][8];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            const int slot = (MODE == 1) ? 0 : m;
+            const int tch = (MODE == 2) ? 0 : m;         // P-frame: luminance table for every block
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int q = ibuf[u * kStageU + slot * 64 + zr[j]];
+                x[m][j] = dequantize_f64(q, s_tT[tch * 64 + j * 8 + r]);
+            }
+            dct3_8(x[m]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) buf[u * kTU + (m * 8 + j) * kTJ + r] = x[m][j];
+        __syncwarp();
+
+        // ---- phase 3: column IDCT.  lane (j,u), j == r ----
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double2 v = *reinterpret_cast<const double2 *>(buf + u * kTU + (m * 8 + r) * kTJ + 2 * k);
+                x[m][2 * k] = v.x;
+                x[m][2 * k + 1] = v.y;
+            }
+            dct3_8(x[m]);                               // x[m][i] = pixel (row i, column j)
+        }
+        __syncwarp();
+
+        // ---- phase 4: un-patch through a padded row tile, then coalesced 16-byte stores ----
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int col = (MODE == 2) ? (3 * u + m) * 8 + r : (8 * u + r) * 3 + m;
+                buf[i * kRowPitch + col] = x[m][i];
+            }
+        __syncwarp();
+        const int nchunk = nb * (MODE == 2 ? 4 : 12);
+        double *dst = a.out + frame * out_frame + (int64_t)by * 8 * row_elems + (int64_t)tx * 96;
+        if (MODE != 2) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const int id = lane + 32 * k, row = id / 48, c16 = id % 48;
+                if (c16 < nchunk)
+                    stg_stream(dst + row * row_elems + 2 * c16,
+                               *reinterpret_cast<const double2 *>(buf + row * kRowPitch + 2 * c16));
+            }
+        } else {
+            int dy = 0, dx = 0;
+            if (!a.pred && lane < nb) mv_decode(a.mv[(frame * g.Hp + by) * g.Wp + b0 + lane], a.sr, dy, dx);
+            const double *predp = a.pred ? a.pred + frame * out_frame + (int64_t)by * 8 * row_elems + (int64_t)tx * 96 : nullptr;
+            const double *refp = a.ref ? a.ref + frame * out_frame : nullptr;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const int id = lane + 32 * k, row = id / 48, c16 = id % 48;
+                const int blk = c16 >> 2;
+                const int bdy = __shfl_sync(0xffffffffu, dy, blk), bdx = __shfl_sync(0xffffffffu, dx, blk);
+                if (c16 < nchunk) {
+                    double2 pr = make_double2(0.0, 0.0);
+                    if (predp) {
+                        pr = ldg_stream(predp + row * row_elems + 2 * c16);
+                    } else {
+                        const int sy = by * 8 + bdy, sx = (b0 + blk) * 8 + bdx;
+                        if (sy >= 0 && sy + 8 <= g.H && sx >= 0 && sx + 8 <= g.W) {
+                            const double *rp = refp + (int64_t)(sy + row) * row_elems + sx + ((2 * c16) & 7);
+                            pr.x = __ldg(rp);
+                            pr.y = __ldg(rp + 1);
+                        }
+                    }
+                    const double2 rec = *reinterpret_cast<const double2 *>(buf + row * kRowPitch + 2 * c16);
+                    // recon = prediction + recon_residual (videocodec.py:74)
+                    stg_stream(dst + row * row_elems + 2 * c16,
+                               make_double2(__dadd_rn(pr.x, rec.x), __dadd_rn(pr.y, rec.y)));
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ================================================================================================
+// unfused per-method kernels (each class method alone; simple, still coalesced where it matters)
+// ================================================================================================
+template <typename TI>
+__device__ __forceinline__ double load_as_f64(const void *p, int64_t i) { return (double)((const TI *)p)[i]; }
+
+struct DctArgs {
+    const void *x;
+    int x_dtype;
+    int64_t nblocks;                 // n0*n1*C
+    int64_t n1, C;
+    int64_t s[5];
+    void *out;
+};
+
+// one warp = 4 blocks; lane (r,u) row pass, lane (j,u) column pass, T buffer [u][j][r] pitch 9
+template <typename T, bool INVERSE>
+__global__ void __launch_bounds__(256) k_dct8x8(const DctArgs a) {
+    __shared__ T s_T[8][4 * 8 * 9];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = lane & 7, u = lane >> 3;
+    T *tb = s_T[warp] + u * 72;
+    const int64_t gw = (int64_t)blockIdx.x * 8 + warp, nw = (int64_t)gridDim.x * 8;
+    const int64_t ngroups = (a.nblocks + 3) / 4;
+    for (int64_t grp = gw; grp < ngroups; grp += nw) {
+        const int64_t blk = grp * 4 + u;
+        const bool valid = blk < a.nblocks;
+        T x[8];
+        if (valid) {
+            const int64_t c = blk % a.C, q = blk / a.C, i1 = q % a.n1, i0 = q / a.n1;
+            const int64_t base = i0 * a.s[0] + i1 * a.s[1] + c * a.s[2] + r * a.s[3];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int64_t off = base + j * a.s[4];
+                switch (a.x_dtype) {
+                    case IVC_U8: x[j] = (T)((const unsigned char *)a.x)[off]; break;
+                    case IVC_I32: x[j] = (T)((const int *)a.x)[off]; break;
+                    case IVC_F32: x[j] = (T)((const float *)a.x)[off]; break;
+                    default: x[j] = (T)((const double *)a.x)[off]; break;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = (T)0;
+        }
+        if (INVERSE) dct3_8(x); else dct2_8(x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tb[j * 9 + r] = x[j];
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = tb[r * 9 + i];
+        __syncwarp();
+        if (INVERSE) dct3_8(x); else dct2_8(x);
+        if (valid) {
+            T *o = (T *)a.out + blk * 64;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) o[v * 8 + r] = x[v];
+        }
+    }
+}
+
+struct QuantArgs {
+    const void *x;
+    int x_dtype;
+    int64_t n0, n1, C;               // input channels (1 or 3)
+    int64_t s[5];
+    const void *table;
+    int table_dtype;
+    int32_t *out;                    // [n0,n1,3,8,8]
+};
+
+template <typename TI>
+__device__ __forceinline__ TI ld_elem(const void *p, int64_t i) { return ((const TI *)p)[i]; }
+
+// one thread per OUTPUT element; COMPUTE_F32 selects numpy's float32 division path
+template <bool COMPUTE_F32, bool DEQUANT>
+__global__ void __launch_bounds__(256) k_quant(const QuantArgs a) {
+    const int64_t total = a.n0 * a.n1 * 3 * 64;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i & 63);
+        int64_t q = i >> 6;
+        const int ch = (int)(q % 3);
+        q /= 3;
+        const int64_t i1 = q % a.n1, i0 = q / a.n1;
+        const int64_t cin = (a.C == 1) ? 0 : ch;
+        const int64_t off = i0 * a.s[0] + i1 * a.s[1] + cin * a.s[2] + (k >> 3) * a.s[3] + (k & 7) * a.s[4];
+        const int ti = ch * 64 + k;
+        if (COMPUTE_F32) {
+            float x;
+            switch (a.x_dtype) {
+                case IVC_U8: x = (float)ld_elem<unsigned char>(a.x, off); break;
+                case IVC_I32: x = (float)ld_elem<int>(a.x, off); break;
+                default: x = ld_elem<float>(a.x, off); break;
+            }
+            const float t = ((const float *)a.table)[ti];
+            if (!DEQUANT) {
+                a.out[i] = quantize_f32(x, t);
+            } else {
+                const float p = __fmul_rn(x, t);
+                a.out[i] = (p >= -2147483648.0f && p < 2147483648.0f) ? __float2int_rz(p) : (int)0x80000000;
+            }
+        } else {
+            double x;
+            switch (a.x_dtype) {
+                case IVC_U8: x = (double)ld_elem<unsigned char>(a.x, off); break;
+                case IVC_I32: x = (double)ld_elem<int>(a.x, off); break;
+                case IVC_F32: x = (double)ld_elem<float>(a.x, off); break;
+                case IVC_I64: x = (double)ld_elem<long long>(a.x, off); break;
+                default: x = ld_elem<double>(a.x, off); break;
+            }
+            const double t = load_table_elem(a.table, a.table_dtype, ti);
+            if (!DEQUANT) a.out[i] = quantize_exact_f64(x, t);
+            else a.out[i] = cast_i32_x86(__dmul_rn(x, t));
+        }
+    }
+}
+
+template <typename E>
+__global__ void __launch_bounds__(256) k_zigzag(const E *__restrict__ x, E *__restrict__ out, int64_t nelem, int inverse) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nelem; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i & 63);
+        const int64_t base = i - k;
+        if (!inverse) out[base + ZZ_ORDER[k]] = x[i];           // scatter (shape.py:26)
+        else out[i] = x[base + ZZ_ORDER[k]];                    // gather  (shape.py:32)
+    }
+}
+
+// ================================================================================================
+// host-side launchers (called from ivc_abi.cu)
+// ================================================================================================
+static int grid_for(int64_t work_items, int per_cta, int device, int ctas_per_sm) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int64_t need = (work_items + per_cta - 1) / per_cta;
+    const int64_t cap = (int64_t)sms * ctas_per_sm;
+    return (int)(need < 1 ? 1 : (need < cap ? need : cap));
+}
+
+static TileGeom make_geom(int64_t n, int64_t H, int64_t W, int C, int blocks_per_tile) {
+    TileGeom g;
+    g.n_frames = n; g.H = H; g.W = W; g.Hp = (int)(H / 8); g.Wp = (int)(W / 8); g.C = C;
+    g.tiles_per_row = (g.Wp + blocks_per_tile - 1) / blocks_per_tile;
+    g.total_tiles = n * g.Hp * (int64_t)g.tiles_per_row;
+    return g;
+}
+
+template <typename K>
+static cudaError_t set_smem(K kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+cudaError_t launch_forward(int device, cudaStream_t st, const void *img, int64_t n, int64_t H, int64_t W, int C,
+                           int64_t frame_stride, const void *table, int table_dtype, int32_t *out,
+                           const void *ref, const int64_t *mv, int sr, void *pred_out, bool pframe) {
+    FwdArgs a;
+    a.g = make_geom(n, H, W, C, C == 3 ? 4 : 12);
+    a.img = (const double *)img; a.frame_stride = frame_stride; a.table = table; a.table_dtype = table_dtype;
+    a.out = out; a.ref = (const double *)ref; a.mv = mv; a.sr = sr; a.pred_out = (double *)pred_out;
+    if (a.g.total_tiles == 0) return cudaSuccess;
+    const size_t smem = 2 * 192 * sizeof(double) + kWarpsPerCta * kWarpBufBytes;
+    const int grid = grid_for(a.g.total_tiles, kWarpsPerCta, device, 2);
+    cudaError_t e;
+    if (pframe) {
+        if ((e = set_smem(k_forward<1, true>, smem)) != cudaSuccess) return e;
+        k_forward<1, true><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
+    } else if (C == 3) {
+        if ((e = set_smem(k_forward<3, false>, smem)) != cudaSuccess) return e;
+        k_forward<3, false><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
+    } else {
+        if ((e = set_smem(k_forward<1, false>, smem)) != cudaSuccess) return e;
+        k_forward<1, false><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_inverse(int device, cudaStream_t st, const int32_t *zz, int64_t n, int64_t Hp, int64_t Wp, int Czz,
+                           const void *table, int table_dtype, void *out, int mode,
+                           const void *pred, const void *ref, const int64_t *mv, int sr) {
+    InvArgs a;
+    a.g = make_geom(n, Hp * 8, Wp * 8, Czz, mode == 2 ? 12 : 4);
+    a.zz = zz; a.Czz = Czz; a.table = table; a.table_dtype = table_dtype; a.out = (double *)out;
+    a.pred = (const double *)pred; a.ref = (const double *)ref; a.mv = mv; a.sr = sr;
+    if (a.g.total_tiles == 0) return cudaSuccess;
+    const size_t smem = 192 * sizeof(double) + kWarpsPerCta * kWarpBufBytes;
+    const int grid = grid_for(a.g.total_tiles, kWarpsPerCta, device, 2);
+    cudaError_t e;
+    if (mode == 0) {
+        if ((e = set_smem(k_inverse<0>, smem)) != cudaSuccess) return e;
+        k_inverse<0><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
+    } else if (mode == 1) {
+        if ((e = set_smem(k_inverse<1>, smem)) != cudaSuccess) return e;
+        k_inverse<1><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
+    } else {
+        if ((e = set_smem(k_inverse<2>, smem)) != cudaSuccess) return e;
+        k_inverse<2><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dct(int device, cudaStream_t st, bool inverse, const void *x, int x_dtype, int64_t n0, int64_t n1,
+                       int64_t C, const int64_t s[5], void *out, bool f32) {
+    DctArgs a;
+    a.x = x; a.x_dtype = x_dtype; a.nblocks = n0 * n1 * C; a.n1 = n1; a.C = C; a.out = out;
+    for (int i = 0; i < 5; ++i) a.s[i] = s[i];
+    if (a.nblocks == 0) return cudaSuccess;
+    const int grid = grid_for((a.nblocks + 3) / 4, 8, device, 8);
+    if (f32) {
+        if (inverse) k_dct8x8<float, true><<<grid, 256, 0, st>>>(a);
+        else k_dct8x8<float, false><<<grid, 256, 0, st>>>(a);
+    } else {
+        if (inverse) k_dct8x8<double, true><<<grid, 256, 0, st>>>(a);
+        else k_dct8x8<double, false><<<grid, 256, 0, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_quant(int device, cudaStream_t st, bool dequant, const void *x, int x_dtype, int64_t n0, int64_t n1,
+                         int64_t C, const int64_t s[5], const void *table, int table_dtype, bool f32, int32_t *out) {
+    QuantArgs a;
+    a.x = x; a.x_dtype = x_dtype; a.n0 = n0; a.n1 = n1; a.C = C; a.table = table; a.table_dtype = table_dtype; a.out = out;
+    for (int i = 0; i < 5; ++i) a.s[i] = s[i];
+    const int64_t total = n0 * n1 * 3 * 64;
+    if (total == 0) return cudaSuccess;
+    const int grid = grid_for(total, 256 * 4, device, 16);
+    if (f32) {
+        if (dequant) k_quant<true, true><<<grid, 256, 0, st>>>(a);
+        else k_quant<true, false><<<grid, 256, 0, st>>>(a);
+    } else {
+        if (dequant) k_quant<false, true><<<grid, 256, 0, st>>>(a);
+        else k_quant<false, false><<<grid, 256, 0, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_zigzag(int device, cudaStream_t st, bool inverse, const void *x, int elem_size, int64_t nblocks, void *out) {
+    const int64_t nelem = nblocks * 64;
+    if (nelem == 0) return cudaSuccess;
+    const int grid = grid_for(nelem, 256 * 4, device, 16);
+    switch (elem_size) {
+        case 1: k_zigzag<unsigned char><<<grid, 256, 0, st>>>((const unsigned char *)x, (unsigned char *)out, nelem, inverse); break;
+        case 2: k_zigzag<unsigned short><<<grid, 256, 0, st>>>((const unsigned short *)x, (unsigned short *)out, nelem, inverse); break;
+        case 4: k_zigzag<unsigned int><<<grid, 256, 0, st>>>((const unsigned int *)x, (unsigned int *)out, nelem, inverse); break;
+        case 8: k_zigzag<unsigned long long><<<grid, 256, 0, st>>>((const unsigned long long *)x, (unsigned long long *)out, nelem, inverse); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace ivc

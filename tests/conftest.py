@@ -1,0 +1,68 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    # a GPU test on a box without a GPU is a hard failure when explicitly selected with -m gpu
+    # (never a silent skip); under the default CPU run (-m "not gpu") they are deselected anyway.
+    pass
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLD, name), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def g1():
+    return load_golden("g1_intra_color_48x64.npz")
+
+
+@pytest.fixture(scope="session")
+def g2():
+    return load_golden("g2_intra_luma_ties_40x56.npz")
+
+
+@pytest.fixture(scope="session")
+def g3():
+    return load_golden("g3_dtypes.npz")
+
+
+@pytest.fixture(scope="session")
+def g4():
+    return load_golden("g4_motion.npz")
+
+
+@pytest.fixture(scope="session")
+def g5():
+    return load_golden("g5_pframe.npz")
+
+
+@pytest.fixture(scope="session")
+def g6():
+    return load_golden("g6_neighbours.npz")
+
+
+@pytest.fixture(scope="session")
+def g7():
+    return load_golden("g7_qcif_mv.npz")
+
+
+QSCALES = [0.07, 1.0, 4.5, np.float64(0.4)]      # index qi in the golden files
+ME_CASES = ["int_sr4", "int_sr2", "int_sr16", "float_sr4", "float_sr7", "flat_sr4", "flat255_sr3",
+            "f32_sr4", "mixed_f32ref_f64cur_sr3", "tiny_8x8_sr4", "row_8x64_sr5"]
+
+
+def case_sr(name):
+    return int(name.rsplit("sr", 1)[1])

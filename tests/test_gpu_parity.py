@@ -1,0 +1,326 @@
+"""GPU parity tests (run with ``-m gpu`` on the B200): the CUDA path, called through the drop-in
+classes and hence through the C ABI, against (a) the golden vectors produced by the real
+reference (tests/golden, oracle/gen_golden.py) and (b) the oracle on seeded inputs.
+Bar: bit-exact for indices, motion vectors and -- because the DCT replays scipy's operation
+order -- also for every float64/float32 transform output (tolerance 0)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLD, ME_CASES, QSCALES, case_sr
+
+pytestmark = pytest.mark.gpu
+
+import ivclab_b200 as ivc  # noqa: E402
+from oracle import ivc_oracle as O  # noqa: E402  (the checker)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    assert torch.cuda.is_available(), "GPU tests selected but no CUDA device is visible"
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+# ---------------------------------------------------------------- per-op, golden vectors
+def test_dct_forward_golden_strided_view(g1):
+    img = g1["img"]
+    patches = ivc.Patcher().patch(img)                       # strided view, like intracodec.py:66
+    assert not patches.flags.c_contiguous
+    out = ivc.DiscreteCosineTransform().transform(patches)
+    assert out.dtype == np.float64 and out.flags.c_contiguous
+    assert np.array_equal(out, g1["coef"])                   # bit-exact vs scipy
+
+
+@pytest.mark.parametrize("qi", range(4))
+def test_quantize_zigzag_dequantize_idct_golden(g1, qi):
+    q = QSCALES[qi]
+    pq = ivc.PatchQuant(quantization_scale=q)
+    tab = pq.get_quantization_table()
+    assert np.array_equal(tab, g1[f"table{qi}"]) and tab.dtype == g1[f"table{qi}"].dtype
+    qz = pq.quantize(g1["coef"])
+    assert qz.dtype == np.int32 and qz.shape == (6, 8, 3, 8, 8)
+    zz = ivc.ZigZag().flatten(qz)
+    assert np.array_equal(zz, g1[f"zz{qi}"])
+    un = ivc.ZigZag().unflatten(zz)
+    assert np.array_equal(un, qz)
+    dq = pq.dequantize(un)
+    assert dq.dtype == np.int32 and np.array_equal(dq, g1[f"dq{qi}"])
+    rec = ivc.DiscreteCosineTransform().inverse_transform(dq)
+    assert rec.dtype == np.float64
+    assert np.array_equal(ivc.Patcher().unpatch(rec), g1[f"rec{qi}"])
+
+
+@pytest.mark.parametrize("qi", range(4))
+def test_luma_broadcast_and_ties_golden(g2, qi):
+    """C=1 input broadcasts to 3 channels; the frame holds exact rounding ties (DC/16 = k+0.5)."""
+    luma = g2["luma"]
+    pq = ivc.PatchQuant(quantization_scale=QSCALES[qi])
+    coef = ivc.DiscreteCosineTransform().transform(ivc.Patcher().patch(luma[..., None]))
+    assert np.array_equal(coef, g2["coef"])
+    qz = pq.quantize(coef)
+    assert qz.shape == (5, 7, 3, 8, 8)
+    assert np.array_equal(ivc.ZigZag().flatten(qz), g2[f"zz{qi}"])
+    dq = pq.dequantize(qz[:, :, :1])
+    assert dq.shape == (5, 7, 3, 8, 8)
+    rec = ivc.Patcher().unpatch(ivc.DiscreteCosineTransform().inverse_transform(dq))
+    assert np.array_equal(rec, g2[f"rec{qi}"])
+
+
+def test_other_dtypes_golden(g3):
+    D = ivc.DiscreteCosineTransform()
+    c32 = D.transform(g3["x32"])
+    assert c32.dtype == np.float32 and np.array_equal(c32, g3["c32"])
+    i32 = D.inverse_transform(g3["x32"])
+    assert i32.dtype == np.float32 and np.array_equal(i32, g3["i32"])
+    cu8 = D.transform(g3["xu8"])
+    assert cu8.dtype == np.float64 and np.array_equal(cu8, g3["cu8"])
+    c_one = D.transform(g3["one"])                                  # plain (8,8) input
+    assert c_one.shape == (8, 8) and np.array_equal(c_one, g3["c_one"])
+    assert np.array_equal(ivc.PatchQuant().quantize(g3["xu8"]), g3["q_u8"])       # float32 division path
+    assert np.array_equal(ivc.PatchQuant(0.07).quantize(g3["c32"]), g3["q_f32"])
+    q388 = ivc.PatchQuant().quantize(g3["c32"][0, 0])
+    assert q388.shape == (1, 1, 3, 8, 8)
+    assert np.array_equal(q388, O.quantize(g3["c32"][0, 0], g3["tab1"]))
+
+
+def test_zigzag_dtypes_and_roundtrip():
+    rng = np.random.default_rng(3)
+    Z = ivc.ZigZag()
+    for dt in (np.int32, np.float64, np.float32, np.int16, np.uint8, np.int64):
+        x = rng.integers(0, 100, size=(3, 5, 2, 8, 8)).astype(dt)
+        f = Z.flatten(x)
+        assert f.dtype == dt and np.array_equal(f, O.zigzag_flatten(x))
+        assert np.array_equal(Z.unflatten(f), x)
+    with pytest.raises(ValueError):
+        Z.flatten(np.zeros((2, 2, 8, 8)))
+
+
+# ---------------------------------------------------------------- fused kernels
+@pytest.mark.parametrize("qi", range(4))
+def test_fused_intra_forward_inverse_golden(g1, qi):
+    coder = ivc.IntraBlockCoder(quantization_scale=QSCALES[qi])
+    zz = coder.forward(g1["img"])
+    assert zz.dtype == np.int32 and np.array_equal(zz, g1[f"zz{qi}"])
+    rec = coder.inverse(g1[f"zz{qi}"])
+    assert rec.dtype == np.float64 and np.array_equal(rec, g1[f"rec{qi}"])
+
+
+@pytest.mark.parametrize("qi", range(4))
+def test_fused_luma_golden(g2, qi):
+    coder = ivc.IntraBlockCoder(quantization_scale=QSCALES[qi])
+    zz = coder.forward(g2["luma"])                                   # [H,W] -> C=1 -> 3 tables
+    assert np.array_equal(zz, g2[f"zz{qi}"])
+    rec = coder.inverse(g2[f"zz{qi}"][:, :, :1])                     # 1 scan channel -> 3 image channels
+    assert np.array_equal(rec, g2[f"rec{qi}"])
+
+
+@pytest.mark.parametrize("shape", [(8, 8, 3), (8, 24, 3), (16, 40, 3), (24, 104, 1), (8, 8, 1), (32, 200, 1),
+                                   (40, 136, 3)])
+def test_fused_ragged_tile_widths_vs_oracle(shape):
+    """widths that are not a multiple of the 4-block (C=3) / 12-block (C=1) tile"""
+    rng = np.random.default_rng(sum(shape))
+    img = rng.uniform(-50, 300, size=shape)
+    coder = ivc.IntraBlockCoder(quantization_scale=0.3)
+    tab = coder.quant.get_quantization_table()
+    zz = coder.forward(img)
+    assert np.array_equal(zz, O.intra_forward(img, tab))
+    zin = zz if shape[2] == 3 else zz[:, :, :1]
+    assert np.array_equal(coder.inverse(zin), O.intra_inverse(zin, tab))
+
+
+def test_fused_batch_equals_per_frame():
+    rng = np.random.default_rng(8)
+    batch = rng.uniform(0, 255, size=(5, 24, 40, 3))
+    coder = ivc.IntraBlockCoder(quantization_scale=1.0)
+    zz = coder.forward(batch)
+    for i in range(5):
+        assert np.array_equal(zz[i], O.intra_forward(batch[i], coder.quant.get_quantization_table()))
+    rec = coder.inverse(zz)
+    for i in range(5):
+        assert np.array_equal(rec[i], O.intra_inverse(zz[i], coder.quant.get_quantization_table()))
+
+
+def test_quantizer_extremes_match_x86_semantics():
+    """huge / non-finite coefficients: the int32 cast follows numpy-on-x86 (0x80000000)."""
+    x = np.zeros((1, 1, 3, 8, 8))
+    x[0, 0, 0, 0, :4] = [1e300, -1e300, np.inf, np.nan]
+    x[0, 0, 1, 0, :4] = [2147483647.0 * 17, -2147483648.0 * 17, 40000.0 * 17, -40000.5 * 17]
+    tab = O.quant_table(1.0)
+    with np.errstate(all="ignore"):
+        want = O.quantize(x, tab)
+    assert np.array_equal(ivc.PatchQuant().quantize(x), want)
+
+
+# ---------------------------------------------------------------- motion
+@pytest.mark.parametrize("name", ME_CASES)
+@pytest.mark.parametrize("mode", ["auto", "exact"])
+def test_motion_vectors_golden(g4, name, mode):
+    sr = case_sr(name)
+    mc = ivc.MotionCompensator(search_range=sr, me_mode=mode)
+    mv = mc.compute_motion_vector(g4[f"{name}__ref"], g4[f"{name}__cur"])
+    assert mv.dtype == np.int64 and mv.shape == g4[f"{name}__mv"].shape
+    assert np.array_equal(mv, g4[f"{name}__mv"])
+    pred = mc.reconstruct_with_motion_vector(g4[f"{name}__ref"][..., None], g4[f"{name}__mv"])
+    assert pred.dtype == g4[f"{name}__pred"].dtype and np.array_equal(pred, g4[f"{name}__pred"])
+
+
+def test_motion_int_kernel_forced(g4):
+    for name in ("int_sr4", "int_sr2", "int_sr16", "flat_sr4", "flat255_sr3"):
+        mc = ivc.MotionCompensator(search_range=case_sr(name), me_mode="int")
+        assert np.array_equal(mc.compute_motion_vector(g4[f"{name}__ref"], g4[f"{name}__cur"]), g4[f"{name}__mv"])
+
+
+def test_mc_out_of_frame_vectors_golden(g4):
+    mc = ivc.MotionCompensator(search_range=4)
+    assert np.array_equal(mc.reconstruct_with_motion_vector(g4["mc_ref3"], g4["mc_mv_rand"]), g4["mc_pred3"])
+
+
+def test_qcif_motion_golden(g7):
+    """cfg2: QCIF sequence, vectors produced by the reference's own loops (open loop + float reference)."""
+    seq = O.moving_sequence(2, 6, 144, 176)
+    pin = json.load(open(os.path.join(GOLD, "PINNING.json")))
+    assert sha(seq) == pin["hashes"]["cfg2_seq_sha"]
+    mc = ivc.MotionCompensator(search_range=4)
+    for t in range(1, 6):
+        assert np.array_equal(mc.compute_motion_vector(seq[t - 1], seq[t])[..., 0], g7["mvs"][t - 1][..., 0])
+    ref_q = seq[0] + np.random.default_rng(9).normal(0, 0.5, size=seq[0].shape)
+    assert np.array_equal(mc.compute_motion_vector(ref_q, seq[1])[..., 0], g7["mv_float"][..., 0])
+
+
+@pytest.mark.parametrize("sr", [1, 4, 7, 16])
+def test_motion_float_frames_vs_oracle(sr):
+    rng = np.random.default_rng(100 + sr)
+    ref = rng.uniform(0, 255, size=(72, 200))
+    cur = np.roll(ref, (2, -3), axis=(0, 1)) + rng.normal(0, 2.0, size=ref.shape)
+    for dt in (np.float64, np.float32):
+        r, c = ref.astype(dt), cur.astype(dt)
+        mv = ivc.MotionCompensator(search_range=sr).compute_motion_vector(r, c)
+        assert np.array_equal(mv, O.me_full_search(r, c, sr))
+
+
+def test_motion_near_ties_float():
+    """periodic texture: many candidates have almost equal SSD, so the summation order matters."""
+    rng = np.random.default_rng(77)
+    base = np.tile(rng.uniform(0, 255, size=(8, 8)), (6, 12))
+    ref = base + rng.normal(0, 1e-7, size=base.shape)
+    cur = base + rng.normal(0, 1e-7, size=base.shape)
+    mv = ivc.MotionCompensator(search_range=8).compute_motion_vector(ref, cur)
+    assert np.array_equal(mv, O.me_full_search(ref, cur, 8))
+
+
+def test_motion_ragged_frame_raises():
+    with pytest.raises(IndexError):
+        ivc.MotionCompensator().compute_motion_vector(np.zeros((20, 24)), np.zeros((20, 24)))
+
+
+# ---------------------------------------------------------------- P-frame step
+def test_pframe_fused_golden(g5):
+    coder = ivc.PFrameBlockCoder(quantization_scale=0.4, search_range=4)
+    mv = coder.estimate(g5["ref"], g5["cur"])
+    assert np.array_equal(mv, g5["mv"])
+    zz, pred = coder.forward(g5["cur"], g5["ref"], g5["mv"], return_prediction=True)
+    assert np.array_equal(pred, g5["pred"]) and np.array_equal(zz, g5["zz"])
+    assert np.array_equal(coder.forward(g5["cur"], g5["ref"], g5["mv"]), g5["zz"])
+    rec_a = coder.inverse(g5["zz"], pred=g5["pred"])
+    rec_b = coder.inverse(g5["zz"], ref=g5["ref"], mv=g5["mv"])
+    rec_c = coder.inverse(g5["zz"][:, :, :1], pred=g5["pred"])
+    for rec in (rec_a, rec_b, rec_c):
+        assert rec.dtype == np.float64 and np.array_equal(rec, g5["recon"])
+
+
+def test_pframe_out_of_frame_vectors_vs_oracle():
+    rng = np.random.default_rng(21)
+    H, W, sr = 32, 208, 4
+    ref = rng.uniform(0, 255, size=(H, W))
+    cur = rng.uniform(0, 255, size=(H, W))
+    mv = rng.integers(0, 81, size=(H // 8, W // 8, 1))
+    coder = ivc.PFrameBlockCoder(quantization_scale=0.2, search_range=sr)
+    tab = coder.quant.get_quantization_table()
+    pred_o, zz_o = O.pframe_forward(cur, ref, mv, sr, tab)
+    zz, pred = coder.forward(cur, ref, mv, return_prediction=True)
+    assert np.array_equal(pred, pred_o) and np.array_equal(zz, zz_o)
+    assert np.array_equal(coder.inverse(zz, ref=ref, mv=mv), O.pframe_inverse(zz_o[:, :, :1], pred_o, tab))
+
+
+# ---------------------------------------------------------------- full-size configs
+def test_cfg1_full_size_hashes():
+    """cfg1 (512x768 RGB->YCbCr, qScale 0.07/1/4.5): hashes recorded from the real reference."""
+    pin = json.load(open(os.path.join(GOLD, "PINNING.json")))["hashes"]
+    img = O.rgb2ycbcr(O.smooth_noise_rgb(0, 512, 768))
+    assert sha(img) == pin["cfg1_img_sha"]
+    for q in (0.07, 1.0, 4.5):
+        coder = ivc.IntraBlockCoder(quantization_scale=q)
+        zz = coder.forward(img)
+        assert sha(zz) == pin[f"cfg1_zz_sha[{q}]"]
+        assert sha(coder.inverse(zz)) == pin[f"cfg1_rec_sha[{q}]"]
+        # and the unfused drop-in classes give the same bytes
+        pq = ivc.PatchQuant(q)
+        zz2 = ivc.ZigZag().flatten(pq.quantize(ivc.DiscreteCosineTransform().transform(ivc.Patcher().patch(img))))
+        assert sha(zz2) == pin[f"cfg1_zz_sha[{q}]"]
+
+
+def test_1080p_batch_vs_oracle_and_roundtrip_property():
+    """cfg3 shape: 1080p frames.  Parity vs the oracle on 2 frames; on the device-resident batch the
+    size-independent property decode(encode(x)) ~ x within half a quantisation step per coefficient."""
+    frames = np.stack([O.rgb2ycbcr(O.smooth_noise_rgb(3000 + i, 1080, 1920)) for i in range(2)])
+    coder = ivc.IntraBlockCoder(quantization_scale=0.07)
+    tab = coder.quant.get_quantization_table()
+    d = torch.from_numpy(frames).cuda()
+    zz = coder.forward(d)
+    assert zz.is_cuda and zz.dtype == torch.int32
+    rec = coder.inverse(zz)
+    for i in range(2):
+        zo = O.intra_forward(frames[i], tab)
+        assert np.array_equal(zz[i].cpu().numpy(), zo)
+        assert np.array_equal(rec[i].cpu().numpy(), O.intra_inverse(zo, tab))
+    # orthonormal transform: reconstruction error energy <= sum((t/2 + 1)^2) per block
+    err = (rec - d).reshape(2, 135, 8, 240, 8, 3)
+    e_blk = (err ** 2).sum(dim=(2, 4))
+    bound = float(((tab.astype(np.float64) / 2 + 1.0) ** 2).sum(axis=(1, 2)).max())
+    assert float(e_blk.max()) <= bound
+
+
+def test_4k_motion_crops_and_linearity():
+    """cfg4 shape: +-16 search.  Bit-exact vs the oracle on 256x256 crops; on the full 4K frame the
+    estimator must be invariant to adding a constant to both frames (SSD is translation invariant)
+    and the int and exact kernels must agree."""
+    seq = O.moving_sequence(4000, 2, 2160, 3840, max_shift=12, obj=128)
+    mc = ivc.MotionCompensator(search_range=16)
+    crop_r, crop_c = seq[0][512:768, 1024:1280], seq[1][512:768, 1024:1280]
+    assert np.array_equal(mc.compute_motion_vector(crop_r, crop_c), O.me_full_search(crop_r, crop_c, 16))
+    r, c = torch.from_numpy(seq[0]).cuda(), torch.from_numpy(seq[1]).cuda()
+    mv_auto = mc.compute_motion_vector(r, c)
+    mv_exact = ivc.MotionCompensator(16, me_mode="exact").compute_motion_vector(r, c)
+    assert torch.equal(mv_auto, mv_exact)
+    r2, c2 = (r * 0.5 + 3.0), (c * 0.5 + 3.0)           # exact in binary: SSD scales by 1/4, argmin unchanged
+    assert torch.equal(ivc.MotionCompensator(16).compute_motion_vector(r2, c2), mv_exact)
+
+
+def test_cuda_tensor_in_out_no_host_copy(g1):
+    d = torch.from_numpy(g1["img"]).cuda()
+    p = ivc.Patcher().patch(d)
+    out = ivc.DiscreteCosineTransform().transform(p)
+    assert isinstance(out, torch.Tensor) and out.is_cuda
+    assert np.array_equal(out.cpu().numpy(), g1["coef"])
+    q = ivc.PatchQuant(1.0).quantize(out)
+    assert q.is_cuda and np.array_equal(ivc.ZigZag().flatten(q).cpu().numpy(), g1["zz1"])
+
+
+def test_unmodified_caller_chain_like_intracodec(g1, g6):
+    """The call chain of IntraCodec.image2symbols / symbols2image (intracodec.py:66-75, :115-124)
+    executed with the drop-in objects, checked against the reference's zero-run symbol stream."""
+    dct, quant, zigzag, patcher = ivc.DiscreteCosineTransform(), ivc.PatchQuant(1.0), ivc.ZigZag(), ivc.Patcher()
+    patches = patcher.patch(g1["img"])
+    zz = zigzag.flatten(quant.quantize(dct.transform(patches)))
+    assert np.array_equal(O.zerorun_encode(zz), g6["sym"])
+    dec = O.zerorun_decode(g6["sym"], zz.shape[:3])
+    ycbcr = patcher.unpatch(dct.inverse_transform(quant.dequantize(zigzag.unflatten(dec))))
+    assert np.array_equal(O.ycbcr2rgb(ycbcr), g6["rec_rgb"])
+    assert O.calc_psnr(g1["rgb"], O.ycbcr2rgb(ycbcr)) == float(g6["psnr"])
