@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py -- Mpixel/s of the intra + ME coding loop on B200 (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--impl b200|reference]
+
+One STEP = one pass of the whole hot path over this rank's resident shard of F synthetic 1080p
+frames (cfg3 shape for the intra half, cfg4/cfg5-style frame pairs for the inter half):
+
+    K1  intra forward   YCbCr f64 HWC -> DCT -> quantize -> zig-zag        (ivc_intra_forward)
+    K2  intra inverse   scan indices -> dequantize -> IDCT -> HWC f64      (ivc_intra_inverse)
+    K3  motion search   luma(t) vs luma(t-1), +-4 full search, auto kernel  (ivc_me_full_search)
+    K1p P-frame forward MC + residual + DCT + quantize + zig-zag           (ivc_pframe_forward)
+    K2p P-frame inverse dequantize + IDCT + prediction add                 (ivc_pframe_inverse)
+
+`value` = F*H*W pixels / step time: every pixel is intra-coded AND inter-coded once per step.
+Inputs are resident in HBM and much larger than L2 (F=32: 2.7 GB read, 3.5 GB written per step).
+`e2e` is the same step through the public Python API with pinned HOST buffers (H2D of the frames and
+D2H of the scan indices / motion vectors inside the timed region).  `--impl reference` times the
+CPU port that makes the reference's own library calls (oracle/ref_port.py) on all host cores.
+The oracle is used ONLY in the cpu_baseline / reference legs (as baseline and as checker).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W = 1080, 1920
+QSCALE = 1.0
+SR = 4
+METRIC = "Mpixel/s of intra+ME coding loop (1080p, qScale 1.0, +-4 full search)"
+UNIT = "Mpixel/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--frames", type=int, default=32, help="resident 1080p frames per GPU")
+    ap.add_argument("--e2e-frames", type=int, default=8)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--me-mode", default="auto", choices=["auto", "exact", "int"])
+    return ap.parse_args()
+
+
+def workload_config(frames, n_gpus):
+    return {
+        "workload": f"{frames} synthetic 1920x1080 frames per GPU: intra loop on YCbCr f64 HWC (cfg3 shape) + "
+                    f"P-frame loop (ME +-{SR}, MC/residual, recon) on the luma planes; qScale {QSCALE}",
+        "frames_per_gpu": frames, "height": H, "width": W, "qscale": QSCALE, "search_range": SR,
+        "sharding": f"{n_gpus} rank(s), independent frames, no data-path collective",
+        "l2": "inputs larger than L2 (per-step working set >> 126 MB); no flush needed",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for n, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic inputs, generated on the device (input synthesis is not part of the measured path)
+# ------------------------------------------------------------------------------------------------
+def make_inputs(torch, device, frames, seed):
+    """-> ycbcr [F,H,W,3] f64 (float YCbCr of smooth-noise RGB), luma [F,H,W] f64 integer-valued,
+    consecutive luma frames related by small global shifts + noise."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    F = torch.nn.functional
+    m = 16
+    base = torch.randint(0, 256, (1, 3, H + 2 * m, W + 2 * m), generator=g, device=device).double()
+    sm = F.avg_pool2d(base, 5, stride=1, padding=2)
+    canvas = ((sm - 127.5) * 3.0 + 127.5)
+    ycbcr = torch.empty((frames, H, W, 3), dtype=torch.float64, device=device)
+    luma = torch.empty((frames, H, W), dtype=torch.float64, device=device)
+    M = torch.tensor([[0.299, 0.587, 0.114], [-0.168736, -0.331264, 0.5], [0.5, -0.418688, -0.081312]],
+                     dtype=torch.float64, device=device)
+    off = torch.tensor([0.0, 128.0, 128.0], dtype=torch.float64, device=device)
+    shifts = torch.randint(-3, 4, (frames, 2), generator=g, device="cuda").cpu().tolist()
+    for i, (dy, dx) in enumerate(shifts):
+        crop = canvas[0, :, m + dy:m + dy + H, m + dx:m + dx + W]
+        rgb = (crop + 4.0 * torch.randn(crop.shape, generator=g, device=device, dtype=torch.float64)).clamp(0, 255).floor()
+        img = rgb.permute(1, 2, 0) @ M.T + off
+        ycbcr[i] = img
+        luma[i] = img[..., 0].round().clamp(0, 255)
+    return ycbcr, luma
+
+
+# ------------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    import ivclab_b200 as ivc
+    from ivclab_b200 import _lib
+    from ivclab_b200._runtime import to_device
+    L = _lib.lib
+
+    Fr = args.frames
+    ycbcr, luma = make_inputs(torch, device, Fr, 1234 + rank)
+    ref = torch.roll(luma, 1, dims=0).contiguous()          # frame t-1 (cyclic) is the ME reference
+    Hp, Wp = H // 8, W // 8
+    pq = ivc.PatchQuant(QSCALE)
+    _, dtab = pq._table_on(device)
+    tcode = _lib.F32 if dtab.dtype == torch.float32 else _lib.F64
+    zz_i = torch.empty((Fr, Hp, Wp, 3, 64), dtype=torch.int32, device=device)
+    rec_i = torch.empty((Fr, H, W, 3), dtype=torch.float64, device=device)
+    mv = torch.empty((Fr, Hp, Wp, 1), dtype=torch.int64, device=device)
+    zz_p = torch.empty((Fr, Hp, Wp, 3, 64), dtype=torch.int32, device=device)
+    rec_p = torch.empty((Fr, H, W), dtype=torch.float64, device=device)
+    me_mode = {"auto": _lib.ME_AUTO, "exact": _lib.ME_EXACT, "int": _lib.ME_INT}[args.me_mode]
+    ws_bytes = L.ivc_me_workspace_bytes(Fr, H, W)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+    stream = torch.cuda.current_stream(device)
+    sp = stream.cuda_stream
+    launches_per_step = {"auto": 7, "exact": 5, "int": 6}[args.me_mode]
+
+    def k1():
+        _lib.check(L.ivc_intra_forward(local, sp, ycbcr.data_ptr(), _lib.F64, Fr, H, W, 3, H * W * 3, dtab.data_ptr(),
+                                       tcode, zz_i.data_ptr()), "k1")
+
+    def k2():
+        _lib.check(L.ivc_intra_inverse(local, sp, zz_i.data_ptr(), Fr, Hp, Wp, 3, dtab.data_ptr(), tcode,
+                                       rec_i.data_ptr(), _lib.F64), "k2")
+
+    def k3():
+        _lib.check(L.ivc_me_full_search(local, sp, ref.data_ptr(), luma.data_ptr(), _lib.F64, Fr, H, W, H * W, H * W,
+                                        SR, me_mode, mv.data_ptr(), ws.data_ptr(), ws_bytes), "k3")
+
+    def k1p():
+        _lib.check(L.ivc_pframe_forward(local, sp, luma.data_ptr(), ref.data_ptr(), mv.data_ptr(), _lib.F64, Fr, H, W,
+                                        SR, dtab.data_ptr(), tcode, None, zz_p.data_ptr()), "k1p")
+
+    def k2p():
+        _lib.check(L.ivc_pframe_inverse(local, sp, zz_p.data_ptr(), 3, None, ref.data_ptr(), mv.data_ptr(), _lib.F64,
+                                        Fr, H, W, SR, dtab.data_ptr(), tcode, rec_p.data_ptr()), "k2p")
+
+    phases = [("intra_fwd", k1), ("intra_inv", k2), ("me", k3), ("pframe_fwd", k1p), ("pframe_inv", k2p)]
+
+    def step(evs=None):
+        for i, (_, fn) in enumerate(phases):
+            if evs is not None:
+                evs[i].record(stream)
+            fn()
+        if evs is not None:
+            evs[len(phases)].record(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    K = args.steps
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(phases) + 1)] for _ in range(K)]
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for k in range(K):
+        step(evs[k])
+    t1.record(stream)
+    barrier()
+    ms_total = t0.elapsed_time(t1)
+    clk = clocks.stop() if rank == 0 else None
+    ms_step = ms_total / K
+    if world > 1:
+        t = torch.tensor([ms_step], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item())
+    phase_ms = {name: sum(evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(K)) / K
+                for i, (name, _) in enumerate(phases)}
+    px = Fr * H * W
+    value = world * px / (ms_step * 1e-3) / 1e6
+
+    # ---- e2e through the public API, host buffers in pinned memory ----
+    Fe = min(args.e2e_frames, Fr)
+    h_y = ycbcr[:Fe].cpu().pin_memory()
+    h_l = luma[:Fe].cpu().pin_memory()
+    h_r = ref[:Fe].cpu().pin_memory()
+    intra = ivc.IntraBlockCoder(QSCALE)
+    pcod = ivc.PFrameBlockCoder(QSCALE, SR, me_mode=args.me_mode)
+    h_zz_i = torch.empty((Fe, Hp, Wp, 3, 64), dtype=torch.int32).pin_memory()
+    h_zz_p = torch.empty((Fe, Hp, Wp, 3, 64), dtype=torch.int32).pin_memory()
+    h_mv = torch.empty((Fe, Hp, Wp, 1), dtype=torch.int64).pin_memory()
+    h_stat = torch.empty(2, dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        # the API is handed HOST (pinned) buffers; it uploads them itself and returns device tensors
+        d_y = to_device(h_y)[0]
+        d_l = to_device(h_l)[0]
+        d_r = to_device(h_r)[0]
+        z = intra.forward(d_y)
+        r = intra.inverse(z)
+        m = pcod.estimate(d_r, d_l)
+        zp = pcod.forward(d_l, d_r, m)
+        rp = pcod.inverse(zp, ref=d_r, mv=m)
+        h_zz_i.copy_(z, non_blocking=True)
+        h_zz_p.copy_(zp, non_blocking=True)
+        h_mv.copy_(m, non_blocking=True)
+        stat = torch.stack([((r - d_y) ** 2).mean(), ((rp - d_l) ** 2).mean()])      # MSE of both loops (PSNR input)
+        h_stat.copy_(stat, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    Ke = max(3, min(K, 10))
+    w0 = time.perf_counter()
+    for _ in range(Ke):
+        e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - w0) * 1e3 / Ke
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_val = world * Fe * H * W / (e2e_ms * 1e-3) / 1e6
+    h2d = h_y.numel() * 8 + h_l.numel() * 8 + h_r.numel() * 8
+    d2h = h_zz_i.numel() * 4 + h_zz_p.numel() * 4 + h_mv.numel() * 8 + 16
+
+    out = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        which = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        # dominant HBM-bound kernel: K1 fused forward.  algorithmic bytes = 8 B in + 4 B out per sample
+        k1_bytes = Fr * H * W * 3 * 12
+        k1_gbs = k1_bytes / (phase_ms["intra_fwd"] * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        algo = {"intra_fwd": px * 36, "intra_inv": px * 36, "pframe_fwd": px * 28, "pframe_inv": px * 20}
+        out = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": max(3, args.warmup), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(Fr, world),
+            "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "frames_per_step": Fe, "ms_per_step": round(e2e_ms, 3),
+                    "api": "IntraBlockCoder.forward/inverse + PFrameBlockCoder.estimate/forward/inverse, pinned host buffers"},
+            "gpu_launches": K * launches_per_step,
+            "clocks": clk,
+            "roofline": {"kernel": "k_forward<3,false> (fused DCT+quantize+zig-zag)", "bound": "hbm",
+                         "achieved": round(k1_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(k1_gbs / peak, 4),
+                         "traffic": traffic, "algorithmic_bytes_per_launch": k1_bytes, "peak_source": which,
+                         "avg_launch_ms": round(phase_ms["intra_fwd"], 4)},
+            "phases_ms": {k: round(v, 4) for k, v in phase_ms.items()},
+            "phases_mpixel_s": {k: round(px / (v * 1e-3) / 1e6, 1) for k, v in phase_ms.items()},
+            "phases_hbm_frac": {k: round(algo[k] / (phase_ms[k] * 1e-3) / 1e9 / peak, 4) for k in algo},
+            "me_mode": args.me_mode,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(np, ivc, cores=1)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the oracle as baseline and checker)
+# ------------------------------------------------------------------------------------------------
+def _cpu_sample(seed, hi=360, wi=640, hm=136, wm=240):
+    """one bounded sample of the step, with the reference's own library calls; returns per-pixel seconds"""
+    import numpy as np
+    from oracle import ivc_oracle as O, ref_port as R
+    tab = O.quant_table(QSCALE)
+    img = O.rgb2ycbcr(O.smooth_noise_rgb(seed, hi, wi))
+    seq = O.moving_sequence(seed + 7, 2, hm, wm)
+    t0 = time.perf_counter()
+    zz, rec = R.intra_loop(img, tab)
+    t1 = time.perf_counter()
+    mv, zzp, recon = R.pframe_loop(seq[1], seq[0], SR, tab)
+    t2 = time.perf_counter()
+    return {"s_per_px": (t1 - t0) / (hi * wi) + (t2 - t1) / (hm * wm), "t_intra": t1 - t0, "t_pframe": t2 - t1,
+            "img": img, "seq": seq, "zz": zz, "rec": rec, "mv": mv, "zzp": zzp, "recon": recon}
+
+
+def cpu_baseline(np, ivc, cores=1):
+    """rank 0, N=1: the reference-call port on ONE host core (as shipped), and the GPU result on the
+    same sample checked against it (the oracle as checker)."""
+    s = _cpu_sample(99)
+    res = {"value": round(1.0 / s["s_per_px"] / 1e6, 5), "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": "reference-call port (scipy.fft + numpy + python ME loops, oracle/ref_port.py): intra loop on one "
+                     "360x640x3 frame + P-frame loop (ME +-4) on one 136x240 luma pair; per-pixel times added",
+           "t_intra_s": round(s["t_intra"], 3), "t_pframe_s": round(s["t_pframe"], 3),
+           "host_cores_available": len(os.sched_getaffinity(0))}
+    coder = ivc.IntraBlockCoder(QSCALE)
+    pc = ivc.PFrameBlockCoder(QSCALE, SR)
+    ok = np.array_equal(coder.forward(s["img"]), s["zz"]) and np.array_equal(coder.inverse(s["zz"]), s["rec"])
+    mv = pc.estimate(s["seq"][0], s["seq"][1])
+    ok = ok and np.array_equal(mv, s["mv"]) and np.array_equal(pc.forward(s["seq"][1], s["seq"][0], mv), s["zzp"])
+    ok = ok and np.array_equal(pc.inverse(s["zzp"], ref=s["seq"][0], mv=mv), s["recon"])
+    res["gpu_matches_cpu_on_sample"] = bool(ok)
+    return res
+
+
+def _ref_worker(seed):
+    s = _cpu_sample(seed)
+    return s["s_per_px"]
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the step (its own library calls) on all host cores.
+    Under torchrun only rank 0 works."""
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    K, Wm = args.steps, max(0, args.warmup)
+    # bound the whole run to a few minutes: each step is one sample per core (~0.5-1 s)
+    K_eff = min(K, 12)
+    Wm = min(Wm, 2)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for w in range(Wm):
+            pool.map(_ref_worker, [1000 * w + c for c in range(cores)])
+        t0 = time.perf_counter()
+        spp = []
+        for k in range(K_eff):
+            spp += pool.map(_ref_worker, [5000 + 100 * k + c for c in range(cores)])
+        wall = time.perf_counter() - t0
+    mean_spp = sum(spp) / len(spp)                          # seconds one core needs per pixel of the full step
+    value = cores / mean_spp / 1e6                          # all cores busy at the same time
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": K_eff, "warmup": Wm, "ms_per_step": round(wall / K_eff * 1e3, 2), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.frames, args.gpus),
+        "cpu_baseline": {"value": round(value, 5), "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "per step and core: intra loop on a 360x640x3 frame + P-frame loop (ME +-4) on a "
+                                   "136x240 luma pair, reference-call port (oracle/ref_port.py); Mpixel/s = cores / "
+                                   "(per-pixel seconds of the full step)"},
+        "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "steps capped at 12 and warmup at 2 so that the CPU run stays within a few minutes",
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

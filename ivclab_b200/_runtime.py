@@ -31,7 +31,7 @@ def to_device(x, device=None):
     require_cuda()
     if isinstance(x, torch.Tensor):
         if not x.is_cuda:
-            return x.to(device or "cuda"), False
+            return x.to(device or "cuda", non_blocking=x.is_pinned()), False
         return x, False
     a = np.asarray(x)
     if a.dtype.type not in _NP_OK:
