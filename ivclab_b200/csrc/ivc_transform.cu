@@ -16,6 +16,7 @@
 //   * persistent grid: every warp strides over the tile list of the whole batch.
 // HBM traffic is exactly the algorithmic bytes (each input element read once, each output written
 // once); arithmetic is FP64 (14 rounded operations per sample for the 2-D transform).
+#include <cstdlib>
 #include "ivc_dct.cuh"
 #include "ivc_common.cuh"
 
@@ -455,6 +456,268 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_inverse(const InvArgs 
 }
 
 // ================================================================================================
+// v2 of K1 / K2 for the 3-channel intra path: same arithmetic and lane mapping, but the tile moves
+// through the TMA unit.  Each warp owns an mbarrier and two buffers:
+//   IN   (6272 B) filled by cp.async.bulk (one 1-D bulk copy per pixel row / per scan block) --
+//        the copy of tile i+1 is issued as soon as the row pass has pulled tile i into registers,
+//        so HBM latency overlaps the column pass, the quantiser and the store of tile i;
+//   WORK (6400 B) transposition buffer (dense, XOR-swizzled 16-byte chunks instead of padding),
+//        then output staging that a cp.async.bulk store drains asynchronously.
+// No warp ever waits on another warp; no registers are spent on staging.
+// ================================================================================================
+constexpr int kInBytes = 8 * kRowPitch * 8;      // 6272
+constexpr int kWorkBytes = 6400;
+constexpr int kWarpBuf2 = kInBytes + kWorkBytes; // 12672 = 99 * 128
+constexpr int kTU2 = 200;                        // doubles per u-plane: 24 rows * 8 + 8 skew (64 B)
+static_assert(kWarpBuf2 % 128 == 0, "per-warp buffers stay 128-byte aligned");
+static_assert(8 * kRowPitch * 8 <= kWorkBytes, "the output row tile reuses WORK");
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1u << 24)) __trap();          // a lost copy must not hang the GPU
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// swizzled transposition buffer: element (row = m*8+j, r) of plane u
+__device__ __forceinline__ int t2_index(int u, int row, int j, int r) {
+    return u * kTU2 + row * 8 + ((((r >> 1) ^ (j >> 1)) & 3) << 1) + (r & 1);
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_c3_tma(const FwdArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *s_rt = reinterpret_cast<double *>(smem_raw);                       // [192]
+    double *s_t = s_rt + 192;                                                   // [192]
+    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem_raw + 3072);   // [8]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *wbuf = smem_raw + 3200 + warp * kWarpBuf2;
+    double *in = reinterpret_cast<double *>(wbuf);
+    double *work = reinterpret_cast<double *>(wbuf + kInBytes);
+    int *iwork = reinterpret_cast<int *>(work);
+    const uint32_t bar = smem_u32(s_bar + warp), in_s = smem_u32(in), work_s = smem_u32(work);
+
+    for (int i = threadIdx.x; i < 192; i += blockDim.x) {
+        const double t = load_table_elem(a.table, a.table_dtype, i);
+        s_t[i] = t;
+        s_rt[i] = __drcp_rn(t);
+    }
+    if (lane == 0) mbar_init(bar, 1);
+    fence_mbar_init();
+    __syncthreads();
+
+    const int r = lane & 7, u = lane >> 3;
+    int zz[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) zz[v] = ZZ_ORDER[v * 8 + r];
+
+    const TileGeom &g = a.g;
+    const int64_t row_elems = g.W * 3;
+    const int64_t gw = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+    const int64_t nw = (int64_t)gridDim.x * kWarpsPerCta;
+
+    auto issue = [&](int64_t t) {                  // lane 0 only
+        int64_t frame; int by, tx;
+        tile_coords(g, t, frame, by, tx);
+        const int nb = min(4, g.Wp - tx * 4);
+        const uint32_t row_bytes = (uint32_t)nb * 192u;
+        const double *src = a.img + frame * a.frame_stride + (int64_t)by * 8 * row_elems + (int64_t)tx * 96;
+        mbar_expect_tx(bar, 8u * row_bytes);
+#pragma unroll
+        for (int row = 0; row < 8; ++row) bulk_g2s(in_s + row * (kRowPitch * 8), src + row * row_elems, row_bytes, bar);
+    };
+
+    int64_t t = gw;
+    if (t < g.total_tiles && lane == 0) issue(t);
+    uint32_t parity = 0;
+    for (; t < g.total_tiles; t += nw, parity ^= 1u) {
+        int64_t frame; int by, tx;
+        tile_coords(g, t, frame, by, tx);
+        const int b0 = tx * 4;
+        const int nb = min(4, g.Wp - b0);
+
+        mbar_wait(bar, parity);
+        double x[3][8];
+        {
+            double raw[24];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const double2 v = *reinterpret_cast<const double2 *>(in + r * kRowPitch + 24 * u + 2 * k);
+                raw[2 * k] = v.x;
+                raw[2 * k + 1] = v.y;
+            }
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+#pragma unroll
+                for (int p = 0; p < 8; ++p) x[m][p] = raw[3 * p + m];
+        }
+        __syncwarp();                                   // IN is consumed: prefetch the next tile into it
+        if (lane == 0) {
+            if (t + nw < g.total_tiles) { fence_proxy_async(); issue(t + nw); }
+            bulk_wait_read0();                          // previous tile's store has drained WORK
+        }
+#pragma unroll
+        for (int m = 0; m < 3; ++m) dct2_8(x[m]);
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) work[t2_index(u, m * 8 + j, j, r)] = x[m][j];
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double2 v = *reinterpret_cast<const double2 *>(work + u * kTU2 + (m * 8 + r) * 8 + ((k ^ (r >> 1)) << 1));
+                x[m][2 * k] = v.x;
+                x[m][2 * k + 1] = v.y;
+            }
+            dct2_8(x[m]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                const int k = m * 64 + v * 8 + r;
+                iwork[u * kStageU + m * 64 + zz[v]] = quantize_f64(x[m][v], s_t[k], s_rt[k]);
+            }
+        fence_proxy_async();                            // make the staging visible to the bulk-copy unit
+        __syncwarp();
+        if (lane == 0) {
+            int32_t *outf = a.out + ((frame * g.Hp + by) * (int64_t)g.Wp + b0) * 192;
+            for (int cu = 0; cu < nb; ++cu) bulk_s2g(outf + cu * 192, work_s + cu * (kStageU * 4), 768u);
+            bulk_commit();
+        }
+    }
+    if (lane == 0) bulk_wait_all0();
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_inverse_c3_tma(const InvArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *s_tT = reinterpret_cast<double *>(smem_raw);                        // [192]
+    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem_raw + 1536);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kIn2 = 4 * kStageU * 4;                                        // 3200 B
+    constexpr int kBuf = kIn2 + kWorkBytes;                                      // 9600 B
+    unsigned char *wbuf = smem_raw + 1664 + warp * kBuf;
+    int *in = reinterpret_cast<int *>(wbuf);
+    double *work = reinterpret_cast<double *>(wbuf + kIn2);
+    const uint32_t bar = smem_u32(s_bar + warp), in_s = smem_u32(in), work_s = smem_u32(work);
+
+    for (int i = threadIdx.x; i < 192; i += blockDim.x) {
+        const int ch = i >> 6, k = i & 63, rr = k >> 3, jj = k & 7;
+        s_tT[ch * 64 + jj * 8 + rr] = load_table_elem(a.table, a.table_dtype, i);
+    }
+    if (lane == 0) mbar_init(bar, 1);
+    fence_mbar_init();
+    __syncthreads();
+
+    const int r = lane & 7, u = lane >> 3;
+    int zr[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) zr[j] = ZZ_ORDER[r * 8 + j];
+    double tq[3][8];                                    // table entries of raster row r (lane-constant)
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tq[m][j] = s_tT[m * 64 + j * 8 + r];
+
+    const TileGeom &g = a.g;
+    const int64_t row_elems = g.W * 3, out_frame = g.H * row_elems;
+    const int64_t gw = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+    const int64_t nw = (int64_t)gridDim.x * kWarpsPerCta;
+
+    auto issue = [&](int64_t t) {
+        int64_t frame; int by, tx;
+        tile_coords(g, t, frame, by, tx);
+        const int b0 = tx * 4, nb = min(4, g.Wp - b0);
+        const int32_t *zsrc = a.zz + ((frame * g.Hp + by) * (int64_t)g.Wp + b0) * 192;
+        mbar_expect_tx(bar, (uint32_t)nb * 768u);
+        for (int cu = 0; cu < nb; ++cu) bulk_g2s(in_s + cu * (kStageU * 4), zsrc + cu * 192, 768u, bar);
+    };
+
+    int64_t t = gw;
+    if (t < g.total_tiles && lane == 0) issue(t);
+    uint32_t parity = 0;
+    for (; t < g.total_tiles; t += nw, parity ^= 1u) {
+        int64_t frame; int by, tx;
+        tile_coords(g, t, frame, by, tx);
+        const int b0 = tx * 4, nb = min(4, g.Wp - b0);
+
+        mbar_wait(bar, parity);
+        int q[3][8];
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) q[m][j] = in[u * kStageU + m * 64 + zr[j]];
+        __syncwarp();
+        if (lane == 0) {
+            if (t + nw < g.total_tiles) { fence_proxy_async(); issue(t + nw); }
+            bulk_wait_read0();
+        }
+        double x[3][8];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[m][j] = dequantize_f64(q[m][j], tq[m][j]);
+            dct3_8(x[m]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) work[t2_index(u, m * 8 + j, j, r)] = x[m][j];
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double2 v = *reinterpret_cast<const double2 *>(work + u * kTU2 + (m * 8 + r) * 8 + ((k ^ (r >> 1)) << 1));
+                x[m][2 * k] = v.x;
+                x[m][2 * k + 1] = v.y;
+            }
+            dct3_8(x[m]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) work[i * kRowPitch + (8 * u + r) * 3 + m] = x[m][i];
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            double *dst = a.out + frame * out_frame + (int64_t)by * 8 * row_elems + (int64_t)tx * 96;
+            const uint32_t row_bytes = (uint32_t)nb * 192u;
+#pragma unroll
+            for (int row = 0; row < 8; ++row) bulk_s2g(dst + row * row_elems, work_s + row * (kRowPitch * 8), row_bytes);
+            bulk_commit();
+        }
+    }
+    if (lane == 0) bulk_wait_all0();
+}
+
+// ================================================================================================
 // unfused per-method kernels (each class method alone; simple, still coalesced where it matters)
 // ================================================================================================
 template <typename TI>
@@ -584,6 +847,11 @@ __global__ void __launch_bounds__(256) k_zigzag(const E *__restrict__ x, E *__re
 // ================================================================================================
 // host-side launchers (called from ivc_abi.cu)
 // ================================================================================================
+static bool use_v1() {            // A/B switch for profiling: IVC_FUSED_V1=1 selects the first-generation kernels
+    static const bool v = [] { const char *e = getenv("IVC_FUSED_V1"); return e && e[0] == '1'; }();
+    return v;
+}
+
 static int grid_for(int64_t work_items, int per_cta, int device, int ctas_per_sm) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -619,6 +887,10 @@ cudaError_t launch_forward(int device, cudaStream_t st, const void *img, int64_t
     if (pframe) {
         if ((e = set_smem(k_forward<1, true>, smem)) != cudaSuccess) return e;
         k_forward<1, true><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
+    } else if (C == 3 && !use_v1()) {
+        const size_t smem2 = 3200 + (size_t)kWarpsPerCta * kWarpBuf2;
+        if ((e = set_smem(k_forward_c3_tma, smem2)) != cudaSuccess) return e;
+        k_forward_c3_tma<<<grid, kWarpsPerCta * 32, smem2, st>>>(a);
     } else if (C == 3) {
         if ((e = set_smem(k_forward<3, false>, smem)) != cudaSuccess) return e;
         k_forward<3, false><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
@@ -640,7 +912,11 @@ cudaError_t launch_inverse(int device, cudaStream_t st, const int32_t *zz, int64
     const size_t smem = 192 * sizeof(double) + kWarpsPerCta * kWarpBufBytes;
     const int grid = grid_for(a.g.total_tiles, kWarpsPerCta, device, 2);
     cudaError_t e;
-    if (mode == 0) {
+    if (mode == 0 && !use_v1()) {
+        const size_t smem2 = 1664 + (size_t)kWarpsPerCta * (4 * kStageU * 4 + kWorkBytes);
+        if ((e = set_smem(k_inverse_c3_tma, smem2)) != cudaSuccess) return e;
+        k_inverse_c3_tma<<<grid, kWarpsPerCta * 32, smem2, st>>>(a);
+    } else if (mode == 0) {
         if ((e = set_smem(k_inverse<0>, smem)) != cudaSuccess) return e;
         k_inverse<0><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
     } else if (mode == 1) {
