@@ -500,10 +500,45 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// swizzled transposition buffer: element (row = m*8+j, r) of plane u
-__device__ __forceinline__ int t2_index(int u, int row, int j, int r) {
-    return u * kTU2 + row * 8 + ((((r >> 1) ^ (j >> 1)) & 3) << 1) + (r & 1);
-}
+// tile iterator: (frame, block row, tile column) advanced by a fixed stride without divisions
+struct TileIter {
+    int tx, by, dtx, dby;
+    int64_t frame, dframe;
+    __device__ __forceinline__ void init(const TileGeom &g, int64_t t0, int64_t step) {
+        tx = (int)(t0 % g.tiles_per_row);
+        int64_t q = t0 / g.tiles_per_row;
+        by = (int)(q % g.Hp);
+        frame = q / g.Hp;
+        dtx = (int)(step % g.tiles_per_row);
+        q = step / g.tiles_per_row;
+        dby = (int)(q % g.Hp);
+        dframe = q / g.Hp;
+    }
+    __device__ __forceinline__ void advance(const TileGeom &g) {
+        tx += dtx;
+        int c = tx >= g.tiles_per_row;
+        tx -= c ? g.tiles_per_row : 0;
+        by += dby + c;
+        c = by >= g.Hp;
+        by -= c ? g.Hp : 0;
+        frame += dframe + c;
+    }
+};
+
+// branch-free quantiser: always produces the fast-path integer and folds "this sample needs the
+// exact division" into two running values (see quantize_f64 in ivc_dct.cuh for the argument).
+struct QuantGuard {
+    int mx = 0;                      // max of |y| high words
+    unsigned nz = 0xffffffffu;       // min of (frac16 ^ 0x8000): 0 <=> some sample sits exactly on a half
+    __device__ __forceinline__ int q(double x, double rt) {
+        const double y = __dmul_rn(x, rt);
+        const int lo = __double2loint(__dadd_rn(y, 103079215104.0));         // 1.5 * 2^36
+        mx = max(mx, __double2hiint(y) & 0x7fffffff);
+        nz = min(nz, (unsigned)((lo & 0xFFFF) ^ 0x8000));
+        return (lo + 0x8000) >> 16;
+    }
+    __device__ __forceinline__ bool risky() const { return (mx >= 0x40E00000) | (nz == 0u); }   // |y| >= 2^15, NaN, tie
+};
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_c3_tma(const FwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -511,11 +546,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_c3_tma(const F
     double *s_t = s_rt + 192;                                                   // [192]
     unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem_raw + 3072);   // [8]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char *wbuf = smem_raw + 3200 + warp * kWarpBuf2;
-    double *in = reinterpret_cast<double *>(wbuf);
-    double *work = reinterpret_cast<double *>(wbuf + kInBytes);
-    int *iwork = reinterpret_cast<int *>(work);
-    const uint32_t bar = smem_u32(s_bar + warp), in_s = smem_u32(in), work_s = smem_u32(work);
+    unsigned char *in_b = smem_raw + 3200 + warp * kWarpBuf2;
+    unsigned char *work_b = in_b + kInBytes;
+    const uint32_t bar = smem_u32(s_bar + warp), in_s = smem_u32(in_b), work_s = smem_u32(work_b);
 
     for (int i = threadIdx.x; i < 192; i += blockDim.x) {
         const double t = load_table_elem(a.table, a.table_dtype, i);
@@ -526,43 +559,50 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_c3_tma(const F
     fence_mbar_init();
     __syncthreads();
 
+    // lane-constant addresses (everything below indexes them with compile-time offsets)
     const int r = lane & 7, u = lane >> 3;
-    int zz[8];
+    const unsigned char *rd_in = in_b + r * (kRowPitch * 8) + u * 192;
+    unsigned char *t_wr[4], *zz_wr[8];
+    const unsigned char *t_rd[4];
 #pragma unroll
-    for (int v = 0; v < 8; ++v) zz[v] = ZZ_ORDER[v * 8 + r];
+    for (int h = 0; h < 4; ++h) {
+        t_wr[h] = work_b + u * (kTU2 * 8) + ((((r >> 1) ^ h) << 1) + (r & 1)) * 8;    // + row*64
+        t_rd[h] = work_b + u * (kTU2 * 8) + r * 64 + ((h ^ (r >> 1)) << 4);           // + m*512
+    }
+#pragma unroll
+    for (int v = 0; v < 8; ++v) zz_wr[v] = work_b + (u * kStageU + ZZ_ORDER[v * 8 + r]) * 4;   // + m*256
+    const double *rt_l = s_rt + r, *t_l = s_t + r;
 
     const TileGeom &g = a.g;
     const int64_t row_elems = g.W * 3;
     const int64_t gw = (int64_t)blockIdx.x * kWarpsPerCta + warp;
     const int64_t nw = (int64_t)gridDim.x * kWarpsPerCta;
+    if (gw >= g.total_tiles) return;
+    const int64_t my_tiles = (g.total_tiles - gw + nw - 1) / nw;
+    TileIter cur, nxt;
+    cur.init(g, gw, nw);
+    nxt = cur;
 
-    auto issue = [&](int64_t t) {                  // lane 0 only
-        int64_t frame; int by, tx;
-        tile_coords(g, t, frame, by, tx);
-        const int nb = min(4, g.Wp - tx * 4);
+    auto issue = [&](const TileIter &ti) {                  // lane 0 only: 8 row copies of nb*192 bytes
+        const int nb = min(4, g.Wp - ti.tx * 4);
         const uint32_t row_bytes = (uint32_t)nb * 192u;
-        const double *src = a.img + frame * a.frame_stride + (int64_t)by * 8 * row_elems + (int64_t)tx * 96;
+        const double *src = a.img + ti.frame * a.frame_stride + (int64_t)ti.by * 8 * row_elems + (int64_t)ti.tx * 96;
         mbar_expect_tx(bar, 8u * row_bytes);
 #pragma unroll
         for (int row = 0; row < 8; ++row) bulk_g2s(in_s + row * (kRowPitch * 8), src + row * row_elems, row_bytes, bar);
     };
 
-    int64_t t = gw;
-    if (t < g.total_tiles && lane == 0) issue(t);
+    if (lane == 0) issue(cur);
     uint32_t parity = 0;
-    for (; t < g.total_tiles; t += nw, parity ^= 1u) {
-        int64_t frame; int by, tx;
-        tile_coords(g, t, frame, by, tx);
-        const int b0 = tx * 4;
-        const int nb = min(4, g.Wp - b0);
-
+    for (int64_t it = 0; it < my_tiles; ++it, parity ^= 1u) {
+        nxt.advance(g);
         mbar_wait(bar, parity);
         double x[3][8];
         {
             double raw[24];
 #pragma unroll
             for (int k = 0; k < 12; ++k) {
-                const double2 v = *reinterpret_cast<const double2 *>(in + r * kRowPitch + 24 * u + 2 * k);
+                const double2 v = *reinterpret_cast<const double2 *>(rd_in + 16 * k);
                 raw[2 * k] = v.x;
                 raw[2 * k + 1] = v.y;
             }
@@ -573,7 +613,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_c3_tma(const F
         }
         __syncwarp();                                   // IN is consumed: prefetch the next tile into it
         if (lane == 0) {
-            if (t + nw < g.total_tiles) { fence_proxy_async(); issue(t + nw); }
+            if (it + 1 < my_tiles) { fence_proxy_async(); issue(nxt); }
             bulk_wait_read0();                          // previous tile's store has drained WORK
         }
 #pragma unroll
@@ -582,33 +622,41 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_c3_tma(const F
 #pragma unroll
         for (int m = 0; m < 3; ++m)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) work[t2_index(u, m * 8 + j, j, r)] = x[m][j];
+            for (int j = 0; j < 8; ++j) *reinterpret_cast<double *>(t_wr[j >> 1] + (m * 8 + j) * 64) = x[m][j];
         __syncwarp();
 #pragma unroll
         for (int m = 0; m < 3; ++m) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const double2 v = *reinterpret_cast<const double2 *>(work + u * kTU2 + (m * 8 + r) * 8 + ((k ^ (r >> 1)) << 1));
+                const double2 v = *reinterpret_cast<const double2 *>(t_rd[k] + m * 512);
                 x[m][2 * k] = v.x;
                 x[m][2 * k + 1] = v.y;
             }
             dct2_8(x[m]);
         }
         __syncwarp();
+        QuantGuard qg;
 #pragma unroll
         for (int m = 0; m < 3; ++m)
 #pragma unroll
-            for (int v = 0; v < 8; ++v) {
-                const int k = m * 64 + v * 8 + r;
-                iwork[u * kStageU + m * 64 + zz[v]] = quantize_f64(x[m][v], s_t[k], s_rt[k]);
-            }
+            for (int v = 0; v < 8; ++v)
+                *reinterpret_cast<int *>(zz_wr[v] + m * 256) = qg.q(x[m][v], rt_l[m * 64 + v * 8]);
+        if (__builtin_expect(qg.risky(), 0)) {          // rare: redo this lane's 24 samples with the IEEE division
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+#pragma unroll
+                for (int v = 0; v < 8; ++v)
+                    *reinterpret_cast<int *>(zz_wr[v] + m * 256) = quantize_exact_f64(x[m][v], t_l[m * 64 + v * 8]);
+        }
         fence_proxy_async();                            // make the staging visible to the bulk-copy unit
         __syncwarp();
         if (lane == 0) {
-            int32_t *outf = a.out + ((frame * g.Hp + by) * (int64_t)g.Wp + b0) * 192;
+            const int b0 = cur.tx * 4, nb = min(4, g.Wp - b0);
+            int32_t *outf = a.out + ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0) * 192;
             for (int cu = 0; cu < nb; ++cu) bulk_s2g(outf + cu * 192, work_s + cu * (kStageU * 4), 768u);
             bulk_commit();
         }
+        cur = nxt;
     }
     if (lane == 0) bulk_wait_all0();
 }
@@ -620,10 +668,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_inverse_c3_tma(const I
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int kIn2 = 4 * kStageU * 4;                                        // 3200 B
     constexpr int kBuf = kIn2 + kWorkBytes;                                      // 9600 B
-    unsigned char *wbuf = smem_raw + 1664 + warp * kBuf;
-    int *in = reinterpret_cast<int *>(wbuf);
-    double *work = reinterpret_cast<double *>(wbuf + kIn2);
-    const uint32_t bar = smem_u32(s_bar + warp), in_s = smem_u32(in), work_s = smem_u32(work);
+    unsigned char *in_b = smem_raw + 1664 + warp * kBuf;
+    unsigned char *work_b = in_b + kIn2;
+    const uint32_t bar = smem_u32(s_bar + warp), in_s = smem_u32(in_b), work_s = smem_u32(work_b);
 
     for (int i = threadIdx.x; i < 192; i += blockDim.x) {
         const int ch = i >> 6, k = i & 63, rr = k >> 3, jj = k & 7;
@@ -634,66 +681,80 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_inverse_c3_tma(const I
     __syncthreads();
 
     const int r = lane & 7, u = lane >> 3;
-    int zr[8];
+    const unsigned char *q_rd[8];
+    unsigned char *t_wr[4], *o_wr;
+    const unsigned char *t_rd[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) zr[j] = ZZ_ORDER[r * 8 + j];
-    double tq[3][8];                                    // table entries of raster row r (lane-constant)
+    for (int j = 0; j < 8; ++j) q_rd[j] = in_b + (u * kStageU + ZZ_ORDER[r * 8 + j]) * 4;   // + m*256
 #pragma unroll
-    for (int m = 0; m < 3; ++m)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) tq[m][j] = s_tT[m * 64 + j * 8 + r];
+    for (int h = 0; h < 4; ++h) {
+        t_wr[h] = work_b + u * (kTU2 * 8) + ((((r >> 1) ^ h) << 1) + (r & 1)) * 8;
+        t_rd[h] = work_b + u * (kTU2 * 8) + r * 64 + ((h ^ (r >> 1)) << 4);
+    }
+    o_wr = work_b + ((8 * u + r) * 3) * 8;                                     // + i*784 + m*8
+    const double *tq_l = s_tT + r;                      // table entry of raster (r, j), channel m: tq_l[m*64 + j*8]
 
     const TileGeom &g = a.g;
     const int64_t row_elems = g.W * 3, out_frame = g.H * row_elems;
     const int64_t gw = (int64_t)blockIdx.x * kWarpsPerCta + warp;
     const int64_t nw = (int64_t)gridDim.x * kWarpsPerCta;
+    if (gw >= g.total_tiles) return;
+    const int64_t my_tiles = (g.total_tiles - gw + nw - 1) / nw;
+    TileIter cur, nxt;
+    cur.init(g, gw, nw);
+    nxt = cur;
 
-    auto issue = [&](int64_t t) {
-        int64_t frame; int by, tx;
-        tile_coords(g, t, frame, by, tx);
-        const int b0 = tx * 4, nb = min(4, g.Wp - b0);
-        const int32_t *zsrc = a.zz + ((frame * g.Hp + by) * (int64_t)g.Wp + b0) * 192;
+    auto issue = [&](const TileIter &ti) {
+        const int b0 = ti.tx * 4, nb = min(4, g.Wp - b0);
+        const int32_t *zsrc = a.zz + ((ti.frame * g.Hp + ti.by) * (int64_t)g.Wp + b0) * 192;
         mbar_expect_tx(bar, (uint32_t)nb * 768u);
         for (int cu = 0; cu < nb; ++cu) bulk_g2s(in_s + cu * (kStageU * 4), zsrc + cu * 192, 768u, bar);
     };
 
-    int64_t t = gw;
-    if (t < g.total_tiles && lane == 0) issue(t);
+    if (lane == 0) issue(cur);
     uint32_t parity = 0;
-    for (; t < g.total_tiles; t += nw, parity ^= 1u) {
-        int64_t frame; int by, tx;
-        tile_coords(g, t, frame, by, tx);
-        const int b0 = tx * 4, nb = min(4, g.Wp - b0);
-
+    for (int64_t it = 0; it < my_tiles; ++it, parity ^= 1u) {
+        nxt.advance(g);
         mbar_wait(bar, parity);
         int q[3][8];
 #pragma unroll
         for (int m = 0; m < 3; ++m)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) q[m][j] = in[u * kStageU + m * 64 + zr[j]];
+            for (int j = 0; j < 8; ++j) q[m][j] = *reinterpret_cast<const int *>(q_rd[j] + m * 256);
         __syncwarp();
         if (lane == 0) {
-            if (t + nw < g.total_tiles) { fence_proxy_async(); issue(t + nw); }
+            if (it + 1 < my_tiles) { fence_proxy_async(); issue(nxt); }
             bulk_wait_read0();
         }
         double x[3][8];
+        int mx = 0;
 #pragma unroll
-        for (int m = 0; m < 3; ++m) {
+        for (int m = 0; m < 3; ++m)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[m][j] = dequantize_f64(q[m][j], tq[m][j]);
-            dct3_8(x[m]);
+            for (int j = 0; j < 8; ++j) {
+                const double p = __dmul_rn(i32_to_f64(q[m][j]), tq_l[m * 64 + j * 8]);
+                mx = max(mx, __double2hiint(p) & 0x7fffffff);
+                x[m][j] = trunc_f64_small(p);
+            }
+        if (__builtin_expect(mx >= 0x41E00000, 0)) {    // |q*t| >= 2^31: numpy's int32 cast saturates to INT_MIN
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[m][j] = dequantize_f64(q[m][j], tq_l[m * 64 + j * 8]);
         }
+#pragma unroll
+        for (int m = 0; m < 3; ++m) dct3_8(x[m]);
         __syncwarp();
 #pragma unroll
         for (int m = 0; m < 3; ++m)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) work[t2_index(u, m * 8 + j, j, r)] = x[m][j];
+            for (int j = 0; j < 8; ++j) *reinterpret_cast<double *>(t_wr[j >> 1] + (m * 8 + j) * 64) = x[m][j];
         __syncwarp();
 #pragma unroll
         for (int m = 0; m < 3; ++m) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const double2 v = *reinterpret_cast<const double2 *>(work + u * kTU2 + (m * 8 + r) * 8 + ((k ^ (r >> 1)) << 1));
+                const double2 v = *reinterpret_cast<const double2 *>(t_rd[k] + m * 512);
                 x[m][2 * k] = v.x;
                 x[m][2 * k + 1] = v.y;
             }
@@ -703,16 +764,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_inverse_c3_tma(const I
 #pragma unroll
         for (int m = 0; m < 3; ++m)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) work[i * kRowPitch + (8 * u + r) * 3 + m] = x[m][i];
+            for (int i = 0; i < 8; ++i) *reinterpret_cast<double *>(o_wr + i * (kRowPitch * 8) + m * 8) = x[m][i];
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-            double *dst = a.out + frame * out_frame + (int64_t)by * 8 * row_elems + (int64_t)tx * 96;
+            const int nb = min(4, g.Wp - cur.tx * 4);
+            double *dst = a.out + cur.frame * out_frame + (int64_t)cur.by * 8 * row_elems + (int64_t)cur.tx * 96;
             const uint32_t row_bytes = (uint32_t)nb * 192u;
 #pragma unroll
             for (int row = 0; row < 8; ++row) bulk_s2g(dst + row * row_elems, work_s + row * (kRowPitch * 8), row_bytes);
             bulk_commit();
         }
+        cur = nxt;
     }
     if (lane == 0) bulk_wait_all0();
 }
