@@ -175,7 +175,7 @@ def run_b200(args):
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
     stream = torch.cuda.current_stream(device)
     sp = stream.cuda_stream
-    launches_per_step = {"auto": 7, "exact": 5, "int": 6}[args.me_mode]
+    launches_per_step = {"auto": 6, "exact": 5, "int": 5}[args.me_mode]
 
     def k1():
         _lib.check(L.ivc_intra_forward(local, sp, ycbcr.data_ptr(), _lib.F64, Fr, H, W, 3, H * W * 3, dtab.data_ptr(),

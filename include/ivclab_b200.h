@@ -115,7 +115,8 @@ int ivc_intra_inverse(int device, void *stream,
  * ref, cur: n_frames luma planes [H,W] (dtype F32 or F64, both the same), contiguous rows.
  * mv_out: [n_frames, H/8, W/8, 1] int64, index = (dy+sr)*(2sr+1) + (dx+sr); first minimum in
  * (dy asc, dx asc) order over in-bounds candidates.
- * workspace: needed for IVC_ME_AUTO / IVC_ME_INT, ivc_me_workspace_bytes() bytes (else NULL). */
+ * workspace: needed for IVC_ME_AUTO only (holds the device-side "not an integer frame" flag),
+ * ivc_me_workspace_bytes() bytes; NULL otherwise. */
 int64_t ivc_me_workspace_bytes(int64_t n_frames, int64_t H, int64_t W);
 int ivc_me_full_search(int device, void *stream,
                        const void *ref, const void *cur, int dtype,

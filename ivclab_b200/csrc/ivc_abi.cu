@@ -148,8 +148,7 @@ int ivc_intra_inverse(int device, void *stream, const int32_t *zz, int64_t n_fra
 
 int64_t ivc_me_workspace_bytes(int64_t n_frames, int64_t H, int64_t W) {
     if (n_frames < 0 || H < 0 || W < 0) return -1;
-    const int64_t plane = ((n_frames * H * W + 255) / 256) * 256;
-    return 256 + 2 * plane;                    // [flag | ref8 | cur8]
+    return 256;                                // one device flag (kept 256-byte sized/aligned)
 }
 
 int ivc_me_full_search(int device, void *stream, const void *ref, const void *cur, int dtype, int64_t n_frames,
@@ -161,28 +160,24 @@ int ivc_me_full_search(int device, void *stream, const void *ref, const void *cu
     if (mode != IVC_ME_AUTO && mode != IVC_ME_EXACT && mode != IVC_ME_INT) return IVC_ERR_ARG;
     if (n_frames * H * W == 0) return IVC_OK;
     if (!ref || !cur || !mv_out) return IVC_ERR_ARG;
+    if (mode == IVC_ME_AUTO && (!workspace || workspace_bytes < ivc_me_workspace_bytes(n_frames, H, W)))
+        return IVC_ERR_WORKSPACE;
     int rc = enter(device);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const bool f32 = dtype == IVC_F32;
     cudaError_t e;
-    if (mode == IVC_ME_EXACT) {
-        e = ivc::launch_me_exact(device, st, ref, cur, f32, n_frames, H, W, ref_frame_stride, cur_frame_stride,
-                                 search_range, mv_out, nullptr, 0);
-        return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+    if (mode != IVC_ME_EXACT) {
+        // integer kernel: converts the frames to packed u8 while staging; in AUTO mode it validates them
+        // and raises the device flag instead of producing vectors from a non-integer frame
+        e = ivc::launch_me_int(device, st, ref, cur, f32, n_frames, H, W, ref_frame_stride, cur_frame_stride,
+                               search_range, mv_out, (int *)workspace, mode == IVC_ME_AUTO ? 1 : 0);
+        if (e != cudaSuccess) return cuda_fail(e);
     }
-    if (!workspace || workspace_bytes < ivc_me_workspace_bytes(n_frames, H, W)) return IVC_ERR_WORKSPACE;
-    const int64_t plane = ((n_frames * H * W + 255) / 256) * 256;
-    int *flag = (int *)workspace;
-    unsigned char *ref8 = (unsigned char *)workspace + 256, *cur8 = ref8 + plane;
-    e = ivc::launch_me_pack_u8(device, st, ref, cur, f32, n_frames, H, W, ref_frame_stride, cur_frame_stride, ref8, cur8, flag);
-    if (e != cudaSuccess) return cuda_fail(e);
-    // exactly one of the next two kernels does work, chosen by the device-side flag (no host sync)
-    e = ivc::launch_me_int(device, st, ref8, cur8, n_frames, H, W, search_range, mv_out, mode == IVC_ME_AUTO ? flag : nullptr);
-    if (e != cudaSuccess) return cuda_fail(e);
-    if (mode == IVC_ME_AUTO) {
+    if (mode != IVC_ME_INT) {
+        // exact kernel: always in EXACT mode; in AUTO mode it exits at once unless the flag was raised
         e = ivc::launch_me_exact(device, st, ref, cur, f32, n_frames, H, W, ref_frame_stride, cur_frame_stride,
-                                 search_range, mv_out, flag, 1);
+                                 search_range, mv_out, mode == IVC_ME_AUTO ? (int *)workspace : nullptr, 1);
         if (e != cudaSuccess) return cuda_fail(e);
     }
     return IVC_OK;

@@ -23,12 +23,10 @@ cudaError_t launch_zigzag(int device, cudaStream_t st, bool inverse, const void 
 // launchers implemented in ivc_motion.cu
 cudaError_t launch_me_exact(int device, cudaStream_t st, const void *ref, const void *cur, bool f32, int64_t n,
                             int64_t H, int64_t W, int64_t ref_fs, int64_t cur_fs, int sr, int64_t *mv,
-                            const int *skip_flag, int run_if_flag);
-cudaError_t launch_me_pack_u8(int device, cudaStream_t st, const void *ref, const void *cur, bool f32, int64_t n,
-                              int64_t H, int64_t W, int64_t ref_fs, int64_t cur_fs, unsigned char *ref8,
-                              unsigned char *cur8, int *flag);
-cudaError_t launch_me_int(int device, cudaStream_t st, const unsigned char *ref8, const unsigned char *cur8, int64_t n,
-                          int64_t H, int64_t W, int sr, int64_t *mv, const int *skip_flag);
+                            int *flag, int run_if);
+cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const void *cur, bool f32, int64_t n,
+                          int64_t H, int64_t W, int64_t ref_fs, int64_t cur_fs, int sr, int64_t *mv, int *flag,
+                          int check);
 cudaError_t launch_mc(int device, cudaStream_t st, const void *ref, int elem_size, int64_t n, int64_t H, int64_t W,
                       int64_t C, const int64_t *mv, int sr, void *out);
 

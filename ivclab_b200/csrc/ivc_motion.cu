@@ -2,85 +2,114 @@
 //
 // Reference: ivclab/video/motion.py:8-58 (compute_motion_vector), :60-97 (reconstruct_with_motion_vector).
 //
-// K3 (exact): one CTA stages the reference search window (+halo, zero outside the frame) and the
-// current strip of up to 16 blocks in shared memory.  One WARP owns one 8x8 block at a time; its
-// lanes enumerate (dx, dy-group) tasks, a task being G=3 vertically adjacent candidates that share
-// their reference rows in registers.  Each SSD is accumulated in numpy's own summation order
-// (8 column accumulators filled row by row, then a fixed pairwise tree; motion.py:46 == np.sum of
-// a contiguous 64-element array) with individually rounded sub/mul/add, so motion vectors are
-// bit-exact for arbitrary float frames.  The argmin is lexicographic on (ssd, index), which equals
-// the reference's "first strict minimum in (dy, dx) raster order" (motion.py:35-51).
+// Both search kernels work on a 2-D CTA tile of TBY x TBX blocks: the CTA stages the reference search
+// window of the whole tile (+-sr halo, zero outside the frame) and the current blocks in shared memory
+// once, so halo re-reads are ~1.3x instead of 2-5x and every CTA has thousands of candidates to chew on.
+// A TASK is G=3 vertically adjacent candidates (dy0..dy0+2, dx) of one block: the three candidates
+// share their reference rows in registers.
 //
-// K3 (integer): the same decomposition on packed uint8 planes with __vabsdiffu4 + __dp4a (4 pixels
-// per instruction, exact integers), valid -- and bit-identical -- whenever both frames are
-// integer-valued in [0,255]; ivc_me_full_search(IVC_ME_AUTO) checks that on the device and runs
-// exactly one of the two kernels without a host round trip.
+// K3 exact (k_me_exact<T>): one WARP owns one block at a time, lanes enumerate its tasks.  Each SSD
+// is accumulated in numpy's own summation order (8 column accumulators filled row by row, then a
+// fixed pairwise tree; motion.py:46 == np.sum of a contiguous 64-element array) with individually
+// rounded sub/mul/add, so motion vectors are bit-exact for arbitrary float frames.  The argmin is
+// lexicographic on (ssd, index) == the reference's "first strict minimum in (dy, dx) raster order"
+// (motion.py:35-51).
+//
+// K3 integer (k_me_int<T>): reads the float frames directly, converts them to packed uint8 while
+// staging (raising a device flag if any value is not an integer in [0,255]) and evaluates SSDs with
+// __vabsdiffu4 + __dp4a (4 pixels per instruction, exact integers).  Tasks of all blocks of the tile
+// are flattened over the CTA's threads; the per-block argmin is a shared-memory atomicMin on the
+// packed key (ssd << k | index).  ivc_me_full_search(IVC_ME_AUTO) launches k_me_int and then
+// k_me_exact, which exits immediately unless the flag was raised -- no host round trip, no workspace
+// beyond the 4-byte flag.
 #include "ivc_dct.cuh"
 #include "ivc_common.cuh"
 
 namespace ivc {
 
 constexpr int kMeWarps = 8;
+constexpr int kMeThreads = kMeWarps * 32;
 constexpr int kMeG = 3;            // candidates per task (vertically adjacent)
 
 struct MeArgs {
     const void *ref, *cur;
     int64_t n, H, W, ref_fs, cur_fs;
-    int Hp, Wp, sr, span, ngrp, ntask;
-    int nbx;                       // blocks per strip
-    int strips_per_row;
-    int R, P;                      // window rows / pitch (elements)
+    int Hp, Wp, sr, span, ngrp, ntpb;      // ntpb = tasks per block
+    int tby, tbx;                          // CTA tile in blocks
+    int tiles_y, tiles_x;
+    int R, P, Wc;                          // window rows / pitch / used columns (elements or bytes)
+    int cur_off;                           // byte offset of the current-blocks area in dynamic smem
     int64_t *mv;
-    const int *flag;               // optional device flag; kernel runs only if *flag == run_if
-    int run_if;
+    int *flag;                             // device flag (may be null)
+    int run_if;                            // exact kernel: run only if *flag == run_if (when flag != null)
+    int check;                             // int kernel: 1 = validate integer-valuedness and raise the flag
 };
 
 template <typename T> struct Inf;
 template <> struct Inf<double> { static __device__ __forceinline__ double v() { return __longlong_as_double(0x7ff0000000000000LL); } };
 template <> struct Inf<float> { static __device__ __forceinline__ float v() { return __int_as_float(0x7f800000); } };
 
+struct MeTile {
+    int64_t frame;
+    int by0, bx0, nby, nbx;
+};
+__device__ __forceinline__ MeTile me_tile(const MeArgs &a) {
+    MeTile t;
+    int64_t cta = blockIdx.x;
+    const int tx = (int)(cta % a.tiles_x);
+    cta /= a.tiles_x;
+    const int ty = (int)(cta % a.tiles_y);
+    t.frame = cta / a.tiles_y;
+    t.by0 = ty * a.tby;
+    t.bx0 = tx * a.tbx;
+    t.nby = min(a.tby, a.Hp - t.by0);
+    t.nbx = min(a.tbx, a.Wp - t.bx0);
+    return t;
+}
+
+// ================================================================================================
+// exact float kernel
+// ================================================================================================
 template <typename T>
-__global__ void __launch_bounds__(kMeWarps * 32, 2) k_me_exact(const MeArgs a) {
+__global__ void __launch_bounds__(kMeThreads, 2) k_me_exact(const MeArgs a) {
     if (a.flag && *a.flag != a.run_if) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *s_win = reinterpret_cast<T *>(smem_raw);                 // [R][P]
-    T *s_cur = s_win + (size_t)a.R * a.P;                        // [nbx][64]
+    T *s_win = reinterpret_cast<T *>(smem_raw);                         // [R][P]
+    T *s_cur = reinterpret_cast<T *>(smem_raw + a.cur_off);             // [tby*tbx][64]
     using R_ = Rn<T>;
-
-    int64_t cta = blockIdx.x;
-    const int strip = (int)(cta % a.strips_per_row);
-    cta /= a.strips_per_row;
-    const int by = (int)(cta % a.Hp);
-    const int64_t frame = cta / a.Hp;
-    const int bx0 = strip * a.nbx;
-    const int nb = min(a.nbx, a.Wp - bx0);
-    const T *ref = (const T *)a.ref + frame * a.ref_fs;
-    const T *cur = (const T *)a.cur + frame * a.cur_fs;
+    const MeTile tl = me_tile(a);
+    const T *ref = (const T *)a.ref + tl.frame * a.ref_fs;
+    const T *cur = (const T *)a.cur + tl.frame * a.cur_fs;
     const int sr = a.sr, span = a.span;
 
-    // ---- stage window and current strip (coalesced along x) ----
-    const int Wc = 8 * a.nbx + 2 * sr;
-    for (int idx = threadIdx.x; idx < a.R * Wc; idx += blockDim.x) {
-        const int row = idx / Wc, col = idx - row * Wc;
-        const int64_t gy = (int64_t)8 * by - sr + row, gx = (int64_t)8 * bx0 - sr + col;
+    // ---- stage window and current blocks (coalesced along x) ----
+    const int rows_used = 8 * tl.nby + 2 * sr;
+    for (int idx = threadIdx.x; idx < a.R * a.Wc; idx += blockDim.x) {
+        const int row = idx / a.Wc, col = idx - row * a.Wc;
+        const int64_t gy = (int64_t)8 * tl.by0 - sr + row, gx = (int64_t)8 * tl.bx0 - sr + col;
         T v = (T)0;
-        if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) v = ref[gy * a.W + gx];
+        if (row < rows_used && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) v = ref[gy * a.W + gx];
         s_win[row * a.P + col] = v;
     }
-    for (int idx = threadIdx.x; idx < 64 * nb; idx += blockDim.x) {
-        const int row = idx / (8 * nb), col = idx - row * 8 * nb;
-        s_cur[(col >> 3) * 64 + row * 8 + (col & 7)] = cur[((int64_t)8 * by + row) * a.W + 8 * bx0 + col];
+    const int cw = 8 * tl.nbx;
+    for (int idx = threadIdx.x; idx < 8 * tl.nby * cw; idx += blockDim.x) {
+        const int row = idx / cw, col = idx - row * cw;
+        s_cur[((row >> 3) * a.tbx + (col >> 3)) * 64 + (row & 7) * 8 + (col & 7)] =
+            cur[((int64_t)8 * tl.by0 + row) * a.W + 8 * tl.bx0 + col];
     }
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int center = sr * span + sr;
-    for (int b = warp; b < nb; b += kMeWarps) {
-        const T *cb = s_cur + b * 64;
+    const int nblk = tl.nby * tl.nbx;
+    for (int blk = warp; blk < nblk; blk += kMeWarps) {
+        const int brow = blk / tl.nbx, b = blk - brow * tl.nbx;
+        const T *cb = s_cur + (brow * a.tbx + b) * 64;
         T best = Inf<T>::v();
         int bidx = center;
-        const int gx0 = 8 * (bx0 + b);
-        for (int task = lane; task < a.ntask; task += 32) {
+        const int gx0 = 8 * (tl.bx0 + b);
+        const int64_t gy0 = (int64_t)8 * (tl.by0 + brow);
+        for (int task = lane; task < a.ntpb; task += 32) {
             const int g = task / span, dxi = task - g * span;
             const int dy0 = g * kMeG - sr;
             const int gx = gx0 + dxi - sr;
@@ -90,7 +119,7 @@ __global__ void __launch_bounds__(kMeWarps * 32, 2) k_me_exact(const MeArgs a) {
             for (int gg = 0; gg < kMeG; ++gg)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[gg][j] = (T)0;
-            const T *wp = s_win + (dy0 + sr) * a.P + 8 * b + dxi;
+            const T *wp = s_win + (8 * brow + dy0 + sr) * a.P + 8 * b + dxi;
 #pragma unroll
             for (int rr = 0; rr < kMeG + 7; ++rr) {
                 T rv[8];
@@ -111,7 +140,7 @@ __global__ void __launch_bounds__(kMeWarps * 32, 2) k_me_exact(const MeArgs a) {
 #pragma unroll
             for (int gg = 0; gg < kMeG; ++gg) {
                 const int dy = dy0 + gg;
-                const int64_t gy = (int64_t)8 * by + dy;
+                const int64_t gy = gy0 + dy;
                 if (dy <= sr && gy >= 0 && gy + 8 <= a.H) {                  // motion.py:41-43 (y bound)
                     const T s = R_::add(R_::add(R_::add(acc[gg][0], acc[gg][1]), R_::add(acc[gg][2], acc[gg][3])),
                                         R_::add(R_::add(acc[gg][4], acc[gg][5]), R_::add(acc[gg][6], acc[gg][7])));
@@ -126,122 +155,123 @@ __global__ void __launch_bounds__(kMeWarps * 32, 2) k_me_exact(const MeArgs a) {
             const int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
             if (os < best || (os == best && oi < bidx && os != Inf<T>::v())) { best = os; bidx = oi; }
         }
-        if (lane == 0) a.mv[(frame * a.Hp + by) * (int64_t)a.Wp + bx0 + b] = bidx;
+        if (lane == 0) a.mv[(tl.frame * a.Hp + tl.by0 + brow) * (int64_t)a.Wp + tl.bx0 + b] = bidx;
     }
 }
 
-// ---- integer fast path -------------------------------------------------------------------------
-struct PackArgs {
-    const void *ref, *cur;
-    int64_t n, HW, ref_fs, cur_fs;
-    unsigned char *ref8, *cur8;
-    int *flag;
-};
+// ================================================================================================
+// integer kernel (packed uint8, converted from the float frames while staging)
+// ================================================================================================
+template <typename T>
+__device__ __forceinline__ unsigned pack4(const T *p, int64_t base, int64_t gx, int64_t W, bool row_ok, bool &bad) {
+    unsigned w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (row_ok && gx + k >= 0 && gx + k < W) {
+            const T v = p[base + gx + k];
+            const int iv = (int)v;                                            // saturating; NaN -> 0
+            bad |= !((T)iv == v && iv >= 0 && iv <= 255);
+            w |= (unsigned)(iv & 255) << (8 * k);
+        }
+    }
+    return w;
+}
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_me_pack_u8(const PackArgs a) {
-    const int64_t total = a.n * a.HW;
-    bool bad = false;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t f = i / a.HW, p = i - f * a.HW;
-        const T r = ((const T *)a.ref)[f * a.ref_fs + p], c = ((const T *)a.cur)[f * a.cur_fs + p];
-        const int ri = (int)r, ci = (int)c;                                  // saturating; NaN -> 0
-        bad |= !((T)ri == r && ri >= 0 && ri <= 255 && (T)ci == c && ci >= 0 && ci <= 255);
-        a.ref8[i] = (unsigned char)ri;
-        a.cur8[i] = (unsigned char)ci;
-    }
-    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(a.flag, 1);
-}
-
-struct MeIntArgs {
-    const unsigned char *ref8, *cur8;
-    int64_t n, H, W;
-    int Hp, Wp, sr, span, ngrp, ntask, nbx, strips_per_row, R, P;           // P in bytes, multiple of 4
-    int64_t *mv;
-    const int *flag;
-};
-
-__global__ void __launch_bounds__(kMeWarps * 32, 4) k_me_int(const MeIntArgs a) {
-    if (a.flag && *a.flag != 0) return;
+__global__ void __launch_bounds__(kMeThreads, 3) k_me_int(const MeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned char *s_win = smem_raw;                                         // [R][P] bytes
-    unsigned int *s_cur = reinterpret_cast<unsigned int *>(smem_raw + (((size_t)a.R * a.P + 15) & ~(size_t)15));   // [nbx][8 rows][2 words]
-
-    int64_t cta = blockIdx.x;
-    const int strip = (int)(cta % a.strips_per_row);
-    cta /= a.strips_per_row;
-    const int by = (int)(cta % a.Hp);
-    const int64_t frame = cta / a.Hp;
-    const int bx0 = strip * a.nbx;
-    const int nb = min(a.nbx, a.Wp - bx0);
-    const unsigned char *ref = a.ref8 + frame * a.H * a.W;
-    const unsigned char *cur = a.cur8 + frame * a.H * a.W;
+    unsigned *s_win = reinterpret_cast<unsigned *>(smem_raw);                 // [R][P/4] words
+    unsigned *s_cur = reinterpret_cast<unsigned *>(smem_raw + a.cur_off);     // [tby*tbx][8 rows][2 words]
+    __shared__ unsigned long long s_best[64];
+    __shared__ int s_bad;
+    const MeTile tl = me_tile(a);
+    const T *ref = (const T *)a.ref + tl.frame * a.ref_fs;
+    const T *cur = (const T *)a.cur + tl.frame * a.cur_fs;
     const int sr = a.sr, span = a.span;
+    const int nblk = tl.nby * tl.nbx;
 
-    const int Wc = 8 * a.nbx + 2 * sr;
-    for (int idx = threadIdx.x; idx < a.R * a.P; idx += blockDim.x) {
-        const int row = idx / a.P, col = idx - row * a.P;
-        const int64_t gy = (int64_t)8 * by - sr + row, gx = (int64_t)8 * bx0 - sr + col;
-        unsigned char v = 0;
-        if (col < Wc && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) v = ref[gy * a.W + gx];
-        s_win[idx] = v;
+    if (threadIdx.x < 64) s_best[threadIdx.x] = ~0ull;
+    if (threadIdx.x == 0) s_bad = 0;
+    bool bad = false;
+    const int pw = a.P >> 2, rows_used = 8 * tl.nby + 2 * sr;
+    for (int idx = threadIdx.x; idx < a.R * pw; idx += blockDim.x) {
+        const int row = idx / pw, w = idx - row * pw;
+        const int64_t gy = (int64_t)8 * tl.by0 - sr + row, gx = (int64_t)8 * tl.bx0 - sr + 4 * w;
+        s_win[idx] = pack4(ref, gy * a.W, gx, a.W, row < rows_used && gy >= 0 && gy < a.H && 4 * w < a.Wc, bad);
     }
-    unsigned char *s_cur_b = reinterpret_cast<unsigned char *>(s_cur);
-    for (int idx = threadIdx.x; idx < 64 * nb; idx += blockDim.x) {
-        const int row = idx / (8 * nb), col = idx - row * 8 * nb;
-        s_cur_b[(col >> 3) * 64 + row * 8 + (col & 7)] = cur[((int64_t)8 * by + row) * a.W + 8 * bx0 + col];
+    const int cww = 2 * tl.nbx;                                               // words per current row
+    for (int idx = threadIdx.x; idx < 8 * tl.nby * cww; idx += blockDim.x) {
+        const int row = idx / cww, w = idx - row * cww;
+        const int64_t gy = (int64_t)8 * tl.by0 + row;
+        s_cur[((row >> 3) * a.tbx + (w >> 1)) * 16 + (row & 7) * 2 + (w & 1)] =
+            pack4(cur, gy * a.W, (int64_t)8 * tl.bx0 + 4 * w, a.W, true, bad);
     }
     __syncthreads();
+    if (a.check) {
+        if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) s_bad = 1;
+        __syncthreads();
+        if (s_bad) {                                                          // not an integer frame: leave it to k_me_exact
+            if (threadIdx.x == 0) atomicOr(a.flag, 1);
+            return;
+        }
+    }
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned long long kNone = ~0ull;
-    for (int b = warp; b < nb; b += kMeWarps) {
-        const uint2 *cb = reinterpret_cast<const uint2 *>(s_cur + b * 16);
-        unsigned long long best = kNone;
-        const int gx0 = 8 * (bx0 + b);
-        for (int task = lane; task < a.ntask; task += 32) {
-            const int g = task / span, dxi = task - g * span;
-            const int dy0 = g * kMeG - sr;
-            const int gx = gx0 + dxi - sr;
-            if (gx < 0 || gx + 8 > a.W) continue;
-            unsigned int acc[kMeG];
+    const bool small = span * span <= 512;                                    // ssd < 2^22, index < 2^9: key fits 32 bits
+    unsigned *s_best32 = reinterpret_cast<unsigned *>(s_best);
+    const int total = nblk * a.ntpb;
+    for (int task = threadIdx.x; task < total; task += blockDim.x) {
+        const int blk = task / a.ntpb, rem = task - blk * a.ntpb;
+        const int g = rem / span, dxi = rem - g * span;
+        const int brow = blk / tl.nbx, b = blk - brow * tl.nbx;
+        const int dy0 = g * kMeG - sr;
+        const int gx = 8 * (tl.bx0 + b) + dxi - sr;
+        if (gx < 0 || gx + 8 > a.W) continue;
+        const uint2 *cb = reinterpret_cast<const uint2 *>(s_cur + (brow * a.tbx + b) * 16);
+        uint2 c[8];
 #pragma unroll
-            for (int gg = 0; gg < kMeG; ++gg) acc[gg] = 0u;
-            const int colb = 8 * b + dxi;                                    // byte column in the window
-            const unsigned int *wrow = reinterpret_cast<const unsigned int *>(s_win + (dy0 + sr) * a.P) + (colb >> 2);
-            const int sh = (colb & 3) * 8;
+        for (int i = 0; i < 8; ++i) c[i] = cb[i];
+        unsigned acc[kMeG];
 #pragma unroll
-            for (int rr = 0; rr < kMeG + 7; ++rr) {
-                const unsigned int *w = wrow + rr * (a.P >> 2);
-                const unsigned int w0 = w[0], w1 = w[1], w2 = w[2];
-                const unsigned int r0 = __funnelshift_r(w0, w1, sh), r1 = __funnelshift_r(w1, w2, sh);
+        for (int gg = 0; gg < kMeG; ++gg) acc[gg] = 0u;
+        const int colb = 8 * b + dxi;                                         // byte column in the window
+        const unsigned *wrow = s_win + (8 * brow + dy0 + sr) * pw + (colb >> 2);
+        const int sh = (colb & 3) * 8;
 #pragma unroll
-                for (int gg = 0; gg < kMeG; ++gg) {
-                    const int i = rr - gg;
-                    if (i >= 0 && i < 8) {
-                        const uint2 c = cb[i];
-                        const unsigned int d0 = __vabsdiffu4(c.x, r0), d1 = __vabsdiffu4(c.y, r1);
-                        acc[gg] = __dp4a(d0, d0, acc[gg]);
-                        acc[gg] = __dp4a(d1, d1, acc[gg]);
-                    }
-                }
-            }
+        for (int rr = 0; rr < kMeG + 7; ++rr) {
+            const unsigned *w = wrow + rr * pw;
+            const unsigned w0 = w[0], w1 = w[1], w2 = w[2];
+            const unsigned r0 = __funnelshift_r(w0, w1, sh), r1 = __funnelshift_r(w1, w2, sh);
 #pragma unroll
             for (int gg = 0; gg < kMeG; ++gg) {
-                const int dy = dy0 + gg;
-                const int64_t gy = (int64_t)8 * by + dy;
-                if (dy <= sr && gy >= 0 && gy + 8 <= a.H) {
-                    const unsigned long long key = ((unsigned long long)acc[gg] << 32) | (unsigned int)((dy + sr) * span + dxi);
-                    best = key < best ? key : best;
+                const int i = rr - gg;
+                if (i >= 0 && i < 8) {
+                    const unsigned d0 = __vabsdiffu4(c[i].x, r0), d1 = __vabsdiffu4(c[i].y, r1);
+                    acc[gg] = __dp4a(d0, d0, acc[gg]);
+                    acc[gg] = __dp4a(d1, d1, acc[gg]);
                 }
             }
         }
+        unsigned long long key = ~0ull;
+        const int64_t gy0 = (int64_t)8 * (tl.by0 + brow);
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
-            best = o < best ? o : best;
+        for (int gg = 0; gg < kMeG; ++gg) {
+            const int dy = dy0 + gg;
+            const int64_t gy = gy0 + dy;
+            if (dy <= sr && gy >= 0 && gy + 8 <= a.H) {
+                const unsigned long long k = ((unsigned long long)acc[gg] << 32) | (unsigned)((dy + sr) * span + dxi);
+                key = k < key ? k : key;
+            }
         }
-        if (lane == 0) a.mv[(frame * a.Hp + by) * (int64_t)a.Wp + bx0 + b] = (int64_t)(best & 0xffffffffull);
+        if (key != ~0ull) {
+            if (small) atomicMin(s_best32 + blk, ((unsigned)(key >> 32) << 9) | (unsigned)(key & 511u));
+            else atomicMin(s_best + blk, key);
+        }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nblk) {
+        const int blk = threadIdx.x, brow = blk / tl.nbx, b = blk - brow * tl.nbx;
+        const int64_t idx = small ? (int64_t)(s_best32[blk] & 511u) : (int64_t)(s_best[blk] & 0xffffffffull);
+        a.mv[(tl.frame * a.Hp + tl.by0 + brow) * (int64_t)a.Wp + tl.bx0 + b] = idx;
     }
 }
 
@@ -281,81 +311,72 @@ static int sm_count(int device) {
     return sms;
 }
 
-template <typename A>
-static void me_geometry(A &a, int64_t H, int64_t W, int sr, int elem, size_t &smem, int pitch_quantum, int pitch_skew) {
+// choose the CTA tile (at most 64 blocks) and the shared-memory layout
+static size_t me_geometry(MeArgs &a, int64_t H, int64_t W, int sr, int elem, int pitch_quantum, int pitch_skew,
+                          size_t budget) {
     a.Hp = (int)(H / 8); a.Wp = (int)(W / 8); a.sr = sr; a.span = 2 * sr + 1;
     a.ngrp = (a.span + kMeG - 1) / kMeG;
-    a.ntask = a.ngrp * a.span;
-    a.R = a.ngrp * kMeG + 7;
-    int nbx = 16;
-    for (;;) {
-        const int Wc = 8 * nbx + 2 * sr;
-        a.P = ((Wc + pitch_quantum - 1) / pitch_quantum) * pitch_quantum + pitch_skew;
-        smem = (size_t)a.R * a.P * elem + (size_t)nbx * 64 * elem;
-        if (smem <= 100 * 1024 || nbx == 1) break;
-        nbx >>= 1;
+    a.ntpb = a.ngrp * a.span;
+    static const int shapes[][2] = {{4, 16}, {2, 16}, {2, 8}, {1, 8}, {1, 4}, {1, 2}, {1, 1}};
+    size_t smem = 0;
+    for (auto &s : shapes) {
+        a.tby = s[0]; a.tbx = s[1];
+        a.R = 8 * (a.tby - 1) + a.ngrp * kMeG + 7;                 // >= 8*tby + 2*sr, covers the last dy-group
+        a.Wc = 8 * a.tbx + 2 * sr;
+        a.P = ((a.Wc + pitch_quantum - 1) / pitch_quantum) * pitch_quantum + pitch_skew;
+        a.cur_off = (int)((((size_t)a.R * a.P * elem) + 15) & ~(size_t)15);
+        smem = (size_t)a.cur_off + (size_t)a.tby * a.tbx * 64 * elem;
+        if (smem <= budget) break;
     }
-    if (nbx > a.Wp) nbx = a.Wp > 0 ? a.Wp : 1;
-    a.nbx = nbx;
-    a.strips_per_row = (a.Wp + nbx - 1) / nbx;
+    a.tiles_y = (a.Hp + a.tby - 1) / a.tby;
+    a.tiles_x = (a.Wp + a.tbx - 1) / a.tbx;
+    return smem;
 }
 
 cudaError_t launch_me_exact(int device, cudaStream_t st, const void *ref, const void *cur, bool f32, int64_t n,
                             int64_t H, int64_t W, int64_t ref_fs, int64_t cur_fs, int sr, int64_t *mv,
-                            const int *flag, int run_if) {
+                            int *flag, int run_if) {
     MeArgs a;
     a.ref = ref; a.cur = cur; a.n = n; a.H = H; a.W = W; a.ref_fs = ref_fs; a.cur_fs = cur_fs; a.mv = mv;
-    a.flag = flag; a.run_if = run_if;
-    size_t smem = 0;
-    me_geometry(a, H, W, sr, f32 ? 4 : 8, smem, 32, 3);
+    a.flag = flag; a.run_if = run_if; a.check = 0;
+    const size_t smem = me_geometry(a, H, W, sr, f32 ? 4 : 8, 32, 3, 100 * 1024);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    const int64_t ctas = n * a.Hp * (int64_t)a.strips_per_row;
+    const int64_t ctas = n * a.tiles_y * (int64_t)a.tiles_x;
     if (ctas == 0) return cudaSuccess;
     if (ctas > 2147483647LL) return cudaErrorInvalidValue;
     cudaError_t e;
     if (f32) {
         if ((e = cudaFuncSetAttribute(k_me_exact<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k_me_exact<float><<<(unsigned)ctas, kMeWarps * 32, smem, st>>>(a);
+        k_me_exact<float><<<(unsigned)ctas, kMeThreads, smem, st>>>(a);
     } else {
         if ((e = cudaFuncSetAttribute(k_me_exact<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k_me_exact<double><<<(unsigned)ctas, kMeWarps * 32, smem, st>>>(a);
+        k_me_exact<double><<<(unsigned)ctas, kMeThreads, smem, st>>>(a);
     }
     (void)device;
     return cudaGetLastError();
 }
 
-cudaError_t launch_me_pack_u8(int device, cudaStream_t st, const void *ref, const void *cur, bool f32, int64_t n,
-                              int64_t H, int64_t W, int64_t ref_fs, int64_t cur_fs, unsigned char *ref8,
-                              unsigned char *cur8, int *flag) {
-    PackArgs a;
-    a.ref = ref; a.cur = cur; a.n = n; a.HW = H * W; a.ref_fs = ref_fs; a.cur_fs = cur_fs; a.ref8 = ref8; a.cur8 = cur8;
-    a.flag = flag;
-    cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), st);
-    if (e != cudaSuccess) return e;
-    const int64_t total = n * H * W;
-    if (total == 0) return cudaSuccess;
-    int64_t grid = (total + 256 * 8 - 1) / (256 * 8);
-    const int64_t cap = (int64_t)sm_count(device) * 16;
-    if (grid > cap) grid = cap;
-    if (f32) k_me_pack_u8<float><<<(unsigned)grid, 256, 0, st>>>(a);
-    else k_me_pack_u8<double><<<(unsigned)grid, 256, 0, st>>>(a);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_me_int(int device, cudaStream_t st, const unsigned char *ref8, const unsigned char *cur8, int64_t n,
-                          int64_t H, int64_t W, int sr, int64_t *mv, const int *flag) {
-    MeIntArgs a;
-    a.ref8 = ref8; a.cur8 = cur8; a.n = n; a.H = H; a.W = W; a.mv = mv; a.flag = flag;
-    size_t smem = 0;
-    me_geometry(a, H, W, sr, 1, smem, 4, 4);      // +4 bytes: the funnel shift reads one word past the last column
-    smem = (((size_t)a.R * a.P + 15) & ~(size_t)15) + (size_t)a.nbx * 64;
+cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const void *cur, bool f32, int64_t n,
+                          int64_t H, int64_t W, int64_t ref_fs, int64_t cur_fs, int sr, int64_t *mv, int *flag,
+                          int check) {
+    MeArgs a;
+    a.ref = ref; a.cur = cur; a.n = n; a.H = H; a.W = W; a.ref_fs = ref_fs; a.cur_fs = cur_fs; a.mv = mv;
+    a.flag = flag; a.run_if = 0; a.check = check;
+    // pitch in bytes: multiple of 4 plus 4 (the funnel shift reads one word past the last column)
+    const size_t smem = me_geometry(a, H, W, sr, 1, 4, 4, 64 * 1024);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    const int64_t ctas = n * a.Hp * (int64_t)a.strips_per_row;
+    const int64_t ctas = n * a.tiles_y * (int64_t)a.tiles_x;
     if (ctas == 0) return cudaSuccess;
     if (ctas > 2147483647LL) return cudaErrorInvalidValue;
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_me_int, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    k_me_int<<<(unsigned)ctas, kMeWarps * 32, smem, st>>>(a);
+    if (check && (e = cudaMemsetAsync(flag, 0, sizeof(int), st)) != cudaSuccess) return e;
+    if (f32) {
+        if ((e = cudaFuncSetAttribute(k_me_int<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        k_me_int<float><<<(unsigned)ctas, kMeThreads, smem, st>>>(a);
+    } else {
+        if ((e = cudaFuncSetAttribute(k_me_int<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        k_me_int<double><<<(unsigned)ctas, kMeThreads, smem, st>>>(a);
+    }
     (void)device;
     return cudaGetLastError();
 }
