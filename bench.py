@@ -32,6 +32,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line
 
 H, W = 1080, 1920
 QSCALE = 1.0
@@ -315,7 +317,7 @@ def run_b200(args):
                     "api": "IntraBlockCoder.forward/inverse + PFrameBlockCoder.estimate/forward/inverse, pinned host buffers"},
             "gpu_launches": K * launches_per_step,
             "clocks": clk,
-            "roofline": {"kernel": "k_forward<3,false> (fused DCT+quantize+zig-zag)", "bound": "hbm",
+            "roofline": {"kernel": "k_forward_c3_tma (K1: fused DCT+quantize+zig-zag, 3-channel intra)", "bound": "hbm",
                          "achieved": round(k1_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(k1_gbs / peak, 4),
                          "traffic": traffic, "algorithmic_bytes_per_launch": k1_bytes, "peak_source": which,
                          "avg_launch_ms": round(phase_ms["intra_fwd"], 4)},

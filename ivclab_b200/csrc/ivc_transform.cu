@@ -781,6 +781,348 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_inverse_c3_tma(const I
 }
 
 // ================================================================================================
+// v2 of the P-frame kernels (K1p / K2p): the same per-warp pipeline, with the motion-compensated
+// prediction gathered asynchronously.  Per warp: IN (current rows / scan blocks, TMA bulk copies),
+// PRED (8 x 96 doubles: cp.async 8-byte copies from ref at the block's motion vector -- sources are
+// only 8-byte aligned; zero-fill when the source window leaves the frame, motion.py:90-92) and WORK.
+// Both land on one mbarrier (1 expect_tx arrival + 32 deferred cp.async arrivals).  The vectors of
+// tile i+2 are fetched while tile i is computed, so no global load is ever waited on.
+// One CTA of 12 warps per SM (3200 + 12 * 18944 bytes of shared memory).
+// ================================================================================================
+constexpr int kPfWarps = 12;
+constexpr int kPfBuf = 2 * kInBytes + kWorkBytes;        // 18944
+static_assert(kPfBuf % 128 == 0, "alignment");
+
+__device__ __forceinline__ void cp_async8_zfill(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// Issue the gather of one tile's prediction into PRED.  Copy k of a lane (k = 0..23) is pixel row
+// k/3, tile column 32*(k%3) + lane, so a lane touches three blocks per tile.
+struct PredGather {
+    const double *ref;       // frame base is added per tile
+    int64_t H, W;
+    int sr;
+    __device__ __forceinline__ void issue(uint32_t pred_s, uint32_t bar, int lane, int64_t mvidx, int nb,
+                                          const double *ref_frame, int by, int b0) const {
+        int dy = 0, dx = 0;
+        if (lane < nb) mv_decode(mvidx, sr, dy, dx);
+#pragma unroll
+        for (int c3 = 0; c3 < 3; ++c3) {
+            const int col = 32 * c3 + lane, blk = col >> 3;
+            const int bdy = __shfl_sync(0xffffffffu, dy, blk), bdx = __shfl_sync(0xffffffffu, dx, blk);
+            if (blk < nb) {
+                const int64_t sy = (int64_t)by * 8 + bdy, sx = (int64_t)(b0 + blk) * 8 + bdx;
+                const bool ok = sy >= 0 && sy + 8 <= H && sx >= 0 && sx + 8 <= W;
+                const double *src = ok ? ref_frame + sy * W + sx + (col & 7) : ref_frame;
+                const uint32_t nbytes = ok ? 8u : 0u;
+#pragma unroll
+                for (int row = 0; row < 8; ++row)
+                    cp_async8_zfill(pred_s + (row * kRowPitch + col) * 8, src + (ok ? row * W : 0), nbytes);
+            }
+        }
+        cp_async_mbar_arrive(bar);
+    }
+};
+
+__global__ void __launch_bounds__(kPfWarps * 32, 1) k_pframe_forward_tma(const FwdArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *s_rt = reinterpret_cast<double *>(smem_raw);                       // [192]
+    double *s_t = s_rt + 192;                                                   // [192]
+    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem_raw + 3072);   // [12]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *in_b = smem_raw + 3200 + warp * kPfBuf;
+    unsigned char *pred_b = in_b + kInBytes;
+    unsigned char *work_b = pred_b + kInBytes;
+    const uint32_t bar = smem_u32(s_bar + warp), in_s = smem_u32(in_b), pred_s = smem_u32(pred_b), work_s = smem_u32(work_b);
+
+    for (int i = threadIdx.x; i < 192; i += blockDim.x) {
+        const double t = load_table_elem(a.table, a.table_dtype, i);
+        s_t[i] = t;
+        s_rt[i] = __drcp_rn(t);
+    }
+    if (lane == 0) mbar_init(bar, 33);
+    fence_mbar_init();
+    __syncthreads();
+
+    const int r = lane & 7, u = lane >> 3;
+    const unsigned char *rd_in = in_b + r * (kRowPitch * 8) + u * 192;
+    const unsigned char *rd_pr = pred_b + r * (kRowPitch * 8) + u * 192;
+    unsigned char *t_wr[4], *zz_wr[8];
+    const unsigned char *t_rd[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        t_wr[h] = work_b + u * (kTU2 * 8) + ((((r >> 1) ^ h) << 1) + (r & 1)) * 8;
+        t_rd[h] = work_b + u * (kTU2 * 8) + r * 64 + ((h ^ (r >> 1)) << 4);
+    }
+#pragma unroll
+    for (int v = 0; v < 8; ++v) zz_wr[v] = work_b + (u * kStageU + ZZ_ORDER[v * 8 + r]) * 4;   // + ch*256 (+3200 for region B)
+    const double *rt_l = s_rt + r, *t_l = s_t + r;
+
+    const TileGeom &g = a.g;
+    const int64_t row_elems = g.W, frame_elems = g.H * g.W;
+    const int64_t gw = (int64_t)blockIdx.x * kPfWarps + warp;
+    const int64_t nw = (int64_t)gridDim.x * kPfWarps;
+    if (gw >= g.total_tiles) return;
+    const int64_t my_tiles = (g.total_tiles - gw + nw - 1) / nw;
+    TileIter cur, nxt, nx2;
+    cur.init(g, gw, nw);
+    nxt = cur;
+    PredGather pg{a.ref, g.H, g.W, a.sr};
+
+    auto load_mv = [&](const TileIter &ti) -> int64_t {          // lanes 0..11: vector of block (b0 + lane)
+        const int b0 = ti.tx * 12;
+        return (lane < min(12, g.Wp - b0)) ? a.mv[(ti.frame * g.Hp + ti.by) * (int64_t)g.Wp + b0 + lane] : 0;
+    };
+    auto issue = [&](const TileIter &ti, int64_t mvidx) {        // whole warp
+        const int b0 = ti.tx * 12, nb = min(12, g.Wp - b0);
+        if (lane == 0) {
+            const uint32_t row_bytes = (uint32_t)nb * 64u;
+            const double *src = a.img + ti.frame * a.frame_stride + (int64_t)ti.by * 8 * row_elems + (int64_t)b0 * 8;
+            fence_proxy_async();
+            mbar_expect_tx(bar, 8u * row_bytes);
+#pragma unroll
+            for (int row = 0; row < 8; ++row) bulk_g2s(in_s + row * (kRowPitch * 8), src + row * row_elems, row_bytes, bar);
+        }
+        pg.issue(pred_s, bar, lane, mvidx, nb, a.ref + ti.frame * frame_elems, ti.by, b0);
+    };
+
+    int64_t mv_nxt = load_mv(cur);
+    issue(cur, mv_nxt);
+    nxt.advance(g);
+    mv_nxt = (my_tiles > 1) ? load_mv(nxt) : 0;
+    nx2 = nxt;
+    uint32_t parity = 0;
+    for (int64_t it = 0; it < my_tiles; ++it, parity ^= 1u) {
+        nx2.advance(g);
+        const int b0 = cur.tx * 12, nb = min(12, g.Wp - b0);
+        mbar_wait(bar, parity);
+        double x[3][8];
+        {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const double2 c = *reinterpret_cast<const double2 *>(rd_in + 16 * k);
+                const double2 p = *reinterpret_cast<const double2 *>(rd_pr + 16 * k);
+                if (a.pred_out && (3 * u + (k >> 2)) < nb)
+                    stg_stream(a.pred_out + cur.frame * frame_elems + ((int64_t)cur.by * 8 + r) * row_elems +
+                                   (int64_t)b0 * 8 + 24 * u + 2 * k, p);
+                x[k >> 2][(2 * k) & 7] = __dsub_rn(c.x, p.x);              // residual = cur - prediction
+                x[k >> 2][(2 * k + 1) & 7] = __dsub_rn(c.y, p.y);
+            }
+        }
+        __syncwarp();                                   // IN / PRED are consumed
+        const int64_t mv_cur_next = mv_nxt;
+        if (it + 1 < my_tiles) {
+            issue(nxt, mv_cur_next);
+            mv_nxt = (it + 2 < my_tiles) ? load_mv(nx2) : 0;      // consumed one iteration later
+        }
+#pragma unroll
+        for (int m = 0; m < 3; ++m) dct2_8(x[m]);
+        if (lane == 0) bulk_wait_read0();               // previous tile's stores have drained WORK
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) *reinterpret_cast<double *>(t_wr[j >> 1] + (m * 8 + j) * 64) = x[m][j];
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double2 v = *reinterpret_cast<const double2 *>(t_rd[k] + m * 512);
+                x[m][2 * k] = v.x;
+                x[m][2 * k + 1] = v.y;
+            }
+            dct2_8(x[m]);
+        }
+        __syncwarp();
+        // numpy broadcasting: the single luma channel is quantised with all three tables
+        // (patchquant.py:59).  One round per sub-block m; staging regions A/B/A.
+        int32_t *outf = a.out + ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0) * 192;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            const int reg = (m & 1) * 3200;
+            if (m == 2) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); __syncwarp(); }
+            QuantGuard qg;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                for (int v = 0; v < 8; ++v)
+                    *reinterpret_cast<int *>(zz_wr[v] + reg + ch * 256) = qg.q(x[m][v], rt_l[ch * 64 + v * 8]);
+            if (__builtin_expect(qg.risky(), 0)) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                    for (int v = 0; v < 8; ++v)
+                        *reinterpret_cast<int *>(zz_wr[v] + reg + ch * 256) = quantize_exact_f64(x[m][v], t_l[ch * 64 + v * 8]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                for (int cu = 0; cu < 4; ++cu)
+                    if (3 * cu + m < nb) bulk_s2g(outf + (3 * cu + m) * 192, work_s + reg + cu * (kStageU * 4), 768u);
+                bulk_commit();
+            }
+        }
+        cur = nxt;
+        nxt = nx2;
+    }
+    if (lane == 0) bulk_wait_all0();
+}
+
+__global__ void __launch_bounds__(kPfWarps * 32, 1) k_pframe_inverse_tma(const InvArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *s_tT = reinterpret_cast<double *>(smem_raw);                        // [64] luminance table, transposed
+    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem_raw + 3072);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // per-warp: IN = scan blocks (uses 3200 of the 6272 bytes), PRED, WORK
+    unsigned char *in_b = smem_raw + 3200 + warp * kPfBuf;
+    unsigned char *pred_b = in_b + kInBytes;
+    unsigned char *work_b = pred_b + kInBytes;
+    const uint32_t bar = smem_u32(s_bar + warp), in_s = smem_u32(in_b), pred_s = smem_u32(pred_b), work_s = smem_u32(work_b);
+
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_tT[(i & 7) * 8 + (i >> 3)] = load_table_elem(a.table, a.table_dtype, i);
+    const bool gather = a.pred == nullptr;
+    if (lane == 0) mbar_init(bar, gather ? 33 : 1);
+    fence_mbar_init();
+    __syncthreads();
+
+    const int r = lane & 7, u = lane >> 3;
+    const unsigned char *q_rd[8];
+    unsigned char *t_wr[4], *o_wr;
+    const unsigned char *t_rd[4], *p_rd;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q_rd[j] = in_b + (u * kStageU + ZZ_ORDER[r * 8 + j]) * 4;   // + m*256
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        t_wr[h] = work_b + u * (kTU2 * 8) + ((((r >> 1) ^ h) << 1) + (r & 1)) * 8;
+        t_rd[h] = work_b + u * (kTU2 * 8) + r * 64 + ((h ^ (r >> 1)) << 4);
+    }
+    o_wr = work_b + (24 * u + r) * 8;                                          // + i*784 + m*64
+    p_rd = pred_b + (24 * u + r) * 8;
+    const double *tq_l = s_tT + r;                                             // tq_l[j*8] = lum[r][j]
+
+    const TileGeom &g = a.g;
+    const int64_t row_elems = g.W, frame_elems = g.H * g.W;
+    const int64_t gw = (int64_t)blockIdx.x * kPfWarps + warp;
+    const int64_t nw = (int64_t)gridDim.x * kPfWarps;
+    if (gw >= g.total_tiles) return;
+    const int64_t my_tiles = (g.total_tiles - gw + nw - 1) / nw;
+    TileIter cur, nxt, nx2;
+    cur.init(g, gw, nw);
+    nxt = cur;
+    PredGather pg{a.ref, g.H, g.W, a.sr};
+
+    auto load_mv = [&](const TileIter &ti) -> int64_t {
+        const int b0 = ti.tx * 12;
+        return (gather && lane < min(12, g.Wp - b0)) ? a.mv[(ti.frame * g.Hp + ti.by) * (int64_t)g.Wp + b0 + lane] : 0;
+    };
+    auto issue = [&](const TileIter &ti, int64_t mvidx) {
+        const int b0 = ti.tx * 12, nb = min(12, g.Wp - b0);
+        if (lane == 0) {
+            const int32_t *zsrc = a.zz + ((ti.frame * g.Hp + ti.by) * (int64_t)g.Wp + b0) * a.Czz * 64;
+            const uint32_t row_bytes = (uint32_t)nb * 64u;
+            fence_proxy_async();
+            mbar_expect_tx(bar, (uint32_t)nb * 256u + (gather ? 0u : 8u * row_bytes));
+            for (int blk = 0; blk < nb; ++blk) {          // scan channel 0 of every block (stride Czz*64 ints)
+                const int cu = blk / 3;
+                bulk_g2s(in_s + (cu * kStageU + (blk - cu * 3) * 64) * 4, zsrc + (int64_t)blk * a.Czz * 64, 256u, bar);
+            }
+            if (!gather) {
+                const double *psrc = a.pred + ti.frame * frame_elems + (int64_t)ti.by * 8 * row_elems + (int64_t)b0 * 8;
+#pragma unroll
+                for (int row = 0; row < 8; ++row) bulk_g2s(pred_s + row * (kRowPitch * 8), psrc + row * row_elems, row_bytes, bar);
+            }
+        }
+        if (gather) pg.issue(pred_s, bar, lane, mvidx, nb, a.ref + ti.frame * frame_elems, ti.by, b0);
+    };
+
+    int64_t mv_nxt = load_mv(cur);
+    issue(cur, mv_nxt);
+    nxt.advance(g);
+    mv_nxt = (my_tiles > 1) ? load_mv(nxt) : 0;
+    nx2 = nxt;
+    uint32_t parity = 0;
+    for (int64_t it = 0; it < my_tiles; ++it, parity ^= 1u) {
+        nx2.advance(g);
+        const int b0 = cur.tx * 12, nb = min(12, g.Wp - b0);
+        mbar_wait(bar, parity);
+        int q[3][8];
+        double pr[3][8];                                 // prediction of column r of the three blocks
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) q[m][j] = *reinterpret_cast<const int *>(q_rd[j] + m * 256);
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pr[m][i] = *reinterpret_cast<const double *>(p_rd + i * (kRowPitch * 8) + m * 64);
+        __syncwarp();
+        const int64_t mv_cur_next = mv_nxt;
+        if (it + 1 < my_tiles) {
+            issue(nxt, mv_cur_next);
+            mv_nxt = (it + 2 < my_tiles) ? load_mv(nx2) : 0;
+        }
+        double x[3][8];
+        int mx = 0;
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const double p = __dmul_rn(i32_to_f64(q[m][j]), tq_l[j * 8]);       // luminance table for every block
+                mx = max(mx, __double2hiint(p) & 0x7fffffff);
+                x[m][j] = trunc_f64_small(p);
+            }
+        if (__builtin_expect(mx >= 0x41E00000, 0)) {
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[m][j] = dequantize_f64(q[m][j], tq_l[j * 8]);
+        }
+#pragma unroll
+        for (int m = 0; m < 3; ++m) dct3_8(x[m]);
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) *reinterpret_cast<double *>(t_wr[j >> 1] + (m * 8 + j) * 64) = x[m][j];
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double2 v = *reinterpret_cast<const double2 *>(t_rd[k] + m * 512);
+                x[m][2 * k] = v.x;
+                x[m][2 * k + 1] = v.y;
+            }
+            dct3_8(x[m]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)                  // recon = prediction + recon_residual (videocodec.py:74)
+                *reinterpret_cast<double *>(o_wr + i * (kRowPitch * 8) + m * 64) = __dadd_rn(pr[m][i], x[m][i]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            double *dst = a.out + cur.frame * frame_elems + (int64_t)cur.by * 8 * row_elems + (int64_t)b0 * 8;
+            const uint32_t row_bytes = (uint32_t)nb * 64u;
+#pragma unroll
+            for (int row = 0; row < 8; ++row) bulk_s2g(dst + row * row_elems, work_s + row * (kRowPitch * 8), row_bytes);
+            bulk_commit();
+        }
+        cur = nxt;
+        nxt = nx2;
+    }
+    if (lane == 0) bulk_wait_all0();
+}
+
+// ================================================================================================
 // unfused per-method kernels (each class method alone; simple, still coalesced where it matters)
 // ================================================================================================
 template <typename TI>
@@ -947,7 +1289,11 @@ cudaError_t launch_forward(int device, cudaStream_t st, const void *img, int64_t
     const size_t smem = 2 * 192 * sizeof(double) + kWarpsPerCta * kWarpBufBytes;
     const int grid = grid_for(a.g.total_tiles, kWarpsPerCta, device, 2);
     cudaError_t e;
-    if (pframe) {
+    if (pframe && !use_v1()) {
+        const size_t smem2 = 3200 + (size_t)kPfWarps * kPfBuf;
+        if ((e = set_smem(k_pframe_forward_tma, smem2)) != cudaSuccess) return e;
+        k_pframe_forward_tma<<<grid_for(a.g.total_tiles, kPfWarps, device, 1), kPfWarps * 32, smem2, st>>>(a);
+    } else if (pframe) {
         if ((e = set_smem(k_forward<1, true>, smem)) != cudaSuccess) return e;
         k_forward<1, true><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
     } else if (C == 3 && !use_v1()) {
@@ -985,6 +1331,10 @@ cudaError_t launch_inverse(int device, cudaStream_t st, const int32_t *zz, int64
     } else if (mode == 1) {
         if ((e = set_smem(k_inverse<1>, smem)) != cudaSuccess) return e;
         k_inverse<1><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
+    } else if (!use_v1()) {
+        const size_t smem2 = 3200 + (size_t)kPfWarps * kPfBuf;
+        if ((e = set_smem(k_pframe_inverse_tma, smem2)) != cudaSuccess) return e;
+        k_pframe_inverse_tma<<<grid_for(a.g.total_tiles, kPfWarps, device, 1), kPfWarps * 32, smem2, st>>>(a);
     } else {
         if ((e = set_smem(k_inverse<2>, smem)) != cudaSuccess) return e;
         k_inverse<2><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
