@@ -1,0 +1,113 @@
+#!/usr/bin/env python
+"""Secondary measurements on the five configurations BASELINE.json names (device-resident inputs,
+CUDA events, one GPU).  `bench.py` is the contract benchmark; this script fills the per-config table
+of DESIGN.md.    python bench_configs.py [--quick] > profiles/<round>_configs.json"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import ivclab_b200 as ivc  # noqa: E402
+
+QS = [0.07, 0.2, 0.4, 0.8, 1.0, 1.5, 2, 3, 4, 4.5]     # exercises/ch4/ex1.py:385
+
+
+def timed(fn, reps, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def luma_seq(T, H, W, seed, shift=3):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    m = 4 * shift + 8
+    base = torch.randint(0, 256, (1, 1, H + 2 * m, W + 2 * m), generator=g, device="cuda").double()
+    canvas = ((torch.nn.functional.avg_pool2d(base, 5, stride=1, padding=2) - 127.5) * 3 + 127.5)[0, 0]
+    out = torch.empty((T, H, W), dtype=torch.float64, device="cuda")
+    sh = torch.randint(-shift, shift + 1, (T, 2), generator=g, device="cuda").cpu().tolist()
+    for t, (dy, dx) in enumerate(sh):
+        f = canvas[m + dy:m + dy + H, m + dx:m + dx + W] + torch.randn((H, W), generator=g, device="cuda", dtype=torch.float64)
+        out[t] = f.round().clamp(0, 255)
+    return out
+
+
+def main():
+    quick = "--quick" in sys.argv
+    res = {"gpu": torch.cuda.get_device_name(0)}
+    g = torch.Generator(device="cuda").manual_seed(0)
+
+    # cfg1: one 512x768 YCbCr image, qScale 1: device time of the fused pair and of the six per-method calls
+    img = torch.rand((512, 768, 3), generator=g, device="cuda", dtype=torch.float64) * 255
+    c = ivc.IntraBlockCoder(1.0)
+    D, Q, Z, P = ivc.DiscreteCosineTransform(), ivc.PatchQuant(1.0), ivc.ZigZag(), ivc.Patcher()
+    t_f = timed(lambda: c.inverse(c.forward(img)), 50)
+    t_u = timed(lambda: D.inverse_transform(Q.dequantize(Z.unflatten(Z.flatten(Q.quantize(D.transform(P.patch(img))))))), 50)
+    h = img.cpu().numpy()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        c.inverse(c.forward(h))
+    t_h = (time.perf_counter() - t0) / 10 * 1e3
+    res["cfg1_512x768_rgb"] = {"fused_fwd_inv_ms": t_f, "six_method_calls_ms": t_u, "numpy_in_numpy_out_ms": t_h,
+                               "mpixel_s_fused": 512 * 768 / t_f / 1e3}
+
+    # cfg2: QCIF 21 frames closed loop
+    seq = luma_seq(21, 144, 176, 2)
+    for graph in (False, True):
+        cl = ivc.ClosedLoopLumaCoder(1.0, 4, decode="luma", me_mode="exact", use_graph=graph)
+        t = timed(lambda: cl.code_sequence(seq), 20)
+        res[f"cfg2_qcif_21f_closed_loop_graph={graph}"] = {"ms_per_sequence": t, "us_per_frame": t / 21 * 1e3,
+                                                          "mpixel_s": 21 * 144 * 176 / t / 1e3}
+
+    # cfg3: intra RD sweep, 10 qScales over a resident shard of 1080p frames
+    F = 16 if quick else 64
+    frames = torch.rand((F, 1080, 1920, 3), generator=g, device="cuda", dtype=torch.float64) * 255
+    coders = [ivc.IntraBlockCoder(q) for q in QS]
+
+    def sweep():
+        for cd in coders:
+            rec = cd.inverse(cd.forward(frames))
+            ((rec - frames) ** 2).mean(dim=(1, 2, 3))          # per-frame MSE for PSNR (torch reduction; N3 is a "next" row)
+    t = timed(sweep, 3, warm=1)
+    res["cfg3_rd_sweep_1080p"] = {"frames": F, "qscales": len(QS), "ms_per_sweep": t,
+                                  "mpixel_s_incl_psnr": F * len(QS) * 1080 * 1920 / t / 1e3}
+    t = timed(lambda: [cd.inverse(cd.forward(frames)) for cd in coders], 3, warm=1)
+    res["cfg3_rd_sweep_1080p"]["mpixel_s_kernels_only"] = F * len(QS) * 1080 * 1920 / t / 1e3
+    del frames
+    torch.cuda.empty_cache()
+
+    # cfg4: 4K, +-16 full search, open loop on integer-valued frames (integer kernel) and forced exact kernel
+    T4 = 3 if quick else 9
+    s4 = luma_seq(T4, 2160, 3840, 4000, shift=12)
+    for mode in ("auto", "exact"):
+        pc = ivc.PFrameBlockCoder(1.0, 16, me_mode=mode)
+        t = timed(lambda: pc.estimate(s4[:-1], s4[1:]), 3 if mode == "auto" else 1, warm=1)
+        res[f"cfg4_4k_sr16_me_{mode}"] = {"frame_pairs": T4 - 1, "ms_per_frame": t / (T4 - 1),
+                                          "mpixel_s": (T4 - 1) * 2160 * 3840 / t / 1e3}
+    del s4
+
+    # cfg5: 1080p closed loop, per-frame latency
+    T5 = 30 if quick else 300
+    s5 = luma_seq(T5, 1080, 1920, 5000)
+    for graph in (False, True):
+        cl = ivc.ClosedLoopLumaCoder(1.0, 4, decode="luma", me_mode="exact", use_graph=graph)
+        t = timed(lambda: cl.code_sequence(s5), 3, warm=1)
+        res[f"cfg5_1080p_{T5}f_closed_loop_graph={graph}"] = {"ms_per_sequence": t, "us_per_frame": t / T5 * 1e3,
+                                                               "fps": T5 / t * 1e3, "mpixel_s": T5 * 1080 * 1920 / t / 1e3}
+    print(json.dumps(res, indent=1))
+
+
+if __name__ == "__main__":
+    main()

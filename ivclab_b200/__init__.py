@@ -19,8 +19,8 @@ from .install import inject, install
 from .quantization import PatchQuant
 from .signal import DiscreteCosineTransform
 from .utils import Patcher, ZigZag
-from .video import MotionCompensator
+from .video import ClosedLoopLumaCoder, MotionCompensator
 
 __version__ = "0.1.0"
 __all__ = ["DiscreteCosineTransform", "PatchQuant", "ZigZag", "Patcher", "MotionCompensator",
-           "IntraBlockCoder", "PFrameBlockCoder", "install", "inject"]
+           "IntraBlockCoder", "PFrameBlockCoder", "ClosedLoopLumaCoder", "install", "inject"]

@@ -49,6 +49,13 @@ template <typename T> struct Inf;
 template <> struct Inf<double> { static __device__ __forceinline__ double v() { return __longlong_as_double(0x7ff0000000000000LL); } };
 template <> struct Inf<float> { static __device__ __forceinline__ float v() { return __int_as_float(0x7f800000); } };
 
+template <int BYTES>
+__device__ __forceinline__ void cp_async_zfill(uint32_t dst, const void *src, bool valid) {
+    const uint32_t n = valid ? BYTES : 0;
+    if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+
 struct MeTile {
     int64_t frame;
     int by0, bx0, nby, nbx;
@@ -82,24 +89,31 @@ __global__ void __launch_bounds__(kMeThreads, 2) k_me_exact(const MeArgs a) {
     const T *cur = (const T *)a.cur + tl.frame * a.cur_fs;
     const int sr = a.sr, span = a.span;
 
-    // ---- stage window and current blocks (coalesced along x) ----
+    // ---- stage window and current blocks with cp.async (element-wise, zero-fill outside the frame):
+    //      every copy of the tile is in flight at once, so the HBM/L2 latency is paid once per CTA ----
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rows_used = 8 * tl.nby + 2 * sr;
-    for (int idx = threadIdx.x; idx < a.R * a.Wc; idx += blockDim.x) {
-        const int row = idx / a.Wc, col = idx - row * a.Wc;
-        const int64_t gy = (int64_t)8 * tl.by0 - sr + row, gx = (int64_t)8 * tl.bx0 - sr + col;
-        T v = (T)0;
-        if (row < rows_used && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) v = ref[gy * a.W + gx];
-        s_win[row * a.P + col] = v;
+    const uint32_t win_s = (uint32_t)__cvta_generic_to_shared(s_win), cur_s = (uint32_t)__cvta_generic_to_shared(s_cur);
+    for (int row = warp; row < a.R; row += kMeWarps) {
+        const int64_t gy = (int64_t)8 * tl.by0 - sr + row;
+        const bool row_ok = row < rows_used && gy >= 0 && gy < a.H;
+        const T *rp = ref + (row_ok ? gy : 0) * a.W;
+        for (int col = lane; col < a.Wc; col += 32) {
+            const int64_t gx = (int64_t)8 * tl.bx0 - sr + col;
+            const bool ok = row_ok && gx >= 0 && gx < a.W;
+            cp_async_zfill<sizeof(T)>(win_s + (uint32_t)(row * a.P + col) * (uint32_t)sizeof(T), ok ? rp + gx : ref, ok);
+        }
     }
     const int cw = 8 * tl.nbx;
-    for (int idx = threadIdx.x; idx < 8 * tl.nby * cw; idx += blockDim.x) {
-        const int row = idx / cw, col = idx - row * cw;
-        s_cur[((row >> 3) * a.tbx + (col >> 3)) * 64 + (row & 7) * 8 + (col & 7)] =
-            cur[((int64_t)8 * tl.by0 + row) * a.W + 8 * tl.bx0 + col];
+    for (int row = warp; row < 8 * tl.nby; row += kMeWarps) {
+        const T *cp = cur + ((int64_t)8 * tl.by0 + row) * a.W + 8 * tl.bx0;
+        for (int col = lane; col < cw; col += 32)
+            cp_async_zfill<sizeof(T)>(cur_s + (uint32_t)(((row >> 3) * a.tbx + (col >> 3)) * 64 + (row & 7) * 8 + (col & 7)) *
+                                                  (uint32_t)sizeof(T), cp + col, true);
     }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int center = sr * span + sr;
     const int nblk = tl.nby * tl.nbx;
     for (int blk = warp; blk < nblk; blk += kMeWarps) {
@@ -312,15 +326,19 @@ static int sm_count(int device) {
 }
 
 // choose the CTA tile (at most 64 blocks) and the shared-memory layout
-static size_t me_geometry(MeArgs &a, int64_t H, int64_t W, int sr, int elem, int pitch_quantum, int pitch_skew,
-                          size_t budget) {
+static size_t me_geometry(MeArgs &a, int64_t n_frames, int64_t H, int64_t W, int sr, int elem, int pitch_quantum,
+                          int pitch_skew, size_t budget, int64_t min_ctas) {
     a.Hp = (int)(H / 8); a.Wp = (int)(W / 8); a.sr = sr; a.span = 2 * sr + 1;
     a.ngrp = (a.span + kMeG - 1) / kMeG;
     a.ntpb = a.ngrp * a.span;
+    // largest tile that fits the shared-memory budget AND still yields enough CTAs to fill the GPU a few
+    // times over (single small frames -- QCIF, one 1080p frame of a closed loop -- get smaller tiles)
     static const int shapes[][2] = {{4, 16}, {2, 16}, {2, 8}, {1, 8}, {1, 4}, {1, 2}, {1, 1}};
     size_t smem = 0;
     for (auto &s : shapes) {
         a.tby = s[0]; a.tbx = s[1];
+        const int64_t ctas = n_frames * ((a.Hp + a.tby - 1) / a.tby) * (int64_t)((a.Wp + a.tbx - 1) / a.tbx);
+        if (ctas < min_ctas && !(s[0] == 1 && s[1] == 1) && s[0] * s[1] > 8) continue;
         a.R = 8 * (a.tby - 1) + a.ngrp * kMeG + 7;                 // >= 8*tby + 2*sr, covers the last dy-group
         a.Wc = 8 * a.tbx + 2 * sr;
         a.P = ((a.Wc + pitch_quantum - 1) / pitch_quantum) * pitch_quantum + pitch_skew;
@@ -339,7 +357,7 @@ cudaError_t launch_me_exact(int device, cudaStream_t st, const void *ref, const 
     MeArgs a;
     a.ref = ref; a.cur = cur; a.n = n; a.H = H; a.W = W; a.ref_fs = ref_fs; a.cur_fs = cur_fs; a.mv = mv;
     a.flag = flag; a.run_if = run_if; a.check = 0;
-    const size_t smem = me_geometry(a, H, W, sr, f32 ? 4 : 8, 32, 3, 100 * 1024);
+    const size_t smem = me_geometry(a, n, H, W, sr, f32 ? 4 : 8, 32, 3, 100 * 1024, 4 * 2 * (int64_t)sm_count(device));
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     const int64_t ctas = n * a.tiles_y * (int64_t)a.tiles_x;
     if (ctas == 0) return cudaSuccess;
@@ -363,7 +381,7 @@ cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const vo
     a.ref = ref; a.cur = cur; a.n = n; a.H = H; a.W = W; a.ref_fs = ref_fs; a.cur_fs = cur_fs; a.mv = mv;
     a.flag = flag; a.run_if = 0; a.check = check;
     // pitch in bytes: multiple of 4 plus 4 (the funnel shift reads one word past the last column)
-    const size_t smem = me_geometry(a, H, W, sr, 1, 4, 4, 64 * 1024);
+    const size_t smem = me_geometry(a, n, H, W, sr, 1, 4, 4, 64 * 1024, 4 * 3 * (int64_t)sm_count(device));
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     const int64_t ctas = n * a.tiles_y * (int64_t)a.tiles_x;
     if (ctas == 0) return cudaSuccess;

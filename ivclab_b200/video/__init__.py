@@ -1,3 +1,4 @@
 from .motion import MotionCompensator  # noqa: F401
+from .closed_loop import ClosedLoopLumaCoder  # noqa: F401
 
-__all__ = ["MotionCompensator"]
+__all__ = ["MotionCompensator", "ClosedLoopLumaCoder"]

@@ -1,0 +1,99 @@
+"""Closed-loop luma video coding on the B200: the per-frame loop of the ch4 exercise codecs
+(exercises/ch4/E4-1.py:212-306; ivclab/video/videocodec.py:41-75) at the symbol level.
+
+Per P-frame three kernels run back to back on one stream, with no host synchronisation and every
+intermediate resident in HBM:  K3 motion search (decoder reconstruction vs current frame) ->
+K1p (MC + residual + DCT + quantise + zig-zag) -> K2p (dequantise + IDCT + prediction add), the last
+of which produces the reference frame of the next iteration.  A whole sequence can be captured in
+one CUDA graph (``use_graph=True``) so the sequential dependency costs launches, not host time.
+The entropy coder (zero-run + Huffman) stays on the host and consumes the returned scan indices and
+motion vectors; it is outside the hot path."""
+from __future__ import annotations
+
+import torch
+
+from .. import _lib
+from .._runtime import code, to_device, to_host
+from ..quantization import PatchQuant
+
+__all__ = ["ClosedLoopLumaCoder"]
+
+
+class ClosedLoopLumaCoder:
+    """``decode='faithful'`` reproduces the reference's luma decode bit for bit (``symbols2image``
+    with a 2-D shape consumes the first Hp*Wp scan blocks of the flat (h w c) list, SURVEY.md
+    section 0 item 10); ``decode='luma'`` decodes channel 0 of every block."""
+
+    def __init__(self, quantization_scale=1.0, search_range=4, decode="faithful", me_mode="exact", use_graph=False):
+        if decode not in ("faithful", "luma"):
+            raise ValueError("decode must be 'faithful' or 'luma'")
+        self.quant = PatchQuant(quantization_scale)
+        self.search_range = int(search_range)
+        self.decode = decode
+        self.me_mode = {"auto": _lib.ME_AUTO, "exact": _lib.ME_EXACT, "int": _lib.ME_INT}[me_mode]
+        self.use_graph = use_graph
+        self._graphs = {}
+
+    # one sequence = T frames [T,H,W] float64 on the device
+    def _enqueue(self, frames, zz, mv, recon, ws, dtab, tcode):
+        L = _lib.lib
+        T, H, W = frames.shape
+        dev = frames.device.index
+        sp = torch.cuda.current_stream(frames.device).cuda_stream
+        czz = 1 if self.decode == "faithful" else 3
+        fsz, zsz, msz = H * W * 8, (H // 8) * (W // 8) * 192 * 4, (H // 8) * (W // 8) * 8
+        fp, zp, mp, rp = frames.data_ptr(), zz.data_ptr(), mv.data_ptr(), recon.data_ptr()
+        chk = _lib.check
+        # I-frame: intra forward with the 3-table broadcast, decode against a zero prediction
+        chk(L.ivc_intra_forward(dev, sp, fp, _lib.F64, 1, H, W, 1, H * W, dtab, tcode, zp), "ivc_intra_forward")
+        chk(L.ivc_pframe_inverse(dev, sp, zp, czz, self._zero.data_ptr(), None, None, _lib.F64, 1, H, W,
+                                 self.search_range, dtab, tcode, rp), "ivc_pframe_inverse")
+        for t in range(1, T):
+            cur, ref, out = fp + t * fsz, rp + (t - 1) * fsz, rp + t * fsz
+            z, m = zp + t * zsz, mp + (t - 1) * msz
+            chk(L.ivc_me_full_search(dev, sp, ref, cur, _lib.F64, 1, H, W, H * W, H * W, self.search_range,
+                                     self.me_mode, m, ws.data_ptr(), ws.numel()), "ivc_me_full_search")
+            chk(L.ivc_pframe_forward(dev, sp, cur, ref, m, _lib.F64, 1, H, W, self.search_range, dtab, tcode, None, z),
+                "ivc_pframe_forward")
+            chk(L.ivc_pframe_inverse(dev, sp, z, czz, None, ref, m, _lib.F64, 1, H, W, self.search_range, dtab, tcode, out),
+                "ivc_pframe_inverse")
+
+    def code_sequence(self, frames):
+        """frames [T,H,W] (numpy or CUDA tensor, float64) -> dict(zz [T,Hp,Wp,3,64] int32,
+        mv [T-1,Hp,Wp,1] int64, recon [T,H,W] float64 = the decoder's reconstructions)."""
+        f, was_np = to_device(frames)
+        f = f.to(torch.float64).contiguous()
+        if f.ndim != 3 or f.shape[1] % 8 or f.shape[2] % 8:
+            raise ValueError(f"expected [T,H,W] with H,W multiples of 8, got {tuple(f.shape)}")
+        T, H, W = f.shape
+        dev = f.device
+        _, dtab_t = self.quant._table_on(dev)
+        dtab, tcode = dtab_t.data_ptr(), code(dtab_t.dtype)
+        key = (T, H, W, str(dev), self.decode, self.me_mode, dtab)
+        st = self._graphs.get(key) if self.use_graph else None
+        if st is None:
+            st = {"frames": torch.empty_like(f) if self.use_graph else f,
+                  "zz": torch.empty((T, H // 8, W // 8, 3, 64), dtype=torch.int32, device=dev),
+                  "mv": torch.empty((max(T - 1, 0), H // 8, W // 8, 1), dtype=torch.int64, device=dev),
+                  "recon": torch.empty((T, H, W), dtype=torch.float64, device=dev),
+                  "ws": torch.empty(256, dtype=torch.uint8, device=dev)}
+            self._zero = torch.zeros((H, W), dtype=torch.float64, device=dev)
+            if self.use_graph:
+                st["frames"].copy_(f)
+                # warm up once outside capture (sets kernel attributes), then capture the whole sequence
+                self._enqueue(st["frames"], st["zz"], st["mv"], st["recon"], st["ws"], dtab, tcode)
+                torch.cuda.synchronize(dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue(st["frames"], st["zz"], st["mv"], st["recon"], st["ws"], dtab, tcode)
+                st["graph"] = g
+                self._graphs[key] = st
+        if self.use_graph:
+            st["frames"].copy_(f)
+            st["graph"].replay()
+        else:
+            self._enqueue(st["frames"], st["zz"], st["mv"], st["recon"], st["ws"], dtab, tcode)
+        out = {"zz": st["zz"], "mv": st["mv"], "recon": st["recon"]}
+        if self.use_graph:                                  # hand out copies: the graph owns its buffers
+            out = {k: v.clone() for k, v in out.items()}
+        return {k: to_host(v, was_np) for k, v in out.items()}

@@ -324,3 +324,34 @@ def test_unmodified_caller_chain_like_intracodec(g1, g6):
     ycbcr = patcher.unpatch(dct.inverse_transform(quant.dequantize(zigzag.unflatten(dec))))
     assert np.array_equal(O.ycbcr2rgb(ycbcr), g6["rec_rgb"])
     assert O.calc_psnr(g1["rgb"], O.ycbcr2rgb(ycbcr)) == float(g6["psnr"])
+
+
+# ---------------------------------------------------------------- closed loop (cfg2 / cfg5 shape)
+def test_closed_loop_golden_from_reference_codec_classes():
+    """5-frame closed loop recorded from the real IntraCodec + MotionCompensator (oracle/gen_golden_video.py):
+    no teacher forcing -- every frame depends on the previous reconstruction and still matches bit for bit."""
+    from conftest import load_golden
+    g8 = load_golden("g8_closed_loop.npz")
+    for use_graph in (False, True):
+        coder = ivc.ClosedLoopLumaCoder(float(g8["qscale"]), int(g8["sr"]), decode="faithful", use_graph=use_graph)
+        out = coder.code_sequence(g8["frames"])
+        assert np.array_equal(out["mv"], g8["mv"])
+        assert np.array_equal(out["zz"], g8["zz"])
+        assert np.array_equal(out["recon"], g8["recon"])
+        out2 = coder.code_sequence(g8["frames"])            # second call replays the captured graph
+        assert np.array_equal(out2["recon"], g8["recon"])
+    luma = ivc.ClosedLoopLumaCoder(float(g8["qscale"]), int(g8["sr"]), decode="luma").code_sequence(g8["frames"])
+    assert np.array_equal(luma["recon"], g8["recon_luma"]) and np.array_equal(luma["mv"], g8["mv_luma"])
+
+
+def test_closed_loop_qcif_21_frames_vs_oracle():
+    """cfg2: QCIF 176x144, 21 frames, +-4 search, closed loop, against the oracle's loop."""
+    from oracle import closed_loop as CL
+    frames = O.moving_sequence(2, 21, 144, 176)
+    want = CL.code_sequence(frames, 1.0, 4, "luma")
+    got = ivc.ClosedLoopLumaCoder(1.0, 4, decode="luma", me_mode="auto").code_sequence(frames)
+    assert np.array_equal(got["mv"], want["mv"])
+    assert np.array_equal(got["zz"], want["zz"])
+    assert np.array_equal(got["recon"], want["recon"])
+    psnr = 10 * np.log10(255.0 ** 2 / np.mean((got["recon"] - frames) ** 2))
+    assert psnr > 20.0
