@@ -176,20 +176,43 @@ __global__ void __launch_bounds__(kMeThreads, 2) k_me_exact(const MeArgs a) {
 // ================================================================================================
 // integer kernel (packed uint8, converted from the float frames while staging)
 // ================================================================================================
+// value -> uint8 plus "is an integer in [0,255]" without the (quarter-rate) FP64 conversion instructions:
+// v + 2^52 leaves the integer in the low mantissa word; (v + 2^52) - 2^52 == v proves v had no fraction.
+__device__ __forceinline__ unsigned to_u8_checked(double v, bool &bad) {
+    const double s = __dadd_rn(v, 4503599627370496.0);
+    const unsigned iv = (unsigned)__double2loint(s);
+    bad |= !((__double2hiint(s) == 0x43300000) & (iv <= 255u) & (__dsub_rn(s, 4503599627370496.0) == v));
+    return iv & 255u;
+}
+__device__ __forceinline__ unsigned to_u8_checked(float v, bool &bad) {
+    const int iv = (int)v;                                                    // saturating; NaN -> 0
+    bad |= !((float)iv == v && iv >= 0 && iv <= 255);
+    return (unsigned)iv & 255u;
+}
+
 template <typename T>
 __device__ __forceinline__ unsigned pack4(const T *p, int64_t base, int64_t gx, int64_t W, bool row_ok, bool &bad) {
     unsigned w = 0;
+    if (row_ok && gx >= 0 && gx + 3 < W) {                                    // interior word: four independent loads
+        T v[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (row_ok && gx + k >= 0 && gx + k < W) {
-            const T v = p[base + gx + k];
-            const int iv = (int)v;                                            // saturating; NaN -> 0
-            bad |= !((T)iv == v && iv >= 0 && iv <= 255);
-            w |= (unsigned)(iv & 255) << (8 * k);
-        }
+        for (int k = 0; k < 4; ++k) v[k] = p[base + gx + k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w |= to_u8_checked(v[k], bad) << (8 * k);
+    } else if (row_ok) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (gx + k >= 0 && gx + k < W) w |= to_u8_checked(p[base + gx + k], bad) << (8 * k);
     }
     return w;
 }
+
+// floor(x / d) for the small operands of the task decomposition: one multiply-high
+struct FastDiv {
+    unsigned magic, d;
+    __device__ __forceinline__ explicit FastDiv(unsigned dd) : magic(dd > 1 ? 0xFFFFFFFFu / dd + 1u : 0u), d(dd) {}
+    __device__ __forceinline__ int div(int x) const { return d > 1 ? (int)__umulhi((unsigned)x, magic) : x; }   // x*d < 2^32
+};
 
 template <typename T>
 __global__ void __launch_bounds__(kMeThreads, 3) k_me_int(const MeArgs a) {
@@ -233,10 +256,11 @@ __global__ void __launch_bounds__(kMeThreads, 3) k_me_int(const MeArgs a) {
     const bool small = span * span <= 512;                                    // ssd < 2^22, index < 2^9: key fits 32 bits
     unsigned *s_best32 = reinterpret_cast<unsigned *>(s_best);
     const int total = nblk * a.ntpb;
+    const FastDiv d_ntpb((unsigned)a.ntpb), d_span((unsigned)span), d_nbx((unsigned)tl.nbx);
     for (int task = threadIdx.x; task < total; task += blockDim.x) {
-        const int blk = task / a.ntpb, rem = task - blk * a.ntpb;
-        const int g = rem / span, dxi = rem - g * span;
-        const int brow = blk / tl.nbx, b = blk - brow * tl.nbx;
+        const int blk = d_ntpb.div(task), rem = task - blk * a.ntpb;
+        const int g = d_span.div(rem), dxi = rem - g * span;
+        const int brow = d_nbx.div(blk), b = blk - brow * tl.nbx;
         const int dy0 = g * kMeG - sr;
         const int gx = 8 * (tl.bx0 + b) + dxi - sr;
         if (gx < 0 || gx + 8 > a.W) continue;

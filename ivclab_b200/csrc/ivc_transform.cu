@@ -79,11 +79,19 @@ __device__ __forceinline__ double load_table_elem(const void *table, int table_d
 
 // decode a motion-vector index (motion.py:83-84) and test the source window (motion.py:90-92)
 __device__ __forceinline__ void mv_decode(int64_t idx, int sr, int &dy, int &dx) {
-    const int64_t span = 2 * (int64_t)sr + 1;
-    // python floor division / modulo semantics for negative indices
-    int64_t qd = idx / span, rm = idx % span;
-    if (rm < 0) { rm += span; qd -= 1; }
-    dy = (int)(qd - sr);
+    const unsigned span = 2u * (unsigned)sr + 1u;
+    if (__builtin_expect((unsigned long long)idx < 0x7fffffffull, 1)) {     // every vector ME produces: 32-bit divide
+        const unsigned q = (unsigned)idx / span;
+        dy = (int)q - sr;
+        dx = (int)((unsigned)idx - q * span) - sr;
+        return;
+    }
+    // python floor division / modulo semantics for arbitrary (negative, huge) indices
+    const int64_t sp = (int64_t)span;
+    int64_t qd = idx / sp, rm = idx % sp;
+    if (rm < 0) { rm += sp; qd -= 1; }
+    qd -= sr;
+    dy = qd > 0x3fffffff ? 0x3fffffff : (qd < -0x3fffffff ? -0x3fffffff : (int)qd);   // clamped: window is out of frame anyway
     dx = (int)(rm - sr);
 }
 
@@ -636,11 +644,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_c3_tma(const F
         }
         __syncwarp();
         QuantGuard qg;
+        {
+            double rtv[3][8];                           // loaded as one batch: the staging stores below would otherwise
+#pragma unroll                                          // serialise each (possibly aliasing) shared-memory load
+            for (int m = 0; m < 3; ++m)
 #pragma unroll
-        for (int m = 0; m < 3; ++m)
+                for (int v = 0; v < 8; ++v) rtv[m][v] = rt_l[m * 64 + v * 8];
+            int qv[3][8];
 #pragma unroll
-            for (int v = 0; v < 8; ++v)
-                *reinterpret_cast<int *>(zz_wr[v] + m * 256) = qg.q(x[m][v], rt_l[m * 64 + v * 8]);
+            for (int m = 0; m < 3; ++m)
+#pragma unroll
+                for (int v = 0; v < 8; ++v) qv[m][v] = qg.q(x[m][v], rtv[m][v]);
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+#pragma unroll
+                for (int v = 0; v < 8; ++v) *reinterpret_cast<int *>(zz_wr[v] + m * 256) = qv[m][v];
+        }
         if (__builtin_expect(qg.risky(), 0)) {          // rare: redo this lane's 24 samples with the IEEE division
 #pragma unroll
             for (int m = 0; m < 3; ++m)
@@ -810,18 +829,23 @@ struct PredGather {
                                           const double *ref_frame, int by, int b0) const {
         int dy = 0, dx = 0;
         if (lane < nb) mv_decode(mvidx, sr, dy, dx);
+        const int64_t pitch = W * 8;                                          // bytes per frame row
+        const int Hi = (int)H, Wi = (int)W;
 #pragma unroll
         for (int c3 = 0; c3 < 3; ++c3) {
             const int col = 32 * c3 + lane, blk = col >> 3;
             const int bdy = __shfl_sync(0xffffffffu, dy, blk), bdx = __shfl_sync(0xffffffffu, dx, blk);
             if (blk < nb) {
-                const int64_t sy = (int64_t)by * 8 + bdy, sx = (int64_t)(b0 + blk) * 8 + bdx;
-                const bool ok = sy >= 0 && sy + 8 <= H && sx >= 0 && sx + 8 <= W;
-                const double *src = ok ? ref_frame + sy * W + sx + (col & 7) : ref_frame;
-                const uint32_t nbytes = ok ? 8u : 0u;
+                const int sy = by * 8 + bdy, sx = (b0 + blk) * 8 + bdx;
+                const bool ok = sy >= 0 && sy <= Hi - 8 && sx >= 0 && sx <= Wi - 8;
+                const char *src = reinterpret_cast<const char *>(ref_frame) + (ok ? (int64_t)sy * pitch + (int64_t)(sx + (col & 7)) * 8 : 0);
+                const int64_t step = ok ? pitch : 0;
+                const uint32_t nbytes = ok ? 8u : 0u, dst = pred_s + col * 8;
 #pragma unroll
-                for (int row = 0; row < 8; ++row)
-                    cp_async8_zfill(pred_s + (row * kRowPitch + col) * 8, src + (ok ? row * W : 0), nbytes);
+                for (int row = 0; row < 8; ++row) {
+                    cp_async8_zfill(dst + row * (kRowPitch * 8), src, nbytes);
+                    src += step;
+                }
             }
         }
         cp_async_mbar_arrive(bar);
@@ -947,11 +971,22 @@ __global__ void __launch_bounds__(kPfWarps * 32, 1) k_pframe_forward_tma(const F
             const int reg = (m & 1) * 3200;
             if (m == 2) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); __syncwarp(); }
             QuantGuard qg;
+            {
+                double rtv[3][8];
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch)
+                for (int ch = 0; ch < 3; ++ch)
 #pragma unroll
-                for (int v = 0; v < 8; ++v)
-                    *reinterpret_cast<int *>(zz_wr[v] + reg + ch * 256) = qg.q(x[m][v], rt_l[ch * 64 + v * 8]);
+                    for (int v = 0; v < 8; ++v) rtv[ch][v] = rt_l[ch * 64 + v * 8];
+                int qv[3][8];
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) qv[ch][v] = qg.q(x[m][v], rtv[ch][v]);
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) *reinterpret_cast<int *>(zz_wr[v] + reg + ch * 256) = qv[ch][v];
+            }
             if (__builtin_expect(qg.risky(), 0)) {
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch)
