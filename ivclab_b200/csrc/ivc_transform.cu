@@ -1008,15 +1008,21 @@ __global__ void __launch_bounds__(kPfWarps * 32, 1) k_pframe_forward_tma(const F
     if (lane == 0) bulk_wait_all0();
 }
 
-__global__ void __launch_bounds__(kPfWarps * 32, 1) k_pframe_inverse_tma(const InvArgs a) {
+// K2p: per warp IN (scan blocks, 3200 B) + PRED x2 (double-buffered so that the prediction can be read
+// at the very end of a tile while the next tile's gather is already in flight) + WORK; 10 warps per SM.
+constexpr int kPiWarps = 10;
+constexpr int kPiIn = 4 * kStageU * 4;                         // 3200
+constexpr int kPiBuf = kPiIn + 2 * kInBytes + kWorkBytes;      // 22144
+static_assert(kPiBuf % 128 == 0, "alignment");
+
+__global__ void __launch_bounds__(kPiWarps * 32, 1) k_pframe_inverse_tma(const InvArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_tT = reinterpret_cast<double *>(smem_raw);                        // [64] luminance table, transposed
     unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem_raw + 3072);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // per-warp: IN = scan blocks (uses 3200 of the 6272 bytes), PRED, WORK
-    unsigned char *in_b = smem_raw + 3200 + warp * kPfBuf;
-    unsigned char *pred_b = in_b + kInBytes;
-    unsigned char *work_b = pred_b + kInBytes;
+    unsigned char *in_b = smem_raw + 3200 + warp * kPiBuf;
+    unsigned char *pred_b = in_b + kPiIn;                                       // two buffers of kInBytes
+    unsigned char *work_b = pred_b + 2 * kInBytes;
     const uint32_t bar = smem_u32(s_bar + warp), in_s = smem_u32(in_b), pred_s = smem_u32(pred_b), work_s = smem_u32(work_b);
 
     for (int i = threadIdx.x; i < 64; i += blockDim.x) s_tT[(i & 7) * 8 + (i >> 3)] = load_table_elem(a.table, a.table_dtype, i);
@@ -1037,13 +1043,13 @@ __global__ void __launch_bounds__(kPfWarps * 32, 1) k_pframe_inverse_tma(const I
         t_rd[h] = work_b + u * (kTU2 * 8) + r * 64 + ((h ^ (r >> 1)) << 4);
     }
     o_wr = work_b + (24 * u + r) * 8;                                          // + i*784 + m*64
-    p_rd = pred_b + (24 * u + r) * 8;
+    p_rd = pred_b + (24 * u + r) * 8;                                          // + buffer*kInBytes
     const double *tq_l = s_tT + r;                                             // tq_l[j*8] = lum[r][j]
 
     const TileGeom &g = a.g;
     const int64_t row_elems = g.W, frame_elems = g.H * g.W;
-    const int64_t gw = (int64_t)blockIdx.x * kPfWarps + warp;
-    const int64_t nw = (int64_t)gridDim.x * kPfWarps;
+    const int64_t gw = (int64_t)blockIdx.x * kPiWarps + warp;
+    const int64_t nw = (int64_t)gridDim.x * kPiWarps;
     if (gw >= g.total_tiles) return;
     const int64_t my_tiles = (g.total_tiles - gw + nw - 1) / nw;
     TileIter cur, nxt, nx2;
@@ -1055,7 +1061,7 @@ __global__ void __launch_bounds__(kPfWarps * 32, 1) k_pframe_inverse_tma(const I
         const int b0 = ti.tx * 12;
         return (gather && lane < min(12, g.Wp - b0)) ? a.mv[(ti.frame * g.Hp + ti.by) * (int64_t)g.Wp + b0 + lane] : 0;
     };
-    auto issue = [&](const TileIter &ti, int64_t mvidx) {
+    auto issue = [&](const TileIter &ti, int64_t mvidx, uint32_t pbuf_s) {
         const int b0 = ti.tx * 12, nb = min(12, g.Wp - b0);
         if (lane == 0) {
             const int32_t *zsrc = a.zz + ((ti.frame * g.Hp + ti.by) * (int64_t)g.Wp + b0) * a.Czz * 64;
@@ -1069,14 +1075,14 @@ __global__ void __launch_bounds__(kPfWarps * 32, 1) k_pframe_inverse_tma(const I
             if (!gather) {
                 const double *psrc = a.pred + ti.frame * frame_elems + (int64_t)ti.by * 8 * row_elems + (int64_t)b0 * 8;
 #pragma unroll
-                for (int row = 0; row < 8; ++row) bulk_g2s(pred_s + row * (kRowPitch * 8), psrc + row * row_elems, row_bytes, bar);
+                for (int row = 0; row < 8; ++row) bulk_g2s(pbuf_s + row * (kRowPitch * 8), psrc + row * row_elems, row_bytes, bar);
             }
         }
-        if (gather) pg.issue(pred_s, bar, lane, mvidx, nb, a.ref + ti.frame * frame_elems, ti.by, b0);
+        if (gather) pg.issue(pbuf_s, bar, lane, mvidx, nb, a.ref + ti.frame * frame_elems, ti.by, b0);
     };
 
     int64_t mv_nxt = load_mv(cur);
-    issue(cur, mv_nxt);
+    issue(cur, mv_nxt, pred_s);
     nxt.advance(g);
     mv_nxt = (my_tiles > 1) ? load_mv(nxt) : 0;
     nx2 = nxt;
@@ -1084,21 +1090,17 @@ __global__ void __launch_bounds__(kPfWarps * 32, 1) k_pframe_inverse_tma(const I
     for (int64_t it = 0; it < my_tiles; ++it, parity ^= 1u) {
         nx2.advance(g);
         const int b0 = cur.tx * 12, nb = min(12, g.Wp - b0);
+        const int pb = (int)(it & 1);
         mbar_wait(bar, parity);
         int q[3][8];
-        double pr[3][8];                                 // prediction of column r of the three blocks
 #pragma unroll
         for (int m = 0; m < 3; ++m)
 #pragma unroll
             for (int j = 0; j < 8; ++j) q[m][j] = *reinterpret_cast<const int *>(q_rd[j] + m * 256);
-#pragma unroll
-        for (int m = 0; m < 3; ++m)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pr[m][i] = *reinterpret_cast<const double *>(p_rd + i * (kRowPitch * 8) + m * 64);
         __syncwarp();
         const int64_t mv_cur_next = mv_nxt;
         if (it + 1 < my_tiles) {
-            issue(nxt, mv_cur_next);
+            issue(nxt, mv_cur_next, pred_s + (uint32_t)((pb ^ 1) * kInBytes));
             mv_nxt = (it + 2 < my_tiles) ? load_mv(nx2) : 0;
         }
         double x[3][8];
@@ -1137,11 +1139,19 @@ __global__ void __launch_bounds__(kPfWarps * 32, 1) k_pframe_inverse_tma(const I
             dct3_8(x[m]);
         }
         __syncwarp();
+        {
+            double pr[3][8];                             // prediction of column r of the three blocks (loaded as a batch)
+            const unsigned char *pp = p_rd + pb * kInBytes;
 #pragma unroll
-        for (int m = 0; m < 3; ++m)
+            for (int m = 0; m < 3; ++m)
 #pragma unroll
-            for (int i = 0; i < 8; ++i)                  // recon = prediction + recon_residual (videocodec.py:74)
-                *reinterpret_cast<double *>(o_wr + i * (kRowPitch * 8) + m * 64) = __dadd_rn(pr[m][i], x[m][i]);
+                for (int i = 0; i < 8; ++i) pr[m][i] = *reinterpret_cast<const double *>(pp + i * (kRowPitch * 8) + m * 64);
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+#pragma unroll
+                for (int i = 0; i < 8; ++i)              // recon = prediction + recon_residual (videocodec.py:74)
+                    *reinterpret_cast<double *>(o_wr + i * (kRowPitch * 8) + m * 64) = __dadd_rn(pr[m][i], x[m][i]);
+        }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
@@ -1367,9 +1377,9 @@ cudaError_t launch_inverse(int device, cudaStream_t st, const int32_t *zz, int64
         if ((e = set_smem(k_inverse<1>, smem)) != cudaSuccess) return e;
         k_inverse<1><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
     } else if (!use_v1()) {
-        const size_t smem2 = 3200 + (size_t)kPfWarps * kPfBuf;
+        const size_t smem2 = 3200 + (size_t)kPiWarps * kPiBuf;
         if ((e = set_smem(k_pframe_inverse_tma, smem2)) != cudaSuccess) return e;
-        k_pframe_inverse_tma<<<grid_for(a.g.total_tiles, kPfWarps, device, 1), kPfWarps * 32, smem2, st>>>(a);
+        k_pframe_inverse_tma<<<grid_for(a.g.total_tiles, kPiWarps, device, 1), kPiWarps * 32, smem2, st>>>(a);
     } else {
         if ((e = set_smem(k_inverse<2>, smem)) != cudaSuccess) return e;
         k_inverse<2><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
