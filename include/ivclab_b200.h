@@ -152,6 +152,26 @@ int ivc_pframe_inverse(int device, void *stream,
                        const void *table, int table_dtype,
                        void *recon_out);
 
+/* ---- N3 (next row): calc_mse / calc_psnr (ivclab/utils/metrics.py:3-40) ------------------------
+ * sse_out[u] = sum_i (double(a[u][i / a_broadcast]) - double(b[u][i]))^2 over unit_elems elements of b,
+ * for n_units units (frames).  a_broadcast = 3 pairs a gray `a` with an RGB `b` (metrics.py:16-19),
+ * else 1.  Deterministic two-stage reduction; mse = sse / unit_elems, psnr = 20*log10(max/sqrt(mse))
+ * are left to the caller.  workspace: ivc_sse_workspace_bytes() bytes. */
+int64_t ivc_sse_workspace_bytes(int64_t n_units, int64_t unit_elems);
+int ivc_sum_squared_error(int device, void *stream,
+                          const void *a, int a_dtype, const void *b, int b_dtype,
+                          int64_t n_units, int64_t unit_elems, int a_broadcast,
+                          void *workspace, int64_t workspace_bytes, double *sse_out);
+
+/* ---- N2 (next row): ZeroRunCoder.encode (ivclab/entropy/zerorun.py:10-43) ---------------------
+ * zz: nblocks contiguous scan blocks of 64 int32.  Two passes around an exclusive scan that the
+ * caller performs: counts_out[b] = number of symbols block b emits (non-zeros + 2 per zero run that
+ * precedes a non-zero + 1 EOB); then symbols are written at offsets[b] (exclusive prefix sum of the
+ * counts, int64).  The symbol stream equals the reference's list bit for bit. */
+int ivc_zerorun_count(int device, void *stream, const int32_t *zz, int64_t nblocks, int32_t *counts_out);
+int ivc_zerorun_write(int device, void *stream, const int32_t *zz, int64_t nblocks, int32_t end_of_block,
+                      const int64_t *offsets, int32_t *symbols_out);
+
 #ifdef __cplusplus
 }
 #endif

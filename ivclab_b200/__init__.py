@@ -15,12 +15,14 @@ extension has not been built, and calling it fails if no CUDA device is visible.
 """
 from . import _lib  # noqa: F401  (loads libivcb200.so or raises)
 from .codec import IntraBlockCoder, PFrameBlockCoder
+from .entropy import ZeroRunCoder
 from .install import inject, install
 from .quantization import PatchQuant
 from .signal import DiscreteCosineTransform
-from .utils import Patcher, ZigZag
+from .utils import Patcher, ZigZag, calc_mse, calc_psnr, frame_sse
 from .video import ClosedLoopLumaCoder, MotionCompensator
 
 __version__ = "0.1.0"
 __all__ = ["DiscreteCosineTransform", "PatchQuant", "ZigZag", "Patcher", "MotionCompensator",
-           "IntraBlockCoder", "PFrameBlockCoder", "ClosedLoopLumaCoder", "install", "inject"]
+           "IntraBlockCoder", "PFrameBlockCoder", "ClosedLoopLumaCoder", "ZeroRunCoder", "calc_mse", "calc_psnr",
+           "frame_sse", "install", "inject"]

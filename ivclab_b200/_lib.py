@@ -38,6 +38,10 @@ SIGNATURES = {
     "ivc_mc_reconstruct": (_i, [_i, _p, _p, _i, _i64, _i64, _i64, _i64, _p, _i, _p]),
     "ivc_pframe_forward": (_i, [_i, _p, _p, _p, _p, _i, _i64, _i64, _i64, _i, _p, _i, _p, _p]),
     "ivc_pframe_inverse": (_i, [_i, _p, _p, _i64, _p, _p, _p, _i, _i64, _i64, _i64, _i, _p, _i, _p]),
+    "ivc_sse_workspace_bytes": (_i64, [_i64, _i64]),
+    "ivc_sum_squared_error": (_i, [_i, _p, _p, _i, _p, _i, _i64, _i64, _i, _p, _i64, _p]),
+    "ivc_zerorun_count": (_i, [_i, _p, _p, _i64, _p]),
+    "ivc_zerorun_write": (_i, [_i, _p, _p, _i64, C.c_int32, _p, _p]),
 }
 
 

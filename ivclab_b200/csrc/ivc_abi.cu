@@ -229,4 +229,47 @@ int ivc_pframe_inverse(int device, void *stream, const int32_t *zz, int64_t Czz,
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
 
+int64_t ivc_sse_workspace_bytes(int64_t n_units, int64_t unit_elems) {
+    if (n_units < 0 || unit_elems < 0) return -1;
+    return (n_units * (int64_t)ivc::sse_chunks(n_units, unit_elems, 148) + 1) * (int64_t)sizeof(double);
+}
+
+int ivc_sum_squared_error(int device, void *stream, const void *a, int a_dtype, const void *b, int b_dtype,
+                          int64_t n_units, int64_t unit_elems, int a_broadcast, void *workspace, int64_t workspace_bytes,
+                          double *sse_out) {
+    if (n_units < 0 || unit_elems < 0 || (a_broadcast != 1 && a_broadcast != 3)) return IVC_ERR_ARG;
+    if (elem_size(a_dtype) == 0 || elem_size(b_dtype) == 0) return IVC_ERR_DTYPE;
+    if (a_broadcast == 3 && unit_elems % 3) return IVC_ERR_SHAPE;
+    if (n_units == 0) return IVC_OK;
+    if (!sse_out) return IVC_ERR_ARG;
+    if (unit_elems > 0 && (!a || !b)) return IVC_ERR_ARG;
+    if (!workspace || workspace_bytes < ivc_sse_workspace_bytes(n_units, unit_elems)) return IVC_ERR_WORKSPACE;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_sse(device, (cudaStream_t)stream, a, a_dtype, b, b_dtype, n_units, unit_elems, a_broadcast,
+                                    (double *)workspace, sse_out);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
+int ivc_zerorun_count(int device, void *stream, const int32_t *zz, int64_t nblocks, int32_t *counts_out) {
+    if (nblocks < 0) return IVC_ERR_ARG;
+    if (nblocks == 0) return IVC_OK;
+    if (!zz || !counts_out || !aligned16(zz)) return IVC_ERR_ARG;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_zr_count(device, (cudaStream_t)stream, zz, nblocks, counts_out);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
+int ivc_zerorun_write(int device, void *stream, const int32_t *zz, int64_t nblocks, int32_t end_of_block,
+                      const int64_t *offsets, int32_t *symbols_out) {
+    if (nblocks < 0) return IVC_ERR_ARG;
+    if (nblocks == 0) return IVC_OK;
+    if (!zz || !offsets || !symbols_out || !aligned16(zz)) return IVC_ERR_ARG;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_zr_write(device, (cudaStream_t)stream, zz, nblocks, end_of_block, offsets, symbols_out);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
 }  // extern "C"

@@ -30,4 +30,14 @@ cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const vo
 cudaError_t launch_mc(int device, cudaStream_t st, const void *ref, int elem_size, int64_t n, int64_t H, int64_t W,
                       int64_t C, const int64_t *mv, int sr, void *out);
 
+// implemented in ivc_metrics.cu
+int sse_chunks(int64_t n_units, int64_t unit_elems, int sms);
+cudaError_t launch_sse(int device, cudaStream_t st, const void *a, int a_dtype, const void *b, int b_dtype,
+                       int64_t n_units, int64_t unit_elems, int a_div, double *partial, double *out);
+
+// implemented in ivc_zerorun.cu
+cudaError_t launch_zr_count(int device, cudaStream_t st, const int32_t *zz, int64_t nblocks, int32_t *counts);
+cudaError_t launch_zr_write(int device, cudaStream_t st, const int32_t *zz, int64_t nblocks, int32_t eob,
+                            const int64_t *offsets, int32_t *out);
+
 }  // namespace ivc

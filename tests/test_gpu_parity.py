@@ -355,3 +355,39 @@ def test_closed_loop_qcif_21_frames_vs_oracle():
     assert np.array_equal(got["recon"], want["recon"])
     psnr = 10 * np.log10(255.0 ** 2 / np.mean((got["recon"] - frames) ** 2))
     assert psnr > 20.0
+
+
+# ---------------------------------------------------------------- "next" rows N2 / N3
+def test_zerorun_encode_matches_reference_stream(g1, g6):
+    """N2: the GPU zero-run encoder reproduces the reference's symbol list (zerorun.py:10-43)."""
+    zr = ivc.ZeroRunCoder()
+    sym = zr.encode(g1["zz1"])
+    assert sym.dtype == np.int32 and np.array_equal(sym, g6["sym"])
+    assert np.array_equal(zr.decode(sym, g1["zz1"].shape[:3]), g1["zz1"])
+    assert np.array_equal(zr.decode(sym, (6, 8, 1)), g6["dec_trunc"])            # the 2-D-shape truncation rule
+    rng = np.random.default_rng(4)
+    for density in (0.0, 0.02, 0.3, 1.0):
+        zz = (rng.integers(-9, 10, size=(7, 9, 3, 64)) * (rng.random((7, 9, 3, 64)) < density)).astype(np.int32)
+        zz[0, 0, 0, :] = 0
+        zz[0, 0, 1, 63] = 5                                                      # run of 63 zeros then a value
+        zz[0, 0, 2, :] = np.arange(1, 65)                                        # no zeros at all
+        assert np.array_equal(zr.encode(zz), O.zerorun_encode(zz))
+    big = ivc.IntraBlockCoder(0.4).forward(O.rgb2ycbcr(O.smooth_noise_rgb(5, 256, 384)))
+    assert np.array_equal(zr.encode(big), O.zerorun_encode(big))
+
+
+def test_metrics_match_reference(g1, g6):
+    """N3: calc_mse / calc_psnr (metrics.py:3-40); reduction order differs from numpy's pairwise mean,
+    so the comparison is relative 1e-12 (PSNR: far below the 0.01 dB bar)."""
+    rgb, rec = g1["rgb"], g6["rec_rgb"]
+    assert abs(ivc.calc_mse(rgb, rec) / float(g6["mse"]) - 1.0) < 1e-12
+    assert abs(ivc.calc_psnr(rgb, rec) - float(g6["psnr"])) < 1e-9
+    gray = rgb[..., 0]
+    assert abs(ivc.calc_mse(gray, rec) / O.calc_mse(gray, rec) - 1.0) < 1e-12     # gray vs RGB stacking
+    assert abs(ivc.calc_mse(rec, gray) / O.calc_mse(rec, gray) - 1.0) < 1e-12
+    a = np.random.default_rng(2).uniform(0, 255, size=(5, 40, 56, 3))
+    b = a + np.random.default_rng(3).normal(0, 2, size=a.shape)
+    sse = ivc.frame_sse(a, b).cpu().numpy()
+    want = ((a - b) ** 2).reshape(5, -1).sum(axis=1)
+    assert np.allclose(sse, want, rtol=1e-12, atol=0)
+    assert np.array_equal(sse, ivc.frame_sse(a, b).cpu().numpy())                 # deterministic
