@@ -17,8 +17,8 @@ HERE = os.path.join(ROOT, "ivclab_b200")
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 OUT = os.path.join(OUT_DIR, "libivcb200.so")
-SOURCES = ["ivc_abi.cu", "ivc_transform.cu", "ivc_motion.cu", "ivc_metrics.cu", "ivc_zerorun.cu"]
-HEADERS = ["ivc_dct.cuh", "ivc_common.cuh", os.path.join("..", "..", "include", "ivclab_b200.h")]
+SOURCES = ["ivc_abi.cu", "ivc_transform.cu", "ivc_motion.cu", "ivc_metrics.cu", "ivc_zerorun.cu", "ivc_color.cu"]
+HEADERS = ["ivc_dct.cuh", "ivc_common.cuh", "ivc_color.cuh", os.path.join("..", "..", "include", "ivclab_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

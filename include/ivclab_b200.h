@@ -172,6 +172,19 @@ int ivc_zerorun_count(int device, void *stream, const int32_t *zz, int64_t nbloc
 int ivc_zerorun_write(int device, void *stream, const int32_t *zz, int64_t nblocks, int32_t end_of_block,
                       const int64_t *offsets, int32_t *symbols_out);
 
+/* ---- N1 (next row): colour transforms (ivclab/signal/color.py:15-63) --------------------------
+ * rgb: npixels x 3 (U8/I32/F32/F64) -> ycbcr float64, bit-identical to numpy's `image @ M.T + offset`
+ * (one FMA chain per output, as BLAS evaluates it).  ycbcr2rgb: float64 in/out, clipped to [0,255]. */
+int ivc_rgb2ycbcr(int device, void *stream, const void *rgb, int dtype, int64_t npixels, void *ycbcr_out);
+int ivc_ycbcr2rgb(int device, void *stream, const void *ycbcr, int64_t npixels, void *rgb_out);
+
+/* K1 with rgb2ycbcr fused in front: uint8 RGB HWC images (W % 16 == 0, frames frame_stride_bytes apart)
+ * -> [n_frames, H/8, W/8, 3, 64] int32, identical to ivc_intra_forward(rgb2ycbcr(rgb)); reads 3 bytes per
+ * pixel instead of 24. */
+int ivc_intra_forward_rgb8(int device, void *stream,
+                           const void *rgb, int64_t n_frames, int64_t H, int64_t W, int64_t frame_stride_bytes,
+                           const void *table, int table_dtype, int32_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,28 @@ class IntraBlockCoder:
         _lib.check(st, "ivc_intra_forward")
         return to_host(out if batched else out[0], was_np)
 
+    def forward_rgb(self, rgb):
+        """uint8 RGB ``[H, W, 3]`` / ``[N, H, W, 3]`` -> the scan indices of ``forward(rgb2ycbcr(rgb))``
+        (intracodec.py:45 + :66-75) in one kernel that reads 3 bytes per pixel.  Frames whose width is
+        not a multiple of 16 take the two-kernel route (colour kernel, then ``forward``)."""
+        t, was_np = to_device(rgb)
+        batched = t.ndim == 4
+        if t.ndim not in (3, 4) or t.shape[-1] != 3:
+            raise ValueError(f"expected [H,W,3] or [N,H,W,3], got shape {tuple(t.shape)}")
+        v = t if batched else t[None]
+        N, H, W, _ = v.shape
+        if v.dtype != torch.uint8 or W % 16:
+            from .signal.color import rgb2ycbcr
+            out = self.forward(rgb2ycbcr(v))
+            return to_host(out if batched else out[0], was_np)
+        v = aligned16(v)
+        _, dtab = self.quant._table_on(v.device)
+        out = torch.empty((N, H // 8, W // 8, 3, 64), dtype=torch.int32, device=v.device)
+        st = _lib.lib.ivc_intra_forward_rgb8(dev_index(v), stream_ptr(v.device), v.data_ptr(), N, H, W, H * W * 3,
+                                             dtab.data_ptr(), code(dtab.dtype), out.data_ptr())
+        _lib.check(st, "ivc_intra_forward_rgb8")
+        return to_host(out if batched else out[0], was_np)
+
     def inverse(self, zz):
         """int32 scan indices ``[(N,) Hp, Wp, C, 64]`` (C in {1,3}) -> float64 ``[(N,) 8Hp, 8Wp, 3]``."""
         t, was_np = to_device(zz)

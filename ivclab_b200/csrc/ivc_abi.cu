@@ -272,4 +272,40 @@ int ivc_zerorun_write(int device, void *stream, const int32_t *zz, int64_t nbloc
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
 
+int ivc_rgb2ycbcr(int device, void *stream, const void *rgb, int dtype, int64_t npixels, void *ycbcr_out) {
+    if (npixels < 0) return IVC_ERR_ARG;
+    if (dtype != IVC_U8 && dtype != IVC_I32 && dtype != IVC_F32 && dtype != IVC_F64) return IVC_ERR_DTYPE;
+    if (npixels == 0) return IVC_OK;
+    if (!rgb || !ycbcr_out) return IVC_ERR_ARG;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_color(device, (cudaStream_t)stream, false, rgb, dtype, npixels, (double *)ycbcr_out);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
+int ivc_ycbcr2rgb(int device, void *stream, const void *ycbcr, int64_t npixels, void *rgb_out) {
+    if (npixels < 0) return IVC_ERR_ARG;
+    if (npixels == 0) return IVC_OK;
+    if (!ycbcr || !rgb_out) return IVC_ERR_ARG;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_color(device, (cudaStream_t)stream, true, ycbcr, IVC_F64, npixels, (double *)rgb_out);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
+int ivc_intra_forward_rgb8(int device, void *stream, const void *rgb, int64_t n_frames, int64_t H, int64_t W,
+                           int64_t frame_stride_bytes, const void *table, int table_dtype, int32_t *out) {
+    if (n_frames < 0 || H < 0 || W < 0 || frame_stride_bytes < 0) return IVC_ERR_ARG;
+    if (!is_float(table_dtype)) return IVC_ERR_DTYPE;
+    if ((H & 7) || (W & 15)) return IVC_ERR_SHAPE;          // 16-byte rows for the bulk copies: W % 16 == 0
+    if (n_frames * H * W == 0) return IVC_OK;
+    if (!rgb || !table || !out) return IVC_ERR_ARG;
+    if (!aligned16(rgb) || !aligned16(out) || (frame_stride_bytes & 15)) return IVC_ERR_ARG;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_forward_rgb8(device, (cudaStream_t)stream, rgb, n_frames, H, W, frame_stride_bytes, table,
+                                             table_dtype, out);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
 }  // extern "C"

@@ -40,4 +40,9 @@ cudaError_t launch_zr_count(int device, cudaStream_t st, const int32_t *zz, int6
 cudaError_t launch_zr_write(int device, cudaStream_t st, const int32_t *zz, int64_t nblocks, int32_t eob,
                             const int64_t *offsets, int32_t *out);
 
+// colour (ivc_color.cu) and the RGB front end of K1 (ivc_transform.cu)
+cudaError_t launch_color(int device, cudaStream_t st, bool to_rgb, const void *in, int in_dtype, int64_t npix, double *out);
+cudaError_t launch_forward_rgb8(int device, cudaStream_t st, const void *rgb, int64_t n, int64_t H, int64_t W,
+                                int64_t frame_stride_bytes, const void *table, int table_dtype, int32_t *out);
+
 }  // namespace ivc

@@ -18,6 +18,7 @@
 // once); arithmetic is FP64 (14 rounded operations per sample for the 2-D transform).
 #include <cstdlib>
 #include "ivc_dct.cuh"
+#include "ivc_color.cuh"
 #include "ivc_common.cuh"
 
 namespace ivc {
@@ -618,6 +619,149 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_c3_tma(const F
             for (int m = 0; m < 3; ++m)
 #pragma unroll
                 for (int p = 0; p < 8; ++p) x[m][p] = raw[3 * p + m];
+        }
+        __syncwarp();                                   // IN is consumed: prefetch the next tile into it
+        if (lane == 0) {
+            if (it + 1 < my_tiles) { fence_proxy_async(); issue(nxt); }
+            bulk_wait_read0();                          // previous tile's store has drained WORK
+        }
+#pragma unroll
+        for (int m = 0; m < 3; ++m) dct2_8(x[m]);
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) *reinterpret_cast<double *>(t_wr[j >> 1] + (m * 8 + j) * 64) = x[m][j];
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double2 v = *reinterpret_cast<const double2 *>(t_rd[k] + m * 512);
+                x[m][2 * k] = v.x;
+                x[m][2 * k + 1] = v.y;
+            }
+            dct2_8(x[m]);
+        }
+        __syncwarp();
+        QuantGuard qg;
+        {
+            double rtv[3][8];                           // loaded as one batch: the staging stores below would otherwise
+#pragma unroll                                          // serialise each (possibly aliasing) shared-memory load
+            for (int m = 0; m < 3; ++m)
+#pragma unroll
+                for (int v = 0; v < 8; ++v) rtv[m][v] = rt_l[m * 64 + v * 8];
+            int qv[3][8];
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+#pragma unroll
+                for (int v = 0; v < 8; ++v) qv[m][v] = qg.q(x[m][v], rtv[m][v]);
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+#pragma unroll
+                for (int v = 0; v < 8; ++v) *reinterpret_cast<int *>(zz_wr[v] + m * 256) = qv[m][v];
+        }
+        if (__builtin_expect(qg.risky(), 0)) {          // rare: redo this lane's 24 samples with the IEEE division
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+#pragma unroll
+                for (int v = 0; v < 8; ++v)
+                    *reinterpret_cast<int *>(zz_wr[v] + m * 256) = quantize_exact_f64(x[m][v], t_l[m * 64 + v * 8]);
+        }
+        fence_proxy_async();                            // make the staging visible to the bulk-copy unit
+        __syncwarp();
+        if (lane == 0) {
+            const int b0 = cur.tx * 4, nb = min(4, g.Wp - b0);
+            int32_t *outf = a.out + ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0) * 192;
+            for (int cu = 0; cu < nb; ++cu) bulk_s2g(outf + cu * 192, work_s + cu * (kStageU * 4), 768u);
+            bulk_commit();
+        }
+        cur = nxt;
+    }
+    if (lane == 0) bulk_wait_all0();
+}
+
+// K1 with the colour transform in front (row N1): uint8 RGB HWC in, same scan indices out.
+constexpr int kRgbPitch = 112;                       // 96 B of pixels + 16 B pad (bulk copies need 16-byte rows)
+constexpr int kRgbIn = 8 * kRgbPitch;                // 896
+constexpr int kRgbBuf = 7424;                        // kRgbIn + kWorkBytes rounded up to 128
+static_assert(kRgbIn + kWorkBytes <= kRgbBuf && kRgbBuf % 128 == 0, "layout");
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_rgb8_tma(const FwdArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *s_rt = reinterpret_cast<double *>(smem_raw);                       // [192]
+    double *s_t = s_rt + 192;                                                   // [192]
+    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem_raw + 3072);   // [8]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *in_b = smem_raw + 3200 + warp * kRgbBuf;          // 8 rows x 96 B of packed RGB, pitch 112 B
+    unsigned char *work_b = in_b + kRgbIn;
+    const uint32_t bar = smem_u32(s_bar + warp), in_s = smem_u32(in_b), work_s = smem_u32(work_b);
+
+    for (int i = threadIdx.x; i < 192; i += blockDim.x) {
+        const double t = load_table_elem(a.table, a.table_dtype, i);
+        s_t[i] = t;
+        s_rt[i] = __drcp_rn(t);
+    }
+    if (lane == 0) mbar_init(bar, 1);
+    fence_mbar_init();
+    __syncthreads();
+
+    // lane-constant addresses (everything below indexes them with compile-time offsets)
+    const int r = lane & 7, u = lane >> 3;
+    const unsigned char *rd_in = in_b + r * kRgbPitch + u * 24;
+    unsigned char *t_wr[4], *zz_wr[8];
+    const unsigned char *t_rd[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        t_wr[h] = work_b + u * (kTU2 * 8) + ((((r >> 1) ^ h) << 1) + (r & 1)) * 8;    // + row*64
+        t_rd[h] = work_b + u * (kTU2 * 8) + r * 64 + ((h ^ (r >> 1)) << 4);           // + m*512
+    }
+#pragma unroll
+    for (int v = 0; v < 8; ++v) zz_wr[v] = work_b + (u * kStageU + ZZ_ORDER[v * 8 + r]) * 4;   // + m*256
+    const double *rt_l = s_rt + r, *t_l = s_t + r;
+
+    const TileGeom &g = a.g;
+    const int64_t row_elems = g.W * 3;                                   // BYTES per image row (uint8 RGB)
+    const int64_t gw = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+    const int64_t nw = (int64_t)gridDim.x * kWarpsPerCta;
+    if (gw >= g.total_tiles) return;
+    const int64_t my_tiles = (g.total_tiles - gw + nw - 1) / nw;
+    TileIter cur, nxt;
+    cur.init(g, gw, nw);
+    nxt = cur;
+
+    auto issue = [&](const TileIter &ti) {                  // lane 0 only: 8 row copies of nb*192 bytes
+        const int nb = min(4, g.Wp - ti.tx * 4);
+        const uint32_t row_bytes = (uint32_t)nb * 24u;                      // nb is even (W % 16 == 0): multiple of 16
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(a.img) + ti.frame * a.frame_stride +
+                                   (int64_t)ti.by * 8 * row_elems + (int64_t)ti.tx * 96;
+        mbar_expect_tx(bar, 8u * row_bytes);
+#pragma unroll
+        for (int row = 0; row < 8; ++row) bulk_g2s(in_s + row * kRgbPitch, src + row * row_elems, row_bytes, bar);
+    };
+
+    if (lane == 0) issue(cur);
+    uint32_t parity = 0;
+    for (int64_t it = 0; it < my_tiles; ++it, parity ^= 1u) {
+        nxt.advance(g);
+        mbar_wait(bar, parity);
+        double x[3][8];
+        {
+            // 8 pixels x RGB = 24 bytes; rgb2ycbcr (color.py:15-37) on the fly, then the same path as K1
+            const uint2 w0 = *reinterpret_cast<const uint2 *>(rd_in), w1 = *reinterpret_cast<const uint2 *>(rd_in + 8),
+                        w2 = *reinterpret_cast<const uint2 *>(rd_in + 16);
+            const unsigned w[6] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y};
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                double c[3];
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const int bi = 3 * p + ch;
+                    const unsigned byte = (w[bi >> 2] >> (8 * (bi & 3))) & 255u;
+                    c[ch] = __dsub_rn(__hiloint2double(0x43300000, (int)byte), 4503599627370496.0);   // exact u8 -> f64
+                }
+                rgb2ycbcr_px(c[0], c[1], c[2], x[0][p], x[1][p], x[2][p]);
+            }
         }
         __syncwarp();                                   // IN is consumed: prefetch the next tile into it
         if (lane == 0) {
@@ -1352,6 +1496,20 @@ cudaError_t launch_forward(int device, cudaStream_t st, const void *img, int64_t
         if ((e = set_smem(k_forward<1, false>, smem)) != cudaSuccess) return e;
         k_forward<1, false><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_forward_rgb8(int device, cudaStream_t st, const void *rgb, int64_t n, int64_t H, int64_t W,
+                                int64_t frame_stride_bytes, const void *table, int table_dtype, int32_t *out) {
+    FwdArgs a;
+    a.g = make_geom(n, H, W, 3, 4);
+    a.img = (const double *)rgb; a.frame_stride = frame_stride_bytes; a.table = table; a.table_dtype = table_dtype;
+    a.out = out; a.ref = nullptr; a.mv = nullptr; a.sr = 0; a.pred_out = nullptr;
+    if (a.g.total_tiles == 0) return cudaSuccess;
+    const size_t smem = 3200 + (size_t)kWarpsPerCta * kRgbBuf;
+    cudaError_t e;
+    if ((e = set_smem(k_forward_rgb8_tma, smem)) != cudaSuccess) return e;
+    k_forward_rgb8_tma<<<grid_for(a.g.total_tiles, kWarpsPerCta, device, 2), kWarpsPerCta * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -391,3 +391,25 @@ def test_metrics_match_reference(g1, g6):
     want = ((a - b) ** 2).reshape(5, -1).sum(axis=1)
     assert np.allclose(sse, want, rtol=1e-12, atol=0)
     assert np.array_equal(sse, ivc.frame_sse(a, b).cpu().numpy())                 # deterministic
+
+
+def test_colour_transforms_and_fused_rgb_front_end(g1, g6):
+    """N1: rgb2ycbcr replays numpy's BLAS FMA chain, ycbcr2rgb the elementwise ops; both bit-identical
+    to the reference's outputs recorded in the golden files, and the fused uint8 front end of K1
+    produces the same indices as the two-step route."""
+    rgb = g1["rgb"]
+    ycc = ivc.rgb2ycbcr(rgb)
+    assert ycc.dtype == np.float64 and np.array_equal(ycc, g1["img"])            # golden: reference rgb2ycbcr here
+    assert np.array_equal(ivc.rgb2ycbcr(rgb.astype(np.float32)), g1["img"])      # videocodec.py:38 feeds float32
+    assert np.array_equal(ivc.ycbcr2rgb(g1["rec1"]), g6["rec_rgb"])
+    big = O.smooth_noise_rgb(8, 128, 192)
+    assert np.array_equal(ivc.rgb2ycbcr(big), O.rgb2ycbcr(big))                  # vs numpy on this box
+    wild = np.random.default_rng(1).uniform(-500, 700, size=(64, 64, 3))
+    assert np.array_equal(ivc.ycbcr2rgb(wild), O.ycbcr2rgb(wild))
+    for q in (0.07, 1.0):
+        coder = ivc.IntraBlockCoder(q)
+        assert np.array_equal(coder.forward_rgb(rgb), g1[f"zz{0 if q == 0.07 else 1}"])
+        batch = np.stack([O.smooth_noise_rgb(30 + i, 64, 160) for i in range(3)])
+        assert np.array_equal(coder.forward_rgb(batch), coder.forward(np.stack([O.rgb2ycbcr(b) for b in batch])))
+        odd = O.smooth_noise_rgb(9, 24, 40)                                      # W % 16 != 0: two-kernel route
+        assert np.array_equal(coder.forward_rgb(odd), O.intra_forward(O.rgb2ycbcr(odd), coder.quant.get_quantization_table()))
