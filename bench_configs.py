@@ -63,6 +63,23 @@ def main():
     res["cfg1_512x768_rgb"] = {"fused_fwd_inv_ms": t_f, "six_method_calls_ms": t_u, "numpy_in_numpy_out_ms": t_h,
                                "mpixel_s_fused": 512 * 768 / t_f / 1e3}
 
+    # neighbours of the path (next rows): zero-run encode of the cfg1 scan indices, colour front end, SSE
+    zz1 = c.forward(img)
+    zr = ivc.ZeroRunCoder()
+    rgb8 = (torch.rand((8, 1080, 1920, 3), generator=g, device="cuda") * 255).to(torch.uint8)
+    ycc = ivc.rgb2ycbcr(rgb8)
+    zzb = c.forward(ycc)
+    res["next_rows"] = {
+        "zerorun_encode_cfg1_ms": timed(lambda: zr.encode(zz1), 20),
+        "zerorun_encode_8x1080p_ms": timed(lambda: zr.encode(zzb), 10),
+        "zerorun_symbols_per_pixel_8x1080p": zr.encode(zzb).numel() / (8 * 1080 * 1920),
+        "forward_rgb8_8x1080p_ms": timed(lambda: c.forward_rgb(rgb8), 20),
+        "forward_f64_8x1080p_ms": timed(lambda: c.forward(ycc), 20),
+        "rgb2ycbcr_8x1080p_ms": timed(lambda: ivc.rgb2ycbcr(rgb8), 20),
+        "frame_sse_8x1080p_rgb_f64_ms": timed(lambda: ivc.frame_sse(ycc, ycc), 20),
+    }
+    del rgb8, ycc, zzb
+
     # cfg2: QCIF 21 frames closed loop
     seq = luma_seq(21, 144, 176, 2)
     for graph in (False, True):

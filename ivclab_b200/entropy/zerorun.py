@@ -23,8 +23,8 @@ class ZeroRunCoder:
         if self.block_size != 64:
             raise NotImplementedError("only 64-coefficient blocks are implemented on the device")
         t, was_np = to_device(flat_patch_img)
-        if t.ndim != 4 or t.shape[-1] != 64:
-            raise ValueError(f"expected [h, w, c, 64] scan blocks, got shape {tuple(t.shape)}")
+        if t.ndim not in (4, 5) or t.shape[-1] != 64:        # 5-D = a batch of frames, streams concatenated in order
+            raise ValueError(f"expected [h, w, c, 64] (or [n, h, w, c, 64]) scan blocks, got shape {tuple(t.shape)}")
         t = aligned16(t.to(torch.int32))
         nblk = t.numel() // 64
         dev, sp = dev_index(t), stream_ptr(t.device)
