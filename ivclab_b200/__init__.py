@@ -19,10 +19,11 @@ from .entropy import ZeroRunCoder
 from .install import inject, install
 from .quantization import PatchQuant
 from .signal import DiscreteCosineTransform, rgb2ycbcr, ycbcr2rgb
+from .streaming import StreamedCoder
 from .utils import Patcher, ZigZag, calc_mse, calc_psnr, frame_sse
 from .video import ClosedLoopLumaCoder, MotionCompensator
 
 __version__ = "0.1.0"
 __all__ = ["DiscreteCosineTransform", "PatchQuant", "ZigZag", "Patcher", "MotionCompensator",
            "IntraBlockCoder", "PFrameBlockCoder", "ClosedLoopLumaCoder", "ZeroRunCoder", "calc_mse", "calc_psnr",
-           "frame_sse", "rgb2ycbcr", "ycbcr2rgb", "install", "inject"]
+           "frame_sse", "rgb2ycbcr", "ycbcr2rgb", "StreamedCoder", "install", "inject"]

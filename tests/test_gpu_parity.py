@@ -413,3 +413,27 @@ def test_colour_transforms_and_fused_rgb_front_end(g1, g6):
         assert np.array_equal(coder.forward_rgb(batch), coder.forward(np.stack([O.rgb2ycbcr(b) for b in batch])))
         odd = O.smooth_noise_rgb(9, 24, 40)                                      # W % 16 != 0: two-kernel route
         assert np.array_equal(coder.forward_rgb(odd), O.intra_forward(O.rgb2ycbcr(odd), coder.quant.get_quantization_table()))
+
+
+def test_streamed_coder_matches_direct_calls():
+    """host-fed streaming (3 streams, chunked) returns exactly what the direct API calls return"""
+    F, H, W = 5, 64, 96
+    rgb = np.stack([O.smooth_noise_rgb(50 + i, H, W) for i in range(F)])
+    seq = O.moving_sequence(60, F + 1, H, W).astype(np.uint8)
+    cur, ref = seq[1:], seq[:-1]
+    out = ivc.StreamedCoder(0.4, 4, chunk_frames=2).run(rgb, cur, ref)
+    intra, pc, zr = ivc.IntraBlockCoder(0.4), ivc.PFrameBlockCoder(0.4, 4), ivc.ZeroRunCoder()
+    tab = intra.quant.get_quantization_table()
+    sym_i, sym_p = [], []
+    for i in range(F):
+        zz = O.intra_forward(O.rgb2ycbcr(rgb[i]), tab)
+        sym_i.append(O.zerorun_encode(zz))
+        mv = O.me_full_search(ref[i].astype(np.float64), cur[i].astype(np.float64), 4)
+        assert np.array_equal(out["mv"][i].numpy(), mv)
+        pred, zzp = O.pframe_forward(cur[i].astype(np.float64), ref[i].astype(np.float64), mv, 4, tab)
+        sym_p.append(O.zerorun_encode(zzp))
+        rec = O.intra_inverse(zz, tab)
+        assert abs(out["sse"][0, i].item() / ((O.rgb2ycbcr(rgb[i]) - rec) ** 2).sum() - 1) < 1e-12
+    assert np.array_equal(out["sym_intra"].numpy(), np.concatenate(sym_i))
+    assert np.array_equal(out["sym_inter"].numpy(), np.concatenate(sym_p))
+    assert sum(out["len_intra"]) == out["sym_intra"].numel()
