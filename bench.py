@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--e2e-frames", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the host-fed legs (e2e keys become null)")
     ap.add_argument("--me-mode", default="auto", choices=["auto", "exact", "int"])
     return ap.parse_args()
 
@@ -243,100 +244,104 @@ def run_b200(args):
     px = Fr * H * W
     value = world * px / (ms_step * 1e-3) / 1e6
 
-    # ---- e2e through the public API, host buffers in pinned memory ----
-    # (a) "codec" form: what a caller of IntraCodec.image2symbols / the video codecs hands over and gets back --
-    #     uint8 RGB frames + uint8 luma planes in (H2D), zero-run symbol streams + motion vectors + MSE out (D2H);
-    #     colour transform (N1), zero-run coding (N2) and the squared-error reduction (N3) run on the device so
-    #     only compact data crosses PCIe.  Same transform / ME work per pixel as `value`.
-    # (b) "raw" form: float64 planes in, raw int32 scan indices out (the per-method classes' array types).
+    e2e_ms = serial_ms = raw_ms = e2e_val = raw_val = None
+    h2d = d2h = raw_h2d = raw_d2h = None
     Fe = min(args.e2e_frames, Fr)
-    intra = ivc.IntraBlockCoder(QSCALE)
-    pcod = ivc.PFrameBlockCoder(QSCALE, SR, me_mode=args.me_mode)
-    zr = ivc.ZeroRunCoder()
-    M_inv = torch.linalg.inv(torch.tensor([[0.299, 0.587, 0.114], [-0.168736, -0.331264, 0.5], [0.5, -0.418688, -0.081312]],
-                                          dtype=torch.float64, device=device))
-    rgb8 = ((ycbcr[:Fe] - torch.tensor([0.0, 128.0, 128.0], dtype=torch.float64, device=device)) @ M_inv.T).round().clamp(0, 255).to(torch.uint8)
-    h_rgb = rgb8.cpu().pin_memory()
-    h_l8 = luma[:Fe].to(torch.uint8).cpu().pin_memory()
-    h_r8 = ref[:Fe].to(torch.uint8).cpu().pin_memory()
-    h_mv = torch.empty((Fe, Hp, Wp, 1), dtype=torch.int64).pin_memory()
-    h_stat = torch.empty((2, Fe), dtype=torch.float64).pin_memory()
-    sym_bytes = [0]
-    h_sym_i = torch.empty(Fe * Hp * Wp * 3 * 65, dtype=torch.int32).pin_memory()     # generous bound on the stream length
-    h_sym_p = torch.empty(Fe * Hp * Wp * 3 * 65, dtype=torch.int32).pin_memory()
+    if not args.no_e2e:
+        # ---- e2e through the public API, host buffers in pinned memory ----
+        # (a) "codec" form: what a caller of IntraCodec.image2symbols / the video codecs hands over and gets back --
+        #     uint8 RGB frames + uint8 luma planes in (H2D), zero-run symbol streams + motion vectors + MSE out (D2H);
+        #     colour transform (N1), zero-run coding (N2) and the squared-error reduction (N3) run on the device so
+        #     only compact data crosses PCIe.  Same transform / ME work per pixel as `value`.
+        # (b) "raw" form: float64 planes in, raw int32 scan indices out (the per-method classes' array types).
+        Fe = min(args.e2e_frames, Fr)
+        intra = ivc.IntraBlockCoder(QSCALE)
+        pcod = ivc.PFrameBlockCoder(QSCALE, SR, me_mode=args.me_mode)
+        zr = ivc.ZeroRunCoder()
+        M_inv = torch.linalg.inv(torch.tensor([[0.299, 0.587, 0.114], [-0.168736, -0.331264, 0.5], [0.5, -0.418688, -0.081312]],
+                                              dtype=torch.float64, device=device))
+        rgb8 = ((ycbcr[:Fe] - torch.tensor([0.0, 128.0, 128.0], dtype=torch.float64, device=device)) @ M_inv.T).round().clamp(0, 255).to(torch.uint8)
+        h_rgb = rgb8.cpu().pin_memory()
+        h_l8 = luma[:Fe].to(torch.uint8).cpu().pin_memory()
+        h_r8 = ref[:Fe].to(torch.uint8).cpu().pin_memory()
+        h_mv = torch.empty((Fe, Hp, Wp, 1), dtype=torch.int64).pin_memory()
+        h_stat = torch.empty((2, Fe), dtype=torch.float64).pin_memory()
+        sym_bytes = [0]
+        h_sym_i = torch.empty(Fe * Hp * Wp * 3 * 65, dtype=torch.int32).pin_memory()     # generous bound on the stream length
+        h_sym_p = torch.empty(Fe * Hp * Wp * 3 * 65, dtype=torch.int32).pin_memory()
 
-    def e2e_step():
-        d_rgb = to_device(h_rgb)[0]                       # the API uploads the pinned HOST buffers itself
-        d_l = to_device(h_l8)[0].double()
-        d_r = to_device(h_r8)[0].double()
-        z = intra.forward_rgb(d_rgb)                      # rgb2ycbcr + DCT + quantise + zig-zag
-        s_i = zr.encode(z)                                # symbols go to the host (entropy coder input)
-        h_sym_i[:s_i.numel()].copy_(s_i, non_blocking=True)
-        r = intra.inverse(z)
-        sse_i = ivc.frame_sse(ivc.rgb2ycbcr(d_rgb), r)
-        m = pcod.estimate(d_r, d_l)
-        zp = pcod.forward(d_l, d_r, m)
-        s_p = zr.encode(zp)
-        h_sym_p[:s_p.numel()].copy_(s_p, non_blocking=True)
-        rp = pcod.inverse(zp, ref=d_r, mv=m)
-        sse_p = ivc.frame_sse(d_l, rp)
-        h_mv.copy_(m, non_blocking=True)
-        h_stat.copy_(torch.stack([sse_i, sse_p]), non_blocking=True)
-        torch.cuda.synchronize()
-        sym_bytes[0] = (s_i.numel() + s_p.numel()) * 4
+        def e2e_step():
+            d_rgb = to_device(h_rgb)[0]                       # the API uploads the pinned HOST buffers itself
+            d_l = to_device(h_l8)[0].double()
+            d_r = to_device(h_r8)[0].double()
+            z = intra.forward_rgb(d_rgb)                      # rgb2ycbcr + DCT + quantise + zig-zag
+            s_i = zr.encode(z)                                # symbols go to the host (entropy coder input)
+            h_sym_i[:s_i.numel()].copy_(s_i, non_blocking=True)
+            r = intra.inverse(z)
+            sse_i = ivc.frame_sse(ivc.rgb2ycbcr(d_rgb), r)
+            m = pcod.estimate(d_r, d_l)
+            zp = pcod.forward(d_l, d_r, m)
+            s_p = zr.encode(zp)
+            h_sym_p[:s_p.numel()].copy_(s_p, non_blocking=True)
+            rp = pcod.inverse(zp, ref=d_r, mv=m)
+            sse_p = ivc.frame_sse(d_l, rp)
+            h_mv.copy_(m, non_blocking=True)
+            h_stat.copy_(torch.stack([sse_i, sse_p]), non_blocking=True)
+            torch.cuda.synchronize()
+            sym_bytes[0] = (s_i.numel() + s_p.numel()) * 4
 
-    h_y = ycbcr[:Fe].cpu().pin_memory()
-    h_l = luma[:Fe].cpu().pin_memory()
-    h_r = ref[:Fe].cpu().pin_memory()
-    h_zz_i = torch.empty((Fe, Hp, Wp, 3, 64), dtype=torch.int32).pin_memory()
-    h_zz_p = torch.empty((Fe, Hp, Wp, 3, 64), dtype=torch.int32).pin_memory()
+        h_y = ycbcr[:Fe].cpu().pin_memory()
+        h_l = luma[:Fe].cpu().pin_memory()
+        h_r = ref[:Fe].cpu().pin_memory()
+        h_zz_i = torch.empty((Fe, Hp, Wp, 3, 64), dtype=torch.int32).pin_memory()
+        h_zz_p = torch.empty((Fe, Hp, Wp, 3, 64), dtype=torch.int32).pin_memory()
 
-    def e2e_raw_step():
-        d_y = to_device(h_y)[0]
-        d_l = to_device(h_l)[0]
-        d_r = to_device(h_r)[0]
-        z = intra.forward(d_y)
-        r = intra.inverse(z)
-        m = pcod.estimate(d_r, d_l)
-        zp = pcod.forward(d_l, d_r, m)
-        rp = pcod.inverse(zp, ref=d_r, mv=m)
-        h_zz_i.copy_(z, non_blocking=True)
-        h_zz_p.copy_(zp, non_blocking=True)
-        h_mv.copy_(m, non_blocking=True)
-        h_stat.copy_(torch.stack([ivc.frame_sse(d_y, r), ivc.frame_sse(d_l, rp)]), non_blocking=True)
-        torch.cuda.synchronize()
+        def e2e_raw_step():
+            d_y = to_device(h_y)[0]
+            d_l = to_device(h_l)[0]
+            d_r = to_device(h_r)[0]
+            z = intra.forward(d_y)
+            r = intra.inverse(z)
+            m = pcod.estimate(d_r, d_l)
+            zp = pcod.forward(d_l, d_r, m)
+            rp = pcod.inverse(zp, ref=d_r, mv=m)
+            h_zz_i.copy_(z, non_blocking=True)
+            h_zz_p.copy_(zp, non_blocking=True)
+            h_mv.copy_(m, non_blocking=True)
+            h_stat.copy_(torch.stack([ivc.frame_sse(d_y, r), ivc.frame_sse(d_l, rp)]), non_blocking=True)
+            torch.cuda.synchronize()
 
-    def time_e2e(fn):
-        for _ in range(3):
-            fn()
-        barrier()
-        Ke = max(3, min(K, 10))
-        w0 = time.perf_counter()
-        for _ in range(Ke):
-            fn()
-        barrier()
-        ms = (time.perf_counter() - w0) * 1e3 / Ke
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        def time_e2e(fn):
+            for _ in range(3):
+                fn()
+            barrier()
+            Ke = max(3, min(K, 10))
+            w0 = time.perf_counter()
+            for _ in range(Ke):
+                fn()
+            barrier()
+            ms = (time.perf_counter() - w0) * 1e3 / Ke
+            if world > 1:
+                t = torch.tensor([ms], dtype=torch.float64, device=device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms
 
-    serial_ms = time_e2e(e2e_step)                         # one stream, copies and kernels back to back
-    streamed = ivc.StreamedCoder(QSCALE, SR, me_mode=args.me_mode, chunk_frames=2, device=device)
-    last = [None]
+        serial_ms = time_e2e(e2e_step)                         # one stream, copies and kernels back to back
+        streamed = ivc.StreamedCoder(QSCALE, SR, me_mode=args.me_mode, chunk_frames=2, device=device)
+        last = [None]
 
-    def e2e_streamed_step():                               # the same work, uploads/downloads overlapped with the kernels
-        last[0] = streamed.run(h_rgb, h_l8, h_r8)
+        def e2e_streamed_step():                               # the same work, uploads/downloads overlapped with the kernels
+            last[0] = streamed.run(h_rgb, h_l8, h_r8)
 
-    e2e_ms = time_e2e(e2e_streamed_step)
-    e2e_val = world * Fe * H * W / (e2e_ms * 1e-3) / 1e6
-    h2d = last[0]["h2d_bytes"]
-    d2h = last[0]["d2h_bytes"]
-    raw_ms = time_e2e(e2e_raw_step)
-    raw_val = world * Fe * H * W / (raw_ms * 1e-3) / 1e6
-    raw_h2d = h_y.numel() * 8 + h_l.numel() * 8 + h_r.numel() * 8
-    raw_d2h = h_zz_i.numel() * 4 + h_zz_p.numel() * 4 + h_mv.numel() * 8 + h_stat.numel() * 8
+        e2e_ms = time_e2e(e2e_streamed_step)
+        e2e_val = world * Fe * H * W / (e2e_ms * 1e-3) / 1e6
+        h2d = last[0]["h2d_bytes"]
+        d2h = last[0]["d2h_bytes"]
+        raw_ms = time_e2e(e2e_raw_step)
+        raw_val = world * Fe * H * W / (raw_ms * 1e-3) / 1e6
+        raw_h2d = h_y.numel() * 8 + h_l.numel() * 8 + h_r.numel() * 8
+        raw_d2h = h_zz_i.numel() * 4 + h_zz_p.numel() * 4 + h_mv.numel() * 8 + h_stat.numel() * 8
 
     out = None
     if rank == 0:
@@ -361,11 +366,11 @@ def run_b200(args):
             "warmup": max(3, args.warmup), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(Fr, world),
-            "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "e2e": None if args.no_e2e else {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "frames_per_step": Fe, "ms_per_step": round(e2e_ms, 3), "ms_per_step_single_stream": round(serial_ms, 3),
                     "api": "StreamedCoder.run (3 streams, 2-frame chunks): pinned host uint8 RGB + uint8 luma in; IntraBlockCoder.forward_rgb/inverse, PFrameBlockCoder."
                            "estimate/forward/inverse, ZeroRunCoder.encode, frame_sse; zero-run symbols + MVs + SSE back to host"},
-            "e2e_raw": {"value": round(raw_val, 1), "unit": UNIT, "h2d_bytes_per_step": raw_h2d, "d2h_bytes_per_step": raw_d2h,
+            "e2e_raw": None if args.no_e2e else {"value": round(raw_val, 1), "unit": UNIT, "h2d_bytes_per_step": raw_h2d, "d2h_bytes_per_step": raw_d2h,
                         "frames_per_step": Fe, "ms_per_step": round(raw_ms, 3),
                         "api": "pinned host float64 YCbCr + luma in, raw int32 scan indices + MVs + SSE out (PCIe-bound)"},
             "gpu_launches": K * launches_per_step,

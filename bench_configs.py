@@ -96,7 +96,7 @@ def main():
     def sweep():
         for cd in coders:
             rec = cd.inverse(cd.forward(frames))
-            ((rec - frames) ** 2).mean(dim=(1, 2, 3))          # per-frame MSE for PSNR (torch reduction; N3 is a "next" row)
+            ivc.frame_sse(frames, rec)                          # per-frame squared error for PSNR (row N3)
     t = timed(sweep, 3, warm=1)
     res["cfg3_rd_sweep_1080p"] = {"frames": F, "qscales": len(QS), "ms_per_sweep": t,
                                   "mpixel_s_incl_psnr": F * len(QS) * 1080 * 1920 / t / 1e3}
