@@ -475,6 +475,9 @@ def run_reference(args):
 
 def main():
     args = parse()
+    if not os.path.exists(os.path.join(ROOT, "ivclab_b200", "_C", "libivcb200.so")):
+        import __graft_entry__                      # fresh checkout: build the (git-ignored) extension first
+        __graft_entry__.build()
     if args.impl == "reference":
         run_reference(args)
     else:

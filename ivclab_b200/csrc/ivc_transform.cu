@@ -592,16 +592,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_c3_tma(const F
     cur.init(g, gw, nw);
     nxt = cur;
 
-    auto issue = [&](const TileIter &ti) {                  // lane 0 only: 8 row copies of nb*192 bytes
+    auto issue = [&](const TileIter &ti) {                  // whole warp: lanes 0..7 each copy one row
         const int nb = min(4, g.Wp - ti.tx * 4);
         const uint32_t row_bytes = (uint32_t)nb * 192u;
-        const double *src = a.img + ti.frame * a.frame_stride + (int64_t)ti.by * 8 * row_elems + (int64_t)ti.tx * 96;
-        mbar_expect_tx(bar, 8u * row_bytes);
-#pragma unroll
-        for (int row = 0; row < 8; ++row) bulk_g2s(in_s + row * (kRowPitch * 8), src + row * row_elems, row_bytes, bar);
+        fence_proxy_async();
+        if (lane == 0) mbar_expect_tx(bar, 8u * row_bytes);
+        __syncwarp();
+        if (lane < 8) {                                     // lane r copies pixel row r
+            const double *src = a.img + ti.frame * a.frame_stride + ((int64_t)ti.by * 8 + lane) * row_elems + (int64_t)ti.tx * 96;
+            bulk_g2s(in_s + lane * (kRowPitch * 8), src, row_bytes, bar);
+        }
     };
 
-    if (lane == 0) issue(cur);
+    issue(cur);
     uint32_t parity = 0;
     for (int64_t it = 0; it < my_tiles; ++it, parity ^= 1u) {
         nxt.advance(g);
@@ -621,10 +624,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_c3_tma(const F
                 for (int p = 0; p < 8; ++p) x[m][p] = raw[3 * p + m];
         }
         __syncwarp();                                   // IN is consumed: prefetch the next tile into it
-        if (lane == 0) {
-            if (it + 1 < my_tiles) { fence_proxy_async(); issue(nxt); }
-            bulk_wait_read0();                          // previous tile's store has drained WORK
-        }
+        if (it + 1 < my_tiles) issue(nxt);
+        bulk_wait_read0();                              // previous tile's stores (each lane its own group) have drained WORK
 #pragma unroll
         for (int m = 0; m < 3; ++m) dct2_8(x[m]);
         __syncwarp();
@@ -670,15 +671,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_c3_tma(const F
         }
         fence_proxy_async();                            // make the staging visible to the bulk-copy unit
         __syncwarp();
-        if (lane == 0) {
+        {
             const int b0 = cur.tx * 4, nb = min(4, g.Wp - b0);
-            int32_t *outf = a.out + ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0) * 192;
-            for (int cu = 0; cu < nb; ++cu) bulk_s2g(outf + cu * 192, work_s + cu * (kStageU * 4), 768u);
-            bulk_commit();
+            if (lane < nb) {                              // lane u stores the 3 scan blocks of image block u
+                int32_t *outf = a.out + ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0 + lane) * 192;
+                bulk_s2g(outf, work_s + lane * (kStageU * 4), 768u);
+                bulk_commit();
+            }
         }
         cur = nxt;
     }
-    if (lane == 0) bulk_wait_all0();
+    bulk_wait_all0();
 }
 
 // K1 with the colour transform in front (row N1): uint8 RGB HWC in, same scan indices out.
@@ -730,17 +733,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_rgb8_tma(const
     cur.init(g, gw, nw);
     nxt = cur;
 
-    auto issue = [&](const TileIter &ti) {                  // lane 0 only: 8 row copies of nb*192 bytes
+    auto issue = [&](const TileIter &ti) {                  // whole warp: lanes 0..7 each copy one row
         const int nb = min(4, g.Wp - ti.tx * 4);
         const uint32_t row_bytes = (uint32_t)nb * 24u;                      // nb is even (W % 16 == 0): multiple of 16
-        const unsigned char *src = reinterpret_cast<const unsigned char *>(a.img) + ti.frame * a.frame_stride +
-                                   (int64_t)ti.by * 8 * row_elems + (int64_t)ti.tx * 96;
-        mbar_expect_tx(bar, 8u * row_bytes);
-#pragma unroll
-        for (int row = 0; row < 8; ++row) bulk_g2s(in_s + row * kRgbPitch, src + row * row_elems, row_bytes, bar);
+        fence_proxy_async();
+        if (lane == 0) mbar_expect_tx(bar, 8u * row_bytes);
+        __syncwarp();
+        if (lane < 8) {
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(a.img) + ti.frame * a.frame_stride +
+                                       ((int64_t)ti.by * 8 + lane) * row_elems + (int64_t)ti.tx * 96;
+            bulk_g2s(in_s + lane * kRgbPitch, src, row_bytes, bar);
+        }
     };
 
-    if (lane == 0) issue(cur);
+    issue(cur);
     uint32_t parity = 0;
     for (int64_t it = 0; it < my_tiles; ++it, parity ^= 1u) {
         nxt.advance(g);
@@ -764,10 +770,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_rgb8_tma(const
             }
         }
         __syncwarp();                                   // IN is consumed: prefetch the next tile into it
-        if (lane == 0) {
-            if (it + 1 < my_tiles) { fence_proxy_async(); issue(nxt); }
-            bulk_wait_read0();                          // previous tile's store has drained WORK
-        }
+        if (it + 1 < my_tiles) issue(nxt);
+        bulk_wait_read0();                              // previous tile's stores (each lane its own group) have drained WORK
 #pragma unroll
         for (int m = 0; m < 3; ++m) dct2_8(x[m]);
         __syncwarp();
@@ -813,15 +817,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_rgb8_tma(const
         }
         fence_proxy_async();                            // make the staging visible to the bulk-copy unit
         __syncwarp();
-        if (lane == 0) {
+        {
             const int b0 = cur.tx * 4, nb = min(4, g.Wp - b0);
-            int32_t *outf = a.out + ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0) * 192;
-            for (int cu = 0; cu < nb; ++cu) bulk_s2g(outf + cu * 192, work_s + cu * (kStageU * 4), 768u);
-            bulk_commit();
+            if (lane < nb) {                              // lane u stores the 3 scan blocks of image block u
+                int32_t *outf = a.out + ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0 + lane) * 192;
+                bulk_s2g(outf, work_s + lane * (kStageU * 4), 768u);
+                bulk_commit();
+            }
         }
         cur = nxt;
     }
-    if (lane == 0) bulk_wait_all0();
+    bulk_wait_all0();
 }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_inverse_c3_tma(const InvArgs a) {
@@ -1047,13 +1053,13 @@ __global__ void __launch_bounds__(kPfWarps * 32, 1) k_pframe_forward_tma(const F
     };
     auto issue = [&](const TileIter &ti, int64_t mvidx) {        // whole warp
         const int b0 = ti.tx * 12, nb = min(12, g.Wp - b0);
-        if (lane == 0) {
-            const uint32_t row_bytes = (uint32_t)nb * 64u;
-            const double *src = a.img + ti.frame * a.frame_stride + (int64_t)ti.by * 8 * row_elems + (int64_t)b0 * 8;
-            fence_proxy_async();
-            mbar_expect_tx(bar, 8u * row_bytes);
-#pragma unroll
-            for (int row = 0; row < 8; ++row) bulk_g2s(in_s + row * (kRowPitch * 8), src + row * row_elems, row_bytes, bar);
+        const uint32_t row_bytes = (uint32_t)nb * 64u;
+        fence_proxy_async();
+        if (lane == 0) mbar_expect_tx(bar, 8u * row_bytes);
+        __syncwarp();
+        if (lane < 8) {                                     // lane r copies current-frame row r
+            const double *src = a.img + ti.frame * a.frame_stride + ((int64_t)ti.by * 8 + lane) * row_elems + (int64_t)b0 * 8;
+            bulk_g2s(in_s + lane * (kRowPitch * 8), src, row_bytes, bar);
         }
         pg.issue(pred_s, bar, lane, mvidx, nb, a.ref + ti.frame * frame_elems, ti.by, b0);
     };
@@ -1089,7 +1095,7 @@ __global__ void __launch_bounds__(kPfWarps * 32, 1) k_pframe_forward_tma(const F
         }
 #pragma unroll
         for (int m = 0; m < 3; ++m) dct2_8(x[m]);
-        if (lane == 0) bulk_wait_read0();               // previous tile's stores have drained WORK
+        bulk_wait_read0();                              // previous tile's stores have drained WORK
         __syncwarp();
 #pragma unroll
         for (int m = 0; m < 3; ++m)
@@ -1113,7 +1119,7 @@ __global__ void __launch_bounds__(kPfWarps * 32, 1) k_pframe_forward_tma(const F
 #pragma unroll
         for (int m = 0; m < 3; ++m) {
             const int reg = (m & 1) * 3200;
-            if (m == 2) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); __syncwarp(); }
+            if (m == 2) { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); __syncwarp(); }
             QuantGuard qg;
             {
                 double rtv[3][8];
@@ -1140,16 +1146,13 @@ __global__ void __launch_bounds__(kPfWarps * 32, 1) k_pframe_forward_tma(const F
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
-                for (int cu = 0; cu < 4; ++cu)
-                    if (3 * cu + m < nb) bulk_s2g(outf + (3 * cu + m) * 192, work_s + reg + cu * (kStageU * 4), 768u);
-                bulk_commit();
-            }
+            if (lane < 4 && 3 * lane + m < nb) bulk_s2g(outf + (3 * lane + m) * 192, work_s + reg + lane * (kStageU * 4), 768u);
+            bulk_commit();                                // every lane commits (possibly empty) groups: counts stay in step
         }
         cur = nxt;
         nxt = nx2;
     }
-    if (lane == 0) bulk_wait_all0();
+    bulk_wait_all0();
 }
 
 // K2p: per warp IN (scan blocks, 3200 B) + PRED x2 (double-buffered so that the prediction can be read
@@ -1207,20 +1210,21 @@ __global__ void __launch_bounds__(kPiWarps * 32, 1) k_pframe_inverse_tma(const I
     };
     auto issue = [&](const TileIter &ti, int64_t mvidx, uint32_t pbuf_s) {
         const int b0 = ti.tx * 12, nb = min(12, g.Wp - b0);
-        if (lane == 0) {
-            const int32_t *zsrc = a.zz + ((ti.frame * g.Hp + ti.by) * (int64_t)g.Wp + b0) * a.Czz * 64;
-            const uint32_t row_bytes = (uint32_t)nb * 64u;
-            fence_proxy_async();
-            mbar_expect_tx(bar, (uint32_t)nb * 256u + (gather ? 0u : 8u * row_bytes));
-            for (int blk = 0; blk < nb; ++blk) {          // scan channel 0 of every block (stride Czz*64 ints)
-                const int cu = blk / 3;
-                bulk_g2s(in_s + (cu * kStageU + (blk - cu * 3) * 64) * 4, zsrc + (int64_t)blk * a.Czz * 64, 256u, bar);
-            }
-            if (!gather) {
-                const double *psrc = a.pred + ti.frame * frame_elems + (int64_t)ti.by * 8 * row_elems + (int64_t)b0 * 8;
-#pragma unroll
-                for (int row = 0; row < 8; ++row) bulk_g2s(pbuf_s + row * (kRowPitch * 8), psrc + row * row_elems, row_bytes, bar);
-            }
+        // the bulk copies of a tile are issued by different lanes in parallel (lane b: scan block b,
+        // lanes 16..23: prediction rows) after lane 0 has armed the barrier
+        const uint32_t row_bytes = (uint32_t)nb * 64u;
+        fence_proxy_async();
+        if (lane == 0) mbar_expect_tx(bar, (uint32_t)nb * 256u + (gather ? 0u : 8u * row_bytes));
+        __syncwarp();
+        if (lane < nb) {                                  // scan channel 0 of block `lane` (stride Czz*64 ints)
+            const int32_t *zsrc = a.zz + ((ti.frame * g.Hp + ti.by) * (int64_t)g.Wp + b0 + lane) * a.Czz * 64;
+            const int cu = lane / 3;
+            bulk_g2s(in_s + (cu * kStageU + (lane - cu * 3) * 64) * 4, zsrc, 256u, bar);
+        }
+        if (!gather && lane >= 16 && lane < 24) {
+            const int row = lane - 16;
+            const double *psrc = a.pred + ti.frame * frame_elems + ((int64_t)ti.by * 8 + row) * row_elems + (int64_t)b0 * 8;
+            bulk_g2s(pbuf_s + row * (kRowPitch * 8), psrc, row_bytes, bar);
         }
         if (gather) pg.issue(pbuf_s, bar, lane, mvidx, nb, a.ref + ti.frame * frame_elems, ti.by, b0);
     };
@@ -1265,7 +1269,7 @@ __global__ void __launch_bounds__(kPiWarps * 32, 1) k_pframe_inverse_tma(const I
         }
 #pragma unroll
         for (int m = 0; m < 3; ++m) dct3_8(x[m]);
-        if (lane == 0) bulk_wait_read0();
+        bulk_wait_read0();                              // every lane drains its own bulk-store group
         __syncwarp();
 #pragma unroll
         for (int m = 0; m < 3; ++m)
@@ -1298,17 +1302,15 @@ __global__ void __launch_bounds__(kPiWarps * 32, 1) k_pframe_inverse_tma(const I
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
-            double *dst = a.out + cur.frame * frame_elems + (int64_t)cur.by * 8 * row_elems + (int64_t)b0 * 8;
-            const uint32_t row_bytes = (uint32_t)nb * 64u;
-#pragma unroll
-            for (int row = 0; row < 8; ++row) bulk_s2g(dst + row * row_elems, work_s + row * (kRowPitch * 8), row_bytes);
+        if (lane < 8) {                                   // lane r stores output row r
+            double *dst = a.out + cur.frame * frame_elems + ((int64_t)cur.by * 8 + lane) * row_elems + (int64_t)b0 * 8;
+            bulk_s2g(dst, work_s + lane * (kRowPitch * 8), (uint32_t)nb * 64u);
             bulk_commit();
         }
         cur = nxt;
         nxt = nx2;
     }
-    if (lane == 0) bulk_wait_all0();
+    bulk_wait_all0();
 }
 
 // ================================================================================================
