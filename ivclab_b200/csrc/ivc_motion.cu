@@ -39,6 +39,11 @@ struct MeArgs {
     int tiles_y, tiles_x;
     int R, P, Wc;                          // window rows / pitch / used columns (elements or bytes)
     int cur_off;                           // byte offset of the current-blocks area in dynamic smem
+    int pw, hs_off, b_off;                 // integer kernel: words per packed row, offsets of HS and B
+    int pwl, nseg;                         // ... words per row actually staged, 8-row segments of S
+    int vec;                               // ... 16-byte staging loads are legal (alignment of base, strides, sr)
+    unsigned m_pwl, m_q4, m_p4, m_ntpb, m_span;     // multiply-high reciprocals (host-computed)
+    unsigned m_nbx[2], m_cww[2];                    // ... of nbx and 2*nbx for full / last-column tiles
     int64_t *mv;
     int *flag;                             // device flag (may be null)
     int run_if;                            // exact kernel: run only if *flag == run_if (when flag != null)
@@ -60,13 +65,11 @@ struct MeTile {
     int64_t frame;
     int by0, bx0, nby, nbx;
 };
+// grid: x = tile (row-major over tiles_y x tiles_x), y = frame (launchers chunk batches above 65535 frames)
 __device__ __forceinline__ MeTile me_tile(const MeArgs &a) {
     MeTile t;
-    int64_t cta = blockIdx.x;
-    const int tx = (int)(cta % a.tiles_x);
-    cta /= a.tiles_x;
-    const int ty = (int)(cta % a.tiles_y);
-    t.frame = cta / a.tiles_y;
+    const int ty = (int)blockIdx.x / a.tiles_x, tx = (int)blockIdx.x - ty * a.tiles_x;
+    t.frame = blockIdx.y;
     t.by0 = ty * a.tby;
     t.bx0 = tx * a.tbx;
     t.nby = min(a.tby, a.Hp - t.by0);
@@ -176,138 +179,267 @@ __global__ void __launch_bounds__(kMeThreads, 2) k_me_exact(const MeArgs a) {
 // ================================================================================================
 // integer kernel (packed uint8, converted from the float frames while staging)
 // ================================================================================================
+// SSD = sum(c^2) + sum(r^2) - 2 sum(c r): the cross term is ONE dp4a per four candidate-pixels (the direct
+// form needs an absolute difference and a dp4a); sum(r^2) over an 8x8 window depends on the window
+// position only and is computed once per position of the CTA's search window (a horizontal dp4a pass and
+// a vertical running sum), sum(c^2) once per block.  All three terms are exact integers, so the key
+// (ssd, index) and therefore the vector is exactly the reference's.
+//
+// Shared-memory layout per CTA:
+//   B  [R][pw]  packed bytes of the search window (4 pixels per word), zero outside the frame
+//   U  [R][P4]  "unaligned word" view: U[y][x] = bytes x..x+3 of row y, so a candidate's 8-byte row is
+//               U[y][x], U[y][x+4] for ANY x and 32 consecutive candidates read 32 consecutive banks
+//   HS [R][P4]  H[y][x] = sum_{j<8} r[y][x+j]^2, then in place S[y][x] = sum_{i<8} H[y+i][x]
+//   cur         current blocks, 8 rows x 2 words each (+2 words padding per block)
+// A TASK is G vertically adjacent candidates (dy0..dy0+G-1, dx) of one block sharing their G+7 window
+// rows in registers; tasks of all blocks are flattened over the CTA, dx fastest.
+
 // value -> uint8 plus "is an integer in [0,255]" without the (quarter-rate) FP64 conversion instructions:
-// v + 2^52 leaves the integer in the low mantissa word; (v + 2^52) - 2^52 == v proves v had no fraction.
-__device__ __forceinline__ unsigned to_u8_checked(double v, bool &bad) {
-    const double s = __dadd_rn(v, 4503599627370496.0);
-    const unsigned iv = (unsigned)__double2loint(s);
-    bad |= !((__double2hiint(s) == 0x43300000) & (iv <= 255u) & (__dsub_rn(s, 4503599627370496.0) == v));
-    return iv & 255u;
-}
-__device__ __forceinline__ unsigned to_u8_checked(float v, bool &bad) {
-    const int iv = (int)v;                                                    // saturating; NaN -> 0
-    bad |= !((float)iv == v && iv >= 0 && iv <= 255);
-    return (unsigned)iv & 255u;
-}
-
-template <typename T>
-__device__ __forceinline__ unsigned pack4(const T *p, int64_t base, int64_t gx, int64_t W, bool row_ok, bool &bad) {
-    unsigned w = 0;
-    if (row_ok && gx >= 0 && gx + 3 < W) {                                    // interior word: four independent loads
-        T v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = p[base + gx + k];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) w |= to_u8_checked(v[k], bad) << (8 * k);
-    } else if (row_ok) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (gx + k >= 0 && gx + k < W) w |= to_u8_checked(p[base + gx + k], bad) << (8 * k);
-    }
-    return w;
-}
-
-// floor(x / d) for the small operands of the task decomposition: one multiply-high
-struct FastDiv {
-    unsigned magic, d;
-    __device__ __forceinline__ explicit FastDiv(unsigned dd) : magic(dd > 1 ? 0xFFFFFFFFu / dd + 1u : 0u), d(dd) {}
-    __device__ __forceinline__ int div(int x) const { return d > 1 ? (int)__umulhi((unsigned)x, magic) : x; }   // x*d < 2^32
+// s = v + 2^52 leaves rint(v) in the low mantissa word, s - 2^52 == v proves v had no fraction, and the
+// word pair of s must read (0x43300000, 0..255).  err accumulates violated bits, ne "not exact".
+struct U8Check {
+    unsigned err = 0;
+    bool ne = false;
+    __device__ __forceinline__ bool bad() const { return (err != 0) | ne; }
 };
+__device__ __forceinline__ unsigned to_u8(double v, U8Check &c) {
+    const double s = __dadd_rn(v, 4503599627370496.0);
+    const unsigned lo = (unsigned)__double2loint(s);
+    c.err |= ((unsigned)__double2hiint(s) ^ 0x43300000u) | (lo & 0xffffff00u);
+    c.ne |= __dsub_rn(s, 4503599627370496.0) != v;
+    return lo;
+}
+__device__ __forceinline__ unsigned to_u8(float v, U8Check &c) {
+    const float s = __fadd_rn(v, 8388608.0f);                                 // 2^23
+    const unsigned n = __float_as_uint(s) ^ 0x4b000000u;
+    c.err |= n & 0xffffff00u;
+    c.ne |= __fsub_rn(s, 8388608.0f) != v;
+    return n;
+}
+__device__ __forceinline__ unsigned pack_bytes(unsigned b0, unsigned b1, unsigned b2, unsigned b3) {
+    return __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+}
 
-template <typename T>
+// floor(x / d) for the small operands of the index decompositions: one multiply-high (x*d < 2^32)
+struct FastDiv {
+    unsigned magic;                                                           // 0 = divide by one
+    __device__ __forceinline__ explicit FastDiv(unsigned m) : magic(m) {}
+    __device__ __forceinline__ int div(int x) const { return magic ? (int)__umulhi((unsigned)x, magic) : x; }
+};
+static unsigned fastdiv_magic(unsigned d) { return d > 1 ? 0xFFFFFFFFu / d + 1u : 0u; }
+
+constexpr int kCurPitch = 18;      // words per current block in shared memory (16 + 2: blocks on distinct banks)
+constexpr int kStageUnroll = 4;    // packed words (16 pixel loads) in flight per thread while staging
+
+// 16-byte read-only loads (two doubles / four floats)
+__device__ __forceinline__ void ldg16(const double *p, double (&v)[2]) {
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+}
+__device__ __forceinline__ void ldg16(const float *p, float (&v)[4]) {
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
+}
+
+// Stage `total` packed words: word idx covers pixels (y0 + idx / wpr, x0 + 4 * (idx % wpr) .. +3) of `frame`,
+// zero where that leaves the frame; dst(row, w) gives the shared-memory word index.  Loads of kStageUnroll
+// words are issued before the first conversion so that a thread keeps 16 pixel loads in flight.  VEC: x0, W
+// and the frame base are multiples of 16 bytes, so 16-byte groups are loaded whole (never straddle an edge).
+template <bool VEC, typename T, typename Dst>
+__device__ __forceinline__ void stage_words(const T *frame, int H, int W, int y0, int x0, int total, int wpr,
+                                            FastDiv d_wpr, U8Check &chk, unsigned *smem, Dst dst) {
+    constexpr int V = 16 / (int)sizeof(T);                                    // elements per 16-byte group
+    for (int base = threadIdx.x; base < total; base += kMeThreads * kStageUnroll) {
+        T v[kStageUnroll][4];
+        int out[kStageUnroll];
+#pragma unroll
+        for (int u = 0; u < kStageUnroll; ++u) {
+            const int idx = base + u * kMeThreads;
+            const int row = d_wpr.div(idx), w = idx - row * wpr;
+            const int gy = y0 + row, gx = x0 + 4 * w;
+            const bool rok = idx < total && (unsigned)gy < (unsigned)H;
+            const T *p = frame + (gy * W + gx);                               // H * W < 2^31 (checked by the launcher)
+            out[u] = idx < total ? dst(row, w) : -1;
+            if (VEC) {
+#pragma unroll
+                for (int k = 0; k < 4; k += V) {
+                    T t[V];
+#pragma unroll
+                    for (int j = 0; j < V; ++j) t[j] = (T)0;
+                    if (rok && (unsigned)(gx + k) < (unsigned)W) ldg16(p + k, t);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) v[u][k + j] = t[j];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[u][k] = (rok && (unsigned)(gx + k) < (unsigned)W) ? __ldg(p + k) : (T)0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kStageUnroll; ++u) {
+            const unsigned b0 = to_u8(v[u][0], chk), b1 = to_u8(v[u][1], chk), b2 = to_u8(v[u][2], chk), b3 = to_u8(v[u][3], chk);
+            if (out[u] >= 0) smem[out[u]] = pack_bytes(b0, b1, b2, b3);
+        }
+    }
+}
+
+template <typename T, int G>
 __global__ void __launch_bounds__(kMeThreads, 3) k_me_int(const MeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned *s_win = reinterpret_cast<unsigned *>(smem_raw);                 // [R][P/4] words
-    unsigned *s_cur = reinterpret_cast<unsigned *>(smem_raw + a.cur_off);     // [tby*tbx][8 rows][2 words]
+    unsigned *s_u = reinterpret_cast<unsigned *>(smem_raw);                   // [R][P4]
+    unsigned *s_hs = reinterpret_cast<unsigned *>(smem_raw + a.hs_off);       // [8*nseg+7][P4]
+    unsigned *s_b = reinterpret_cast<unsigned *>(smem_raw + a.b_off);         // [R][pw]
+    unsigned *s_cur = reinterpret_cast<unsigned *>(smem_raw + a.cur_off);     // [tby*tbx][kCurPitch]
     __shared__ unsigned long long s_best[64];
+    __shared__ unsigned s_c2[64];
     __shared__ int s_bad;
     const MeTile tl = me_tile(a);
     const T *ref = (const T *)a.ref + tl.frame * a.ref_fs;
     const T *cur = (const T *)a.cur + tl.frame * a.cur_fs;
-    const int sr = a.sr, span = a.span;
+    const int sr = a.sr, span = a.span, P4 = a.P, pw = a.pw, R = a.R;
+    const int H = (int)a.H, W = (int)a.W;
     const int nblk = tl.nby * tl.nbx;
+    const int tid = threadIdx.x;
+    const int last_col = tl.nbx != a.tbx;
+    const FastDiv d_nbx(a.m_nbx[last_col]);
 
-    if (threadIdx.x < 64) s_best[threadIdx.x] = ~0ull;
-    if (threadIdx.x == 0) s_bad = 0;
-    bool bad = false;
-    const int pw = a.P >> 2, rows_used = 8 * tl.nby + 2 * sr;
-    for (int idx = threadIdx.x; idx < a.R * pw; idx += blockDim.x) {
-        const int row = idx / pw, w = idx - row * pw;
-        const int64_t gy = (int64_t)8 * tl.by0 - sr + row, gx = (int64_t)8 * tl.bx0 - sr + 4 * w;
-        s_win[idx] = pack4(ref, gy * a.W, gx, a.W, row < rows_used && gy >= 0 && gy < a.H && 4 * w < a.Wc, bad);
-    }
-    const int cww = 2 * tl.nbx;                                               // words per current row
-    for (int idx = threadIdx.x; idx < 8 * tl.nby * cww; idx += blockDim.x) {
-        const int row = idx / cww, w = idx - row * cww;
-        const int64_t gy = (int64_t)8 * tl.by0 + row;
-        s_cur[((row >> 3) * a.tbx + (w >> 1)) * 16 + (row & 7) * 2 + (w & 1)] =
-            pack4(cur, gy * a.W, (int64_t)8 * tl.bx0 + 4 * w, a.W, true, bad);
+    if (tid < 64) s_best[tid] = ~0ull;
+    if (tid == 0) s_bad = 0;
+
+    // ---- phase A: float frames -> packed bytes (window with halo, current blocks).  Rows / words past
+    //      the part of the window this tile can use stay unwritten: only discarded candidates see them ----
+    {
+        U8Check chk;
+        const int rows = min(R, 8 * tl.nby + 2 * sr);
+        const int cww = 2 * tl.nbx;                                           // words per current row
+        auto dst_ref = [&](int row, int w) { return row * pw + w; };
+        auto dst_cur = [&](int row, int w) { return ((row >> 3) * a.tbx + (w >> 1)) * kCurPitch + (row & 7) * 2 + (w & 1); };
+        if (a.vec) {
+            stage_words<true>(ref, H, W, 8 * tl.by0 - sr, 8 * tl.bx0 - sr, rows * a.pwl, a.pwl, FastDiv(a.m_pwl), chk, s_b, dst_ref);
+            stage_words<true>(cur, H, W, 8 * tl.by0, 8 * tl.bx0, 8 * tl.nby * cww, cww, FastDiv(a.m_cww[last_col]), chk, s_cur, dst_cur);
+        } else {
+            stage_words<false>(ref, H, W, 8 * tl.by0 - sr, 8 * tl.bx0 - sr, rows * a.pwl, a.pwl, FastDiv(a.m_pwl), chk, s_b, dst_ref);
+            stage_words<false>(cur, H, W, 8 * tl.by0, 8 * tl.bx0, 8 * tl.nby * cww, cww, FastDiv(a.m_cww[last_col]), chk, s_cur, dst_cur);
+        }
+        if (a.check && __any_sync(0xffffffffu, chk.bad()) && (tid & 31) == 0) s_bad = 1;
     }
     __syncthreads();
-    if (a.check) {
-        if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) s_bad = 1;
-        __syncthreads();
-        if (s_bad) {                                                          // not an integer frame: leave it to k_me_exact
-            if (threadIdx.x == 0) atomicOr(a.flag, 1);
-            return;
-        }
+    if (a.check && s_bad) {                                                   // not an integer frame: leave it to k_me_exact
+        if (tid == 0) atomicOr(a.flag, 1);
+        return;
     }
 
+    // ---- phase B: unaligned-word view U and horizontal sums of squares H; sum(c^2) per block ----
+    {
+        const int q4 = P4 >> 2;
+        const FastDiv d_q4(a.m_q4);
+        for (int idx = tid; idx < R * q4; idx += kMeThreads) {
+            const int row = d_q4.div(idx), w = idx - row * q4;
+            const unsigned *bp = s_b + row * pw + w;                          // pw >= q4 + 2: no guards
+            const unsigned w0 = bp[0], w1 = bp[1], w2 = bp[2];
+            uint4 u, h;
+            u.x = w0;
+            u.y = __funnelshift_r(w0, w1, 8);
+            u.z = __funnelshift_r(w0, w1, 16);
+            u.w = __funnelshift_r(w0, w1, 24);
+            const unsigned v1 = __funnelshift_r(w1, w2, 8), v2 = __funnelshift_r(w1, w2, 16), v3 = __funnelshift_r(w1, w2, 24);
+            h.x = __dp4a(u.x, u.x, __dp4a(w1, w1, 0u));
+            h.y = __dp4a(u.y, u.y, __dp4a(v1, v1, 0u));
+            h.z = __dp4a(u.z, u.z, __dp4a(v2, v2, 0u));
+            h.w = __dp4a(u.w, u.w, __dp4a(v3, v3, 0u));
+            *reinterpret_cast<uint4 *>(s_u + idx * 4) = u;                    // == row * P4 + 4 * w
+            *reinterpret_cast<uint4 *>(s_hs + idx * 4) = h;
+        }
+        if (tid < nblk) {
+            const int brow = d_nbx.div(tid), b = tid - brow * tl.nbx;
+            const unsigned *cb = s_cur + (brow * a.tbx + b) * kCurPitch;
+            unsigned c2 = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) c2 = __dp4a(cb[i], cb[i], c2);
+            s_c2[tid] = c2;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase C: S[y][x] = sum_{i<8} H[y+i][x], in place.  An item = 8 output rows of one column;
+    //      items are ordered by rows, so what a round overwrites is never read by a later round.  HS has
+    //      8*nseg+7 rows: the tail rows hold garbage and only feed S rows no candidate uses ----
+    {
+        const int total = a.nseg * P4;
+        for (int base = 0; base < total; base += kMeThreads) {
+            const int item = base + tid;
+            const bool active = item < total;
+            const int seg = active ? FastDiv(a.m_p4).div(item) : 0;
+            unsigned *hp = s_hs + item + 7 * seg * P4;                        // == (8 * seg) * P4 + x
+            unsigned s[8];
+            if (active) {
+                unsigned h[15];
+#pragma unroll
+                for (int i = 0; i < 15; ++i) h[i] = hp[i * P4];
+                s[0] = ((h[0] + h[1]) + (h[2] + h[3])) + ((h[4] + h[5]) + (h[6] + h[7]));
+#pragma unroll
+                for (int j = 1; j < 8; ++j) s[j] = s[j - 1] + h[j + 7] - h[j - 1];
+            }
+            __syncthreads();
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) hp[j * P4] = s[j];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- main loop ------------------------------------------------------------------------------
     const bool small = span * span <= 512;                                    // ssd < 2^22, index < 2^9: key fits 32 bits
     unsigned *s_best32 = reinterpret_cast<unsigned *>(s_best);
     const int total = nblk * a.ntpb;
-    const FastDiv d_ntpb((unsigned)a.ntpb), d_span((unsigned)span), d_nbx((unsigned)tl.nbx);
-    for (int task = threadIdx.x; task < total; task += blockDim.x) {
+    const FastDiv d_ntpb(a.m_ntpb), d_span(a.m_span);
+    for (int task = tid; task < total; task += kMeThreads) {
         const int blk = d_ntpb.div(task), rem = task - blk * a.ntpb;
         const int g = d_span.div(rem), dxi = rem - g * span;
         const int brow = d_nbx.div(blk), b = blk - brow * tl.nbx;
-        const int dy0 = g * kMeG - sr;
         const int gx = 8 * (tl.bx0 + b) + dxi - sr;
-        if (gx < 0 || gx + 8 > a.W) continue;
-        const uint2 *cb = reinterpret_cast<const uint2 *>(s_cur + (brow * a.tbx + b) * 16);
+        if (gx < 0 || gx + 8 > W) continue;                                   // motion.py:41-43 (x bound)
+        const uint2 *cb = reinterpret_cast<const uint2 *>(s_cur + (brow * a.tbx + b) * kCurPitch);
         uint2 c[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) c[i] = cb[i];
-        unsigned acc[kMeG];
+        unsigned acc[G];
 #pragma unroll
-        for (int gg = 0; gg < kMeG; ++gg) acc[gg] = 0u;
-        const int colb = 8 * b + dxi;                                         // byte column in the window
-        const unsigned *wrow = s_win + (8 * brow + dy0 + sr) * pw + (colb >> 2);
-        const int sh = (colb & 3) * 8;
+        for (int gg = 0; gg < G; ++gg) acc[gg] = 0u;
+        const int off = (8 * brow + g * G) * P4 + 8 * b + dxi;                // window row of dy0, byte column of dx
+        const unsigned *up = s_u + off;
 #pragma unroll
-        for (int rr = 0; rr < kMeG + 7; ++rr) {
-            const unsigned *w = wrow + rr * pw;
-            const unsigned w0 = w[0], w1 = w[1], w2 = w[2];
-            const unsigned r0 = __funnelshift_r(w0, w1, sh), r1 = __funnelshift_r(w1, w2, sh);
+        for (int rr = 0; rr < G + 7; ++rr) {
+            const unsigned r0 = up[rr * P4], r1 = up[rr * P4 + 4];
 #pragma unroll
-            for (int gg = 0; gg < kMeG; ++gg) {
-                const int i = rr - gg;
+            for (int gg = 0; gg < G; ++gg) {
+                const int i = rr - gg;                                        // row of the block for candidate gg
                 if (i >= 0 && i < 8) {
-                    const unsigned d0 = __vabsdiffu4(c[i].x, r0), d1 = __vabsdiffu4(c[i].y, r1);
-                    acc[gg] = __dp4a(d0, d0, acc[gg]);
-                    acc[gg] = __dp4a(d1, d1, acc[gg]);
+                    acc[gg] = __dp4a(c[i].x, r0, acc[gg]);
+                    acc[gg] = __dp4a(c[i].y, r1, acc[gg]);
                 }
             }
         }
-        unsigned long long key = ~0ull;
-        const int64_t gy0 = (int64_t)8 * (tl.by0 + brow);
+        // candidates gg in [lo, hi) are inside the search range and the frame (motion.py:41-43, y bound)
+        const int gyb = 8 * (tl.by0 + brow) - sr + g * G;
+        const int lo = max(0, -gyb), hi = min(min(G, span - g * G), H - 7 - gyb);
+        const unsigned valid = hi > lo ? (0xffffffffu >> (32 - hi)) & (0xffffffffu << lo) : 0u;
+        const unsigned c2 = s_c2[blk];
+        const unsigned *sp = s_hs + off;
+        const unsigned idx0 = (unsigned)(g * G * span + dxi);                 // motion.py:55
+        unsigned best_ssd = 0xffffffffu, best_idx = 0;
 #pragma unroll
-        for (int gg = 0; gg < kMeG; ++gg) {
-            const int dy = dy0 + gg;
-            const int64_t gy = gy0 + dy;
-            if (dy <= sr && gy >= 0 && gy + 8 <= a.H) {
-                const unsigned long long k = ((unsigned long long)acc[gg] << 32) | (unsigned)((dy + sr) * span + dxi);
-                key = k < key ? k : key;
-            }
+        for (int gg = 0; gg < G; ++gg) {
+            const unsigned ssd = c2 + sp[gg * P4] - 2u * acc[gg];
+            if (((valid >> gg) & 1u) && ssd < best_ssd) { best_ssd = ssd; best_idx = idx0 + gg * span; }
         }
-        if (key != ~0ull) {
-            if (small) atomicMin(s_best32 + blk, ((unsigned)(key >> 32) << 9) | (unsigned)(key & 511u));
-            else atomicMin(s_best + blk, key);
+        if (valid) {
+            if (small) atomicMin(s_best32 + blk, (best_ssd << 9) | best_idx);
+            else atomicMin(s_best + blk, ((unsigned long long)best_ssd << 32) | best_idx);
         }
     }
     __syncthreads();
-    if ((int)threadIdx.x < nblk) {
-        const int blk = threadIdx.x, brow = blk / tl.nbx, b = blk - brow * tl.nbx;
+    if (tid < nblk) {
+        const int blk = tid, brow = d_nbx.div(blk), b = blk - brow * tl.nbx;
         const int64_t idx = small ? (int64_t)(s_best32[blk] & 511u) : (int64_t)(s_best[blk] & 0xffffffffull);
         a.mv[(tl.frame * a.Hp + tl.by0 + brow) * (int64_t)a.Wp + tl.bx0 + b] = idx;
     }
@@ -375,6 +507,25 @@ static size_t me_geometry(MeArgs &a, int64_t n_frames, int64_t H, int64_t W, int
     return smem;
 }
 
+// launch over a 2-D grid (x = tile, y = frame), in chunks of at most 65535 frames
+template <typename K>
+static cudaError_t me_launch_chunks(K kernel, MeArgs a, int elem, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int64_t tiles = (int64_t)a.tiles_y * a.tiles_x;
+    if (tiles == 0 || a.n == 0) return cudaSuccess;
+    if (tiles > 2147483647LL) return cudaErrorInvalidValue;
+    const int64_t n = a.n;
+    for (int64_t f0 = 0; f0 < n; f0 += 65535) {
+        const int64_t nf = n - f0 < 65535 ? n - f0 : 65535;
+        kernel<<<dim3((unsigned)tiles, (unsigned)nf), kMeThreads, smem, st>>>(a);
+        a.ref = (const char *)a.ref + 65535 * a.ref_fs * elem;
+        a.cur = (const char *)a.cur + 65535 * a.cur_fs * elem;
+        a.mv += 65535 * (int64_t)a.Hp * a.Wp;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_me_exact(int device, cudaStream_t st, const void *ref, const void *cur, bool f32, int64_t n,
                             int64_t H, int64_t W, int64_t ref_fs, int64_t cur_fs, int sr, int64_t *mv,
                             int *flag, int run_if) {
@@ -383,19 +534,53 @@ cudaError_t launch_me_exact(int device, cudaStream_t st, const void *ref, const 
     a.flag = flag; a.run_if = run_if; a.check = 0;
     const size_t smem = me_geometry(a, n, H, W, sr, f32 ? 4 : 8, 32, 3, 100 * 1024, 4 * 2 * (int64_t)sm_count(device));
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    const int64_t ctas = n * a.tiles_y * (int64_t)a.tiles_x;
-    if (ctas == 0) return cudaSuccess;
-    if (ctas > 2147483647LL) return cudaErrorInvalidValue;
-    cudaError_t e;
-    if (f32) {
-        if ((e = cudaFuncSetAttribute(k_me_exact<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k_me_exact<float><<<(unsigned)ctas, kMeThreads, smem, st>>>(a);
-    } else {
-        if ((e = cudaFuncSetAttribute(k_me_exact<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k_me_exact<double><<<(unsigned)ctas, kMeThreads, smem, st>>>(a);
-    }
     (void)device;
-    return cudaGetLastError();
+    if (f32) return me_launch_chunks(k_me_exact<float>, a, 4, smem, st);
+    return me_launch_chunks(k_me_exact<double>, a, 8, smem, st);
+}
+
+// integer kernel: candidates per task for a search span (least padding of the last dy-group, then larger)
+static int me_int_group(int span) {
+    static const int gs[] = {11, 9, 5, 3};
+    int best = 3, waste = 1 << 30;
+    for (int g : gs) {
+        const int w = (span + g - 1) / g * g - span;
+        if (w < waste) { waste = w; best = g; }
+    }
+    return best;
+}
+
+static size_t me_int_geometry(MeArgs &a, int G, int64_t n_frames, int64_t H, int64_t W, int sr, size_t budget,
+                              int64_t min_ctas) {
+    a.Hp = (int)(H / 8); a.Wp = (int)(W / 8); a.sr = sr; a.span = 2 * sr + 1;
+    a.ngrp = (a.span + G - 1) / G;
+    a.ntpb = a.ngrp * a.span;
+    static const int shapes[][2] = {{4, 16}, {2, 16}, {2, 8}, {1, 8}, {1, 4}, {1, 2}, {1, 1}};
+    size_t smem = 0;
+    for (auto &s : shapes) {
+        a.tby = s[0]; a.tbx = s[1];
+        const int64_t ctas = n_frames * ((a.Hp + a.tby - 1) / a.tby) * (int64_t)((a.Wp + a.tbx - 1) / a.tbx);
+        if (ctas < min_ctas && !(s[0] == 1 && s[1] == 1) && s[0] * s[1] > 8) continue;
+        a.R = 8 * (a.tby - 1) + a.ngrp * G + 7;                    // covers the last (padded) dy-group
+        a.Wc = 8 * a.tbx + 2 * sr;
+        a.P = (a.Wc + 3) & ~3;                                     // U / HS pitch in words (one per byte column)
+        a.pw = a.P / 4 + 2;                                        // packed words per row, two zero words at the end
+        a.pwl = (a.Wc + 3) / 4;
+        a.nseg = (a.R - 7 + 7) / 8;                                // S has R - 7 rows
+        a.hs_off = a.R * a.P * 4;
+        a.b_off = a.hs_off + (8 * a.nseg + 7) * a.P * 4;
+        a.cur_off = (a.b_off + a.R * a.pw * 4 + 15) & ~15;
+        smem = (size_t)a.cur_off + (size_t)a.tby * a.tbx * kCurPitch * 4;
+        if (smem <= budget) break;
+    }
+    a.tiles_y = (a.Hp + a.tby - 1) / a.tby;
+    a.tiles_x = (a.Wp + a.tbx - 1) / a.tbx;
+    const int last_nbx = a.Wp - (a.tiles_x - 1) * a.tbx;
+    a.m_pwl = fastdiv_magic(a.pwl); a.m_q4 = fastdiv_magic(a.P / 4); a.m_p4 = fastdiv_magic(a.P);
+    a.m_ntpb = fastdiv_magic(a.ntpb); a.m_span = fastdiv_magic(a.span);
+    a.m_nbx[0] = fastdiv_magic(a.tbx); a.m_nbx[1] = fastdiv_magic(last_nbx);
+    a.m_cww[0] = fastdiv_magic(2 * a.tbx); a.m_cww[1] = fastdiv_magic(2 * last_nbx);
+    return smem;
 }
 
 cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const void *cur, bool f32, int64_t n,
@@ -404,23 +589,25 @@ cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const vo
     MeArgs a;
     a.ref = ref; a.cur = cur; a.n = n; a.H = H; a.W = W; a.ref_fs = ref_fs; a.cur_fs = cur_fs; a.mv = mv;
     a.flag = flag; a.run_if = 0; a.check = check;
-    // pitch in bytes: multiple of 4 plus 4 (the funnel shift reads one word past the last column)
-    const size_t smem = me_geometry(a, n, H, W, sr, 1, 4, 4, 64 * 1024, 4 * 3 * (int64_t)sm_count(device));
+    const int G = me_int_group(2 * sr + 1);
+    const size_t smem = me_int_geometry(a, G, n, H, W, sr, 200 * 1024, 4 * 3 * (int64_t)sm_count(device));
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    const int64_t ctas = n * a.tiles_y * (int64_t)a.tiles_x;
-    if (ctas == 0) return cudaSuccess;
-    if (ctas > 2147483647LL) return cudaErrorInvalidValue;
+    if (H * W >= 2147483647LL) return cudaErrorInvalidValue;                  // 32-bit pixel coordinates inside a frame
+    const int elem = f32 ? 4 : 8;
+    a.vec = sr % (16 / elem) == 0 && ((uintptr_t)ref & 15) == 0 && ((uintptr_t)cur & 15) == 0 &&
+            (ref_fs * elem) % 16 == 0 && (cur_fs * elem) % 16 == 0;            // W is a multiple of 8
     cudaError_t e;
     if (check && (e = cudaMemsetAsync(flag, 0, sizeof(int), st)) != cudaSuccess) return e;
-    if (f32) {
-        if ((e = cudaFuncSetAttribute(k_me_int<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k_me_int<float><<<(unsigned)ctas, kMeThreads, smem, st>>>(a);
-    } else {
-        if ((e = cudaFuncSetAttribute(k_me_int<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k_me_int<double><<<(unsigned)ctas, kMeThreads, smem, st>>>(a);
+    switch (G * 2 + (f32 ? 1 : 0)) {
+        case 22: return me_launch_chunks(k_me_int<double, 11>, a, 8, smem, st);
+        case 23: return me_launch_chunks(k_me_int<float, 11>, a, 4, smem, st);
+        case 18: return me_launch_chunks(k_me_int<double, 9>, a, 8, smem, st);
+        case 19: return me_launch_chunks(k_me_int<float, 9>, a, 4, smem, st);
+        case 10: return me_launch_chunks(k_me_int<double, 5>, a, 8, smem, st);
+        case 11: return me_launch_chunks(k_me_int<float, 5>, a, 4, smem, st);
+        case 6: return me_launch_chunks(k_me_int<double, 3>, a, 8, smem, st);
+        default: return me_launch_chunks(k_me_int<float, 3>, a, 4, smem, st);
     }
-    (void)device;
-    return cudaGetLastError();
 }
 
 cudaError_t launch_mc(int device, cudaStream_t st, const void *ref, int elem_size, int64_t n, int64_t H, int64_t W,

@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""Developer aid: integer-kernel vs exact-kernel agreement over many shapes / search ranges, then ME timings
+(+-4 on 32 x 1080p, +-16 on 4K).   python tools/me_dev.py [--time-only]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ivclab_b200 as ivc  # noqa: E402
+from bench_configs import luma_seq, timed  # noqa: E402
+
+
+def main():
+    if "--time-only" not in sys.argv:
+        g = torch.Generator(device="cuda").manual_seed(1)
+        bad = 0
+        for (n, H, W) in [(1, 8, 8), (2, 16, 24), (3, 40, 72), (1, 144, 176), (2, 136, 264), (1, 264, 1032)]:
+            for sr in (1, 2, 3, 4, 5, 6, 7, 8, 11, 16, 20):
+                for kind in ("noise", "flat", "smooth"):
+                    if kind == "noise":
+                        r = torch.randint(0, 256, (n, H, W), generator=g, device="cuda").double()
+                        c = torch.randint(0, 256, (n, H, W), generator=g, device="cuda").double()
+                    elif kind == "flat":
+                        r = torch.full((n, H, W), 255.0, device="cuda", dtype=torch.float64)
+                        c = torch.zeros((n, H, W), device="cuda", dtype=torch.float64)
+                    else:
+                        s = luma_seq(n + 1, H, W, 7 + sr, shift=min(sr, 3))
+                        r, c = s[:-1].contiguous(), s[1:].contiguous()
+                    a = ivc.PFrameBlockCoder(1.0, sr, me_mode="int").estimate(r, c)
+                    b = ivc.PFrameBlockCoder(1.0, sr, me_mode="exact").estimate(r, c)
+                    if not torch.equal(a, b):
+                        bad += 1
+                        print("MISMATCH", n, H, W, sr, kind, int((a != b).sum()), "of", a.numel())
+        print("parity sweep done, mismatching cases:", bad)
+    s = luma_seq(33, 1080, 1920, 5000)
+    for mode in ("int", "auto", "exact"):
+        pc = ivc.PFrameBlockCoder(1.0, 4, me_mode=mode)
+        t = timed(lambda: pc.estimate(s[:-1], s[1:]), 10)
+        print(f"1080p x32 sr=4 {mode}: {t:.3f} ms  {32 * 1080 * 1920 / t / 1e3:.0f} Mpixel/s")
+    pc = ivc.PFrameBlockCoder(1.0, 4, me_mode="auto")
+    t = timed(lambda: pc.estimate(s[:1], s[1:2]), 20)
+    print(f"1080p x1 sr=4 auto: {t * 1e3:.1f} us")
+    for sr in (8, 16):
+        pc = ivc.PFrameBlockCoder(1.0, sr, me_mode="int")
+        t = timed(lambda: pc.estimate(s[:-1], s[1:]), 5)
+        print(f"1080p x32 sr={sr} int: {t:.3f} ms  {32 * 1080 * 1920 / t / 1e3:.0f} Mpixel/s")
+    del s
+    s4 = luma_seq(5, 2160, 3840, 4000, shift=12)
+    for mode in ("int", "exact"):
+        pc = ivc.PFrameBlockCoder(1.0, 16, me_mode=mode)
+        t = timed(lambda: pc.estimate(s4[:-1], s4[1:]), 3, warm=1)
+        print(f"4K x4 sr=16 {mode}: {t / 4:.3f} ms/frame  {4 * 2160 * 3840 / t / 1e3:.0f} Mpixel/s")
+
+
+if __name__ == "__main__":
+    main()
