@@ -281,7 +281,9 @@ __device__ __forceinline__ void stage_words(const T *frame, int H, int W, int y0
     }
 }
 
-template <typename T, int G>
+// PC: compile-time U / HS pitch (0 = take it from the arguments).  With a constant pitch every row offset of
+// the unrolled loops is an immediate, which keeps address IMADs off the pipe the dp4a instructions need.
+template <typename T, int G, int PC>
 __global__ void __launch_bounds__(kMeThreads, 3) k_me_int(const MeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned *s_u = reinterpret_cast<unsigned *>(smem_raw);                   // [R][P4]
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(kMeThreads, 3) k_me_int(const MeArgs a) {
     const MeTile tl = me_tile(a);
     const T *ref = (const T *)a.ref + tl.frame * a.ref_fs;
     const T *cur = (const T *)a.cur + tl.frame * a.cur_fs;
-    const int sr = a.sr, span = a.span, P4 = a.P, pw = a.pw, R = a.R;
+    const int sr = a.sr, span = a.span, P4 = PC ? PC : a.P, pw = PC ? PC / 4 + 2 : a.pw, R = a.R;
     const int H = (int)a.H, W = (int)a.W;
     const int nblk = tl.nby * tl.nbx;
     const int tid = threadIdx.x;
@@ -550,7 +552,7 @@ static int me_int_group(int span) {
     return best;
 }
 
-static size_t me_int_geometry(MeArgs &a, int G, int64_t n_frames, int64_t H, int64_t W, int sr, size_t budget,
+static size_t me_int_geometry(MeArgs &a, int G, int pitch, int64_t n_frames, int64_t H, int64_t W, int sr, size_t budget,
                               int64_t min_ctas) {
     a.Hp = (int)(H / 8); a.Wp = (int)(W / 8); a.sr = sr; a.span = 2 * sr + 1;
     a.ngrp = (a.span + G - 1) / G;
@@ -563,7 +565,7 @@ static size_t me_int_geometry(MeArgs &a, int G, int64_t n_frames, int64_t H, int
         if (ctas < min_ctas && !(s[0] == 1 && s[1] == 1) && s[0] * s[1] > 8) continue;
         a.R = 8 * (a.tby - 1) + a.ngrp * G + 7;                    // covers the last (padded) dy-group
         a.Wc = 8 * a.tbx + 2 * sr;
-        a.P = (a.Wc + 3) & ~3;                                     // U / HS pitch in words (one per byte column)
+        a.P = pitch ? pitch : (a.Wc + 3) & ~3;                     // U / HS pitch in words (one per byte column)
         a.pw = a.P / 4 + 2;                                        // packed words per row, two zero words at the end
         a.pwl = (a.Wc + 3) / 4;
         a.nseg = (a.R - 7 + 7) / 8;                                // S has R - 7 rows
@@ -590,7 +592,9 @@ cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const vo
     a.ref = ref; a.cur = cur; a.n = n; a.H = H; a.W = W; a.ref_fs = ref_fs; a.cur_fs = cur_fs; a.mv = mv;
     a.flag = flag; a.run_if = 0; a.check = check;
     const int G = me_int_group(2 * sr + 1);
-    const size_t smem = me_int_geometry(a, G, n, H, W, sr, 200 * 1024, 4 * 3 * (int64_t)sm_count(device));
+    // common cases get a compile-time pitch: 16-block-wide tiles at +-4 (136) and up to +-16 (160)
+    const int pitch = (G == 9 && sr <= 4) ? 136 : (G == 11 && sr <= 16) ? 160 : 0;
+    const size_t smem = me_int_geometry(a, G, pitch, n, H, W, sr, 200 * 1024, 4 * 3 * (int64_t)sm_count(device));
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     if (H * W >= 2147483647LL) return cudaErrorInvalidValue;                  // 32-bit pixel coordinates inside a frame
     const int elem = f32 ? 4 : 8;
@@ -598,16 +602,18 @@ cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const vo
             (ref_fs * elem) % 16 == 0 && (cur_fs * elem) % 16 == 0;            // W is a multiple of 8
     cudaError_t e;
     if (check && (e = cudaMemsetAsync(flag, 0, sizeof(int), st)) != cudaSuccess) return e;
-    switch (G * 2 + (f32 ? 1 : 0)) {
-        case 22: return me_launch_chunks(k_me_int<double, 11>, a, 8, smem, st);
-        case 23: return me_launch_chunks(k_me_int<float, 11>, a, 4, smem, st);
-        case 18: return me_launch_chunks(k_me_int<double, 9>, a, 8, smem, st);
-        case 19: return me_launch_chunks(k_me_int<float, 9>, a, 4, smem, st);
-        case 10: return me_launch_chunks(k_me_int<double, 5>, a, 8, smem, st);
-        case 11: return me_launch_chunks(k_me_int<float, 5>, a, 4, smem, st);
-        case 6: return me_launch_chunks(k_me_int<double, 3>, a, 8, smem, st);
-        default: return me_launch_chunks(k_me_int<float, 3>, a, 4, smem, st);
-    }
+#define IVC_ME_INT_CASE(GG, PP)                                                                  \
+    if (G == GG && pitch == PP)                                                                  \
+        return f32 ? me_launch_chunks(k_me_int<float, GG, PP>, a, 4, smem, st)                   \
+                   : me_launch_chunks(k_me_int<double, GG, PP>, a, 8, smem, st);
+    IVC_ME_INT_CASE(9, 136)
+    IVC_ME_INT_CASE(11, 160)
+    IVC_ME_INT_CASE(11, 0)
+    IVC_ME_INT_CASE(9, 0)
+    IVC_ME_INT_CASE(5, 0)
+    IVC_ME_INT_CASE(3, 0)
+#undef IVC_ME_INT_CASE
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_mc(int device, cudaStream_t st, const void *ref, int elem_size, int64_t n, int64_t H, int64_t W,
