@@ -228,6 +228,7 @@ struct FastDiv {
 };
 static unsigned fastdiv_magic(unsigned d) { return d > 1 ? 0xFFFFFFFFu / d + 1u : 0u; }
 
+constexpr int kMeIntMaxThreads = 512;   // integer kernel, constant-pitch variants: 256..512 threads per CTA (chosen by the launcher), <= 64 registers
 constexpr int kCurPitch = 18;      // words per current block in shared memory (16 + 2: blocks on distinct banks)
 constexpr int kStageUnroll = 4;    // packed words (16 pixel loads) in flight per thread while staging
 
@@ -243,48 +244,63 @@ __device__ __forceinline__ void ldg16(const float *p, float (&v)[4]) {
 // zero where that leaves the frame; dst(row, w) gives the shared-memory word index.  Loads of kStageUnroll
 // words are issued before the first conversion so that a thread keeps 16 pixel loads in flight.  VEC: x0, W
 // and the frame base are multiples of 16 bytes, so 16-byte groups are loaded whole (never straddle an edge).
+template <bool VEC, int UNR, typename T, typename Dst>
+__device__ __forceinline__ void stage_batch(const T *frame, int H, int W, int y0, int x0, int base, int total, int wpr,
+                                            FastDiv d_wpr, U8Check &chk, unsigned *smem, Dst dst) {
+    constexpr int V = 16 / (int)sizeof(T);                                    // elements per 16-byte group
+    const int nthr = blockDim.x;
+    T v[UNR][4];
+    int out[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+        const int idx = base + u * nthr;
+        const int row = d_wpr.div(idx), w = idx - row * wpr;
+        const int gy = y0 + row, gx = x0 + 4 * w;
+        const bool rok = idx < total && (unsigned)gy < (unsigned)H;
+        const T *p = frame + (gy * W + gx);                                   // H * W < 2^31 (checked by the launcher)
+        out[u] = idx < total ? dst(row, w) : -1;
+        if (VEC) {
+#pragma unroll
+            for (int k = 0; k < 4; k += V) {
+                T t[V];
+#pragma unroll
+                for (int j = 0; j < V; ++j) t[j] = (T)0;
+                if (rok && (unsigned)(gx + k) < (unsigned)W) ldg16(p + k, t);
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[u][k + j] = t[j];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[u][k] = (rok && (unsigned)(gx + k) < (unsigned)W) ? __ldg(p + k) : (T)0;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+        const unsigned b0 = to_u8(v[u][0], chk), b1 = to_u8(v[u][1], chk), b2 = to_u8(v[u][2], chk), b3 = to_u8(v[u][3], chk);
+        if (out[u] >= 0) smem[out[u]] = pack_bytes(b0, b1, b2, b3);
+    }
+}
+
+// Stage `total` packed words: word idx covers pixels (y0 + idx / wpr, x0 + 4 * (idx % wpr) .. +3) of `frame`,
+// zero where that leaves the frame; dst(row, w) gives the shared-memory word index.  Batches of
+// kStageUnroll words per thread issue all their loads before the first conversion (16 pixel loads in flight
+// per thread); what is left after the full batches goes in batches of one.  VEC: x0, W and the frame base
+// are multiples of 16 bytes, so 16-byte groups are loaded whole (they never straddle a frame edge).
 template <bool VEC, typename T, typename Dst>
 __device__ __forceinline__ void stage_words(const T *frame, int H, int W, int y0, int x0, int total, int wpr,
                                             FastDiv d_wpr, U8Check &chk, unsigned *smem, Dst dst) {
-    constexpr int V = 16 / (int)sizeof(T);                                    // elements per 16-byte group
-    for (int base = threadIdx.x; base < total; base += kMeThreads * kStageUnroll) {
-        T v[kStageUnroll][4];
-        int out[kStageUnroll];
-#pragma unroll
-        for (int u = 0; u < kStageUnroll; ++u) {
-            const int idx = base + u * kMeThreads;
-            const int row = d_wpr.div(idx), w = idx - row * wpr;
-            const int gy = y0 + row, gx = x0 + 4 * w;
-            const bool rok = idx < total && (unsigned)gy < (unsigned)H;
-            const T *p = frame + (gy * W + gx);                               // H * W < 2^31 (checked by the launcher)
-            out[u] = idx < total ? dst(row, w) : -1;
-            if (VEC) {
-#pragma unroll
-                for (int k = 0; k < 4; k += V) {
-                    T t[V];
-#pragma unroll
-                    for (int j = 0; j < V; ++j) t[j] = (T)0;
-                    if (rok && (unsigned)(gx + k) < (unsigned)W) ldg16(p + k, t);
-#pragma unroll
-                    for (int j = 0; j < V; ++j) v[u][k + j] = t[j];
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) v[u][k] = (rok && (unsigned)(gx + k) < (unsigned)W) ? __ldg(p + k) : (T)0;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kStageUnroll; ++u) {
-            const unsigned b0 = to_u8(v[u][0], chk), b1 = to_u8(v[u][1], chk), b2 = to_u8(v[u][2], chk), b3 = to_u8(v[u][3], chk);
-            if (out[u] >= 0) smem[out[u]] = pack_bytes(b0, b1, b2, b3);
-        }
-    }
+    const int nthr = blockDim.x;
+    int base = threadIdx.x;
+    for (; base - (int)threadIdx.x + kStageUnroll * nthr <= total; base += kStageUnroll * nthr)
+        stage_batch<VEC, kStageUnroll>(frame, H, W, y0, x0, base, total, wpr, d_wpr, chk, smem, dst);
+    for (; base < total; base += nthr)
+        stage_batch<VEC, 1>(frame, H, W, y0, x0, base, total, wpr, d_wpr, chk, smem, dst);
 }
 
 // PC: compile-time U / HS pitch (0 = take it from the arguments).  With a constant pitch every row offset of
 // the unrolled loops is an immediate, which keeps address IMADs off the pipe the dp4a instructions need.
 template <typename T, int G, int PC>
-__global__ void __launch_bounds__(kMeThreads, 3) k_me_int(const MeArgs a) {
+__global__ void __launch_bounds__(PC ? kMeIntMaxThreads : kMeThreads, PC ? 2 : 3) k_me_int(const MeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned *s_u = reinterpret_cast<unsigned *>(smem_raw);                   // [R][P4]
     unsigned *s_hs = reinterpret_cast<unsigned *>(smem_raw + a.hs_off);       // [8*nseg+7][P4]
@@ -299,7 +315,7 @@ __global__ void __launch_bounds__(kMeThreads, 3) k_me_int(const MeArgs a) {
     const int sr = a.sr, span = a.span, P4 = PC ? PC : a.P, pw = PC ? PC / 4 + 2 : a.pw, R = a.R;
     const int H = (int)a.H, W = (int)a.W;
     const int nblk = tl.nby * tl.nbx;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, nthr = blockDim.x;
     const int last_col = tl.nbx != a.tbx;
     const FastDiv d_nbx(a.m_nbx[last_col]);
 
@@ -333,7 +349,7 @@ __global__ void __launch_bounds__(kMeThreads, 3) k_me_int(const MeArgs a) {
     {
         const int q4 = P4 >> 2;
         const FastDiv d_q4(a.m_q4);
-        for (int idx = tid; idx < R * q4; idx += kMeThreads) {
+        for (int idx = tid; idx < R * q4; idx += nthr) {
             const int row = d_q4.div(idx), w = idx - row * q4;
             const unsigned *bp = s_b + row * pw + w;                          // pw >= q4 + 2: no guards
             const unsigned w0 = bp[0], w1 = bp[1], w2 = bp[2];
@@ -356,7 +372,7 @@ __global__ void __launch_bounds__(kMeThreads, 3) k_me_int(const MeArgs a) {
             unsigned c2 = 0;
 #pragma unroll
             for (int i = 0; i < 16; ++i) c2 = __dp4a(cb[i], cb[i], c2);
-            s_c2[tid] = c2;
+            s_c2[tid] = c2 << 4;
         }
     }
     __syncthreads();
@@ -366,7 +382,7 @@ __global__ void __launch_bounds__(kMeThreads, 3) k_me_int(const MeArgs a) {
     //      8*nseg+7 rows: the tail rows hold garbage and only feed S rows no candidate uses ----
     {
         const int total = a.nseg * P4;
-        for (int base = 0; base < total; base += kMeThreads) {
+        for (int base = 0; base < total; base += nthr) {
             const int item = base + tid;
             const bool active = item < total;
             const int seg = active ? FastDiv(a.m_p4).div(item) : 0;
@@ -383,7 +399,7 @@ __global__ void __launch_bounds__(kMeThreads, 3) k_me_int(const MeArgs a) {
             __syncthreads();
             if (active) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) hp[j * P4] = s[j];
+                for (int j = 0; j < 8; ++j) hp[j * P4] = s[j] << 4;           // S * 16: room for the candidate number
             }
         }
     }
@@ -394,47 +410,66 @@ __global__ void __launch_bounds__(kMeThreads, 3) k_me_int(const MeArgs a) {
     unsigned *s_best32 = reinterpret_cast<unsigned *>(s_best);
     const int total = nblk * a.ntpb;
     const FastDiv d_ntpb(a.m_ntpb), d_span(a.m_span);
-    for (int task = tid; task < total; task += kMeThreads) {
-        const int blk = d_ntpb.div(task), rem = task - blk * a.ntpb;
+    // every warp runs the same number of rounds: lanes without a task (or whose dx leaves the frame) carry
+    // an empty result into the warp-level argmin, so that one lane per block issues the shared atomic
+    for (int tbase = tid & ~31; tbase < total; tbase += nthr) {
+        const int task = tbase + (tid & 31);
+        const int blk = d_ntpb.div(min(task, total - 1)), rem = task - blk * a.ntpb;
         const int g = d_span.div(rem), dxi = rem - g * span;
         const int brow = d_nbx.div(blk), b = blk - brow * tl.nbx;
         const int gx = 8 * (tl.bx0 + b) + dxi - sr;
-        if (gx < 0 || gx + 8 > W) continue;                                   // motion.py:41-43 (x bound)
-        const uint2 *cb = reinterpret_cast<const uint2 *>(s_cur + (brow * a.tbx + b) * kCurPitch);
-        uint2 c[8];
+        unsigned best_ssd = 0xffffffffu, best_idx = 0xffffffffu;
+        if (task < total && gx >= 0 && gx + 8 <= W) {                         // motion.py:41-43 (x bound)
+            const uint2 *cb = reinterpret_cast<const uint2 *>(s_cur + (brow * a.tbx + b) * kCurPitch);
+            uint2 c[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) c[i] = cb[i];
-        unsigned acc[G];
+            for (int i = 0; i < 8; ++i) c[i] = cb[i];
+            unsigned acc[G];
 #pragma unroll
-        for (int gg = 0; gg < G; ++gg) acc[gg] = 0u;
-        const int off = (8 * brow + g * G) * P4 + 8 * b + dxi;                // window row of dy0, byte column of dx
-        const unsigned *up = s_u + off;
+            for (int gg = 0; gg < G; ++gg) acc[gg] = 0u;
+            const int off = (8 * brow + g * G) * P4 + 8 * b + dxi;            // window row of dy0, byte column of dx
+            const unsigned *up = s_u + off;
 #pragma unroll
-        for (int rr = 0; rr < G + 7; ++rr) {
-            const unsigned r0 = up[rr * P4], r1 = up[rr * P4 + 4];
+            for (int rr = 0; rr < G + 7; ++rr) {
+                const unsigned r0 = up[rr * P4], r1 = up[rr * P4 + 4];
 #pragma unroll
-            for (int gg = 0; gg < G; ++gg) {
-                const int i = rr - gg;                                        // row of the block for candidate gg
-                if (i >= 0 && i < 8) {
-                    acc[gg] = __dp4a(c[i].x, r0, acc[gg]);
-                    acc[gg] = __dp4a(c[i].y, r1, acc[gg]);
+                for (int gg = 0; gg < G; ++gg) {
+                    const int i = rr - gg;                                    // row of the block for candidate gg
+                    if (i >= 0 && i < 8) {
+                        acc[gg] = __dp4a(c[i].x, r0, acc[gg]);
+                        acc[gg] = __dp4a(c[i].y, r1, acc[gg]);
+                    }
                 }
             }
-        }
-        // candidates gg in [lo, hi) are inside the search range and the frame (motion.py:41-43, y bound)
-        const int gyb = 8 * (tl.by0 + brow) - sr + g * G;
-        const int lo = max(0, -gyb), hi = min(min(G, span - g * G), H - 7 - gyb);
-        const unsigned valid = hi > lo ? (0xffffffffu >> (32 - hi)) & (0xffffffffu << lo) : 0u;
-        const unsigned c2 = s_c2[blk];
-        const unsigned *sp = s_hs + off;
-        const unsigned idx0 = (unsigned)(g * G * span + dxi);                 // motion.py:55
-        unsigned best_ssd = 0xffffffffu, best_idx = 0;
+            // key = ssd * 16 + gg (ssd < 2^22, gg < 16) = (16 c2 + gg) + 16 S - 32 acc; its minimum is the first
+            // best candidate of the task.  Candidates gg in [lo, hi) are inside the search range and the frame
+            // (motion.py:41-43, y bound); almost every task has all G of them.
+            const int gyb = 8 * (tl.by0 + brow) - sr + g * G;
+            const int lo = max(0, -gyb), hi = min(min(G, span - g * G), H - 7 - gyb);
+            const unsigned c2 = s_c2[blk];
+            const unsigned *sp = s_hs + off;
+            unsigned key = 0xffffffffu;
+            if (lo == 0 && hi == G) {
 #pragma unroll
-        for (int gg = 0; gg < G; ++gg) {
-            const unsigned ssd = c2 + sp[gg * P4] - 2u * acc[gg];
-            if (((valid >> gg) & 1u) && ssd < best_ssd) { best_ssd = ssd; best_idx = idx0 + gg * span; }
+                for (int gg = 0; gg < G; ++gg) key = min(key, (c2 + gg) + sp[gg * P4] - (acc[gg] << 5));
+            } else {
+#pragma unroll
+                for (int gg = 0; gg < G; ++gg)
+                    if (gg >= lo && gg < hi) key = min(key, (c2 + gg) + sp[gg * P4] - (acc[gg] << 5));
+            }
+            if (key != 0xffffffffu) {
+                best_ssd = key >> 4;
+                best_idx = (unsigned)((g * G + (int)(key & 15u)) * span + dxi);   // motion.py:55
+            }
         }
-        if (valid) {
+        // lexicographic (ssd, index) argmin: when the whole warp works on one block (the usual case for wide
+        // searches) two warp reductions and ONE shared atomic; otherwise one atomic per lane
+        if (__all_sync(0xffffffffu, blk == __shfl_sync(0xffffffffu, blk, 0))) {
+            const unsigned m = __reduce_min_sync(0xffffffffu, best_ssd);
+            const unsigned mi = __reduce_min_sync(0xffffffffu, best_ssd == m ? best_idx : 0xffffffffu);
+            if ((tid & 31) == 0) { best_ssd = m; best_idx = mi; } else best_ssd = 0xffffffffu;
+        }
+        if (best_ssd != 0xffffffffu) {
             if (small) atomicMin(s_best32 + blk, (best_ssd << 9) | best_idx);
             else atomicMin(s_best + blk, ((unsigned long long)best_ssd << 32) | best_idx);
         }
@@ -511,7 +546,7 @@ static size_t me_geometry(MeArgs &a, int64_t n_frames, int64_t H, int64_t W, int
 
 // launch over a 2-D grid (x = tile, y = frame), in chunks of at most 65535 frames
 template <typename K>
-static cudaError_t me_launch_chunks(K kernel, MeArgs a, int elem, size_t smem, cudaStream_t st) {
+static cudaError_t me_launch_chunks(K kernel, MeArgs a, int elem, size_t smem, cudaStream_t st, int threads = kMeThreads) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t tiles = (int64_t)a.tiles_y * a.tiles_x;
@@ -520,7 +555,7 @@ static cudaError_t me_launch_chunks(K kernel, MeArgs a, int elem, size_t smem, c
     const int64_t n = a.n;
     for (int64_t f0 = 0; f0 < n; f0 += 65535) {
         const int64_t nf = n - f0 < 65535 ? n - f0 : 65535;
-        kernel<<<dim3((unsigned)tiles, (unsigned)nf), kMeThreads, smem, st>>>(a);
+        kernel<<<dim3((unsigned)tiles, (unsigned)nf), threads, smem, st>>>(a);
         a.ref = (const char *)a.ref + 65535 * a.ref_fs * elem;
         a.cur = (const char *)a.cur + 65535 * a.cur_fs * elem;
         a.mv += 65535 * (int64_t)a.Hp * a.Wp;
@@ -593,7 +628,7 @@ cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const vo
     a.flag = flag; a.run_if = 0; a.check = check;
     const int G = me_int_group(2 * sr + 1);
     // common cases get a compile-time pitch: 16-block-wide tiles at +-4 (136) and up to +-16 (160)
-    const int pitch = (G == 9 && sr <= 4) ? 136 : (G == 11 && sr <= 16) ? 160 : 0;
+    const int pitch = (G == 9 && sr <= 4) ? 136 : (G == 9 && sr <= 8) ? 144 : (G == 11 && sr <= 16) ? 160 : 0;
     const size_t smem = me_int_geometry(a, G, pitch, n, H, W, sr, 200 * 1024, 4 * 3 * (int64_t)sm_count(device));
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     if (H * W >= 2147483647LL) return cudaErrorInvalidValue;                  // 32-bit pixel coordinates inside a frame
@@ -602,11 +637,24 @@ cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const vo
             (ref_fs * elem) % 16 == 0 && (cur_fs * elem) % 16 == 0;            // W is a multiple of 8
     cudaError_t e;
     if (check && (e = cudaMemsetAsync(flag, 0, sizeof(int), st)) != cudaSuccess) return e;
+    // threads per CTA: when three CTAs fit an SM by shared memory, the count in 256..352 that wastes the
+    // fewest lanes in the last round of tasks; otherwise two CTAs of 512
+    int threads = kMeIntMaxThreads;
+    if (pitch == 0) threads = kMeThreads;
+    else if (smem * 3 + 3 * 1024 <= 227 * 1024) {
+        const int tasks = a.tby * a.tbx * a.ntpb;
+        double best = 1e30;
+        for (int t = 256; t <= 352; t += 32) {
+            const double waste = (double)((tasks + t - 1) / t) * t / tasks;
+            if (waste < best - 1e-9) { best = waste; threads = t; }
+        }
+    }
 #define IVC_ME_INT_CASE(GG, PP)                                                                  \
     if (G == GG && pitch == PP)                                                                  \
-        return f32 ? me_launch_chunks(k_me_int<float, GG, PP>, a, 4, smem, st)                   \
-                   : me_launch_chunks(k_me_int<double, GG, PP>, a, 8, smem, st);
+        return f32 ? me_launch_chunks(k_me_int<float, GG, PP>, a, 4, smem, st, threads)          \
+                   : me_launch_chunks(k_me_int<double, GG, PP>, a, 8, smem, st, threads);
     IVC_ME_INT_CASE(9, 136)
+    IVC_ME_INT_CASE(9, 144)
     IVC_ME_INT_CASE(11, 160)
     IVC_ME_INT_CASE(11, 0)
     IVC_ME_INT_CASE(9, 0)
