@@ -172,6 +172,33 @@ int ivc_zerorun_count(int device, void *stream, const int32_t *zz, int64_t nbloc
 int ivc_zerorun_write(int device, void *stream, const int32_t *zz, int64_t nblocks, int32_t end_of_block,
                       const int64_t *offsets, int32_t *symbols_out);
 
+/* ---- N2 (next row): ZeroRunCoder.decode (ivclab/entropy/zerorun.py:44-87) ---------------------
+ * Three passes around an inclusive scan that the caller performs.  mark: is_eob[i] = 1 iff symbols[i] is
+ * an end-of-block in a symbol slot (not the run length that follows a zero marker).  ends: with
+ * rank = inclusive prefix sum of is_eob (int64), ends_out[k] = position of the (k+1)-th EOB for the
+ * first n_blocks blocks -- later symbols are ignored, as the reference stops after h*w*c blocks
+ * (zerorun.py:62).  write: block k = symbols (ends[k-1], ends[k]) expanded to 64 int32 coefficients.
+ * *err_out (device int) = 0, or bit 0: a block expands to more than 64 coefficients (the reference's
+ * "Block size exceeded"), bit 1: a run length <= 0 (never emitted by the encoder; the reference accepts
+ * it, this decoder does not).  The caller checks rank[n-1] >= n_blocks (else the reference raises
+ * "Unexpected end of encoded symbols" / "Expected N blocks"). */
+int ivc_zerorun_decode_mark(int device, void *stream, const int32_t *symbols, int64_t n_symbols, int32_t end_of_block,
+                            int32_t *is_eob_out);
+int ivc_zerorun_decode_ends(int device, void *stream, const int32_t *is_eob, const int64_t *rank, int64_t n_symbols,
+                            int64_t n_blocks, int64_t *ends_out);
+int ivc_zerorun_decode_write(int device, void *stream, const int32_t *symbols, const int64_t *ends, int64_t n_blocks,
+                             int32_t *blocks_out, int32_t *err_out);
+
+/* ---- N3 (next row): symbol statistics for stats_marg (ivclab/entropy/entropy.py:6-29) as
+ * IntraCodec.train_huffman_from_image uses it (intracodec.py:160-166) ----------------------------
+ * minmax_out[0..1] = min, max of x (U8 / I32 / I64), int64.
+ * histogram: counts_out[k] (uint64, n_bins entries, zeroed by the call) = what
+ * np.histogram(x, bins=np.arange(lo, lo + n_bins + 1)) returns: unit bins, the last one closed on the
+ * right.  `hot` names one frequent value besides 0, +-1, +-2 (the EOB marker) that is counted per warp. */
+int ivc_symbol_minmax(int device, void *stream, const void *x, int dtype, int64_t n, int64_t *minmax_out);
+int ivc_symbol_histogram(int device, void *stream, const void *x, int dtype, int64_t n, int64_t lo, int64_t n_bins,
+                         int64_t hot, uint64_t *counts_out);
+
 /* ---- N1 (next row): colour transforms (ivclab/signal/color.py:15-63) --------------------------
  * rgb: npixels x 3 (U8/I32/F32/F64) -> ycbcr float64, bit-identical to numpy's `image @ M.T + offset`
  * (one FMA chain per output, as BLAS evaluates it).  ycbcr2rgb: float64 in/out, clipped to [0,255]. */

@@ -15,7 +15,7 @@ extension has not been built, and calling it fails if no CUDA device is visible.
 """
 from . import _lib  # noqa: F401  (loads libivcb200.so or raises)
 from .codec import IntraBlockCoder, PFrameBlockCoder
-from .entropy import ZeroRunCoder
+from .entropy import ZeroRunCoder, stats_marg, symbol_histogram, symbol_minmax
 from .install import inject, install
 from .quantization import PatchQuant
 from .signal import DiscreteCosineTransform, rgb2ycbcr, ycbcr2rgb
@@ -26,4 +26,5 @@ from .video import ClosedLoopLumaCoder, MotionCompensator
 __version__ = "0.1.0"
 __all__ = ["DiscreteCosineTransform", "PatchQuant", "ZigZag", "Patcher", "MotionCompensator",
            "IntraBlockCoder", "PFrameBlockCoder", "ClosedLoopLumaCoder", "ZeroRunCoder", "calc_mse", "calc_psnr",
-           "frame_sse", "rgb2ycbcr", "ycbcr2rgb", "StreamedCoder", "install", "inject"]
+           "frame_sse", "rgb2ycbcr", "ycbcr2rgb", "StreamedCoder", "stats_marg", "symbol_minmax", "symbol_histogram",
+           "install", "inject"]

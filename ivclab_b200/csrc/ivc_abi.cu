@@ -272,6 +272,61 @@ int ivc_zerorun_write(int device, void *stream, const int32_t *zz, int64_t nbloc
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
 
+int ivc_zerorun_decode_mark(int device, void *stream, const int32_t *symbols, int64_t n_symbols, int32_t end_of_block,
+                            int32_t *is_eob_out) {
+    if (n_symbols < 0) return IVC_ERR_ARG;
+    if (n_symbols == 0) return IVC_OK;
+    if (!symbols || !is_eob_out) return IVC_ERR_ARG;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_zrd_mark(device, (cudaStream_t)stream, symbols, n_symbols, end_of_block, is_eob_out);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
+int ivc_zerorun_decode_ends(int device, void *stream, const int32_t *is_eob, const int64_t *rank, int64_t n_symbols,
+                            int64_t n_blocks, int64_t *ends_out) {
+    if (n_symbols < 0 || n_blocks < 0) return IVC_ERR_ARG;
+    if (n_symbols == 0 || n_blocks == 0) return IVC_OK;
+    if (!is_eob || !rank || !ends_out) return IVC_ERR_ARG;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_zrd_ends(device, (cudaStream_t)stream, is_eob, rank, n_symbols, n_blocks, ends_out);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
+int ivc_zerorun_decode_write(int device, void *stream, const int32_t *symbols, const int64_t *ends, int64_t n_blocks,
+                             int32_t *blocks_out, int32_t *err_out) {
+    if (n_blocks < 0) return IVC_ERR_ARG;
+    if (n_blocks == 0) return IVC_OK;
+    if (!symbols || !ends || !blocks_out || !err_out) return IVC_ERR_ARG;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_zrd_write(device, (cudaStream_t)stream, symbols, ends, n_blocks, blocks_out, (int *)err_out);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
+int ivc_symbol_minmax(int device, void *stream, const void *x, int dtype, int64_t n, int64_t *minmax_out) {
+    if (n < 0) return IVC_ERR_ARG;
+    if (dtype != IVC_U8 && dtype != IVC_I32 && dtype != IVC_I64) return IVC_ERR_DTYPE;
+    if (!minmax_out || (n > 0 && !x)) return IVC_ERR_ARG;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_minmax(device, (cudaStream_t)stream, x, dtype, n, minmax_out);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
+int ivc_symbol_histogram(int device, void *stream, const void *x, int dtype, int64_t n, int64_t lo, int64_t n_bins,
+                         int64_t hot, uint64_t *counts_out) {
+    if (n < 0 || n_bins < 0 || n_bins > 2147483647LL) return IVC_ERR_ARG;
+    if (dtype != IVC_U8 && dtype != IVC_I32 && dtype != IVC_I64) return IVC_ERR_DTYPE;
+    if (n_bins == 0) return IVC_OK;
+    if (!counts_out || (n > 0 && !x)) return IVC_ERR_ARG;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_hist(device, (cudaStream_t)stream, x, dtype, n, lo, n_bins, hot, counts_out);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
 int ivc_rgb2ycbcr(int device, void *stream, const void *rgb, int dtype, int64_t npixels, void *ycbcr_out) {
     if (npixels < 0) return IVC_ERR_ARG;
     if (dtype != IVC_U8 && dtype != IVC_I32 && dtype != IVC_F32 && dtype != IVC_F64) return IVC_ERR_DTYPE;

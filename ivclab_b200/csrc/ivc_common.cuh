@@ -40,6 +40,17 @@ cudaError_t launch_zr_count(int device, cudaStream_t st, const int32_t *zz, int6
 cudaError_t launch_zr_write(int device, cudaStream_t st, const int32_t *zz, int64_t nblocks, int32_t eob,
                             const int64_t *offsets, int32_t *out);
 
+cudaError_t launch_zrd_mark(int device, cudaStream_t st, const int32_t *sym, int64_t n, int32_t eob, int32_t *is_eob);
+cudaError_t launch_zrd_ends(int device, cudaStream_t st, const int32_t *is_eob, const int64_t *rank, int64_t n,
+                            int64_t want, int64_t *ends);
+cudaError_t launch_zrd_write(int device, cudaStream_t st, const int32_t *sym, const int64_t *ends, int64_t nblocks,
+                             int32_t *out, int *err);
+
+// symbol statistics (ivc_metrics.cu)
+cudaError_t launch_hist(int device, cudaStream_t st, const void *x, int dtype, int64_t n, int64_t lo, int64_t nbins,
+                        int64_t hot, uint64_t *counts);
+cudaError_t launch_minmax(int device, cudaStream_t st, const void *x, int dtype, int64_t n, int64_t *out);
+
 // colour (ivc_color.cu) and the RGB front end of K1 (ivc_transform.cu)
 cudaError_t launch_color(int device, cudaStream_t st, bool to_rgb, const void *in, int in_dtype, int64_t npix, double *out);
 cudaError_t launch_forward_rgb8(int device, cudaStream_t st, const void *rgb, int64_t n, int64_t H, int64_t W,

@@ -95,4 +95,102 @@ cudaError_t launch_sse(int device, cudaStream_t st, const void *a, int a_dtype, 
     return cudaGetLastError();
 }
 
+// ---- symbol statistics: min/max and unit-width histogram (stats_marg, ivclab/entropy/entropy.py:6-29, as
+//      IntraCodec.train_huffman_from_image uses it: intracodec.py:160-166) ---------------------------
+// np.histogram(x, bins=np.arange(lo, hi)) has hi-lo-1 unit bins [lo+k, lo+k+1), the last one closed:
+// x == hi-1 lands in bin hi-lo-2.  Zero-run symbol streams are dominated by a handful of values (0, +-1,
+// +-2, EOB): those are counted with warp ballots (one shared atomic per warp and value), the rest with
+// shared-memory atomics on a per-CTA histogram, flushed with one global atomic per non-empty bin.
+constexpr int kHistThreads = 256;
+
+__device__ __forceinline__ long long ld_i64(const void *p, int dtype, int64_t i) {
+    switch (dtype) {
+        case IVC_U8: return ((const unsigned char *)p)[i];
+        case IVC_I32: return ((const int *)p)[i];
+        default: return ((const long long *)p)[i];
+    }
+}
+
+__global__ void __launch_bounds__(kHistThreads) k_hist(const void *x, int dtype, int64_t n, long long lo, int nbins,
+                                                       long long hot, unsigned long long *counts, int use_smem) {
+    extern __shared__ unsigned sh[];
+    if (use_smem) {
+        for (int i = threadIdx.x; i < nbins; i += kHistThreads) sh[i] = 0;
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * kHistThreads;
+    for (int64_t i0 = (int64_t)blockIdx.x * kHistThreads; i0 < n; i0 += stride) {       // warp-uniform trip count
+        const int64_t i = i0 + threadIdx.x;
+        const bool in = i < n;
+        const long long v = in ? ld_i64(x, dtype, i) : 0;
+        long long b = v - lo;
+        if (b == nbins) b = nbins - 1;                                                  // closed last bin
+        bool todo = in && b >= 0 && b < nbins;
+        if (use_smem) {
+            const long long hots[6] = {0, 1, -1, 2, -2, hot};
+#pragma unroll
+            for (int h = 0; h < 6; ++h) {
+                const bool is = todo && v == hots[h] && (h < 5 || (hot > 2 || hot < -2));
+                const unsigned mask = __ballot_sync(0xffffffffu, is);
+                if (mask && lane == __ffs(mask) - 1) atomicAdd(&sh[(int)b], (unsigned)__popc(mask));
+                todo = todo && !is;
+            }
+            if (todo) atomicAdd(&sh[(int)b], 1u);
+        } else if (todo) {
+            atomicAdd(&counts[b], 1ull);
+        }
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nbins; i += kHistThreads)
+            if (sh[i]) atomicAdd(&counts[i], (unsigned long long)sh[i]);
+    }
+}
+
+// out[0] = min, out[1] = max (int64; the caller initialises them to INT64_MAX / INT64_MIN)
+__global__ void __launch_bounds__(kHistThreads) k_minmax(const void *x, int dtype, int64_t n, long long *out) {
+    long long mn = 0x7fffffffffffffffLL, mx = -0x7fffffffffffffffLL - 1;
+    for (int64_t i = (int64_t)blockIdx.x * kHistThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kHistThreads) {
+        const long long v = ld_i64(x, dtype, i);
+        mn = min(mn, v);
+        mx = max(mx, v);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(out, mn);
+        atomicMax(out + 1, mx);
+    }
+}
+
+cudaError_t launch_hist(int device, cudaStream_t st, const void *x, int dtype, int64_t n, int64_t lo, int64_t nbins,
+                        int64_t hot, uint64_t *counts) {
+    cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(uint64_t) * (size_t)nbins, st);
+    if (e != cudaSuccess || n == 0) return e;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    int64_t grid = (n + kHistThreads * 16 - 1) / (kHistThreads * 16);
+    if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
+    const int use_smem = nbins <= 12 * 1024;                                   // 48 KB of 32-bit bins per CTA
+    k_hist<<<(unsigned)grid, kHistThreads, use_smem ? (size_t)nbins * 4 : 0, st>>>(x, dtype, n, lo, (int)nbins, hot,
+                                                                                   (unsigned long long *)counts, use_smem);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_minmax(int device, cudaStream_t st, const void *x, int dtype, int64_t n, int64_t *out) {
+    const long long init[2] = {0x7fffffffffffffffLL, -0x7fffffffffffffffLL - 1};
+    cudaError_t e = cudaMemcpyAsync(out, init, sizeof(init), cudaMemcpyHostToDevice, st);   // pageable 16 B: staged by the driver
+    if (e != cudaSuccess || n == 0) return e;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    int64_t grid = (n + kHistThreads * 16 - 1) / (kHistThreads * 16);
+    if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
+    k_minmax<<<(unsigned)grid, kHistThreads, 0, st>>>(x, dtype, n, (long long *)out);
+    return cudaGetLastError();
+}
+
 }  // namespace ivc

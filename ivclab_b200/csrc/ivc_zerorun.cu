@@ -1,103 +1,222 @@
-// ivc_zerorun.cu -- zero-run encoder over scan blocks (ivclab/entropy/zerorun.py:10-43; SURVEY.md
-// section 8f row N2: the first host-side consumer of K1's output and the real bottleneck of
-// IntraCodec.image2symbols).
+// ivc_zerorun.cu -- zero-run coder over scan blocks, both directions (ivclab/entropy/zerorun.py:10-87;
+// the first host-side consumer of K1's output and the real bottleneck of
+// IntraCodec.image2symbols / symbols2image).
 //
-// Per 64-coefficient block the reference emits: every non-zero value as itself; every run of zeros
-// that is followed by a non-zero value as the pair (0, run_length); then EOB.  With m = the 64-bit
-// "non-zero" mask of a block, L = its highest set bit and S = the zero positions below L that start a
-// run (S = ~m & ((m << 1) | 1)), the block contributes popc(m) + 2*popc(S) + 1 symbols, and position
-// p writes at offset popc(m & below(p)) + 2*popc(S & below(p)); a run starting at p has length
-// ctz(m >> p).  Two passes: count (-> exclusive scan on the caller's side) and write.
-// One warp stages 32 blocks (8 KB, coalesced 16-byte loads, row pitch 65 words so that the per-thread
-// scans are bank-conflict free); one thread then owns one block.
+// ENCODE (zerorun.py:10-43).  Per 64-coefficient block the reference emits: every non-zero value as
+// itself; every run of zeros that is followed by a non-zero value as the pair (0, run_length); then EOB.
+// With m = the 64-bit "non-zero" mask of a block, L = its highest set bit and S = the zero positions below
+// L that start a run (S = ~m & ((m << 1) | 1)), the block contributes popc(m) + 2*popc(S) + 1 symbols, and
+// position p writes at offset popc(m & below(p)) + 2*popc(S & below(p)); a run starting at p has length
+// ctz(m >> p).  Two passes: count (-> exclusive scan on the caller's side) and write.  One WARP owns one
+// block at a time (lane l holds coefficients l and l+32: two coalesced 128-byte loads, the mask is two
+// ballots, every lane places its own symbols), eight blocks' loads in flight per warp.
+//
+// DECODE (zerorun.py:44-87).  A symbol slot holds a value, the zero marker or EOB; the slot after a zero
+// marker holds a run length.  With run lengths >= 1 (all the encoder emits) a slot is a run length iff its
+// predecessor reads 0, so EOBs can be marked independently (mark), numbered by the caller's inclusive scan,
+// turned into block boundaries (ends), and every block is then expanded by one warp (write): per-slot
+// output counts, a warp scan, a scatter into a zeroed 64-entry row.  Streams the reference would reject
+// (or a zero run length) raise a flag instead of producing blocks.
 #include "ivc_common.cuh"
 
 namespace ivc {
 
-constexpr int kZrWarps = 4;
-constexpr int kZrPitch = 65;
+constexpr int kZrWarps = 8;
+constexpr int kZrBatch = 8;        // blocks whose loads are in flight per warp
 
-__device__ __forceinline__ unsigned long long stage_and_mask(const int32_t *zz, int64_t nblocks, int64_t blk0, int *sm, int lane) {
-    // coalesced: the 32 blocks of this warp are 8 KB contiguous = 512 int4
-#pragma unroll 4
-    for (int k = 0; k < 16; ++k) {
-        const int id = lane + 32 * k, b = id >> 4, q = id & 15;
-        int4 v = make_int4(0, 0, 0, 0);
-        if (blk0 + b < nblocks) v = *reinterpret_cast<const int4 *>(zz + (blk0 + b) * 64 + q * 4);
-        int *d = sm + b * kZrPitch + q * 4;
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-    }
-    __syncwarp();
-    unsigned long long m = 0;
-    const int *mine = sm + lane * kZrPitch;
-#pragma unroll 16
-    for (int p = 0; p < 64; ++p) m |= (unsigned long long)(mine[p] != 0) << p;
-    return m;
+__device__ __forceinline__ unsigned long long zr_run_starts(unsigned long long m) {
+    const unsigned long long below_top = (2ull << (63 - __clzll((long long)m))) - 1ull;        // m != 0
+    return ~m & ((m << 1) | 1ull) & below_top;
 }
 
-__global__ void __launch_bounds__(kZrWarps * 32) k_zr_count(const int32_t *zz, int64_t nblocks, int32_t *counts) {
-    __shared__ int sm_all[kZrWarps][32 * kZrPitch];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t nw = (int64_t)gridDim.x * kZrWarps;
-    for (int64_t grp = (int64_t)blockIdx.x * kZrWarps + warp; grp * 32 < nblocks; grp += nw) {
-        const unsigned long long m = stage_and_mask(zz, nblocks, grp * 32, sm_all[warp], lane);
-        const int64_t blk = grp * 32 + lane;
-        if (blk < nblocks) {
-            int c = 1;                                                       // EOB
-            if (m) {
-                const unsigned long long below_top = (m == 0) ? 0 : ((2ull << (63 - __clzll((long long)m))) - 1ull);
-                const unsigned long long S = ~m & ((m << 1) | 1ull) & below_top;
-                c += __popcll(m) + 2 * __popcll(S);
+__global__ void __launch_bounds__(kZrWarps * 32) k_zr_count(const int32_t *__restrict__ zz, int64_t nblocks,
+                                                            int32_t *__restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * kZrWarps + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * kZrWarps;
+    for (int64_t blk0 = warp * 32; blk0 < nblocks; blk0 += nw * 32) {                 // 32 blocks per warp and round
+        int mine = 0;
+#pragma unroll 1
+        for (int sub = 0; sub < 32; sub += kZrBatch) {
+            int a[kZrBatch], b[kZrBatch];
+#pragma unroll
+            for (int j = 0; j < kZrBatch; ++j) {
+                const int64_t blk = blk0 + sub + j;
+                a[j] = b[j] = 0;
+                if (blk < nblocks) {
+                    a[j] = __ldg(zz + blk * 64 + lane);
+                    b[j] = __ldg(zz + blk * 64 + 32 + lane);
+                }
             }
-            counts[blk] = c;
+#pragma unroll
+            for (int j = 0; j < kZrBatch; ++j) {
+                const unsigned long long m = (unsigned long long)__ballot_sync(0xffffffffu, a[j] != 0) |
+                                             ((unsigned long long)__ballot_sync(0xffffffffu, b[j] != 0) << 32);
+                int c = 1;                                                            // EOB
+                if (m) c += __popcll(m) + 2 * __popcll(zr_run_starts(m));
+                if (lane == sub + j) mine = c;
+            }
         }
+        if (blk0 + lane < nblocks) counts[blk0 + lane] = mine;
+    }
+}
+
+__global__ void __launch_bounds__(kZrWarps * 32) k_zr_write(const int32_t *__restrict__ zz, int64_t nblocks, int32_t eob,
+                                                            const int64_t *__restrict__ offsets, int32_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * kZrWarps + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * kZrWarps;
+    const unsigned long long low0 = (1ull << lane) - 1ull, low1 = (1ull << (lane + 32)) - 1ull;
+    for (int64_t blk0 = warp * 32; blk0 < nblocks; blk0 += nw * 32) {
+        const int64_t my_off = blk0 + lane < nblocks ? offsets[blk0 + lane] : 0;
+#pragma unroll 1
+        for (int sub = 0; sub < 32; sub += kZrBatch) {
+            int a[kZrBatch], b[kZrBatch];
+#pragma unroll
+            for (int j = 0; j < kZrBatch; ++j) {
+                const int64_t blk = blk0 + sub + j;
+                a[j] = b[j] = 0;
+                if (blk < nblocks) {
+                    a[j] = __ldg(zz + blk * 64 + lane);
+                    b[j] = __ldg(zz + blk * 64 + 32 + lane);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kZrBatch; ++j) {
+                const int64_t off = __shfl_sync(0xffffffffu, my_off, sub + j);
+                if (blk0 + sub + j >= nblocks) break;                                 // warp-uniform
+                const unsigned long long m = (unsigned long long)__ballot_sync(0xffffffffu, a[j] != 0) |
+                                             ((unsigned long long)__ballot_sync(0xffffffffu, b[j] != 0) << 32);
+                int32_t *o = out + off;
+                if (m == 0) {
+                    if (lane == 0) o[0] = eob;
+                    continue;
+                }
+                const unsigned long long S = zr_run_starts(m);
+                const int p0 = __popcll(m & low0) + 2 * __popcll(S & low0);
+                const int p1 = __popcll(m & low1) + 2 * __popcll(S & low1);
+                if (a[j] != 0) o[p0] = a[j];
+                else if ((S >> lane) & 1ull) { o[p0] = 0; o[p0 + 1] = __ffsll((long long)(m >> lane)) - 1; }
+                if (b[j] != 0) o[p1] = b[j];
+                else if ((S >> (lane + 32)) & 1ull) { o[p1] = 0; o[p1 + 1] = __ffsll((long long)(m >> (lane + 32))) - 1; }
+                if (lane == 0) o[__popcll(m) + 2 * __popcll(S)] = eob;
+            }
+        }
+    }
+}
+
+// ---- decode --------------------------------------------------------------------------------------
+// is_eob[i] = 1 iff symbol i is an EOB in a symbol slot (i.e. not the run length after a zero marker)
+__global__ void __launch_bounds__(256) k_zrd_mark(const int32_t *__restrict__ sym, int64_t n, int32_t eob,
+                                                  int32_t *__restrict__ is_eob) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        is_eob[i] = (sym[i] == eob && !(i > 0 && sym[i - 1] == 0)) ? 1 : 0;
+}
+
+// rank[i] = number of marked EOBs in [0, i] (the caller's inclusive scan): EOB number k ends block k-1
+__global__ void __launch_bounds__(256) k_zrd_ends(const int32_t *__restrict__ is_eob, const int64_t *__restrict__ rank,
+                                                  int64_t n, int64_t want, int64_t *__restrict__ ends) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (is_eob[i] && rank[i] <= want) ends[rank[i] - 1] = i;
+}
+
+// err bits: 1 = a block expands to more than 64 coefficients (zerorun.py:76-77), 2 = zero run length
+__global__ void __launch_bounds__(kZrWarps * 32) k_zrd_write(const int32_t *__restrict__ sym, const int64_t *__restrict__ ends,
+                                                             int64_t nblocks, int32_t *__restrict__ out, int *err) {
+    __shared__ int32_t rows[kZrWarps][64];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t warp = (int64_t)blockIdx.x * kZrWarps + w, nw = (int64_t)gridDim.x * kZrWarps;
+    int32_t *row = rows[w];
+    for (int64_t blk = warp; blk < nblocks; blk += nw) {
+        const int64_t start = blk ? ends[blk - 1] + 1 : 0, end = ends[blk];           // [start, end) = the block's symbols
+        const int64_t len = end - start;
+        row[lane] = 0;
+        row[lane + 32] = 0;
+        __syncwarp();
+        int bad = 0;
+        int base = 0;                                                                 // coefficients emitted by earlier slots
+        for (int64_t c0 = 0; c0 < len && base <= 64; c0 += 128) {                     // a legal block has <= 127 symbols
+            int s[5], e[4];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {                                             // slots 4*lane-1 .. 4*lane+3 of this chunk
+                const int64_t i = start + c0 + 4 * lane + k - 1;
+                s[k] = (i >= start && i < end) ? sym[i] : 1;                           // "1" = harmless predecessor / filler
+            }
+            int tot = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool in = c0 + 4 * lane + k < len, is_run = in && s[k] == 0 && (c0 + 4 * lane + k > 0);
+                const int v = s[k + 1];
+                e[k] = !in ? 0 : is_run ? v : (v != 0 ? 1 : 0);
+                if (is_run && v <= 0) bad |= 2;
+                if (is_run && v > 64) e[k] = 65;                                      // clamp: only "more than 64" matters
+                tot += e[k];
+            }
+            int incl = tot;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            int pos = base + incl - tot;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool in = c0 + 4 * lane + k < len, is_run = in && s[k] == 0 && (c0 + 4 * lane + k > 0);
+                if (in && !is_run && s[k + 1] != 0) {
+                    if (pos < 64) row[pos] = s[k + 1];
+                    else bad |= 1;
+                }
+                pos += e[k];
+            }
+            base += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (base > 64 || len > 128) bad |= 1;
+        __syncwarp();
+        out[blk * 64 + lane] = row[lane];
+        out[blk * 64 + 32 + lane] = row[lane + 32];
+        if (bad) atomicOr(err, bad);
         __syncwarp();
     }
 }
 
-__global__ void __launch_bounds__(kZrWarps * 32) k_zr_write(const int32_t *zz, int64_t nblocks, int32_t eob,
-                                                            const int64_t *offsets, int32_t *out) {
-    __shared__ int sm_all[kZrWarps][32 * kZrPitch];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t nw = (int64_t)gridDim.x * kZrWarps;
-    for (int64_t grp = (int64_t)blockIdx.x * kZrWarps + warp; grp * 32 < nblocks; grp += nw) {
-        unsigned long long m = stage_and_mask(zz, nblocks, grp * 32, sm_all[warp], lane);
-        const int64_t blk = grp * 32 + lane;
-        if (blk < nblocks) {
-            const int *mine = sm_all[warp] + lane * kZrPitch;
-            int32_t *o = out + offsets[blk];
-            int p = 0;
-            while (m >> p) {                                                 // there is a non-zero at or above p
-                const int run = __ffsll((long long)(m >> p)) - 1;            // zeros before the next non-zero
-                if (run > 0) { *o++ = 0; *o++ = run; p += run; }
-                *o++ = mine[p];
-                ++p;
-                if (p >= 64) break;
-            }
-            *o = eob;
-        }
-        __syncwarp();
-    }
+static int zr_grid(int device, int64_t units, int per_cta) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    int64_t grid = (units + per_cta - 1) / per_cta;
+    if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
+    return (int)(grid < 1 ? 1 : grid);
 }
 
 cudaError_t launch_zr_count(int device, cudaStream_t st, const int32_t *zz, int64_t nblocks, int32_t *counts) {
     if (nblocks == 0) return cudaSuccess;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    int64_t grid = (nblocks + 32 * kZrWarps - 1) / (32 * kZrWarps);
-    if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
-    k_zr_count<<<(unsigned)grid, kZrWarps * 32, 0, st>>>(zz, nblocks, counts);
+    k_zr_count<<<zr_grid(device, nblocks, 32 * kZrWarps), kZrWarps * 32, 0, st>>>(zz, nblocks, counts);
     return cudaGetLastError();
 }
 
 cudaError_t launch_zr_write(int device, cudaStream_t st, const int32_t *zz, int64_t nblocks, int32_t eob,
                             const int64_t *offsets, int32_t *out) {
     if (nblocks == 0) return cudaSuccess;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    int64_t grid = (nblocks + 32 * kZrWarps - 1) / (32 * kZrWarps);
-    if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
-    k_zr_write<<<(unsigned)grid, kZrWarps * 32, 0, st>>>(zz, nblocks, eob, offsets, out);
+    k_zr_write<<<zr_grid(device, nblocks, 32 * kZrWarps), kZrWarps * 32, 0, st>>>(zz, nblocks, eob, offsets, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_zrd_mark(int device, cudaStream_t st, const int32_t *sym, int64_t n, int32_t eob, int32_t *is_eob) {
+    if (n == 0) return cudaSuccess;
+    k_zrd_mark<<<zr_grid(device, n, 256 * 8), 256, 0, st>>>(sym, n, eob, is_eob);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_zrd_ends(int device, cudaStream_t st, const int32_t *is_eob, const int64_t *rank, int64_t n,
+                            int64_t want, int64_t *ends) {
+    if (n == 0 || want == 0) return cudaSuccess;
+    k_zrd_ends<<<zr_grid(device, n, 256 * 8), 256, 0, st>>>(is_eob, rank, n, want, ends);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_zrd_write(int device, cudaStream_t st, const int32_t *sym, const int64_t *ends, int64_t nblocks,
+                             int32_t *out, int *err) {
+    if (nblocks == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(err, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    k_zrd_write<<<zr_grid(device, nblocks, kZrWarps), kZrWarps * 32, 0, st>>>(sym, ends, nblocks, out, err);
     return cudaGetLastError();
 }
 

@@ -1,6 +1,7 @@
-"""``ivclab.entropy.ZeroRunCoder.encode`` on the B200 (reference: ivclab/entropy/zerorun.py:4-43;
-SURVEY.md section 8f row N2).  ``decode`` is host-side parsing of a variable-length stream and is
-not on the device path; it is provided for round trips with the reference's exact semantics."""
+"""``ivclab.entropy.ZeroRunCoder`` on the B200 (reference: ivclab/entropy/zerorun.py:4-87; SURVEY.md
+section 8f row N2).  Both directions run on the device: ``encode`` is two kernels around one prefix sum,
+``decode`` three kernels around one prefix sum; each needs a single device->host read (the stream length /
+the block count and error flag)."""
 from __future__ import annotations
 
 import numpy as np
@@ -12,60 +13,105 @@ from .._runtime import aligned16, dev_index, stream_ptr, to_device, to_host
 __all__ = ["ZeroRunCoder"]
 
 
+class _PendingEncode:
+    """Device-side state of an encode whose stream length is still on its way to the host."""
+    __slots__ = ("blocks", "offsets", "total_host", "event", "nblk", "stream")
+
+
 class ZeroRunCoder:
     def __init__(self, end_of_block=4000, block_size=64):
         self.EOB = end_of_block
         self.block_size = block_size
 
-    def encode(self, flat_patch_img):
-        """[h, w, c, 64] scan blocks -> int32 symbol stream, blocks in (h w c) order (zerorun.py:15-41).
-        Two kernels around one ``cumsum``; the stream length needs one device->host read."""
+    # ---- encode --------------------------------------------------------------------------------
+    def _check(self, flat_patch_img):
         if self.block_size != 64:
             raise NotImplementedError("only 64-coefficient blocks are implemented on the device")
         t, was_np = to_device(flat_patch_img)
         if t.ndim not in (4, 5) or t.shape[-1] != 64:        # 5-D = a batch of frames, streams concatenated in order
             raise ValueError(f"expected [h, w, c, 64] (or [n, h, w, c, 64]) scan blocks, got shape {tuple(t.shape)}")
-        t = aligned16(t.to(torch.int32))
-        nblk = t.numel() // 64
-        dev, sp = dev_index(t), stream_ptr(t.device)
-        counts = torch.empty(nblk, dtype=torch.int32, device=t.device)
-        _lib.check(_lib.lib.ivc_zerorun_count(dev, sp, t.data_ptr(), nblk, counts.data_ptr()), "ivc_zerorun_count")
-        ends = torch.cumsum(counts, 0, dtype=torch.int64)
-        offsets = (ends - counts).contiguous()
-        total = int(ends[-1].item()) if nblk else 0
-        out = torch.empty(total, dtype=torch.int32, device=t.device)
-        _lib.check(_lib.lib.ivc_zerorun_write(dev, sp, t.data_ptr(), nblk, int(self.EOB), offsets.data_ptr(), out.data_ptr()),
-                   "ivc_zerorun_write")
-        return to_host(out, was_np)
+        return aligned16(t.to(torch.int32)), was_np
 
+    def encode_begin(self, flat_patch_img) -> _PendingEncode:
+        """First half of :meth:`encode` without a host synchronisation: counts the symbols of every block,
+        scans them and starts an asynchronous copy of the stream length into pinned host memory.  Lets a
+        pipeline enqueue further work before :meth:`encode_finish` waits for that one number."""
+        t, _ = self._check(flat_patch_img)
+        p = _PendingEncode()
+        p.blocks, p.nblk, p.stream = t, t.numel() // 64, torch.cuda.current_stream(t.device)
+        dev, sp = dev_index(t), stream_ptr(t.device)
+        counts = torch.empty(p.nblk, dtype=torch.int32, device=t.device)
+        _lib.check(_lib.lib.ivc_zerorun_count(dev, sp, t.data_ptr(), p.nblk, counts.data_ptr()), "ivc_zerorun_count")
+        ends = torch.cumsum(counts, 0, dtype=torch.int64)
+        p.offsets = (ends - counts).contiguous()
+        p.total_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+        if p.nblk:
+            p.total_host.copy_(ends[-1:], non_blocking=True)
+        p.event = torch.cuda.Event()
+        p.event.record(p.stream)
+        return p
+
+    def encode_finish(self, p: _PendingEncode) -> torch.Tensor:
+        """Second half: waits for the stream length (one event), then writes the symbols on the current stream."""
+        p.event.synchronize()
+        total = int(p.total_host[0])
+        t = p.blocks
+        out = torch.empty(total, dtype=torch.int32, device=t.device)
+        cur = torch.cuda.current_stream(t.device)
+        if cur != p.stream:
+            cur.wait_event(p.event)
+        _lib.check(_lib.lib.ivc_zerorun_write(dev_index(t), stream_ptr(t.device), t.data_ptr(), p.nblk, int(self.EOB),
+                                              p.offsets.data_ptr(), out.data_ptr()), "ivc_zerorun_write")
+        return out
+
+    def encode(self, flat_patch_img):
+        """[h, w, c, 64] scan blocks -> int32 symbol stream, blocks in (h w c) order (zerorun.py:10-43)."""
+        was_np = not isinstance(flat_patch_img, torch.Tensor)
+        return to_host(self.encode_finish(self.encode_begin(flat_patch_img)), was_np)
+
+    # ---- decode --------------------------------------------------------------------------------
     def decode(self, encoded, original_shape):
-        """Host-side inverse with the reference's stop-after-h*w*c-blocks rule and error conditions
-        (zerorun.py:44-87)."""
-        enc = encoded.cpu().numpy() if isinstance(encoded, torch.Tensor) else np.asarray(encoded)
-        h, w, c = original_shape
-        want = h * w * c
-        blocks = np.zeros((want, self.block_size), dtype=np.int32)
-        i = n = 0
-        while i < len(enc) and n < want:
-            pos = 0
-            while True:
-                if i >= len(enc):
-                    raise ValueError("Unexpected end of encoded symbols")
-                s = int(enc[i])
-                i += 1
-                if s == self.EOB:
-                    break
-                if s == 0:
-                    pos += int(enc[i])
-                    i += 1
-                else:
-                    if pos >= self.block_size:
-                        raise ValueError(f"Block size exceeded: {pos + 1}")
-                    blocks[n, pos] = s
-                    pos += 1
-                if pos > self.block_size:
-                    raise ValueError(f"Block size exceeded: {pos}")
-            n += 1
-        if n != want:
-            raise ValueError(f"Expected {want} blocks, got {n}")
-        return blocks.reshape(h, w, c, self.block_size)
+        """Symbol stream -> ``[h, w, c, 64]`` int32 blocks with the reference's semantics (zerorun.py:44-87):
+        parsing stops after ``h*w*c`` blocks (later symbols are ignored), a stream that ends early or a
+        block that expands past 64 coefficients raises ``ValueError``.  Divergence: a run length of 0 --
+        which the encoder never emits and the reference silently accepts -- raises ``ValueError`` here."""
+        if self.block_size != 64:
+            raise NotImplementedError("only 64-coefficient blocks are implemented on the device")
+        if not isinstance(encoded, (torch.Tensor, np.ndarray)):
+            encoded = np.asarray(encoded, dtype=np.int64)
+        sym, was_np = to_device(encoded)
+        sym = sym.reshape(-1)
+        if sym.dtype != torch.int32:
+            sym = sym.to(torch.int32)
+        sym = sym.contiguous()
+        h, w, c = (int(v) for v in original_shape)
+        want, n = h * w * c, sym.numel()
+        dev, sp = dev_index(sym), stream_ptr(sym.device)
+        out = torch.empty((h, w, c, 64), dtype=torch.int32, device=sym.device)
+        if want == 0:
+            return to_host(out, was_np)
+        found, last_is_eob = 0, True
+        if n:
+            is_eob = torch.empty(n, dtype=torch.int32, device=sym.device)
+            _lib.check(_lib.lib.ivc_zerorun_decode_mark(dev, sp, sym.data_ptr(), n, int(self.EOB), is_eob.data_ptr()),
+                       "ivc_zerorun_decode_mark")
+            rank = torch.cumsum(is_eob, 0, dtype=torch.int64)
+            ends = torch.empty(want, dtype=torch.int64, device=sym.device)
+            err = torch.zeros(1, dtype=torch.int32, device=sym.device)
+            _lib.check(_lib.lib.ivc_zerorun_decode_ends(dev, sp, is_eob.data_ptr(), rank.data_ptr(), n, want, ends.data_ptr()),
+                       "ivc_zerorun_decode_ends")
+            tail = torch.stack([rank[-1], is_eob[-1].to(torch.int64)])
+            found, last_is_eob = (int(v) for v in tail.tolist())
+            nb = min(found, want)
+            _lib.check(_lib.lib.ivc_zerorun_decode_write(dev, sp, sym.data_ptr(), ends.data_ptr(), nb, out.data_ptr(),
+                                                         err.data_ptr()), "ivc_zerorun_decode_write")
+            flags = int(err.item()) if nb else 0
+            if flags & 1:
+                raise ValueError("Block size exceeded: a block expands to more than 64 coefficients")
+            if flags & 2:
+                raise ValueError("zero-length run in the symbol stream (never produced by ZeroRunCoder.encode)")
+        if found < want:
+            if n and not last_is_eob:
+                raise ValueError("Unexpected end of encoded symbols")
+            raise ValueError(f"Expected {want} blocks, got {found}")
+        return to_host(out, was_np)

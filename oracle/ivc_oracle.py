@@ -562,6 +562,20 @@ def zerorun_decode(symbols, shape, eob: int = 4000) -> np.ndarray:
     return blocks.reshape(h, w, c, 64)
 
 
+def stats_marg(image: np.ndarray, pixel_range: np.ndarray) -> np.ndarray:
+    """``stats_marg`` (entropy.py:6-29): histogram over the bin EDGES ``pixel_range`` (last bin closed),
+    normalised by the number of samples (not by the number of counted samples)."""
+    flat = np.asarray(image).astype(np.float64).flatten()
+    counts, _ = np.histogram(flat, bins=pixel_range)
+    return counts / flat.size
+
+
+def symbol_bounds(symbols: np.ndarray, margin: int = 20):
+    """Bin range of ``IntraCodec.train_huffman_from_image`` (intracodec.py:161-164)."""
+    s = np.asarray(symbols, dtype=np.int32)
+    return int(s.min()) - margin, int(s.max()) + margin + 1
+
+
 # --------------------------------------------------------------------------
 # 8. Seeded synthetic inputs (SURVEY.md section 8d)
 # --------------------------------------------------------------------------

@@ -73,3 +73,8 @@ ME_CASES = ["int_sr4", "int_sr2", "int_sr16", "float_sr4", "float_sr7", "flat_sr
 
 def case_sr(name):
     return int(name.rsplit("sr", 1)[1])
+
+
+@pytest.fixture(scope="session")
+def g9():
+    return load_golden("g9_entropy.npz")

@@ -376,6 +376,64 @@ def test_zerorun_encode_matches_reference_stream(g1, g6):
     assert np.array_equal(zr.encode(big), O.zerorun_encode(big))
 
 
+def test_zerorun_decode_on_device(g9):
+    """N2, decoding direction (zerorun.py:44-87): blocks, truncation rule and error conditions recorded from the
+    real reference; round trips at 1080p size; cuda tensors in -> cuda tensor out."""
+    zr = ivc.ZeroRunCoder()
+    assert np.array_equal(zr.decode(g9["sym"], (6, 8, 3)), g9["dec_full"])
+    assert np.array_equal(zr.decode(g9["sym"], [6, 8, 1]), g9["dec_trunc"])        # later symbols are ignored
+    assert np.array_equal(zr.decode(g9["sym2"], (5, 7, 3)), g9["blocks"])
+    assert np.array_equal(zr.decode(list(g9["sym2"]), (5, 7, 3)), g9["blocks"])    # the reference is handed lists too
+    with pytest.raises(ValueError, match="Unexpected end"):
+        zr.decode(g9["sym2"][:-1], (5, 7, 3))
+    with pytest.raises(ValueError, match="Expected 140 blocks, got 105"):
+        zr.decode(g9["sym2"], (5, 7, 4))
+    with pytest.raises(ValueError, match="Block size exceeded"):
+        zr.decode(np.concatenate([np.arange(1, 66), [4000]]).astype(np.int32), (1, 1, 1))
+    with pytest.raises(ValueError, match="Block size exceeded"):
+        zr.decode(np.array([7, 0, 4000, 4000], dtype=np.int32), (1, 1, 1))         # EOB value in a run-length slot
+    with pytest.raises(ValueError, match="Expected 2 blocks, got 0"):
+        zr.decode(np.zeros(0, dtype=np.int32), (1, 2, 1))
+    rng = np.random.default_rng(11)
+    for density in (0.0, 0.03, 0.5, 1.0):
+        zz = (rng.integers(-300, 301, size=(9, 11, 3, 64)) * (rng.random((9, 11, 3, 64)) < density)).astype(np.int32)
+        zz[0, 0, 1, 63] = 5
+        zz[0, 0, 2, :] = np.arange(1, 65)
+        sym = O.zerorun_encode(zz)
+        assert np.array_equal(zr.decode(sym, zz.shape[:3]), zz)
+        assert np.array_equal(zr.decode(sym, zz.shape[:3]), O.zerorun_decode(sym, zz.shape[:3]))
+    big = ivc.IntraBlockCoder(0.2).forward(torch.from_numpy(O.rgb2ycbcr(O.smooth_noise_rgb(6, 1080, 1920))).cuda())
+    sym = zr.encode(big)
+    back = zr.decode(sym, big.shape[:3])
+    assert back.is_cuda and back.dtype == torch.int32 and torch.equal(back, big)
+    luma_only = zr.decode(sym, (135, 240, 1))                                      # SURVEY A13: first Hp*Wp blocks
+    assert torch.equal(luma_only.reshape(-1, 64), big.reshape(-1, 64)[:135 * 240])
+
+
+def test_symbol_statistics_match_reference(g9):
+    """N3: stats_marg over the bins IntraCodec.train_huffman_from_image picks (entropy.py:6-29,
+    intracodec.py:160-166), bit-identical pmf; min/max on the device."""
+    lo, hi = int(g9["lo"]), int(g9["hi"])
+    assert ivc.symbol_minmax(g9["sym"]) == (lo + 20, hi - 21)
+    pmf = ivc.stats_marg(g9["sym"], np.arange(lo, hi))
+    assert pmf.dtype == np.float64 and np.array_equal(pmf, g9["pmf"])
+    assert np.array_equal(ivc.stats_marg(g9["sym"], np.arange(-3, 9)), g9["pmf_cut"])      # clipped range, closed last bin
+    assert np.array_equal(ivc.stats_marg(g9["img8"], np.arange(256)), g9["pmf8"])
+    assert np.array_equal(ivc.stats_marg(g9["img8"].astype(np.float64), np.arange(256)), g9["pmf8"])
+    with pytest.raises(NotImplementedError):
+        ivc.stats_marg(g9["sym"], np.arange(0, 64, 2))
+    rng = np.random.default_rng(12)
+    x = rng.integers(-70000, 70001, size=300001).astype(np.int32)                         # wide range: global-atomic path
+    assert np.array_equal(ivc.stats_marg(x, np.arange(-70000, 70002)), O.stats_marg(x, np.arange(-70000, 70002)))
+    assert ivc.symbol_minmax(x) == (int(x.min()), int(x.max()))
+    zz = ivc.IntraBlockCoder(1.0).forward(torch.from_numpy(O.rgb2ycbcr(O.smooth_noise_rgb(7, 1080, 1920))).cuda())
+    sym = ivc.ZeroRunCoder().encode(zz)
+    s = sym.cpu().numpy()
+    b = O.symbol_bounds(s)
+    assert ivc.symbol_minmax(sym) == (b[0] + 20, b[1] - 21)
+    assert np.array_equal(ivc.stats_marg(sym, np.arange(*b)), O.stats_marg(s, np.arange(*b)))
+
+
 def test_metrics_match_reference(g1, g6):
     """N3: calc_mse / calc_psnr (metrics.py:3-40); reduction order differs from numpy's pairwise mean,
     so the comparison is relative 1e-12 (PSNR: far below the 0.01 dB bar)."""

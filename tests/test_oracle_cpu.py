@@ -86,6 +86,24 @@ def test_oracle_qcif_golden(g7):
         assert np.array_equal(O.me_full_search(seq[t - 1], seq[t], 4)[..., 0], g7["mvs"][t - 1][..., 0])
 
 
+def test_oracle_entropy_golden(g9):
+    """Zero-run decoder (incl. the stop-after-h*w*c rule) and stats_marg against outputs recorded from the
+    real reference (oracle/gen_golden_entropy.py)."""
+    assert np.array_equal(O.zerorun_decode(g9["sym"], (6, 8, 3)), g9["dec_full"])
+    assert np.array_equal(O.zerorun_decode(g9["sym"], (6, 8, 1)), g9["dec_trunc"])
+    assert np.array_equal(O.zerorun_encode(g9["blocks"]), g9["sym2"])
+    assert np.array_equal(O.zerorun_decode(g9["sym2"], (5, 7, 3)), g9["blocks"])
+    lo, hi = int(g9["lo"]), int(g9["hi"])
+    assert O.symbol_bounds(g9["sym"]) == (lo, hi)
+    assert np.array_equal(O.stats_marg(g9["sym"], np.arange(lo, hi)), g9["pmf"])
+    assert np.array_equal(O.stats_marg(g9["sym"], np.arange(-3, 9)), g9["pmf_cut"])
+    assert np.array_equal(O.stats_marg(g9["img8"], np.arange(256)), g9["pmf8"])
+    with pytest.raises(ValueError, match="Unexpected end"):
+        O.zerorun_decode(g9["sym2"][:-1], (5, 7, 3))
+    with pytest.raises(ValueError, match="Expected 140 blocks, got 105"):
+        O.zerorun_decode(g9["sym2"], (5, 7, 4))
+
+
 def test_flat_frame_tie_break():
     """all-tie search: interior -> first candidate (index 0), borders -> first in-bounds."""
     z = np.zeros((40, 48))
