@@ -172,6 +172,11 @@ int ivc_zerorun_count(int device, void *stream, const int32_t *zz, int64_t nbloc
 int ivc_zerorun_write(int device, void *stream, const int32_t *zz, int64_t nblocks, int32_t end_of_block,
                       const int64_t *offsets, int32_t *symbols_out);
 
+/* Post n (<= 32) int64 words from device memory to MAPPED pinned host memory with a kernel (no copy engine):
+ * how a pipeline learns a symbol-stream length (the last element of the caller's prefix sum) without the
+ * small copy queueing behind bulk transfers.  dst_mapped: a cudaHostAlloc'd / pinned pointer valid on the device. */
+int ivc_post_words_to_host(int device, void *stream, const int64_t *src, int64_t *dst_mapped, int n);
+
 /* ---- N2 (next row): ZeroRunCoder.decode (ivclab/entropy/zerorun.py:44-87) ---------------------
  * Three passes around an inclusive scan that the caller performs.  mark: is_eob[i] = 1 iff symbols[i] is
  * an end-of-block in a symbol slot (not the run length that follows a zero marker).  ends: with

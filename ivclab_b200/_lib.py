@@ -42,6 +42,7 @@ SIGNATURES = {
     "ivc_sum_squared_error": (_i, [_i, _p, _p, _i, _p, _i, _i64, _i64, _i, _p, _i64, _p]),
     "ivc_zerorun_count": (_i, [_i, _p, _p, _i64, _p]),
     "ivc_zerorun_write": (_i, [_i, _p, _p, _i64, C.c_int32, _p, _p]),
+    "ivc_post_words_to_host": (_i, [_i, _p, _p, _p, _i]),
     "ivc_zerorun_decode_mark": (_i, [_i, _p, _p, _i64, C.c_int32, _p]),
     "ivc_zerorun_decode_ends": (_i, [_i, _p, _p, _p, _i64, _i64, _p]),
     "ivc_zerorun_decode_write": (_i, [_i, _p, _p, _p, _i64, _p, _p]),

@@ -272,6 +272,16 @@ int ivc_zerorun_write(int device, void *stream, const int32_t *zz, int64_t nbloc
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
 
+int ivc_post_words_to_host(int device, void *stream, const int64_t *src, int64_t *dst_mapped, int n) {
+    if (n < 0 || n > 32) return IVC_ERR_ARG;
+    if (n == 0) return IVC_OK;
+    if (!src || !dst_mapped) return IVC_ERR_ARG;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_post_words((cudaStream_t)stream, src, dst_mapped, n);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
 int ivc_zerorun_decode_mark(int device, void *stream, const int32_t *symbols, int64_t n_symbols, int32_t end_of_block,
                             int32_t *is_eob_out) {
     if (n_symbols < 0) return IVC_ERR_ARG;

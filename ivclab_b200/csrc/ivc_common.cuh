@@ -46,6 +46,8 @@ cudaError_t launch_zrd_ends(int device, cudaStream_t st, const int32_t *is_eob, 
 cudaError_t launch_zrd_write(int device, cudaStream_t st, const int32_t *sym, const int64_t *ends, int64_t nblocks,
                              int32_t *out, int *err);
 
+cudaError_t launch_post_words(cudaStream_t st, const int64_t *src, int64_t *dst_mapped, int n);
+
 // symbol statistics (ivc_metrics.cu)
 cudaError_t launch_hist(int device, cudaStream_t st, const void *x, int dtype, int64_t n, int64_t lo, int64_t nbins,
                         int64_t hot, uint64_t *counts);

@@ -177,6 +177,19 @@ __global__ void __launch_bounds__(kZrWarps * 32) k_zrd_write(const int32_t *__re
     }
 }
 
+// A few 64-bit words from device memory into MAPPED pinned host memory, written by a kernel: a pipeline's
+// stream lengths reach the host without queueing behind bulk transfers on the copy engines.
+__global__ void k_post_words(const int64_t *__restrict__ src, volatile int64_t *dst, int n) {
+    if ((int)threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
+}
+
+cudaError_t launch_post_words(cudaStream_t st, const int64_t *src, int64_t *dst_mapped, int n) {
+    if (n == 0) return cudaSuccess;
+    k_post_words<<<1, 32, 0, st>>>(src, dst_mapped, n);
+    return cudaGetLastError();
+}
+
 static int zr_grid(int device, int64_t units, int per_cta) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);

@@ -32,10 +32,13 @@ class ZeroRunCoder:
             raise ValueError(f"expected [h, w, c, 64] (or [n, h, w, c, 64]) scan blocks, got shape {tuple(t.shape)}")
         return aligned16(t.to(torch.int32)), was_np
 
-    def encode_begin(self, flat_patch_img) -> _PendingEncode:
+    def encode_begin(self, flat_patch_img, total_host=None, record=True) -> _PendingEncode:
         """First half of :meth:`encode` without a host synchronisation: counts the symbols of every block,
         scans them and starts an asynchronous copy of the stream length into pinned host memory.  Lets a
-        pipeline enqueue further work before :meth:`encode_finish` waits for that one number."""
+        pipeline enqueue further work before :meth:`encode_finish` waits for that one number.
+        ``total_host``: a caller-owned pinned int64[1] to receive the length (nothing is allocated on the host
+        then -- required inside CUDA-graph capture); ``record=False`` leaves the synchronisation to the caller
+        (who must have waited for this call's work before calling :meth:`encode_finish`)."""
         t, _ = self._check(flat_patch_img)
         p = _PendingEncode()
         p.blocks, p.nblk, p.stream = t, t.numel() // 64, torch.cuda.current_stream(t.device)
@@ -44,21 +47,27 @@ class ZeroRunCoder:
         _lib.check(_lib.lib.ivc_zerorun_count(dev, sp, t.data_ptr(), p.nblk, counts.data_ptr()), "ivc_zerorun_count")
         ends = torch.cumsum(counts, 0, dtype=torch.int64)
         p.offsets = (ends - counts).contiguous()
-        p.total_host = torch.zeros(1, dtype=torch.int64).pin_memory()
-        if p.nblk:
-            p.total_host.copy_(ends[-1:], non_blocking=True)
-        p.event = torch.cuda.Event()
-        p.event.record(p.stream)
+        p.total_host = total_host if total_host is not None else torch.zeros(1, dtype=torch.int64).pin_memory()
+        if p.nblk:                                           # written by a kernel into the mapped pinned word
+            _lib.check(_lib.lib.ivc_post_words_to_host(dev, sp, ends[-1:].data_ptr(), p.total_host.data_ptr(), 1),
+                       "ivc_post_words_to_host")
+        else:
+            p.total_host.zero_()
+        p.event = None
+        if record:
+            p.event = torch.cuda.Event()
+            p.event.record(p.stream)
         return p
 
     def encode_finish(self, p: _PendingEncode) -> torch.Tensor:
         """Second half: waits for the stream length (one event), then writes the symbols on the current stream."""
-        p.event.synchronize()
+        if p.event is not None:
+            p.event.synchronize()
         total = int(p.total_host[0])
         t = p.blocks
         out = torch.empty(total, dtype=torch.int32, device=t.device)
         cur = torch.cuda.current_stream(t.device)
-        if cur != p.stream:
+        if cur != p.stream and p.event is not None:
             cur.wait_event(p.event)
         _lib.check(_lib.lib.ivc_zerorun_write(dev_index(t), stream_ptr(t.device), t.data_ptr(), p.nblk, int(self.EOB),
                                               p.offsets.data_ptr(), out.data_ptr()), "ivc_zerorun_write")

@@ -2,11 +2,20 @@
 and the results of chunk k-1 are downloaded, on three CUDA streams with pinned staging buffers.
 
 This is the form in which the path is fed from HOST memory (what ``bench.py`` reports as ``e2e``):
-uint8 RGB frames and uint8 luma planes go up (4-5 bytes per pixel), zero-run symbol streams, motion
+uint8 RGB frames and uint8 luma planes go up (5 bytes per pixel), zero-run symbol streams, motion
 vectors and squared errors come back; the colour transform, both transform loops, the motion search,
 the zero-run coder and the error reduction all run on the device in between.  Frames are independent
-(intra) or frame pairs (inter), so chunks never depend on each other."""
+(intra) or frame pairs (inter), so chunks never depend on each other.
+
+Two things keep the device busy rather than waiting for Python:
+* the ~25 launches that code one chunk are captured ONCE per input slot as a CUDA graph (the slots and the
+  graph's outputs are static buffers) and replayed with a single call per chunk;
+* the only host-dependent step -- sizing the symbol streams -- is software-pipelined: the host waits for the
+  two stream lengths of chunk k-1 (copied to pinned memory inside the graph) only after chunk k's graph has
+  been enqueued."""
 from __future__ import annotations
+
+import time
 
 import numpy as np
 import torch
@@ -20,26 +29,93 @@ from .utils.metrics import frame_sse
 __all__ = ["StreamedCoder"]
 
 
+class _Slot:
+    """Static device buffers of one pipeline slot, the graph that codes them and that graph's outputs."""
+    __slots__ = ("rgb", "cur", "ref", "graph", "out", "totals")
+
+
 class StreamedCoder:
-    def __init__(self, quantization_scale=1.0, search_range=4, me_mode="auto", chunk_frames=2, device=None):
+    def __init__(self, quantization_scale=1.0, search_range=4, me_mode="auto", chunk_frames=2, device=None, use_graph=True):
         self.intra = IntraBlockCoder(quantization_scale)
         self.pframe = PFrameBlockCoder(quantization_scale, search_range, me_mode)
         self.zr = ZeroRunCoder()
         self.chunk = int(chunk_frames)
+        self.use_graph = bool(use_graph)
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self._s_in, self._s_cmp, self._s_out = (torch.cuda.Stream(self.device) for _ in range(3))
         self._host = None
+        self._slots = None         # ((C, H, W), [_Slot, _Slot])
+        self.trace = None          # set to [] to collect (label, chunk, start event, end event, host t0, host t1) per stage
 
+    # ---- buffers -------------------------------------------------------------------------------
     def _host_buffers(self, F, H, W):
         key = (F, H, W)
         if self._host is None or self._host[0] != key:
             nb = (H // 8) * (W // 8)
             pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
             self._host = (key, {
-                "sym_intra": pin(F * nb * 3 * 65, torch.int32), "sym_inter": pin(F * nb * 3 * 65, torch.int32),
+                # symbol streams: room for 24 symbols per block to start with (a block emits 1..97); grown on demand
+                "sym_intra": pin(F * nb * 3 * 24, torch.int32), "sym_inter": pin(F * nb * 3 * 24, torch.int32),
                 "mv": pin((F, H // 8, W // 8, 1), torch.int64), "sse": pin((2, F), torch.float64)})
         return self._host[1]
 
+    def _device_slots(self, C, H, W):
+        key = (C, H, W)
+        if self._slots is None or self._slots[0] != key:
+            slots = []
+            for _ in range(2):
+                s = _Slot()
+                s.rgb = torch.empty((C, H, W, 3), dtype=torch.uint8, device=self.device)
+                s.cur = torch.empty((C, H, W), dtype=torch.uint8, device=self.device)
+                s.ref = torch.empty((C, H, W), dtype=torch.uint8, device=self.device)
+                s.graph, s.out = None, None
+                s.totals = torch.zeros(2, dtype=torch.int64).pin_memory()      # the two stream lengths of the chunk in flight
+                slots.append(s)
+            self._slots = (key, slots)
+        return self._slots[1]
+
+    def _mark(self, label, k, stream):
+        """Tracing aid: returns a function that closes the interval opened here (no-op unless ``self.trace`` is a list)."""
+        if self.trace is None:
+            return lambda: None
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        t0 = time.perf_counter()
+
+        def close():
+            b.record(stream)
+            self.trace.append((label, k, a, b, t0, time.perf_counter()))
+        return close
+
+    # ---- one chunk on the device -------------------------------------------------------------------
+    def _code(self, s: _Slot, n: int):
+        """Everything of a chunk that does not need a stream length on the host (current stream = compute stream)."""
+        d_rgb, d_cur, d_ref = s.rgb[:n], s.cur[:n].double(), s.ref[:n].double()
+        zz = self.intra.forward_rgb(d_rgb)
+        pend_i = self.zr.encode_begin(zz, total_host=s.totals[0:1], record=False)
+        rec = self.intra.inverse(zz)
+        sse_i = frame_sse(rgb2ycbcr(d_rgb), rec)
+        mv = self.pframe.estimate(d_ref, d_cur)
+        zzp = self.pframe.forward(d_cur, d_ref, mv)
+        pend_p = self.zr.encode_begin(zzp, total_host=s.totals[1:2], record=False)
+        recp = self.pframe.inverse(zzp, ref=d_ref, mv=mv)
+        sse_p = frame_sse(d_cur, recp)
+        return pend_i, pend_p, mv, sse_i, sse_p
+
+    def _launch(self, s: _Slot, n: int, C: int):
+        if not self.use_graph or n != C:
+            return self._code(s, n)                     # partial last chunk (or graphs disabled): eager launches
+        if s.graph is None:
+            self._code(s, n)                            # warm-up outside capture (function attributes, workspaces)
+            torch.cuda.current_stream(self.device).synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=torch.cuda.current_stream(self.device)):
+                s.out = self._code(s, n)
+            s.graph = g
+        s.graph.replay()
+        return s.out
+
+    # ---- the pipeline ----------------------------------------------------------------------------
     def run(self, rgb, cur, ref):
         """rgb [F,H,W,3] uint8, cur/ref [F,H,W] uint8 luma planes -- pinned host tensors (numpy arrays are
         accepted and pinned once).  Returns host-side results: ``sym_intra`` / ``sym_inter`` (int32 streams
@@ -48,16 +124,16 @@ class StreamedCoder:
         rgb, cur, ref = (t if t.is_pinned() else t.pin_memory() for t in map(pinned, (rgb, cur, ref)))
         F, H, W, _ = rgb.shape
         hb = self._host_buffers(F, H, W)
-        dev = self.device
         C = self.chunk
         nchunks = (F + C - 1) // C
-        slots = [{"rgb": torch.empty((C, H, W, 3), dtype=torch.uint8, device=dev),
-                  "cur": torch.empty((C, H, W), dtype=torch.uint8, device=dev),
-                  "ref": torch.empty((C, H, W), dtype=torch.uint8, device=dev)} for _ in range(2)]
+        slots = self._device_slots(C, H, W)
         ev_in = [torch.cuda.Event() for _ in range(nchunks)]
         ev_cmp = [torch.cuda.Event() for _ in range(nchunks)]
+        ev_fin = [torch.cuda.Event() for _ in range(nchunks)]
         ev_out = [torch.cuda.Event() for _ in range(nchunks)]
-        keep = {}                                     # device results of in-flight chunks
+        lens_i, lens_p = [], []
+        off = [0, 0]
+        pending = {}                                  # chunk -> device results whose symbol streams are not written yet
 
         def upload(k):
             lo, hi = k * C, min(F, (k + 1) * C)
@@ -65,51 +141,71 @@ class StreamedCoder:
                 if k >= 2:
                     self._s_in.wait_event(ev_cmp[k - 2])          # the slot's previous chunk has been consumed
                 s = slots[k & 1]
-                for name, src in (("rgb", rgb), ("cur", cur), ("ref", ref)):
-                    s[name][:hi - lo].copy_(src[lo:hi], non_blocking=True)
+                done = self._mark("h2d", k, self._s_in)
+                for dst, src in ((s.rgb, rgb), (s.cur, cur), (s.ref, ref)):
+                    dst[:hi - lo].copy_(src[lo:hi], non_blocking=True)
+                done()
                 ev_in[k].record(self._s_in)
 
-        lens_i, lens_p = [], []
-        off_i = off_p = 0
-        upload(0)
-        for k in range(nchunks):
-            lo, hi = k * C, min(F, (k + 1) * C)
-            n = hi - lo
-            if k + 1 < nchunks:
-                upload(k + 1)                                      # overlaps with the work below
+        def compute(k):
+            n = min(F, (k + 1) * C) - k * C
             with torch.cuda.stream(self._s_cmp):
                 self._s_cmp.wait_event(ev_in[k])
-                s = slots[k & 1]
-                d_rgb, d_cur, d_ref = s["rgb"][:n], s["cur"][:n].double(), s["ref"][:n].double()
-                zz = self.intra.forward_rgb(d_rgb)
-                rec = self.intra.inverse(zz)
-                sse_i = frame_sse(rgb2ycbcr(d_rgb), rec)
-                mv = self.pframe.estimate(d_ref, d_cur)
-                zzp = self.pframe.forward(d_cur, d_ref, mv)
-                recp = self.pframe.inverse(zzp, ref=d_ref, mv=mv)
-                sse_p = frame_sse(d_cur, recp)
-                sym_i = self.zr.encode(zz)                         # (reads the stream lengths: syncs this stream only)
-                sym_p = self.zr.encode(zzp)
-                ev_cmp[k].record(self._s_cmp)
+                if k >= 2:
+                    self._s_cmp.wait_event(ev_fin[k - 2])          # the slot's previous results have been picked up
+                done = self._mark("code", k, self._s_cmp)
+                pending[k] = self._launch(slots[k & 1], n, C)
+                done()
+                ev_cmp[k].record(self._s_cmp)                      # the input slot may be overwritten from here on
+
+        def finish(k):
+            """Write chunk k's symbol streams (their lengths have arrived by now) and send the results home."""
+            lo, hi = k * C, min(F, (k + 1) * C)
+            pend_i, pend_p, mv, sse_i, sse_p = pending.pop(k)
+            ev_cmp[k].synchronize()                                # waits for TWO numbers, with chunk k+1 already queued
+            with torch.cuda.stream(self._s_cmp):
+                tr = self._mark("symbols", k, self._s_cmp)
+                sym_i = self.zr.encode_finish(pend_i)
+                sym_p = self.zr.encode_finish(pend_p)
+                mv, sse_i, sse_p = mv.clone(), sse_i.clone(), sse_p.clone()     # frees the slot's (static) result buffers
+                tr()
+                ev_fin[k].record(self._s_cmp)
+            for name, o, sym in (("sym_intra", off[0], sym_i), ("sym_inter", off[1], sym_p)):
+                if o + sym.numel() > hb[name].numel():             # rare: denser streams than provisioned
+                    self._s_out.synchronize()                      # earlier downloads into the old buffer are complete
+                    grown = torch.empty(max(2 * hb[name].numel(), o + sym.numel()), dtype=torch.int32).pin_memory()
+                    grown[:o].copy_(hb[name][:o])
+                    hb[name] = grown
             with torch.cuda.stream(self._s_out):
-                self._s_out.wait_event(ev_cmp[k])
+                self._s_out.wait_event(ev_fin[k])
                 for t in (sym_i, sym_p, mv, sse_i, sse_p):
                     t.record_stream(self._s_out)
-                hb["sym_intra"][off_i:off_i + sym_i.numel()].copy_(sym_i, non_blocking=True)
-                hb["sym_inter"][off_p:off_p + sym_p.numel()].copy_(sym_p, non_blocking=True)
+                tr = self._mark("d2h", k, self._s_out)
+                hb["sym_intra"][off[0]:off[0] + sym_i.numel()].copy_(sym_i, non_blocking=True)
+                hb["sym_inter"][off[1]:off[1] + sym_p.numel()].copy_(sym_p, non_blocking=True)
                 hb["mv"][lo:hi].copy_(mv, non_blocking=True)
                 hb["sse"][0, lo:hi].copy_(sse_i, non_blocking=True)
                 hb["sse"][1, lo:hi].copy_(sse_p, non_blocking=True)
+                tr()
                 ev_out[k].record(self._s_out)
-            keep[k] = (sym_i, sym_p, mv, sse_i, sse_p)
-            keep.pop(k - 2, None)
             lens_i.append(sym_i.numel())
             lens_p.append(sym_p.numel())
-            off_i += sym_i.numel()
-            off_p += sym_p.numel()
+            off[0] += sym_i.numel()
+            off[1] += sym_p.numel()
+
+        # software pipeline on the host: chunk k is enqueued BEFORE the host waits for the stream lengths of chunk
+        # k-1, so the device always has work queued and the host never waits on fresh work
+        upload(0)
+        for k in range(nchunks):
+            if k + 1 < nchunks:
+                upload(k + 1)
+            compute(k)
+            if k >= 1:
+                finish(k - 1)
+        finish(nchunks - 1)
         ev_out[-1].synchronize()
         self._s_cmp.synchronize()
-        return {"sym_intra": hb["sym_intra"][:off_i], "sym_inter": hb["sym_inter"][:off_p], "len_intra": lens_i,
+        return {"sym_intra": hb["sym_intra"][:off[0]], "sym_inter": hb["sym_inter"][:off[1]], "len_intra": lens_i,
                 "len_inter": lens_p, "mv": hb["mv"], "sse": hb["sse"],
                 "h2d_bytes": rgb.numel() + cur.numel() + ref.numel(),
-                "d2h_bytes": (off_i + off_p) * 4 + hb["mv"].numel() * 8 + hb["sse"].numel() * 8}
+                "d2h_bytes": (off[0] + off[1]) * 4 + hb["mv"].numel() * 8 + hb["sse"].numel() * 8}
