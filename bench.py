@@ -48,7 +48,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--frames", type=int, default=32, help="resident 1080p frames per GPU")
-    ap.add_argument("--e2e-frames", type=int, default=8)
+    ap.add_argument("--e2e-frames", type=int, default=0, help="frames per host-fed step (0 = the same as --frames)")
+    ap.add_argument("--e2e-aux-frames", type=int, default=8, help="frames per step of the two secondary host-fed legs")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the host-fed legs (e2e keys become null)")
@@ -246,7 +247,8 @@ def run_b200(args):
 
     e2e_ms = serial_ms = raw_ms = e2e_val = raw_val = None
     h2d = d2h = raw_h2d = raw_d2h = None
-    Fe = min(args.e2e_frames, Fr)
+    Fe = min(args.e2e_frames or Fr, Fr)
+    Fa = min(args.e2e_aux_frames, Fr)
     if not args.no_e2e:
         # ---- e2e through the public API, host buffers in pinned memory ----
         # (a) "codec" form: what a caller of IntraCodec.image2symbols / the video codecs hands over and gets back --
@@ -254,7 +256,6 @@ def run_b200(args):
         #     colour transform (N1), zero-run coding (N2) and the squared-error reduction (N3) run on the device so
         #     only compact data crosses PCIe.  Same transform / ME work per pixel as `value`.
         # (b) "raw" form: float64 planes in, raw int32 scan indices out (the per-method classes' array types).
-        Fe = min(args.e2e_frames, Fr)
         intra = ivc.IntraBlockCoder(QSCALE)
         pcod = ivc.PFrameBlockCoder(QSCALE, SR, me_mode=args.me_mode)
         zr = ivc.ZeroRunCoder()
@@ -264,16 +265,16 @@ def run_b200(args):
         h_rgb = rgb8.cpu().pin_memory()
         h_l8 = luma[:Fe].to(torch.uint8).cpu().pin_memory()
         h_r8 = ref[:Fe].to(torch.uint8).cpu().pin_memory()
-        h_mv = torch.empty((Fe, Hp, Wp, 1), dtype=torch.int64).pin_memory()
-        h_stat = torch.empty((2, Fe), dtype=torch.float64).pin_memory()
+        h_mv = torch.empty((Fa, Hp, Wp, 1), dtype=torch.int64).pin_memory()
+        h_stat = torch.empty((2, Fa), dtype=torch.float64).pin_memory()
         sym_bytes = [0]
-        h_sym_i = torch.empty(Fe * Hp * Wp * 3 * 65, dtype=torch.int32).pin_memory()     # generous bound on the stream length
-        h_sym_p = torch.empty(Fe * Hp * Wp * 3 * 65, dtype=torch.int32).pin_memory()
+        h_sym_i = torch.empty(Fa * Hp * Wp * 3 * 97, dtype=torch.int32).pin_memory()     # a block emits at most 97 symbols
+        h_sym_p = torch.empty(Fa * Hp * Wp * 3 * 97, dtype=torch.int32).pin_memory()
 
-        def e2e_step():
-            d_rgb = to_device(h_rgb)[0]                       # the API uploads the pinned HOST buffers itself
-            d_l = to_device(h_l8)[0].double()
-            d_r = to_device(h_r8)[0].double()
+        def e2e_step():                                       # secondary leg: one stream, Fa frames
+            d_rgb = to_device(h_rgb[:Fa])[0]                  # the API uploads the pinned HOST buffers itself
+            d_l = to_device(h_l8[:Fa])[0].double()
+            d_r = to_device(h_r8[:Fa])[0].double()
             z = intra.forward_rgb(d_rgb)                      # rgb2ycbcr + DCT + quantise + zig-zag
             s_i = zr.encode(z)                                # symbols go to the host (entropy coder input)
             h_sym_i[:s_i.numel()].copy_(s_i, non_blocking=True)
@@ -290,11 +291,11 @@ def run_b200(args):
             torch.cuda.synchronize()
             sym_bytes[0] = (s_i.numel() + s_p.numel()) * 4
 
-        h_y = ycbcr[:Fe].cpu().pin_memory()
-        h_l = luma[:Fe].cpu().pin_memory()
-        h_r = ref[:Fe].cpu().pin_memory()
-        h_zz_i = torch.empty((Fe, Hp, Wp, 3, 64), dtype=torch.int32).pin_memory()
-        h_zz_p = torch.empty((Fe, Hp, Wp, 3, 64), dtype=torch.int32).pin_memory()
+        h_y = ycbcr[:Fa].cpu().pin_memory()
+        h_l = luma[:Fa].cpu().pin_memory()
+        h_r = ref[:Fa].cpu().pin_memory()
+        h_zz_i = torch.empty((Fa, Hp, Wp, 3, 64), dtype=torch.int32).pin_memory()
+        h_zz_p = torch.empty((Fa, Hp, Wp, 3, 64), dtype=torch.int32).pin_memory()
 
         def e2e_raw_step():
             d_y = to_device(h_y)[0]
@@ -339,7 +340,7 @@ def run_b200(args):
         h2d = last[0]["h2d_bytes"]
         d2h = last[0]["d2h_bytes"]
         raw_ms = time_e2e(e2e_raw_step)
-        raw_val = world * Fe * H * W / (raw_ms * 1e-3) / 1e6
+        raw_val = world * Fa * H * W / (raw_ms * 1e-3) / 1e6
         raw_h2d = h_y.numel() * 8 + h_l.numel() * 8 + h_r.numel() * 8
         raw_d2h = h_zz_i.numel() * 4 + h_zz_p.numel() * 4 + h_mv.numel() * 8 + h_stat.numel() * 8
 
@@ -367,11 +368,14 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(Fr, world),
             "e2e": None if args.no_e2e else {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "frames_per_step": Fe, "ms_per_step": round(e2e_ms, 3), "ms_per_step_single_stream": round(serial_ms, 3),
-                    "api": "StreamedCoder.run (3 streams, 2-frame chunks): pinned host uint8 RGB + uint8 luma in; IntraBlockCoder.forward_rgb/inverse, PFrameBlockCoder."
-                           "estimate/forward/inverse, ZeroRunCoder.encode, frame_sse; zero-run symbols + MVs + SSE back to host"},
+                    "frames_per_step": Fe, "ms_per_step": round(e2e_ms, 3),
+                    "single_stream": {"frames_per_step": Fa, "ms_per_step": round(serial_ms, 3),
+                                      "value": round(world * Fa * H * W / (serial_ms * 1e-3) / 1e6, 1)},
+                    "api": "StreamedCoder.run (3 streams, 2-frame chunks, one CUDA graph per slot): pinned host uint8 RGB + uint8 luma in; "
+                           "IntraBlockCoder.forward_rgb/inverse, PFrameBlockCoder.estimate/forward/inverse, ZeroRunCoder.encode, "
+                           "frame_sse; zero-run symbols + MVs + SSE back to host"},
             "e2e_raw": None if args.no_e2e else {"value": round(raw_val, 1), "unit": UNIT, "h2d_bytes_per_step": raw_h2d, "d2h_bytes_per_step": raw_d2h,
-                        "frames_per_step": Fe, "ms_per_step": round(raw_ms, 3),
+                        "frames_per_step": Fa, "ms_per_step": round(raw_ms, 3),
                         "api": "pinned host float64 YCbCr + luma in, raw int32 scan indices + MVs + SSE out (PCIe-bound)"},
             "gpu_launches": K * launches_per_step,
             "clocks": clk,

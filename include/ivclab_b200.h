@@ -155,8 +155,11 @@ int ivc_pframe_inverse(int device, void *stream,
 /* ---- N3 (next row): calc_mse / calc_psnr (ivclab/utils/metrics.py:3-40) ------------------------
  * sse_out[u] = sum_i (double(a[u][i / a_broadcast]) - double(b[u][i]))^2 over unit_elems elements of b,
  * for n_units units (frames).  a_broadcast = 3 pairs a gray `a` with an RGB `b` (metrics.py:16-19),
- * else 1.  Deterministic two-stage reduction; mse = sse / unit_elems, psnr = 20*log10(max/sqrt(mse))
+ * else 1; a_broadcast = IVC_SSE_RGB8_AS_YCBCR takes a = uint8 RGB and b = float64 YCbCr of the same shape and
+ * compares rgb2ycbcr(a) with b without materialising it (same bits as the two-step form).
+ * Deterministic two-stage reduction; mse = sse / unit_elems, psnr = 20*log10(max/sqrt(mse))
  * are left to the caller.  workspace: ivc_sse_workspace_bytes() bytes. */
+#define IVC_SSE_RGB8_AS_YCBCR 103
 int64_t ivc_sse_workspace_bytes(int64_t n_units, int64_t unit_elems);
 int ivc_sum_squared_error(int device, void *stream,
                           const void *a, int a_dtype, const void *b, int b_dtype,
@@ -171,6 +174,12 @@ int ivc_sum_squared_error(int device, void *stream,
 int ivc_zerorun_count(int device, void *stream, const int32_t *zz, int64_t nblocks, int32_t *counts_out);
 int ivc_zerorun_write(int device, void *stream, const int32_t *zz, int64_t nblocks, int32_t end_of_block,
                       const int64_t *offsets, int32_t *symbols_out);
+/* The same two passes with the per-block 64-bit non-zero masks handed from the first to the second
+ * (masks: nblocks uint64): the write pass then fetches only the parts of each block that hold symbols. */
+int ivc_zerorun_count_masks(int device, void *stream, const int32_t *zz, int64_t nblocks, int32_t *counts_out,
+                            uint64_t *masks_out);
+int ivc_zerorun_write_masks(int device, void *stream, const int32_t *zz, int64_t nblocks, int32_t end_of_block,
+                            const int64_t *offsets, const uint64_t *masks, int32_t *symbols_out);
 
 /* Post n (<= 32) int64 words from device memory to MAPPED pinned host memory with a kernel (no copy engine):
  * how a pipeline learns a symbol-stream length (the last element of the caller's prefix sum) without the

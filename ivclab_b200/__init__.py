@@ -20,11 +20,11 @@ from .install import inject, install
 from .quantization import PatchQuant
 from .signal import DiscreteCosineTransform, rgb2ycbcr, ycbcr2rgb
 from .streaming import StreamedCoder
-from .utils import Patcher, ZigZag, calc_mse, calc_psnr, frame_sse
+from .utils import Patcher, ZigZag, calc_mse, calc_psnr, frame_sse, frame_sse_rgb8_vs_ycbcr
 from .video import ClosedLoopLumaCoder, MotionCompensator
 
 __version__ = "0.1.0"
 __all__ = ["DiscreteCosineTransform", "PatchQuant", "ZigZag", "Patcher", "MotionCompensator",
            "IntraBlockCoder", "PFrameBlockCoder", "ClosedLoopLumaCoder", "ZeroRunCoder", "calc_mse", "calc_psnr",
-           "frame_sse", "rgb2ycbcr", "ycbcr2rgb", "StreamedCoder", "stats_marg", "symbol_minmax", "symbol_histogram",
+           "frame_sse", "frame_sse_rgb8_vs_ycbcr", "rgb2ycbcr", "ycbcr2rgb", "StreamedCoder", "stats_marg", "symbol_minmax", "symbol_histogram",
            "install", "inject"]

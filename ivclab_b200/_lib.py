@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "_C", "libivcb200.so")
 # element type codes (include/ivclab_b200.h)
 U8, I32, F32, F64, I64 = 0, 1, 2, 3, 4
 ME_AUTO, ME_EXACT, ME_INT = 0, 1, 2
+SSE_RGB8_AS_YCBCR = 103
 OK, ERR_ARG, ERR_DTYPE, ERR_SHAPE, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4, -5
 
 _i, _i64, _p = C.c_int, C.c_int64, C.c_void_p
@@ -42,6 +43,8 @@ SIGNATURES = {
     "ivc_sum_squared_error": (_i, [_i, _p, _p, _i, _p, _i, _i64, _i64, _i, _p, _i64, _p]),
     "ivc_zerorun_count": (_i, [_i, _p, _p, _i64, _p]),
     "ivc_zerorun_write": (_i, [_i, _p, _p, _i64, C.c_int32, _p, _p]),
+    "ivc_zerorun_count_masks": (_i, [_i, _p, _p, _i64, _p, _p]),
+    "ivc_zerorun_write_masks": (_i, [_i, _p, _p, _i64, C.c_int32, _p, _p, _p]),
     "ivc_post_words_to_host": (_i, [_i, _p, _p, _p, _i]),
     "ivc_zerorun_decode_mark": (_i, [_i, _p, _p, _i64, C.c_int32, _p]),
     "ivc_zerorun_decode_ends": (_i, [_i, _p, _p, _p, _i64, _i64, _p]),

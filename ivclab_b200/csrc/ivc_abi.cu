@@ -237,9 +237,11 @@ int64_t ivc_sse_workspace_bytes(int64_t n_units, int64_t unit_elems) {
 int ivc_sum_squared_error(int device, void *stream, const void *a, int a_dtype, const void *b, int b_dtype,
                           int64_t n_units, int64_t unit_elems, int a_broadcast, void *workspace, int64_t workspace_bytes,
                           double *sse_out) {
-    if (n_units < 0 || unit_elems < 0 || (a_broadcast != 1 && a_broadcast != 3)) return IVC_ERR_ARG;
+    if (n_units < 0 || unit_elems < 0 || (a_broadcast != 1 && a_broadcast != 3 && a_broadcast != IVC_SSE_RGB8_AS_YCBCR))
+        return IVC_ERR_ARG;
+    if (a_broadcast == IVC_SSE_RGB8_AS_YCBCR && (a_dtype != IVC_U8 || b_dtype != IVC_F64)) return IVC_ERR_DTYPE;
     if (elem_size(a_dtype) == 0 || elem_size(b_dtype) == 0) return IVC_ERR_DTYPE;
-    if (a_broadcast == 3 && unit_elems % 3) return IVC_ERR_SHAPE;
+    if (a_broadcast != 1 && unit_elems % 3) return IVC_ERR_SHAPE;
     if (n_units == 0) return IVC_OK;
     if (!sse_out) return IVC_ERR_ARG;
     if (unit_elems > 0 && (!a || !b)) return IVC_ERR_ARG;
@@ -257,7 +259,29 @@ int ivc_zerorun_count(int device, void *stream, const int32_t *zz, int64_t nbloc
     if (!zz || !counts_out || !aligned16(zz)) return IVC_ERR_ARG;
     int rc = enter(device);
     if (rc) return rc;
-    cudaError_t e = ivc::launch_zr_count(device, (cudaStream_t)stream, zz, nblocks, counts_out);
+    cudaError_t e = ivc::launch_zr_count(device, (cudaStream_t)stream, zz, nblocks, counts_out, nullptr);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
+int ivc_zerorun_count_masks(int device, void *stream, const int32_t *zz, int64_t nblocks, int32_t *counts_out,
+                            uint64_t *masks_out) {
+    if (nblocks < 0) return IVC_ERR_ARG;
+    if (nblocks == 0) return IVC_OK;
+    if (!zz || !counts_out || !masks_out || !aligned16(zz)) return IVC_ERR_ARG;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_zr_count(device, (cudaStream_t)stream, zz, nblocks, counts_out, masks_out);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
+int ivc_zerorun_write_masks(int device, void *stream, const int32_t *zz, int64_t nblocks, int32_t end_of_block,
+                            const int64_t *offsets, const uint64_t *masks, int32_t *symbols_out) {
+    if (nblocks < 0) return IVC_ERR_ARG;
+    if (nblocks == 0) return IVC_OK;
+    if (!zz || !offsets || !masks || !symbols_out || !aligned16(zz)) return IVC_ERR_ARG;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_zr_write(device, (cudaStream_t)stream, zz, nblocks, end_of_block, offsets, masks, symbols_out);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
 
@@ -268,7 +292,7 @@ int ivc_zerorun_write(int device, void *stream, const int32_t *zz, int64_t nbloc
     if (!zz || !offsets || !symbols_out || !aligned16(zz)) return IVC_ERR_ARG;
     int rc = enter(device);
     if (rc) return rc;
-    cudaError_t e = ivc::launch_zr_write(device, (cudaStream_t)stream, zz, nblocks, end_of_block, offsets, symbols_out);
+    cudaError_t e = ivc::launch_zr_write(device, (cudaStream_t)stream, zz, nblocks, end_of_block, offsets, nullptr, symbols_out);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
 

@@ -6,6 +6,7 @@
 // shuffle/shared tree; stage 2 lets one warp add the chunk partials of a unit in a fixed order.  The
 // result differs from numpy's pairwise mean only by summation order (relative ~1e-15); the parity
 // tests use a 1e-12 relative tolerance, far inside the north star's 0.01 dB PSNR bar.
+#include "ivc_color.cuh"
 #include "ivc_common.cuh"
 
 namespace ivc {
@@ -38,13 +39,29 @@ __global__ void __launch_bounds__(kSseThreads) k_sse_stage1(const SseArgs s) {
     const int chunk = blockIdx.x % s.chunks;
     const int64_t per = (s.unit_elems + s.chunks - 1) / s.chunks;
     const int64_t lo = chunk * per, hi = min(s.unit_elems, lo + per);
-    const int64_t a_unit = s.unit_elems / s.a_div;
+    const int64_t a_unit = s.unit_elems / (s.a_div == 3 ? 3 : 1);
     double acc = 0.0;
     if (s.a_dtype == IVC_F64 && s.b_dtype == IVC_F64 && s.a_div == 1) {
         const double *pa = (const double *)s.a + unit * s.unit_elems, *pb = (const double *)s.b + unit * s.unit_elems;
         for (int64_t i = lo + threadIdx.x; i < hi; i += kSseThreads) {
             const double d = pa[i] - pb[i];
             acc += d * d;
+        }
+    } else if (s.a_div == IVC_SSE_RGB8_AS_YCBCR) {
+        // a = uint8 RGB, compared in YCbCr space (rgb2ycbcr fused in, color.py:27-36): element i is channel i % 3 of
+        // pixel i / 3, visited in exactly the order of the float64 path above, so both give the same bits
+        const unsigned char *pa = (const unsigned char *)s.a + unit * s.unit_elems;
+        const double *pb = (const double *)s.b + unit * s.unit_elems;
+        int64_t i = lo + threadIdx.x;
+        int64_t px = i / 3;
+        int c = (int)(i - 3 * px);
+        for (; i < hi; i += kSseThreads) {
+            double y, cb, cr;
+            rgb2ycbcr_px((double)pa[3 * px], (double)pa[3 * px + 1], (double)pa[3 * px + 2], y, cb, cr);
+            const double d = (c == 0 ? y : (c == 1 ? cb : cr)) - pb[i];
+            acc += d * d;
+            px += kSseThreads / 3;                                   // 256 = 3 * 85 + 1
+            if (++c == 3) { c = 0; ++px; }
         }
     } else {
         for (int64_t i = lo + threadIdx.x; i < hi; i += kSseThreads) {

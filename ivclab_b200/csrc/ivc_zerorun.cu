@@ -29,12 +29,15 @@ __device__ __forceinline__ unsigned long long zr_run_starts(unsigned long long m
     return ~m & ((m << 1) | 1ull) & below_top;
 }
 
+// counts[b] = symbols of block b; masks[b] (optional) = its 64-bit non-zero mask, which lets the write pass skip
+// the parts of a block that hold no symbol (most of it, for typical quantised blocks)
 __global__ void __launch_bounds__(kZrWarps * 32) k_zr_count(const int32_t *__restrict__ zz, int64_t nblocks,
-                                                            int32_t *__restrict__ counts) {
+                                                            int32_t *__restrict__ counts, unsigned long long *__restrict__ masks) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * kZrWarps + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * kZrWarps;
     for (int64_t blk0 = warp * 32; blk0 < nblocks; blk0 += nw * 32) {                 // 32 blocks per warp and round
         int mine = 0;
+        unsigned long long mine_m = 0;
 #pragma unroll 1
         for (int sub = 0; sub < 32; sub += kZrBatch) {
             int a[kZrBatch], b[kZrBatch];
@@ -53,28 +56,41 @@ __global__ void __launch_bounds__(kZrWarps * 32) k_zr_count(const int32_t *__res
                                              ((unsigned long long)__ballot_sync(0xffffffffu, b[j] != 0) << 32);
                 int c = 1;                                                            // EOB
                 if (m) c += __popcll(m) + 2 * __popcll(zr_run_starts(m));
-                if (lane == sub + j) mine = c;
+                if (lane == sub + j) { mine = c; mine_m = m; }
             }
         }
-        if (blk0 + lane < nblocks) counts[blk0 + lane] = mine;
+        if (blk0 + lane < nblocks) {
+            counts[blk0 + lane] = mine;
+            if (masks) masks[blk0 + lane] = mine_m;
+        }
     }
 }
 
+// masks == nullptr: the masks are recomputed from the blocks (every block is read whole).  With masks, a lane
+// loads its coefficient only if it is non-zero, so only the 32-byte sectors that hold symbols are fetched.
+template <bool MASKS>
 __global__ void __launch_bounds__(kZrWarps * 32) k_zr_write(const int32_t *__restrict__ zz, int64_t nblocks, int32_t eob,
-                                                            const int64_t *__restrict__ offsets, int32_t *__restrict__ out) {
+                                                            const int64_t *__restrict__ offsets,
+                                                            const unsigned long long *__restrict__ masks, int32_t *__restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * kZrWarps + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * kZrWarps;
     const unsigned long long low0 = (1ull << lane) - 1ull, low1 = (1ull << (lane + 32)) - 1ull;
     for (int64_t blk0 = warp * 32; blk0 < nblocks; blk0 += nw * 32) {
         const int64_t my_off = blk0 + lane < nblocks ? offsets[blk0 + lane] : 0;
+        const unsigned long long my_m = (MASKS && blk0 + lane < nblocks) ? masks[blk0 + lane] : 0ull;
 #pragma unroll 1
         for (int sub = 0; sub < 32; sub += kZrBatch) {
             int a[kZrBatch], b[kZrBatch];
+            unsigned long long mm[kZrBatch];
 #pragma unroll
             for (int j = 0; j < kZrBatch; ++j) {
                 const int64_t blk = blk0 + sub + j;
                 a[j] = b[j] = 0;
-                if (blk < nblocks) {
+                if (MASKS) {
+                    mm[j] = __shfl_sync(0xffffffffu, my_m, sub + j);               // 0 past the last block
+                    if ((mm[j] >> lane) & 1ull) a[j] = __ldg(zz + blk * 64 + lane);
+                    if ((mm[j] >> (lane + 32)) & 1ull) b[j] = __ldg(zz + blk * 64 + 32 + lane);
+                } else if (blk < nblocks) {
                     a[j] = __ldg(zz + blk * 64 + lane);
                     b[j] = __ldg(zz + blk * 64 + 32 + lane);
                 }
@@ -83,8 +99,9 @@ __global__ void __launch_bounds__(kZrWarps * 32) k_zr_write(const int32_t *__res
             for (int j = 0; j < kZrBatch; ++j) {
                 const int64_t off = __shfl_sync(0xffffffffu, my_off, sub + j);
                 if (blk0 + sub + j >= nblocks) break;                                 // warp-uniform
-                const unsigned long long m = (unsigned long long)__ballot_sync(0xffffffffu, a[j] != 0) |
-                                             ((unsigned long long)__ballot_sync(0xffffffffu, b[j] != 0) << 32);
+                const unsigned long long m = MASKS ? mm[j]
+                                                   : (unsigned long long)__ballot_sync(0xffffffffu, a[j] != 0) |
+                                                         ((unsigned long long)__ballot_sync(0xffffffffu, b[j] != 0) << 32);
                 int32_t *o = out + off;
                 if (m == 0) {
                     if (lane == 0) o[0] = eob;
@@ -93,9 +110,9 @@ __global__ void __launch_bounds__(kZrWarps * 32) k_zr_write(const int32_t *__res
                 const unsigned long long S = zr_run_starts(m);
                 const int p0 = __popcll(m & low0) + 2 * __popcll(S & low0);
                 const int p1 = __popcll(m & low1) + 2 * __popcll(S & low1);
-                if (a[j] != 0) o[p0] = a[j];
+                if ((m >> lane) & 1ull) o[p0] = a[j];
                 else if ((S >> lane) & 1ull) { o[p0] = 0; o[p0 + 1] = __ffsll((long long)(m >> lane)) - 1; }
-                if (b[j] != 0) o[p1] = b[j];
+                if ((m >> (lane + 32)) & 1ull) o[p1] = b[j];
                 else if ((S >> (lane + 32)) & 1ull) { o[p1] = 0; o[p1 + 1] = __ffsll((long long)(m >> (lane + 32))) - 1; }
                 if (lane == 0) o[__popcll(m) + 2 * __popcll(S)] = eob;
             }
@@ -198,16 +215,20 @@ static int zr_grid(int device, int64_t units, int per_cta) {
     return (int)(grid < 1 ? 1 : grid);
 }
 
-cudaError_t launch_zr_count(int device, cudaStream_t st, const int32_t *zz, int64_t nblocks, int32_t *counts) {
+cudaError_t launch_zr_count(int device, cudaStream_t st, const int32_t *zz, int64_t nblocks, int32_t *counts,
+                            uint64_t *masks) {
     if (nblocks == 0) return cudaSuccess;
-    k_zr_count<<<zr_grid(device, nblocks, 32 * kZrWarps), kZrWarps * 32, 0, st>>>(zz, nblocks, counts);
+    k_zr_count<<<zr_grid(device, nblocks, 32 * kZrWarps), kZrWarps * 32, 0, st>>>(zz, nblocks, counts,
+                                                                                  (unsigned long long *)masks);
     return cudaGetLastError();
 }
 
 cudaError_t launch_zr_write(int device, cudaStream_t st, const int32_t *zz, int64_t nblocks, int32_t eob,
-                            const int64_t *offsets, int32_t *out) {
+                            const int64_t *offsets, const uint64_t *masks, int32_t *out) {
     if (nblocks == 0) return cudaSuccess;
-    k_zr_write<<<zr_grid(device, nblocks, 32 * kZrWarps), kZrWarps * 32, 0, st>>>(zz, nblocks, eob, offsets, out);
+    const int grid = zr_grid(device, nblocks, 32 * kZrWarps);
+    if (masks) k_zr_write<true><<<grid, kZrWarps * 32, 0, st>>>(zz, nblocks, eob, offsets, (const unsigned long long *)masks, out);
+    else k_zr_write<false><<<grid, kZrWarps * 32, 0, st>>>(zz, nblocks, eob, offsets, nullptr, out);
     return cudaGetLastError();
 }
 

@@ -15,7 +15,7 @@ __all__ = ["ZeroRunCoder"]
 
 class _PendingEncode:
     """Device-side state of an encode whose stream length is still on its way to the host."""
-    __slots__ = ("blocks", "offsets", "total_host", "event", "nblk", "stream")
+    __slots__ = ("blocks", "offsets", "masks", "total_host", "event", "nblk", "stream")
 
 
 class ZeroRunCoder:
@@ -44,7 +44,9 @@ class ZeroRunCoder:
         p.blocks, p.nblk, p.stream = t, t.numel() // 64, torch.cuda.current_stream(t.device)
         dev, sp = dev_index(t), stream_ptr(t.device)
         counts = torch.empty(p.nblk, dtype=torch.int32, device=t.device)
-        _lib.check(_lib.lib.ivc_zerorun_count(dev, sp, t.data_ptr(), p.nblk, counts.data_ptr()), "ivc_zerorun_count")
+        p.masks = torch.empty(p.nblk, dtype=torch.int64, device=t.device)      # 64-bit non-zero masks, count pass -> write pass
+        _lib.check(_lib.lib.ivc_zerorun_count_masks(dev, sp, t.data_ptr(), p.nblk, counts.data_ptr(), p.masks.data_ptr()),
+                   "ivc_zerorun_count_masks")
         ends = torch.cumsum(counts, 0, dtype=torch.int64)
         p.offsets = (ends - counts).contiguous()
         p.total_host = total_host if total_host is not None else torch.zeros(1, dtype=torch.int64).pin_memory()
@@ -69,8 +71,9 @@ class ZeroRunCoder:
         cur = torch.cuda.current_stream(t.device)
         if cur != p.stream and p.event is not None:
             cur.wait_event(p.event)
-        _lib.check(_lib.lib.ivc_zerorun_write(dev_index(t), stream_ptr(t.device), t.data_ptr(), p.nblk, int(self.EOB),
-                                              p.offsets.data_ptr(), out.data_ptr()), "ivc_zerorun_write")
+        _lib.check(_lib.lib.ivc_zerorun_write_masks(dev_index(t), stream_ptr(t.device), t.data_ptr(), p.nblk, int(self.EOB),
+                                                    p.offsets.data_ptr(), p.masks.data_ptr(), out.data_ptr()),
+                   "ivc_zerorun_write_masks")
         return out
 
     def encode(self, flat_patch_img):

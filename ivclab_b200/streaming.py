@@ -23,8 +23,7 @@ import torch
 from . import _lib  # noqa: F401
 from .codec import IntraBlockCoder, PFrameBlockCoder
 from .entropy import ZeroRunCoder
-from .signal.color import rgb2ycbcr
-from .utils.metrics import frame_sse
+from .utils.metrics import frame_sse, frame_sse_rgb8_vs_ycbcr
 
 __all__ = ["StreamedCoder"]
 
@@ -35,12 +34,14 @@ class _Slot:
 
 
 class StreamedCoder:
-    def __init__(self, quantization_scale=1.0, search_range=4, me_mode="auto", chunk_frames=2, device=None, use_graph=True):
+    def __init__(self, quantization_scale=1.0, search_range=4, me_mode="auto", chunk_frames=2, device=None, use_graph=True,
+                 slots=3):
         self.intra = IntraBlockCoder(quantization_scale)
         self.pframe = PFrameBlockCoder(quantization_scale, search_range, me_mode)
         self.zr = ZeroRunCoder()
         self.chunk = int(chunk_frames)
         self.use_graph = bool(use_graph)
+        self.nslots = max(2, int(slots))          # input buffers in rotation: uploads run ahead of the coder by nslots-1 chunks
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self._s_in, self._s_cmp, self._s_out = (torch.cuda.Stream(self.device) for _ in range(3))
         self._host = None
@@ -63,7 +64,7 @@ class StreamedCoder:
         key = (C, H, W)
         if self._slots is None or self._slots[0] != key:
             slots = []
-            for _ in range(2):
+            for _ in range(self.nslots):
                 s = _Slot()
                 s.rgb = torch.empty((C, H, W, 3), dtype=torch.uint8, device=self.device)
                 s.cur = torch.empty((C, H, W), dtype=torch.uint8, device=self.device)
@@ -94,7 +95,7 @@ class StreamedCoder:
         zz = self.intra.forward_rgb(d_rgb)
         pend_i = self.zr.encode_begin(zz, total_host=s.totals[0:1], record=False)
         rec = self.intra.inverse(zz)
-        sse_i = frame_sse(rgb2ycbcr(d_rgb), rec)
+        sse_i = frame_sse_rgb8_vs_ycbcr(d_rgb, rec)             # == frame_sse(rgb2ycbcr(d_rgb), rec), same bits
         mv = self.pframe.estimate(d_ref, d_cur)
         zzp = self.pframe.forward(d_cur, d_ref, mv)
         pend_p = self.zr.encode_begin(zzp, total_host=s.totals[1:2], record=False)
@@ -127,6 +128,7 @@ class StreamedCoder:
         C = self.chunk
         nchunks = (F + C - 1) // C
         slots = self._device_slots(C, H, W)
+        S = self.nslots
         ev_in = [torch.cuda.Event() for _ in range(nchunks)]
         ev_cmp = [torch.cuda.Event() for _ in range(nchunks)]
         ev_fin = [torch.cuda.Event() for _ in range(nchunks)]
@@ -138,9 +140,9 @@ class StreamedCoder:
         def upload(k):
             lo, hi = k * C, min(F, (k + 1) * C)
             with torch.cuda.stream(self._s_in):
-                if k >= 2:
-                    self._s_in.wait_event(ev_cmp[k - 2])          # the slot's previous chunk has been consumed
-                s = slots[k & 1]
+                if k >= S:
+                    self._s_in.wait_event(ev_cmp[k - S])          # the slot's previous chunk has been consumed
+                s = slots[k % S]
                 done = self._mark("h2d", k, self._s_in)
                 for dst, src in ((s.rgb, rgb), (s.cur, cur), (s.ref, ref)):
                     dst[:hi - lo].copy_(src[lo:hi], non_blocking=True)
@@ -151,10 +153,8 @@ class StreamedCoder:
             n = min(F, (k + 1) * C) - k * C
             with torch.cuda.stream(self._s_cmp):
                 self._s_cmp.wait_event(ev_in[k])
-                if k >= 2:
-                    self._s_cmp.wait_event(ev_fin[k - 2])          # the slot's previous results have been picked up
-                done = self._mark("code", k, self._s_cmp)
-                pending[k] = self._launch(slots[k & 1], n, C)
+                done = self._mark("code", k, self._s_cmp)      # (the slot's previous results were picked up by finish(k-S),
+                pending[k] = self._launch(slots[k % S], n, C)  #  enqueued on this same stream S-1 iterations ago)
                 done()
                 ev_cmp[k].record(self._s_cmp)                      # the input slot may be overwritten from here on
 
@@ -195,10 +195,11 @@ class StreamedCoder:
 
         # software pipeline on the host: chunk k is enqueued BEFORE the host waits for the stream lengths of chunk
         # k-1, so the device always has work queued and the host never waits on fresh work
-        upload(0)
+        for k in range(min(S - 1, nchunks)):
+            upload(k)
         for k in range(nchunks):
-            if k + 1 < nchunks:
-                upload(k + 1)
+            if k + S - 1 < nchunks:
+                upload(k + S - 1)
             compute(k)
             if k >= 1:
                 finish(k - 1)

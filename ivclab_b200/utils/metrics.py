@@ -10,7 +10,7 @@ import torch
 from .. import _lib
 from .._runtime import code, dev_index, stream_ptr, to_device
 
-__all__ = ["calc_mse", "calc_psnr", "frame_sse"]
+__all__ = ["calc_mse", "calc_psnr", "frame_sse", "frame_sse_rgb8_vs_ycbcr"]
 
 
 def frame_sse(orig, rec):
@@ -38,6 +38,25 @@ def frame_sse(orig, rec):
     ws = torch.empty(max(wsb, 8), dtype=torch.uint8, device=b.device)
     st = _lib.lib.ivc_sum_squared_error(dev_index(b), stream_ptr(b.device), a.data_ptr(), code(a.dtype), b.data_ptr(),
                                         code(b.dtype), n, unit, bc, ws.data_ptr(), ws.numel(), out.data_ptr())
+    _lib.check(st, "ivc_sum_squared_error")
+    return out
+
+
+def frame_sse_rgb8_vs_ycbcr(rgb8, rec_ycbcr):
+    """``frame_sse(rgb2ycbcr(rgb8), rec_ycbcr)`` without materialising the float64 YCbCr original: uint8 RGB
+    ``[N,H,W,3]`` against float64 YCbCr of the same shape -> float64 ``[N]``, the same bits as the two-step form."""
+    a, _ = to_device(rgb8)
+    b, _ = to_device(rec_ycbcr, a.device)
+    if a.dtype != torch.uint8 or b.dtype != torch.float64 or tuple(a.shape) != tuple(b.shape) or a.shape[-1] != 3:
+        raise ValueError(f"expected uint8 RGB and float64 YCbCr of one shape [N,...,3], got {a.dtype} {tuple(a.shape)} / {b.dtype} {tuple(b.shape)}")
+    a, b = a.contiguous(), b.contiguous()
+    n = b.shape[0]
+    unit = b.numel() // n if n else 0
+    out = torch.empty(n, dtype=torch.float64, device=b.device)
+    wsb = _lib.lib.ivc_sse_workspace_bytes(n, unit)
+    ws = torch.empty(max(wsb, 8), dtype=torch.uint8, device=b.device)
+    st = _lib.lib.ivc_sum_squared_error(dev_index(b), stream_ptr(b.device), a.data_ptr(), _lib.U8, b.data_ptr(), _lib.F64,
+                                        n, unit, _lib.SSE_RGB8_AS_YCBCR, ws.data_ptr(), ws.numel(), out.data_ptr())
     _lib.check(st, "ivc_sum_squared_error")
     return out
 

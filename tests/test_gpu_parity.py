@@ -434,6 +434,16 @@ def test_symbol_statistics_match_reference(g9):
     assert np.array_equal(ivc.stats_marg(sym, np.arange(*b)), O.stats_marg(s, np.arange(*b)))
 
 
+def test_fused_colour_sse_equals_two_step_form():
+    """frame_sse_rgb8_vs_ycbcr(rgb, rec) == frame_sse(rgb2ycbcr(rgb), rec) bit for bit (same visiting order)."""
+    rng = np.random.default_rng(21)
+    rgb = torch.from_numpy(rng.integers(0, 256, size=(3, 72, 104, 3), dtype=np.uint8)).cuda()
+    rec = ivc.rgb2ycbcr(rgb) + torch.from_numpy(rng.normal(0, 3, size=(3, 72, 104, 3))).cuda()
+    assert torch.equal(ivc.frame_sse_rgb8_vs_ycbcr(rgb, rec), ivc.frame_sse(ivc.rgb2ycbcr(rgb), rec))
+    want = ((O.rgb2ycbcr(rgb.cpu().numpy()) - rec.cpu().numpy()) ** 2).reshape(3, -1).sum(1)
+    assert np.allclose(ivc.frame_sse_rgb8_vs_ycbcr(rgb, rec).cpu().numpy(), want, rtol=1e-12, atol=0)
+
+
 def test_metrics_match_reference(g1, g6):
     """N3: calc_mse / calc_psnr (metrics.py:3-40); reduction order differs from numpy's pairwise mean,
     so the comparison is relative 1e-12 (PSNR: far below the 0.01 dB bar)."""

@@ -31,3 +31,7 @@ print(f"run: {(t1 - t0) * 1e3:.3f} ms host wall")
 for label, k, a, b, h0, h1 in sorted(sc.trace, key=lambda r: origin.elapsed_time(r[2])):
     print(f"{label:8s} chunk {k:2d}  device {origin.elapsed_time(a):7.3f} -> {origin.elapsed_time(b):7.3f} ms"
           f"   host enqueue {(h0 - t0) * 1e3:7.3f} -> {(h1 - t0) * 1e3:7.3f} ms")
+busy = {}
+for label, k, a, b, h0, h1 in sc.trace:
+    busy[label] = busy.get(label, 0.0) + a.elapsed_time(b)
+print("busy ms per stage:", {k: round(v, 3) for k, v in busy.items()})
