@@ -156,7 +156,19 @@ def run_b200(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL prints its version banner on STDOUT when the communicator comes up; stdout carries exactly one JSON
+        # line, so point fd 1 at stderr until the first collective has run
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     import ivclab_b200 as ivc
     from ivclab_b200 import _lib
     from ivclab_b200._runtime import to_device
