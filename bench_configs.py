@@ -123,6 +123,13 @@ def main():
         t = timed(lambda: cl.code_sequence(s5), 3, warm=1)
         res[f"cfg5_1080p_{T5}f_closed_loop_graph={graph}"] = {"ms_per_sequence": t, "us_per_frame": t / T5 * 1e3,
                                                                "fps": T5 / t * 1e3, "mpixel_s": T5 * 1080 * 1920 / t / 1e3}
+    # the same closed loop over 8 independent 1080p sequences in lockstep (sequences / GOPs are the unit of parallelism)
+    S8, T8 = 8, (10 if quick else 30)
+    s8 = torch.stack([luma_seq(T8, 1080, 1920, 5100 + i) for i in range(S8)])
+    cl = ivc.ClosedLoopLumaCoder(1.0, 4, decode="luma", me_mode="exact", use_graph=False)
+    t = timed(lambda: cl.code_sequences(s8), 3, warm=1)
+    res[f"cfg5_lockstep_{S8}x{T8}f_1080p_closed_loop"] = {"ms_per_run": t, "us_per_frame": t / (S8 * T8) * 1e3,
+                                                          "fps": S8 * T8 / t * 1e3, "mpixel_s": S8 * T8 * 1080 * 1920 / t / 1e3}
     print(json.dumps(res, indent=1))
 
 

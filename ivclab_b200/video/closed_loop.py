@@ -34,50 +34,70 @@ class ClosedLoopLumaCoder:
         self.use_graph = use_graph
         self._graphs = {}
 
-    # one sequence = T frames [T,H,W] float64 on the device
+    # S sequences in lockstep, time-major [T,S,H,W] float64 on the device: every launch codes frame t of all S
     def _enqueue(self, frames, zz, mv, recon, ws, dtab, tcode):
         L = _lib.lib
-        T, H, W = frames.shape
+        T, S, H, W = frames.shape
         dev = frames.device.index
         sp = torch.cuda.current_stream(frames.device).cuda_stream
         czz = 1 if self.decode == "faithful" else 3
-        fsz, zsz, msz = H * W * 8, (H // 8) * (W // 8) * 192 * 4, (H // 8) * (W // 8) * 8
+        fsz, zsz, msz = S * H * W * 8, S * (H // 8) * (W // 8) * 192 * 4, S * (H // 8) * (W // 8) * 8
         fp, zp, mp, rp = frames.data_ptr(), zz.data_ptr(), mv.data_ptr(), recon.data_ptr()
         chk = _lib.check
-        # I-frame: intra forward with the 3-table broadcast, decode against a zero prediction
-        chk(L.ivc_intra_forward(dev, sp, fp, _lib.F64, 1, H, W, 1, H * W, dtab, tcode, zp), "ivc_intra_forward")
-        chk(L.ivc_pframe_inverse(dev, sp, zp, czz, self._zero.data_ptr(), None, None, _lib.F64, 1, H, W,
-                                 self.search_range, dtab, tcode, rp), "ivc_pframe_inverse")
+        # I-frames: intra forward with the 3-table broadcast, decode against a zero prediction
+        def inverse(z, pred, ref, m, out):
+            # 'faithful' reads each frame's first Hp*Wp scan blocks as [Hp,Wp,1,64]: that view is contiguous per
+            # frame only, so lockstep batches decode frame by frame; 'luma' decodes the whole batch at once
+            groups = [(0, S)] if (czz == 3 or S == 1) else [(i, 1) for i in range(S)]
+            for i, n in groups:
+                chk(L.ivc_pframe_inverse(dev, sp, z + i * (zsz // S), czz, pred + i * (fsz // S) if pred else None,
+                                         ref + i * (fsz // S) if ref else None, m + i * (msz // S) if m else None,
+                                         _lib.F64, n, H, W, self.search_range, dtab, tcode, out + i * (fsz // S)),
+                    "ivc_pframe_inverse")
+
+        chk(L.ivc_intra_forward(dev, sp, fp, _lib.F64, S, H, W, 1, H * W, dtab, tcode, zp), "ivc_intra_forward")
+        inverse(zp, self._zero.data_ptr(), None, None, rp)
         for t in range(1, T):
             cur, ref, out = fp + t * fsz, rp + (t - 1) * fsz, rp + t * fsz
             z, m = zp + t * zsz, mp + (t - 1) * msz
-            chk(L.ivc_me_full_search(dev, sp, ref, cur, _lib.F64, 1, H, W, H * W, H * W, self.search_range,
+            chk(L.ivc_me_full_search(dev, sp, ref, cur, _lib.F64, S, H, W, H * W, H * W, self.search_range,
                                      self.me_mode, m, ws.data_ptr(), ws.numel()), "ivc_me_full_search")
-            chk(L.ivc_pframe_forward(dev, sp, cur, ref, m, _lib.F64, 1, H, W, self.search_range, dtab, tcode, None, z),
+            chk(L.ivc_pframe_forward(dev, sp, cur, ref, m, _lib.F64, S, H, W, self.search_range, dtab, tcode, None, z),
                 "ivc_pframe_forward")
-            chk(L.ivc_pframe_inverse(dev, sp, z, czz, None, ref, m, _lib.F64, 1, H, W, self.search_range, dtab, tcode, out),
-                "ivc_pframe_inverse")
+            inverse(z, None, ref, m, out)
 
     def code_sequence(self, frames):
         """frames [T,H,W] (numpy or CUDA tensor, float64) -> dict(zz [T,Hp,Wp,3,64] int32,
         mv [T-1,Hp,Wp,1] int64, recon [T,H,W] float64 = the decoder's reconstructions)."""
+        shape = tuple(frames.shape)
+        if len(shape) != 3:
+            raise ValueError(f"expected [T,H,W] with H,W multiples of 8, got {shape}")
+        out = self.code_sequences(frames[None])
+        return {k: v[0] for k, v in out.items()}
+
+    def code_sequences(self, frames):
+        """S independent sequences coded in LOCKSTEP: frames [S,T,H,W] -> dict(zz [S,T,Hp,Wp,3,64], mv
+        [S,T-1,Hp,Wp,1], recon [S,T,H,W]).  Each sequence is its own closed loop (frame t needs its own
+        reconstruction t-1), but frame t of all S sequences goes through one launch per kernel, which is what
+        fills the GPU when a single frame does not (sequences / GOPs are the unit of parallelism: SURVEY 8e)."""
         f, was_np = to_device(frames)
-        f = f.to(torch.float64).contiguous()
-        if f.ndim != 3 or f.shape[1] % 8 or f.shape[2] % 8:
-            raise ValueError(f"expected [T,H,W] with H,W multiples of 8, got {tuple(f.shape)}")
-        T, H, W = f.shape
+        f = f.to(torch.float64)
+        if f.ndim != 4 or f.shape[2] % 8 or f.shape[3] % 8:
+            raise ValueError(f"expected [S,T,H,W] with H,W multiples of 8, got {tuple(f.shape)}")
+        f = f.permute(1, 0, 2, 3).contiguous()                                  # time-major
+        T, S, H, W = f.shape
         dev = f.device
         _, dtab_t = self.quant._table_on(dev)
         dtab, tcode = dtab_t.data_ptr(), code(dtab_t.dtype)
-        key = (T, H, W, str(dev), self.decode, self.me_mode, dtab)
+        key = (T, S, H, W, str(dev), self.decode, self.me_mode, dtab)
         st = self._graphs.get(key) if self.use_graph else None
         if st is None:
             st = {"frames": torch.empty_like(f) if self.use_graph else f,
-                  "zz": torch.empty((T, H // 8, W // 8, 3, 64), dtype=torch.int32, device=dev),
-                  "mv": torch.empty((max(T - 1, 0), H // 8, W // 8, 1), dtype=torch.int64, device=dev),
-                  "recon": torch.empty((T, H, W), dtype=torch.float64, device=dev),
+                  "zz": torch.empty((T, S, H // 8, W // 8, 3, 64), dtype=torch.int32, device=dev),
+                  "mv": torch.empty((max(T - 1, 0), S, H // 8, W // 8, 1), dtype=torch.int64, device=dev),
+                  "recon": torch.empty((T, S, H, W), dtype=torch.float64, device=dev),
                   "ws": torch.empty(256, dtype=torch.uint8, device=dev)}
-            self._zero = torch.zeros((H, W), dtype=torch.float64, device=dev)
+            self._zero = torch.zeros((S, H, W), dtype=torch.float64, device=dev)
             if self.use_graph:
                 st["frames"].copy_(f)
                 # warm up once outside capture (sets kernel attributes), then capture the whole sequence
@@ -92,8 +112,9 @@ class ClosedLoopLumaCoder:
             st["frames"].copy_(f)
             st["graph"].replay()
         else:
+            if self._zero.shape != (S, H, W) or self._zero.device != dev:
+                self._zero = torch.zeros((S, H, W), dtype=torch.float64, device=dev)
             self._enqueue(st["frames"], st["zz"], st["mv"], st["recon"], st["ws"], dtab, tcode)
-        out = {"zz": st["zz"], "mv": st["mv"], "recon": st["recon"]}
-        if self.use_graph:                                  # hand out copies: the graph owns its buffers
-            out = {k: v.clone() for k, v in out.items()}
+        # back to sequence-major (a copy, so a graph's static buffers are never handed out)
+        out = {k: st[k].transpose(0, 1).contiguous() for k in ("zz", "mv", "recon")}
         return {k: to_host(v, was_np) for k, v in out.items()}

@@ -357,6 +357,25 @@ def test_closed_loop_qcif_21_frames_vs_oracle():
     assert psnr > 20.0
 
 
+@pytest.mark.parametrize("decode", ["faithful", "luma"])
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_closed_loop_lockstep_sequences(decode, use_graph):
+    """Several independent sequences coded in lockstep (one launch per kernel and time step) give exactly what
+    coding them one after the other gives -- which is what the oracle's loop gives."""
+    from oracle import closed_loop as CL
+    seqs = np.stack([O.moving_sequence(31 + s, 4, 40, 72) for s in range(3)])
+    coder = ivc.ClosedLoopLumaCoder(0.4, 3, decode=decode, me_mode="auto", use_graph=use_graph)
+    got = coder.code_sequences(seqs)
+    assert got["zz"].shape == (3, 4, 5, 9, 3, 64) and got["mv"].shape == (3, 3, 5, 9, 1) and got["recon"].shape == seqs.shape
+    for s in range(3):
+        want = CL.code_sequence(seqs[s], 0.4, 3, decode)
+        for k in ("zz", "mv", "recon"):
+            assert np.array_equal(got[k][s], want[k]), (s, k)
+        one = coder.code_sequence(seqs[s])
+        for k in ("zz", "mv", "recon"):
+            assert np.array_equal(one[k], want[k]), (s, k)
+
+
 # ---------------------------------------------------------------- "next" rows N2 / N3
 def test_zerorun_encode_matches_reference_stream(g1, g6):
     """N2: the GPU zero-run encoder reproduces the reference's symbol list (zerorun.py:10-43)."""
