@@ -30,6 +30,8 @@ namespace ivc {
 constexpr int kMeWarps = 8;
 constexpr int kMeThreads = kMeWarps * 32;
 constexpr int kMeG = 3;            // candidates per task (vertically adjacent)
+constexpr int kExactCurPitch = 66; // elements per current block in the exact kernel's shared memory (64 + 2: a warp
+                                   // that straddles two blocks reads them from different banks)
 
 struct MeArgs {
     const void *ref, *cur;
@@ -39,6 +41,7 @@ struct MeArgs {
     int tiles_y, tiles_x;
     int R, P, Wc;                          // window rows / pitch / used columns (elements or bytes)
     int cur_off;                           // byte offset of the current-blocks area in dynamic smem
+    int part_off, npieces;                 // exact kernel: partial (ssd, index) results per block and lane
     int pw, hs_off, b_off;                 // integer kernel: words per packed row, offsets of HS and B
     int pwl, nseg;                         // ... words per row actually staged, 8-row segments of S
     int vec;                               // ... 16-byte staging loads are legal (alignment of base, strides, sr)
@@ -60,6 +63,14 @@ __device__ __forceinline__ void cp_async_zfill(uint32_t dst, const void *src, bo
     if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
     else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
 }
+
+// floor(x / d) for the small operands of the index decompositions: one multiply-high (x*d < 2^32)
+struct FastDiv {
+    unsigned magic;                                                           // 0 = divide by one
+    __device__ __forceinline__ explicit FastDiv(unsigned m) : magic(m) {}
+    __device__ __forceinline__ int div(int x) const { return magic ? (int)__umulhi((unsigned)x, magic) : x; }
+};
+static unsigned fastdiv_magic(unsigned d) { return d > 1 ? 0xFFFFFFFFu / d + 1u : 0u; }
 
 struct MeTile {
     int64_t frame;
@@ -85,7 +96,7 @@ __global__ void __launch_bounds__(kMeThreads, 2) k_me_exact(const MeArgs a) {
     if (a.flag && *a.flag != a.run_if) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *s_win = reinterpret_cast<T *>(smem_raw);                         // [R][P]
-    T *s_cur = reinterpret_cast<T *>(smem_raw + a.cur_off);             // [tby*tbx][64]
+    T *s_cur = reinterpret_cast<T *>(smem_raw + a.cur_off);             // [tby*tbx][kExactCurPitch]
     using R_ = Rn<T>;
     const MeTile tl = me_tile(a);
     const T *ref = (const T *)a.ref + tl.frame * a.ref_fs;
@@ -111,26 +122,44 @@ __global__ void __launch_bounds__(kMeThreads, 2) k_me_exact(const MeArgs a) {
     for (int row = warp; row < 8 * tl.nby; row += kMeWarps) {
         const T *cp = cur + ((int64_t)8 * tl.by0 + row) * a.W + 8 * tl.bx0;
         for (int col = lane; col < cw; col += 32)
-            cp_async_zfill<sizeof(T)>(cur_s + (uint32_t)(((row >> 3) * a.tbx + (col >> 3)) * 64 + (row & 7) * 8 + (col & 7)) *
+            cp_async_zfill<sizeof(T)>(cur_s + (uint32_t)(((row >> 3) * a.tbx + (col >> 3)) * kExactCurPitch + (row & 7) * 8 + (col & 7)) *
                                                   (uint32_t)sizeof(T), cp + col, true);
     }
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
+    // A warp owns a contiguous range of the tile's blocks and walks the tasks of ALL its blocks as one list, 32
+    // at a time (a block has ntpb tasks, rarely a multiple of 32: one block per round would idle 5 of 32 lanes
+    // at +-4).  Every lane folds its result into a private shared-memory slot (block, lane); one butterfly per
+    // block at the end turns the 32 slots into the block's vector.  No warp ever waits on another warp.
     const int center = sr * span + sr;
     const int nblk = tl.nby * tl.nbx;
-    for (int blk = warp; blk < nblk; blk += kMeWarps) {
-        const int brow = blk / tl.nbx, b = blk - brow * tl.nbx;
-        const T *cb = s_cur + (brow * a.tbx + b) * 64;
+    const int per_w = (nblk + kMeWarps - 1) / kMeWarps, blk0 = warp * per_w;        // blocks blk0 .. blk0+nb_w-1
+    const int nb_w = max(0, min(per_w, nblk - blk0));
+    const int total = nb_w * a.ntpb;
+    T *s_pssd = reinterpret_cast<T *>(smem_raw + a.part_off);                // [64][32]
+    int *s_pidx = reinterpret_cast<int *>(s_pssd + 64 * 32);                  // [64][32]
+    for (int k = 0; k < nb_w; ++k) {
+        s_pssd[(blk0 + k) * 32 + lane] = Inf<T>::v();
+        s_pidx[(blk0 + k) * 32 + lane] = center;
+    }
+    __syncwarp();
+    const FastDiv d_ntpb(a.m_ntpb), d_span(a.m_span), d_nbx(a.m_nbx[tl.nbx != a.tbx]);
+    for (int tbase = 0; tbase < total; tbase += 32) {
+        const int task = tbase + lane;
+        const bool have = task < total;
+        const int tk = have ? task : total - 1;
+        const int kb = d_ntpb.div(tk), tt = tk - kb * a.ntpb;
+        const int blk = blk0 + kb;
+        const int brow = d_nbx.div(blk), b = blk - brow * tl.nbx;
+        const int g = d_span.div(tt), dxi = tt - g * span;
+        const T *cb = s_cur + (brow * a.tbx + b) * kExactCurPitch;
         T best = Inf<T>::v();
         int bidx = center;
-        const int gx0 = 8 * (tl.bx0 + b);
+        const int gx = 8 * (tl.bx0 + b) + dxi - sr;
         const int64_t gy0 = (int64_t)8 * (tl.by0 + brow);
-        for (int task = lane; task < a.ntpb; task += 32) {
-            const int g = task / span, dxi = task - g * span;
-            const int dy0 = g * kMeG - sr;
-            const int gx = gx0 + dxi - sr;
-            if (gx < 0 || gx + 8 > a.W) continue;                            // motion.py:41-43 (x bound)
+        const int dy0 = g * kMeG - sr;
+        if (have && gx >= 0 && gx + 8 <= a.W) {                                  // motion.py:41-43 (x bound)
             T acc[kMeG][8];
 #pragma unroll
             for (int gg = 0; gg < kMeG; ++gg)
@@ -166,6 +195,20 @@ __global__ void __launch_bounds__(kMeThreads, 2) k_me_exact(const MeArgs a) {
                 }
             }
         }
+        if (have) {                                                          // fold into this lane's slot of the block
+            const T ps = s_pssd[blk * 32 + lane];
+            const int pi = s_pidx[blk * 32 + lane];
+            if (best < ps || (best == ps && bidx < pi && best != Inf<T>::v())) {
+                s_pssd[blk * 32 + lane] = best;
+                s_pidx[blk * 32 + lane] = bidx;
+            }
+        }
+    }
+    __syncwarp();
+    for (int k = 0; k < nb_w; ++k) {
+        const int blk = blk0 + k, brow = d_nbx.div(blk), b = blk - brow * tl.nbx;
+        T best = s_pssd[blk * 32 + lane];
+        int bidx = s_pidx[blk * 32 + lane];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             const T os = __shfl_xor_sync(0xffffffffu, best, off);
@@ -219,14 +262,6 @@ __device__ __forceinline__ unsigned to_u8(float v, U8Check &c) {
 __device__ __forceinline__ unsigned pack_bytes(unsigned b0, unsigned b1, unsigned b2, unsigned b3) {
     return __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
 }
-
-// floor(x / d) for the small operands of the index decompositions: one multiply-high (x*d < 2^32)
-struct FastDiv {
-    unsigned magic;                                                           // 0 = divide by one
-    __device__ __forceinline__ explicit FastDiv(unsigned m) : magic(m) {}
-    __device__ __forceinline__ int div(int x) const { return magic ? (int)__umulhi((unsigned)x, magic) : x; }
-};
-static unsigned fastdiv_magic(unsigned d) { return d > 1 ? 0xFFFFFFFFu / d + 1u : 0u; }
 
 constexpr int kMeIntMaxThreads = 512;   // integer kernel, constant-pitch variants: 256..512 threads per CTA (chosen by the launcher), <= 64 registers
 constexpr int kCurPitch = 18;      // words per current block in shared memory (16 + 2: blocks on distinct banks)
@@ -536,11 +571,15 @@ static size_t me_geometry(MeArgs &a, int64_t n_frames, int64_t H, int64_t W, int
         a.Wc = 8 * a.tbx + 2 * sr;
         a.P = ((a.Wc + pitch_quantum - 1) / pitch_quantum) * pitch_quantum + pitch_skew;
         a.cur_off = (int)((((size_t)a.R * a.P * elem) + 15) & ~(size_t)15);
-        smem = (size_t)a.cur_off + (size_t)a.tby * a.tbx * 64 * elem;
+        a.npieces = 32;                                            // one (ssd, index) slot per block and lane
+        a.part_off = (int)(((size_t)a.cur_off + (size_t)a.tby * a.tbx * kExactCurPitch * elem + 15) & ~(size_t)15);
+        smem = (size_t)a.part_off + (size_t)64 * 32 * (elem + 4);
         if (smem <= budget) break;
     }
     a.tiles_y = (a.Hp + a.tby - 1) / a.tby;
     a.tiles_x = (a.Wp + a.tbx - 1) / a.tbx;
+    a.m_ntpb = fastdiv_magic(a.ntpb); a.m_span = fastdiv_magic(a.span);
+    a.m_nbx[0] = fastdiv_magic(a.tbx); a.m_nbx[1] = fastdiv_magic(a.Wp - (a.tiles_x - 1) * a.tbx);
     return smem;
 }
 
@@ -569,7 +608,7 @@ cudaError_t launch_me_exact(int device, cudaStream_t st, const void *ref, const 
     MeArgs a;
     a.ref = ref; a.cur = cur; a.n = n; a.H = H; a.W = W; a.ref_fs = ref_fs; a.cur_fs = cur_fs; a.mv = mv;
     a.flag = flag; a.run_if = run_if; a.check = 0;
-    const size_t smem = me_geometry(a, n, H, W, sr, f32 ? 4 : 8, 32, 3, 100 * 1024, 4 * 2 * (int64_t)sm_count(device));
+    const size_t smem = me_geometry(a, n, H, W, sr, f32 ? 4 : 8, 32, 3, 113 * 1024, 4 * 2 * (int64_t)sm_count(device));
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     (void)device;
     if (f32) return me_launch_chunks(k_me_exact<float>, a, 4, smem, st);
