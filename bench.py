@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the host-fed legs (e2e keys become null)")
     ap.add_argument("--me-mode", default="auto", choices=["auto", "exact", "int"])
+    ap.add_argument("--cpu-configs", action="store_true",
+                    help="with --impl reference: also time the reference-call port on bounded samples of the five "
+                         "configurations BASELINE.json names (adds the key cpu_configs; about a minute of CPU time)")
     return ap.parse_args()
 
 
@@ -447,6 +450,60 @@ def cpu_baseline(np, ivc, cores=1):
     return res
 
 
+def _best_of(fn, n=3):
+    best = 1e30
+    for _ in range(n):
+        t0 = time.perf_counter()
+        fn()
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def cpu_configs():
+    """SURVEY.md section 8d, 'Timing (CPU reference, same run)': the reference-call port on ONE core on a bounded
+    sample of each configuration; measured and extrapolated figures are kept apart.  Candidate counts follow
+    section 8's formula (in-bounds (dy, dx) pairs summed over the blocks of a frame)."""
+    import contextlib
+    import io
+    from oracle import ivc_oracle as O, ref_port as R
+
+    def cands(H, W, sr):
+        hp, wp = H // 8, W // 8
+        rows = sum(min(sr, (hp - 1 - i) * 8) + min(sr, i * 8) + 1 for i in range(hp))
+        cols = sum(min(sr, (wp - 1 - i) * 8) + min(sr, i * 8) + 1 for i in range(wp))
+        return rows * cols
+
+    res = {}
+    with contextlib.redirect_stdout(io.StringIO()):
+        tab = O.quant_table(1.0)
+        img = O.rgb2ycbcr(O.smooth_noise_rgb(0, 512, 768))
+        t = _best_of(lambda: R.intra_loop(img, tab))
+        res["cfg1_512x768_rgb_intra_loop"] = {"measured_s": round(t, 4), "sample": "the full configuration", "mpixel_s": round(512 * 768 / t / 1e6, 3)}
+        seq = O.moving_sequence(2, 2, 144, 176)
+        t = _best_of(lambda: R.pframe_loop(seq[1], seq[0], 4, tab), 2)
+        res["cfg2_qcif_21f"] = {"measured_s": round(t, 3), "sample": "one QCIF P-frame (ME +-4, MC, residual transform, reconstruction)",
+                                "extrapolated_full_config_s": round(20 * t, 1), "mpixel_s": round(144 * 176 / t / 1e6, 4)}
+        img3 = O.rgb2ycbcr(O.smooth_noise_rgb(3000, 1080, 1920))
+        t = _best_of(lambda: [R.intra_loop(img3, O.quant_table(q)) for q in (0.07, 1.0)], 1)
+        res["cfg3_rd_sweep_1024x1080p_x10"] = {"measured_s": round(t, 3), "sample": "one 1080p frame x 2 qScales (forward + inverse)",
+                                               "extrapolated_full_config_s": round(t / 2 * 10 * 1024, 0),
+                                               "mpixel_s": round(2 * 1080 * 1920 / t / 1e6, 3)}
+        s4 = O.moving_sequence(4000, 2, 64, 64)
+        t = _best_of(lambda: R.compute_motion_vector(s4[0], s4[1], 16), 1)
+        full = cands(2160, 3840, 16)
+        res["cfg4_8x120x4k_sr16_me"] = {"measured_s": round(t, 3), "sample": "ME on one 64x64 crop pair at +-16",
+                                        "candidates_sample": cands(64, 64, 16), "candidates_per_4k_frame": full,
+                                        "extrapolated_s_per_4k_frame": round(t * full / cands(64, 64, 16), 0),
+                                        "extrapolated_full_config_core_days": round(t * full / cands(64, 64, 16) * 8 * 119 / 86400, 1)}
+        s5 = O.moving_sequence(5000, 2, 136, 240)
+        t = _best_of(lambda: R.pframe_loop(s5[1], s5[0], 4, tab), 1)
+        ratio = cands(1080, 1920, 4) / cands(136, 240, 4)
+        res["cfg5_300f_1080p_closed_loop"] = {"measured_s": round(t, 3), "sample": "one 136x240 P-frame (ME +-4 dominates)",
+                                              "extrapolated_s_per_1080p_frame": round(t * ratio, 1),
+                                              "extrapolated_full_config_s": round(t * ratio * 299, 0)}
+    return res
+
+
 def _ref_worker(seed):
     s = _cpu_sample(seed)
     return s["s_per_px"]
@@ -486,6 +543,8 @@ def run_reference(args):
         "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "steps capped at 12 and warmup at 2 so that the CPU run stays within a few minutes",
     }
+    if args.cpu_configs:
+        line["cpu_configs"] = cpu_configs()
     print(json.dumps(line))
 
 
