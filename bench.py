@@ -344,7 +344,7 @@ def run_b200(args):
             return ms
 
         serial_ms = time_e2e(e2e_step)                         # one stream, copies and kernels back to back
-        streamed = ivc.StreamedCoder(QSCALE, SR, me_mode=args.me_mode, chunk_frames=2, device=device)
+        streamed = ivc.StreamedCoder(QSCALE, SR, me_mode=args.me_mode, chunk_frames=4, device=device)
         last = [None]
 
         def e2e_streamed_step():                               # the same work, uploads/downloads overlapped with the kernels
@@ -386,7 +386,7 @@ def run_b200(args):
                     "frames_per_step": Fe, "ms_per_step": round(e2e_ms, 3),
                     "single_stream": {"frames_per_step": Fa, "ms_per_step": round(serial_ms, 3),
                                       "value": round(world * Fa * H * W / (serial_ms * 1e-3) / 1e6, 1)},
-                    "api": "StreamedCoder.run (3 streams, 2-frame chunks, one CUDA graph per slot): pinned host uint8 RGB + uint8 luma in; "
+                    "api": "StreamedCoder.run (upload / 2 compute / download streams, 4-frame chunks, one CUDA graph per slot): pinned host uint8 RGB + uint8 luma in; "
                            "IntraBlockCoder.forward_rgb/inverse, PFrameBlockCoder.estimate/forward/inverse, ZeroRunCoder.encode, "
                            "frame_sse; zero-run symbols + MVs + SSE back to host"},
             "e2e_raw": None if args.no_e2e else {"value": round(raw_val, 1), "unit": UNIT, "h2d_bytes_per_step": raw_h2d, "d2h_bytes_per_step": raw_d2h,

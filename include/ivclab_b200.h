@@ -181,6 +181,15 @@ int ivc_zerorun_count_masks(int device, void *stream, const int32_t *zz, int64_t
 int ivc_zerorun_write_masks(int device, void *stream, const int32_t *zz, int64_t nblocks, int32_t end_of_block,
                             const int64_t *offsets, const uint64_t *masks, int32_t *symbols_out);
 
+/* The scan between the two passes, for callers that do not want to bring their own: offsets_out[b] = sum of
+ * counts[0..b) (int64), in one kernel (decoupled look-back over 4096-count tiles).  The grand total is written
+ * to total_dev_out (device int64, may be NULL) and, by the kernel itself, to total_mapped_out (MAPPED pinned host
+ * memory, may be NULL) -- a pipeline learns the stream length without a copy-engine operation.
+ * workspace: ivc_zerorun_offsets_workspace_bytes(nblocks) bytes of device memory. */
+int64_t ivc_zerorun_offsets_workspace_bytes(int64_t nblocks);
+int ivc_zerorun_offsets(int device, void *stream, const int32_t *counts, int64_t nblocks, int64_t *offsets_out,
+                        void *workspace, int64_t workspace_bytes, int64_t *total_mapped_out, int64_t *total_dev_out);
+
 /* Post n (<= 32) int64 words from device memory to MAPPED pinned host memory with a kernel (no copy engine):
  * how a pipeline learns a symbol-stream length (the last element of the caller's prefix sum) without the
  * small copy queueing behind bulk transfers.  dst_mapped: a cudaHostAlloc'd / pinned pointer valid on the device. */

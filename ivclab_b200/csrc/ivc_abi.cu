@@ -296,6 +296,24 @@ int ivc_zerorun_write(int device, void *stream, const int32_t *zz, int64_t nbloc
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
 
+int64_t ivc_zerorun_offsets_workspace_bytes(int64_t nblocks) {
+    if (nblocks < 0) return -1;
+    return ivc::zr_offsets_workspace_bytes(nblocks);
+}
+
+int ivc_zerorun_offsets(int device, void *stream, const int32_t *counts, int64_t nblocks, int64_t *offsets_out,
+                        void *workspace, int64_t workspace_bytes, int64_t *total_mapped_out, int64_t *total_dev_out) {
+    if (nblocks < 0) return IVC_ERR_ARG;
+    if (nblocks == 0) return IVC_OK;
+    if (!counts || !offsets_out || !aligned16(counts)) return IVC_ERR_ARG;
+    if (!workspace || workspace_bytes < ivc::zr_offsets_workspace_bytes(nblocks)) return IVC_ERR_WORKSPACE;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_zr_offsets((cudaStream_t)stream, counts, nblocks, offsets_out, workspace, total_mapped_out,
+                                           total_dev_out);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
 int ivc_post_words_to_host(int device, void *stream, const int64_t *src, int64_t *dst_mapped, int n) {
     if (n < 0 || n > 32) return IVC_ERR_ARG;
     if (n == 0) return IVC_OK;

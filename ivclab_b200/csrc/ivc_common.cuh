@@ -47,6 +47,9 @@ cudaError_t launch_zrd_ends(int device, cudaStream_t st, const int32_t *is_eob, 
 cudaError_t launch_zrd_write(int device, cudaStream_t st, const int32_t *sym, const int64_t *ends, int64_t nblocks,
                              int32_t *out, int *err);
 
+int64_t zr_offsets_workspace_bytes(int64_t n);
+cudaError_t launch_zr_offsets(cudaStream_t st, const int32_t *counts, int64_t n, int64_t *offsets, void *workspace,
+                              int64_t *total_mapped, int64_t *total_dev);
 cudaError_t launch_post_words(cudaStream_t st, const int64_t *src, int64_t *dst_mapped, int n);
 
 // symbol statistics (ivc_metrics.cu)

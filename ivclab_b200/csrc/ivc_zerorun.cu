@@ -207,6 +207,97 @@ cudaError_t launch_post_words(cudaStream_t st, const int64_t *src, int64_t *dst_
     return cudaGetLastError();
 }
 
+// Exclusive prefix sum of the per-block symbol counts (int32 -> int64 offsets) in ONE kernel: tiles of 4096
+// counts, decoupled look-back between tiles (state word = flag << 62 | value; 1 = tile aggregate, 2 = inclusive
+// prefix), and the grand total posted to mapped pinned host memory by the last tile.  Replaces a library scan,
+// a subtraction, a copy and a separate post kernel on the compute chain of the host-fed pipeline.
+constexpr int kScanThreads = 1024, kScanTile = 4 * kScanThreads;
+
+__global__ void __launch_bounds__(kScanThreads) k_zr_offsets(const int32_t *__restrict__ counts, int64_t n,
+                                                             int64_t *__restrict__ offsets, unsigned long long *state,
+                                                             volatile int64_t *total_mapped, int64_t *total_dev) {
+    __shared__ long long s_warp[32];
+    __shared__ long long s_prefix;
+    const int tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t base = (int64_t)tile * kScanTile + 4 * threadIdx.x;
+    int c[4] = {0, 0, 0, 0};
+    if (base + 3 < n) {
+        const int4 v = *reinterpret_cast<const int4 *>(counts + base);
+        c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (base + k < n) c[k] = counts[base + k];
+    }
+    const long long mine = (long long)c[0] + c[1] + c[2] + c[3];
+    long long incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        long long w = s_warp[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += t;
+        }
+        s_warp[lane] = w;                                                     // inclusive over warps
+    }
+    __syncthreads();
+    const long long tile_sum = s_warp[31];
+    if (warp == 0) {                                                          // warp 0 looks back 32 tiles at a time
+        long long prefix = 0;
+        if (tile > 0) {
+            if (lane == 0) atomicExch(&state[tile], (1ull << 62) | (unsigned long long)tile_sum);
+            for (int p0 = tile - 1; p0 >= 0; p0 -= 32) {
+                const int p = p0 - lane;
+                unsigned long long st = 2ull << 62;                           // lanes before tile 0: "inclusive, value 0"
+                if (p >= 0)
+                    do { st = *reinterpret_cast<volatile unsigned long long *>(&state[p]); } while ((st >> 62) == 0);
+                const unsigned incl_mask = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+                const int first = incl_mask ? __ffs(incl_mask) - 1 : 32;      // nearest predecessor with an inclusive prefix
+                long long v = lane <= first ? (long long)(st & ((1ull << 62) - 1)) : 0;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                prefix += v;
+                if (incl_mask) break;
+            }
+        }
+        if (lane == 0) {
+            atomicExch(&state[tile], (2ull << 62) | (unsigned long long)(prefix + tile_sum));
+            s_prefix = prefix;
+            if (tile == (int)gridDim.x - 1) {
+                if (total_dev) *total_dev = prefix + tile_sum;
+                if (total_mapped) { *total_mapped = prefix + tile_sum; __threadfence_system(); }
+            }
+        }
+    }
+    __syncthreads();
+    long long off = s_prefix + (warp ? s_warp[warp - 1] : 0) + (incl - mine);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (base + k < n) offsets[base + k] = off;
+        off += c[k];
+    }
+}
+
+int64_t zr_offsets_workspace_bytes(int64_t n) { return ((n + kScanTile - 1) / kScanTile + 1) * (int64_t)sizeof(unsigned long long); }
+
+cudaError_t launch_zr_offsets(cudaStream_t st, const int32_t *counts, int64_t n, int64_t *offsets, void *workspace,
+                              int64_t *total_mapped, int64_t *total_dev) {
+    if (n == 0) return cudaSuccess;
+    const int64_t tiles = (n + kScanTile - 1) / kScanTile;
+    if (tiles > 2147483647LL) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)tiles * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    k_zr_offsets<<<(unsigned)tiles, kScanThreads, 0, st>>>(counts, n, offsets, (unsigned long long *)workspace, total_mapped, total_dev);
+    return cudaGetLastError();
+}
+
 static int zr_grid(int device, int64_t units, int per_cta) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);

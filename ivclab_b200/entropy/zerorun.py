@@ -47,12 +47,13 @@ class ZeroRunCoder:
         p.masks = torch.empty(p.nblk, dtype=torch.int64, device=t.device)      # 64-bit non-zero masks, count pass -> write pass
         _lib.check(_lib.lib.ivc_zerorun_count_masks(dev, sp, t.data_ptr(), p.nblk, counts.data_ptr(), p.masks.data_ptr()),
                    "ivc_zerorun_count_masks")
-        ends = torch.cumsum(counts, 0, dtype=torch.int64)
-        p.offsets = (ends - counts).contiguous()
+        p.offsets = torch.empty(p.nblk, dtype=torch.int64, device=t.device)
         p.total_host = total_host if total_host is not None else torch.zeros(1, dtype=torch.int64).pin_memory()
-        if p.nblk:                                           # written by a kernel into the mapped pinned word
-            _lib.check(_lib.lib.ivc_post_words_to_host(dev, sp, ends[-1:].data_ptr(), p.total_host.data_ptr(), 1),
-                       "ivc_post_words_to_host")
+        if p.nblk:              # one scan kernel; it posts the stream length into the mapped pinned word itself
+            wsb = _lib.lib.ivc_zerorun_offsets_workspace_bytes(p.nblk)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=t.device)
+            _lib.check(_lib.lib.ivc_zerorun_offsets(dev, sp, counts.data_ptr(), p.nblk, p.offsets.data_ptr(), ws.data_ptr(), wsb,
+                                                    p.total_host.data_ptr(), None), "ivc_zerorun_offsets")
         else:
             p.total_host.zero_()
         p.event = None

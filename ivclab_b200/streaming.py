@@ -35,7 +35,7 @@ class _Slot:
 
 class StreamedCoder:
     def __init__(self, quantization_scale=1.0, search_range=4, me_mode="auto", chunk_frames=2, device=None, use_graph=True,
-                 slots=3):
+                 slots=3, compute_streams=2):
         self.intra = IntraBlockCoder(quantization_scale)
         self.pframe = PFrameBlockCoder(quantization_scale, search_range, me_mode)
         self.zr = ZeroRunCoder()
@@ -44,6 +44,8 @@ class StreamedCoder:
         self.nslots = max(2, int(slots))          # input buffers in rotation: uploads run ahead of the coder by nslots-1 chunks
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self._s_in, self._s_cmp, self._s_out = (torch.cuda.Stream(self.device) for _ in range(3))
+        # chunks alternate between two compute streams: the tail of one chunk's kernels overlaps the head of the next
+        self._s_cmp2 = torch.cuda.Stream(self.device) if compute_streams > 1 else self._s_cmp
         self._host = None
         self._slots = None         # ((C, H, W), [_Slot, _Slot])
         self.trace = None          # set to [] to collect (label, chunk, start event, end event, host t0, host t1) per stage
@@ -151,25 +153,29 @@ class StreamedCoder:
 
         def compute(k):
             n = min(F, (k + 1) * C) - k * C
-            with torch.cuda.stream(self._s_cmp):
-                self._s_cmp.wait_event(ev_in[k])
-                done = self._mark("code", k, self._s_cmp)      # (the slot's previous results were picked up by finish(k-S),
-                pending[k] = self._launch(slots[k % S], n, C)  #  enqueued on this same stream S-1 iterations ago)
+            sc = self._s_cmp if k % 2 == 0 else self._s_cmp2
+            with torch.cuda.stream(sc):
+                sc.wait_event(ev_in[k])
+                if k >= S:
+                    sc.wait_event(ev_fin[k - S])                  # the slot's previous results have been picked up
+                done = self._mark("code", k, sc)
+                pending[k] = self._launch(slots[k % S], n, C)
                 done()
-                ev_cmp[k].record(self._s_cmp)                      # the input slot may be overwritten from here on
+                ev_cmp[k].record(sc)                               # the input slot may be overwritten from here on
 
         def finish(k):
             """Write chunk k's symbol streams (their lengths have arrived by now) and send the results home."""
             lo, hi = k * C, min(F, (k + 1) * C)
             pend_i, pend_p, mv, sse_i, sse_p = pending.pop(k)
             ev_cmp[k].synchronize()                                # waits for TWO numbers, with chunk k+1 already queued
-            with torch.cuda.stream(self._s_cmp):
-                tr = self._mark("symbols", k, self._s_cmp)
+            sc = self._s_cmp if k % 2 == 0 else self._s_cmp2
+            with torch.cuda.stream(sc):
+                tr = self._mark("symbols", k, sc)
                 sym_i = self.zr.encode_finish(pend_i)
                 sym_p = self.zr.encode_finish(pend_p)
                 mv, sse_i, sse_p = mv.clone(), sse_i.clone(), sse_p.clone()     # frees the slot's (static) result buffers
                 tr()
-                ev_fin[k].record(self._s_cmp)
+                ev_fin[k].record(sc)
             for name, o, sym in (("sym_intra", off[0], sym_i), ("sym_inter", off[1], sym_p)):
                 if o + sym.numel() > hb[name].numel():             # rare: denser streams than provisioned
                     self._s_out.synchronize()                      # earlier downloads into the old buffer are complete
@@ -206,6 +212,7 @@ class StreamedCoder:
         finish(nchunks - 1)
         ev_out[-1].synchronize()
         self._s_cmp.synchronize()
+        self._s_cmp2.synchronize()
         return {"sym_intra": hb["sym_intra"][:off[0]], "sym_inter": hb["sym_inter"][:off[1]], "len_intra": lens_i,
                 "len_inter": lens_p, "mv": hb["mv"], "sse": hb["sse"],
                 "h2d_bytes": rgb.numel() + cur.numel() + ref.numel(),

@@ -45,7 +45,7 @@ def main():
     ref, cur = s[:-1].contiguous().pin_memory(), s[1:].contiguous().pin_memory()
     for frames in (8, 32):
         for chunk in (1, 2, 4, 8):
-            sc = ivc.StreamedCoder(1.0, 4, chunk_frames=chunk, slots=int(os.environ.get("SLOTS", "3")))
+            sc = ivc.StreamedCoder(1.0, 4, chunk_frames=chunk, slots=int(os.environ.get("SLOTS", "3")), compute_streams=int(os.environ.get("CS", "2")))
             for _ in range(2):
                 out = sc.run(rgb[:frames], cur[:frames], ref[:frames])
             torch.cuda.synchronize()
