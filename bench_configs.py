@@ -102,6 +102,23 @@ def main():
                                   "mpixel_s_incl_psnr": F * len(QS) * 1080 * 1920 / t / 1e3}
     t = timed(lambda: [cd.inverse(cd.forward(frames)) for cd in coders], 3, warm=1)
     res["cfg3_rd_sweep_1080p"]["mpixel_s_kernels_only"] = F * len(QS) * 1080 * 1920 / t / 1e3
+    # the same sweep from uint8 RGB originals with the distortion measured inside the decoder (one RD point = two
+    # kernels: forward_rgb, inverse_with_distortion in RGB space as calc_psnr(img, symbols2image(...)) does)
+    rgb8s = (torch.rand((F, 1080, 1920, 3), generator=g, device="cuda") * 255).to(torch.uint8)
+
+    def sweep_fused():
+        for cd in coders:
+            cd.inverse_with_distortion(cd.forward_rgb(rgb8s), rgb8s, space="rgb")
+
+    def sweep_unfused():
+        for cd in coders:
+            rec = ivc.ycbcr2rgb(cd.inverse(cd.forward_rgb(rgb8s)))
+            ivc.frame_sse(rgb8s, rec)
+    t_f, t_u = timed(sweep_fused, 3, warm=1), timed(sweep_unfused, 3, warm=1)
+    res["cfg3_rd_sweep_1080p"].update({"rgb8_psnr_fused_ms_per_sweep": t_f, "rgb8_psnr_unfused_ms_per_sweep": t_u,
+                                       "mpixel_s_rgb8_psnr_fused": F * len(QS) * 1080 * 1920 / t_f / 1e3,
+                                       "mpixel_s_rgb8_psnr_unfused": F * len(QS) * 1080 * 1920 / t_u / 1e3})
+    del rgb8s
     del frames
     torch.cuda.empty_cache()
 

@@ -111,6 +111,24 @@ int ivc_intra_inverse(int device, void *stream,
                       const void *table, int table_dtype,
                       void *out, int out_dtype);
 
+/* ---- fused intra inverse + distortion: one rate-distortion point of a sweep -----------------------
+ * Decodes like ivc_intra_inverse (C = 3) and, in the same kernel, measures the squared error of every frame
+ * against its uint8 RGB original (orig_rgb8: [n_frames, 8*Hp, 8*Wp, 3], W % 16 == 0, frames
+ * orig_frame_stride_bytes apart, 16-byte aligned):
+ *   mode IVC_DIST_RGB   : sse[f] = sum (orig - ycbcr2rgb(rec))^2 -- what calc_psnr(img, symbols2image(...))
+ *                         measures (utils/metrics.py:3-40, image/intracodec.py:139-141, signal/color.py:39-63);
+ *   mode IVC_DIST_YCBCR : sse[f] = sum (rgb2ycbcr(orig) - rec)^2.
+ * out may be NULL: the reconstruction is then not stored (decode + PSNR moves 15 bytes per pixel).
+ * Deterministic (per-tile partial sums added in a fixed order).  workspace: ivc_intra_inverse_sse_workspace_bytes(). */
+#define IVC_DIST_RGB   1
+#define IVC_DIST_YCBCR 2
+int64_t ivc_intra_inverse_sse_workspace_bytes(int64_t n_frames, int64_t Hp, int64_t Wp);
+int ivc_intra_inverse_sse(int device, void *stream,
+                          const int32_t *zz, int64_t n_frames, int64_t Hp, int64_t Wp,
+                          const void *table, int table_dtype,
+                          void *out, const void *orig_rgb8, int64_t orig_frame_stride_bytes, int mode,
+                          void *workspace, int64_t workspace_bytes, double *sse_out);
+
 /* ---- a13: MotionCompensator.compute_motion_vector (motion.py:8-58) ---------------------------
  * ref, cur: n_frames luma planes [H,W] (dtype F32 or F64, both the same), contiguous rows.
  * mv_out: [n_frames, H/8, W/8, 1] int64, index = (dy+sr)*(2sr+1) + (dx+sr); first minimum in

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "_C", "libivcb200.so")
 U8, I32, F32, F64, I64 = 0, 1, 2, 3, 4
 ME_AUTO, ME_EXACT, ME_INT = 0, 1, 2
 SSE_RGB8_AS_YCBCR = 103
+DIST_RGB, DIST_YCBCR = 1, 2
 OK, ERR_ARG, ERR_DTYPE, ERR_SHAPE, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4, -5
 
 _i, _i64, _p = C.c_int, C.c_int64, C.c_void_p
@@ -34,6 +35,8 @@ SIGNATURES = {
     "ivc_zigzag": (_i, [_i, _p, _i, _p, _i, _i64, _p]),
     "ivc_intra_forward": (_i, [_i, _p, _p, _i, _i64, _i64, _i64, _i64, _i64, _p, _i, _p]),
     "ivc_intra_inverse": (_i, [_i, _p, _p, _i64, _i64, _i64, _i64, _p, _i, _p, _i]),
+    "ivc_intra_inverse_sse_workspace_bytes": (_i64, [_i64, _i64, _i64]),
+    "ivc_intra_inverse_sse": (_i, [_i, _p, _p, _i64, _i64, _i64, _p, _i, _p, _p, _i64, _i, _p, _i64, _p]),
     "ivc_me_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "ivc_me_full_search": (_i, [_i, _p, _p, _p, _i, _i64, _i64, _i64, _i64, _i64, _i, _i, _p, _p, _i64]),
     "ivc_mc_reconstruct": (_i, [_i, _p, _p, _i, _i64, _i64, _i64, _i64, _p, _i, _p]),

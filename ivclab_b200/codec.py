@@ -85,6 +85,45 @@ class IntraBlockCoder:
         return to_host(out if batched else out[0], was_np)
 
 
+    def inverse_with_distortion(self, zz, original_rgb8, space="rgb", return_reconstruction=False):
+        """One rate-distortion point without intermediate images: decode ``zz`` ``[(N,) Hp, Wp, 3, 64]`` and, in the
+        same kernel, sum the squared error of every frame against its uint8 RGB original ``[(N,) H, W, 3]``.
+        ``space='rgb'``: error between the original and ``ycbcr2rgb(reconstruction)`` -- what
+        ``calc_psnr(img, codec.symbols2image(...))`` measures (metrics.py:3-40, intracodec.py:139-141);
+        ``space='ycbcr'``: error between ``rgb2ycbcr(original)`` and the reconstruction.
+        Returns the float64 CUDA tensor ``sse [N]`` (``mse = sse / (H*W*3)``), plus the float64 YCbCr reconstruction
+        when asked for; without it the decoder stores nothing (15 bytes of traffic per pixel)."""
+        t, _ = to_device(zz)
+        o, _ = to_device(original_rgb8, t.device)
+        batched = t.ndim == 5
+        if t.ndim not in (4, 5) or t.shape[-1] != 64 or t.shape[-2] != 3:
+            raise ValueError(f"expected [Hp,Wp,3,64] or [N,Hp,Wp,3,64], got shape {tuple(t.shape)}")
+        t = aligned16(t.to(torch.int32))
+        v = t if batched else t[None]
+        ov = o if o.ndim == 4 else o[None]
+        N, Hp, Wp, _, _ = v.shape
+        if o.dtype != torch.uint8 or tuple(ov.shape) != (N, Hp * 8, Wp * 8, 3):
+            raise ValueError(f"original must be uint8 RGB of shape {(N, Hp * 8, Wp * 8, 3)}, got {o.dtype} {tuple(o.shape)}")
+        if Wp % 2:
+            raise ValueError("the fused distortion path needs an image width that is a multiple of 16")
+        if space not in ("rgb", "ycbcr"):
+            raise ValueError("space must be 'rgb' or 'ycbcr'")
+        ov = aligned16(ov)
+        _, dtab = self.quant._table_on(v.device)
+        out = torch.empty((N, Hp * 8, Wp * 8, 3), dtype=torch.float64, device=v.device) if return_reconstruction else None
+        sse = torch.empty(N, dtype=torch.float64, device=v.device)
+        wsb = _lib.lib.ivc_intra_inverse_sse_workspace_bytes(N, Hp, Wp)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=v.device)
+        st = _lib.lib.ivc_intra_inverse_sse(dev_index(v), stream_ptr(v.device), v.data_ptr(), N, Hp, Wp, dtab.data_ptr(),
+                                            code(dtab.dtype), out.data_ptr() if out is not None else None, ov.data_ptr(),
+                                            Hp * 8 * Wp * 8 * 3, _lib.DIST_RGB if space == "rgb" else _lib.DIST_YCBCR,
+                                            ws.data_ptr(), wsb, sse.data_ptr())
+        _lib.check(st, "ivc_intra_inverse_sse")
+        if not batched:
+            sse, out = sse[0], (out[0] if out is not None else None)
+        return (sse, out) if return_reconstruction else sse
+
+
 class PFrameBlockCoder:
     """Motion estimation, then MC + residual fused into the forward transform and
     prediction + residual fused into the inverse transform (luma planes, float64)."""

@@ -146,6 +146,33 @@ int ivc_intra_inverse(int device, void *stream, const int32_t *zz, int64_t n_fra
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
 
+int64_t ivc_intra_inverse_sse_workspace_bytes(int64_t n_frames, int64_t Hp, int64_t Wp) {
+    if (n_frames < 0 || Hp < 0 || Wp < 0) return -1;
+    return (ivc::inverse_sse_tiles(n_frames, Hp, Wp) + 1) * (int64_t)sizeof(double);
+}
+
+int ivc_intra_inverse_sse(int device, void *stream, const int32_t *zz, int64_t n_frames, int64_t Hp, int64_t Wp,
+                          const void *table, int table_dtype, void *out, const void *orig_rgb8,
+                          int64_t orig_frame_stride_bytes, int mode, void *workspace, int64_t workspace_bytes,
+                          double *sse_out) {
+    if (n_frames < 0 || Hp < 0 || Wp < 0 || orig_frame_stride_bytes < 0) return IVC_ERR_ARG;
+    if (mode != IVC_DIST_RGB && mode != IVC_DIST_YCBCR) return IVC_ERR_ARG;
+    if (!is_float(table_dtype)) return IVC_ERR_DTYPE;
+    if (Wp & 1) return IVC_ERR_SHAPE;                                       // 16-byte rows of packed RGB
+    if (n_frames == 0) return IVC_OK;
+    if (!sse_out) return IVC_ERR_ARG;
+    if (Hp * Wp > 0) {
+        if (!zz || !table || !orig_rgb8) return IVC_ERR_ARG;
+        if (!aligned16(zz) || !aligned16(orig_rgb8) || (out && !aligned16(out)) || (orig_frame_stride_bytes & 15)) return IVC_ERR_ARG;
+    }
+    if (!workspace || workspace_bytes < ivc_intra_inverse_sse_workspace_bytes(n_frames, Hp, Wp)) return IVC_ERR_WORKSPACE;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_inverse_sse(device, (cudaStream_t)stream, zz, n_frames, Hp, Wp, table, table_dtype, out,
+                                            orig_rgb8, orig_frame_stride_bytes, mode, (double *)workspace, sse_out);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
 int64_t ivc_me_workspace_bytes(int64_t n_frames, int64_t H, int64_t W) {
     if (n_frames < 0 || H < 0 || W < 0) return -1;
     return 256;                                // one device flag (kept 256-byte sized/aligned)

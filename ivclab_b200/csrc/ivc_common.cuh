@@ -13,6 +13,10 @@ cudaError_t launch_forward(int device, cudaStream_t st, const void *img, int64_t
 cudaError_t launch_inverse(int device, cudaStream_t st, const int32_t *zz, int64_t n, int64_t Hp, int64_t Wp, int Czz,
                            const void *table, int table_dtype, void *out, int mode,
                            const void *pred, const void *ref, const int64_t *mv, int sr);
+int64_t inverse_sse_tiles(int64_t n, int64_t Hp, int64_t Wp);
+cudaError_t launch_inverse_sse(int device, cudaStream_t st, const int32_t *zz, int64_t n, int64_t Hp, int64_t Wp,
+                               const void *table, int table_dtype, void *out, const void *orig_rgb8,
+                               int64_t orig_frame_stride, int sse_mode, double *partial, double *sse_out);
 cudaError_t launch_dct(int device, cudaStream_t st, bool inverse, const void *x, int x_dtype, int64_t n0, int64_t n1,
                        int64_t C, const int64_t s[5], void *out, bool f32);
 cudaError_t launch_quant(int device, cudaStream_t st, bool dequant, const void *x, int x_dtype, int64_t n0, int64_t n1,

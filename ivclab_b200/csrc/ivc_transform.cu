@@ -296,6 +296,10 @@ struct InvArgs {
     const double *ref;
     const int64_t *mv;
     int sr;
+    // intra + distortion (k_inverse_c3_tma<SSE>): uint8 RGB originals and one partial sum per tile
+    const unsigned char *orig;       // [n, H, W, 3] uint8, frames orig_frame_stride bytes apart
+    int64_t orig_frame_stride;
+    double *sse_partial;             // [total_tiles]
 };
 
 // MODE 0: intra, 3 scan channels -> 3 image channels      (tile = 4 blocks x 3 channels)
@@ -830,13 +834,26 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_rgb8_tma(const
     bulk_wait_all0();
 }
 
+// SSE != 0 fuses the distortion measurement of a rate-distortion point into the decoder: the uint8 RGB original of
+// the tile rides along on the same mbarrier (8 bulk rows, double-buffered: it is needed at the END of a tile while
+// the next tile's copy is issued at its start), and each warp leaves one partial sum per tile --
+//   SSE 1: sum (orig_rgb - ycbcr2rgb(rec))^2, what calc_psnr(img, symbols2image(...)) measures (metrics.py:3-40,
+//          intracodec.py:139-141, color.py:39-63);   SSE 2: sum (rgb2ycbcr(orig_rgb) - rec)^2.
+// A second kernel adds the partials of a frame in a fixed order (deterministic).  a.out == nullptr skips the
+// reconstruction store: decode + PSNR then moves 15 bytes per pixel instead of 36 + 24 + 48 + 27.
+constexpr int kInvIn = 4 * kStageU * 4;                                          // 3200 B of scan blocks
+constexpr int kInvBuf = kInvIn + kWorkBytes;                                     // 9600 B
+constexpr int kInvBufSse = kInvBuf + 2 * kRgbIn + 128;                           // + two 896-byte RGB tiles -> 11520 B
+static_assert(kInvBufSse % 128 == 0, "alignment");
+
+template <int SSE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_inverse_c3_tma(const InvArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_tT = reinterpret_cast<double *>(smem_raw);                        // [192]
     unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem_raw + 1536);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int kIn2 = 4 * kStageU * 4;                                        // 3200 B
-    constexpr int kBuf = kIn2 + kWorkBytes;                                      // 9600 B
+    constexpr int kIn2 = kInvIn;
+    constexpr int kBuf = SSE ? kInvBufSse : kInvBuf;
     unsigned char *in_b = smem_raw + 1664 + warp * kBuf;
     unsigned char *work_b = in_b + kIn2;
     const uint32_t bar = smem_u32(s_bar + warp), in_s = smem_u32(in_b), work_s = smem_u32(work_b);
@@ -873,14 +890,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_inverse_c3_tma(const I
     cur.init(g, gw, nw);
     nxt = cur;
 
-    auto issue = [&](const TileIter &ti) {
+    auto issue = [&](const TileIter &ti, uint32_t slot) {
         const int b0 = ti.tx * 4, nb = min(4, g.Wp - b0);
         const int32_t *zsrc = a.zz + ((ti.frame * g.Hp + ti.by) * (int64_t)g.Wp + b0) * 192;
-        mbar_expect_tx(bar, (uint32_t)nb * 768u);
+        mbar_expect_tx(bar, (uint32_t)nb * (SSE ? 768u + 192u : 768u));         // + 8 rows x nb x 24 bytes of RGB
         for (int cu = 0; cu < nb; ++cu) bulk_g2s(in_s + cu * (kStageU * 4), zsrc + cu * 192, 768u, bar);
+        if (SSE) {
+            const unsigned char *osrc = a.orig + ti.frame * a.orig_frame_stride + (int64_t)ti.by * 8 * (g.W * 3) + (int64_t)ti.tx * 96;
+            for (int row = 0; row < 8; ++row)                                    // nb is even (W % 16 == 0): 16-byte multiples
+                bulk_g2s(work_s + kWorkBytes + slot * kRgbIn + row * kRgbPitch, osrc + row * (g.W * 3), (uint32_t)nb * 24u, bar);
+        }
     };
 
-    if (lane == 0) issue(cur);
+    if (lane == 0) issue(cur, 0u);
     uint32_t parity = 0;
     for (int64_t it = 0; it < my_tiles; ++it, parity ^= 1u) {
         nxt.advance(g);
@@ -892,7 +914,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_inverse_c3_tma(const I
             for (int j = 0; j < 8; ++j) q[m][j] = *reinterpret_cast<const int *>(q_rd[j] + m * 256);
         __syncwarp();
         if (lane == 0) {
-            if (it + 1 < my_tiles) { fence_proxy_async(); issue(nxt); }
+            if (it + 1 < my_tiles) { fence_proxy_async(); issue(nxt, parity ^ 1u); }
             bulk_wait_read0();
         }
         double x[3][8];
@@ -930,23 +952,63 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_inverse_c3_tma(const I
             dct3_8(x[m]);
         }
         __syncwarp();
+        if (SSE) {
+            // this lane holds pixel column 8u + r of the tile, rows 0..7, all three channels
+            const unsigned char *ob = work_b + kWorkBytes + parity * kRgbIn + (8 * u + r) * 3;     // [2][8 rows][kRgbPitch]
+            double acc = 0.0;
+            if (u < min(4, g.Wp - cur.tx * 4)) {
 #pragma unroll
-        for (int m = 0; m < 3; ++m)
+                for (int i = 0; i < 8; ++i) {
+                    const double o0 = (double)ob[i * kRgbPitch], o1 = (double)ob[i * kRgbPitch + 1], o2 = (double)ob[i * kRgbPitch + 2];
+                    double d0, d1, d2;
+                    if (SSE == 1) {
+                        double rr, gg, bb;
+                        ycbcr2rgb_px(x[0][i], x[1][i], x[2][i], rr, gg, bb);
+                        d0 = __dsub_rn(o0, rr); d1 = __dsub_rn(o1, gg); d2 = __dsub_rn(o2, bb);
+                    } else {
+                        double yy, cb, cr;
+                        rgb2ycbcr_px(o0, o1, o2, yy, cb, cr);
+                        d0 = __dsub_rn(yy, x[0][i]); d1 = __dsub_rn(cb, x[1][i]); d2 = __dsub_rn(cr, x[2][i]);
+                    }
+                    acc = __dadd_rn(acc, __dmul_rn(d0, d0));
+                    acc = __dadd_rn(acc, __dmul_rn(d1, d1));
+                    acc = __dadd_rn(acc, __dmul_rn(d2, d2));
+                }
+            }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) *reinterpret_cast<double *>(o_wr + i * (kRowPitch * 8) + m * 8) = x[m][i];
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-            const int nb = min(4, g.Wp - cur.tx * 4);
-            double *dst = a.out + cur.frame * out_frame + (int64_t)cur.by * 8 * row_elems + (int64_t)cur.tx * 96;
-            const uint32_t row_bytes = (uint32_t)nb * 192u;
+            for (int off = 16; off > 0; off >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, off));
+            if (lane == 0) a.sse_partial[(cur.frame * g.Hp + cur.by) * (int64_t)g.tiles_per_row + cur.tx] = acc;
+        }
+        if (!SSE || a.out) {
 #pragma unroll
-            for (int row = 0; row < 8; ++row) bulk_s2g(dst + row * row_elems, work_s + row * (kRowPitch * 8), row_bytes);
-            bulk_commit();
+            for (int m = 0; m < 3; ++m)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) *reinterpret_cast<double *>(o_wr + i * (kRowPitch * 8) + m * 8) = x[m][i];
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                const int nb = min(4, g.Wp - cur.tx * 4);
+                double *dst = a.out + cur.frame * out_frame + (int64_t)cur.by * 8 * row_elems + (int64_t)cur.tx * 96;
+                const uint32_t row_bytes = (uint32_t)nb * 192u;
+#pragma unroll
+                for (int row = 0; row < 8; ++row) bulk_s2g(dst + row * row_elems, work_s + row * (kRowPitch * 8), row_bytes);
+                bulk_commit();
+            }
         }
         cur = nxt;
     }
     if (lane == 0) bulk_wait_all0();
+}
+
+// sum the tile partials of each frame in a fixed order (one warp per frame)
+__global__ void __launch_bounds__(32) k_sum_tile_partials(const double *__restrict__ partial, int64_t tiles_per_frame,
+                                                          double *__restrict__ out) {
+    const double *p = partial + (int64_t)blockIdx.x * tiles_per_frame;
+    double acc = 0.0;
+    for (int64_t c = threadIdx.x; c < tiles_per_frame; c += 32) acc = __dadd_rn(acc, p[c]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, off));
+    if (threadIdx.x == 0) out[blockIdx.x] = acc;
 }
 
 // ================================================================================================
@@ -1522,14 +1584,15 @@ cudaError_t launch_inverse(int device, cudaStream_t st, const int32_t *zz, int64
     a.g = make_geom(n, Hp * 8, Wp * 8, Czz, mode == 2 ? 12 : 4);
     a.zz = zz; a.Czz = Czz; a.table = table; a.table_dtype = table_dtype; a.out = (double *)out;
     a.pred = (const double *)pred; a.ref = (const double *)ref; a.mv = mv; a.sr = sr;
+    a.orig = nullptr; a.orig_frame_stride = 0; a.sse_partial = nullptr;
     if (a.g.total_tiles == 0) return cudaSuccess;
     const size_t smem = 192 * sizeof(double) + kWarpsPerCta * kWarpBufBytes;
     const int grid = grid_for(a.g.total_tiles, kWarpsPerCta, device, 2);
     cudaError_t e;
     if (mode == 0 && !use_v1()) {
-        const size_t smem2 = 1664 + (size_t)kWarpsPerCta * (4 * kStageU * 4 + kWorkBytes);
-        if ((e = set_smem(k_inverse_c3_tma, smem2)) != cudaSuccess) return e;
-        k_inverse_c3_tma<<<grid, kWarpsPerCta * 32, smem2, st>>>(a);
+        const size_t smem2 = 1664 + (size_t)kWarpsPerCta * kInvBuf;
+        if ((e = set_smem(k_inverse_c3_tma<0>, smem2)) != cudaSuccess) return e;
+        k_inverse_c3_tma<0><<<grid, kWarpsPerCta * 32, smem2, st>>>(a);
     } else if (mode == 0) {
         if ((e = set_smem(k_inverse<0>, smem)) != cudaSuccess) return e;
         k_inverse<0><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
@@ -1544,6 +1607,32 @@ cudaError_t launch_inverse(int device, cudaStream_t st, const int32_t *zz, int64
         if ((e = set_smem(k_inverse<2>, smem)) != cudaSuccess) return e;
         k_inverse<2><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
     }
+    return cudaGetLastError();
+}
+
+int64_t inverse_sse_tiles(int64_t n, int64_t Hp, int64_t Wp) { return n * Hp * ((Wp + 3) / 4); }
+
+// decode (3 scan channels) and measure the distortion against uint8 RGB originals in the same kernel
+cudaError_t launch_inverse_sse(int device, cudaStream_t st, const int32_t *zz, int64_t n, int64_t Hp, int64_t Wp,
+                               const void *table, int table_dtype, void *out, const void *orig_rgb8,
+                               int64_t orig_frame_stride, int sse_mode, double *partial, double *sse_out) {
+    InvArgs a;
+    a.g = make_geom(n, Hp * 8, Wp * 8, 3, 4);
+    a.zz = zz; a.Czz = 3; a.table = table; a.table_dtype = table_dtype; a.out = (double *)out;
+    a.pred = nullptr; a.ref = nullptr; a.mv = nullptr; a.sr = 0;
+    a.orig = (const unsigned char *)orig_rgb8; a.orig_frame_stride = orig_frame_stride; a.sse_partial = partial;
+    if (a.g.total_tiles == 0) return cudaSuccess;
+    const int grid = grid_for(a.g.total_tiles, kWarpsPerCta, device, 2);
+    const size_t smem = 1664 + (size_t)kWarpsPerCta * kInvBufSse;
+    cudaError_t e;
+    if (sse_mode == 1) {
+        if ((e = set_smem(k_inverse_c3_tma<1>, smem)) != cudaSuccess) return e;
+        k_inverse_c3_tma<1><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
+    } else {
+        if ((e = set_smem(k_inverse_c3_tma<2>, smem)) != cudaSuccess) return e;
+        k_inverse_c3_tma<2><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
+    }
+    k_sum_tile_partials<<<(unsigned)n, 32, 0, st>>>(partial, Hp * (int64_t)a.g.tiles_per_row, sse_out);
     return cudaGetLastError();
 }
 

@@ -23,7 +23,7 @@ import torch
 from . import _lib  # noqa: F401
 from .codec import IntraBlockCoder, PFrameBlockCoder
 from .entropy import ZeroRunCoder
-from .utils.metrics import frame_sse, frame_sse_rgb8_vs_ycbcr
+from .utils.metrics import frame_sse
 
 __all__ = ["StreamedCoder"]
 
@@ -96,8 +96,7 @@ class StreamedCoder:
         d_rgb, d_cur, d_ref = s.rgb[:n], s.cur[:n].double(), s.ref[:n].double()
         zz = self.intra.forward_rgb(d_rgb)
         pend_i = self.zr.encode_begin(zz, total_host=s.totals[0:1], record=False)
-        rec = self.intra.inverse(zz)
-        sse_i = frame_sse_rgb8_vs_ycbcr(d_rgb, rec)             # == frame_sse(rgb2ycbcr(d_rgb), rec), same bits
+        sse_i = self.intra.inverse_with_distortion(zz, d_rgb, space="ycbcr")   # decode + error in one kernel, nothing stored
         mv = self.pframe.estimate(d_ref, d_cur)
         zzp = self.pframe.forward(d_cur, d_ref, mv)
         pend_p = self.zr.encode_begin(zzp, total_host=s.totals[1:2], record=False)

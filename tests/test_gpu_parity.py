@@ -463,6 +463,33 @@ def test_fused_colour_sse_equals_two_step_form():
     assert np.allclose(ivc.frame_sse_rgb8_vs_ycbcr(rgb, rec).cpu().numpy(), want, rtol=1e-12, atol=0)
 
 
+@pytest.mark.parametrize("space", ["rgb", "ycbcr"])
+def test_fused_decode_and_distortion(space):
+    """ivc_intra_inverse_sse: the reconstruction equals the plain decoder's bit for bit; the squared error equals
+    the reference's PSNR pipeline (ycbcr2rgb + calc_mse, or rgb2ycbcr of the original) within reduction order."""
+    rgb = np.stack([O.smooth_noise_rgb(40 + i, 72, 112) for i in range(3)])
+    for q in (0.07, 1.0, 4.5):
+        coder = ivc.IntraBlockCoder(q)
+        zz = coder.forward_rgb(torch.from_numpy(rgb).cuda())
+        sse, rec = coder.inverse_with_distortion(zz, torch.from_numpy(rgb).cuda(), space=space, return_reconstruction=True)
+        assert torch.equal(rec, coder.inverse(zz))
+        only = coder.inverse_with_distortion(zz, torch.from_numpy(rgb).cuda(), space=space)
+        assert torch.equal(only, sse)                                              # same sums without the store
+        rec_np = rec.cpu().numpy()
+        if space == "rgb":
+            want = [((rgb[i].astype(np.float64) - O.ycbcr2rgb(rec_np[i])) ** 2).sum() for i in range(3)]
+            psnr_ref = [O.calc_psnr(rgb[i], O.ycbcr2rgb(rec_np[i])) for i in range(3)]
+            psnr = [20 * np.log10(255.0 / np.sqrt(float(s) / rgb[i].size)) for i, s in enumerate(sse.cpu().numpy())]
+            assert np.allclose(psnr, psnr_ref, rtol=0, atol=1e-9)                 # north star: PSNR within 0.01 dB
+        else:
+            want = [((O.rgb2ycbcr(rgb[i]) - rec_np[i]) ** 2).sum() for i in range(3)]
+        assert np.allclose(sse.cpu().numpy(), want, rtol=1e-12, atol=0)
+    one = coder.inverse_with_distortion(zz[0], torch.from_numpy(rgb[0]).cuda(), space=space)
+    assert one.ndim == 0 and float(one) == float(sse[0])
+    with pytest.raises(ValueError):
+        coder.inverse_with_distortion(zz, torch.from_numpy(rgb.astype(np.float64)).cuda())
+
+
 def test_metrics_match_reference(g1, g6):
     """N3: calc_mse / calc_psnr (metrics.py:3-40); reduction order differs from numpy's pairwise mean,
     so the comparison is relative 1e-12 (PSNR: far below the 0.01 dB bar)."""
