@@ -62,15 +62,16 @@ class StreamedCoder:
                 "mv": pin((F, H // 8, W // 8, 1), torch.int64), "sse": pin((2, F), torch.float64)})
         return self._host[1]
 
-    def _device_slots(self, C, H, W):
-        key = (C, H, W)
+    def _device_slots(self, C, H, W, seq):
+        key = (C, H, W, seq)
         if self._slots is None or self._slots[0] != key:
             slots = []
             for _ in range(self.nslots):
                 s = _Slot()
                 s.rgb = torch.empty((C, H, W, 3), dtype=torch.uint8, device=self.device)
-                s.cur = torch.empty((C, H, W), dtype=torch.uint8, device=self.device)
-                s.ref = torch.empty((C, H, W), dtype=torch.uint8, device=self.device)
+                # sequence mode: one luma buffer of C+1 frames, frame 0 = the frame before the chunk (its reference)
+                s.cur = torch.empty((C + 1 if seq else C, H, W), dtype=torch.uint8, device=self.device)
+                s.ref = None if seq else torch.empty((C, H, W), dtype=torch.uint8, device=self.device)
                 s.graph, s.out = None, None
                 s.totals = torch.zeros(2, dtype=torch.int64).pin_memory()      # the two stream lengths of the chunk in flight
                 slots.append(s)
@@ -93,7 +94,12 @@ class StreamedCoder:
     # ---- one chunk on the device -------------------------------------------------------------------
     def _code(self, s: _Slot, n: int):
         """Everything of a chunk that does not need a stream length on the host (current stream = compute stream)."""
-        d_rgb, d_cur, d_ref = s.rgb[:n], s.cur[:n].double(), s.ref[:n].double()
+        d_rgb = s.rgb[:n]
+        if s.ref is None:                              # sequence mode: frame t is predicted from frame t-1
+            luma = s.cur[:n + 1].double()
+            d_ref, d_cur = luma[:n], luma[1:]
+        else:
+            d_cur, d_ref = s.cur[:n].double(), s.ref[:n].double()
         zz = self.intra.forward_rgb(d_rgb)
         pend_i = self.zr.encode_begin(zz, total_host=s.totals[0:1], record=False)
         sse_i = self.intra.inverse_with_distortion(zz, d_rgb, space="ycbcr")   # decode + error in one kernel, nothing stored
@@ -118,17 +124,23 @@ class StreamedCoder:
         return s.out
 
     # ---- the pipeline ----------------------------------------------------------------------------
-    def run(self, rgb, cur, ref):
-        """rgb [F,H,W,3] uint8, cur/ref [F,H,W] uint8 luma planes -- pinned host tensors (numpy arrays are
-        accepted and pinned once).  Returns host-side results: ``sym_intra`` / ``sym_inter`` (int32 streams
-        and per-chunk lengths), ``mv`` [F,Hp,Wp,1] int64, ``sse`` [2,F] (intra on YCbCr, inter on luma)."""
+    def run(self, rgb, cur, ref=None, first_ref=None):
+        """rgb [F,H,W,3] uint8, cur [F,H,W] uint8 luma planes -- pinned host tensors (numpy arrays are accepted and
+        pinned once).  The P-frame references are either given frame by frame (``ref`` [F,H,W]) or implied by the
+        sequence (``ref=None``): frame t is predicted from frame t-1 and frame 0 from ``first_ref`` [H,W] -- every
+        luma frame then crosses PCIe once instead of twice.  Returns host-side results: ``sym_intra`` /
+        ``sym_inter`` (int32 streams and per-chunk lengths), ``mv`` [F,Hp,Wp,1] int64, ``sse`` [2,F] (intra on
+        YCbCr, inter on luma)."""
         pinned = lambda x: (torch.from_numpy(x) if isinstance(x, np.ndarray) else x)
-        rgb, cur, ref = (t if t.is_pinned() else t.pin_memory() for t in map(pinned, (rgb, cur, ref)))
+        seq = ref is None
+        if seq and first_ref is None:
+            raise ValueError("sequence mode (ref=None) needs first_ref, the reference of frame 0")
+        rgb, cur, ref = (t if t.is_pinned() else t.pin_memory() for t in map(pinned, (rgb, cur, first_ref if seq else ref)))
         F, H, W, _ = rgb.shape
         hb = self._host_buffers(F, H, W)
         C = self.chunk
         nchunks = (F + C - 1) // C
-        slots = self._device_slots(C, H, W)
+        slots = self._device_slots(C, H, W, seq)
         S = self.nslots
         ev_in = [torch.cuda.Event() for _ in range(nchunks)]
         ev_cmp = [torch.cuda.Event() for _ in range(nchunks)]
@@ -145,8 +157,16 @@ class StreamedCoder:
                     self._s_in.wait_event(ev_cmp[k - S])          # the slot's previous chunk has been consumed
                 s = slots[k % S]
                 done = self._mark("h2d", k, self._s_in)
-                for dst, src in ((s.rgb, rgb), (s.cur, cur), (s.ref, ref)):
-                    dst[:hi - lo].copy_(src[lo:hi], non_blocking=True)
+                s.rgb[:hi - lo].copy_(rgb[lo:hi], non_blocking=True)
+                if seq:
+                    s.cur[1:1 + hi - lo].copy_(cur[lo:hi], non_blocking=True)
+                    if k == 0:
+                        s.cur[0].copy_(ref.reshape(H, W), non_blocking=True)
+                    else:                                         # the last frame of the previous chunk, already on the
+                        s.cur[0].copy_(slots[(k - 1) % S].cur[C])  # device (this stream uploaded it): device-to-device
+                else:
+                    s.cur[:hi - lo].copy_(cur[lo:hi], non_blocking=True)
+                    s.ref[:hi - lo].copy_(ref[lo:hi], non_blocking=True)
                 done()
                 ev_in[k].record(self._s_in)
 
@@ -214,5 +234,5 @@ class StreamedCoder:
         self._s_cmp2.synchronize()
         return {"sym_intra": hb["sym_intra"][:off[0]], "sym_inter": hb["sym_inter"][:off[1]], "len_intra": lens_i,
                 "len_inter": lens_p, "mv": hb["mv"], "sse": hb["sse"],
-                "h2d_bytes": rgb.numel() + cur.numel() + ref.numel(),
+                "h2d_bytes": rgb.numel() + cur.numel() + ref.numel(),            # ref = one frame in sequence mode
                 "d2h_bytes": (off[0] + off[1]) * 4 + hb["mv"].numel() * 8 + hb["sse"].numel() * 8}

@@ -551,3 +551,10 @@ def test_streamed_coder_matches_direct_calls():
     assert np.array_equal(out["sym_intra"].numpy(), np.concatenate(sym_i))
     assert np.array_equal(out["sym_inter"].numpy(), np.concatenate(sym_p))
     assert sum(out["len_intra"]) == out["sym_intra"].numel()
+    # sequence mode: the references are implied (frame t-1), every luma frame is uploaded once -- same results
+    keep = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
+    for chunk, slots in ((2, 3), (3, 2), (8, 2)):
+        out2 = ivc.StreamedCoder(0.4, 4, chunk_frames=chunk, slots=slots).run(rgb, cur, first_ref=seq[0])
+        for k in ("sym_intra", "sym_inter", "mv", "sse"):
+            assert torch.equal(out2[k], keep[k]), (chunk, k)
+        assert out2["h2d_bytes"] == rgb.size + cur.size + seq[0].size
