@@ -117,6 +117,28 @@ class Clocks:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def pin_to_gpu_cpus(local_rank):
+    """One process per GPU: run (and therefore first-touch the pinned staging buffers) on the CPUs NVML reports as
+    local to this GPU, so that host<->device copies of the N ranks do not all cross the same socket link.
+    Best effort: returns the CPU count it was pinned to, or None (no NVML, restricted cpuset, ...)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(visible.split(",")[local_rank]) if visible and all(v.strip().isdigit() for v in visible.split(",")) else local_rank
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------------
 # synthetic inputs, generated on the device (input synthesis is not part of the measured path)
 # ------------------------------------------------------------------------------------------------
@@ -158,6 +180,7 @@ def run_b200(args):
     assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa = pin_to_gpu_cpus(local) if world > 1 else None   # pinned staging buffers then live next to this GPU's PCIe root
     if world > 1:
         # NCCL prints its version banner on STDOUT when the communicator comes up; stdout carries exactly one JSON
         # line, so point fd 1 at stderr until the first collective has run
@@ -385,7 +408,7 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(Fr, world),
             "e2e": None if args.no_e2e else {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "frames_per_step": Fe, "ms_per_step": round(e2e_ms, 3),
+                    "frames_per_step": Fe, "ms_per_step": round(e2e_ms, 3), "host_cpus_per_rank": numa,
                     "single_stream": {"frames_per_step": Fa, "ms_per_step": round(serial_ms, 3),
                                       "value": round(world * Fa * H * W / (serial_ms * 1e-3) / 1e6, 1)},
                     "api": "StreamedCoder.run (upload / 2 compute / download streams, 4-frame chunks, one CUDA graph per slot): pinned host uint8 RGB + uint8 luma in; "
