@@ -41,6 +41,7 @@ extern "C" {
 #define IVC_F32  2
 #define IVC_F64  3
 #define IVC_I64  4
+#define IVC_I16  5
 
 /* status codes */
 #define IVC_OK            0
@@ -142,6 +143,15 @@ int ivc_me_full_search(int device, void *stream,
                        int64_t ref_frame_stride, int64_t cur_frame_stride,
                        int search_range, int mode,
                        int64_t *mv_out, void *workspace, int64_t workspace_bytes);
+
+/* a13 on INTEGER-dtype frames (U8, I16 or I32, both frames the same): numpy evaluates (block - ref_block)**2 in the
+ * frames' dtype -- a uint8 difference and its square wrap mod 256, 255**2 is -511 in int16 -- and sums in
+ * uint64 / int64 (motion.py:46).  This entry replays exactly that arithmetic, so the
+ * vectors equal the reference's on such inputs. */
+int ivc_me_full_search_intdtype(int device, void *stream,
+                                const void *ref, const void *cur, int dtype, int64_t n_frames,
+                                int64_t H, int64_t W, int64_t ref_frame_stride, int64_t cur_frame_stride,
+                                int search_range, int64_t *mv_out);
 
 /* ---- a14: MotionCompensator.reconstruct_with_motion_vector (motion.py:60-97) -----------------
  * ref: [n_frames, H, W, C] of elem_size-byte elements; mv: [n_frames, H/8, W/8, 1] int64.

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_C", "libivcb200.so")
 
 # element type codes (include/ivclab_b200.h)
-U8, I32, F32, F64, I64 = 0, 1, 2, 3, 4
+U8, I32, F32, F64, I64, I16 = 0, 1, 2, 3, 4, 5
 ME_AUTO, ME_EXACT, ME_INT = 0, 1, 2
 SSE_RGB8_AS_YCBCR = 103
 DIST_RGB, DIST_YCBCR = 1, 2
@@ -39,6 +39,7 @@ SIGNATURES = {
     "ivc_intra_inverse_sse": (_i, [_i, _p, _p, _i64, _i64, _i64, _p, _i, _p, _p, _i64, _i, _p, _i64, _p]),
     "ivc_me_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "ivc_me_full_search": (_i, [_i, _p, _p, _p, _i, _i64, _i64, _i64, _i64, _i64, _i, _i, _p, _p, _i64]),
+    "ivc_me_full_search_intdtype": (_i, [_i, _p, _p, _p, _i, _i64, _i64, _i64, _i64, _i64, _i, _p]),
     "ivc_mc_reconstruct": (_i, [_i, _p, _p, _i, _i64, _i64, _i64, _i64, _p, _i, _p]),
     "ivc_pframe_forward": (_i, [_i, _p, _p, _p, _p, _i, _i64, _i64, _i64, _i, _p, _i, _p, _p]),
     "ivc_pframe_inverse": (_i, [_i, _p, _p, _i64, _p, _p, _p, _i, _i64, _i64, _i64, _i, _p, _i, _p]),

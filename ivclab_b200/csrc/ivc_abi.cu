@@ -210,6 +210,21 @@ int ivc_me_full_search(int device, void *stream, const void *ref, const void *cu
     return IVC_OK;
 }
 
+int ivc_me_full_search_intdtype(int device, void *stream, const void *ref, const void *cur, int dtype, int64_t n_frames,
+                                int64_t H, int64_t W, int64_t ref_frame_stride, int64_t cur_frame_stride,
+                                int search_range, int64_t *mv_out) {
+    if (n_frames < 0 || H < 0 || W < 0 || search_range < 0 || search_range > 64) return IVC_ERR_ARG;
+    if (dtype != IVC_U8 && dtype != IVC_I16 && dtype != IVC_I32) return IVC_ERR_DTYPE;
+    if ((H & 7) || (W & 7)) return IVC_ERR_SHAPE;                         // the reference raises on ragged frames
+    if (n_frames * H * W == 0) return IVC_OK;
+    if (!ref || !cur || !mv_out || H > 2147483647LL || W > 2147483647LL) return IVC_ERR_ARG;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_me_wrap(device, (cudaStream_t)stream, ref, cur, dtype, n_frames, H, W, ref_frame_stride,
+                                        cur_frame_stride, search_range, mv_out);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
 int ivc_mc_reconstruct(int device, void *stream, const void *ref, int elem_sz, int64_t n_frames, int64_t H, int64_t W,
                        int64_t C, const int64_t *mv, int search_range, void *out) {
     if (n_frames < 0 || H < 0 || W < 0 || C < 0 || search_range < 0) return IVC_ERR_ARG;

@@ -31,6 +31,8 @@ cudaError_t launch_me_exact(int device, cudaStream_t st, const void *ref, const 
 cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const void *cur, bool f32, int64_t n,
                           int64_t H, int64_t W, int64_t ref_fs, int64_t cur_fs, int sr, int64_t *mv, int *flag,
                           int check);
+cudaError_t launch_me_wrap(int device, cudaStream_t st, const void *ref, const void *cur, int dtype, int64_t n, int64_t H,
+                           int64_t W, int64_t ref_fs, int64_t cur_fs, int sr, int64_t *mv);
 cudaError_t launch_mc(int device, cudaStream_t st, const void *ref, int elem_size, int64_t n, int64_t H, int64_t W,
                       int64_t C, const int64_t *mv, int sr, void *out);
 

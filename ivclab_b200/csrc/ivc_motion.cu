@@ -517,6 +517,80 @@ __global__ void __launch_bounds__(PC ? kMeIntMaxThreads : kMeThreads, PC ? 2 : 3
     }
 }
 
+static int sm_count(int device) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    return sms;
+}
+
+// ================================================================================================
+// integer-DTYPE frames: numpy's own wrap-around arithmetic
+// ================================================================================================
+// For uint8 / int16 / int32 frames `(block - ref_block) ** 2` is evaluated IN THAT DTYPE (a uint8 difference
+// wraps mod 256 and so does its square; 255**2 is -511 in int16) and np.sum then accumulates in uint64 / int64
+// (motion.py:46).  The reference's vectors on such inputs are whatever this arithmetic yields, so it is replayed
+// literally: one warp per block, lanes over candidates, T-typed difference and square, 64-bit accumulation,
+// lexicographic (ssd, index) argmin in the accumulator's signedness.  Not a fast path: uint8 / int16 frames are a
+// corner of the reference's behaviour, the codecs hand over floats.
+template <typename T> struct WrapAcc { using type = long long; };
+template <> struct WrapAcc<unsigned char> { using type = unsigned long long; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_me_wrap(const T *__restrict__ ref, const T *__restrict__ cur, int64_t n, int H, int W,
+                                                 int64_t ref_fs, int64_t cur_fs, int sr, int64_t *__restrict__ mv) {
+    using A = typename WrapAcc<T>::type;
+    const int lane = threadIdx.x & 31;
+    const int Hp = H / 8, Wp = W / 8, span = 2 * sr + 1;
+    const int64_t nblocks = n * Hp * (int64_t)Wp;
+    for (int64_t blk = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); blk < nblocks; blk += (int64_t)gridDim.x * 8) {
+        const int bx = (int)(blk % Wp), by = (int)((blk / Wp) % Hp);
+        const int64_t f = blk / ((int64_t)Wp * Hp);
+        const T *c = cur + f * cur_fs + (int64_t)(8 * by) * W + 8 * bx, *r0 = ref + f * ref_fs;
+        bool have = false;
+        A best = 0;
+        int bidx = sr * span + sr;                                              // default (0, 0): motion.py:31-33
+        for (int cand = lane; cand < span * span; cand += 32) {
+            const int dyi = cand / span, dxi = cand - dyi * span;
+            const int yy = 8 * by + dyi - sr, xx = 8 * bx + dxi - sr;
+            if (yy < 0 || yy + 8 > H || xx < 0 || xx + 8 > W) continue;        // motion.py:41-43
+            const T *r = r0 + (int64_t)yy * W + xx;
+            A ssd = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const T d = (T)((unsigned)c[i * W + j] - (unsigned)r[i * W + j]);   // wraps like numpy's T - T
+                    ssd += (A)(T)((unsigned)d * (unsigned)d);                           // T ** 2 wraps, the sum does not
+                }
+            if (!have || ssd < best) { best = ssd; bidx = cand; have = true; }  // candidates ascend per lane
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const A os = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
+            const bool oh = __shfl_xor_sync(0xffffffffu, (int)have, off) != 0;
+            if (oh && (!have || os < best || (os == best && oi < bidx))) { best = os; bidx = oi; have = true; }
+        }
+        if (lane == 0) mv[blk] = bidx;
+    }
+}
+
+cudaError_t launch_me_wrap(int device, cudaStream_t st, const void *ref, const void *cur, int dtype, int64_t n, int64_t H,
+                           int64_t W, int64_t ref_fs, int64_t cur_fs, int sr, int64_t *mv) {
+    const int64_t nblocks = n * (H / 8) * (W / 8);
+    if (nblocks == 0) return cudaSuccess;
+    int64_t grid = (nblocks + 7) / 8;
+    const int64_t cap = (int64_t)sm_count(device) * 16;
+    if (grid > cap) grid = cap;
+    switch (dtype) {
+        case IVC_U8: k_me_wrap<unsigned char><<<(unsigned)grid, 256, 0, st>>>((const unsigned char *)ref, (const unsigned char *)cur, n, (int)H, (int)W, ref_fs, cur_fs, sr, mv); break;
+        case IVC_I16: k_me_wrap<short><<<(unsigned)grid, 256, 0, st>>>((const short *)ref, (const short *)cur, n, (int)H, (int)W, ref_fs, cur_fs, sr, mv); break;
+        case IVC_I32: k_me_wrap<int><<<(unsigned)grid, 256, 0, st>>>((const int *)ref, (const int *)cur, n, (int)H, (int)W, ref_fs, cur_fs, sr, mv); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 // ---- K4: motion compensation (motion.py:60-97) --------------------------------------------------
 struct McArgs {
     const void *ref;
@@ -547,11 +621,6 @@ __global__ void __launch_bounds__(256) k_mc(const McArgs a) {
 }
 
 // ---- launchers ----------------------------------------------------------------------------------
-static int sm_count(int device) {
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    return sms;
-}
 
 // choose the CTA tile (at most 64 blocks) and the shared-memory layout
 static size_t me_geometry(MeArgs &a, int64_t n_frames, int64_t H, int64_t W, int sr, int elem, int pitch_quantum,

@@ -21,9 +21,11 @@ class MotionCompensator:
     (motion.py:28-57).  SSDs are accumulated in numpy's summation order with
     individually rounded operations, so vectors are bit-exact for float32 /
     float64 frames; integer-valued [0,255] frames take an exact packed-integer
-    kernel (``me_mode='auto'``, decided on the device).  Integer-dtype inputs
-    are upcast to float64 (the reference lets uint8/int16 wrap -- documented
-    divergence).  ``reconstruct_with_motion_vector(ref[H,W,C], mv) -> [H,W,C]``
+    kernel (``me_mode='auto'``, decided on the device).  uint8 / int16 / int32
+    frames (both of one dtype) get numpy's own wrap-around arithmetic
+    (``(block - ref_block) ** 2`` evaluated in that dtype, summed in 64 bits:
+    SURVEY.md A10), so the vectors equal the reference's there too; other
+    integer dtypes and mixed integer pairs are upcast to float64.  ``reconstruct_with_motion_vector(ref[H,W,C], mv) -> [H,W,C]``
     copies blocks, leaving out-of-frame sources zero (motion.py:76-95).
     """
 
@@ -44,6 +46,15 @@ class MotionCompensator:
         if cur.ndim != 2 or cur.shape[0] < H or cur.shape[1] < W:
             raise ValueError(f"operands could not be broadcast together: image {tuple(cur.shape)} vs ref_image {(H, W)}")
         cur = cur[:H, :W]
+        wrap = {torch.uint8: _lib.U8, torch.int16: _lib.I16, torch.int32: _lib.I32}
+        if ref.dtype == cur.dtype and ref.dtype in wrap:          # numpy's integer-dtype arithmetic, replayed literally
+            ref, cur = ref.contiguous(), cur.contiguous()
+            mv = torch.empty((H // 8, W // 8, 1), dtype=torch.int64, device=ref.device)
+            st = _lib.lib.ivc_me_full_search_intdtype(dev_index(ref), stream_ptr(ref.device), ref.data_ptr(), cur.data_ptr(),
+                                                      wrap[ref.dtype], 1, H, W, H * W, H * W, int(self.search_range),
+                                                      mv.data_ptr())
+            _lib.check(st, "ivc_me_full_search_intdtype")
+            return to_host(mv, was_np)
         both_f32 = ref.dtype == torch.float32 and cur.dtype == torch.float32
         dt = torch.float32 if both_f32 else torch.float64
         ref = ref.to(dt).contiguous()

@@ -215,6 +215,23 @@ def test_motion_near_ties_float():
     assert np.array_equal(mv, O.me_full_search(ref, cur, 8))
 
 
+@pytest.mark.parametrize("dtype", [np.uint8, np.int16, np.int32])
+def test_motion_integer_dtype_frames_wrap_like_numpy(dtype):
+    """on integer-dtype frames numpy evaluates (block - ref_block)**2 in that dtype (uint8 wraps mod 256,
+    255**2 == -511 in int16) and sums in 64 bits; the vectors must equal the reference loop's on such inputs."""
+    rng = np.random.default_rng(77)
+    for sr in (2, 4):
+        hi = 256 if dtype != np.int32 else 70000
+        ref = rng.integers(0, hi, size=(24, 40)).astype(dtype)
+        cur = np.roll(ref, (1, -2), axis=(0, 1))
+        cur[8:16, 8:24] = rng.integers(0, hi, size=(8, 16)).astype(dtype)
+        want = O.me_full_search_loops(ref, cur, sr)
+        got = ivc.MotionCompensator(search_range=sr).compute_motion_vector(ref, cur)
+        assert got.dtype == want.dtype and np.array_equal(got, want)
+        if dtype == np.uint8:                                   # and it differs from the float result: the wrap matters
+            assert not np.array_equal(want, O.me_full_search(ref.astype(np.float64), cur.astype(np.float64), sr))
+
+
 def test_motion_ragged_frame_raises():
     with pytest.raises(IndexError):
         ivc.MotionCompensator().compute_motion_vector(np.zeros((20, 24)), np.zeros((20, 24)))
