@@ -16,6 +16,7 @@ extension has not been built, and calling it fails if no CUDA device is visible.
 from . import _lib  # noqa: F401  (loads libivcb200.so or raises)
 from .codec import IntraBlockCoder, PFrameBlockCoder
 from .entropy import ZeroRunCoder, stats_marg, symbol_histogram, symbol_minmax
+from .image import IntraCodec
 from .install import inject, install
 from .quantization import PatchQuant
 from .signal import DiscreteCosineTransform, rgb2ycbcr, ycbcr2rgb
@@ -25,6 +26,6 @@ from .video import ClosedLoopLumaCoder, MotionCompensator
 
 __version__ = "0.1.0"
 __all__ = ["DiscreteCosineTransform", "PatchQuant", "ZigZag", "Patcher", "MotionCompensator",
-           "IntraBlockCoder", "PFrameBlockCoder", "ClosedLoopLumaCoder", "ZeroRunCoder", "calc_mse", "calc_psnr",
+           "IntraBlockCoder", "PFrameBlockCoder", "IntraCodec", "ClosedLoopLumaCoder", "ZeroRunCoder", "calc_mse", "calc_psnr",
            "frame_sse", "frame_sse_rgb8_vs_ycbcr", "rgb2ycbcr", "ycbcr2rgb", "StreamedCoder", "stats_marg", "symbol_minmax", "symbol_histogram",
            "install", "inject"]

@@ -74,6 +74,25 @@ def main():
         # a range that cuts the data: values below lo / above the last edge are dropped, the last bin is closed
         pmf_cut = stats_marg(sym, pixel_range=np.arange(-3, 9))
         ok["stats_marg_cut"] = np.array_equal(O.stats_marg(sym, np.arange(-3, 9)), pmf_cut)
+        # IntraCodec-level calls: colour image -> symbols -> image; luma plane (2-D) both ways; ragged size (edge padding)
+        rec_rgb = codec.symbols2image(sym, img.shape)
+        luma = O.smooth_noise_luma(11, 48, 64)
+        sym_luma = np.asarray(codec.image2symbols(luma, is_source_rgb=False), dtype=np.int32)
+        rec_luma = codec.symbols2image(sym_luma, luma.shape)                # (H, W, 3): SURVEY A13
+        ragged = O.smooth_noise_rgb(12, 45, 61)
+        sym_ragged = np.asarray(codec.image2symbols(ragged, is_source_rgb=True), dtype=np.int32)
+        codec.train_huffman_from_image = None                                # (needs constriction; statistics are pinned below)
+        ok["intracodec_symbols_rgb"] = np.array_equal(
+            O.zerorun_encode(O.intra_forward(O.rgb2ycbcr(img), O.quant_table(0.4))), sym)
+        ok["intracodec_image_rgb"] = np.array_equal(
+            O.ycbcr2rgb(O.intra_inverse(O.zerorun_decode(sym, (6, 8, 3)), O.quant_table(0.4))), rec_rgb)
+        ok["intracodec_symbols_luma"] = np.array_equal(
+            O.zerorun_encode(O.intra_forward(luma[..., None], O.quant_table(0.4))), sym_luma)
+        ok["intracodec_image_luma"] = np.array_equal(
+            O.intra_inverse(O.zerorun_decode(sym_luma, (6, 8, 1)), O.quant_table(0.4)), rec_luma)
+        padded = np.pad(O.rgb2ycbcr(ragged), ((0, 3), (0, 3), (0, 0)), mode="edge")
+        ok["intracodec_symbols_ragged"] = np.array_equal(
+            O.zerorun_encode(O.intra_forward(padded, O.quant_table(0.4))), sym_ragged)
         img8 = O.smooth_noise_luma(10, 40, 56).astype(np.uint8)
         pmf8 = stats_marg(img8, pixel_range=np.arange(256))
         ok["stats_marg_u8"] = np.array_equal(O.stats_marg(img8, np.arange(256)), pmf8)
@@ -84,7 +103,8 @@ def main():
         raise SystemExit("entropy oracle is NOT pinned")
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "g9_entropy.npz"), sym=sym, dec_full=dec_full,
                         dec_trunc=dec_trunc, blocks=blocks, sym2=sym2, lo=lo, hi=hi, pmf=pmf, pmf_cut=pmf_cut,
-                        img8=img8, pmf8=pmf8)
+                        img8=img8, pmf8=pmf8, img=img, rec_rgb=rec_rgb, luma=luma, sym_luma=sym_luma, rec_luma=rec_luma,
+                        ragged=ragged, sym_ragged=sym_ragged)
 
 
 if __name__ == "__main__":

@@ -446,6 +446,30 @@ def test_zerorun_decode_on_device(g9):
     assert torch.equal(luma_only.reshape(-1, 64), big.reshape(-1, 64)[:135 * 240])
 
 
+def test_intracodec_symbol_level_calls(g9):
+    """IntraCodec.image2symbols / symbols2image / the statistics half of train_huffman_from_image against outputs of
+    the REAL reference codec (oracle/gen_golden_entropy.py): colour image, luma plane (2-D), ragged size."""
+    codec = ivc.IntraCodec(quantization_scale=0.4)
+    sym = codec.image2symbols(g9["img"], is_source_rgb=True)                       # uint8, 48x64: fused colour front end
+    assert sym.dtype == np.int32 and np.array_equal(sym, g9["sym"])
+    assert np.array_equal(codec.image2symbols(g9["img"].astype(np.float64), True), g9["sym"])   # two-kernel route
+    assert np.array_equal(codec.symbols2image(sym, g9["img"].shape), g9["rec_rgb"])
+    assert np.array_equal(codec.symbols2image(list(sym), g9["img"].shape), g9["rec_rgb"])
+    sl = codec.image2symbols(g9["luma"], is_source_rgb=False)
+    assert np.array_equal(sl, g9["sym_luma"])
+    assert np.array_equal(codec.symbols2image(sl, g9["luma"].shape), g9["rec_luma"])           # (H, W, 3): SURVEY A13
+    assert np.array_equal(codec.image2symbols(g9["ragged"], True), g9["sym_ragged"])           # edge padding to 48x64
+    assert codec.bounds is None
+    codec.train_huffman_from_image(g9["img"], is_source_rgb=True)
+    assert codec.bounds == (int(g9["lo"]), int(g9["hi"]))
+    want = g9["pmf"] + 1e-9
+    assert np.array_equal(codec.pmf, want / want.sum())
+    dev = codec.image2symbols(torch.from_numpy(g9["img"]).cuda())
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), g9["sym"])
+    with pytest.raises(NotImplementedError):
+        codec.intra_encode(g9["img"])
+
+
 def test_symbol_statistics_match_reference(g9):
     """N3: stats_marg over the bins IntraCodec.train_huffman_from_image picks (entropy.py:6-29,
     intracodec.py:160-166), bit-identical pmf; min/max on the device."""
