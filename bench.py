@@ -413,7 +413,7 @@ def run_b200(args):
                                       "value": round(world * Fa * H * W / (serial_ms * 1e-3) / 1e6, 1)},
                     "api": "StreamedCoder.run (upload / 2 compute / download streams, 4-frame chunks, one CUDA graph per slot): pinned host uint8 RGB + uint8 luma in; "
                            "IntraBlockCoder.forward_rgb/inverse, PFrameBlockCoder.estimate/forward/inverse, ZeroRunCoder.encode, "
-                           "frame_sse; zero-run symbols + MVs + SSE back to host"},
+                           "frame_sse; zero-run symbols (int16 transfer format: |symbol| <= 2040/min(table) for 8-bit input) + MVs + SSE back to host"},
             "e2e_raw": None if args.no_e2e else {"value": round(raw_val, 1), "unit": UNIT, "h2d_bytes_per_step": raw_h2d, "d2h_bytes_per_step": raw_d2h,
                         "frames_per_step": Fa, "ms_per_step": round(raw_ms, 3),
                         "api": "pinned host float64 YCbCr + luma in, raw int32 scan indices + MVs + SSE out (PCIe-bound)"},

@@ -209,6 +209,12 @@ int ivc_zerorun_count_masks(int device, void *stream, const int32_t *zz, int64_t
 int ivc_zerorun_write_masks(int device, void *stream, const int32_t *zz, int64_t nblocks, int32_t end_of_block,
                             const int64_t *offsets, const uint64_t *masks, int32_t *symbols_out);
 
+/* The write pass with 16-bit symbols: a lossless TRANSFER format for callers that know every symbol fits (e.g.
+ * |coefficient| <= 2040 / min(table) for 8-bit images; end_of_block must fit too).  Values are truncated to int16
+ * without a check -- the reference's dtype is int32 (ivc_zerorun_write). */
+int ivc_zerorun_write_masks_i16(int device, void *stream, const int32_t *zz, int64_t nblocks, int32_t end_of_block,
+                                const int64_t *offsets, const uint64_t *masks, int16_t *symbols_out);
+
 /* The scan between the two passes, for callers that do not want to bring their own: offsets_out[b] = sum of
  * counts[0..b) (int64), in one kernel (decoupled look-back over 4096-count tiles).  The grand total is written
  * to total_dev_out (device int64, may be NULL) and, by the kernel itself, to total_mapped_out (MAPPED pinned host

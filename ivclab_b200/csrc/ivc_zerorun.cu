@@ -68,10 +68,11 @@ __global__ void __launch_bounds__(kZrWarps * 32) k_zr_count(const int32_t *__res
 
 // masks == nullptr: the masks are recomputed from the blocks (every block is read whole).  With masks, a lane
 // loads its coefficient only if it is non-zero, so only the 32-byte sectors that hold symbols are fetched.
-template <bool MASKS>
+// OutT = int32_t (the reference's dtype) or int16_t (a lossless transfer format when every symbol is known to fit).
+template <bool MASKS, typename OutT>
 __global__ void __launch_bounds__(kZrWarps * 32) k_zr_write(const int32_t *__restrict__ zz, int64_t nblocks, int32_t eob,
                                                             const int64_t *__restrict__ offsets,
-                                                            const unsigned long long *__restrict__ masks, int32_t *__restrict__ out) {
+                                                            const unsigned long long *__restrict__ masks, OutT *__restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * kZrWarps + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * kZrWarps;
     const unsigned long long low0 = (1ull << lane) - 1ull, low1 = (1ull << (lane + 32)) - 1ull;
@@ -102,19 +103,19 @@ __global__ void __launch_bounds__(kZrWarps * 32) k_zr_write(const int32_t *__res
                 const unsigned long long m = MASKS ? mm[j]
                                                    : (unsigned long long)__ballot_sync(0xffffffffu, a[j] != 0) |
                                                          ((unsigned long long)__ballot_sync(0xffffffffu, b[j] != 0) << 32);
-                int32_t *o = out + off;
+                OutT *o = out + off;
                 if (m == 0) {
-                    if (lane == 0) o[0] = eob;
+                    if (lane == 0) o[0] = (OutT)eob;
                     continue;
                 }
                 const unsigned long long S = zr_run_starts(m);
                 const int p0 = __popcll(m & low0) + 2 * __popcll(S & low0);
                 const int p1 = __popcll(m & low1) + 2 * __popcll(S & low1);
-                if ((m >> lane) & 1ull) o[p0] = a[j];
-                else if ((S >> lane) & 1ull) { o[p0] = 0; o[p0 + 1] = __ffsll((long long)(m >> lane)) - 1; }
-                if ((m >> (lane + 32)) & 1ull) o[p1] = b[j];
-                else if ((S >> (lane + 32)) & 1ull) { o[p1] = 0; o[p1 + 1] = __ffsll((long long)(m >> (lane + 32))) - 1; }
-                if (lane == 0) o[__popcll(m) + 2 * __popcll(S)] = eob;
+                if ((m >> lane) & 1ull) o[p0] = (OutT)a[j];
+                else if ((S >> lane) & 1ull) { o[p0] = 0; o[p0 + 1] = (OutT)(__ffsll((long long)(m >> lane)) - 1); }
+                if ((m >> (lane + 32)) & 1ull) o[p1] = (OutT)b[j];
+                else if ((S >> (lane + 32)) & 1ull) { o[p1] = 0; o[p1 + 1] = (OutT)(__ffsll((long long)(m >> (lane + 32))) - 1); }
+                if (lane == 0) o[__popcll(m) + 2 * __popcll(S)] = (OutT)eob;
             }
         }
     }
@@ -315,11 +316,18 @@ cudaError_t launch_zr_count(int device, cudaStream_t st, const int32_t *zz, int6
 }
 
 cudaError_t launch_zr_write(int device, cudaStream_t st, const int32_t *zz, int64_t nblocks, int32_t eob,
-                            const int64_t *offsets, const uint64_t *masks, int32_t *out) {
+                            const int64_t *offsets, const uint64_t *masks, void *out, int out_elem_size) {
     if (nblocks == 0) return cudaSuccess;
     const int grid = zr_grid(device, nblocks, 32 * kZrWarps);
-    if (masks) k_zr_write<true><<<grid, kZrWarps * 32, 0, st>>>(zz, nblocks, eob, offsets, (const unsigned long long *)masks, out);
-    else k_zr_write<false><<<grid, kZrWarps * 32, 0, st>>>(zz, nblocks, eob, offsets, nullptr, out);
+    const unsigned long long *mk = (const unsigned long long *)masks;
+    if (out_elem_size == 2) {
+        if (!masks) return cudaErrorInvalidValue;
+        k_zr_write<true, int16_t><<<grid, kZrWarps * 32, 0, st>>>(zz, nblocks, eob, offsets, mk, (int16_t *)out);
+    } else if (masks) {
+        k_zr_write<true, int32_t><<<grid, kZrWarps * 32, 0, st>>>(zz, nblocks, eob, offsets, mk, (int32_t *)out);
+    } else {
+        k_zr_write<false, int32_t><<<grid, kZrWarps * 32, 0, st>>>(zz, nblocks, eob, offsets, nullptr, (int32_t *)out);
+    }
     return cudaGetLastError();
 }
 

@@ -62,19 +62,23 @@ class ZeroRunCoder:
             p.event.record(p.stream)
         return p
 
-    def encode_finish(self, p: _PendingEncode) -> torch.Tensor:
-        """Second half: waits for the stream length (one event), then writes the symbols on the current stream."""
+    def encode_finish(self, p: _PendingEncode, dtype=torch.int32) -> torch.Tensor:
+        """Second half: waits for the stream length (one event), then writes the symbols on the current stream.
+        ``dtype=torch.int16`` writes a lossless 16-bit transfer format; the CALLER guarantees that every coefficient
+        and the EOB marker fit (values are not checked) -- the reference's dtype, and the default, is int32."""
         if p.event is not None:
             p.event.synchronize()
         total = int(p.total_host[0])
         t = p.blocks
-        out = torch.empty(total, dtype=torch.int32, device=t.device)
+        if dtype not in (torch.int32, torch.int16):
+            raise ValueError("symbol dtype must be torch.int32 or torch.int16")
+        out = torch.empty(total, dtype=dtype, device=t.device)
         cur = torch.cuda.current_stream(t.device)
         if cur != p.stream and p.event is not None:
             cur.wait_event(p.event)
-        _lib.check(_lib.lib.ivc_zerorun_write_masks(dev_index(t), stream_ptr(t.device), t.data_ptr(), p.nblk, int(self.EOB),
-                                                    p.offsets.data_ptr(), p.masks.data_ptr(), out.data_ptr()),
-                   "ivc_zerorun_write_masks")
+        fn = _lib.lib.ivc_zerorun_write_masks if dtype == torch.int32 else _lib.lib.ivc_zerorun_write_masks_i16
+        _lib.check(fn(dev_index(t), stream_ptr(t.device), t.data_ptr(), p.nblk, int(self.EOB), p.offsets.data_ptr(),
+                      p.masks.data_ptr(), out.data_ptr()), "ivc_zerorun_write_masks")
         return out
 
     def encode(self, flat_patch_img):

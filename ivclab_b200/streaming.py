@@ -35,11 +35,22 @@ class _Slot:
 
 class StreamedCoder:
     def __init__(self, quantization_scale=1.0, search_range=4, me_mode="auto", chunk_frames=2, device=None, use_graph=True,
-                 slots=3, compute_streams=2):
+                 slots=3, compute_streams=2, symbol_dtype="auto"):
         self.intra = IntraBlockCoder(quantization_scale)
         self.pframe = PFrameBlockCoder(quantization_scale, search_range, me_mode)
         self.zr = ZeroRunCoder()
         self.chunk = int(chunk_frames)
+        # Symbol streams are the bulk of the download.  The inputs are 8-bit images, so every DCT coefficient is
+        # bounded by 8 * 255 and every quantised value by 2040 / min(table): when that (and the EOB marker) fits 16
+        # bits, "auto" sends int16 symbols -- a lossless transfer format, half the bytes; torch.int32 forces the
+        # reference's dtype.
+        tab = np.asarray(self.intra.quant.get_quantization_table(), dtype=np.float64)
+        fits16 = bool(np.all(tab > 0)) and 2040.0 / float(tab.min()) < 32000 and abs(int(self.zr.EOB)) < 32768
+        if symbol_dtype == "auto":
+            symbol_dtype = torch.int16 if fits16 else torch.int32
+        if symbol_dtype not in (torch.int16, torch.int32) or (symbol_dtype == torch.int16 and not fits16):
+            raise ValueError("symbol_dtype must be 'auto', torch.int32, or torch.int16 with a table that keeps symbols in 16 bits")
+        self.symbol_dtype = symbol_dtype
         self.use_graph = bool(use_graph)
         self.nslots = max(2, int(slots))          # input buffers in rotation: uploads run ahead of the coder by nslots-1 chunks
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -52,13 +63,13 @@ class StreamedCoder:
 
     # ---- buffers -------------------------------------------------------------------------------
     def _host_buffers(self, F, H, W):
-        key = (F, H, W)
+        key = (F, H, W, self.symbol_dtype)
         if self._host is None or self._host[0] != key:
             nb = (H // 8) * (W // 8)
             pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
             self._host = (key, {
                 # symbol streams: room for 24 symbols per block to start with (a block emits 1..97); grown on demand
-                "sym_intra": pin(F * nb * 3 * 24, torch.int32), "sym_inter": pin(F * nb * 3 * 24, torch.int32),
+                "sym_intra": pin(F * nb * 3 * 24, self.symbol_dtype), "sym_inter": pin(F * nb * 3 * 24, self.symbol_dtype),
                 "mv": pin((F, H // 8, W // 8, 1), torch.int64), "sse": pin((2, F), torch.float64)})
         return self._host[1]
 
@@ -190,15 +201,15 @@ class StreamedCoder:
             sc = self._s_cmp if k % 2 == 0 else self._s_cmp2
             with torch.cuda.stream(sc):
                 tr = self._mark("symbols", k, sc)
-                sym_i = self.zr.encode_finish(pend_i)
-                sym_p = self.zr.encode_finish(pend_p)
+                sym_i = self.zr.encode_finish(pend_i, self.symbol_dtype)
+                sym_p = self.zr.encode_finish(pend_p, self.symbol_dtype)
                 mv, sse_i, sse_p = mv.clone(), sse_i.clone(), sse_p.clone()     # frees the slot's (static) result buffers
                 tr()
                 ev_fin[k].record(sc)
             for name, o, sym in (("sym_intra", off[0], sym_i), ("sym_inter", off[1], sym_p)):
                 if o + sym.numel() > hb[name].numel():             # rare: denser streams than provisioned
                     self._s_out.synchronize()                      # earlier downloads into the old buffer are complete
-                    grown = torch.empty(max(2 * hb[name].numel(), o + sym.numel()), dtype=torch.int32).pin_memory()
+                    grown = torch.empty(max(2 * hb[name].numel(), o + sym.numel()), dtype=self.symbol_dtype).pin_memory()
                     grown[:o].copy_(hb[name][:o])
                     hb[name] = grown
             with torch.cuda.stream(self._s_out):
@@ -235,4 +246,4 @@ class StreamedCoder:
         return {"sym_intra": hb["sym_intra"][:off[0]], "sym_inter": hb["sym_inter"][:off[1]], "len_intra": lens_i,
                 "len_inter": lens_p, "mv": hb["mv"], "sse": hb["sse"],
                 "h2d_bytes": rgb.numel() + cur.numel() + ref.numel(),            # ref = one frame in sequence mode
-                "d2h_bytes": (off[0] + off[1]) * 4 + hb["mv"].numel() * 8 + hb["sse"].numel() * 8}
+                "d2h_bytes": (off[0] + off[1]) * hb["sym_intra"].element_size() + hb["mv"].numel() * 8 + hb["sse"].numel() * 8}

@@ -576,7 +576,15 @@ def test_streamed_coder_matches_direct_calls():
     rgb = np.stack([O.smooth_noise_rgb(50 + i, H, W) for i in range(F)])
     seq = O.moving_sequence(60, F + 1, H, W).astype(np.uint8)
     cur, ref = seq[1:], seq[:-1]
-    out = ivc.StreamedCoder(0.4, 4, chunk_frames=2).run(rgb, cur, ref)
+    sc = ivc.StreamedCoder(0.4, 4, chunk_frames=2)
+    out = sc.run(rgb, cur, ref)
+    assert sc.symbol_dtype == torch.int16 and out["sym_intra"].dtype == torch.int16       # lossless 16-bit transfer format
+    out32 = ivc.StreamedCoder(0.4, 4, chunk_frames=2, symbol_dtype=torch.int32).run(rgb, cur, ref)
+    assert out32["sym_intra"].dtype == torch.int32 and torch.equal(out32["sym_intra"], out["sym_intra"].to(torch.int32))
+    assert torch.equal(out32["sym_inter"], out["sym_inter"].to(torch.int32)) and out32["d2h_bytes"] > out["d2h_bytes"]
+    with pytest.raises(ValueError):
+        ivc.StreamedCoder(0.001, 4, symbol_dtype=torch.int16)                              # 2040 / 0.01 does not fit
+    assert ivc.StreamedCoder(0.001, 4).symbol_dtype == torch.int32
     intra, pc, zr = ivc.IntraBlockCoder(0.4), ivc.PFrameBlockCoder(0.4, 4), ivc.ZeroRunCoder()
     tab = intra.quant.get_quantization_table()
     sym_i, sym_p = [], []
