@@ -203,17 +203,19 @@ int ivc_zerorun_count(int device, void *stream, const int32_t *zz, int64_t nbloc
 int ivc_zerorun_write(int device, void *stream, const int32_t *zz, int64_t nblocks, int32_t end_of_block,
                       const int64_t *offsets, int32_t *symbols_out);
 /* The same two passes with the per-block 64-bit non-zero masks handed from the first to the second
- * (masks: nblocks uint64): the write pass then fetches only the parts of each block that hold symbols. */
+ * (masks: nblocks uint64): the write pass then fetches only the parts of each block that hold symbols.
+ * total_symbols: the stream length if the caller knows it (it sized symbols_out with it), else -1 -- sparse
+ * streams (< 16 symbols per block on average) take a one-thread-per-block kernel. */
 int ivc_zerorun_count_masks(int device, void *stream, const int32_t *zz, int64_t nblocks, int32_t *counts_out,
                             uint64_t *masks_out);
 int ivc_zerorun_write_masks(int device, void *stream, const int32_t *zz, int64_t nblocks, int32_t end_of_block,
-                            const int64_t *offsets, const uint64_t *masks, int32_t *symbols_out);
+                            const int64_t *offsets, const uint64_t *masks, int32_t *symbols_out, int64_t total_symbols);
 
 /* The write pass with 16-bit symbols: a lossless TRANSFER format for callers that know every symbol fits (e.g.
  * |coefficient| <= 2040 / min(table) for 8-bit images; end_of_block must fit too).  Values are truncated to int16
  * without a check -- the reference's dtype is int32 (ivc_zerorun_write). */
 int ivc_zerorun_write_masks_i16(int device, void *stream, const int32_t *zz, int64_t nblocks, int32_t end_of_block,
-                                const int64_t *offsets, const uint64_t *masks, int16_t *symbols_out);
+                                const int64_t *offsets, const uint64_t *masks, int16_t *symbols_out, int64_t total_symbols);
 
 /* The scan between the two passes, for callers that do not want to bring their own: offsets_out[b] = sum of
  * counts[0..b) (int64), in one kernel (decoupled look-back over 4096-count tiles).  The grand total is written

@@ -48,8 +48,8 @@ SIGNATURES = {
     "ivc_zerorun_count": (_i, [_i, _p, _p, _i64, _p]),
     "ivc_zerorun_write": (_i, [_i, _p, _p, _i64, C.c_int32, _p, _p]),
     "ivc_zerorun_count_masks": (_i, [_i, _p, _p, _i64, _p, _p]),
-    "ivc_zerorun_write_masks": (_i, [_i, _p, _p, _i64, C.c_int32, _p, _p, _p]),
-    "ivc_zerorun_write_masks_i16": (_i, [_i, _p, _p, _i64, C.c_int32, _p, _p, _p]),
+    "ivc_zerorun_write_masks": (_i, [_i, _p, _p, _i64, C.c_int32, _p, _p, _p, _i64]),
+    "ivc_zerorun_write_masks_i16": (_i, [_i, _p, _p, _i64, C.c_int32, _p, _p, _p, _i64]),
     "ivc_zerorun_offsets_workspace_bytes": (_i64, [_i64]),
     "ivc_zerorun_offsets": (_i, [_i, _p, _p, _i64, _p, _p, _i64, _p, _p]),
     "ivc_post_words_to_host": (_i, [_i, _p, _p, _p, _i]),

@@ -317,13 +317,13 @@ int ivc_zerorun_count_masks(int device, void *stream, const int32_t *zz, int64_t
 }
 
 int ivc_zerorun_write_masks(int device, void *stream, const int32_t *zz, int64_t nblocks, int32_t end_of_block,
-                            const int64_t *offsets, const uint64_t *masks, int32_t *symbols_out) {
+                            const int64_t *offsets, const uint64_t *masks, int32_t *symbols_out, int64_t total_symbols) {
     if (nblocks < 0) return IVC_ERR_ARG;
     if (nblocks == 0) return IVC_OK;
     if (!zz || !offsets || !masks || !symbols_out || !aligned16(zz)) return IVC_ERR_ARG;
     int rc = enter(device);
     if (rc) return rc;
-    cudaError_t e = ivc::launch_zr_write(device, (cudaStream_t)stream, zz, nblocks, end_of_block, offsets, masks, symbols_out, 4);
+    cudaError_t e = ivc::launch_zr_write(device, (cudaStream_t)stream, zz, nblocks, end_of_block, offsets, masks, symbols_out, 4, total_symbols);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
 
@@ -334,18 +334,18 @@ int ivc_zerorun_write(int device, void *stream, const int32_t *zz, int64_t nbloc
     if (!zz || !offsets || !symbols_out || !aligned16(zz)) return IVC_ERR_ARG;
     int rc = enter(device);
     if (rc) return rc;
-    cudaError_t e = ivc::launch_zr_write(device, (cudaStream_t)stream, zz, nblocks, end_of_block, offsets, nullptr, symbols_out, 4);
+    cudaError_t e = ivc::launch_zr_write(device, (cudaStream_t)stream, zz, nblocks, end_of_block, offsets, nullptr, symbols_out, 4, -1);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
 
 int ivc_zerorun_write_masks_i16(int device, void *stream, const int32_t *zz, int64_t nblocks, int32_t end_of_block,
-                                const int64_t *offsets, const uint64_t *masks, int16_t *symbols_out) {
+                                const int64_t *offsets, const uint64_t *masks, int16_t *symbols_out, int64_t total_symbols) {
     if (nblocks < 0 || end_of_block > 32767 || end_of_block < -32768) return IVC_ERR_ARG;
     if (nblocks == 0) return IVC_OK;
     if (!zz || !offsets || !masks || !symbols_out || !aligned16(zz)) return IVC_ERR_ARG;
     int rc = enter(device);
     if (rc) return rc;
-    cudaError_t e = ivc::launch_zr_write(device, (cudaStream_t)stream, zz, nblocks, end_of_block, offsets, masks, symbols_out, 2);
+    cudaError_t e = ivc::launch_zr_write(device, (cudaStream_t)stream, zz, nblocks, end_of_block, offsets, masks, symbols_out, 2, total_symbols);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
 

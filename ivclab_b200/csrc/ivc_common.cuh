@@ -45,7 +45,8 @@ cudaError_t launch_sse(int device, cudaStream_t st, const void *a, int a_dtype, 
 cudaError_t launch_zr_count(int device, cudaStream_t st, const int32_t *zz, int64_t nblocks, int32_t *counts,
                             uint64_t *masks);
 cudaError_t launch_zr_write(int device, cudaStream_t st, const int32_t *zz, int64_t nblocks, int32_t eob,
-                            const int64_t *offsets, const uint64_t *masks, void *out, int out_elem_size);
+                            const int64_t *offsets, const uint64_t *masks, void *out, int out_elem_size,
+                            int64_t total_symbols);
 
 cudaError_t launch_zrd_mark(int device, cudaStream_t st, const int32_t *sym, int64_t n, int32_t eob, int32_t *is_eob);
 cudaError_t launch_zrd_ends(int device, cudaStream_t st, const int32_t *is_eob, const int64_t *rank, int64_t n,

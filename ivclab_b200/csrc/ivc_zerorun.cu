@@ -121,6 +121,33 @@ __global__ void __launch_bounds__(kZrWarps * 32) k_zr_write(const int32_t *__res
     }
 }
 
+// Sparse variant of the write pass: ONE THREAD per block walks the set bits of the block's mask.  Typical quantised
+// blocks hold a handful of non-zero coefficients (chroma blocks often none), so a thread issues a few scattered
+// 4-byte loads and stores where the cooperative kernel spends ~60 warp instructions per block regardless; the
+// launcher picks this kernel when the stream averages fewer than kZrSparseLimit symbols per block.
+constexpr int kZrSparseLimit = 16;
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) k_zr_write_sparse(const int32_t *__restrict__ zz, int64_t nblocks, int32_t eob,
+                                                         const int64_t *__restrict__ offsets,
+                                                         const unsigned long long *__restrict__ masks, OutT *__restrict__ out) {
+    for (int64_t blk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; blk < nblocks; blk += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long m = masks[blk];
+        OutT *o = out + offsets[blk];
+        const int32_t *z = zz + blk * 64;
+        int p = 0;
+        while (m) {
+            const int pos = __ffsll((long long)m) - 1;
+            const int32_t v = __ldg(z + pos);
+            if (pos > p) { o[0] = 0; o[1] = (OutT)(pos - p); o += 2; }            // the zeros since the last value
+            *o++ = (OutT)v;
+            p = pos + 1;
+            m &= m - 1;
+        }
+        *o = (OutT)eob;
+    }
+}
+
 // ---- decode --------------------------------------------------------------------------------------
 // is_eob[i] = 1 iff symbol i is an EOB in a symbol slot (i.e. not the run length after a zero marker)
 __global__ void __launch_bounds__(256) k_zrd_mark(const int32_t *__restrict__ sym, int64_t n, int32_t eob,
@@ -316,10 +343,17 @@ cudaError_t launch_zr_count(int device, cudaStream_t st, const int32_t *zz, int6
 }
 
 cudaError_t launch_zr_write(int device, cudaStream_t st, const int32_t *zz, int64_t nblocks, int32_t eob,
-                            const int64_t *offsets, const uint64_t *masks, void *out, int out_elem_size) {
+                            const int64_t *offsets, const uint64_t *masks, void *out, int out_elem_size,
+                            int64_t total_symbols) {
     if (nblocks == 0) return cudaSuccess;
     const int grid = zr_grid(device, nblocks, 32 * kZrWarps);
     const unsigned long long *mk = (const unsigned long long *)masks;
+    if (masks && total_symbols >= 0 && total_symbols < (int64_t)kZrSparseLimit * nblocks) {      // sparse stream
+        const int g2 = zr_grid(device, nblocks, 256);
+        if (out_elem_size == 2) k_zr_write_sparse<int16_t><<<g2, 256, 0, st>>>(zz, nblocks, eob, offsets, mk, (int16_t *)out);
+        else k_zr_write_sparse<int32_t><<<g2, 256, 0, st>>>(zz, nblocks, eob, offsets, mk, (int32_t *)out);
+        return cudaGetLastError();
+    }
     if (out_elem_size == 2) {
         if (!masks) return cudaErrorInvalidValue;
         k_zr_write<true, int16_t><<<grid, kZrWarps * 32, 0, st>>>(zz, nblocks, eob, offsets, mk, (int16_t *)out);

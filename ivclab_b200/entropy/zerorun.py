@@ -78,7 +78,7 @@ class ZeroRunCoder:
             cur.wait_event(p.event)
         fn = _lib.lib.ivc_zerorun_write_masks if dtype == torch.int32 else _lib.lib.ivc_zerorun_write_masks_i16
         _lib.check(fn(dev_index(t), stream_ptr(t.device), t.data_ptr(), p.nblk, int(self.EOB), p.offsets.data_ptr(),
-                      p.masks.data_ptr(), out.data_ptr()), "ivc_zerorun_write_masks")
+                      p.masks.data_ptr(), out.data_ptr(), total), "ivc_zerorun_write_masks")
         return out
 
     def encode(self, flat_patch_img):
