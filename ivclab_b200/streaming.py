@@ -30,12 +30,12 @@ __all__ = ["StreamedCoder"]
 
 class _Slot:
     """Static device buffers of one pipeline slot, the graph that codes them and that graph's outputs."""
-    __slots__ = ("rgb", "cur", "ref", "graph", "out", "totals")
+    __slots__ = ("rgb", "cur", "ref", "graphs", "totals")
 
 
 class StreamedCoder:
     def __init__(self, quantization_scale=1.0, search_range=4, me_mode="auto", chunk_frames=2, device=None, use_graph=True,
-                 slots=3, compute_streams=2, symbol_dtype="auto"):
+                 slots=3, compute_streams=2, symbol_dtype="auto", ramp=False):
         self.intra = IntraBlockCoder(quantization_scale)
         self.pframe = PFrameBlockCoder(quantization_scale, search_range, me_mode)
         self.zr = ZeroRunCoder()
@@ -52,6 +52,8 @@ class StreamedCoder:
             raise ValueError("symbol_dtype must be 'auto', torch.int32, or torch.int16 with a table that keeps symbols in 16 bits")
         self.symbol_dtype = symbol_dtype
         self.use_graph = bool(use_graph)
+        self.ramp = bool(ramp)                    # short chunks at both ends of a run (see _schedule); measured neutral:
+                                                  # a 1-frame chunk costs 0.33 ms of launches against 0.6 ms for 4 frames
         self.nslots = max(2, int(slots))          # input buffers in rotation: uploads run ahead of the coder by nslots-1 chunks
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self._s_in, self._s_cmp, self._s_out = (torch.cuda.Stream(self.device) for _ in range(3))
@@ -83,7 +85,7 @@ class StreamedCoder:
                 # sequence mode: one luma buffer of C+1 frames, frame 0 = the frame before the chunk (its reference)
                 s.cur = torch.empty((C + 1 if seq else C, H, W), dtype=torch.uint8, device=self.device)
                 s.ref = None if seq else torch.empty((C, H, W), dtype=torch.uint8, device=self.device)
-                s.graph, s.out = None, None
+                s.graphs = {}                       # frames in the chunk -> (CUDA graph, its static outputs)
                 s.totals = torch.zeros(2, dtype=torch.int64).pin_memory()      # the two stream lengths of the chunk in flight
                 slots.append(s)
             self._slots = (key, slots)
@@ -121,18 +123,40 @@ class StreamedCoder:
         sse_p = frame_sse(d_cur, recp)
         return pend_i, pend_p, mv, sse_i, sse_p
 
-    def _launch(self, s: _Slot, n: int, C: int):
-        if not self.use_graph or n != C:
-            return self._code(s, n)                     # partial last chunk (or graphs disabled): eager launches
-        if s.graph is None:
+    def _launch(self, s: _Slot, n: int):
+        if not self.use_graph:
+            return self._code(s, n)
+        if n not in s.graphs:                           # one graph per slot and chunk size, captured on first use
             self._code(s, n)                            # warm-up outside capture (function attributes, workspaces)
             torch.cuda.current_stream(self.device).synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=torch.cuda.current_stream(self.device)):
-                s.out = self._code(s, n)
-            s.graph = g
-        s.graph.replay()
-        return s.out
+                out = self._code(s, n)
+            s.graphs[n] = (g, out)
+        g, out = s.graphs[n]
+        g.replay()
+        return out
+
+    def _schedule(self, F):
+        """Chunk boundaries: full chunks in the middle, short chunks at both ends -- the first upload and the last
+        download are the part of the pipeline nothing overlaps with, so they are kept small."""
+        C = self.chunk
+        ramp = []
+        n = 1
+        while n < C:
+            ramp.append(n)
+            n *= 2
+        ramp = [1] + ramp if C > 1 else []                       # e.g. C = 4 -> 1, 1, 2
+        if not self.ramp or F < 2 * sum(ramp) + C:
+            sizes = [C] * (F // C) + ([F % C] if F % C else [])
+        else:
+            body = F - 2 * sum(ramp)
+            sizes = ramp + [C] * (body // C) + ([body % C] if body % C else []) + ramp[::-1]
+        bounds, lo = [], 0
+        for n in sizes:
+            bounds.append((lo, lo + n))
+            lo += n
+        return bounds
 
     # ---- the pipeline ----------------------------------------------------------------------------
     def run(self, rgb, cur, ref=None, first_ref=None):
@@ -150,7 +174,8 @@ class StreamedCoder:
         F, H, W, _ = rgb.shape
         hb = self._host_buffers(F, H, W)
         C = self.chunk
-        nchunks = (F + C - 1) // C
+        bounds = self._schedule(F)
+        nchunks = len(bounds)
         slots = self._device_slots(C, H, W, seq)
         S = self.nslots
         ev_in = [torch.cuda.Event() for _ in range(nchunks)]
@@ -162,7 +187,7 @@ class StreamedCoder:
         pending = {}                                  # chunk -> device results whose symbol streams are not written yet
 
         def upload(k):
-            lo, hi = k * C, min(F, (k + 1) * C)
+            lo, hi = bounds[k]
             with torch.cuda.stream(self._s_in):
                 if k >= S:
                     self._s_in.wait_event(ev_cmp[k - S])          # the slot's previous chunk has been consumed
@@ -174,7 +199,8 @@ class StreamedCoder:
                     if k == 0:
                         s.cur[0].copy_(ref.reshape(H, W), non_blocking=True)
                     else:                                         # the last frame of the previous chunk, already on the
-                        s.cur[0].copy_(slots[(k - 1) % S].cur[C])  # device (this stream uploaded it): device-to-device
+                        n_prev = bounds[k - 1][1] - bounds[k - 1][0]
+                        s.cur[0].copy_(slots[(k - 1) % S].cur[n_prev])   # device (this stream uploaded it): device-to-device
                 else:
                     s.cur[:hi - lo].copy_(cur[lo:hi], non_blocking=True)
                     s.ref[:hi - lo].copy_(ref[lo:hi], non_blocking=True)
@@ -182,20 +208,20 @@ class StreamedCoder:
                 ev_in[k].record(self._s_in)
 
         def compute(k):
-            n = min(F, (k + 1) * C) - k * C
+            n = bounds[k][1] - bounds[k][0]
             sc = self._s_cmp if k % 2 == 0 else self._s_cmp2
             with torch.cuda.stream(sc):
                 sc.wait_event(ev_in[k])
                 if k >= S:
                     sc.wait_event(ev_fin[k - S])                  # the slot's previous results have been picked up
                 done = self._mark("code", k, sc)
-                pending[k] = self._launch(slots[k % S], n, C)
+                pending[k] = self._launch(slots[k % S], n)
                 done()
                 ev_cmp[k].record(sc)                               # the input slot may be overwritten from here on
 
         def finish(k):
             """Write chunk k's symbol streams (their lengths have arrived by now) and send the results home."""
-            lo, hi = k * C, min(F, (k + 1) * C)
+            lo, hi = bounds[k]
             pend_i, pend_p, mv, sse_i, sse_p = pending.pop(k)
             ev_cmp[k].synchronize()                                # waits for TWO numbers, with chunk k+1 already queued
             sc = self._s_cmp if k % 2 == 0 else self._s_cmp2
