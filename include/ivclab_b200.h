@@ -112,6 +112,13 @@ int ivc_intra_inverse(int device, void *stream,
                       const void *table, int table_dtype,
                       void *out, int out_dtype);
 
+/* ivc_intra_inverse (C = 3) with ycbcr2rgb + clip applied in the store (ivclab/signal/color.py:39-63): the last
+ * step of symbols2image for colour images (image/intracodec.py:139-141) without a second pass.  out: float64 RGB in
+ * [0, 255], bit-identical to ivc_ycbcr2rgb(ivc_intra_inverse(...)). */
+int ivc_intra_inverse_rgb(int device, void *stream,
+                          const int32_t *zz, int64_t n_frames, int64_t Hp, int64_t Wp,
+                          const void *table, int table_dtype, void *rgb_out);
+
 /* ---- fused intra inverse + distortion: one rate-distortion point of a sweep -----------------------
  * Decodes like ivc_intra_inverse (C = 3) and, in the same kernel, measures the squared error of every frame
  * against its uint8 RGB original (orig_rgb8: [n_frames, 8*Hp, 8*Wp, 3], W % 16 == 0, frames

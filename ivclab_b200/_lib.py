@@ -35,6 +35,7 @@ SIGNATURES = {
     "ivc_zigzag": (_i, [_i, _p, _i, _p, _i, _i64, _p]),
     "ivc_intra_forward": (_i, [_i, _p, _p, _i, _i64, _i64, _i64, _i64, _i64, _p, _i, _p]),
     "ivc_intra_inverse": (_i, [_i, _p, _p, _i64, _i64, _i64, _i64, _p, _i, _p, _i]),
+    "ivc_intra_inverse_rgb": (_i, [_i, _p, _p, _i64, _i64, _i64, _p, _i, _p]),
     "ivc_intra_inverse_sse_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "ivc_intra_inverse_sse": (_i, [_i, _p, _p, _i64, _i64, _i64, _p, _i, _p, _p, _i64, _i, _p, _i64, _p]),
     "ivc_me_workspace_bytes": (_i64, [_i64, _i64, _i64]),

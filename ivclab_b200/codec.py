@@ -68,8 +68,10 @@ class IntraBlockCoder:
         _lib.check(st, "ivc_intra_forward_rgb8")
         return to_host(out if batched else out[0], was_np)
 
-    def inverse(self, zz):
-        """int32 scan indices ``[(N,) Hp, Wp, C, 64]`` (C in {1,3}) -> float64 ``[(N,) 8Hp, 8Wp, 3]``."""
+    def inverse(self, zz, to_rgb=False):
+        """int32 scan indices ``[(N,) Hp, Wp, C, 64]`` (C in {1,3}) -> float64 ``[(N,) 8Hp, 8Wp, 3]``.
+        ``to_rgb=True`` (C = 3) applies ``ycbcr2rgb`` + clip in the decoder's store, the last step of
+        ``symbols2image`` (intracodec.py:139-141): the same bits as ``ycbcr2rgb(inverse(zz))`` in one pass."""
         t, was_np = to_device(zz)
         batched = t.ndim == 5
         if t.ndim not in (4, 5) or t.shape[-1] != 64:
@@ -79,9 +81,17 @@ class IntraBlockCoder:
         N, Hp, Wp, C, _ = v.shape
         _, dtab = self.quant._table_on(v.device)
         out = torch.empty((N, Hp * 8, Wp * 8, 3), dtype=torch.float64, device=v.device)
+        if to_rgb and C == 3:
+            st = _lib.lib.ivc_intra_inverse_rgb(dev_index(v), stream_ptr(v.device), v.data_ptr(), N, Hp, Wp,
+                                                dtab.data_ptr(), code(dtab.dtype), out.data_ptr())
+            _lib.check(st, "ivc_intra_inverse_rgb")
+            return to_host(out if batched else out[0], was_np)
         st = _lib.lib.ivc_intra_inverse(dev_index(v), stream_ptr(v.device), v.data_ptr(), N, Hp, Wp, C,
                                         dtab.data_ptr(), code(dtab.dtype), out.data_ptr(), _lib.F64)
         _lib.check(st, "ivc_intra_inverse")
+        if to_rgb:                                      # luma-only scan blocks: broadcast decode, then the colour kernel
+            from .signal.color import ycbcr2rgb
+            out = ycbcr2rgb(out)
         return to_host(out if batched else out[0], was_np)
 
 

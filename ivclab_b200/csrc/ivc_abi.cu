@@ -146,6 +146,20 @@ int ivc_intra_inverse(int device, void *stream, const int32_t *zz, int64_t n_fra
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
 
+int ivc_intra_inverse_rgb(int device, void *stream, const int32_t *zz, int64_t n_frames, int64_t Hp, int64_t Wp,
+                          const void *table, int table_dtype, void *rgb_out) {
+    if (n_frames < 0 || Hp < 0 || Wp < 0) return IVC_ERR_ARG;
+    if (!is_float(table_dtype)) return IVC_ERR_DTYPE;
+    if (n_frames * Hp * Wp == 0) return IVC_OK;
+    if (!zz || !table || !rgb_out) return IVC_ERR_ARG;
+    if (!aligned16(zz) || !aligned16(rgb_out)) return IVC_ERR_ARG;
+    int rc = enter(device);
+    if (rc) return rc;
+    cudaError_t e = ivc::launch_inverse(device, (cudaStream_t)stream, zz, n_frames, Hp, Wp, 3, table, table_dtype, rgb_out, 3,
+                                        nullptr, nullptr, nullptr, 0);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
 int64_t ivc_intra_inverse_sse_workspace_bytes(int64_t n_frames, int64_t Hp, int64_t Wp) {
     if (n_frames < 0 || Hp < 0 || Wp < 0) return -1;
     return (ivc::inverse_sse_tiles(n_frames, Hp, Wp) + 1) * (int64_t)sizeof(double);

@@ -846,7 +846,9 @@ constexpr int kInvBuf = kInvIn + kWorkBytes;                                    
 constexpr int kInvBufSse = kInvBuf + 2 * kRgbIn + 128;                           // + two 896-byte RGB tiles -> 11520 B
 static_assert(kInvBufSse % 128 == 0, "alignment");
 
-template <int SSE>
+// RGB: the store applies ycbcr2rgb + clip (color.py:39-63) to every pixel first -- symbols2image's last step
+// (intracodec.py:139-141) without a second pass over the image (row N1).
+template <int SSE, bool RGB = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_inverse_c3_tma(const InvArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_tT = reinterpret_cast<double *>(smem_raw);                        // [192]
@@ -980,6 +982,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_inverse_c3_tma(const I
             if (lane == 0) a.sse_partial[(cur.frame * g.Hp + cur.by) * (int64_t)g.tiles_per_row + cur.tx] = acc;
         }
         if (!SSE || a.out) {
+            if (RGB) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    double rr, gg, bb;
+                    ycbcr2rgb_px(x[0][i], x[1][i], x[2][i], rr, gg, bb);
+                    x[0][i] = rr; x[1][i] = gg; x[2][i] = bb;
+                }
+            }
 #pragma unroll
             for (int m = 0; m < 3; ++m)
 #pragma unroll
@@ -1581,7 +1591,7 @@ cudaError_t launch_inverse(int device, cudaStream_t st, const int32_t *zz, int64
                            const void *table, int table_dtype, void *out, int mode,
                            const void *pred, const void *ref, const int64_t *mv, int sr) {
     InvArgs a;
-    a.g = make_geom(n, Hp * 8, Wp * 8, Czz, mode == 2 ? 12 : 4);
+    a.g = make_geom(n, Hp * 8, Wp * 8, Czz, mode == 2 ? 12 : 4);      // mode 3: like 0, RGB store
     a.zz = zz; a.Czz = Czz; a.table = table; a.table_dtype = table_dtype; a.out = (double *)out;
     a.pred = (const double *)pred; a.ref = (const double *)ref; a.mv = mv; a.sr = sr;
     a.orig = nullptr; a.orig_frame_stride = 0; a.sse_partial = nullptr;
@@ -1589,7 +1599,11 @@ cudaError_t launch_inverse(int device, cudaStream_t st, const int32_t *zz, int64
     const size_t smem = 192 * sizeof(double) + kWarpsPerCta * kWarpBufBytes;
     const int grid = grid_for(a.g.total_tiles, kWarpsPerCta, device, 2);
     cudaError_t e;
-    if (mode == 0 && !use_v1()) {
+    if (mode == 3) {                                         // C = 3 with the colour transform in the store
+        const size_t smem2 = 1664 + (size_t)kWarpsPerCta * kInvBuf;
+        if ((e = set_smem(k_inverse_c3_tma<0, true>, smem2)) != cudaSuccess) return e;
+        k_inverse_c3_tma<0, true><<<grid, kWarpsPerCta * 32, smem2, st>>>(a);
+    } else if (mode == 0 && !use_v1()) {
         const size_t smem2 = 1664 + (size_t)kWarpsPerCta * kInvBuf;
         if ((e = set_smem(k_inverse_c3_tma<0>, smem2)) != cudaSuccess) return e;
         k_inverse_c3_tma<0><<<grid, kWarpsPerCta * 32, smem2, st>>>(a);

@@ -14,7 +14,7 @@ import torch
 from .._runtime import to_device, to_host
 from ..codec import IntraBlockCoder
 from ..entropy import ZeroRunCoder, stats_marg, symbol_minmax
-from ..signal import DiscreteCosineTransform, rgb2ycbcr, ycbcr2rgb
+from ..signal import DiscreteCosineTransform, rgb2ycbcr
 from ..utils import Patcher, ZigZag
 
 __all__ = ["IntraCodec"]
@@ -69,10 +69,9 @@ class IntraCodec:
         decoded = self.zerorun.decode(symbols if isinstance(symbols, (torch.Tensor, np.ndarray)) else np.asarray(symbols),
                                       [H // 8, W // 8, C])
         d, _ = to_device(decoded)
-        ycbcr = self._coder.inverse(d)                      # [8Hp, 8Wp, 3]
-        if ycbcr.shape[0] != H or ycbcr.shape[1] != W:
-            ycbcr = ycbcr[:H, :W, :]
-        out = ycbcr2rgb(ycbcr.contiguous()) if is_rgb else ycbcr
+        out = self._coder.inverse(d, to_rgb=is_rgb)         # [8Hp, 8Wp, 3]; colour transform inside the decoder's store
+        if out.shape[0] != H or out.shape[1] != W:
+            out = out[:H, :W, :]
         return to_host(out, was_np)
 
     # ---- intracodec.py:144-168, up to the Huffman coder -----------------------------------------------

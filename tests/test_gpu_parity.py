@@ -504,6 +504,21 @@ def test_fused_colour_sse_equals_two_step_form():
     assert np.allclose(ivc.frame_sse_rgb8_vs_ycbcr(rgb, rec).cpu().numpy(), want, rtol=1e-12, atol=0)
 
 
+def test_decoder_with_rgb_store_equals_two_passes():
+    """ivc_intra_inverse_rgb == ycbcr2rgb(ivc_intra_inverse(...)) bit for bit == the oracle's symbols2image tail."""
+    rgb = np.stack([O.smooth_noise_rgb(70 + i, 56, 88) for i in range(2)])
+    for q in (0.07, 1.0):
+        coder = ivc.IntraBlockCoder(q)
+        zz = coder.forward(np.stack([O.rgb2ycbcr(f) for f in rgb]))
+        got = coder.inverse(zz, to_rgb=True)
+        assert np.array_equal(got, ivc.ycbcr2rgb(coder.inverse(zz)))
+        tab = coder.quant.get_quantization_table()
+        assert np.array_equal(got[1], O.ycbcr2rgb(O.intra_inverse(zz[1], tab)))
+    luma = ivc.IntraBlockCoder(1.0).forward(O.smooth_noise_luma(3, 40, 48)[..., None])[:, :, :1]
+    assert np.array_equal(ivc.IntraBlockCoder(1.0).inverse(luma, to_rgb=True),
+                          ivc.ycbcr2rgb(ivc.IntraBlockCoder(1.0).inverse(luma)))
+
+
 @pytest.mark.parametrize("space", ["rgb", "ycbcr"])
 def test_fused_decode_and_distortion(space):
     """ivc_intra_inverse_sse: the reconstruction equals the plain decoder's bit for bit; the squared error equals
