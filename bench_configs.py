@@ -60,7 +60,18 @@ def main():
     for _ in range(10):
         c.inverse(c.forward(h))
     t_h = (time.perf_counter() - t0) / 10 * 1e3
+    # codec level (ivclab_b200.IntraCodec): uint8 RGB numpy image -> symbols (numpy) -> float64 RGB numpy image, i.e.
+    # what IntraCodec.image2symbols + symbols2image do (colour transforms, zero-run coding included), host to host
+    rgb_np = (torch.rand((512, 768, 3), generator=g, device="cuda") * 255).to(torch.uint8).cpu().numpy()
+    ic = ivc.IntraCodec(1.0)
+    ic.symbols2image(ic.image2symbols(rgb_np), rgb_np.shape)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        sym_np = ic.image2symbols(rgb_np)
+        ic.symbols2image(sym_np, rgb_np.shape)
+    t_c = (time.perf_counter() - t0) / 10 * 1e3
     res["cfg1_512x768_rgb"] = {"fused_fwd_inv_ms": t_f, "six_method_calls_ms": t_u, "numpy_in_numpy_out_ms": t_h,
+                               "intracodec_image2symbols_symbols2image_numpy_ms": t_c,
                                "mpixel_s_fused": 512 * 768 / t_f / 1e3}
 
     # neighbours of the path (next rows): zero-run encode of the cfg1 scan indices, colour front end, SSE

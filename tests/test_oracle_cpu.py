@@ -104,6 +104,22 @@ def test_oracle_entropy_golden(g9):
         O.zerorun_decode(g9["sym2"], (5, 7, 4))
 
 
+def test_streamed_coder_chunk_schedule():
+    """Host logic of the pipeline's chunking (no device needed): chunks tile the run exactly, never exceed the slot
+    size, and the ramped schedule puts the short chunks at both ends."""
+    from ivclab_b200.streaming import StreamedCoder
+    sc = object.__new__(StreamedCoder)
+    for C in (1, 2, 4, 8):
+        for ramp in (False, True):
+            sc.chunk, sc.ramp = C, ramp
+            for F in (1, 2, 5, 8, 31, 32, 33, 100):
+                b = sc._schedule(F)
+                assert b[0][0] == 0 and b[-1][1] == F and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+                assert all(0 < hi - lo <= C for lo, hi in b)
+    sc.chunk, sc.ramp = 4, True
+    assert [hi - lo for lo, hi in sc._schedule(32)] == [1, 1, 2, 4, 4, 4, 4, 4, 4, 2, 1, 1]
+
+
 def test_flat_frame_tie_break():
     """all-tie search: interior -> first candidate (index 0), borders -> first in-bounds."""
     z = np.zeros((40, 48))
