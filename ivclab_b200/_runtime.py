@@ -55,7 +55,18 @@ class _quiet_nonwritable:
 
 
 def to_host(t: torch.Tensor, as_numpy: bool):
-    return t.cpu().numpy() if as_numpy else t
+    """numpy result of a numpy-in call.  The download goes into PINNED memory (PyTorch caches such blocks) and the
+    array handed back is a view of it: a pageable ``.cpu()`` moves the same bytes at a fraction of the PCIe rate,
+    and it was most of the latency of the drop-in classes on a single image."""
+    if not as_numpy:
+        return t
+    if not t.is_cuda or t.numel() == 0:
+        return t.cpu().numpy()
+    t = t.contiguous()
+    buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    buf.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return buf.numpy()
 
 
 def stream_ptr(device: torch.device) -> int:
