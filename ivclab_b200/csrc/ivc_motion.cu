@@ -22,6 +22,7 @@
 // packed key (ssd << k | index).  ivc_me_full_search(IVC_ME_AUTO) launches k_me_int and then
 // k_me_exact, which exits immediately unless the flag was raised -- no host round trip, no workspace
 // beyond the 4-byte flag.
+#include <cstdlib>
 #include "ivc_dct.cuh"
 #include "ivc_common.cuh"
 
@@ -632,6 +633,7 @@ static size_t me_geometry(MeArgs &a, int64_t n_frames, int64_t H, int64_t W, int
     // times over (single small frames -- QCIF, one 1080p frame of a closed loop -- get smaller tiles)
     static const int shapes[][2] = {{4, 16}, {2, 16}, {2, 8}, {1, 8}, {1, 4}, {1, 2}, {1, 1}};
     size_t smem = 0;
+    if (const char *env = getenv("IVC_ME_MIN_CTAS")) min_ctas = atoll(env);          // developer override
     for (auto &s : shapes) {
         a.tby = s[0]; a.tbx = s[1];
         const int64_t ctas = n_frames * ((a.Hp + a.tby - 1) / a.tby) * (int64_t)((a.Wp + a.tbx - 1) / a.tbx);
@@ -677,7 +679,7 @@ cudaError_t launch_me_exact(int device, cudaStream_t st, const void *ref, const 
     MeArgs a;
     a.ref = ref; a.cur = cur; a.n = n; a.H = H; a.W = W; a.ref_fs = ref_fs; a.cur_fs = cur_fs; a.mv = mv;
     a.flag = flag; a.run_if = run_if; a.check = 0;
-    const size_t smem = me_geometry(a, n, H, W, sr, f32 ? 4 : 8, 32, 3, 113 * 1024, 4 * 2 * (int64_t)sm_count(device));
+    const size_t smem = me_geometry(a, n, H, W, sr, f32 ? 4 : 8, 32, 3, 113 * 1024, 2 * 2 * (int64_t)sm_count(device));
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     (void)device;
     if (f32) return me_launch_chunks(k_me_exact<float>, a, 4, smem, st);
