@@ -35,7 +35,7 @@ class _Slot:
 
 class StreamedCoder:
     def __init__(self, quantization_scale=1.0, search_range=4, me_mode="auto", chunk_frames=2, device=None, use_graph=True,
-                 slots=3, compute_streams=2, symbol_dtype="auto", ramp=False):
+                 slots=3, compute_streams=2, symbol_dtype="auto", ramp=()):
         self.intra = IntraBlockCoder(quantization_scale)
         self.pframe = PFrameBlockCoder(quantization_scale, search_range, me_mode)
         self.zr = ZeroRunCoder()
@@ -52,8 +52,7 @@ class StreamedCoder:
             raise ValueError("symbol_dtype must be 'auto', torch.int32, or torch.int16 with a table that keeps symbols in 16 bits")
         self.symbol_dtype = symbol_dtype
         self.use_graph = bool(use_graph)
-        self.ramp = bool(ramp)                    # short chunks at both ends of a run (see _schedule); measured neutral:
-                                                  # a 1-frame chunk costs 0.33 ms of launches against 0.6 ms for 4 frames
+        self.ramp = tuple(ramp) if ramp else ()   # sizes of shorter chunks at both ends of a run (see _schedule)
         self.nslots = max(2, int(slots))          # input buffers in rotation: uploads run ahead of the coder by nslots-1 chunks
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self._s_in, self._s_cmp, self._s_out = (torch.cuda.Stream(self.device) for _ in range(3))
@@ -138,16 +137,11 @@ class StreamedCoder:
         return out
 
     def _schedule(self, F):
-        """Chunk boundaries: full chunks in the middle, short chunks at both ends -- the first upload and the last
-        download are the part of the pipeline nothing overlaps with, so they are kept small."""
+        """Chunk boundaries: full chunks in the middle, optionally shorter chunks (``self.ramp``, e.g. ``(2, 2)``) at
+        both ends -- the first upload and the last download are the part of the pipeline nothing overlaps with."""
         C = self.chunk
-        ramp = []
-        n = 1
-        while n < C:
-            ramp.append(n)
-            n *= 2
-        ramp = [1] + ramp if C > 1 else []                       # e.g. C = 4 -> 1, 1, 2
-        if not self.ramp or F < 2 * sum(ramp) + C:
+        ramp = [min(int(n), C) for n in self.ramp if int(n) > 0]
+        if not ramp or F < 2 * sum(ramp) + C:
             sizes = [C] * (F // C) + ([F % C] if F % C else [])
         else:
             body = F - 2 * sum(ramp)

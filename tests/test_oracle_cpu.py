@@ -110,13 +110,13 @@ def test_streamed_coder_chunk_schedule():
     from ivclab_b200.streaming import StreamedCoder
     sc = object.__new__(StreamedCoder)
     for C in (1, 2, 4, 8):
-        for ramp in (False, True):
+        for ramp in ((), (2, 2), (1, 1, 2)):
             sc.chunk, sc.ramp = C, ramp
             for F in (1, 2, 5, 8, 31, 32, 33, 100):
                 b = sc._schedule(F)
                 assert b[0][0] == 0 and b[-1][1] == F and all(x[1] == y[0] for x, y in zip(b, b[1:]))
                 assert all(0 < hi - lo <= C for lo, hi in b)
-    sc.chunk, sc.ramp = 4, True
+    sc.chunk, sc.ramp = 4, (1, 1, 2)
     assert [hi - lo for lo, hi in sc._schedule(32)] == [1, 1, 2, 4, 4, 4, 4, 4, 4, 2, 1, 1]
 
 

@@ -45,13 +45,14 @@ def main():
     ref, cur = s[:-1].contiguous().pin_memory(), s[1:].contiguous().pin_memory()
     for frames in (8, 32):
         for chunk in (1, 2, 4, 8):
-            sc = ivc.StreamedCoder(1.0, 4, chunk_frames=chunk, slots=int(os.environ.get("SLOTS", "3")), compute_streams=int(os.environ.get("CS", "2")))
+            sc = ivc.StreamedCoder(1.0, 4, chunk_frames=chunk, slots=int(os.environ.get("SLOTS", "3")), compute_streams=int(os.environ.get("CS", "2")),
+                                   ramp=tuple(int(v) for v in os.environ.get("RAMP", "").split(",") if v))
             for _ in range(2):
-                out = sc.run(rgb[:frames], cur[:frames], ref[:frames])
+                out = sc.run(rgb[:frames], cur[:frames], first_ref=ref[0])
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for _ in range(5):
-                out = sc.run(rgb[:frames], cur[:frames], ref[:frames])
+                out = sc.run(rgb[:frames], cur[:frames], first_ref=ref[0])
             ms = (time.perf_counter() - t0) / 5 * 1e3
             print(f"frames {frames:2d} chunk {chunk}: {ms:7.3f} ms  {frames * 1080 * 1920 / ms / 1e3:8.0f} Mpixel/s  "
                   f"h2d {out['h2d_bytes'] / 1e6:.0f} MB d2h {out['d2h_bytes'] / 1e6:.0f} MB")

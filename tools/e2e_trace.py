@@ -16,7 +16,7 @@ rgb = (torch.nn.functional.avg_pool2d(torch.rand((F, 3, 1080, 1920), generator=g
        .permute(0, 2, 3, 1).contiguous().to(torch.uint8).cpu().pin_memory())
 s = luma_seq(F + 1, 1080, 1920, 5000).to(torch.uint8).cpu()
 ref, cur = s[:-1].contiguous().pin_memory(), s[1:].contiguous().pin_memory()
-sc = ivc.StreamedCoder(1.0, 4, chunk_frames=chunk, ramp=bool(int(os.environ.get('RAMP', '0'))))
+sc = ivc.StreamedCoder(1.0, 4, chunk_frames=chunk, ramp=tuple(int(v) for v in os.environ.get('RAMP', '').split(',') if v))
 SEQ = bool(int(os.environ.get('SEQ', '1')))
 for _ in range(3):
     sc.run(rgb, cur, first_ref=ref[0]) if SEQ else sc.run(rgb, cur, ref)
