@@ -115,8 +115,8 @@ cudaError_t launch_sse(int device, cudaStream_t st, const void *a, int a_dtype, 
 // ---- symbol statistics: min/max and unit-width histogram (stats_marg, ivclab/entropy/entropy.py:6-29, as
 //      IntraCodec.train_huffman_from_image uses it: intracodec.py:160-166) ---------------------------
 // np.histogram(x, bins=np.arange(lo, hi)) has hi-lo-1 unit bins [lo+k, lo+k+1), the last one closed:
-// x == hi-1 lands in bin hi-lo-2.  Zero-run symbol streams are dominated by a handful of values (0, +-1,
-// +-2, EOB): those are counted with warp ballots (one shared atomic per warp and value), the rest with
+// x == hi-1 lands in bin hi-lo-2.  Zero-run symbol streams are dominated by two values (the zero marker and
+// EOB): those are counted with warp ballots (one shared atomic per warp and value), the rest with
 // shared-memory atomics on a per-CTA histogram, flushed with one global atomic per non-empty bin.
 constexpr int kHistThreads = 256;
 
@@ -136,19 +136,16 @@ __global__ void __launch_bounds__(kHistThreads) k_hist(const void *x, int dtype,
         __syncthreads();
     }
     const int lane = threadIdx.x & 31;
-    const int64_t stride = (int64_t)gridDim.x * kHistThreads;
-    for (int64_t i0 = (int64_t)blockIdx.x * kHistThreads; i0 < n; i0 += stride) {       // warp-uniform trip count
-        const int64_t i = i0 + threadIdx.x;
-        const bool in = i < n;
-        const long long v = in ? ld_i64(x, dtype, i) : 0;
+    auto add = [&](long long v, bool in) {                                             // whole warp calls this together
         long long b = v - lo;
         if (b == nbins) b = nbins - 1;                                                  // closed last bin
         bool todo = in && b >= 0 && b < nbins;
         if (use_smem) {
-            const long long hots[6] = {0, 1, -1, 2, -2, hot};
+            // the two values that dominate a zero-run stream (the zero marker and EOB) are counted per warp
+            const long long hots[2] = {0, hot};
 #pragma unroll
-            for (int h = 0; h < 6; ++h) {
-                const bool is = todo && v == hots[h] && (h < 5 || (hot > 2 || hot < -2));
+            for (int h = 0; h < 2; ++h) {
+                const bool is = todo && v == hots[h] && (h == 0 || hot != 0);
                 const unsigned mask = __ballot_sync(0xffffffffu, is);
                 if (mask && lane == __ffs(mask) - 1) atomicAdd(&sh[(int)b], (unsigned)__popc(mask));
                 todo = todo && !is;
@@ -156,6 +153,27 @@ __global__ void __launch_bounds__(kHistThreads) k_hist(const void *x, int dtype,
             if (todo) atomicAdd(&sh[(int)b], 1u);
         } else if (todo) {
             atomicAdd(&counts[b], 1ull);
+        }
+    };
+    const int64_t stride = (int64_t)gridDim.x * kHistThreads;
+    if (dtype == IVC_I32 && ((uintptr_t)x & 15) == 0) {                                  // four symbols per thread and round
+        const int64_t n4 = n >> 2;
+        for (int64_t i0 = (int64_t)blockIdx.x * kHistThreads; i0 < n4; i0 += stride) {   // warp-uniform trip count
+            const int64_t i = i0 + threadIdx.x;
+            const bool in = i < n4;
+            const int4 v = in ? __ldg(reinterpret_cast<const int4 *>(x) + i) : make_int4(0, 0, 0, 0);
+            add(v.x, in); add(v.y, in); add(v.z, in); add(v.w, in);
+        }
+        if (blockIdx.x == 0) {                                                           // the last n % 4 symbols
+            const int64_t i = 4 * n4 + threadIdx.x;
+            const bool in = threadIdx.x < 32 && i < n;
+            if (threadIdx.x < 32) add(in ? ((const int *)x)[i] : 0, in);
+        }
+    } else {
+        for (int64_t i0 = (int64_t)blockIdx.x * kHistThreads; i0 < n; i0 += stride) {
+            const int64_t i = i0 + threadIdx.x;
+            const bool in = i < n;
+            add(in ? ld_i64(x, dtype, i) : 0, in);
         }
     }
     if (use_smem) {
