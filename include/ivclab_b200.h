@@ -138,7 +138,9 @@ int ivc_intra_inverse_sse(int device, void *stream,
                           void *workspace, int64_t workspace_bytes, double *sse_out);
 
 /* ---- a13: MotionCompensator.compute_motion_vector (motion.py:8-58) ---------------------------
- * ref, cur: n_frames luma planes [H,W] (dtype F32 or F64, both the same), contiguous rows.
+ * ref, cur: n_frames luma planes [H,W] (dtype F32 or F64, both the same), contiguous rows; or U8: uint8 planes
+ * holding the frames' VALUES (float semantics -- what the reference computes after casting them to float; numpy's
+ * wrap-around on uint8-dtype frames is ivc_me_full_search_intdtype) -- always served by the packed-integer kernel.
  * mv_out: [n_frames, H/8, W/8, 1] int64, index = (dy+sr)*(2sr+1) + (dx+sr); first minimum in
  * (dy asc, dx asc) order over in-bounds candidates.
  * workspace: needed for IVC_ME_AUTO only (holds the device-side "not an integer frame" flag),

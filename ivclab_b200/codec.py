@@ -151,7 +151,10 @@ class PFrameBlockCoder:
         r, was_np = to_device(ref)
         c, _ = to_device(cur, r.device)
         batched = r.ndim == 3
-        dt = torch.float32 if (r.dtype == torch.float32 and c.dtype == torch.float32) else torch.float64
+        # uint8 planes keep their dtype: the packed-integer kernel stages them without any conversion (float
+        # semantics -- the values, not numpy's uint8 wrap-around, which is MotionCompensator's business)
+        u8 = r.dtype == torch.uint8 and c.dtype == torch.uint8
+        dt = torch.uint8 if u8 else torch.float32 if (r.dtype == torch.float32 and c.dtype == torch.float32) else torch.float64
         r = r.to(dt).contiguous()
         c = c.to(dt).contiguous()
         rv, cv = (r, c) if batched else (r[None], c[None])

@@ -196,11 +196,20 @@ int ivc_me_full_search(int device, void *stream, const void *ref, const void *cu
                        int64_t H, int64_t W, int64_t ref_frame_stride, int64_t cur_frame_stride, int search_range,
                        int mode, int64_t *mv_out, void *workspace, int64_t workspace_bytes) {
     if (n_frames < 0 || H < 0 || W < 0 || search_range < 0 || search_range > 64) return IVC_ERR_ARG;
-    if (dtype != IVC_F32 && dtype != IVC_F64) return IVC_ERR_DTYPE;
+    if (dtype != IVC_F32 && dtype != IVC_F64 && dtype != IVC_U8) return IVC_ERR_DTYPE;
     if ((H & 7) || (W & 7)) return IVC_ERR_SHAPE;                         // the reference raises on ragged frames
     if (mode != IVC_ME_AUTO && mode != IVC_ME_EXACT && mode != IVC_ME_INT) return IVC_ERR_ARG;
     if (n_frames * H * W == 0) return IVC_OK;
     if (!ref || !cur || !mv_out) return IVC_ERR_ARG;
+    if (dtype == IVC_U8) {
+        // uint8 PLANES holding the frames' values (float semantics, no wrap-around: that is ivc_me_full_search_intdtype).
+        // Always integer-valued, so every mode is served by the packed-integer kernel, whose vectors are exact.
+        int rc8 = enter(device);
+        if (rc8) return rc8;
+        cudaError_t e8 = ivc::launch_me_int(device, (cudaStream_t)stream, ref, cur, IVC_U8, n_frames, H, W, ref_frame_stride,
+                                            cur_frame_stride, search_range, mv_out, nullptr, 0);
+        return e8 == cudaSuccess ? IVC_OK : cuda_fail(e8);
+    }
     if (mode == IVC_ME_AUTO && (!workspace || workspace_bytes < ivc_me_workspace_bytes(n_frames, H, W)))
         return IVC_ERR_WORKSPACE;
     int rc = enter(device);
@@ -211,7 +220,7 @@ int ivc_me_full_search(int device, void *stream, const void *ref, const void *cu
     if (mode != IVC_ME_EXACT) {
         // integer kernel: converts the frames to packed u8 while staging; in AUTO mode it validates them
         // and raises the device flag instead of producing vectors from a non-integer frame
-        e = ivc::launch_me_int(device, st, ref, cur, f32, n_frames, H, W, ref_frame_stride, cur_frame_stride,
+        e = ivc::launch_me_int(device, st, ref, cur, dtype, n_frames, H, W, ref_frame_stride, cur_frame_stride,
                                search_range, mv_out, (int *)workspace, mode == IVC_ME_AUTO ? 1 : 0);
         if (e != cudaSuccess) return cuda_fail(e);
     }

@@ -28,7 +28,7 @@ cudaError_t launch_zigzag(int device, cudaStream_t st, bool inverse, const void 
 cudaError_t launch_me_exact(int device, cudaStream_t st, const void *ref, const void *cur, bool f32, int64_t n,
                             int64_t H, int64_t W, int64_t ref_fs, int64_t cur_fs, int sr, int64_t *mv,
                             int *flag, int run_if);
-cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const void *cur, bool f32, int64_t n,
+cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const void *cur, int dtype, int64_t n,
                           int64_t H, int64_t W, int64_t ref_fs, int64_t cur_fs, int sr, int64_t *mv, int *flag,
                           int check);
 cudaError_t launch_me_wrap(int device, cudaStream_t st, const void *ref, const void *cur, int dtype, int64_t n, int64_t H,

@@ -276,6 +276,36 @@ __device__ __forceinline__ void ldg16(const float *p, float (&v)[4]) {
     asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
 }
 
+// uint8 planes: a packed word IS four consecutive pixels -- one aligned 32-bit load (VEC: the window origin and W are
+// multiples of 4) or four byte loads; nothing to convert, nothing to check.
+template <bool VEC, int UNR, typename Dst>
+__device__ __forceinline__ void stage_batch_u8(const unsigned char *frame, int H, int W, int y0, int x0, int base, int total,
+                                               int wpr, FastDiv d_wpr, unsigned *smem, Dst dst) {
+    const int nthr = blockDim.x;
+    unsigned v[UNR];
+    int out[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+        const int idx = base + u * nthr;
+        const int row = d_wpr.div(idx), w = idx - row * wpr;
+        const int gy = y0 + row, gx = x0 + 4 * w;
+        const bool rok = idx < total && (unsigned)gy < (unsigned)H;
+        const unsigned char *p = frame + (gy * W + gx);
+        out[u] = idx < total ? dst(row, w) : -1;
+        v[u] = 0u;
+        if (VEC) {
+            if (rok && (unsigned)gx < (unsigned)W) v[u] = __ldg(reinterpret_cast<const unsigned *>(p));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (rok && (unsigned)(gx + k) < (unsigned)W) v[u] |= (unsigned)__ldg(p + k) << (8 * k);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+        if (out[u] >= 0) smem[out[u]] = v[u];
+}
+
 // Stage `total` packed words: word idx covers pixels (y0 + idx / wpr, x0 + 4 * (idx % wpr) .. +3) of `frame`,
 // zero where that leaves the frame; dst(row, w) gives the shared-memory word index.  Loads of kStageUnroll
 // words are issued before the first conversion so that a thread keeps 16 pixel loads in flight.  VEC: x0, W
@@ -331,6 +361,16 @@ __device__ __forceinline__ void stage_words(const T *frame, int H, int W, int y0
         stage_batch<VEC, kStageUnroll>(frame, H, W, y0, x0, base, total, wpr, d_wpr, chk, smem, dst);
     for (; base < total; base += nthr)
         stage_batch<VEC, 1>(frame, H, W, y0, x0, base, total, wpr, d_wpr, chk, smem, dst);
+}
+template <bool VEC, typename Dst>
+__device__ __forceinline__ void stage_words(const unsigned char *frame, int H, int W, int y0, int x0, int total, int wpr,
+                                            FastDiv d_wpr, U8Check &, unsigned *smem, Dst dst) {
+    const int nthr = blockDim.x;
+    int base = threadIdx.x;
+    for (; base - (int)threadIdx.x + 2 * kStageUnroll * nthr <= total; base += 2 * kStageUnroll * nthr)
+        stage_batch_u8<VEC, 2 * kStageUnroll>(frame, H, W, y0, x0, base, total, wpr, d_wpr, smem, dst);
+    for (; base < total; base += nthr)
+        stage_batch_u8<VEC, 1>(frame, H, W, y0, x0, base, total, wpr, d_wpr, smem, dst);
 }
 
 // PC: compile-time U / HS pitch (0 = take it from the arguments).  With a constant pitch every row offset of
@@ -730,9 +770,11 @@ static size_t me_int_geometry(MeArgs &a, int G, int pitch, int64_t n_frames, int
     return smem;
 }
 
-cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const void *cur, bool f32, int64_t n,
+cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const void *cur, int dtype, int64_t n,
                           int64_t H, int64_t W, int64_t ref_fs, int64_t cur_fs, int sr, int64_t *mv, int *flag,
                           int check) {
+    const bool f32 = dtype == IVC_F32, u8 = dtype == IVC_U8;
+    if (u8) check = 0;                                                        // uint8 planes are integer-valued by construction
     MeArgs a;
     a.ref = ref; a.cur = cur; a.n = n; a.H = H; a.W = W; a.ref_fs = ref_fs; a.cur_fs = cur_fs; a.mv = mv;
     a.flag = flag; a.run_if = 0; a.check = check;
@@ -742,9 +784,12 @@ cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const vo
     const size_t smem = me_int_geometry(a, G, pitch, n, H, W, sr, 200 * 1024, 4 * 3 * (int64_t)sm_count(device));
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     if (H * W >= 2147483647LL) return cudaErrorInvalidValue;                  // 32-bit pixel coordinates inside a frame
-    const int elem = f32 ? 4 : 8;
-    a.vec = sr % (16 / elem) == 0 && ((uintptr_t)ref & 15) == 0 && ((uintptr_t)cur & 15) == 0 &&
-            (ref_fs * elem) % 16 == 0 && (cur_fs * elem) % 16 == 0;            // W is a multiple of 8
+    const int elem = u8 ? 1 : f32 ? 4 : 8;
+    if (u8)                                                                    // 4-byte loads: window origin and rows 4-aligned
+        a.vec = sr % 4 == 0 && ((uintptr_t)ref & 3) == 0 && ((uintptr_t)cur & 3) == 0 && ref_fs % 4 == 0 && cur_fs % 4 == 0;
+    else
+        a.vec = sr % (16 / elem) == 0 && ((uintptr_t)ref & 15) == 0 && ((uintptr_t)cur & 15) == 0 &&
+                (ref_fs * elem) % 16 == 0 && (cur_fs * elem) % 16 == 0;        // W is a multiple of 8
     cudaError_t e;
     if (check && (e = cudaMemsetAsync(flag, 0, sizeof(int), st)) != cudaSuccess) return e;
     // threads per CTA: when three CTAs fit an SM by shared memory, the count in 256..352 that wastes the
@@ -761,7 +806,8 @@ cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const vo
     }
 #define IVC_ME_INT_CASE(GG, PP)                                                                  \
     if (G == GG && pitch == PP)                                                                  \
-        return f32 ? me_launch_chunks(k_me_int<float, GG, PP>, a, 4, smem, st, threads)          \
+        return u8 ? me_launch_chunks(k_me_int<unsigned char, GG, PP>, a, 1, smem, st, threads)   \
+             : f32 ? me_launch_chunks(k_me_int<float, GG, PP>, a, 4, smem, st, threads)          \
                    : me_launch_chunks(k_me_int<double, GG, PP>, a, 8, smem, st, threads);
     IVC_ME_INT_CASE(9, 136)
     IVC_ME_INT_CASE(9, 144)

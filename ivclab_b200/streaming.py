@@ -108,14 +108,16 @@ class StreamedCoder:
         """Everything of a chunk that does not need a stream length on the host (current stream = compute stream)."""
         d_rgb = s.rgb[:n]
         if s.ref is None:                              # sequence mode: frame t is predicted from frame t-1
-            luma = s.cur[:n + 1].double()
-            d_ref, d_cur = luma[:n], luma[1:]
+            luma8 = s.cur[:n + 1]
+            luma = luma8.double()
+            d_ref, d_cur, r8, c8 = luma[:n], luma[1:], luma8[:n], luma8[1:]
         else:
-            d_cur, d_ref = s.cur[:n].double(), s.ref[:n].double()
+            r8, c8 = s.ref[:n], s.cur[:n]
+            d_cur, d_ref = c8.double(), r8.double()
         zz = self.intra.forward_rgb(d_rgb)
         pend_i = self.zr.encode_begin(zz, total_host=s.totals[0:1], record=False)
         sse_i = self.intra.inverse_with_distortion(zz, d_rgb, space="ycbcr")   # decode + error in one kernel, nothing stored
-        mv = self.pframe.estimate(d_ref, d_cur)
+        mv = self.pframe.estimate(r8, c8)              # the search reads the uint8 planes as they arrived
         zzp = self.pframe.forward(d_cur, d_ref, mv)
         pend_p = self.zr.encode_begin(zzp, total_host=s.totals[1:2], record=False)
         recp = self.pframe.inverse(zzp, ref=d_ref, mv=mv)

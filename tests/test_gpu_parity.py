@@ -232,6 +232,27 @@ def test_motion_integer_dtype_frames_wrap_like_numpy(dtype):
             assert not np.array_equal(want, O.me_full_search(ref.astype(np.float64), cur.astype(np.float64), sr))
 
 
+@pytest.mark.parametrize("sr", [3, 4, 16])
+def test_motion_uint8_planes_equal_float_search(sr):
+    """PFrameBlockCoder.estimate on uint8 planes (float semantics, no conversion pass) == the same search on their
+    float64 values == the oracle; aligned (sr % 4 == 0) and byte-wise staging paths, batches, odd tile counts."""
+    rng = np.random.default_rng(200 + sr)
+    seq = np.clip(O.moving_sequence(90 + sr, 4, 72, 136) + rng.integers(-3, 4, size=(4, 72, 136)), 0, 255).astype(np.uint8)
+    ref8, cur8 = torch.from_numpy(seq[:-1]).cuda(), torch.from_numpy(seq[1:]).cuda()
+    for mode in ("auto", "int", "exact"):
+        pc = ivc.PFrameBlockCoder(1.0, sr, me_mode=mode)
+        got = pc.estimate(ref8, cur8)
+        assert torch.equal(got, pc.estimate(ref8.double(), cur8.double()))
+    want = np.stack([O.me_full_search(seq[i].astype(np.float64), seq[i + 1].astype(np.float64), sr) for i in range(3)])
+    assert np.array_equal(got.cpu().numpy(), want)
+    # planes at an odd byte address: the byte-wise staging path
+    buf_r = torch.empty(72 * 136 + 1, dtype=torch.uint8, device="cuda")
+    buf_c = torch.empty(72 * 136 + 3, dtype=torch.uint8, device="cuda")
+    r_odd, c_odd = buf_r[1:].view(72, 136), buf_c[3:].view(72, 136)
+    r_odd.copy_(ref8[1]); c_odd.copy_(cur8[1])
+    assert r_odd.data_ptr() % 4 and np.array_equal(pc.estimate(r_odd, c_odd).cpu().numpy(), want[1])
+
+
 def test_motion_ragged_frame_raises():
     with pytest.raises(IndexError):
         ivc.MotionCompensator().compute_motion_vector(np.zeros((20, 24)), np.zeros((20, 24)))
