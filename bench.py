@@ -84,7 +84,7 @@ class Clocks:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -92,9 +92,11 @@ class Clocks:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def stop(self, t_from=None, t_to=None):
+        """Statistics over the samples taken between the host times t_from and t_to (the timed region and the
+        identical untimed steps right before it); `samples_timed` counts those inside the timed region proper."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -104,7 +106,10 @@ class Clocks:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        lead = 0.3                                   # seconds of identical load before the timed region
+        rows = [r[1:] for r in self.rows if t_from is None or (t_from - lead <= r[0] <= t_to)]
+        timed = sum(1 for r in self.rows if t_from is not None and t_from <= r[0] <= t_to)
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
                 for n, v in zip(names, r[4:8]):
@@ -114,7 +119,8 @@ class Clocks:
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "samples_timed": timed,
+                "reasons": sorted(reasons)}
 
 
 def pin_to_gpu_cpus(local_rank):
@@ -260,19 +266,24 @@ def run_b200(args):
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
-        time.sleep(0.3)
+    t_spin = time.time()
+    while time.time() - t_spin < 0.4:                # the sampler starts up under the very load it is to observe
+        step()
+        torch.cuda.synchronize()
     K = args.steps
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(phases) + 1)] for _ in range(K)]
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
+    th0 = time.time()
     t0.record(stream)
     for k in range(K):
         step(evs[k])
     t1.record(stream)
     barrier()
+    th1 = time.time()
     ms_total = t0.elapsed_time(t1)
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(th0, th1) if rank == 0 else None
     ms_step = ms_total / K
     if world > 1:
         t = torch.tensor([ms_step], dtype=torch.float64, device=device)
