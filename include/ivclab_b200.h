@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define IVC_ABI_VERSION 1
+#define IVC_ABI_VERSION 2
 
 /* element types */
 #define IVC_U8   0

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "_C", "libivcb200.so")
 
 # element type codes (include/ivclab_b200.h)
 U8, I32, F32, F64, I64, I16 = 0, 1, 2, 3, 4, 5
+ABI_VERSION = 2            # include/ivclab_b200.h IVC_ABI_VERSION (2: entry points added in round 1, zero-run write gained a length)
 ME_AUTO, ME_EXACT, ME_INT = 0, 1, 2
 SSE_RGB8_AS_YCBCR = 103
 DIST_RGB, DIST_YCBCR = 1, 2
@@ -79,8 +80,8 @@ def _load():
         fn = getattr(lib, name)            # AttributeError if the .so lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.ivc_abi_version() != 1:
-        raise ImportError(f"{LIB_PATH}: ABI version {lib.ivc_abi_version()} != 1 (stale build?)")
+    if lib.ivc_abi_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH}: ABI version {lib.ivc_abi_version()} != {ABI_VERSION} (stale build? run build_ext.py --force)")
     return lib
 
 
