@@ -253,6 +253,22 @@ def test_motion_uint8_planes_equal_float_search(sr):
     assert r_odd.data_ptr() % 4 and np.array_equal(pc.estimate(r_odd, c_odd).cpu().numpy(), want[1])
 
 
+def test_motion_more_frames_than_one_grid_dimension():
+    """The search grid is (tiles, frames); batches above 65535 frames go out in chunks -- 70 000 tiny frame pairs through
+    both kernels and the uint8 entry give what the oracle gives on sampled frames (and agree everywhere)."""
+    n = 70000
+    g = torch.Generator(device="cuda").manual_seed(5)
+    ref = torch.randint(0, 256, (n, 8, 16), generator=g, device="cuda", dtype=torch.uint8)
+    cur = torch.roll(ref, 1, dims=2)
+    a = ivc.PFrameBlockCoder(1.0, 2, me_mode="int").estimate(ref.double(), cur.double())
+    b = ivc.PFrameBlockCoder(1.0, 2, me_mode="exact").estimate(ref.double(), cur.double())
+    c = ivc.PFrameBlockCoder(1.0, 2).estimate(ref, cur)
+    assert torch.equal(a, b) and torch.equal(a, c)
+    for i in (0, 65534, 65535, 65536, n - 1):
+        want = O.me_full_search(ref[i].cpu().numpy().astype(np.float64), cur[i].cpu().numpy().astype(np.float64), 2)
+        assert np.array_equal(a[i].cpu().numpy(), want), i
+
+
 def test_motion_ragged_frame_raises():
     with pytest.raises(IndexError):
         ivc.MotionCompensator().compute_motion_vector(np.zeros((20, 24)), np.zeros((20, 24)))
