@@ -430,6 +430,30 @@ def test_closed_loop_lockstep_sequences(decode, use_graph):
             assert np.array_equal(one[k], want[k]), (s, k)
 
 
+def test_closed_loop_full_size_decoder_replay():
+    """cfg5 at its full size (300 x 1080p luma, +-4): a DECODER that only sees the scan indices and vectors rebuilds
+    every reconstruction bit for bit (I-frame: intra inverse; P-frames: prediction from its own previous output),
+    the vectors are what an independent search on (previous reconstruction, frame) gives, and coding is deterministic."""
+    from bench_configs import luma_seq
+    T = 300
+    seq = luma_seq(T, 1080, 1920, 5000)
+    enc = ivc.ClosedLoopLumaCoder(1.0, 4, decode="luma", me_mode="exact")
+    out = enc.code_sequence(seq)
+    assert out["zz"].shape == (T, 135, 240, 3, 64) and out["mv"].shape == (T - 1, 135, 240, 1)
+    pc = ivc.PFrameBlockCoder(1.0, 4, me_mode="exact")
+    prev = pc.inverse(out["zz"][:1], pred=torch.zeros((1, 1080, 1920), dtype=torch.float64, device="cuda"))[0]
+    assert torch.equal(prev, out["recon"][0])
+    for t in range(1, T):
+        if t in (1, 2, 150, T - 1):                              # the encoder's search, re-run from the outside
+            assert torch.equal(pc.estimate(prev, seq[t]), out["mv"][t - 1])
+        prev = pc.inverse(out["zz"][t], ref=prev, mv=out["mv"][t - 1])
+        assert torch.equal(prev, out["recon"][t]), t
+    psnr = 10 * torch.log10(255.0 ** 2 / ((out["recon"] - seq) ** 2).mean(dim=(1, 2)))
+    assert float(psnr.min()) > 24.0 and float(psnr.max()) < 40.0       # busy synthetic texture at qScale 1
+    again = enc.code_sequence(seq)
+    assert all(torch.equal(out[k], again[k]) for k in ("zz", "mv", "recon"))
+
+
 # ---------------------------------------------------------------- "next" rows N2 / N3
 def test_zerorun_encode_matches_reference_stream(g1, g6):
     """N2: the GPU zero-run encoder reproduces the reference's symbol list (zerorun.py:10-43)."""
