@@ -430,6 +430,31 @@ def test_closed_loop_lockstep_sequences(decode, use_graph):
             assert np.array_equal(one[k], want[k]), (s, k)
 
 
+def test_rd_sweep_properties_at_1080p():
+    """cfg3 shape (1080p colour frames, the ten qScales of the sweep), properties that need no oracle: re-encoding a
+    reconstruction reproduces its indices when every table entry exceeds 2 (dequantisation truncates by < 1, i.e. by
+    less than half a quantisation step); distortion grows and the symbol count shrinks monotonically with qScale; the
+    fused decoder's distortion equals the three-kernel form's."""
+    g = torch.Generator(device="cuda").manual_seed(33)
+    rgb = (torch.nn.functional.avg_pool2d(torch.rand((6, 3, 1080, 1920), generator=g, device="cuda") * 255, 5, 1, 2)
+           .permute(0, 2, 3, 1).contiguous()).to(torch.uint8)
+    qs = [0.07, 0.2, 0.4, 0.8, 1.0, 1.5, 2, 3, 4, 4.5]
+    sse_all, nsym = [], []
+    for q in qs:
+        coder = ivc.IntraBlockCoder(q)
+        zz = coder.forward_rgb(rgb)
+        sse, rec = coder.inverse_with_distortion(zz, rgb, space="rgb", return_reconstruction=True)
+        if q >= 0.4:
+            assert torch.equal(coder.forward(rec), zz), q                     # idempotent
+        if q in (0.07, 1.0, 4.5):
+            want = ivc.frame_sse(rgb, ivc.ycbcr2rgb(rec))
+            assert torch.allclose(sse, want, rtol=1e-12, atol=0)
+        sse_all.append(sse.sum().item())
+        nsym.append(ivc.ZeroRunCoder().encode(zz).numel())
+    assert all(a < b for a, b in zip(sse_all, sse_all[1:])), sse_all          # distortion up
+    assert all(a > b for a, b in zip(nsym, nsym[1:])), nsym                   # rate down
+
+
 def test_closed_loop_full_size_decoder_replay():
     """cfg5 at its full size (300 x 1080p luma, +-4): a DECODER that only sees the scan indices and vectors rebuilds
     every reconstruction bit for bit (I-frame: intra inverse; P-frames: prediction from its own previous output),
