@@ -386,10 +386,34 @@ def run_b200(args):
             # sequence, so every luma plane is uploaded once (first_ref = the reference of frame 0 = the last frame)
             last[0] = streamed.run(h_rgb, h_l8, first_ref=h_r8[0])
 
-        e2e_ms = time_e2e(e2e_streamed_step)
-        e2e_val = world * Fe * H * W / (e2e_ms * 1e-3) / 1e6
+        call_ms = time_e2e(e2e_streamed_step)                  # one call per step: every call fills and drains the pipeline
         h2d = last[0]["h2d_bytes"]
         d2h = last[0]["d2h_bytes"]
+        # The K steps as ONE stream: the inputs of the Ke steps are queued in host memory back to back and handed to a
+        # single call, as a service that codes a continuous feed would; every step's frames are still uploaded and every
+        # step's results downloaded inside the timed region, but fill and drain are paid once, not once per step.
+        Ke = max(3, min(K, 10))
+        h_rgb_s = h_rgb.repeat(Ke, 1, 1, 1).pin_memory()
+        h_l8_s = h_l8.repeat(Ke, 1, 1).pin_memory()
+
+        def e2e_stream_call():
+            last[0] = streamed.run(h_rgb_s, h_l8_s, first_ref=h_r8[0])     # cyclic pairs: frame 0 of a step follows frame Fe-1
+
+        for _ in range(2):
+            e2e_stream_call()
+        barrier()
+        w0 = time.perf_counter()
+        e2e_stream_call()
+        barrier()
+        e2e_ms = (time.perf_counter() - w0) * 1e3 / Ke
+        if world > 1:
+            t = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        assert last[0]["h2d_bytes"] == Ke * (h2d - H * W) + H * W       # Ke steps of frames plus one first reference
+        e2e_val = world * Fe * H * W / (e2e_ms * 1e-3) / 1e6
+        h2d, d2h = round(last[0]["h2d_bytes"] / Ke), round(last[0]["d2h_bytes"] / Ke)
+        del h_rgb_s, h_l8_s
         raw_ms = time_e2e(e2e_raw_step)
         raw_val = world * Fa * H * W / (raw_ms * 1e-3) / 1e6
         raw_h2d = h_y.numel() * 8 + h_l.numel() * 8 + h_r.numel() * 8
@@ -419,10 +443,13 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(Fr, world),
             "e2e": None if args.no_e2e else {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "frames_per_step": Fe, "ms_per_step": round(e2e_ms, 3), "host_cpus_per_rank": numa,
+                    "frames_per_step": Fe, "ms_per_step": round(e2e_ms, 3), "steps_per_call": max(3, min(K, 10)),
+                    "one_call_per_step": {"ms_per_step": round(call_ms, 3), "value": round(world * Fe * H * W / (call_ms * 1e-3) / 1e6, 1)},
+                    "host_cpus_per_rank": numa,
                     "single_stream": {"frames_per_step": Fa, "ms_per_step": round(serial_ms, 3),
                                       "value": round(world * Fa * H * W / (serial_ms * 1e-3) / 1e6, 1)},
-                    "api": "StreamedCoder.run (upload / 2 compute / download streams, 4-frame chunks, one CUDA graph per slot): pinned host uint8 RGB + uint8 luma in; "
+                    "api": "StreamedCoder.run (upload / 2 compute / download streams, 4-frame chunks, one CUDA graph per slot), the steps queued in host memory and "
+                           "submitted as one stream (one_call_per_step: a separate call, i.e. pipeline fill and drain, per step): pinned host uint8 RGB + uint8 luma in; "
                            "IntraBlockCoder.forward_rgb/inverse, PFrameBlockCoder.estimate/forward/inverse, ZeroRunCoder.encode, "
                            "frame_sse; zero-run symbols (int16 transfer format: |symbol| <= 2040/min(table) for 8-bit input) + MVs + SSE back to host"},
             "e2e_raw": None if args.no_e2e else {"value": round(raw_val, 1), "unit": UNIT, "h2d_bytes_per_step": raw_h2d, "d2h_bytes_per_step": raw_d2h,
