@@ -17,6 +17,7 @@
 // HBM traffic is exactly the algorithmic bytes (each input element read once, each output written
 // once); arithmetic is FP64 (14 rounded operations per sample for the 2-D transform).
 #include <cstdlib>
+#include <cuda.h>          // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
 #include "ivc_dct.cuh"
 #include "ivc_color.cuh"
 #include "ivc_common.cuh"
@@ -1386,6 +1387,372 @@ __global__ void __launch_bounds__(kPiWarps * 32, 1) k_pframe_inverse_tma(const I
 }
 
 // ================================================================================================
+// v3 of the P-frame kernels (K1p / K2p): the motion-compensated prediction is gathered by the TMA
+// unit itself.  The reference planes are described by ONE tensor map (W x H x frames, float64); a
+// block's prediction is a single box copy landing on the tile's mbarrier.  The unit faults ("illegal
+// instruction") when a box starts at an address that is not a multiple of 16 bytes -- measured here:
+// every odd dx -- so the box is 10 x 8 and starts at the even column sx & ~1; the 8 wanted columns
+// begin at element sx & 1 of each 80-byte row (80 == 16 * 5 mod 128: the row reads are conflict-free
+// without any swizzle).  A window that leaves the frame must give an all-zero block
+// (motion.py:90-92), not a partially filled one: such a block asks for a box that lies entirely
+// outside the tensor and the unit zero-fills it.
+// Against v2 this removes 24 cp.async + their address arithmetic per lane and tile, and the tile
+// shrinks to 8 blocks (lane (r,u): blocks u and u + 4): 13.4 / 11.4 KB of shared memory per warp and
+// <= 128 registers, i.e. 16 warps per SM instead of 12 / 10.
+// ================================================================================================
+constexpr int kP3Blocks = 8;
+constexpr int kP3Pitch = 528;                         // bytes per IN row: 8 blocks * 64 + 16 (== 16 mod 128)
+constexpr int kP3Box = 640;                           // one 10 x 8 box of doubles (80-byte rows)
+constexpr int kP3Pred = kP3Blocks * kP3Box;           // 5120: block-major boxes
+constexpr int kP3In = 8 * kP3Pitch;                   // 4224
+constexpr int kP3TU = 136;                            // doubles per u-plane: 16 rows * 8 + 8 skew (64 B)
+constexpr int kP3Trans = 4 * kP3TU * 8;               // 4352
+constexpr int kP3Region = 4 * kStageU * 4;            // 3200: one round of scan staging (4 blocks x 3 tables)
+constexpr int kP3Header = 3584;                       // tables + barriers (a multiple of 128)
+constexpr int kP3ZzU = 136;                           // K2p IN staging: 2 blocks * 64 ints + 8 pad per u
+constexpr int kP3ZzIn = 4 * kP3ZzU * 4;               // 2176
+__host__ __device__ constexpr int p3_fwd_buf(int regions) {
+    return (kP3Pred + kP3In + (regions * kP3Region > kP3Trans ? regions * kP3Region : kP3Trans) + 127) / 128 * 128;
+}
+constexpr int kP3InvBuf = (kP3Pred + kP3ZzIn + kP3Trans + 127) / 128 * 128;    // 11648
+static_assert(kP3In <= kP3Trans, "the output row tile reuses the transposition buffer");
+
+__device__ __forceinline__ void tma_box_g2s(uint32_t dst, const CUtensorMap *tm, int x, int y, int z, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+
+// lane 8 + b fetches the prediction of block b of the tile (its vector was loaded one tile ahead) and returns
+// the column parity sx & 1 of the block's window inside its box
+__device__ __forceinline__ int p3_gather(const CUtensorMap *tm, uint32_t pred_s, uint32_t bar, int lane, int nb,
+                                         int64_t mvidx, int sr, int Hi, int Wi, int by, int b0, int frame) {
+    const int b = lane - 8;
+    int par = 0;
+    if (b >= 0 && b < nb) {
+        int dy, dx;
+        mv_decode(mvidx, sr, dy, dx);
+        int sy = by * 8 + dy, sx = (b0 + b) * 8 + dx;
+        const bool ok = sy >= 0 && sy <= Hi - 8 && sx >= 0 && sx <= Wi - 8;
+        if (!ok) { sx = -16; sy = -8; }                  // a box entirely outside the tensor: zero-filled
+        par = sx & 1;
+        tma_box_g2s(pred_s + b * kP3Box, tm, sx - par, sy, frame, bar);
+    }
+    return par;
+}
+
+template <int WARPS, int CTAS, int REGIONS>
+__global__ void __launch_bounds__(WARPS * 32, CTAS) k_pframe_forward_tm(const FwdArgs a, const __grid_constant__ CUtensorMap tm_ref) {
+    constexpr int kBuf = p3_fwd_buf(REGIONS);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *s_rt = reinterpret_cast<double *>(smem_raw);                       // [192]
+    double *s_t = s_rt + 192;                                                   // [192]
+    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem_raw + 3072);   // [WARPS]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *pred_b = smem_raw + kP3Header + warp * kBuf;
+    unsigned char *in_b = pred_b + kP3Pred;
+    unsigned char *work_b = in_b + kP3In;
+    const uint32_t bar = smem_u32(s_bar + warp), in_s = smem_u32(in_b), pred_s = smem_u32(pred_b), work_s = smem_u32(work_b);
+
+    for (int i = threadIdx.x; i < 192; i += blockDim.x) {
+        const double t = load_table_elem(a.table, a.table_dtype, i);
+        s_t[i] = t;
+        s_rt[i] = __drcp_rn(t);
+    }
+    if (lane == 0) mbar_init(bar, 1);
+    fence_mbar_init();
+    __syncthreads();
+
+    const int r = lane & 7, u = lane >> 3;
+    const unsigned char *rd_in = in_b + r * kP3Pitch + u * 64;                  // + m*256 + 16k
+    const unsigned char *rd_pr = pred_b + u * kP3Box + r * 80;                  // + m*4*kP3Box + parity*8 + 8e
+    unsigned char *t_wr[4], *zz_wr[8];
+    const unsigned char *t_rd[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        t_wr[h] = work_b + u * (kP3TU * 8) + ((((r >> 1) ^ h) << 1) + (r & 1)) * 8;    // + row*64
+        t_rd[h] = work_b + u * (kP3TU * 8) + r * 64 + ((h ^ (r >> 1)) << 4);           // + m*512
+    }
+#pragma unroll
+    for (int v = 0; v < 8; ++v) zz_wr[v] = work_b + (u * kStageU + ZZ_ORDER[v * 8 + r]) * 4;   // + region + ch*256
+    const double *rt_l = s_rt + r, *t_l = s_t + r;
+
+    const TileGeom &g = a.g;
+    const int64_t row_elems = g.W, frame_elems = g.H * g.W;
+    const int Hi = (int)g.H, Wi = (int)g.W;
+    const int64_t gw = (int64_t)blockIdx.x * WARPS + warp;
+    const int64_t nw = (int64_t)gridDim.x * WARPS;
+    if (gw >= g.total_tiles) return;
+    const int64_t my_tiles = (g.total_tiles - gw + nw - 1) / nw;
+    TileIter cur, nxt, nx2;
+    cur.init(g, gw, nw);
+    nxt = cur;
+
+    auto load_mv = [&](const TileIter &ti) -> int64_t {          // lanes 8..15: vector of block (b0 + lane - 8)
+        const int b0 = ti.tx * kP3Blocks, b = lane - 8;
+        return (b >= 0 && b < min(kP3Blocks, g.Wp - b0)) ? a.mv[(ti.frame * g.Hp + ti.by) * (int64_t)g.Wp + b0 + b] : 0;
+    };
+    auto issue = [&](const TileIter &ti, int64_t mvidx) {        // whole warp
+        const int b0 = ti.tx * kP3Blocks, nb = min(kP3Blocks, g.Wp - b0);
+        fence_proxy_async();
+        if (lane == 0) mbar_expect_tx(bar, (uint32_t)nb * (512u + kP3Box));  // 8 rows of nb*64 bytes + nb boxes
+        __syncwarp();
+        if (lane < 8) {                                     // lane r copies current-frame row r
+            const double *src = a.img + ti.frame * a.frame_stride + ((int64_t)ti.by * 8 + lane) * row_elems + (int64_t)b0 * 8;
+            bulk_g2s(in_s + lane * kP3Pitch, src, (uint32_t)nb * 64u, bar);
+        }
+        return p3_gather(&tm_ref, pred_s, bar, lane, nb, mvidx, a.sr, Hi, Wi, ti.by, b0, (int)ti.frame);
+    };
+
+    int64_t mv_nxt = load_mv(cur);
+    int par_l = issue(cur, mv_nxt);                  // lanes 8..15: column parity of the tile in flight
+    nxt.advance(g);
+    mv_nxt = (my_tiles > 1) ? load_mv(nxt) : 0;
+    nx2 = nxt;
+    uint32_t parity = 0;
+    for (int64_t it = 0; it < my_tiles; ++it, parity ^= 1u) {
+        nx2.advance(g);
+        const int b0 = cur.tx * kP3Blocks, nb = min(kP3Blocks, g.Wp - b0);
+        mbar_wait(bar, parity);
+        double x[2][8];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const unsigned char *pp = rd_pr + m * (4 * kP3Box) + 8 * __shfl_sync(0xffffffffu, par_l, 8 + u + 4 * m);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double2 c = *reinterpret_cast<const double2 *>(rd_in + m * 256 + 16 * k);
+                double2 p;
+                p.x = *reinterpret_cast<const double *>(pp + 16 * k);
+                p.y = *reinterpret_cast<const double *>(pp + 16 * k + 8);
+                if (a.pred_out && (u + 4 * m) < nb)
+                    stg_stream(a.pred_out + cur.frame * frame_elems + ((int64_t)cur.by * 8 + r) * row_elems +
+                                   (int64_t)(b0 + u + 4 * m) * 8 + 2 * k, p);
+                x[m][2 * k] = __dsub_rn(c.x, p.x);                       // residual = cur - prediction
+                x[m][2 * k + 1] = __dsub_rn(c.y, p.y);
+            }
+        }
+        __syncwarp();                                   // IN / PRED are consumed
+        const int64_t mv_cur_next = mv_nxt;
+        if (it + 1 < my_tiles) {
+            par_l = issue(nxt, mv_cur_next);
+            mv_nxt = (it + 2 < my_tiles) ? load_mv(nx2) : 0;      // consumed one iteration later
+        }
+#pragma unroll
+        for (int m = 0; m < 2; ++m) dct2_8(x[m]);
+        bulk_wait_read0();                              // previous tile's stores have drained WORK
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) *reinterpret_cast<double *>(t_wr[j >> 1] + (m * 8 + j) * 64) = x[m][j];
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double2 v = *reinterpret_cast<const double2 *>(t_rd[k] + m * 512);
+                x[m][2 * k] = v.x;
+                x[m][2 * k + 1] = v.y;
+            }
+            dct2_8(x[m]);
+        }
+        __syncwarp();
+        // numpy broadcasting: the single luma channel is quantised with all three tables
+        // (patchquant.py:59).  One round per sub-block m.
+        int32_t *outf = a.out + ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0) * 192;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const int reg = (REGIONS == 2) ? m * kP3Region : 0;
+            if (REGIONS == 1 && m == 1) { bulk_wait_read0(); __syncwarp(); }
+            QuantGuard qg;
+            {
+                double rtv[3][8];
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) rtv[ch][v] = rt_l[ch * 64 + v * 8];
+                int qv[3][8];
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) qv[ch][v] = qg.q(x[m][v], rtv[ch][v]);
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) *reinterpret_cast<int *>(zz_wr[v] + reg + ch * 256) = qv[ch][v];
+            }
+            if (__builtin_expect(qg.risky(), 0)) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                    for (int v = 0; v < 8; ++v)
+                        *reinterpret_cast<int *>(zz_wr[v] + reg + ch * 256) = quantize_exact_f64(x[m][v], t_l[ch * 64 + v * 8]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane < 4 && lane + 4 * m < nb) bulk_s2g(outf + (lane + 4 * m) * 192, work_s + reg + lane * (kStageU * 4), 768u);
+            bulk_commit();                                // every lane commits (possibly empty) groups: counts stay in step
+        }
+        cur = nxt;
+        nxt = nx2;
+    }
+    bulk_wait_all0();
+}
+
+// K2p v3: the prediction is needed only at the very end of a tile, so its gather is issued at the top
+// of the tile's own iteration on a second mbarrier (a single PRED buffer); the scan blocks of the next
+// tile are prefetched as before.
+template <int WARPS, int CTAS>
+__global__ void __launch_bounds__(WARPS * 32, CTAS) k_pframe_inverse_tm(const InvArgs a, const __grid_constant__ CUtensorMap tm_ref) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *s_tT = reinterpret_cast<double *>(smem_raw);                        // [64] luminance table, transposed
+    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem_raw + 3072);   // [2 * WARPS]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *pred_b = smem_raw + kP3Header + warp * kP3InvBuf;
+    unsigned char *in_b = pred_b + kP3Pred;
+    unsigned char *work_b = in_b + kP3ZzIn;
+    const uint32_t bar_in = smem_u32(s_bar + 2 * warp), bar_p = bar_in + 8;
+    const uint32_t in_s = smem_u32(in_b), pred_s = smem_u32(pred_b), work_s = smem_u32(work_b);
+
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_tT[(i & 7) * 8 + (i >> 3)] = load_table_elem(a.table, a.table_dtype, i);
+    if (lane == 0) { mbar_init(bar_in, 1); mbar_init(bar_p, 1); }
+    fence_mbar_init();
+    __syncthreads();
+
+    const int r = lane & 7, u = lane >> 3;
+    const unsigned char *q_rd[8];
+    unsigned char *t_wr[4], *o_wr;
+    const unsigned char *t_rd[4];
+    const unsigned char *p_rd = pred_b + u * kP3Box + r * 8;                    // + m*4*kP3Box + parity*8 + i*80
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q_rd[j] = in_b + (u * kP3ZzU + ZZ_ORDER[r * 8 + j]) * 4;     // + m*256
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        t_wr[h] = work_b + u * (kP3TU * 8) + ((((r >> 1) ^ h) << 1) + (r & 1)) * 8;
+        t_rd[h] = work_b + u * (kP3TU * 8) + r * 64 + ((h ^ (r >> 1)) << 4);
+    }
+    o_wr = work_b + (8 * u + r) * 8;                                            // + i*528 + m*256
+    const double *tq_l = s_tT + r;                                              // tq_l[j*8] = lum[r][j]
+
+    const TileGeom &g = a.g;
+    const int64_t row_elems = g.W, frame_elems = g.H * g.W;
+    const int Hi = (int)g.H, Wi = (int)g.W;
+    const int64_t gw = (int64_t)blockIdx.x * WARPS + warp;
+    const int64_t nw = (int64_t)gridDim.x * WARPS;
+    if (gw >= g.total_tiles) return;
+    const int64_t my_tiles = (g.total_tiles - gw + nw - 1) / nw;
+    TileIter cur, nxt, nx2;
+    cur.init(g, gw, nw);
+    nxt = cur;
+
+    auto load_mv = [&](const TileIter &ti) -> int64_t {
+        const int b0 = ti.tx * kP3Blocks, b = lane - 8;
+        return (b >= 0 && b < min(kP3Blocks, g.Wp - b0)) ? a.mv[(ti.frame * g.Hp + ti.by) * (int64_t)g.Wp + b0 + b] : 0;
+    };
+    auto issue_in = [&](const TileIter &ti) {               // scan channel 0 of block `lane` (stride Czz*64 ints)
+        const int b0 = ti.tx * kP3Blocks, nb = min(kP3Blocks, g.Wp - b0);
+        fence_proxy_async();
+        if (lane == 0) mbar_expect_tx(bar_in, (uint32_t)nb * 256u);
+        __syncwarp();
+        if (lane < nb) {
+            const int32_t *zsrc = a.zz + ((ti.frame * g.Hp + ti.by) * (int64_t)g.Wp + b0 + lane) * a.Czz * 64;
+            bulk_g2s(in_s + ((lane & 3) * kP3ZzU + (lane >> 2) * 64) * 4, zsrc, 256u, bar_in);
+        }
+    };
+    auto issue_pred = [&](const TileIter &ti, int64_t mvidx) {
+        const int b0 = ti.tx * kP3Blocks, nb = min(kP3Blocks, g.Wp - b0);
+        fence_proxy_async();
+        if (lane == 0) mbar_expect_tx(bar_p, (uint32_t)nb * kP3Box);
+        __syncwarp();
+        return p3_gather(&tm_ref, pred_s, bar_p, lane, nb, mvidx, a.sr, Hi, Wi, ti.by, b0, (int)ti.frame);
+    };
+
+    int64_t mv_cur = load_mv(cur);
+    issue_in(cur);
+    nxt.advance(g);
+    int64_t mv_nxt = (my_tiles > 1) ? load_mv(nxt) : 0;
+    nx2 = nxt;
+    uint32_t parity = 0;
+    for (int64_t it = 0; it < my_tiles; ++it, parity ^= 1u) {
+        nx2.advance(g);
+        const int b0 = cur.tx * kP3Blocks, nb = min(kP3Blocks, g.Wp - b0);
+        const int par_l = issue_pred(cur, mv_cur);      // PRED was consumed at the end of the previous iteration
+        mbar_wait(bar_in, parity);
+        int q[2][8];
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) q[m][j] = *reinterpret_cast<const int *>(q_rd[j] + m * 256);
+        __syncwarp();
+        mv_cur = mv_nxt;
+        if (it + 1 < my_tiles) {
+            issue_in(nxt);
+            mv_nxt = (it + 2 < my_tiles) ? load_mv(nx2) : 0;
+        }
+        double x[2][8];
+        int mx = 0;
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const double p = __dmul_rn(i32_to_f64(q[m][j]), tq_l[j * 8]);       // luminance table for every block
+                mx = max(mx, __double2hiint(p) & 0x7fffffff);
+                x[m][j] = trunc_f64_small(p);
+            }
+        if (__builtin_expect(mx >= 0x41E00000, 0)) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[m][j] = dequantize_f64(q[m][j], tq_l[j * 8]);
+        }
+#pragma unroll
+        for (int m = 0; m < 2; ++m) dct3_8(x[m]);
+        bulk_wait_read0();                              // every lane drains its own bulk-store group
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) *reinterpret_cast<double *>(t_wr[j >> 1] + (m * 8 + j) * 64) = x[m][j];
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double2 v = *reinterpret_cast<const double2 *>(t_rd[k] + m * 512);
+                x[m][2 * k] = v.x;
+                x[m][2 * k + 1] = v.y;
+            }
+            dct3_8(x[m]);
+        }
+        __syncwarp();
+        mbar_wait(bar_p, parity);
+        {
+            double pr[2][8];                             // prediction of column r of the two blocks (loaded as a batch)
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const unsigned char *pp = p_rd + m * (4 * kP3Box) + 8 * __shfl_sync(0xffffffffu, par_l, 8 + u + 4 * m);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) pr[m][i] = *reinterpret_cast<const double *>(pp + i * 80);
+            }
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int i = 0; i < 8; ++i)              // recon = prediction + recon_residual (videocodec.py:74)
+                    *reinterpret_cast<double *>(o_wr + i * kP3Pitch + m * 256) = __dadd_rn(pr[m][i], x[m][i]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane < 8) {                                   // lane r stores output row r
+            double *dst = a.out + cur.frame * frame_elems + ((int64_t)cur.by * 8 + lane) * row_elems + (int64_t)b0 * 8;
+            bulk_s2g(dst, work_s + lane * kP3Pitch, (uint32_t)nb * 64u);
+            bulk_commit();
+        }
+        cur = nxt;
+        nxt = nx2;
+    }
+    bulk_wait_all0();
+}
+
+// ================================================================================================
 // unfused per-method kernels (each class method alone; simple, still coalesced where it matters)
 // ================================================================================================
 template <typename TI>
@@ -1520,6 +1887,44 @@ static bool use_v1() {            // A/B switch for profiling: IVC_FUSED_V1=1 se
     return v;
 }
 
+// P-frame kernel generation: IVC_PFRAME=2 keeps the cp.async gather (v2); IVC_PFRAME=3r2 selects the v3 forward
+// kernel with two staging regions (14 warps per SM).  Default: v3, one region, 16 warps.
+static int pframe_variant() {
+    static const int v = [] {
+        const char *e = getenv("IVC_PFRAME");
+        if (!e || !e[0]) return 3;
+        if (e[0] == '2') return 2;
+        return (e[0] == '3' && e[1] == 'r' && e[2] == '2') ? 32 : 3;
+    }();
+    return v;
+}
+
+// Tensor map of the reference planes for the v3 gather: float64 [n, H, W], 10 x 8 boxes, zero fill.
+// Returns false when the driver entry point is missing or the planes do not meet the unit's alignment rules
+// (base 16-byte aligned; W is a multiple of 8, so the row pitch always is) -- the caller then uses the v2 kernels.
+static bool make_ref_map(CUtensorMap *tm, const void *ref, int64_t n, int64_t H, int64_t W) {
+    typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static const EncodeTiled encode = [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        return (EncodeTiled)fn;
+    }();
+    if (!encode || !ref || ((uintptr_t)ref & 15) || n < 1 || n > 0x7fffffff || H > 0x7fffffff || W > 0x7fffffff ||
+        (uint64_t)H * (uint64_t)W * 8ull >= (1ull << 40))
+        return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * 8, (cuuint64_t)H * (cuuint64_t)W * 8};
+    const cuuint32_t box[3] = {10, 8, 1}, estr[3] = {1, 1, 1};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(ref), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int grid_for(int64_t work_items, int per_cta, int device, int ctas_per_sm) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -1552,7 +1957,20 @@ cudaError_t launch_forward(int device, cudaStream_t st, const void *img, int64_t
     const size_t smem = 2 * 192 * sizeof(double) + kWarpsPerCta * kWarpBufBytes;
     const int grid = grid_for(a.g.total_tiles, kWarpsPerCta, device, 2);
     cudaError_t e;
-    if (pframe && !use_v1()) {
+    CUtensorMap tm;
+    if (pframe && !use_v1() && pframe_variant() != 2 && make_ref_map(&tm, ref, n, H, W)) {
+        FwdArgs a3 = a;
+        a3.g = make_geom(n, H, W, 1, kP3Blocks);
+        if (pframe_variant() == 32) {
+            const size_t smem3 = kP3Header + (size_t)14 * p3_fwd_buf(2);
+            if ((e = set_smem(k_pframe_forward_tm<14, 1, 2>, smem3)) != cudaSuccess) return e;
+            k_pframe_forward_tm<14, 1, 2><<<grid_for(a3.g.total_tiles, 14, device, 1), 14 * 32, smem3, st>>>(a3, tm);
+        } else {
+            const size_t smem3 = kP3Header + (size_t)8 * p3_fwd_buf(1);
+            if ((e = set_smem(k_pframe_forward_tm<8, 2, 1>, smem3)) != cudaSuccess) return e;
+            k_pframe_forward_tm<8, 2, 1><<<grid_for(a3.g.total_tiles, 8, device, 2), 8 * 32, smem3, st>>>(a3, tm);
+        }
+    } else if (pframe && !use_v1()) {
         const size_t smem2 = 3200 + (size_t)kPfWarps * kPfBuf;
         if ((e = set_smem(k_pframe_forward_tma, smem2)) != cudaSuccess) return e;
         k_pframe_forward_tma<<<grid_for(a.g.total_tiles, kPfWarps, device, 1), kPfWarps * 32, smem2, st>>>(a);
@@ -1613,6 +2031,11 @@ cudaError_t launch_inverse(int device, cudaStream_t st, const int32_t *zz, int64
     } else if (mode == 1) {
         if ((e = set_smem(k_inverse<1>, smem)) != cudaSuccess) return e;
         k_inverse<1><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
+    } else if (CUtensorMap tm; !use_v1() && !pred && pframe_variant() != 2 && make_ref_map(&tm, ref, n, Hp * 8, Wp * 8)) {
+        a.g = make_geom(n, Hp * 8, Wp * 8, Czz, kP3Blocks);
+        const size_t smem3 = kP3Header + (size_t)8 * kP3InvBuf;
+        if ((e = set_smem(k_pframe_inverse_tm<8, 2>, smem3)) != cudaSuccess) return e;
+        k_pframe_inverse_tm<8, 2><<<grid_for(a.g.total_tiles, 8, device, 2), 8 * 32, smem3, st>>>(a, tm);
     } else if (!use_v1()) {
         const size_t smem2 = 3200 + (size_t)kPiWarps * kPiBuf;
         if ((e = set_smem(k_pframe_inverse_tma, smem2)) != cudaSuccess) return e;
