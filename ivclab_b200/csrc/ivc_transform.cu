@@ -1397,8 +1397,16 @@ __global__ void __launch_bounds__(kPiWarps * 32, 1) k_pframe_inverse_tma(const I
 // (motion.py:90-92), not a partially filled one: such a block asks for a box that lies entirely
 // outside the tensor and the unit zero-fills it.
 // Against v2 this removes 24 cp.async + their address arithmetic per lane and tile, and the tile
-// shrinks to 8 blocks (lane (r,u): blocks u and u + 4): 13.4 / 11.4 KB of shared memory per warp and
+// shrinks to 8 blocks (lane (r,u): blocks u and u + 4): 13.4 / 11.5 KB of shared memory per warp and
 // <= 128 registers, i.e. 16 warps per SM instead of 12 / 10.
+// The eight boxes of a tile are issued by ONE elected lane from warp-uniform operands (the block
+// coordinates are broadcast with shuffles; blocks past the right edge fetch a zero box so that the
+// sequence has no branches): eight back-to-back UTMALDG on distinct uniform registers.  Issued from
+// eight lanes, the compiler serialises them in a loop whose every turn waits for the previous copy
+// to release its operands (K1p 0.365 -> 0.345 ms per 32 frames).  The other transfers of a tile
+// stay 1-D bulk copies (current rows, scan blocks, stores): moving them to tensor boxes as well
+// (66 x 8 row box, {36,6,4,1} / {66,1,8,1} clipped stores: 11 instead of 24 bulk operations per
+// tile) measured SLOWER (K1p 0.355, K2p 0.245 against 0.345 / 0.228 ms) and was dropped.
 // ================================================================================================
 constexpr int kP3Blocks = 8;
 constexpr int kP3Pitch = 528;                         // bytes per IN row: 8 blocks * 64 + 16 (== 16 mod 128)
@@ -1409,45 +1417,64 @@ constexpr int kP3TU = 136;                            // doubles per u-plane: 16
 constexpr int kP3Trans = 4 * kP3TU * 8;               // 4352
 constexpr int kP3Region = 4 * kStageU * 4;            // 3200: one round of scan staging (4 blocks x 3 tables)
 constexpr int kP3Header = 3584;                       // tables + barriers (a multiple of 128)
-constexpr int kP3ZzU = 136;                           // K2p IN staging: 2 blocks * 64 ints + 8 pad per u
-constexpr int kP3ZzIn = 4 * kP3ZzU * 4;               // 2176
-__host__ __device__ constexpr int p3_fwd_buf(int regions) {
-    return (kP3Pred + kP3In + (regions * kP3Region > kP3Trans ? regions * kP3Region : kP3Trans) + 127) / 128 * 128;
-}
-constexpr int kP3InvBuf = (kP3Pred + kP3ZzIn + kP3Trans + 127) / 128 * 128;    // 11648
+constexpr int kP3ZzBlk = 288;                         // K2p IN: one scan block (64 ints) + 8 pad (blocks land 32 B apart mod 128)
+constexpr int kP3ZzIn = kP3Blocks * kP3ZzBlk;         // 2304
+constexpr int kP3FwdBuf = (kP3Pred + kP3In + kP3Trans + 127) / 128 * 128;      // 13696
+static_assert(kP3Region <= kP3Trans, "scan staging reuses the transposition buffer");
+constexpr int kP3InvBuf = (kP3Pred + kP3ZzIn + kP3Trans + 127) / 128 * 128;    // 11776
+static_assert(kP3Box % 128 == 0 && kP3FwdBuf % 128 == 0 && kP3InvBuf % 128 == 0 && kP3Header % 128 == 0, "tensor copies need 128-byte aligned shared addresses");
 static_assert(kP3In <= kP3Trans, "the output row tile reuses the transposition buffer");
 
 __device__ __forceinline__ void tma_box_g2s(uint32_t dst, const CUtensorMap *tm, int x, int y, int z, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  ::"r"(dst), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
 }
+// one lane of the (converged) warp, chosen by the hardware: tells the compiler that what follows runs once per warp,
+// so bulk copies with warp-uniform operands are issued straight from uniform registers
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 
-// lane 8 + b fetches the prediction of block b of the tile (its vector was loaded one tile ahead) and returns
-// the column parity sx & 1 of the block's window inside its box
-__device__ __forceinline__ int p3_gather(const CUtensorMap *tm, uint32_t pred_s, uint32_t bar, int lane, int nb,
-                                         int64_t mvidx, int sr, int Hi, int Wi, int by, int b0, int frame) {
+// Lanes 8..15: box coordinates of block (lane - 8) of a tile from its vector (motion.py:83-92).  bx is the even
+// column the box starts at, par the column parity sx & 1 of the block's window inside its box.
+__device__ __forceinline__ void p3_box(int lane, int nb, int64_t mvidx, int sr, int Hi, int Wi, int by, int b0,
+                                       int &bx, int &byy, int &par) {
     const int b = lane - 8;
-    int par = 0;
+    bx = -16; byy = -8; par = 0;                          // a box entirely outside the tensor: zero-filled
     if (b >= 0 && b < nb) {
         int dy, dx;
         mv_decode(mvidx, sr, dy, dx);
-        int sy = by * 8 + dy, sx = (b0 + b) * 8 + dx;
-        const bool ok = sy >= 0 && sy <= Hi - 8 && sx >= 0 && sx <= Wi - 8;
-        if (!ok) { sx = -16; sy = -8; }                  // a box entirely outside the tensor: zero-filled
-        par = sx & 1;
-        tma_box_g2s(pred_s + b * kP3Box, tm, sx - par, sy, frame, bar);
+        const int sy = by * 8 + dy, sx = (b0 + b) * 8 + dx;
+        if (sy >= 0 && sy <= Hi - 8 && sx >= 0 && sx <= Wi - 8) { par = sx & 1; bx = sx - par; byy = sy; }
     }
-    return par;
+}
+// Whole warp: broadcast the eight boxes' coordinates; one elected lane issues the copies from warp-uniform operands.
+// Always eight copies (blocks past the right edge fetch a zero box): one basic block, so the copies sit on distinct
+// uniform registers and do not wait on one another.
+__device__ __forceinline__ void p3_gather(const CUtensorMap *tm, uint32_t pred_s, uint32_t bar, int bx, int byy, int frame) {
+    int ux[kP3Blocks], uy[kP3Blocks];
+#pragma unroll
+    for (int b = 0; b < kP3Blocks; ++b) {
+        ux[b] = __shfl_sync(0xffffffffu, bx, 8 + b);
+        uy[b] = __shfl_sync(0xffffffffu, byy, 8 + b);
+    }
+    if (elect_one()) {
+#pragma unroll
+        for (int b = 0; b < kP3Blocks; ++b) tma_box_g2s(pred_s + b * kP3Box, tm, ux[b], uy[b], frame, bar);
+    }
 }
 
-template <int WARPS, int CTAS, int REGIONS>
+template <int WARPS, int CTAS>
 __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pframe_forward_tm(const FwdArgs a, const __grid_constant__ CUtensorMap tm_ref) {
-    constexpr int kBuf = p3_fwd_buf(REGIONS);
+    constexpr int kBuf = kP3FwdBuf;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_rt = reinterpret_cast<double *>(smem_raw);                       // [192]
     double *s_t = s_rt + 192;                                                   // [192]
     unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem_raw + 3072);   // [WARPS]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = uniform_warp_idx();
     unsigned char *pred_b = smem_raw + kP3Header + warp * kBuf;
     unsigned char *in_b = pred_b + kP3Pred;
     unsigned char *work_b = in_b + kP3In;
@@ -1473,7 +1500,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pframe_forward_tm(const Fw
         t_rd[h] = work_b + u * (kP3TU * 8) + r * 64 + ((h ^ (r >> 1)) << 4);           // + m*512
     }
 #pragma unroll
-    for (int v = 0; v < 8; ++v) zz_wr[v] = work_b + (u * kStageU + ZZ_ORDER[v * 8 + r]) * 4;   // + region + ch*256
+    for (int v = 0; v < 8; ++v) zz_wr[v] = work_b + (u * kStageU + ZZ_ORDER[v * 8 + r]) * 4;   // + ch*256
     const double *rt_l = s_rt + r, *t_l = s_t + r;
 
     const TileGeom &g = a.g;
@@ -1491,16 +1518,18 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pframe_forward_tm(const Fw
         const int b0 = ti.tx * kP3Blocks, b = lane - 8;
         return (b >= 0 && b < min(kP3Blocks, g.Wp - b0)) ? a.mv[(ti.frame * g.Hp + ti.by) * (int64_t)g.Wp + b0 + b] : 0;
     };
-    auto issue = [&](const TileIter &ti, int64_t mvidx) {        // whole warp
+    auto issue = [&](const TileIter &ti, int64_t mvidx) -> int {  // whole warp; returns the parity (lanes 8..15)
         const int b0 = ti.tx * kP3Blocks, nb = min(kP3Blocks, g.Wp - b0);
+        int bx, byy, par;
+        p3_box(lane, nb, mvidx, a.sr, Hi, Wi, ti.by, b0, bx, byy, par);
         fence_proxy_async();
-        if (lane == 0) mbar_expect_tx(bar, (uint32_t)nb * (512u + kP3Box));  // 8 rows of nb*64 bytes + nb boxes
+        if (lane == 0) mbar_expect_tx(bar, (uint32_t)nb * 512u + (uint32_t)kP3Pred);   // 8 rows of nb*64 bytes + 8 boxes
         __syncwarp();
-        if (lane < 8) {                                     // lane r copies current-frame row r
-            const double *src = a.img + ti.frame * a.frame_stride + ((int64_t)ti.by * 8 + lane) * row_elems + (int64_t)b0 * 8;
-            bulk_g2s(in_s + lane * kP3Pitch, src, (uint32_t)nb * 64u, bar);
-        }
-        return p3_gather(&tm_ref, pred_s, bar, lane, nb, mvidx, a.sr, Hi, Wi, ti.by, b0, (int)ti.frame);
+        if (lane < 8)                                           // lane r copies current-frame row r
+            bulk_g2s(in_s + lane * kP3Pitch, a.img + ti.frame * a.frame_stride + ((int64_t)ti.by * 8 + lane) * row_elems + (int64_t)b0 * 8,
+                     (uint32_t)nb * 64u, bar);
+        p3_gather(&tm_ref, pred_s, bar, bx, byy, (int)ti.frame);
+        return par;
     };
 
     int64_t mv_nxt = load_mv(cur);
@@ -1558,11 +1587,9 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pframe_forward_tm(const Fw
         __syncwarp();
         // numpy broadcasting: the single luma channel is quantised with all three tables
         // (patchquant.py:59).  One round per sub-block m.
-        int32_t *outf = a.out + ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0) * 192;
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
-            const int reg = (REGIONS == 2) ? m * kP3Region : 0;
-            if (REGIONS == 1 && m == 1) { bulk_wait_read0(); __syncwarp(); }
+            if (m == 1) { bulk_wait_read0(); __syncwarp(); }     // round 0's stores have drained the staging area
             QuantGuard qg;
             {
                 double rtv[3][8];
@@ -1578,18 +1605,20 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pframe_forward_tm(const Fw
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch)
 #pragma unroll
-                    for (int v = 0; v < 8; ++v) *reinterpret_cast<int *>(zz_wr[v] + reg + ch * 256) = qv[ch][v];
+                    for (int v = 0; v < 8; ++v) *reinterpret_cast<int *>(zz_wr[v] + ch * 256) = qv[ch][v];
             }
             if (__builtin_expect(qg.risky(), 0)) {
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch)
 #pragma unroll
                     for (int v = 0; v < 8; ++v)
-                        *reinterpret_cast<int *>(zz_wr[v] + reg + ch * 256) = quantize_exact_f64(x[m][v], t_l[ch * 64 + v * 8]);
+                        *reinterpret_cast<int *>(zz_wr[v] + ch * 256) = quantize_exact_f64(x[m][v], t_l[ch * 64 + v * 8]);
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane < 4 && lane + 4 * m < nb) bulk_s2g(outf + (lane + 4 * m) * 192, work_s + reg + lane * (kStageU * 4), 768u);
+            if (lane < 4 && lane + 4 * m < nb)            // lane u stores the 3 scan blocks of image block u + 4m
+                bulk_s2g(a.out + ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0 + lane + 4 * m) * 192,
+                         work_s + lane * (kStageU * 4), 768u);
             bulk_commit();                                // every lane commits (possibly empty) groups: counts stay in step
         }
         cur = nxt;
@@ -1606,7 +1635,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pframe_inverse_tm(const In
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_tT = reinterpret_cast<double *>(smem_raw);                        // [64] luminance table, transposed
     unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem_raw + 3072);   // [2 * WARPS]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = uniform_warp_idx();
     unsigned char *pred_b = smem_raw + kP3Header + warp * kP3InvBuf;
     unsigned char *in_b = pred_b + kP3Pred;
     unsigned char *work_b = in_b + kP3ZzIn;
@@ -1624,7 +1653,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pframe_inverse_tm(const In
     const unsigned char *t_rd[4];
     const unsigned char *p_rd = pred_b + u * kP3Box + r * 8;                    // + m*4*kP3Box + parity*8 + i*80
 #pragma unroll
-    for (int j = 0; j < 8; ++j) q_rd[j] = in_b + (u * kP3ZzU + ZZ_ORDER[r * 8 + j]) * 4;     // + m*256
+    for (int j = 0; j < 8; ++j) q_rd[j] = in_b + u * kP3ZzBlk + ZZ_ORDER[r * 8 + j] * 4;     // + m * 4 * kP3ZzBlk
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
         t_wr[h] = work_b + u * (kP3TU * 8) + ((((r >> 1) ^ h) << 1) + (r & 1)) * 8;
@@ -1648,22 +1677,22 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pframe_inverse_tm(const In
         const int b0 = ti.tx * kP3Blocks, b = lane - 8;
         return (b >= 0 && b < min(kP3Blocks, g.Wp - b0)) ? a.mv[(ti.frame * g.Hp + ti.by) * (int64_t)g.Wp + b0 + b] : 0;
     };
-    auto issue_in = [&](const TileIter &ti) {               // scan channel 0 of block `lane` (stride Czz*64 ints)
+    auto issue_in = [&](const TileIter &ti) {               // lane b: scan channel 0 of block b (stride Czz*64 ints)
         const int b0 = ti.tx * kP3Blocks, nb = min(kP3Blocks, g.Wp - b0);
         fence_proxy_async();
         if (lane == 0) mbar_expect_tx(bar_in, (uint32_t)nb * 256u);
         __syncwarp();
-        if (lane < nb) {
-            const int32_t *zsrc = a.zz + ((ti.frame * g.Hp + ti.by) * (int64_t)g.Wp + b0 + lane) * a.Czz * 64;
-            bulk_g2s(in_s + ((lane & 3) * kP3ZzU + (lane >> 2) * 64) * 4, zsrc, 256u, bar_in);
-        }
+        if (lane < nb)
+            bulk_g2s(in_s + lane * kP3ZzBlk, a.zz + ((ti.frame * g.Hp + ti.by) * (int64_t)g.Wp + b0 + lane) * a.Czz * 64, 256u, bar_in);
     };
-    auto issue_pred = [&](const TileIter &ti, int64_t mvidx) {
+    auto issue_pred = [&](const TileIter &ti, int64_t mvidx) -> int {
         const int b0 = ti.tx * kP3Blocks, nb = min(kP3Blocks, g.Wp - b0);
+        int bx, byy, par;
+        p3_box(lane, nb, mvidx, a.sr, Hi, Wi, ti.by, b0, bx, byy, par);
         fence_proxy_async();
-        if (lane == 0) mbar_expect_tx(bar_p, (uint32_t)nb * kP3Box);
-        __syncwarp();
-        return p3_gather(&tm_ref, pred_s, bar_p, lane, nb, mvidx, a.sr, Hi, Wi, ti.by, b0, (int)ti.frame);
+        if (elect_one()) mbar_expect_tx(bar_p, (uint32_t)kP3Pred);
+        p3_gather(&tm_ref, pred_s, bar_p, bx, byy, (int)ti.frame);
+        return par;
     };
 
     int64_t mv_cur = load_mv(cur);
@@ -1681,7 +1710,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pframe_inverse_tm(const In
 #pragma unroll
         for (int m = 0; m < 2; ++m)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) q[m][j] = *reinterpret_cast<const int *>(q_rd[j] + m * 256);
+            for (int j = 0; j < 8; ++j) q[m][j] = *reinterpret_cast<const int *>(q_rd[j] + m * (4 * kP3ZzBlk));
         __syncwarp();
         mv_cur = mv_nxt;
         if (it + 1 < my_tiles) {
@@ -1887,22 +1916,18 @@ static bool use_v1() {            // A/B switch for profiling: IVC_FUSED_V1=1 se
     return v;
 }
 
-// P-frame kernel generation: IVC_PFRAME=2 keeps the cp.async gather (v2); IVC_PFRAME=3r2 selects the v3 forward
-// kernel with two staging regions (14 warps per SM).  Default: v3, one region, 16 warps.
-static int pframe_variant() {
-    static const int v = [] {
-        const char *e = getenv("IVC_PFRAME");
-        if (!e || !e[0]) return 3;
-        if (e[0] == '2') return 2;
-        return (e[0] == '3' && e[1] == 'r' && e[2] == '2') ? 32 : 3;
-    }();
+// P-frame kernel generation: IVC_PFRAME=2 keeps the cp.async gather (v2, also the fallback when the reference planes
+// cannot be described by a tensor map); default: v3, tensor-map gather, 16 warps per SM.
+static bool pframe_v3() {
+    static const bool v = [] { const char *e = getenv("IVC_PFRAME"); return !(e && e[0] == '2'); }();
     return v;
 }
 
-// Tensor map of the reference planes for the v3 gather: float64 [n, H, W], 10 x 8 boxes, zero fill.
-// Returns false when the driver entry point is missing or the planes do not meet the unit's alignment rules
-// (base 16-byte aligned; W is a multiple of 8, so the row pitch always is) -- the caller then uses the v2 kernels.
-static bool make_ref_map(CUtensorMap *tm, const void *ref, int64_t n, int64_t H, int64_t W) {
+// Tensor maps for the v3 P-frame kernels (no interleave, no swizzle, zero fill).  make_map returns false when the
+// driver entry point is missing or the view does not meet the unit's rules (base and strides multiples of 16 bytes,
+// extents below 2^32, strides below 2^40) -- the caller then uses the v2 kernels.
+static bool make_map(CUtensorMap *tm, CUtensorMapDataType dt, int elem, int rank, const void *base, const uint64_t *dims,
+                     const uint64_t *strides /* bytes, rank - 1 */, const uint32_t *box) {
     typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1914,15 +1939,28 @@ static bool make_ref_map(CUtensorMap *tm, const void *ref, int64_t n, int64_t H,
             fn = nullptr;
         return (EncodeTiled)fn;
     }();
-    if (!encode || !ref || ((uintptr_t)ref & 15) || n < 1 || n > 0x7fffffff || H > 0x7fffffff || W > 0x7fffffff ||
-        (uint64_t)H * (uint64_t)W * 8ull >= (1ull << 40))
-        return false;
-    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
-    const cuuint64_t strides[2] = {(cuuint64_t)W * 8, (cuuint64_t)H * (cuuint64_t)W * 8};
-    const cuuint32_t box[3] = {10, 8, 1}, estr[3] = {1, 1, 1};
-    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(ref), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    if (!encode || !base || ((uintptr_t)base & 15)) return false;
+    cuuint64_t d[5], st[4];
+    cuuint32_t b[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        if (dims[i] < 1 || dims[i] > 0xffffffffull || box[i] < 1 || box[i] > 256) return false;
+        d[i] = dims[i]; b[i] = box[i]; es[i] = 1;
+    }
+    for (int i = 0; i + 1 < rank; ++i) {
+        if ((strides[i] & 15) || strides[i] >= (1ull << 40)) return false;
+        st[i] = strides[i];
+    }
+    if (((uint64_t)box[0] * elem) & 15) return false;
+    return encode(tm, dt, (cuuint32_t)rank, const_cast<void *>(base), d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// float64 planes [n, H, W] (frame stride in elements), boxes of bw x 8 elements
+static bool make_plane_map(CUtensorMap *tm, const void *base, int64_t n, int64_t H, int64_t W, int64_t frame_stride, int bw) {
+    if (n > 0x7fffffff || H > 0x7fffffff || W > 0x7fffffff) return false;       // coordinates are int32
+    const uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)n};
+    const uint64_t strides[2] = {(uint64_t)W * 8, (uint64_t)frame_stride * 8};
+    const uint32_t box[3] = {(uint32_t)bw, 8, 1};
+    return make_map(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, 3, base, dims, strides, box);
 }
 
 static int grid_for(int64_t work_items, int per_cta, int device, int ctas_per_sm) {
@@ -1957,19 +1995,12 @@ cudaError_t launch_forward(int device, cudaStream_t st, const void *img, int64_t
     const size_t smem = 2 * 192 * sizeof(double) + kWarpsPerCta * kWarpBufBytes;
     const int grid = grid_for(a.g.total_tiles, kWarpsPerCta, device, 2);
     cudaError_t e;
-    CUtensorMap tm;
-    if (pframe && !use_v1() && pframe_variant() != 2 && make_ref_map(&tm, ref, n, H, W)) {
-        FwdArgs a3 = a;
-        a3.g = make_geom(n, H, W, 1, kP3Blocks);
-        if (pframe_variant() == 32) {
-            const size_t smem3 = kP3Header + (size_t)14 * p3_fwd_buf(2);
-            if ((e = set_smem(k_pframe_forward_tm<14, 1, 2>, smem3)) != cudaSuccess) return e;
-            k_pframe_forward_tm<14, 1, 2><<<grid_for(a3.g.total_tiles, 14, device, 1), 14 * 32, smem3, st>>>(a3, tm);
-        } else {
-            const size_t smem3 = kP3Header + (size_t)8 * p3_fwd_buf(1);
-            if ((e = set_smem(k_pframe_forward_tm<8, 2, 1>, smem3)) != cudaSuccess) return e;
-            k_pframe_forward_tm<8, 2, 1><<<grid_for(a3.g.total_tiles, 8, device, 2), 8 * 32, smem3, st>>>(a3, tm);
-        }
+    CUtensorMap tm_ref;
+    if (pframe && !use_v1() && pframe_v3() && make_plane_map(&tm_ref, ref, n, H, W, H * W, 10)) {
+        a.g = make_geom(n, H, W, 1, kP3Blocks);
+        const size_t smem3 = kP3Header + (size_t)8 * kP3FwdBuf;
+        if ((e = set_smem(k_pframe_forward_tm<8, 2>, smem3)) != cudaSuccess) return e;
+        k_pframe_forward_tm<8, 2><<<grid_for(a.g.total_tiles, 8, device, 2), 8 * 32, smem3, st>>>(a, tm_ref);
     } else if (pframe && !use_v1()) {
         const size_t smem2 = 3200 + (size_t)kPfWarps * kPfBuf;
         if ((e = set_smem(k_pframe_forward_tma, smem2)) != cudaSuccess) return e;
@@ -2017,6 +2048,7 @@ cudaError_t launch_inverse(int device, cudaStream_t st, const int32_t *zz, int64
     const size_t smem = 192 * sizeof(double) + kWarpsPerCta * kWarpBufBytes;
     const int grid = grid_for(a.g.total_tiles, kWarpsPerCta, device, 2);
     cudaError_t e;
+    CUtensorMap tm_ref;
     if (mode == 3) {                                         // C = 3 with the colour transform in the store
         const size_t smem2 = 1664 + (size_t)kWarpsPerCta * kInvBuf;
         if ((e = set_smem(k_inverse_c3_tma<0, true>, smem2)) != cudaSuccess) return e;
@@ -2031,11 +2063,11 @@ cudaError_t launch_inverse(int device, cudaStream_t st, const int32_t *zz, int64
     } else if (mode == 1) {
         if ((e = set_smem(k_inverse<1>, smem)) != cudaSuccess) return e;
         k_inverse<1><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
-    } else if (CUtensorMap tm; !use_v1() && !pred && pframe_variant() != 2 && make_ref_map(&tm, ref, n, Hp * 8, Wp * 8)) {
+    } else if (!use_v1() && !pred && pframe_v3() && make_plane_map(&tm_ref, ref, n, Hp * 8, Wp * 8, Hp * Wp * 64, 10)) {
         a.g = make_geom(n, Hp * 8, Wp * 8, Czz, kP3Blocks);
         const size_t smem3 = kP3Header + (size_t)8 * kP3InvBuf;
         if ((e = set_smem(k_pframe_inverse_tm<8, 2>, smem3)) != cudaSuccess) return e;
-        k_pframe_inverse_tm<8, 2><<<grid_for(a.g.total_tiles, 8, device, 2), 8 * 32, smem3, st>>>(a, tm);
+        k_pframe_inverse_tm<8, 2><<<grid_for(a.g.total_tiles, 8, device, 2), 8 * 32, smem3, st>>>(a, tm_ref);
     } else if (!use_v1()) {
         const size_t smem2 = 3200 + (size_t)kPiWarps * kPiBuf;
         if ((e = set_smem(k_pframe_inverse_tma, smem2)) != cudaSuccess) return e;

@@ -303,6 +303,44 @@ def test_pframe_out_of_frame_vectors_vs_oracle():
     assert np.array_equal(coder.inverse(zz, ref=ref, mv=mv), O.pframe_inverse(zz_o[:, :, :1], pred_o, tab))
 
 
+def test_pframe_every_vector_ragged_batch_vs_oracle():
+    """Every vector of the +-4 window (even and odd dx: the tensor-map gather fetches boxes at even columns only),
+    three frames, a width that leaves a ragged last tile (11 blocks = 8 + 3)."""
+    rng = np.random.default_rng(33)
+    F, H, W, sr = 3, 40, 88, 4
+    ref = rng.uniform(0, 255, size=(F, H, W))
+    cur = rng.uniform(0, 255, size=(F, H, W))
+    mv = (np.arange(F * (H // 8) * (W // 8)) * 7 % 81).reshape(F, H // 8, W // 8, 1)
+    coder = ivc.PFrameBlockCoder(quantization_scale=1.0, search_range=sr)
+    tab = coder.quant.get_quantization_table()
+    d = lambda a: torch.from_numpy(a).cuda()
+    zz, pred = coder.forward(d(cur), d(ref), d(mv), return_prediction=True)
+    rec = coder.inverse(zz, ref=d(ref), mv=d(mv))
+    for f in range(F):
+        pred_o, zz_o = O.pframe_forward(cur[f], ref[f], mv[f], sr, tab)
+        assert np.array_equal(pred[f].cpu().numpy(), pred_o) and np.array_equal(zz[f].cpu().numpy(), zz_o)
+        assert np.array_equal(rec[f].cpu().numpy(), O.pframe_inverse(zz_o[:, :, :1], pred_o, tab))
+
+
+def test_pframe_reference_plane_only_8_byte_aligned():
+    """A reference plane whose base is not 16-byte aligned cannot be described by a tensor map: the cp.async
+    gather takes over, same results."""
+    rng = np.random.default_rng(34)
+    H, W, sr = 24, 72, 4
+    buf = torch.from_numpy(rng.uniform(0, 255, size=H * W + 1)).cuda()
+    ref_t = buf[1:].view(H, W)
+    assert ref_t.data_ptr() % 16 == 8
+    cur = rng.uniform(0, 255, size=(H, W))
+    mv = rng.integers(0, 81, size=(H // 8, W // 8, 1))
+    coder = ivc.PFrameBlockCoder(quantization_scale=0.4, search_range=sr)
+    tab = coder.quant.get_quantization_table()
+    pred_o, zz_o = O.pframe_forward(cur, ref_t.cpu().numpy(), mv, sr, tab)
+    zz = coder.forward(torch.from_numpy(cur).cuda(), ref_t, torch.from_numpy(mv).cuda())
+    assert np.array_equal(zz.cpu().numpy(), zz_o)
+    rec = coder.inverse(zz, ref=ref_t, mv=torch.from_numpy(mv).cuda())
+    assert np.array_equal(rec.cpu().numpy(), O.pframe_inverse(zz_o[:, :, :1], pred_o, tab))
+
+
 # ---------------------------------------------------------------- full-size configs
 def test_cfg1_full_size_hashes():
     """cfg1 (512x768 RGB->YCbCr, qScale 0.07/1/4.5): hashes recorded from the real reference."""
