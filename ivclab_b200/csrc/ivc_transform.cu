@@ -17,6 +17,7 @@
 // HBM traffic is exactly the algorithmic bytes (each input element read once, each output written
 // once); arithmetic is FP64 (14 rounded operations per sample for the 2-D transform).
 #include <cstdlib>
+#include <type_traits>
 #include <cuda.h>          // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
 #include "ivc_dct.cuh"
 #include "ivc_color.cuh"
@@ -1487,7 +1488,14 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pframe_forward_tm(const Fw
     }
     if (lane == 0) mbar_init(bar, 1);
     fence_mbar_init();
-    __syncthreads();
+    // PatchQuant's table is [lum, chrom, chrom] (patchquant.py:40): when tables 1 and 2 hold the same bits, the third
+    // quantised copy of a block IS the second -- computed once, stored twice
+    bool same = true;
+    if (threadIdx.x < 64) {
+        const double t1 = load_table_elem(a.table, a.table_dtype, 64 + threadIdx.x), t2 = load_table_elem(a.table, a.table_dtype, 128 + threadIdx.x);
+        same = __double_as_longlong(t1) == __double_as_longlong(t2);
+    }
+    const bool chroma_twice = __syncthreads_and(same) != 0;
 
     const int r = lane & 7, u = lane >> 3;
     const unsigned char *rd_in = in_b + r * kP3Pitch + u * 64;                  // + m*256 + 16k
@@ -1590,30 +1598,32 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pframe_forward_tm(const Fw
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
             if (m == 1) { bulk_wait_read0(); __syncwarp(); }     // round 0's stores have drained the staging area
-            QuantGuard qg;
-            {
-                double rtv[3][8];
+            const auto quantise = [&](auto nch_c) {       // NCH tables computed; the last one also stored as channel 2
+                constexpr int NCH = decltype(nch_c)::value;
+                QuantGuard qg;
+                double rtv[NCH][8];
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch)
+                for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
                     for (int v = 0; v < 8; ++v) rtv[ch][v] = rt_l[ch * 64 + v * 8];
-                int qv[3][8];
+                int qv[NCH][8];
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch)
+                for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
                     for (int v = 0; v < 8; ++v) qv[ch][v] = qg.q(x[m][v], rtv[ch][v]);
+                if (__builtin_expect(qg.risky(), 0)) {
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+                        for (int v = 0; v < 8; ++v) qv[ch][v] = quantize_exact_f64(x[m][v], t_l[ch * 64 + v * 8]);
+                }
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch)
 #pragma unroll
-                    for (int v = 0; v < 8; ++v) *reinterpret_cast<int *>(zz_wr[v] + ch * 256) = qv[ch][v];
-            }
-            if (__builtin_expect(qg.risky(), 0)) {
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch)
-#pragma unroll
-                    for (int v = 0; v < 8; ++v)
-                        *reinterpret_cast<int *>(zz_wr[v] + ch * 256) = quantize_exact_f64(x[m][v], t_l[ch * 64 + v * 8]);
-            }
+                    for (int v = 0; v < 8; ++v) *reinterpret_cast<int *>(zz_wr[v] + ch * 256) = qv[ch < NCH ? ch : NCH - 1][v];
+            };
+            if (chroma_twice) quantise(std::integral_constant<int, 2>{});
+            else quantise(std::integral_constant<int, 3>{});
             fence_proxy_async();
             __syncwarp();
             if (lane < 4 && lane + 4 * m < nb)            // lane u stores the 3 scan blocks of image block u + 4m

@@ -341,6 +341,26 @@ def test_pframe_reference_plane_only_8_byte_aligned():
     assert np.array_equal(rec.cpu().numpy(), O.pframe_inverse(zz_o[:, :, :1], pred_o, tab))
 
 
+def test_pframe_forward_three_distinct_tables_through_the_abi():
+    """PatchQuant always hands over [lum, chrom, chrom]; the C ABI takes any [3, 64] table, and the kernel must not
+    assume channels 1 and 2 are equal (it only computes them once when they are)."""
+    from ivclab_b200 import _lib
+    from ivclab_b200._runtime import dev_index, stream_ptr
+    rng = np.random.default_rng(35)
+    H, W, sr = 24, 136, 4
+    ref, cur = rng.uniform(0, 255, size=(H, W)), rng.uniform(0, 255, size=(H, W))
+    mv = rng.integers(0, 81, size=(H // 8, W // 8, 1))
+    tab = rng.uniform(0.5, 40.0, size=(3, 8, 8))
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    dc, dr, dm, dt = d(cur), d(ref), d(mv), d(tab)
+    zz = torch.empty((H // 8, W // 8, 3, 64), dtype=torch.int32, device="cuda")
+    st = _lib.lib.ivc_pframe_forward(dev_index(dc), stream_ptr(dc.device), dc.data_ptr(), dr.data_ptr(), dm.data_ptr(),
+                                     _lib.F64, 1, H, W, sr, dt.data_ptr(), _lib.F64, None, zz.data_ptr())
+    _lib.check(st, "ivc_pframe_forward")
+    _, zz_o = O.pframe_forward(cur, ref, mv, sr, tab)
+    assert np.array_equal(zz.cpu().numpy(), zz_o)
+
+
 # ---------------------------------------------------------------- full-size configs
 def test_cfg1_full_size_hashes():
     """cfg1 (512x768 RGB->YCbCr, qScale 0.07/1/4.5): hashes recorded from the real reference."""
