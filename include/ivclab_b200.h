@@ -171,7 +171,9 @@ int ivc_mc_reconstruct(int device, void *stream,
 
 /* ---- a15 fused: P-frame encoder half (videocodec.py:68-71 + intracodec.py:66-75) -------------
  * pred = MC(ref, mv); residual = cur - pred; zz = flatten(quantize(dct(patch(residual)))).
- * cur/ref: [n_frames,H,W] F64.  pred_out may be NULL.  zz_out: [n_frames,Hp,Wp,3,64] int32. */
+ * cur/ref: [n_frames,H,W] F64.  pred_out may be NULL.  zz_out: [n_frames,Hp,Wp,3,64] int32.
+ * cur, zz_out, pred_out must be 16-byte aligned; ref needs 8 bytes only (a 16-byte aligned ref takes the faster
+ * tensor-map gather, any other the cp.async gather: same results). */
 int ivc_pframe_forward(int device, void *stream,
                        const void *cur, const void *ref, const int64_t *mv, int dtype,
                        int64_t n_frames, int64_t H, int64_t W, int search_range,
