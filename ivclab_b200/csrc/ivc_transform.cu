@@ -34,10 +34,13 @@ constexpr int kRowPitch = 98;        // 96 doubles of tile row + 2 pad: 784 B ==
 constexpr int kTJ = 10;              // transposition buffer: T[u][m*8+j][r], 80-byte rows
 constexpr int kTU = 248;             // 24 rows * 10 + 8 pad: u-planes land 64 B apart (mod 128)
 constexpr int kStageU = 200;         // int32 staging: 3 chunks * 64 ints + 8 pad per u
+constexpr int kStageUF = 204;        // ... of the TMA forward kernels: +12 puts the zig-zag SCATTER of a warp on 16 instead of 20
+                                     // bank wavefronts per 8 stores (the inverse kernels' GATHER is best at +8)
 
 static_assert(8 * kRowPitch * 8 <= kWarpBufBytes, "row tile must fit");
 static_assert(4 * kTU * 8 <= kWarpBufBytes, "transposition buffer must fit");
 static_assert(4 * kStageU * 4 <= kWarpBufBytes, "staging must fit");
+static_assert((kStageUF * 4) % 16 == 0, "bulk-store sources are 16-byte aligned");
 
 struct TileGeom {
     int64_t n_frames, H, W;          // pixels
@@ -585,7 +588,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_c3_tma(const F
         t_rd[h] = work_b + u * (kTU2 * 8) + r * 64 + ((h ^ (r >> 1)) << 4);           // + m*512
     }
 #pragma unroll
-    for (int v = 0; v < 8; ++v) zz_wr[v] = work_b + (u * kStageU + ZZ_ORDER[v * 8 + r]) * 4;   // + m*256
+    for (int v = 0; v < 8; ++v) zz_wr[v] = work_b + (u * kStageUF + ZZ_ORDER[v * 8 + r]) * 4;   // + m*256
     const double *rt_l = s_rt + r, *t_l = s_t + r;
 
     const TileGeom &g = a.g;
@@ -681,7 +684,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_c3_tma(const F
             const int b0 = cur.tx * 4, nb = min(4, g.Wp - b0);
             if (lane < nb) {                              // lane u stores the 3 scan blocks of image block u
                 int32_t *outf = a.out + ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0 + lane) * 192;
-                bulk_s2g(outf, work_s + lane * (kStageU * 4), 768u);
+                bulk_s2g(outf, work_s + lane * (kStageUF * 4), 768u);
                 bulk_commit();
             }
         }
@@ -726,7 +729,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_rgb8_tma(const
         t_rd[h] = work_b + u * (kTU2 * 8) + r * 64 + ((h ^ (r >> 1)) << 4);           // + m*512
     }
 #pragma unroll
-    for (int v = 0; v < 8; ++v) zz_wr[v] = work_b + (u * kStageU + ZZ_ORDER[v * 8 + r]) * 4;   // + m*256
+    for (int v = 0; v < 8; ++v) zz_wr[v] = work_b + (u * kStageUF + ZZ_ORDER[v * 8 + r]) * 4;   // + m*256
     const double *rt_l = s_rt + r, *t_l = s_t + r;
 
     const TileGeom &g = a.g;
@@ -827,7 +830,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_rgb8_tma(const
             const int b0 = cur.tx * 4, nb = min(4, g.Wp - b0);
             if (lane < nb) {                              // lane u stores the 3 scan blocks of image block u
                 int32_t *outf = a.out + ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0 + lane) * 192;
-                bulk_s2g(outf, work_s + lane * (kStageU * 4), 768u);
+                bulk_s2g(outf, work_s + lane * (kStageUF * 4), 768u);
                 bulk_commit();
             }
         }
@@ -1416,7 +1419,7 @@ constexpr int kP3Pred = kP3Blocks * kP3Box;           // 5120: block-major boxes
 constexpr int kP3In = 8 * kP3Pitch;                   // 4224
 constexpr int kP3TU = 136;                            // doubles per u-plane: 16 rows * 8 + 8 skew (64 B)
 constexpr int kP3Trans = 4 * kP3TU * 8;               // 4352
-constexpr int kP3Region = 4 * kStageU * 4;            // 3200: one round of scan staging (4 blocks x 3 tables)
+constexpr int kP3Region = 4 * kStageUF * 4;           // 3264: one round of scan staging (4 blocks x 3 tables)
 constexpr int kP3Header = 3584;                       // tables + barriers (a multiple of 128)
 constexpr int kP3ZzBlk = 288;                         // K2p IN: one scan block (64 ints) + 8 pad (blocks land 32 B apart mod 128)
 constexpr int kP3ZzIn = kP3Blocks * kP3ZzBlk;         // 2304
@@ -1508,7 +1511,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pframe_forward_tm(const Fw
         t_rd[h] = work_b + u * (kP3TU * 8) + r * 64 + ((h ^ (r >> 1)) << 4);           // + m*512
     }
 #pragma unroll
-    for (int v = 0; v < 8; ++v) zz_wr[v] = work_b + (u * kStageU + ZZ_ORDER[v * 8 + r]) * 4;   // + ch*256
+    for (int v = 0; v < 8; ++v) zz_wr[v] = work_b + (u * kStageUF + ZZ_ORDER[v * 8 + r]) * 4;   // + ch*256
     const double *rt_l = s_rt + r, *t_l = s_t + r;
 
     const TileGeom &g = a.g;
@@ -1628,7 +1631,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pframe_forward_tm(const Fw
             __syncwarp();
             if (lane < 4 && lane + 4 * m < nb)            // lane u stores the 3 scan blocks of image block u + 4m
                 bulk_s2g(a.out + ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0 + lane + 4 * m) * 192,
-                         work_s + lane * (kStageU * 4), 768u);
+                         work_s + lane * (kStageUF * 4), 768u);
             bulk_commit();                                // every lane commits (possibly empty) groups: counts stay in step
         }
         cur = nxt;
