@@ -19,7 +19,7 @@ from .entropy import ZeroRunCoder, stats_marg, symbol_histogram, symbol_minmax
 from .image import IntraCodec
 from .install import inject, install
 from .quantization import PatchQuant
-from .signal import DiscreteCosineTransform, rgb2ycbcr, ycbcr2rgb
+from .signal import DiscreteCosineTransform, luma8_from_rgb8, rgb2ycbcr, ycbcr2rgb
 from .streaming import StreamedCoder
 from .utils import Patcher, ZigZag, calc_mse, calc_psnr, frame_sse, frame_sse_rgb8_vs_ycbcr
 from .video import ClosedLoopLumaCoder, MotionCompensator
@@ -27,5 +27,5 @@ from .video import ClosedLoopLumaCoder, MotionCompensator
 __version__ = "0.1.0"
 __all__ = ["DiscreteCosineTransform", "PatchQuant", "ZigZag", "Patcher", "MotionCompensator",
            "IntraBlockCoder", "PFrameBlockCoder", "IntraCodec", "ClosedLoopLumaCoder", "ZeroRunCoder", "calc_mse", "calc_psnr",
-           "frame_sse", "frame_sse_rgb8_vs_ycbcr", "rgb2ycbcr", "ycbcr2rgb", "StreamedCoder", "stats_marg", "symbol_minmax", "symbol_histogram",
+           "frame_sse", "frame_sse_rgb8_vs_ycbcr", "rgb2ycbcr", "ycbcr2rgb", "luma8_from_rgb8", "StreamedCoder", "stats_marg", "symbol_minmax", "symbol_histogram",
            "install", "inject"]

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "_C", "libivcb200.so")
 
 # element type codes (include/ivclab_b200.h)
 U8, I32, F32, F64, I64, I16 = 0, 1, 2, 3, 4, 5
-ABI_VERSION = 2            # include/ivclab_b200.h IVC_ABI_VERSION (2: entry points added in round 1, zero-run write gained a length)
+ABI_VERSION = 3            # include/ivclab_b200.h IVC_ABI_VERSION (2: entry points added in round 1, zero-run write gained a length; 3: ivc_rgb8_to_luma8)
 ME_AUTO, ME_EXACT, ME_INT = 0, 1, 2
 SSE_RGB8_AS_YCBCR = 103
 DIST_RGB, DIST_YCBCR = 1, 2
@@ -62,6 +62,7 @@ SIGNATURES = {
     "ivc_symbol_histogram": (_i, [_i, _p, _p, _i, _i64, _i64, _i64, _i64, _p]),
     "ivc_rgb2ycbcr": (_i, [_i, _p, _p, _i, _i64, _p]),
     "ivc_ycbcr2rgb": (_i, [_i, _p, _p, _i64, _p]),
+    "ivc_rgb8_to_luma8": (_i, [_i, _p, _p, _i64, _p]),
     "ivc_intra_forward_rgb8": (_i, [_i, _p, _p, _i64, _i64, _i64, _i64, _p, _i, _p]),
 }
 

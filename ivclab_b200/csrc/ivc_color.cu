@@ -44,6 +44,43 @@ __global__ void __launch_bounds__(256) k_ycbcr2rgb(const ColorArgs a) {
     }
 }
 
+// uint8 RGB -> uint8 luma plane: clip(rint(Y), 0, 255) with Y exactly as rgb2ycbcr computes it (rint = round half to
+// even = np.round).  What the video codecs code is Y = rgb2ycbcr(frame)[..., 0] (videocodec.py:38); deriving the
+// plane on the device means a host-fed pipeline uploads 3 bytes per pixel instead of 4.  Four pixels per thread:
+// three 32-bit loads, one 32-bit store.
+__global__ void __launch_bounds__(256) k_rgb8_luma8(const unsigned char *__restrict__ rgb, unsigned char *__restrict__ out, int64_t npix,
+                                                    int vec) {
+    const auto luma = [](unsigned r, unsigned g, unsigned b) {
+        double y, cb, cr;
+        rgb2ycbcr_px((double)r, (double)g, (double)b, y, cb, cr);
+        const int v = __double2int_rn(y);
+        return (unsigned)min(max(v, 0), 255);
+    };
+    const int64_t ngrp = vec ? npix / 4 : 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ngrp; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned *p = reinterpret_cast<const unsigned *>(rgb) + 3 * i;
+        const unsigned w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);       // r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
+        const unsigned y0 = luma(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u);
+        const unsigned y1 = luma(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u);
+        const unsigned y2 = luma((w1 >> 16) & 255u, w1 >> 24, w2 & 255u);
+        const unsigned y3 = luma((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24);
+        reinterpret_cast<unsigned *>(out)[i] = y0 | (y1 << 8) | (y2 << 16) | (y3 << 24);
+    }
+    for (int64_t i = 4 * ngrp + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (unsigned char)luma(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+}
+
+cudaError_t launch_rgb8_luma8(int device, cudaStream_t st, const void *rgb, int64_t npix, void *out) {
+    if (npix == 0) return cudaSuccess;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    int64_t grid = (npix / 4 + 255) / 256 + 1;
+    if (grid > (int64_t)sms * 16) grid = (int64_t)sms * 16;
+    const int vec = (((uintptr_t)rgb | (uintptr_t)out) & 3) == 0;
+    k_rgb8_luma8<<<(unsigned)grid, 256, 0, st>>>((const unsigned char *)rgb, (unsigned char *)out, npix, vec);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_color(int device, cudaStream_t st, bool to_rgb, const void *in, int in_dtype, int64_t npix, double *out) {
     if (npix == 0) return cudaSuccess;
     int sms = 148;

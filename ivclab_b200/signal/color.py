@@ -8,7 +8,7 @@ import torch
 from .. import _lib
 from .._runtime import code, dev_index, stream_ptr, to_device, to_host
 
-__all__ = ["rgb2ycbcr", "ycbcr2rgb"]
+__all__ = ["rgb2ycbcr", "ycbcr2rgb", "luma8_from_rgb8"]
 
 
 def rgb2ycbcr(image):
@@ -34,4 +34,20 @@ def ycbcr2rgb(image):
     out = torch.empty_like(t)
     st = _lib.lib.ivc_ycbcr2rgb(dev_index(t), stream_ptr(t.device), t.data_ptr(), t.numel() // 3, out.data_ptr())
     _lib.check(st, "ivc_ycbcr2rgb")
+    return to_host(out, was_np)
+
+
+def luma8_from_rgb8(image, out=None):
+    """uint8 RGB [..., 3] -> uint8 luma plane ``clip(round(rgb2ycbcr(image)[..., 0]), 0, 255)`` (np.round: half to even):
+    the Y channel the video codecs code (ivclab/video/videocodec.py:38) in 8-bit form, computed on the device."""
+    t, was_np = to_device(image)
+    if t.ndim < 1 or t.shape[-1] != 3 or t.dtype != torch.uint8:
+        raise ValueError(f"expected uint8 [..., 3], got {t.dtype} {tuple(t.shape)}")
+    t = t.contiguous()
+    if out is None:
+        out = torch.empty(t.shape[:-1], dtype=torch.uint8, device=t.device)
+    elif out.dtype != torch.uint8 or out.numel() != t.numel() // 3 or not out.is_contiguous() or out.device != t.device:
+        raise ValueError("out must be a contiguous uint8 tensor with one element per pixel on the input's device")
+    st = _lib.lib.ivc_rgb8_to_luma8(dev_index(t), stream_ptr(t.device), t.data_ptr(), t.numel() // 3, out.data_ptr())
+    _lib.check(st, "ivc_rgb8_to_luma8")
     return to_host(out, was_np)

@@ -2,8 +2,10 @@
 and the results of chunk k-1 are downloaded, on three CUDA streams with pinned staging buffers.
 
 This is the form in which the path is fed from HOST memory (what ``bench.py`` reports as ``e2e``):
-uint8 RGB frames and uint8 luma planes go up (5 bytes per pixel), zero-run symbol streams, motion
-vectors and squared errors come back; the colour transform, both transform loops, the motion search,
+uint8 RGB frames and uint8 luma planes go up -- 5 bytes per pixel with explicit references, 4 in sequence
+mode, 3 when the luma plane is the Y channel of the RGB frame and is derived on the device, as the
+reference's video codecs do (``rgb2ycbcr(frame)[..., 0]``, videocodec.py:38) -- and zero-run symbol
+streams, motion vectors and squared errors come back; the colour transform, both transform loops, the motion search,
 the zero-run coder and the error reduction all run on the device in between.  Frames are independent
 (intra) or frame pairs (inter), so chunks never depend on each other.
 
@@ -22,6 +24,7 @@ import torch
 
 from . import _lib  # noqa: F401
 from .codec import IntraBlockCoder, PFrameBlockCoder
+from .signal.color import luma8_from_rgb8
 from .entropy import ZeroRunCoder
 from .utils.metrics import frame_sse
 
@@ -30,7 +33,7 @@ __all__ = ["StreamedCoder"]
 
 class _Slot:
     """Static device buffers of one pipeline slot, the graph that codes them and that graph's outputs."""
-    __slots__ = ("rgb", "cur", "ref", "graphs", "totals")
+    __slots__ = ("rgb", "cur", "ref", "graphs", "totals", "derive")
 
 
 class StreamedCoder:
@@ -74,13 +77,15 @@ class StreamedCoder:
                 "mv": pin((F, H // 8, W // 8, 1), torch.int64), "sse": pin((2, F), torch.float64)})
         return self._host[1]
 
-    def _device_slots(self, C, H, W, seq):
-        key = (C, H, W, seq)
+    def _device_slots(self, C, H, W, seq, derive=False):
+        key = (C, H, W, seq, derive)
         if self._slots is None or self._slots[0] != key:
             slots = []
             for _ in range(self.nslots):
                 s = _Slot()
-                s.rgb = torch.empty((C, H, W, 3), dtype=torch.uint8, device=self.device)
+                s.derive = derive
+                # derived luma: C + 1 RGB frames as well, frame 0 = the frame before the chunk (the source of its reference plane)
+                s.rgb = torch.empty((C + 1 if derive else C, H, W, 3), dtype=torch.uint8, device=self.device)
                 # sequence mode: one luma buffer of C+1 frames, frame 0 = the frame before the chunk (its reference)
                 s.cur = torch.empty((C + 1 if seq else C, H, W), dtype=torch.uint8, device=self.device)
                 s.ref = None if seq else torch.empty((C, H, W), dtype=torch.uint8, device=self.device)
@@ -106,9 +111,11 @@ class StreamedCoder:
     # ---- one chunk on the device -------------------------------------------------------------------
     def _code(self, s: _Slot, n: int):
         """Everything of a chunk that does not need a stream length on the host (current stream = compute stream)."""
-        d_rgb = s.rgb[:n]
+        d_rgb = s.rgb[1:n + 1] if s.derive else s.rgb[:n]
         if s.ref is None:                              # sequence mode: frame t is predicted from frame t-1
             luma8 = s.cur[:n + 1]
+            if s.derive:                               # the planes are the rounded Y channel of the RGB frames (videocodec.py:38)
+                luma8_from_rgb8(s.rgb[:n + 1], out=luma8)
             luma = luma8.double()
             d_ref, d_cur, r8, c8 = luma[:n], luma[1:], luma8[:n], luma8[1:]
         else:
@@ -155,24 +162,34 @@ class StreamedCoder:
         return bounds
 
     # ---- the pipeline ----------------------------------------------------------------------------
-    def run(self, rgb, cur, ref=None, first_ref=None):
+    def run(self, rgb, cur=None, ref=None, first_ref=None):
         """rgb [F,H,W,3] uint8, cur [F,H,W] uint8 luma planes -- pinned host tensors (numpy arrays are accepted and
         pinned once).  The P-frame references are either given frame by frame (``ref`` [F,H,W]) or implied by the
         sequence (``ref=None``): frame t is predicted from frame t-1 and frame 0 from ``first_ref`` [H,W] -- every
-        luma frame then crosses PCIe once instead of twice.  Returns host-side results: ``sym_intra`` /
+        luma frame then crosses PCIe once instead of twice.  ``cur=None`` (sequence mode only): the luma plane of a
+        frame is ``luma8_from_rgb8`` of its RGB frame, derived on the device -- only the RGB frames cross PCIe;
+        ``first_ref`` is then the RGB frame [H,W,3] before frame 0.  Returns host-side results: ``sym_intra`` /
         ``sym_inter`` (int32 streams and per-chunk lengths), ``mv`` [F,Hp,Wp,1] int64, ``sse`` [2,F] (intra on
         YCbCr, inter on luma)."""
         pinned = lambda x: (torch.from_numpy(x) if isinstance(x, np.ndarray) else x)
         seq = ref is None
+        derive = cur is None
         if seq and first_ref is None:
             raise ValueError("sequence mode (ref=None) needs first_ref, the reference of frame 0")
-        rgb, cur, ref = (t if t.is_pinned() else t.pin_memory() for t in map(pinned, (rgb, cur, first_ref if seq else ref)))
+        if derive and not seq:
+            raise ValueError("cur=None (luma derived from the RGB frames) needs sequence mode (ref=None)")
+        rgb, ref = (t if t.is_pinned() else t.pin_memory() for t in map(pinned, (rgb, first_ref if seq else ref)))
+        if not derive:
+            cur = pinned(cur)
+            cur = cur if cur.is_pinned() else cur.pin_memory()
         F, H, W, _ = rgb.shape
+        if derive and tuple(ref.shape) != (H, W, 3):
+            raise ValueError(f"cur=None: first_ref must be the RGB frame [H,W,3] before frame 0, got {tuple(ref.shape)}")
         hb = self._host_buffers(F, H, W)
         C = self.chunk
         bounds = self._schedule(F)
         nchunks = len(bounds)
-        slots = self._device_slots(C, H, W, seq)
+        slots = self._device_slots(C, H, W, seq, derive)
         S = self.nslots
         ev_in = [torch.cuda.Event() for _ in range(nchunks)]
         ev_cmp = [torch.cuda.Event() for _ in range(nchunks)]
@@ -189,15 +206,23 @@ class StreamedCoder:
                     self._s_in.wait_event(ev_cmp[k - S])          # the slot's previous chunk has been consumed
                 s = slots[k % S]
                 done = self._mark("h2d", k, self._s_in)
-                s.rgb[:hi - lo].copy_(rgb[lo:hi], non_blocking=True)
-                if seq:
+                n_prev = bounds[k - 1][1] - bounds[k - 1][0] if k else 0
+                prev = slots[(k - 1) % S]                         # its frames were uploaded by this very stream
+                if derive:                                        # RGB only; frame 0 of the slot = the frame before the chunk
+                    s.rgb[1:1 + hi - lo].copy_(rgb[lo:hi], non_blocking=True)
+                    if k == 0:
+                        s.rgb[0].copy_(ref, non_blocking=True)
+                    else:
+                        s.rgb[0].copy_(prev.rgb[n_prev])          # device-to-device
+                elif seq:
+                    s.rgb[:hi - lo].copy_(rgb[lo:hi], non_blocking=True)
                     s.cur[1:1 + hi - lo].copy_(cur[lo:hi], non_blocking=True)
                     if k == 0:
                         s.cur[0].copy_(ref.reshape(H, W), non_blocking=True)
-                    else:                                         # the last frame of the previous chunk, already on the
-                        n_prev = bounds[k - 1][1] - bounds[k - 1][0]
-                        s.cur[0].copy_(slots[(k - 1) % S].cur[n_prev])   # device (this stream uploaded it): device-to-device
+                    else:                                         # the last plane of the previous chunk: device-to-device
+                        s.cur[0].copy_(prev.cur[n_prev])
                 else:
+                    s.rgb[:hi - lo].copy_(rgb[lo:hi], non_blocking=True)
                     s.cur[:hi - lo].copy_(cur[lo:hi], non_blocking=True)
                     s.ref[:hi - lo].copy_(ref[lo:hi], non_blocking=True)
                 done()
@@ -267,5 +292,5 @@ class StreamedCoder:
         self._s_cmp2.synchronize()
         return {"sym_intra": hb["sym_intra"][:off[0]], "sym_inter": hb["sym_inter"][:off[1]], "len_intra": lens_i,
                 "len_inter": lens_p, "mv": hb["mv"], "sse": hb["sse"],
-                "h2d_bytes": rgb.numel() + cur.numel() + ref.numel(),            # ref = one frame in sequence mode
+                "h2d_bytes": rgb.numel() + (0 if derive else cur.numel()) + ref.numel(),   # ref = one frame in sequence mode
                 "d2h_bytes": (off[0] + off[1]) * hb["sym_intra"].element_size() + hb["mv"].numel() * 8 + hb["sse"].numel() * 8}

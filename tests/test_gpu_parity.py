@@ -766,3 +766,40 @@ def test_streamed_coder_matches_direct_calls():
         for k in ("sym_intra", "sym_inter", "mv", "sse"):
             assert torch.equal(out2[k], keep[k]), (chunk, k)
         assert out2["h2d_bytes"] == rgb.size + cur.size + seq[0].size
+
+
+def test_luma8_from_rgb8_vs_numpy_statement():
+    """clip(np.round(rgb2ycbcr(rgb)[..., 0]), 0, 255) on every (r, g, b) on a 64-step lattice plus random pixels and
+    the extremes; odd pixel counts and unaligned bases take the scalar path."""
+    rng = np.random.default_rng(71)
+    lat = np.stack(np.meshgrid(*[np.r_[0:256:5, 255]] * 3, indexing="ij"), -1).reshape(-1, 3).astype(np.uint8)
+    rgb = np.concatenate([lat, rng.integers(0, 256, size=(100003, 3), dtype=np.uint8)])
+    want = np.clip(np.round(O.rgb2ycbcr(rgb)[..., 0]), 0, 255).astype(np.uint8)
+    assert np.array_equal(ivc.luma8_from_rgb8(rgb), want)
+    d = torch.from_numpy(rgb).cuda()
+    flat = torch.empty(rgb.size + 1, dtype=torch.uint8, device="cuda")
+    flat[1:] = d.reshape(-1)
+    assert np.array_equal(ivc.luma8_from_rgb8(flat[1:].view(-1, 3)).cpu().numpy(), want)       # base not 4-byte aligned
+    img = rgb[: 24 * 40].reshape(24, 40, 3)
+    assert ivc.luma8_from_rgb8(img).shape == (24, 40)
+    with pytest.raises(ValueError):
+        ivc.luma8_from_rgb8(img.astype(np.float64))
+
+
+def test_streamed_coder_luma_derived_on_device():
+    """cur=None: the luma planes are derived from the RGB frames on the device -- same results as handing over the
+    planes, one byte per pixel less across PCIe."""
+    F, H, W = 7, 64, 96
+    rgb = np.stack([O.smooth_noise_rgb(80 + i, H, W) for i in range(F + 1)])
+    luma = np.clip(np.round(np.stack([O.rgb2ycbcr(f)[..., 0] for f in rgb])), 0, 255).astype(np.uint8)
+    want = ivc.StreamedCoder(0.4, 4, chunk_frames=2).run(rgb[1:], luma[1:], first_ref=luma[0])
+    keep = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in want.items()}
+    for chunk, slots, graph in ((2, 3, True), (3, 2, True), (4, 2, False), (16, 2, True)):
+        got = ivc.StreamedCoder(0.4, 4, chunk_frames=chunk, slots=slots, use_graph=graph).run(rgb[1:], first_ref=rgb[0])
+        for k in ("sym_intra", "sym_inter", "mv", "sse"):
+            assert torch.equal(got[k], keep[k]), (chunk, k)
+        assert got["h2d_bytes"] == rgb.size
+    with pytest.raises(ValueError):
+        ivc.StreamedCoder(0.4, 4).run(rgb[1:], first_ref=luma[0])                # the first reference must be an RGB frame
+    with pytest.raises(ValueError):
+        ivc.StreamedCoder(0.4, 4).run(rgb[1:], None, ref=luma[:-1])              # derived planes need sequence mode
