@@ -25,16 +25,17 @@ ycc = rgb2ycbcr(rgb)
 mv = pf.estimate(ref, cur)
 zzp = pf.forward(cur, ref, mv)
 recp = pf.inverse(zzp, ref=ref, mv=mv)
-stages = {
-    "u8->f64 x2": lambda: (cur8.double(), ref8.double()),
+luma8 = torch.empty((n + 1, 1080, 1920), dtype=torch.uint8, device="cuda")
+rgb1 = torch.cat([rgb[-1:], rgb]).contiguous()
+stages = {                                               # the stages of StreamedCoder._code, in its order
+    "luma8_from_rgb8 (n+1 frames)": lambda: ivc.luma8_from_rgb8(rgb1, out=luma8),
+    "u8->f64 (n+1 planes)": lambda: luma8.double(),
     "forward_rgb": lambda: intra.forward_rgb(rgb),
     "zr intra (count+scan+write)": lambda: zr.encode(zz),
-    "intra inverse": lambda: intra.inverse(zz),
-    "rgb2ycbcr": lambda: rgb2ycbcr(rgb),
-    "sse intra": lambda: frame_sse(ycc, rec),
-    "ME": lambda: pf.estimate(ref, cur),
+    "decode + distortion (K2d)": lambda: intra.inverse_with_distortion(zz, rgb, space="ycbcr"),
+    "ME on uint8 planes": lambda: pf.estimate(ref8, cur8),
     "pframe fwd": lambda: pf.forward(cur, ref, mv),
-    "zr inter": lambda: zr.encode(zzp),
+    "zr inter (count+scan+write)": lambda: zr.encode(zzp),
     "pframe inv": lambda: pf.inverse(zzp, ref=ref, mv=mv),
     "sse inter": lambda: frame_sse(cur, recp),
 }
