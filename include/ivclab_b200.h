@@ -276,8 +276,9 @@ int ivc_rgb2ycbcr(int device, void *stream, const void *rgb, int dtype, int64_t 
 int ivc_ycbcr2rgb(int device, void *stream, const void *ycbcr, int64_t npixels, void *rgb_out);
 /* uint8 RGB (npixels x 3) -> uint8 luma plane clip(rint(rgb2ycbcr(rgb)[..., 0]), 0, 255): the plane the video codecs
  * code (videocodec.py:38: Y = rgb2ycbcr(frame)[..., 0]) in the 8-bit form the host-fed pipeline searches on, derived
- * on the device so that only the RGB frames cross PCIe.  ABI version 3. */
-int ivc_rgb8_to_luma8(int device, void *stream, const void *rgb, int64_t npixels, void *luma_out);
+ * on the device so that only the RGB frames cross PCIe.  luma_f64_out (may be NULL) receives the same plane as float64,
+ * the dtype the P-frame entry points read.  ABI version 3. */
+int ivc_rgb8_to_luma8(int device, void *stream, const void *rgb, int64_t npixels, void *luma_out, void *luma_f64_out);
 
 /* K1 with rgb2ycbcr fused in front: uint8 RGB HWC images (W % 16 == 0, frames frame_stride_bytes apart)
  * -> [n_frames, H/8, W/8, 3, 64] int32, identical to ivc_intra_forward(rgb2ycbcr(rgb)); reads 3 bytes per

@@ -62,7 +62,7 @@ SIGNATURES = {
     "ivc_symbol_histogram": (_i, [_i, _p, _p, _i, _i64, _i64, _i64, _i64, _p]),
     "ivc_rgb2ycbcr": (_i, [_i, _p, _p, _i, _i64, _p]),
     "ivc_ycbcr2rgb": (_i, [_i, _p, _p, _i64, _p]),
-    "ivc_rgb8_to_luma8": (_i, [_i, _p, _p, _i64, _p]),
+    "ivc_rgb8_to_luma8": (_i, [_i, _p, _p, _i64, _p, _p]),
     "ivc_intra_forward_rgb8": (_i, [_i, _p, _p, _i64, _i64, _i64, _i64, _p, _i, _p]),
 }
 

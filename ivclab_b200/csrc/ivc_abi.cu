@@ -466,13 +466,13 @@ int ivc_rgb2ycbcr(int device, void *stream, const void *rgb, int dtype, int64_t 
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
 
-int ivc_rgb8_to_luma8(int device, void *stream, const void *rgb, int64_t npixels, void *luma_out) {
+int ivc_rgb8_to_luma8(int device, void *stream, const void *rgb, int64_t npixels, void *luma_out, void *luma_f64_out) {
     if (npixels < 0) return IVC_ERR_ARG;
     if (npixels == 0) return IVC_OK;
     if (!rgb || !luma_out) return IVC_ERR_ARG;
     int rc = enter(device);
     if (rc) return rc;
-    cudaError_t e = ivc::launch_rgb8_luma8(device, (cudaStream_t)stream, rgb, npixels, luma_out);
+    cudaError_t e = ivc::launch_rgb8_luma8(device, (cudaStream_t)stream, rgb, npixels, luma_out, luma_f64_out);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
 

@@ -47,9 +47,10 @@ __global__ void __launch_bounds__(256) k_ycbcr2rgb(const ColorArgs a) {
 // uint8 RGB -> uint8 luma plane: clip(rint(Y), 0, 255) with Y exactly as rgb2ycbcr computes it (rint = round half to
 // even = np.round).  What the video codecs code is Y = rgb2ycbcr(frame)[..., 0] (videocodec.py:38); deriving the
 // plane on the device means a host-fed pipeline uploads 3 bytes per pixel instead of 4.  Four pixels per thread:
-// three 32-bit loads, one 32-bit store.
-__global__ void __launch_bounds__(256) k_rgb8_luma8(const unsigned char *__restrict__ rgb, unsigned char *__restrict__ out, int64_t npix,
-                                                    int vec) {
+// three 32-bit loads, one 32-bit store; out64 (optional) receives the same plane as float64, the dtype the transform
+// kernels read (saves the separate conversion pass).
+__global__ void __launch_bounds__(256) k_rgb8_luma8(const unsigned char *__restrict__ rgb, unsigned char *__restrict__ out,
+                                                    double *__restrict__ out64, int64_t npix, int vec) {
     const auto luma = [](unsigned r, unsigned g, unsigned b) {
         double y, cb, cr;
         rgb2ycbcr_px((double)r, (double)g, (double)b, y, cb, cr);
@@ -65,19 +66,27 @@ __global__ void __launch_bounds__(256) k_rgb8_luma8(const unsigned char *__restr
         const unsigned y2 = luma((w1 >> 16) & 255u, w1 >> 24, w2 & 255u);
         const unsigned y3 = luma((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24);
         reinterpret_cast<unsigned *>(out)[i] = y0 | (y1 << 8) | (y2 << 16) | (y3 << 24);
+        if (out64) {
+            double2 *o = reinterpret_cast<double2 *>(out64 + 4 * i);
+            o[0] = make_double2((double)y0, (double)y1);
+            o[1] = make_double2((double)y2, (double)y3);
+        }
     }
-    for (int64_t i = 4 * ngrp + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x)
-        out[i] = (unsigned char)luma(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+    for (int64_t i = 4 * ngrp + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned y = luma(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+        out[i] = (unsigned char)y;
+        if (out64) out64[i] = (double)y;
+    }
 }
 
-cudaError_t launch_rgb8_luma8(int device, cudaStream_t st, const void *rgb, int64_t npix, void *out) {
+cudaError_t launch_rgb8_luma8(int device, cudaStream_t st, const void *rgb, int64_t npix, void *out, void *out64) {
     if (npix == 0) return cudaSuccess;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     int64_t grid = (npix / 4 + 255) / 256 + 1;
     if (grid > (int64_t)sms * 16) grid = (int64_t)sms * 16;
-    const int vec = (((uintptr_t)rgb | (uintptr_t)out) & 3) == 0;
-    k_rgb8_luma8<<<(unsigned)grid, 256, 0, st>>>((const unsigned char *)rgb, (unsigned char *)out, npix, vec);
+    const int vec = (((uintptr_t)rgb | (uintptr_t)out) & 3) == 0 && ((uintptr_t)out64 & 15) == 0;
+    k_rgb8_luma8<<<(unsigned)grid, 256, 0, st>>>((const unsigned char *)rgb, (unsigned char *)out, (double *)out64, npix, vec);
     return cudaGetLastError();
 }
 

@@ -66,7 +66,7 @@ cudaError_t launch_minmax(int device, cudaStream_t st, const void *x, int dtype,
 
 // colour (ivc_color.cu) and the RGB front end of K1 (ivc_transform.cu)
 cudaError_t launch_color(int device, cudaStream_t st, bool to_rgb, const void *in, int in_dtype, int64_t npix, double *out);
-cudaError_t launch_rgb8_luma8(int device, cudaStream_t st, const void *rgb, int64_t npix, void *out);
+cudaError_t launch_rgb8_luma8(int device, cudaStream_t st, const void *rgb, int64_t npix, void *out, void *out64);
 cudaError_t launch_forward_rgb8(int device, cudaStream_t st, const void *rgb, int64_t n, int64_t H, int64_t W,
                                 int64_t frame_stride_bytes, const void *table, int table_dtype, int32_t *out);
 

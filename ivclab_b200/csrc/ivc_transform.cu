@@ -1015,15 +1015,29 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_inverse_c3_tma(const I
     if (lane == 0) bulk_wait_all0();
 }
 
-// sum the tile partials of each frame in a fixed order (one warp per frame)
-__global__ void __launch_bounds__(32) k_sum_tile_partials(const double *__restrict__ partial, int64_t tiles_per_frame,
-                                                          double *__restrict__ out) {
+// sum the tile partials of each frame in a fixed order: one CTA per frame, thread t adds partials t, t + 256, ... in
+// four interleaved chains, then a fixed shuffle / shared-memory tree (the order does not depend on the batch)
+__global__ void __launch_bounds__(256) k_sum_tile_partials(const double *__restrict__ partial, int64_t tiles_per_frame,
+                                                           double *__restrict__ out) {
+    __shared__ double s_w[8];
     const double *p = partial + (int64_t)blockIdx.x * tiles_per_frame;
-    double acc = 0.0;
-    for (int64_t c = threadIdx.x; c < tiles_per_frame; c += 32) acc = __dadd_rn(acc, p[c]);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int64_t c = threadIdx.x;
+    for (; c + 768 < tiles_per_frame; c += 1024) {
+        a0 = __dadd_rn(a0, p[c]); a1 = __dadd_rn(a1, p[c + 256]); a2 = __dadd_rn(a2, p[c + 512]); a3 = __dadd_rn(a3, p[c + 768]);
+    }
+    for (; c < tiles_per_frame; c += 256) a0 = __dadd_rn(a0, p[c]);
+    double acc = __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, off));
-    if (threadIdx.x == 0) out[blockIdx.x] = acc;
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = s_w[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) t = __dadd_rn(t, s_w[w]);
+        out[blockIdx.x] = t;
+    }
 }
 
 // ================================================================================================
@@ -2114,7 +2128,7 @@ cudaError_t launch_inverse_sse(int device, cudaStream_t st, const int32_t *zz, i
         if ((e = set_smem(k_inverse_c3_tma<2>, smem)) != cudaSuccess) return e;
         k_inverse_c3_tma<2><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
     }
-    k_sum_tile_partials<<<(unsigned)n, 32, 0, st>>>(partial, Hp * (int64_t)a.g.tiles_per_row, sse_out);
+    k_sum_tile_partials<<<(unsigned)n, 256, 0, st>>>(partial, Hp * (int64_t)a.g.tiles_per_row, sse_out);
     return cudaGetLastError();
 }
 

@@ -36,8 +36,7 @@ __global__ void __launch_bounds__(kZrWarps * 32) k_zr_count(const int32_t *__res
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * kZrWarps + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * kZrWarps;
     for (int64_t blk0 = warp * 32; blk0 < nblocks; blk0 += nw * 32) {                 // 32 blocks per warp and round
-        int mine = 0;
-        unsigned long long mine_m = 0;
+        unsigned long long mine_m = 0;                                                // lane j keeps the mask of block j
 #pragma unroll 1
         for (int sub = 0; sub < 32; sub += kZrBatch) {
             int a[kZrBatch], b[kZrBatch];
@@ -52,15 +51,14 @@ __global__ void __launch_bounds__(kZrWarps * 32) k_zr_count(const int32_t *__res
             }
 #pragma unroll
             for (int j = 0; j < kZrBatch; ++j) {
-                const unsigned long long m = (unsigned long long)__ballot_sync(0xffffffffu, a[j] != 0) |
-                                             ((unsigned long long)__ballot_sync(0xffffffffu, b[j] != 0) << 32);
-                int c = 1;                                                            // EOB
-                if (m) c += __popcll(m) + 2 * __popcll(zr_run_starts(m));
-                if (lane == sub + j) { mine = c; mine_m = m; }
+                const unsigned lo = __ballot_sync(0xffffffffu, a[j] != 0), hi = __ballot_sync(0xffffffffu, b[j] != 0);
+                if (lane == sub + j) mine_m = (unsigned long long)lo | ((unsigned long long)hi << 32);
             }
         }
-        if (blk0 + lane < nblocks) {
-            counts[blk0 + lane] = mine;
+        if (blk0 + lane < nblocks) {                                                  // the symbol arithmetic once per block
+            int c = 1;                                                                // EOB
+            if (mine_m) c += __popcll(mine_m) + 2 * __popcll(zr_run_starts(mine_m));
+            counts[blk0 + lane] = c;
             if (masks) masks[blk0 + lane] = mine_m;
         }
     }

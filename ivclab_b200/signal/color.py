@@ -37,17 +37,21 @@ def ycbcr2rgb(image):
     return to_host(out, was_np)
 
 
-def luma8_from_rgb8(image, out=None):
+def luma8_from_rgb8(image, out=None, out_f64=None):
     """uint8 RGB [..., 3] -> uint8 luma plane ``clip(round(rgb2ycbcr(image)[..., 0]), 0, 255)`` (np.round: half to even):
-    the Y channel the video codecs code (ivclab/video/videocodec.py:38) in 8-bit form, computed on the device."""
+    the Y channel the video codecs code (ivclab/video/videocodec.py:38) in 8-bit form, computed on the device.
+    ``out`` / ``out_f64``: caller-owned device tensors for the plane and (optionally) its float64 copy."""
     t, was_np = to_device(image)
     if t.ndim < 1 or t.shape[-1] != 3 or t.dtype != torch.uint8:
         raise ValueError(f"expected uint8 [..., 3], got {t.dtype} {tuple(t.shape)}")
     t = t.contiguous()
+    npix = t.numel() // 3
     if out is None:
         out = torch.empty(t.shape[:-1], dtype=torch.uint8, device=t.device)
-    elif out.dtype != torch.uint8 or out.numel() != t.numel() // 3 or not out.is_contiguous() or out.device != t.device:
-        raise ValueError("out must be a contiguous uint8 tensor with one element per pixel on the input's device")
-    st = _lib.lib.ivc_rgb8_to_luma8(dev_index(t), stream_ptr(t.device), t.data_ptr(), t.numel() // 3, out.data_ptr())
+    for o, dt in ((out, torch.uint8), (out_f64, torch.float64)):
+        if o is not None and (o.dtype != dt or o.numel() != npix or not o.is_contiguous() or o.device != t.device):
+            raise ValueError("out / out_f64 must be contiguous uint8 / float64 tensors with one element per pixel on the input's device")
+    st = _lib.lib.ivc_rgb8_to_luma8(dev_index(t), stream_ptr(t.device), t.data_ptr(), npix, out.data_ptr(),
+                                    out_f64.data_ptr() if out_f64 is not None else None)
     _lib.check(st, "ivc_rgb8_to_luma8")
     return to_host(out, was_np)

@@ -115,8 +115,10 @@ class StreamedCoder:
         if s.ref is None:                              # sequence mode: frame t is predicted from frame t-1
             luma8 = s.cur[:n + 1]
             if s.derive:                               # the planes are the rounded Y channel of the RGB frames (videocodec.py:38)
-                luma8_from_rgb8(s.rgb[:n + 1], out=luma8)
-            luma = luma8.double()
+                luma = torch.empty(luma8.shape, dtype=torch.float64, device=luma8.device)
+                luma8_from_rgb8(s.rgb[:n + 1], out=luma8, out_f64=luma)
+            else:
+                luma = luma8.double()
             d_ref, d_cur, r8, c8 = luma[:n], luma[1:], luma8[:n], luma8[1:]
         else:
             r8, c8 = s.ref[:n], s.cur[:n]

@@ -780,6 +780,9 @@ def test_luma8_from_rgb8_vs_numpy_statement():
     flat = torch.empty(rgb.size + 1, dtype=torch.uint8, device="cuda")
     flat[1:] = d.reshape(-1)
     assert np.array_equal(ivc.luma8_from_rgb8(flat[1:].view(-1, 3)).cpu().numpy(), want)       # base not 4-byte aligned
+    f64 = torch.empty(len(rgb), dtype=torch.float64, device="cuda")               # the same plane as float64, in one pass
+    u8 = ivc.luma8_from_rgb8(d, out_f64=f64)
+    assert np.array_equal(u8.cpu().numpy(), want) and np.array_equal(f64.cpu().numpy(), want.astype(np.float64))
     img = rgb[: 24 * 40].reshape(24, 40, 3)
     assert ivc.luma8_from_rgb8(img).shape == (24, 40)
     with pytest.raises(ValueError):
