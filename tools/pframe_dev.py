@@ -1,8 +1,10 @@
 """Developer aid: P-frame kernels (K1p / K2p) against the oracle on small and ragged frames, then timing at 1080p.
-    IVC_PFRAME=2|3|3r2 python tools/pframe_dev.py [--time]"""
-import os, sys, time
+    IVC_PFRAME=2|3 python tools/pframe_dev.py [--time] [--case H W]    (MV=zero|oob|idxN fixes the vectors)"""
+import os
+import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import numpy as np
+import torch
 import ivclab_b200 as ivc
 from oracle import ivc_oracle as O
 
