@@ -15,7 +15,9 @@ frames (cfg3 shape for the intra half, cfg4/cfg5-style frame pairs for the inter
 `value` = F*H*W pixels / step time: every pixel is intra-coded AND inter-coded once per step.
 Inputs are resident in HBM and much larger than L2 (F=32: 2.7 GB read, 3.5 GB written per step).
 `e2e` is the same step through the public Python API with pinned HOST buffers (H2D of the frames and
-D2H of the scan indices / motion vectors inside the timed region).  `--impl reference` times the
+D2H of the symbol streams / motion vectors / squared errors inside the timed region).  `configs` holds the five
+configurations BASELINE.json names, each measured as named (bench_configs.py): cfg3 (1024-frame RD sweep, 10
+qScales) and cfg4 (8 x 120 x 4K, +-16 search) are strong-scaled over the ranks of a --gpus N run.  `--impl reference` times the
 CPU port that makes the reference's own library calls (oracle/ref_port.py) on all host cores.
 The oracle is used ONLY in the cpu_baseline / reference legs (as baseline and as checker).
 """
@@ -54,6 +56,12 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the host-fed legs (e2e keys become null)")
     ap.add_argument("--me-mode", default="auto", choices=["auto", "exact", "int"])
+    ap.add_argument("--configs", default="all",
+                    help="which of BASELINE.json's five configurations to measure as named into the `configs` key: "
+                         "'all', 'none', or a comma list such as cfg3,cfg4 (bench_configs.py)")
+    ap.add_argument("--cfg3-frames", type=int, default=1024, help="size of the cfg3 frame pool (strong-scaled over the ranks)")
+    ap.add_argument("--cfg4-frames", type=int, default=120, help="frames per 4K sequence of cfg4")
+    ap.add_argument("--cfg5-frames", type=int, default=300, help="frames of the cfg5 closed-loop sequence")
     ap.add_argument("--cpu-configs", action="store_true",
                     help="with --impl reference: also time the reference-call port on bounded samples of the five "
                          "configurations BASELINE.json names (adds the key cpu_configs; about a minute of CPU time)")
@@ -430,6 +438,26 @@ def run_b200(args):
         raw_h2d = h_y.numel() * 8 + h_l.numel() * 8 + h_r.numel() * 8
         raw_d2h = h_zz_i.numel() * 4 + h_zz_p.numel() * 4 + h_mv.numel() * 8 + h_stat.numel() * 8
 
+    # ---- the five named configurations (all ranks take part: cfg3 / cfg4 are sharded) ----
+    cfgs = cfg_clk = None
+    if args.configs != "none":
+        import bench_configs as BC
+        which_cfg = ("cfg1", "cfg2", "cfg3", "cfg4", "cfg5") if args.configs == "all" else tuple(args.configs.split(","))
+        torch.cuda.empty_cache()
+        try:
+            pk = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:
+            pk = 6650.0
+        cclk = Clocks(local)
+        if rank == 0:
+            cclk.start()
+        tc0 = time.time()
+        cx = BC.Ctx(torch, dist, device, rank, world, pk, sm_mhz=(clk or {}).get("sm_mhz"),
+                    sms=torch.cuda.get_device_properties(device).multi_processor_count)
+        cfgs = BC.run_all(cx, ivc, which_cfg, cfg3_frames=args.cfg3_frames, cfg4_frames=args.cfg4_frames,
+                          cfg5_frames=args.cfg5_frames)
+        cfg_clk = cclk.stop(tc0, time.time()) if rank == 0 else None
+
     out = None
     if rank == 0:
         peaks = {}
@@ -439,15 +467,31 @@ def run_b200(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         which = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        # dominant HBM-bound kernel: K1 fused forward.  algorithmic bytes = 8 B in + 4 B out per sample
-        k1_bytes = Fr * H * W * 3 * 12
-        k1_gbs = k1_bytes / (phase_ms["intra_fwd"] * 1e-3) / 1e9
-        traffic = None
+        # algorithmic bytes per pixel of each phase: K1 8 in + 4 out per sample x 3 channels,
+        # K2 the same, ME two float64 frame reads, K1p cur 8 + gathered prediction 8 + 3 x 4 out, K2p 4 in + 8 + 8
+        algo = {"intra_fwd": px * 36, "intra_inv": px * 36, "me": px * 16, "pframe_fwd": px * 28, "pframe_inv": px * 20}
+        kname = {"intra_fwd": "k_forward_c3_tma (K1: DCT + quantise + zig-zag, 3-channel intra)",
+                 "intra_inv": "k_inverse_c3_tma<0,0> (K2: un-zig-zag + dequantise + IDCT, 3-channel intra)",
+                 "me": "k_me_int (K3: +-4 full search, packed-integer kernel)",
+                 "pframe_fwd": "k_pframe_forward_tm (K1p: MC + residual + DCT + quantise + zig-zag)",
+                 "pframe_inv": "k_pframe_inverse_tm (K2p: dequantise + IDCT + prediction add)"}
+        hbm_phases = [k for k in algo if k != "me"]                  # the search is bound by the integer pipe, not by HBM
+        dom = max(hbm_phases, key=lambda k: phase_ms[k])             # the TIME-DOMINANT HBM-bound kernel of the step
+        dom_gbs = algo[dom] / (phase_ms[dom] * 1e-3) / 1e9
+        traffic = traffic_src = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get("dram_bytes_per_launch")
+            kt = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))
+            e = kt["kernels"][dom]
+            traffic = (e["dram_bytes_read"] + e["dram_bytes_write"]) * Fr // kt["frames"]
+            traffic_src = f"constant from {kt['source']} (one ncu --set full capture, scaled to {Fr} frames); NOT measured by this run"
         except Exception:
             pass
-        algo = {"intra_fwd": px * 36, "intra_inv": px * 36, "pframe_fwd": px * 28, "pframe_inv": px * 20}
+        step_bytes = sum(algo.values())
+        sm_hz = (clk.get("sm_mhz") or 1965.0) * 1e6 if clk else 1965.0e6
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        import bench_configs as BC
+        me_lanes = Fr * BC.candidates(H, W, SR) * 16                  # dp4a lane-instructions of the cross term: 64 pixels / 4 per candidate
+        me_pipe = BC.IDP_LANES_PER_CLK_SM * sms * sm_hz
         out = {
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": max(3, args.warmup), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
@@ -471,15 +515,29 @@ def run_b200(args):
                         "api": "pinned host float64 YCbCr + luma in, raw int32 scan indices + MVs + SSE out (PCIe-bound)"},
             "gpu_launches": K * launches_per_step,
             "clocks": clk,
-            "roofline": {"kernel": "k_forward_c3_tma (K1: fused DCT+quantize+zig-zag, 3-channel intra)", "bound": "hbm",
-                         "achieved": round(k1_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(k1_gbs / peak, 4),
-                         "traffic": traffic, "algorithmic_bytes_per_launch": k1_bytes, "peak_source": which,
-                         "avg_launch_ms": round(phase_ms["intra_fwd"], 4)},
+            "roofline": {"kernel": kname[dom], "kernel_choice": "the time-dominant HBM-bound kernel of the step",
+                         "bound": "hbm", "achieved": round(dom_gbs, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(dom_gbs / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": algo[dom], "peak_source": which,
+                         "avg_launch_ms": round(phase_ms[dom], 4),
+                         # the whole step against the same peak: sum of the five kernels' algorithmic bytes / step time
+                         "step_frac": round(step_bytes / (ms_step * 1e-3) / 1e9 / peak, 4),
+                         "step_algorithmic_bytes": step_bytes,
+                         "me": {"kernel": kname["me"], "bound": "IDP (dp4a) pipe", "ms": round(phase_ms["me"], 4),
+                                "idp_lanes_per_launch": me_lanes, "idp_lanes_per_s": round(me_lanes / (phase_ms["me"] * 1e-3), 0),
+                                "idp_pipe_peak_lanes_per_s": round(me_pipe, 0),
+                                "idp_pipe_frac": round(me_lanes / (phase_ms["me"] * 1e-3) / me_pipe, 4),
+                                "hbm_frac": round(algo["me"] / (phase_ms["me"] * 1e-3) / 1e9 / peak, 4),
+                                "peak_source": f"{BC.IDP_LANES_PER_CLK_SM} dp4a lanes/clk/SM (measured, profiles/r1h_ubench_int.txt) x {sms} SMs x "
+                                               f"{sm_hz / 1e6:.0f} MHz (SM clock sampled during the timed region)"}},
             "phases_ms": {k: round(v, 4) for k, v in phase_ms.items()},
             "phases_mpixel_s": {k: round(px / (v * 1e-3) / 1e6, 1) for k, v in phase_ms.items()},
             "phases_hbm_frac": {k: round(algo[k] / (phase_ms[k] * 1e-3) / 1e9 / peak, 4) for k in algo},
             "me_mode": args.me_mode,
         }
+        if cfgs is not None:
+            cfgs["clocks"] = cfg_clk
+            out["configs"] = cfgs
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(np, ivc, cores=1)
     if world > 1:
@@ -524,7 +582,52 @@ def cpu_baseline(np, ivc, cores=1):
     ok = ok and np.array_equal(mv, s["mv"]) and np.array_equal(pc.forward(s["seq"][1], s["seq"][0], mv), s["zzp"])
     ok = ok and np.array_equal(pc.inverse(s["zzp"], ref=s["seq"][0], mv=mv), s["recon"])
     res["gpu_matches_cpu_on_sample"] = bool(ok)
+    res["streamed_coder_1080p_check"] = check_streamed_1080p(np, ivc)
     return res
+
+
+def check_streamed_1080p(np, ivc):
+    """The host-fed pipeline that `e2e` times (StreamedCoder.run, luma planes derived on the device) at the size it is
+    timed at: two full 1080p frames against the oracle -- symbol streams and motion vectors bit for bit, squared
+    errors to 1e-12 relative.  The oracle (C restatement where built, numpy otherwise) is the checker only."""
+    import hashlib
+    import torch
+    from oracle import c_oracle as CO, ivc_oracle as O
+    t0 = time.perf_counter()
+    rgb = np.stack([O.smooth_noise_rgb(7000 + i, H, W) for i in range(3)])
+    sc = ivc.StreamedCoder(QSCALE, SR, chunk_frames=2, device=torch.device("cuda", torch.cuda.current_device()))
+    out = sc.run(rgb[1:], first_ref=rgb[0])
+    tab = O.quant_table(QSCALE)
+    fwd = (lambda img: CO.intra_forward(img, tab, threads=8)) if CO.available() else (lambda img: O.intra_forward(img, tab))
+    inv = (lambda z: CO.intra_inverse(z, tab, threads=8)) if CO.available() else (lambda z: O.intra_inverse(z, tab))
+    me = (lambda r, c: CO.me_full_search(r, c, SR, threads=8)) if CO.available() else (lambda r, c: O.me_full_search(r, c, SR))
+    luma = np.clip(np.round(np.stack([O.rgb2ycbcr(f)[..., 0] for f in rgb])), 0, 255)          # videocodec.py:38, as a uint8 plane
+    sym_i, sym_p, mvs, sse_ok = [], [], [], True
+    for i in (1, 2):
+        y = O.rgb2ycbcr(rgb[i])
+        zz = fwd(y)
+        sym_i.append(O.zerorun_encode_fast(zz))
+        sse_i = float(((y - inv(zz)) ** 2).sum())
+        mv = me(luma[i - 1], luma[i])
+        mvs.append(mv)
+        pred = O.mc_reconstruct(luma[i - 1][..., None], mv, SR)[..., 0]
+        zzp = fwd(luma[i] - pred)
+        sym_p.append(O.zerorun_encode_fast(zzp[:, :, :sc.inter_channels]))
+        rec = pred + inv(zzp[:, :, :1])[..., 0]
+        sse_p = float(((luma[i] - rec) ** 2).sum())
+        got = out["sse"][:, i - 1].tolist()
+        sse_ok = sse_ok and abs(got[0] / sse_i - 1) < 1e-12 and abs(got[1] / sse_p - 1) < 1e-12
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+    want_i, want_p, want_mv = np.concatenate(sym_i), np.concatenate(sym_p), np.stack(mvs)
+    got_i, got_p = out["sym_intra"].numpy().astype(np.int32), out["sym_inter"].numpy().astype(np.int32)
+    got_mv = out["mv"].numpy().astype(np.int64)
+    return {"frames": 2, "height": H, "width": W, "inter_channels": sc.inter_channels,
+            "sym_intra_sha": sha(got_i), "sym_intra_equal": bool(np.array_equal(got_i, want_i)),
+            "sym_inter_sha": sha(got_p), "sym_inter_equal": bool(np.array_equal(got_p, want_p)),
+            "mv_sha": sha(got_mv), "mv_equal": bool(np.array_equal(got_mv, want_mv)),
+            "sse_within_1e-12": bool(sse_ok), "symbols": int(got_i.size + got_p.size),
+            "oracle": "oracle/c (gcc) + oracle/ivc_oracle.py" if CO.available() else "oracle/ivc_oracle.py",
+            "seconds": round(time.perf_counter() - t0, 1)}
 
 
 def _best_of(fn, n=3):

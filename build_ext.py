@@ -35,25 +35,51 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
 
 
-def needs_build() -> bool:
-    if not os.path.exists(OUT):
+def _deps(src: str):
+    return [os.path.join(CSRC, src)] + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def needs_build() -> bool:
+    return any(_stale(OUT, _deps(s)) for s in SOURCES)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """One object per translation unit, compiled in parallel and only when its source (or a header) changed,
+    then one link step: a kernel edit costs the compile time of its own file."""
     if not force and not needs_build():
         return OUT
-    os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", OUT + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    obj_dir = os.path.join(OUT_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    jobs = []
+    for src in SOURCES:
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        if force or _stale(obj, _deps(src)):
+            cmd = [_nvcc()] + flags + ["-c", "-o", obj, os.path.join(CSRC, src)]
+            jobs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = []
+    for src, proc in jobs:
+        out, _ = proc.communicate()
+        if verbose or proc.returncode != 0:
+            sys.stderr.write(out)
+        if proc.returncode != 0:
+            failed.append(src)
+    if failed:
+        raise RuntimeError(f"nvcc failed compiling {', '.join(failed)}")
+    objs = [os.path.join(obj_dir, s.replace(".cu", ".o")) for s in SOURCES]
+    res = subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
+                          "-o", OUT + ".tmp"] + objs, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libivcb200.so")
+        raise RuntimeError("nvcc failed linking libivcb200.so")
     os.replace(OUT + ".tmp", OUT)
     return OUT
 

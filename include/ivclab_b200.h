@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define IVC_ABI_VERSION 3
+#define IVC_ABI_VERSION 4
 
 /* element types */
 #define IVC_U8   0
@@ -179,6 +179,15 @@ int ivc_pframe_forward(int device, void *stream,
                        int64_t n_frames, int64_t H, int64_t W, int search_range,
                        const void *table, int table_dtype,
                        void *pred_out, int32_t *zz_out);
+/* The same with out_channels scan blocks stored per image block: 3 = the reference's layout (above); 2 = channels 0
+ * and 1 only, zz_out [n_frames,Hp,Wp,2,64].  PatchQuant's table is [lum, chrom, chrom] (patchquant.py:40), so channel
+ * 2 of the broadcast luma residual repeats channel 1 bit for bit: a pipeline that ships symbols to a host need not
+ * compute, store or send it (ivc_pframe_inverse reads channel 0 at stride Czz = 2). */
+int ivc_pframe_forward_ch(int device, void *stream,
+                          const void *cur, const void *ref, const int64_t *mv, int dtype,
+                          int64_t n_frames, int64_t H, int64_t W, int search_range,
+                          const void *table, int table_dtype,
+                          void *pred_out, int out_channels, int32_t *zz_out);
 
 /* ---- a15 fused: P-frame decoder half (intracodec.py:115-124 + videocodec.py:74) --------------
  * recon = pred + idct(dequantize(unflatten(zz[..., 0, :])))[channel 0]  (luminance table).
@@ -227,6 +236,16 @@ int ivc_zerorun_write_masks(int device, void *stream, const int32_t *zz, int64_t
  * without a check -- the reference's dtype is int32 (ivc_zerorun_write). */
 int ivc_zerorun_write_masks_i16(int device, void *stream, const int32_t *zz, int64_t nblocks, int32_t end_of_block,
                                 const int64_t *offsets, const uint64_t *masks, int16_t *symbols_out, int64_t total_symbols);
+
+/* The marginal histogram of the symbol stream WITHOUT the stream: what IntraCodec.train_huffman_from_image
+ * (intracodec.py:160-166: image2symbols -> min/max -> stats_marg) needs of ZeroRunCoder.encode's output.
+ * zz: n_units x blocks_per_unit contiguous scan blocks (a unit = one frame's blocks).  counts_out
+ * [n_units, n_bins] uint32 (zeroed by the call): counts_out[u][k] = number of symbols of unit u's stream equal to
+ * lo + k, i.e. np.histogram(ZeroRunCoder.encode(unit u), bins=np.arange(lo, lo + n_bins + 1))[0] whenever every
+ * symbol lies in [lo, lo + n_bins) -- outside_out[u] (uint32) counts the symbols that do not.  n_bins <= 49152. */
+int ivc_zerorun_symbol_histogram(int device, void *stream, const int32_t *zz, int64_t n_units, int64_t blocks_per_unit,
+                                 int32_t end_of_block, int64_t lo, int64_t n_bins, uint32_t *counts_out,
+                                 uint32_t *outside_out);
 
 /* The scan between the two passes, for callers that do not want to bring their own: offsets_out[b] = sum of
  * counts[0..b) (int64), in one kernel (decoupled look-back over 4096-count tiles).  The grand total is written

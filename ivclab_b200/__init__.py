@@ -15,17 +15,19 @@ extension has not been built, and calling it fails if no CUDA device is visible.
 """
 from . import _lib  # noqa: F401  (loads libivcb200.so or raises)
 from .codec import IntraBlockCoder, PFrameBlockCoder
-from .entropy import ZeroRunCoder, stats_marg, symbol_histogram, symbol_minmax
+from .entropy import ZeroRunCoder, stats_marg, symbol_histogram, symbol_minmax, zerorun_symbol_histogram
 from .image import IntraCodec
+from ._runtime import set_device_memo
 from .install import inject, install
 from .quantization import PatchQuant
 from .signal import DiscreteCosineTransform, luma8_from_rgb8, rgb2ycbcr, ycbcr2rgb
 from .streaming import StreamedCoder
+from .sweep import RateDistortionSweep
 from .utils import Patcher, ZigZag, calc_mse, calc_psnr, frame_sse, frame_sse_rgb8_vs_ycbcr
 from .video import ClosedLoopLumaCoder, MotionCompensator
 
 __version__ = "0.1.0"
 __all__ = ["DiscreteCosineTransform", "PatchQuant", "ZigZag", "Patcher", "MotionCompensator",
            "IntraBlockCoder", "PFrameBlockCoder", "IntraCodec", "ClosedLoopLumaCoder", "ZeroRunCoder", "calc_mse", "calc_psnr",
-           "frame_sse", "frame_sse_rgb8_vs_ycbcr", "rgb2ycbcr", "ycbcr2rgb", "luma8_from_rgb8", "StreamedCoder", "stats_marg", "symbol_minmax", "symbol_histogram",
-           "install", "inject"]
+           "frame_sse", "frame_sse_rgb8_vs_ycbcr", "rgb2ycbcr", "ycbcr2rgb", "luma8_from_rgb8", "StreamedCoder", "stats_marg", "symbol_minmax", "symbol_histogram", "zerorun_symbol_histogram",
+           "install", "inject", "set_device_memo", "RateDistortionSweep"]

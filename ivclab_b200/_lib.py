@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, "_C", "libivcb200.so")
 
 # element type codes (include/ivclab_b200.h)
 U8, I32, F32, F64, I64, I16 = 0, 1, 2, 3, 4, 5
-ABI_VERSION = 3            # include/ivclab_b200.h IVC_ABI_VERSION (2: entry points added in round 1, zero-run write gained a length; 3: ivc_rgb8_to_luma8)
+ABI_VERSION = 4            # include/ivclab_b200.h IVC_ABI_VERSION (2: entry points added in round 1, zero-run write gained a length; 3: ivc_rgb8_to_luma8;
+                           # 4: ivc_pframe_forward_ch, ivc_zerorun_symbol_histogram)
 ME_AUTO, ME_EXACT, ME_INT = 0, 1, 2
 SSE_RGB8_AS_YCBCR = 103
 DIST_RGB, DIST_YCBCR = 1, 2
@@ -44,6 +45,7 @@ SIGNATURES = {
     "ivc_me_full_search_intdtype": (_i, [_i, _p, _p, _p, _i, _i64, _i64, _i64, _i64, _i64, _i, _p]),
     "ivc_mc_reconstruct": (_i, [_i, _p, _p, _i, _i64, _i64, _i64, _i64, _p, _i, _p]),
     "ivc_pframe_forward": (_i, [_i, _p, _p, _p, _p, _i, _i64, _i64, _i64, _i, _p, _i, _p, _p]),
+    "ivc_pframe_forward_ch": (_i, [_i, _p, _p, _p, _p, _i, _i64, _i64, _i64, _i, _p, _i, _p, _i, _p]),
     "ivc_pframe_inverse": (_i, [_i, _p, _p, _i64, _p, _p, _p, _i, _i64, _i64, _i64, _i, _p, _i, _p]),
     "ivc_sse_workspace_bytes": (_i64, [_i64, _i64]),
     "ivc_sum_squared_error": (_i, [_i, _p, _p, _i, _p, _i, _i64, _i64, _i, _p, _i64, _p]),
@@ -52,6 +54,7 @@ SIGNATURES = {
     "ivc_zerorun_count_masks": (_i, [_i, _p, _p, _i64, _p, _p]),
     "ivc_zerorun_write_masks": (_i, [_i, _p, _p, _i64, C.c_int32, _p, _p, _p, _i64]),
     "ivc_zerorun_write_masks_i16": (_i, [_i, _p, _p, _i64, C.c_int32, _p, _p, _p, _i64]),
+    "ivc_zerorun_symbol_histogram": (_i, [_i, _p, _p, _i64, _i64, C.c_int32, _i64, _i64, _p, _p]),
     "ivc_zerorun_offsets_workspace_bytes": (_i64, [_i64]),
     "ivc_zerorun_offsets": (_i, [_i, _p, _p, _i64, _p, _p, _i64, _p, _p]),
     "ivc_post_words_to_host": (_i, [_i, _p, _p, _p, _i]),

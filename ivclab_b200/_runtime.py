@@ -25,15 +25,77 @@ def code(dtype: torch.dtype) -> int:
         raise ValueError(f"dtype {dtype} is not supported on this path") from None
 
 
+# ---- device memo: the numpy arrays the drop-in classes hand out stay backed by their device tensors -------------
+# The unmodified IntraCodec chains six methods, each numpy in -> numpy out (intracodec.py:69-75, :115-121): without
+# help every method would upload what the previous one has just downloaded.  `to_host` therefore remembers (weakly)
+# which device tensor is behind each array it returns, and `to_device` finds that tensor again -- for the array
+# itself and for views of it (einops.rearrange, slicing) -- so a chain pays ONE upload (its first input) and the
+# downloads.  To make this safe the returned arrays are READ-ONLY: while an array is read-only its bytes cannot
+# diverge from the device copy; a caller who sets `arr.flags.writeable = True` simply loses the shortcut for that
+# array (it is uploaded again).  `set_device_memo(False)` turns the mechanism off (arrays are then writable).
+_MEMO_ON = True
+_MEMO_MAX = 12
+_memo = {}                      # id(array) -> (weakref to the array, device tensor), insertion-ordered
+
+
+def set_device_memo(enabled: bool) -> None:
+    global _MEMO_ON
+    _MEMO_ON = bool(enabled)
+    if not _MEMO_ON:
+        _memo.clear()
+
+
+def _memo_put(arr: np.ndarray, t: torch.Tensor) -> None:
+    import weakref
+    key = id(arr)
+    arr.flags.writeable = False
+    _memo[key] = (weakref.ref(arr, lambda _r, k=key: _memo.pop(k, None)), t)
+    while len(_memo) > _MEMO_MAX:
+        _memo.pop(next(iter(_memo)))
+
+
+def _memo_get(a: np.ndarray, device):
+    """The device tensor that holds exactly the bytes of `a` (same shape, strides and dtype), or None."""
+    if not _memo or a.flags.writeable:
+        return None
+    root = a
+    while True:                                                   # the array itself or the array it is a view of
+        hit = _memo.get(id(root))
+        if hit is not None and hit[0]() is root:
+            break
+        base = root.base
+        if not isinstance(base, np.ndarray):
+            return None
+        root = base
+    t = hit[1]
+    if root.flags.writeable or root.dtype != a.dtype:
+        return None
+    if device is not None and torch.device(device) != t.device and torch.device(device).index is not None:
+        return None
+    if root is a:
+        return t
+    if a.size == 0 or any(s < 0 or s % a.itemsize for s in a.strides):
+        return None
+    off = a.__array_interface__["data"][0] - root.__array_interface__["data"][0]
+    if off < 0 or off % a.itemsize:
+        return None
+    return torch.as_strided(t.reshape(-1), a.shape, tuple(s // a.itemsize for s in a.strides), off // a.itemsize)
+
+
 def to_device(x, device=None):
     """-> (cuda tensor, was_numpy).  numpy arrays (incl. strided views such as
-    Patcher.patch output) are copied H2D keeping their strides; cuda tensors pass through."""
+    Patcher.patch output) are copied H2D keeping their strides; cuda tensors pass through.  Arrays that this
+    package returned earlier (and views of them) are served from the device memo without a copy."""
     require_cuda()
     if isinstance(x, torch.Tensor):
         if not x.is_cuda:
             return x.to(device or "cuda", non_blocking=x.is_pinned()), False
         return x, False
     a = np.asarray(x)
+    if _MEMO_ON:
+        t = _memo_get(a, device)
+        if t is not None:
+            return t, True
     if a.dtype.type not in _NP_OK:
         a = a.astype(np.float64)
     if any(s < 0 for s in a.strides):
@@ -66,7 +128,10 @@ def to_host(t: torch.Tensor, as_numpy: bool):
     buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
     buf.copy_(t, non_blocking=True)
     torch.cuda.current_stream(t.device).synchronize()
-    return buf.numpy()
+    arr = buf.numpy()
+    if _MEMO_ON:
+        _memo_put(arr, t)
+    return arr
 
 
 def stream_ptr(device: torch.device) -> int:

@@ -173,8 +173,12 @@ class PFrameBlockCoder:
         _lib.check(st, "ivc_me_full_search")
         return to_host(mv if batched else mv[0], was_np)
 
-    def forward(self, cur, ref, mv, return_prediction=False):
-        """residual = cur - MC(ref, mv); -> scan indices ``[(N,) Hp, Wp, 3, 64]`` (and the prediction)."""
+    def forward(self, cur, ref, mv, return_prediction=False, channels=3):
+        """residual = cur - MC(ref, mv); -> scan indices ``[(N,) Hp, Wp, 3, 64]`` (and the prediction).
+        ``channels=2`` stores channels 0 and 1 only (``[(N,) Hp, Wp, 2, 64]``): numpy broadcasting quantises the one
+        luma residual against ``[lum, chrom, chrom]`` (patchquant.py:40,59), so channel 2 repeats channel 1 bit for
+        bit whenever the two chrominance tables are the same array -- a pipeline that ships symbols to the host
+        need not compute, store or send it (``inverse`` reads channel 0 of either layout)."""
         c, was_np = to_device(cur)
         r, _ = to_device(ref, c.device)
         m, _ = to_device(mv, c.device)
@@ -185,12 +189,14 @@ class PFrameBlockCoder:
         cv = c if batched else c[None]
         N, H, W = cv.shape
         _, dtab = self.quant._table_on(c.device)
-        zz = torch.empty((N, H // 8, W // 8, 3, 64), dtype=torch.int32, device=c.device)
+        if channels not in (2, 3):
+            raise ValueError("channels must be 3 (the reference's layout) or 2 (channels 0 and 1)")
+        zz = torch.empty((N, H // 8, W // 8, channels, 64), dtype=torch.int32, device=c.device)
         pred = torch.empty_like(cv) if return_prediction else None
-        st = _lib.lib.ivc_pframe_forward(dev_index(c), stream_ptr(c.device), cv.data_ptr(), r.data_ptr(), m.data_ptr(),
-                                         _lib.F64, N, H, W, int(self.search_range), dtab.data_ptr(), code(dtab.dtype),
-                                         pred.data_ptr() if pred is not None else None, zz.data_ptr())
-        _lib.check(st, "ivc_pframe_forward")
+        st = _lib.lib.ivc_pframe_forward_ch(dev_index(c), stream_ptr(c.device), cv.data_ptr(), r.data_ptr(), m.data_ptr(),
+                                            _lib.F64, N, H, W, int(self.search_range), dtab.data_ptr(), code(dtab.dtype),
+                                            pred.data_ptr() if pred is not None else None, channels, zz.data_ptr())
+        _lib.check(st, "ivc_pframe_forward_ch")
         zz = zz if batched else zz[0]
         if return_prediction:
             return to_host(zz, was_np), to_host(pred if batched else pred[0], was_np)

@@ -17,11 +17,28 @@ int cuda_fail(cudaError_t e) {
     return IVC_ERR_CUDA;
 }
 
-int enter(int device) {
-    cudaError_t e = cudaSetDevice(device);
-    if (e != cudaSuccess) return cuda_fail(e);
-    return IVC_OK;
-}
+// Every entry point runs on `device` and leaves the calling thread's current device as it found it
+// (a caller such as PyTorch keeps its own notion of the current device per thread).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) {
+            err = cudaSetDevice(device);
+            switched = err == cudaSuccess;
+        }
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+#define IVC_ENTER(device)               \
+    DeviceGuard ivc_device_guard_(device); \
+    if (ivc_device_guard_.err != cudaSuccess) return cuda_fail(ivc_device_guard_.err)
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline bool is_float(int dt) { return dt == IVC_F32 || dt == IVC_F64; }
@@ -67,8 +84,7 @@ int ivc_dct8x8(int device, void *stream, int inverse, const void *x, int x_dtype
     if (x_dtype != IVC_U8 && x_dtype != IVC_I32 && x_dtype != IVC_F32 && x_dtype != IVC_F64) return IVC_ERR_DTYPE;
     const int want = (x_dtype == IVC_F32) ? IVC_F32 : IVC_F64;          // scipy keeps f32, promotes the rest to f64
     if (out_dtype != want) return IVC_ERR_DTYPE;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_dct(device, (cudaStream_t)stream, inverse != 0, x, x_dtype, n0, n1, C, strides, out,
                                     want == IVC_F32);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
@@ -88,8 +104,7 @@ static int quant_common(int device, void *stream, bool dequant, const void *x, i
     } else {
         if (elem_size(x_dtype) == 0) return IVC_ERR_DTYPE;
     }
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_quant(device, (cudaStream_t)stream, dequant, x, x_dtype, n0, n1, C, strides, table,
                                       table_dtype, compute_dtype == IVC_F32, out);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
@@ -110,8 +125,7 @@ int ivc_zigzag(int device, void *stream, int inverse, const void *x, int elem_sz
     if (elem_sz != 1 && elem_sz != 2 && elem_sz != 4 && elem_sz != 8) return IVC_ERR_DTYPE;
     if (nblocks == 0) return IVC_OK;
     if (!x || !out || x == out) return IVC_ERR_ARG;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_zigzag(device, (cudaStream_t)stream, inverse != 0, x, elem_sz, nblocks, out);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
@@ -124,8 +138,7 @@ int ivc_intra_forward(int device, void *stream, const void *img, int dtype, int6
     if (n_frames * H * W == 0) return IVC_OK;
     if (!img || !table || !out) return IVC_ERR_ARG;
     if (!aligned16(img) || !aligned16(out) || (frame_stride & 1)) return IVC_ERR_ARG;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_forward(device, (cudaStream_t)stream, img, n_frames, H, W, (int)C, frame_stride, table,
                                         table_dtype, out, nullptr, nullptr, 0, nullptr, false);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
@@ -139,8 +152,7 @@ int ivc_intra_inverse(int device, void *stream, const int32_t *zz, int64_t n_fra
     if (n_frames * Hp * Wp == 0) return IVC_OK;
     if (!zz || !table || !out) return IVC_ERR_ARG;
     if (!aligned16(zz) || !aligned16(out)) return IVC_ERR_ARG;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_inverse(device, (cudaStream_t)stream, zz, n_frames, Hp, Wp, (int)C, table, table_dtype,
                                         out, C == 3 ? 0 : 1, nullptr, nullptr, nullptr, 0);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
@@ -153,8 +165,7 @@ int ivc_intra_inverse_rgb(int device, void *stream, const int32_t *zz, int64_t n
     if (n_frames * Hp * Wp == 0) return IVC_OK;
     if (!zz || !table || !rgb_out) return IVC_ERR_ARG;
     if (!aligned16(zz) || !aligned16(rgb_out)) return IVC_ERR_ARG;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_inverse(device, (cudaStream_t)stream, zz, n_frames, Hp, Wp, 3, table, table_dtype, rgb_out, 3,
                                         nullptr, nullptr, nullptr, 0);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
@@ -180,8 +191,7 @@ int ivc_intra_inverse_sse(int device, void *stream, const int32_t *zz, int64_t n
         if (!aligned16(zz) || !aligned16(orig_rgb8) || (out && !aligned16(out)) || (orig_frame_stride_bytes & 15)) return IVC_ERR_ARG;
     }
     if (!workspace || workspace_bytes < ivc_intra_inverse_sse_workspace_bytes(n_frames, Hp, Wp)) return IVC_ERR_WORKSPACE;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_inverse_sse(device, (cudaStream_t)stream, zz, n_frames, Hp, Wp, table, table_dtype, out,
                                             orig_rgb8, orig_frame_stride_bytes, mode, (double *)workspace, sse_out);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
@@ -204,16 +214,14 @@ int ivc_me_full_search(int device, void *stream, const void *ref, const void *cu
     if (dtype == IVC_U8) {
         // uint8 PLANES holding the frames' values (float semantics, no wrap-around: that is ivc_me_full_search_intdtype).
         // Always integer-valued, so every mode is served by the packed-integer kernel, whose vectors are exact.
-        int rc8 = enter(device);
-        if (rc8) return rc8;
+        IVC_ENTER(device);
         cudaError_t e8 = ivc::launch_me_int(device, (cudaStream_t)stream, ref, cur, IVC_U8, n_frames, H, W, ref_frame_stride,
                                             cur_frame_stride, search_range, mv_out, nullptr, 0);
         return e8 == cudaSuccess ? IVC_OK : cuda_fail(e8);
     }
     if (mode == IVC_ME_AUTO && (!workspace || workspace_bytes < ivc_me_workspace_bytes(n_frames, H, W)))
         return IVC_ERR_WORKSPACE;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaStream_t st = (cudaStream_t)stream;
     const bool f32 = dtype == IVC_F32;
     cudaError_t e;
@@ -241,8 +249,7 @@ int ivc_me_full_search_intdtype(int device, void *stream, const void *ref, const
     if ((H & 7) || (W & 7)) return IVC_ERR_SHAPE;                         // the reference raises on ragged frames
     if (n_frames * H * W == 0) return IVC_OK;
     if (!ref || !cur || !mv_out || H > 2147483647LL || W > 2147483647LL) return IVC_ERR_ARG;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_me_wrap(device, (cudaStream_t)stream, ref, cur, dtype, n_frames, H, W, ref_frame_stride,
                                         cur_frame_stride, search_range, mv_out);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
@@ -255,8 +262,7 @@ int ivc_mc_reconstruct(int device, void *stream, const void *ref, int elem_sz, i
     if ((H & 7) || (W & 7)) return IVC_ERR_SHAPE;
     if (n_frames * H * W * C == 0) return IVC_OK;
     if (!ref || !mv || !out || ref == out) return IVC_ERR_ARG;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_mc(device, (cudaStream_t)stream, ref, elem_sz, n_frames, H, W, C, mv, search_range, out);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
@@ -264,16 +270,22 @@ int ivc_mc_reconstruct(int device, void *stream, const void *ref, int elem_sz, i
 int ivc_pframe_forward(int device, void *stream, const void *cur, const void *ref, const int64_t *mv, int dtype,
                        int64_t n_frames, int64_t H, int64_t W, int search_range, const void *table, int table_dtype,
                        void *pred_out, int32_t *zz_out) {
-    if (n_frames < 0 || H < 0 || W < 0 || search_range < 0) return IVC_ERR_ARG;
+    return ivc_pframe_forward_ch(device, stream, cur, ref, mv, dtype, n_frames, H, W, search_range, table, table_dtype,
+                                 pred_out, 3, zz_out);
+}
+
+int ivc_pframe_forward_ch(int device, void *stream, const void *cur, const void *ref, const int64_t *mv, int dtype,
+                          int64_t n_frames, int64_t H, int64_t W, int search_range, const void *table, int table_dtype,
+                          void *pred_out, int out_channels, int32_t *zz_out) {
+    if (n_frames < 0 || H < 0 || W < 0 || search_range < 0 || (out_channels != 2 && out_channels != 3)) return IVC_ERR_ARG;
     if (dtype != IVC_F64 || !is_float(table_dtype)) return IVC_ERR_DTYPE;
     if ((H & 7) || (W & 7)) return IVC_ERR_SHAPE;
     if (n_frames * H * W == 0) return IVC_OK;
     if (!cur || !ref || !mv || !table || !zz_out) return IVC_ERR_ARG;
     if (!aligned16(cur) || !aligned16(zz_out) || (pred_out && !aligned16(pred_out))) return IVC_ERR_ARG;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_forward(device, (cudaStream_t)stream, cur, n_frames, H, W, 1, H * W, table, table_dtype,
-                                        zz_out, ref, mv, search_range, pred_out, true);
+                                        zz_out, ref, mv, search_range, pred_out, true, out_channels);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
 
@@ -287,8 +299,7 @@ int ivc_pframe_inverse(int device, void *stream, const int32_t *zz, int64_t Czz,
     if (!zz || !table || !recon_out) return IVC_ERR_ARG;
     if (!pred && (!ref || !mv)) return IVC_ERR_ARG;
     if (!aligned16(zz) || !aligned16(recon_out) || (pred && !aligned16(pred))) return IVC_ERR_ARG;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_inverse(device, (cudaStream_t)stream, zz, n_frames, H / 8, W / 8, (int)Czz, table,
                                         table_dtype, recon_out, 2, pred, ref, mv, search_range);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
@@ -311,8 +322,7 @@ int ivc_sum_squared_error(int device, void *stream, const void *a, int a_dtype, 
     if (!sse_out) return IVC_ERR_ARG;
     if (unit_elems > 0 && (!a || !b)) return IVC_ERR_ARG;
     if (!workspace || workspace_bytes < ivc_sse_workspace_bytes(n_units, unit_elems)) return IVC_ERR_WORKSPACE;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_sse(device, (cudaStream_t)stream, a, a_dtype, b, b_dtype, n_units, unit_elems, a_broadcast,
                                     (double *)workspace, sse_out);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
@@ -322,8 +332,7 @@ int ivc_zerorun_count(int device, void *stream, const int32_t *zz, int64_t nbloc
     if (nblocks < 0) return IVC_ERR_ARG;
     if (nblocks == 0) return IVC_OK;
     if (!zz || !counts_out || !aligned16(zz)) return IVC_ERR_ARG;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_zr_count(device, (cudaStream_t)stream, zz, nblocks, counts_out, nullptr);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
@@ -333,9 +342,21 @@ int ivc_zerorun_count_masks(int device, void *stream, const int32_t *zz, int64_t
     if (nblocks < 0) return IVC_ERR_ARG;
     if (nblocks == 0) return IVC_OK;
     if (!zz || !counts_out || !masks_out || !aligned16(zz)) return IVC_ERR_ARG;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_zr_count(device, (cudaStream_t)stream, zz, nblocks, counts_out, masks_out);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
+int ivc_zerorun_symbol_histogram(int device, void *stream, const int32_t *zz, int64_t n_units, int64_t blocks_per_unit,
+                                 int32_t end_of_block, int64_t lo, int64_t n_bins, uint32_t *counts_out,
+                                 uint32_t *outside_out) {
+    if (n_units < 0 || blocks_per_unit < 0 || n_bins < 1 || n_bins > 49152) return IVC_ERR_ARG;      // 192 KB of shared bins
+    if (lo < -2147483647LL || lo > 2147483647LL) return IVC_ERR_ARG;
+    if (n_units == 0) return IVC_OK;
+    if (!counts_out || !outside_out || (blocks_per_unit > 0 && (!zz || !aligned16(zz)))) return IVC_ERR_ARG;
+    IVC_ENTER(device);
+    cudaError_t e = ivc::launch_zr_hist(device, (cudaStream_t)stream, zz, n_units, blocks_per_unit, end_of_block, lo, n_bins,
+                                        counts_out, outside_out);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
 
@@ -344,8 +365,7 @@ int ivc_zerorun_write_masks(int device, void *stream, const int32_t *zz, int64_t
     if (nblocks < 0) return IVC_ERR_ARG;
     if (nblocks == 0) return IVC_OK;
     if (!zz || !offsets || !masks || !symbols_out || !aligned16(zz)) return IVC_ERR_ARG;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_zr_write(device, (cudaStream_t)stream, zz, nblocks, end_of_block, offsets, masks, symbols_out, 4, total_symbols);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
@@ -355,8 +375,7 @@ int ivc_zerorun_write(int device, void *stream, const int32_t *zz, int64_t nbloc
     if (nblocks < 0) return IVC_ERR_ARG;
     if (nblocks == 0) return IVC_OK;
     if (!zz || !offsets || !symbols_out || !aligned16(zz)) return IVC_ERR_ARG;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_zr_write(device, (cudaStream_t)stream, zz, nblocks, end_of_block, offsets, nullptr, symbols_out, 4, -1);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
@@ -366,8 +385,7 @@ int ivc_zerorun_write_masks_i16(int device, void *stream, const int32_t *zz, int
     if (nblocks < 0 || end_of_block > 32767 || end_of_block < -32768) return IVC_ERR_ARG;
     if (nblocks == 0) return IVC_OK;
     if (!zz || !offsets || !masks || !symbols_out || !aligned16(zz)) return IVC_ERR_ARG;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_zr_write(device, (cudaStream_t)stream, zz, nblocks, end_of_block, offsets, masks, symbols_out, 2, total_symbols);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
@@ -383,8 +401,7 @@ int ivc_zerorun_offsets(int device, void *stream, const int32_t *counts, int64_t
     if (nblocks == 0) return IVC_OK;
     if (!counts || !offsets_out || !aligned16(counts)) return IVC_ERR_ARG;
     if (!workspace || workspace_bytes < ivc::zr_offsets_workspace_bytes(nblocks)) return IVC_ERR_WORKSPACE;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_zr_offsets((cudaStream_t)stream, counts, nblocks, offsets_out, workspace, total_mapped_out,
                                            total_dev_out);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
@@ -394,8 +411,7 @@ int ivc_post_words_to_host(int device, void *stream, const int64_t *src, int64_t
     if (n < 0 || n > 32) return IVC_ERR_ARG;
     if (n == 0) return IVC_OK;
     if (!src || !dst_mapped) return IVC_ERR_ARG;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_post_words((cudaStream_t)stream, src, dst_mapped, n);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
@@ -405,8 +421,7 @@ int ivc_zerorun_decode_mark(int device, void *stream, const int32_t *symbols, in
     if (n_symbols < 0) return IVC_ERR_ARG;
     if (n_symbols == 0) return IVC_OK;
     if (!symbols || !is_eob_out) return IVC_ERR_ARG;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_zrd_mark(device, (cudaStream_t)stream, symbols, n_symbols, end_of_block, is_eob_out);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
@@ -416,8 +431,7 @@ int ivc_zerorun_decode_ends(int device, void *stream, const int32_t *is_eob, con
     if (n_symbols < 0 || n_blocks < 0) return IVC_ERR_ARG;
     if (n_symbols == 0 || n_blocks == 0) return IVC_OK;
     if (!is_eob || !rank || !ends_out) return IVC_ERR_ARG;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_zrd_ends(device, (cudaStream_t)stream, is_eob, rank, n_symbols, n_blocks, ends_out);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
@@ -427,8 +441,7 @@ int ivc_zerorun_decode_write(int device, void *stream, const int32_t *symbols, c
     if (n_blocks < 0) return IVC_ERR_ARG;
     if (n_blocks == 0) return IVC_OK;
     if (!symbols || !ends || !blocks_out || !err_out) return IVC_ERR_ARG;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_zrd_write(device, (cudaStream_t)stream, symbols, ends, n_blocks, blocks_out, (int *)err_out);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
@@ -437,8 +450,7 @@ int ivc_symbol_minmax(int device, void *stream, const void *x, int dtype, int64_
     if (n < 0) return IVC_ERR_ARG;
     if (dtype != IVC_U8 && dtype != IVC_I32 && dtype != IVC_I64) return IVC_ERR_DTYPE;
     if (!minmax_out || (n > 0 && !x)) return IVC_ERR_ARG;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_minmax(device, (cudaStream_t)stream, x, dtype, n, minmax_out);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
@@ -449,8 +461,7 @@ int ivc_symbol_histogram(int device, void *stream, const void *x, int dtype, int
     if (dtype != IVC_U8 && dtype != IVC_I32 && dtype != IVC_I64) return IVC_ERR_DTYPE;
     if (n_bins == 0) return IVC_OK;
     if (!counts_out || (n > 0 && !x)) return IVC_ERR_ARG;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_hist(device, (cudaStream_t)stream, x, dtype, n, lo, n_bins, hot, counts_out);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
@@ -460,8 +471,7 @@ int ivc_rgb2ycbcr(int device, void *stream, const void *rgb, int dtype, int64_t 
     if (dtype != IVC_U8 && dtype != IVC_I32 && dtype != IVC_F32 && dtype != IVC_F64) return IVC_ERR_DTYPE;
     if (npixels == 0) return IVC_OK;
     if (!rgb || !ycbcr_out) return IVC_ERR_ARG;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_color(device, (cudaStream_t)stream, false, rgb, dtype, npixels, (double *)ycbcr_out);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
@@ -470,8 +480,7 @@ int ivc_rgb8_to_luma8(int device, void *stream, const void *rgb, int64_t npixels
     if (npixels < 0) return IVC_ERR_ARG;
     if (npixels == 0) return IVC_OK;
     if (!rgb || !luma_out) return IVC_ERR_ARG;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_rgb8_luma8(device, (cudaStream_t)stream, rgb, npixels, luma_out, luma_f64_out);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
@@ -480,8 +489,7 @@ int ivc_ycbcr2rgb(int device, void *stream, const void *ycbcr, int64_t npixels, 
     if (npixels < 0) return IVC_ERR_ARG;
     if (npixels == 0) return IVC_OK;
     if (!ycbcr || !rgb_out) return IVC_ERR_ARG;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_color(device, (cudaStream_t)stream, true, ycbcr, IVC_F64, npixels, (double *)rgb_out);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
@@ -494,8 +502,7 @@ int ivc_intra_forward_rgb8(int device, void *stream, const void *rgb, int64_t n_
     if (n_frames * H * W == 0) return IVC_OK;
     if (!rgb || !table || !out) return IVC_ERR_ARG;
     if (!aligned16(rgb) || !aligned16(out) || (frame_stride_bytes & 15)) return IVC_ERR_ARG;
-    int rc = enter(device);
-    if (rc) return rc;
+    IVC_ENTER(device);
     cudaError_t e = ivc::launch_forward_rgb8(device, (cudaStream_t)stream, rgb, n_frames, H, W, frame_stride_bytes, table,
                                              table_dtype, out);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);

@@ -9,7 +9,7 @@ namespace ivc {
 // launchers implemented in ivc_transform.cu
 cudaError_t launch_forward(int device, cudaStream_t st, const void *img, int64_t n, int64_t H, int64_t W, int C,
                            int64_t frame_stride, const void *table, int table_dtype, int32_t *out,
-                           const void *ref, const int64_t *mv, int sr, void *pred_out, bool pframe);
+                           const void *ref, const int64_t *mv, int sr, void *pred_out, bool pframe, int out_channels = 3);
 cudaError_t launch_inverse(int device, cudaStream_t st, const int32_t *zz, int64_t n, int64_t Hp, int64_t Wp, int Czz,
                            const void *table, int table_dtype, void *out, int mode,
                            const void *pred, const void *ref, const int64_t *mv, int sr);
@@ -47,6 +47,9 @@ cudaError_t launch_zr_count(int device, cudaStream_t st, const int32_t *zz, int6
 cudaError_t launch_zr_write(int device, cudaStream_t st, const int32_t *zz, int64_t nblocks, int32_t eob,
                             const int64_t *offsets, const uint64_t *masks, void *out, int out_elem_size,
                             int64_t total_symbols);
+
+cudaError_t launch_zr_hist(int device, cudaStream_t st, const int32_t *zz, int64_t n_units, int64_t blocks_per_unit, int32_t eob,
+                           int64_t lo, int64_t nbins, uint32_t *counts, uint32_t *outside);
 
 cudaError_t launch_zrd_mark(int device, cudaStream_t st, const int32_t *sym, int64_t n, int32_t eob, int32_t *is_eob);
 cudaError_t launch_zrd_ends(int device, cudaStream_t st, const int32_t *is_eob, const int64_t *rank, int64_t n,

@@ -155,12 +155,12 @@ static __device__ __noinline__ int quantize_exact_f64(double x, double t) {
 // lies within 2^-17 of a half-integer.  y + 1.5*2^36 exposes y as a fixed-point number with 16
 // fractional bits in the low mantissa word; the exact IEEE division is taken only when those 16
 // bits read exactly one half (probability 2^-16 on generic data, always on true ties) or when
-// |y| >= 2^15 (or NaN/Inf).
+// |y| >= 2^15 - 1 (or NaN/Inf; for y in [32767.5, 32768) the rounding add below would wrap).
 __device__ __forceinline__ int quantize_f64(double x, double t, double rt) {
     const double y = __dmul_rn(x, rt);
     const double sft = __dadd_rn(y, 103079215104.0);          // 1.5 * 2^36
     const int lo = __double2loint(sft);
-    const bool ok = (fabs(y) < 32768.0) & ((lo & 0xFFFF) != 0x8000);
+    const bool ok = (fabs(y) < 32767.0) & ((lo & 0xFFFF) != 0x8000);
     if (__builtin_expect(ok, 1)) return (lo + 0x8000) >> 16;
     return quantize_exact_f64(x, t);
 }

@@ -183,7 +183,12 @@ __global__ void __launch_bounds__(kHistThreads) k_hist(const void *x, int dtype,
     }
 }
 
-// out[0] = min, out[1] = max (int64; the caller initialises them to INT64_MAX / INT64_MIN)
+__global__ void k_minmax_init(long long *out) {
+    out[0] = 0x7fffffffffffffffLL;
+    out[1] = -0x7fffffffffffffffLL - 1;
+}
+
+// out[0] = min, out[1] = max (int64; k_minmax_init sets them to INT64_MAX / INT64_MIN first)
 __global__ void __launch_bounds__(kHistThreads) k_minmax(const void *x, int dtype, int64_t n, long long *out) {
     long long mn = 0x7fffffffffffffffLL, mx = -0x7fffffffffffffffLL - 1;
     for (int64_t i = (int64_t)blockIdx.x * kHistThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kHistThreads) {
@@ -217,8 +222,8 @@ cudaError_t launch_hist(int device, cudaStream_t st, const void *x, int dtype, i
 }
 
 cudaError_t launch_minmax(int device, cudaStream_t st, const void *x, int dtype, int64_t n, int64_t *out) {
-    const long long init[2] = {0x7fffffffffffffffLL, -0x7fffffffffffffffLL - 1};
-    cudaError_t e = cudaMemcpyAsync(out, init, sizeof(init), cudaMemcpyHostToDevice, st);   // pageable 16 B: staged by the driver
+    k_minmax_init<<<1, 1, 0, st>>>((long long *)out);      // a kernel, not a copy from host memory: capturable in a CUDA graph
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || n == 0) return e;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);

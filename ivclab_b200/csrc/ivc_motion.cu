@@ -15,13 +15,13 @@
 // lexicographic on (ssd, index) == the reference's "first strict minimum in (dy, dx) raster order"
 // (motion.py:35-51).
 //
-// K3 integer (k_me_int<T>): reads the float frames directly, converts them to packed uint8 while
-// staging (raising a device flag if any value is not an integer in [0,255]) and evaluates SSDs with
-// __vabsdiffu4 + __dp4a (4 pixels per instruction, exact integers).  Tasks of all blocks of the tile
-// are flattened over the CTA's threads; the per-block argmin is a shared-memory atomicMin on the
-// packed key (ssd << k | index).  ivc_me_full_search(IVC_ME_AUTO) launches k_me_int and then
-// k_me_exact, which exits immediately unless the flag was raised -- no host round trip, no workspace
-// beyond the 4-byte flag.
+// K3 integer (k_me_int<T,G,PC>): reads the float frames directly (or uint8 planes as they are), converts them to
+// packed uint8 while staging (raising a device flag if any value is not an integer in [0,255]) and evaluates
+// SSD = sum(c^2) + sum(r^2) - 2 sum(c r): the cross term is one __dp4a per four candidate-pixels, sum(r^2) comes
+// from a per-window-position table built once per CTA, sum(c^2) once per block -- all exact integers.  Tasks of
+// all blocks of the tile are flattened over the CTA's threads; the per-block argmin is a shared-memory atomicMin
+// on the packed key (ssd, index).  ivc_me_full_search(IVC_ME_AUTO) launches k_me_int and then k_me_exact, which
+// exits immediately unless the flag was raised -- no host round trip, no workspace beyond the 4-byte flag.
 #include <cstdlib>
 #include "ivc_dct.cuh"
 #include "ivc_common.cuh"

@@ -116,6 +116,7 @@ struct FwdArgs {
     const int64_t *mv;
     int sr;
     double *pred_out;                // may be null
+    int och;                         // P-frame: scan channels stored per block (3 = the reference's broadcast; 2 = tables 0 and 1 only)
 };
 
 template <int C, bool PFRAME>
@@ -237,7 +238,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward(const FwdArgs 
         __syncwarp();                                   // transposition buffer is dead
 
         // ---- phase 4: quantise, zig-zag scatter into staging, coalesced 16-byte stores ----
-        int32_t *outf = a.out + ((frame * g.Hp + by) * (int64_t)g.Wp) * 192;
+        const int och = PFRAME ? a.och : 3;
+        int32_t *outf = a.out + ((frame * g.Hp + by) * (int64_t)g.Wp) * (64 * och);
         if (C == 3) {
 #pragma unroll
             for (int m = 0; m < 3; ++m)
@@ -275,9 +277,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward(const FwdArgs 
                     const int id = lane + 32 * k, chunk = id >> 4, part = id & 15;
                     const int cu = chunk / 3, ch = chunk - cu * 3;
                     const int blk = 3 * cu + m;
-                    if (blk < nb) {
+                    if (blk < nb && ch < och) {
                         const int4 v = *reinterpret_cast<const int4 *>(ibuf + cu * kStageU + ch * 64 + part * 4);
-                        stg_stream(reinterpret_cast<int4 *>(outf + ((int64_t)(b0 + blk) * 3 + ch) * 64 + part * 4), v);
+                        stg_stream(reinterpret_cast<int4 *>(outf + ((int64_t)(b0 + blk) * och + ch) * 64 + part * 4), v);
                     }
                 }
                 __syncwarp();
@@ -555,7 +557,7 @@ struct QuantGuard {
         nz = min(nz, (unsigned)((lo & 0xFFFF) ^ 0x8000));
         return (lo + 0x8000) >> 16;
     }
-    __device__ __forceinline__ bool risky() const { return (mx >= 0x40E00000) | (nz == 0u); }   // |y| >= 2^15, NaN, tie
+    __device__ __forceinline__ bool risky() const { return (mx >= 0x40DFFFC0) | (nz == 0u); }   // |y| >= 2^15 - 1 (the rounding add would wrap at 32767.5), NaN, tie
 };
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_c3_tma(const FwdArgs a) {
@@ -1206,7 +1208,8 @@ __global__ void __launch_bounds__(kPfWarps * 32, 1) k_pframe_forward_tma(const F
         __syncwarp();
         // numpy broadcasting: the single luma channel is quantised with all three tables
         // (patchquant.py:59).  One round per sub-block m; staging regions A/B/A.
-        int32_t *outf = a.out + ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0) * 192;
+        const int och64 = 64 * a.och;
+        int32_t *outf = a.out + ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0) * och64;
 #pragma unroll
         for (int m = 0; m < 3; ++m) {
             const int reg = (m & 1) * 3200;
@@ -1237,7 +1240,7 @@ __global__ void __launch_bounds__(kPfWarps * 32, 1) k_pframe_forward_tma(const F
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane < 4 && 3 * lane + m < nb) bulk_s2g(outf + (3 * lane + m) * 192, work_s + reg + lane * (kStageU * 4), 768u);
+            if (lane < 4 && 3 * lane + m < nb) bulk_s2g(outf + (3 * lane + m) * och64, work_s + reg + lane * (kStageU * 4), 256u * (uint32_t)a.och);
             bulk_commit();                                // every lane commits (possibly empty) groups: counts stay in step
         }
         cur = nxt;
@@ -1639,13 +1642,13 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pframe_forward_tm(const Fw
 #pragma unroll
                     for (int v = 0; v < 8; ++v) *reinterpret_cast<int *>(zz_wr[v] + ch * 256) = qv[ch < NCH ? ch : NCH - 1][v];
             };
-            if (chroma_twice) quantise(std::integral_constant<int, 2>{});
+            if (chroma_twice || a.och == 2) quantise(std::integral_constant<int, 2>{});
             else quantise(std::integral_constant<int, 3>{});
             fence_proxy_async();
             __syncwarp();
-            if (lane < 4 && lane + 4 * m < nb)            // lane u stores the 3 scan blocks of image block u + 4m
-                bulk_s2g(a.out + ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0 + lane + 4 * m) * 192,
-                         work_s + lane * (kStageUF * 4), 768u);
+            if (lane < 4 && lane + 4 * m < nb)            // lane u stores the och (3, or 2) scan blocks of image block u + 4m
+                bulk_s2g(a.out + ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0 + lane + 4 * m) * (64 * a.och),
+                         work_s + lane * (kStageUF * 4), 256u * (uint32_t)a.och);
             bulk_commit();                                // every lane commits (possibly empty) groups: counts stay in step
         }
         cur = nxt;
@@ -2013,8 +2016,9 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
 
 cudaError_t launch_forward(int device, cudaStream_t st, const void *img, int64_t n, int64_t H, int64_t W, int C,
                            int64_t frame_stride, const void *table, int table_dtype, int32_t *out,
-                           const void *ref, const int64_t *mv, int sr, void *pred_out, bool pframe) {
+                           const void *ref, const int64_t *mv, int sr, void *pred_out, bool pframe, int out_channels) {
     FwdArgs a;
+    a.och = pframe ? out_channels : 3;
     a.g = make_geom(n, H, W, C, C == 3 ? 4 : 12);
     a.img = (const double *)img; a.frame_stride = frame_stride; a.table = table; a.table_dtype = table_dtype;
     a.out = out; a.ref = (const double *)ref; a.mv = mv; a.sr = sr; a.pred_out = (double *)pred_out;
@@ -2054,7 +2058,7 @@ cudaError_t launch_forward_rgb8(int device, cudaStream_t st, const void *rgb, in
     FwdArgs a;
     a.g = make_geom(n, H, W, 3, 4);
     a.img = (const double *)rgb; a.frame_stride = frame_stride_bytes; a.table = table; a.table_dtype = table_dtype;
-    a.out = out; a.ref = nullptr; a.mv = nullptr; a.sr = 0; a.pred_out = nullptr;
+    a.out = out; a.ref = nullptr; a.mv = nullptr; a.sr = 0; a.pred_out = nullptr; a.och = 3;
     if (a.g.total_tiles == 0) return cudaSuccess;
     const size_t smem = 3200 + (size_t)kWarpsPerCta * kRgbBuf;
     cudaError_t e;

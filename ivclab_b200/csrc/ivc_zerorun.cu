@@ -146,6 +146,85 @@ __global__ void __launch_bounds__(256) k_zr_write_sparse(const int32_t *__restri
     }
 }
 
+// ---- symbol statistics of the stream, without the stream -------------------------------------------
+// What IntraCodec.train_huffman_from_image needs from image2symbols is the marginal histogram of the symbols
+// (intracodec.py:160-166), not their order: per block the non-zero coefficients, one zero marker and one run length
+// per zero run below the last non-zero coefficient, and one EOB.  k_zr_hist counts exactly that from the scan
+// blocks, per UNIT (frame): a rate-distortion sweep gets its rate statistics with one read of the indices and
+// neither a count / scan / write pass nor a symbol buffer.  counts[u][k] = symbols of unit u equal to lo + k
+// (uint32), outside[u] = symbols outside [lo, lo + nbins).  Grid: x = CTAs sharing a unit, y = unit; per-CTA
+// histogram in shared memory; zero markers and EOBs (a third of a typical stream) are counted in registers.
+__global__ void __launch_bounds__(kZrWarps * 32) k_zr_hist(const int32_t *__restrict__ zz, int64_t blocks_per_unit, int32_t eob,
+                                                           int lo, int nbins, uint32_t *__restrict__ counts,
+                                                           uint32_t *__restrict__ outside) {
+    extern __shared__ unsigned s_hist[];
+    const int lane = threadIdx.x & 31;
+    for (int k = threadIdx.x; k < nbins; k += kZrWarps * 32) s_hist[k] = 0u;
+    __syncthreads();
+    const int64_t unit = blockIdx.y;
+    const int32_t *zu = zz + unit * blocks_per_unit * 64;
+    unsigned n_zero = 0, n_eob = 0, n_out = 0;
+    const auto add = [&](int v) {
+        const unsigned k = (unsigned)(v - lo);
+        if (k < (unsigned)nbins) atomicAdd(&s_hist[k], 1u);
+        else ++n_out;
+    };
+    const int64_t warp = (int64_t)blockIdx.x * kZrWarps + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * kZrWarps;
+    for (int64_t blk0 = warp * 32; blk0 < blocks_per_unit; blk0 += nw * 32) {
+        unsigned long long mine_m = 0;
+#pragma unroll 1
+        for (int sub = 0; sub < 32; sub += kZrBatch) {
+            int a[kZrBatch], b[kZrBatch];
+#pragma unroll
+            for (int j = 0; j < kZrBatch; ++j) {
+                const int64_t blk = blk0 + sub + j;
+                a[j] = b[j] = 0;
+                if (blk < blocks_per_unit) {
+                    a[j] = __ldg(zu + blk * 64 + lane);
+                    b[j] = __ldg(zu + blk * 64 + 32 + lane);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kZrBatch; ++j) {
+                const unsigned ml = __ballot_sync(0xffffffffu, a[j] != 0), mh = __ballot_sync(0xffffffffu, b[j] != 0);
+                if (lane == sub + j) mine_m = (unsigned long long)ml | ((unsigned long long)mh << 32);
+                if (a[j] != 0) add(a[j]);                                             // every non-zero coefficient is a symbol
+                if (b[j] != 0) add(b[j]);
+            }
+        }
+        if (blk0 + lane < blocks_per_unit) {                                          // lane j: the runs of block blk0 + j
+            ++n_eob;
+            if (mine_m) {
+                unsigned long long S = zr_run_starts(mine_m);
+                n_zero += (unsigned)__popcll(S);
+                while (S) {
+                    const int p = __ffsll((long long)S) - 1;
+                    add(__ffsll((long long)(mine_m >> p)) - 1);                       // the run length that follows the marker
+                    S &= S - 1;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        n_zero += __shfl_xor_sync(0xffffffffu, n_zero, off);
+        n_eob += __shfl_xor_sync(0xffffffffu, n_eob, off);
+        n_out += __shfl_xor_sync(0xffffffffu, n_out, off);
+    }
+    if (lane == 0) {
+        const unsigned kz = (unsigned)(0 - lo), ke = (unsigned)(eob - lo);
+        if (kz < (unsigned)nbins) atomicAdd(&s_hist[kz], n_zero); else n_out += n_zero;
+        if (ke < (unsigned)nbins) atomicAdd(&s_hist[ke], n_eob); else n_out += n_eob;
+        if (n_out) atomicAdd(outside + unit, n_out);
+    }
+    __syncthreads();
+    uint32_t *cu = counts + unit * (int64_t)nbins;
+    for (int k = threadIdx.x; k < nbins; k += kZrWarps * 32) {
+        const unsigned c = s_hist[k];
+        if (c) atomicAdd(cu + k, c);
+    }
+}
+
 // ---- decode --------------------------------------------------------------------------------------
 // is_eob[i] = 1 iff symbol i is an EOB in a symbol slot (i.e. not the run length after a zero marker)
 __global__ void __launch_bounds__(256) k_zrd_mark(const int32_t *__restrict__ sym, int64_t n, int32_t eob,
@@ -359,6 +438,30 @@ cudaError_t launch_zr_write(int device, cudaStream_t st, const int32_t *zz, int6
         k_zr_write<true, int32_t><<<grid, kZrWarps * 32, 0, st>>>(zz, nblocks, eob, offsets, mk, (int32_t *)out);
     } else {
         k_zr_write<false, int32_t><<<grid, kZrWarps * 32, 0, st>>>(zz, nblocks, eob, offsets, nullptr, (int32_t *)out);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_zr_hist(int device, cudaStream_t st, const int32_t *zz, int64_t n_units, int64_t blocks_per_unit, int32_t eob,
+                           int64_t lo, int64_t nbins, uint32_t *counts, uint32_t *outside) {
+    if (n_units == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (size_t)(n_units * nbins), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(outside, 0, sizeof(uint32_t) * (size_t)n_units, st);
+    if (e != cudaSuccess || blocks_per_unit == 0) return e;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const size_t smem = (size_t)nbins * sizeof(unsigned);
+    if ((e = cudaFuncSetAttribute(k_zr_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    // CTAs per unit: enough to fill the GPU about four times over across all units, each with at least a few
+    // rounds of 256 blocks so that zeroing and flushing the shared histogram stays a small part of its work
+    int64_t per_unit = ((int64_t)sms * 4 + n_units - 1) / n_units;
+    const int64_t most = (blocks_per_unit + 4 * 32 * kZrWarps - 1) / (4 * 32 * kZrWarps);
+    if (per_unit > most) per_unit = most;
+    if (per_unit < 1) per_unit = 1;
+    for (int64_t u0 = 0; u0 < n_units; u0 += 65535) {
+        const int64_t nu = n_units - u0 < 65535 ? n_units - u0 : 65535;
+        k_zr_hist<<<dim3((unsigned)per_unit, (unsigned)nu), kZrWarps * 32, smem, st>>>(
+            zz + u0 * blocks_per_unit * 64, blocks_per_unit, eob, (int)lo, (int)nbins, counts + u0 * nbins, outside + u0);
     }
     return cudaGetLastError();
 }

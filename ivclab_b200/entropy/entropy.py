@@ -10,7 +10,7 @@ import torch
 from .. import _lib
 from .._runtime import code, dev_index, stream_ptr, to_device
 
-__all__ = ["stats_marg", "symbol_minmax", "symbol_histogram"]
+__all__ = ["stats_marg", "symbol_minmax", "symbol_histogram", "zerorun_symbol_histogram"]
 
 _INT = (torch.uint8, torch.int32, torch.int64)
 
@@ -51,6 +51,31 @@ def symbol_histogram(symbols, lo: int, n_bins: int, hot: int = 4000) -> torch.Te
     _lib.check(_lib.lib.ivc_symbol_histogram(dev_index(t), stream_ptr(t.device), t.data_ptr(), code(t.dtype), t.numel(),
                                              int(lo), int(n_bins), int(hot), counts.data_ptr()), "ivc_symbol_histogram")
     return counts
+
+
+def zerorun_symbol_histogram(flat_patch_img, lo: int = -4096, n_bins: int = 8192, end_of_block: int = 4000):
+    """Per-frame histogram of the zero-run symbol stream, computed from the scan blocks WITHOUT writing the stream:
+    for ``[N, h, w, c, 64]`` (or ``[h, w, c, 64]``) int32 blocks returns ``(counts, outside)`` with ``counts[i]``
+    == ``np.histogram(ZeroRunCoder(end_of_block).encode(blocks[i]), bins=np.arange(lo, lo + n_bins + 1))[0]`` as
+    int64-compatible uint32 counts (an int32 CUDA tensor ``[N, n_bins]``) and ``outside[i]`` the number of symbols
+    that fall outside ``[lo, lo + n_bins)`` (zero when the range is wide enough: then ``counts[i].sum()`` is the
+    stream length, ``counts / counts.sum()`` the ``stats_marg`` pmf and the first / last non-zero bin the min / max
+    that ``train_huffman_from_image`` derives its bounds from, intracodec.py:160-166).  No host synchronisation."""
+    t, _ = to_device(flat_patch_img)
+    if t.ndim not in (4, 5) or t.shape[-1] != 64:
+        raise ValueError(f"expected [h, w, c, 64] or [n, h, w, c, 64] scan blocks, got shape {tuple(t.shape)}")
+    single = t.ndim == 4
+    t = t.to(torch.int32).contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()
+    n = 1 if single else t.shape[0]
+    bpu = t.numel() // 64 // max(n, 1)
+    counts = torch.empty((n, int(n_bins)), dtype=torch.int32, device=t.device)
+    outside = torch.empty(n, dtype=torch.int32, device=t.device)
+    _lib.check(_lib.lib.ivc_zerorun_symbol_histogram(dev_index(t), stream_ptr(t.device), t.data_ptr(), n, bpu, int(end_of_block),
+                                                     int(lo), int(n_bins), counts.data_ptr(), outside.data_ptr()),
+               "ivc_zerorun_symbol_histogram")
+    return (counts[0], outside[0]) if single else (counts, outside)
 
 
 def stats_marg(image, pixel_range):

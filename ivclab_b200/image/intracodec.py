@@ -51,10 +51,17 @@ class IntraCodec:
                 y = y[:, :, None]
             H, W, C = y.shape
             ph, pw = (8 - H % 8) % 8, (8 - W % 8) % 8
+            keep_f32 = y.dtype == torch.float32             # only reachable with is_source_rgb=False (rgb2ycbcr returns float64)
             if ph or pw:                                    # np.pad(..., mode='edge') of intracodec.py:57-62
-                y = torch.nn.functional.pad(y.permute(2, 0, 1)[None].to(torch.float64), (0, pw, 0, ph), mode="replicate")[0]
+                y = torch.nn.functional.pad(y.permute(2, 0, 1)[None].to(torch.float32 if keep_f32 else torch.float64),
+                                            (0, pw, 0, ph), mode="replicate")[0]
                 y = y.permute(1, 2, 0)
-            zz = self._coder.forward(y.to(torch.float64).contiguous())
+            if keep_f32:
+                # the reference keeps float32 end to end here (scipy's dct stays float32 and the division by a float32
+                # table happens in float32, dct.py:24-26, patchquant.py:59): the per-method classes have those paths
+                zz = self.zigzag.flatten(self.quant.quantize(self.dct.transform(self.patcher.patch(y.contiguous()))))
+            else:
+                zz = self._coder.forward(y.to(torch.float64).contiguous())
         return to_host(self.zerorun.encode(zz), was_np)
 
     # ---- intracodec.py:82-141 ----------------------------------------------------------------------
@@ -69,7 +76,9 @@ class IntraCodec:
         decoded = self.zerorun.decode(symbols if isinstance(symbols, (torch.Tensor, np.ndarray)) else np.asarray(symbols),
                                       [H // 8, W // 8, C])
         d, _ = to_device(decoded)
-        out = self._coder.inverse(d, to_rgb=is_rgb)         # [8Hp, 8Wp, 3]; colour transform inside the decoder's store
+        # [8Hp, 8Wp, 3]; colour transform inside the decoder's store.  A 3-element shape with C == 1 takes the
+        # reference's `if C == 1` branch (intracodec.py:130-136): the three-table decode is returned unconverted
+        out = self._coder.inverse(d, to_rgb=(is_rgb and C == 3))
         if out.shape[0] != H or out.shape[1] != W:
             out = out[:H, :W, :]
         return to_host(out, was_np)

@@ -2,9 +2,10 @@
 
 Images, sequences and GOPs are independent, so the path shards with NO data-path collective:
 rank ``r`` of ``world`` owns a contiguous range of units, runs the kernels on its own GPU and
-stream, and the host gathers the (small) per-unit results -- scan-index tensors, motion vectors,
-PSNR scalars -- in unit order.  The gather uses ``torch.distributed`` object collectives (NCCL
-process group on GPUs, gloo in the CPU tests); NVLink is not on the data path by design."""
+stream, and the host gathers the (small) per-unit results -- symbol statistics, motion vectors,
+PSNR scalars -- in unit order.  Bulk results travel as tensors (``gather_rows``: one ``dist.gather`` of
+equal-sized blocks, device tensors under NCCL, host tensors under gloo), odd-shaped Python results as
+objects (``gather_in_order``).  The gather is the only exchange; nothing on the coding path uses a collective."""
 from __future__ import annotations
 
 from typing import Callable, List, Sequence, Tuple
@@ -12,7 +13,7 @@ from typing import Callable, List, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "shard_round_robin", "run_sharded", "gather_in_order"]
+__all__ = ["shard_range", "shard_round_robin", "run_sharded", "gather_in_order", "gather_rows"]
 
 
 def shard_range(n_units: int, rank: int, world: int) -> Tuple[int, int]:
@@ -62,3 +63,42 @@ def run_sharded(n_units: int, work: Callable[[int], object], contiguous: bool = 
     else:
         mine = shard_round_robin(n_units, rank, world)
     return gather_in_order([work(u) for u in mine], mine, n_units, dst)
+
+
+def gather_rows(local: torch.Tensor, n_units: int, dst: int = 0, axis: int = 0, out: torch.Tensor = None):
+    """Host gather for contiguous-range sharding (``shard_range``): rank r holds the slice ``[lo_r, hi_r)`` of
+    ``axis`` of a ``[.., n_units, ..]`` array; rank ``dst`` gets the whole array in unit order (others None).
+    One ``dist.gather`` of tensors -- no pickling: every rank contributes a block padded to the largest shard
+    (shards differ by at most one unit).  Under NCCL ``local`` is a CUDA tensor and the result arrives on ``dst``'s
+    device; pass a pinned host tensor as ``out`` to have it copied there (the device-to-host read that ends the
+    gather).  Without an initialised process group the input is returned (copied into ``out`` if given)."""
+    on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    if not on:
+        if local.shape[axis] != n_units:
+            raise ValueError(f"single process: the local shard must hold all {n_units} units, got {local.shape[axis]}")
+        if out is not None:
+            out.copy_(local)
+            return out
+        return local
+    rank, world = dist.get_rank(), dist.get_world_size()
+    lo, hi = shard_range(n_units, rank, world)
+    if local.shape[axis] != hi - lo:
+        raise ValueError(f"rank {rank} owns units [{lo}, {hi}) but holds {local.shape[axis]} rows")
+    per = (n_units + world - 1) // world
+    x = local.movedim(axis, 0).contiguous()
+    if x.shape[0] < per:                                        # pad to the common block size
+        pad = torch.zeros((per - x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        x = torch.cat([x, pad], 0)
+    bucket = [torch.empty_like(x) for _ in range(world)] if rank == dst else None
+    dist.gather(x, bucket, dst=dst)
+    if rank != dst:
+        return None
+    parts = []
+    for r in range(world):
+        a, b = shard_range(n_units, r, world)
+        parts.append(bucket[r][:b - a])
+    full = torch.cat(parts, 0).movedim(0, axis)
+    if out is not None:
+        out.copy_(full, non_blocking=False)
+        return out
+    return full

@@ -38,11 +38,30 @@ class _Slot:
 
 class StreamedCoder:
     def __init__(self, quantization_scale=1.0, search_range=4, me_mode="auto", chunk_frames=2, device=None, use_graph=True,
-                 slots=3, compute_streams=2, symbol_dtype="auto", ramp=()):
+                 slots=3, compute_streams=2, symbol_dtype="auto", ramp=(), inter_channels="auto", mv_dtype="auto"):
         self.intra = IntraBlockCoder(quantization_scale)
         self.pframe = PFrameBlockCoder(quantization_scale, search_range, me_mode)
         self.zr = ZeroRunCoder()
         self.chunk = int(chunk_frames)
+        # The P-frame stream of the reference carries the luma residual quantised against [lum, chrom, chrom]
+        # (patchquant.py:40,59): channel 2 repeats channel 1 bit for bit.  "auto" codes and sends channels 0 and 1
+        # only whenever the two chrominance tables really are the same bits (`expand_inter` rebuilds the
+        # reference's three-channel stream on the host); 3 forces the reference's layout.
+        t3 = np.asarray(self.intra.quant.get_quantization_table())
+        same_chroma = t3.shape == (3, 8, 8) and t3[1].tobytes() == t3[2].tobytes()
+        if inter_channels == "auto":
+            inter_channels = 2 if same_chroma else 3
+        if inter_channels not in (2, 3) or (inter_channels == 2 and not same_chroma):
+            raise ValueError("inter_channels must be 'auto', 3, or 2 with identical chrominance tables")
+        self.inter_channels = int(inter_channels)
+        # motion vectors are indices below (2 sr + 1)^2: int16 on the wire when that fits (the reference's dtype is
+        # int64, `dtype=int` at motion.py:26; `.astype(np.int64)` restores it)
+        span2 = (2 * int(search_range) + 1) ** 2
+        if mv_dtype == "auto":
+            mv_dtype = torch.int16 if span2 <= 32767 else torch.int64
+        if mv_dtype not in (torch.int16, torch.int32, torch.int64) or (mv_dtype == torch.int16 and span2 > 32767):
+            raise ValueError("mv_dtype must be 'auto', torch.int64, torch.int32, or torch.int16 with (2 sr + 1)^2 <= 32767")
+        self.mv_dtype = mv_dtype
         # Symbol streams are the bulk of the download.  The inputs are 8-bit images, so every DCT coefficient is
         # bounded by 8 * 255 and every quantised value by 2040 / min(table): when that (and the EOB marker) fits 16
         # bits, "auto" sends int16 symbols -- a lossless transfer format, half the bytes; torch.int32 forces the
@@ -67,14 +86,14 @@ class StreamedCoder:
 
     # ---- buffers -------------------------------------------------------------------------------
     def _host_buffers(self, F, H, W):
-        key = (F, H, W, self.symbol_dtype)
+        key = (F, H, W, self.symbol_dtype, self.mv_dtype)
         if self._host is None or self._host[0] != key:
             nb = (H // 8) * (W // 8)
             pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
             self._host = (key, {
                 # symbol streams: room for 24 symbols per block to start with (a block emits 1..97); grown on demand
                 "sym_intra": pin(F * nb * 3 * 24, self.symbol_dtype), "sym_inter": pin(F * nb * 3 * 24, self.symbol_dtype),
-                "mv": pin((F, H // 8, W // 8, 1), torch.int64), "sse": pin((2, F), torch.float64)})
+                "mv": pin((F, H // 8, W // 8, 1), self.mv_dtype), "sse": pin((2, F), torch.float64)})
         return self._host[1]
 
     def _device_slots(self, C, H, W, seq, derive=False):
@@ -127,10 +146,12 @@ class StreamedCoder:
         pend_i = self.zr.encode_begin(zz, total_host=s.totals[0:1], record=False)
         sse_i = self.intra.inverse_with_distortion(zz, d_rgb, space="ycbcr")   # decode + error in one kernel, nothing stored
         mv = self.pframe.estimate(r8, c8)              # the search reads the uint8 planes as they arrived
-        zzp = self.pframe.forward(d_cur, d_ref, mv)
+        zzp = self.pframe.forward(d_cur, d_ref, mv, channels=self.inter_channels)
         pend_p = self.zr.encode_begin(zzp, total_host=s.totals[1:2], record=False)
         recp = self.pframe.inverse(zzp, ref=d_ref, mv=mv)
         sse_p = frame_sse(d_cur, recp)
+        if self.mv_dtype != torch.int64:
+            mv = mv.to(self.mv_dtype)
         return pend_i, pend_p, mv, sse_i, sse_p
 
     def _launch(self, s: _Slot, n: int):
@@ -171,8 +192,11 @@ class StreamedCoder:
         luma frame then crosses PCIe once instead of twice.  ``cur=None`` (sequence mode only): the luma plane of a
         frame is ``luma8_from_rgb8`` of its RGB frame, derived on the device -- only the RGB frames cross PCIe;
         ``first_ref`` is then the RGB frame [H,W,3] before frame 0.  Returns host-side results: ``sym_intra`` /
-        ``sym_inter`` (int32 streams and per-chunk lengths), ``mv`` [F,Hp,Wp,1] int64, ``sse`` [2,F] (intra on
-        YCbCr, inter on luma)."""
+        ``sym_inter`` (symbol streams in ``self.symbol_dtype`` -- int16 by default, a lossless transfer format --
+        with per-chunk lengths ``len_intra`` / ``len_inter``; the inter stream holds ``self.inter_channels`` scan
+        blocks per image block, see :meth:`expand_inter`), ``mv`` [F,Hp,Wp,1] in ``self.mv_dtype``, ``sse`` [2,F]
+        (intra on YCbCr, inter on luma).  The arrays are VIEWS of this coder's persistent pinned buffers: they are
+        valid until the next ``run`` with the same geometry -- copy what must outlive it."""
         pinned = lambda x: (torch.from_numpy(x) if isinstance(x, np.ndarray) else x)
         seq = ref is None
         derive = cur is None
@@ -188,6 +212,9 @@ class StreamedCoder:
         if derive and tuple(ref.shape) != (H, W, 3):
             raise ValueError(f"cur=None: first_ref must be the RGB frame [H,W,3] before frame 0, got {tuple(ref.shape)}")
         hb = self._host_buffers(F, H, W)
+        if F == 0:
+            return {"sym_intra": hb["sym_intra"][:0], "sym_inter": hb["sym_inter"][:0], "len_intra": [], "len_inter": [],
+                    "mv": hb["mv"], "sse": hb["sse"], "h2d_bytes": 0, "d2h_bytes": 0}
         C = self.chunk
         bounds = self._schedule(F)
         nchunks = len(bounds)
@@ -295,4 +322,31 @@ class StreamedCoder:
         return {"sym_intra": hb["sym_intra"][:off[0]], "sym_inter": hb["sym_inter"][:off[1]], "len_intra": lens_i,
                 "len_inter": lens_p, "mv": hb["mv"], "sse": hb["sse"],
                 "h2d_bytes": rgb.numel() + (0 if derive else cur.numel()) + ref.numel(),   # ref = one frame in sequence mode
-                "d2h_bytes": (off[0] + off[1]) * hb["sym_intra"].element_size() + hb["mv"].numel() * 8 + hb["sse"].numel() * 8}
+                "d2h_bytes": (off[0] + off[1]) * hb["sym_intra"].element_size() + hb["mv"].numel() * hb["mv"].element_size()
+                             + hb["sse"].numel() * 8}
+
+    # ---- the transfer format of the inter stream -----------------------------------------------------
+    @staticmethod
+    def expand_inter(symbols, end_of_block=4000):
+        """Host side: rebuild the reference's three-channel P-frame symbol stream (what ``ZeroRunCoder.encode`` of the
+        ``[Hp, Wp, 3, 64]`` indices yields, E4-1.py:271-279) from the two-channel stream this coder ships: blocks
+        come in (h w c) order, channel 2 repeats channel 1, so every second block is emitted twice.  numpy, vectorised;
+        an EOB is a block end unless it is the run length after a zero marker (zerorun.py:25-35)."""
+        s = np.asarray(symbols.numpy() if isinstance(symbols, torch.Tensor) else symbols)
+        if s.size == 0:
+            return s.astype(np.int32)
+        prev0 = np.concatenate(([False], s[:-1] == 0))
+        runlen = np.zeros(s.size, dtype=bool)                 # a slot after a zero marker is a run length ...
+        idx = np.flatnonzero(prev0)
+        # ... unless that "marker" is itself a run length: impossible, run lengths are >= 1
+        runlen[idx] = True
+        ends = np.flatnonzero((s == end_of_block) & ~runlen)   # last symbol of every block
+        starts = np.concatenate(([0], ends[:-1] + 1))
+        if ends.size % 2:
+            raise ValueError("the two-channel inter stream must hold an even number of blocks")
+        # output order per image block: block 2k, block 2k+1, block 2k+1
+        sel = np.stack([np.arange(0, ends.size, 2), np.arange(1, ends.size, 2), np.arange(1, ends.size, 2)], axis=1).reshape(-1)
+        lens = (ends - starts + 1)[sel]
+        out_off = np.concatenate(([0], np.cumsum(lens)))
+        src = np.repeat(starts[sel] - out_off[:-1], lens) + np.arange(out_off[-1])
+        return s[src].astype(np.int32)

@@ -35,7 +35,7 @@ class ClosedLoopLumaCoder:
         self._graphs = {}
 
     # S sequences in lockstep, time-major [T,S,H,W] float64 on the device: every launch codes frame t of all S
-    def _enqueue(self, frames, zz, mv, recon, ws, dtab, tcode):
+    def _enqueue(self, frames, zz, mv, recon, ws, zero, dtab, tcode):
         L = _lib.lib
         T, S, H, W = frames.shape
         dev = frames.device.index
@@ -56,7 +56,7 @@ class ClosedLoopLumaCoder:
                     "ivc_pframe_inverse")
 
         chk(L.ivc_intra_forward(dev, sp, fp, _lib.F64, S, H, W, 1, H * W, dtab, tcode, zp), "ivc_intra_forward")
-        inverse(zp, self._zero.data_ptr(), None, None, rp)
+        inverse(zp, zero.data_ptr(), None, None, rp)
         for t in range(1, T):
             cur, ref, out = fp + t * fsz, rp + (t - 1) * fsz, rp + t * fsz
             z, m = zp + t * zsz, mp + (t - 1) * msz
@@ -96,25 +96,24 @@ class ClosedLoopLumaCoder:
                   "zz": torch.empty((T, S, H // 8, W // 8, 3, 64), dtype=torch.int32, device=dev),
                   "mv": torch.empty((max(T - 1, 0), S, H // 8, W // 8, 1), dtype=torch.int64, device=dev),
                   "recon": torch.empty((T, S, H, W), dtype=torch.float64, device=dev),
-                  "ws": torch.empty(256, dtype=torch.uint8, device=dev)}
-            self._zero = torch.zeros((S, H, W), dtype=torch.float64, device=dev)
+                  "ws": torch.empty(256, dtype=torch.uint8, device=dev),
+                  # the I-frames' all-zero prediction: owned by this state, so a captured graph keeps ITS buffer alive
+                  "zero": torch.zeros((S, H, W), dtype=torch.float64, device=dev)}
             if self.use_graph:
                 st["frames"].copy_(f)
                 # warm up once outside capture (sets kernel attributes), then capture the whole sequence
-                self._enqueue(st["frames"], st["zz"], st["mv"], st["recon"], st["ws"], dtab, tcode)
+                self._enqueue(st["frames"], st["zz"], st["mv"], st["recon"], st["ws"], st["zero"], dtab, tcode)
                 torch.cuda.synchronize(dev)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._enqueue(st["frames"], st["zz"], st["mv"], st["recon"], st["ws"], dtab, tcode)
+                    self._enqueue(st["frames"], st["zz"], st["mv"], st["recon"], st["ws"], st["zero"], dtab, tcode)
                 st["graph"] = g
                 self._graphs[key] = st
         if self.use_graph:
             st["frames"].copy_(f)
             st["graph"].replay()
         else:
-            if self._zero.shape != (S, H, W) or self._zero.device != dev:
-                self._zero = torch.zeros((S, H, W), dtype=torch.float64, device=dev)
-            self._enqueue(st["frames"], st["zz"], st["mv"], st["recon"], st["ws"], dtab, tcode)
+            self._enqueue(st["frames"], st["zz"], st["mv"], st["recon"], st["ws"], st["zero"], dtab, tcode)
         # back to sequence-major (a copy, so a graph's static buffers are never handed out)
         out = {k: st[k].transpose(0, 1).contiguous() for k in ("zz", "mv", "recon")}
         return {k: to_host(v, was_np) for k, v in out.items()}

@@ -528,6 +528,41 @@ def zerorun_encode(zz: np.ndarray, eob: int = 4000) -> np.ndarray:
     return np.array(out, dtype=np.int32)
 
 
+def zerorun_encode_fast(zz: np.ndarray, eob: int = 4000) -> np.ndarray:
+    """The same stream as :func:`zerorun_encode` (zerorun.py:10-43), vectorised over blocks so that full 1080p
+    frames are affordable: position p of a block emits its value if non-zero, the pair (0, run length) if it starts
+    a run of zeros that a non-zero value follows, nothing otherwise; every block ends with EOB.  Checked against
+    the loop form in tests/test_oracle_cpu.py."""
+    b = np.asarray(zz).reshape(-1, 64)
+    nb = b.shape[0]
+    nz = b != 0
+    idx = np.arange(64)
+    last = np.where(nz.any(axis=1), 63 - np.argmax(nz[:, ::-1], axis=1), -1)
+    below = idx[None, :] <= last[:, None]
+    prev_nz = np.concatenate([np.ones((nb, 1), dtype=bool), nz[:, :-1]], axis=1)
+    start = ~nz & prev_nz & below                                   # a zero run that is followed by a value
+    nxt = np.where(nz, idx[None, :], 64)
+    nxt = np.minimum.accumulate(nxt[:, ::-1], axis=1)[:, ::-1]     # next non-zero position at or after p
+    cnt = nz.astype(np.int64) + 2 * start
+    per_block = cnt.sum(axis=1) + 1
+    offs = np.concatenate([[0], np.cumsum(per_block)])
+    pos = offs[:-1, None] + (np.cumsum(cnt, axis=1) - cnt)
+    out = np.empty(int(offs[-1]), dtype=np.int32)
+    out[pos[nz]] = b[nz]
+    out[pos[start]] = 0
+    out[pos[start] + 1] = (nxt - idx[None, :])[start]
+    out[offs[1:] - 1] = eob
+    return out
+
+
+def symbol_histogram(symbols: np.ndarray, lo: int, n_bins: int) -> np.ndarray:
+    """np.histogram(symbols, bins=np.arange(lo, lo + n_bins + 1))[0] for integer symbols inside the range
+    (entropy.py:24: unit bins), as int64 counts."""
+    s = np.asarray(symbols).astype(np.int64) - lo
+    s = s[(s >= 0) & (s < n_bins)]
+    return np.bincount(s, minlength=n_bins).astype(np.int64)
+
+
 def zerorun_decode(symbols, shape, eob: int = 4000) -> np.ndarray:
     """``ZeroRunCoder.decode`` (zerorun.py:44-87) incl. the "stop after h*w*c
     blocks" rule (:60-62)."""

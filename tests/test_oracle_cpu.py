@@ -191,7 +191,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(raw, n), f"{n} declared in include/ivclab_b200.h but not exported"
     assert set(names) == set(_lib.SIGNATURES), "ctypes table and header disagree"
-    assert _lib.lib.ivc_abi_version() == _lib.ABI_VERSION == 3
+    assert _lib.lib.ivc_abi_version() == _lib.ABI_VERSION == 4
     assert b"sm_100a" in _lib.lib.ivc_build_info()
     assert _lib.lib.ivc_me_workspace_bytes(2, 16, 16) >= 4
     assert ivclab_b200.__version__
@@ -291,3 +291,38 @@ def test_install_swaps_classes_into_a_fake_ivclab():
     c = ivc.inject(FakeCodec())
     assert isinstance(c.dct, ivc.DiscreteCosineTransform) and c.quant.quantization_scale == 0.4
     assert isinstance(c.zigzag, ivc.ZigZag) and isinstance(c.patcher, ivc.Patcher)
+
+
+def test_vectorised_zerorun_oracle_equals_loop_form(g1, g2, g9):
+    """oracle.zerorun_encode_fast (used for full-size 1080p checks) == the loop restatement of zerorun.py:10-43."""
+    rng = np.random.default_rng(17)
+    cases = [g1["zz0"], g1["zz1"], g1["zz2"], g2["zz1"]]
+    zz = np.where(rng.random((4, 5, 3, 64)) < 0.2, rng.integers(-3000, 3000, (4, 5, 3, 64)), 0).astype(np.int32)
+    zz[0, 0, 0] = 0
+    zz[0, 0, 1] = 9
+    zz[0, 0, 2] = 0
+    zz[0, 0, 2, 63] = -1
+    zz[0, 1, 0] = 0
+    zz[0, 1, 0, 0] = 4
+    cases.append(zz)
+    for c in cases:
+        a, b = O.zerorun_encode(c), O.zerorun_encode_fast(c)
+        assert a.dtype == b.dtype and np.array_equal(a, b)
+        assert np.array_equal(O.symbol_histogram(a, -4096, 8192), np.histogram(a, bins=np.arange(-4096, 4097))[0])
+    assert O.zerorun_encode_fast(np.zeros((0, 64), dtype=np.int32)).size == 0
+
+
+def test_expand_inter_rebuilds_the_three_channel_stream():
+    """StreamedCoder.expand_inter: host-side expansion of the two-channel P-frame transfer format."""
+    from ivclab_b200.streaming import StreamedCoder
+    rng = np.random.default_rng(3)
+    zz2 = np.where(rng.random((5, 7, 2, 64)) < 0.1, rng.integers(-40, 40, (5, 7, 2, 64)), 0).astype(np.int32)
+    zz2[0, 0, 0] = 0
+    zz2[1, 1, 1] = 7
+    zz2[2, 2, 0, 5] = 4000 - 3937                                     # a run length that collides with nothing
+    zz3 = np.concatenate([zz2, zz2[:, :, 1:2]], axis=2)
+    got = StreamedCoder.expand_inter(O.zerorun_encode(zz2).astype(np.int16))
+    assert got.dtype == np.int32 and np.array_equal(got, O.zerorun_encode(zz3))
+    assert StreamedCoder.expand_inter(np.zeros(0, dtype=np.int16)).size == 0
+    with pytest.raises(ValueError):
+        StreamedCoder.expand_inter(O.zerorun_encode(zz2[:1, :1, :1]))

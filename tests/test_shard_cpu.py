@@ -83,3 +83,49 @@ def test_world_size_2_gloo_gather_in_unit_order(contiguous):
         assert owners == [0, 0, 0, 0, 1, 1, 1]                         # contiguous frame ranges
     else:
         assert owners == [0, 1, 0, 1, 0, 1, 0]                         # round robin
+
+
+def _rows_worker(rank, world, port, q):
+    from ivclab_b200.shard import gather_rows
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = 7                                                      # uneven: shards of 4 and 3 units
+        lo, hi = shard_range(n, rank, world)
+        # the RD sweep's per-rank results: [Q, F_local] squared errors and [Q, F_local, bins] symbol histograms
+        sse = torch.arange(lo, hi, dtype=torch.float64)[None, :] + torch.tensor([[0.0], [100.0]], dtype=torch.float64)
+        hist = (torch.arange(lo, hi, dtype=torch.int32)[None, :, None] * 10 + torch.arange(5, dtype=torch.int32)[None, None, :]
+                ).expand(2, hi - lo, 5).contiguous()
+        out_sse = gather_rows(sse, n, axis=1)
+        out_hist = gather_rows(hist, n, axis=1, out=torch.empty((2, n, 5), dtype=torch.int32) if rank == 0 else None)
+        if rank == 0:
+            q.put((out_sse.tolist(), out_hist.tolist()))
+        else:
+            assert out_sse is None and out_hist is None
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_gather_rows():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rows_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    sse, hist = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sse == [[float(u) for u in range(7)], [100.0 + u for u in range(7)]]
+    assert hist == [[[10 * u + k for k in range(5)] for u in range(7)]] * 2
+
+
+def test_gather_rows_single_process():
+    from ivclab_b200.shard import gather_rows
+    x = torch.arange(12).reshape(3, 4)
+    assert gather_rows(x, 4, axis=1) is x
+    with pytest.raises(ValueError):
+        gather_rows(x, 5, axis=1)
