@@ -184,7 +184,7 @@ def cfg3(cx, ivc, pool=1024, chunk=8):
 
     def fed():
         r = sweep.run(h_rgb, to_host=False)
-        torch.cuda.current_stream().wait_stream(sweep._s_cmp)
+        sweep._s_cmp.synchronize()                       # so that the gather's own cost can be stated separately
         t0 = time.perf_counter()
         gather_rows(r["sse"], pool, axis=1, out=out_sse)
         gather_rows(r["hist"], pool, axis=1, out=out_hist)

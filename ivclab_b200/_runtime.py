@@ -30,9 +30,10 @@ def code(dtype: torch.dtype) -> int:
 # help every method would upload what the previous one has just downloaded.  `to_host` therefore remembers (weakly)
 # which device tensor is behind each array it returns, and `to_device` finds that tensor again -- for the array
 # itself and for views of it (einops.rearrange, slicing) -- so a chain pays ONE upload (its first input) and the
-# downloads.  To make this safe the returned arrays are READ-ONLY: while an array is read-only its bytes cannot
-# diverge from the device copy; a caller who sets `arr.flags.writeable = True` simply loses the shortcut for that
-# array (it is uploaded again).  `set_device_memo(False)` turns the mechanism off (arrays are then writable).
+# downloads.  To make this safe the returned arrays are READ-ONLY (and numpy does not let a view of foreign memory
+# be made writable again): their bytes cannot diverge from the device copy.  A caller that wants to modify a result
+# takes `arr.copy()` -- an ordinary array, uploaded like any other.  `set_device_memo(False)` turns the mechanism
+# off (results are then writable, and every method uploads its input).
 _MEMO_ON = True
 _MEMO_MAX = 12
 _memo = {}                      # id(array) -> (weakref to the array, device tensor), insertion-ordered

@@ -226,12 +226,17 @@ def test_device_memo_chain_views_and_writability(g1):
     dv = _runtime._memo_get(view, None)
     assert dv is not None and np.array_equal(dv.cpu().numpy(), view)
     assert _runtime._memo_get(rec[::-1], None) is None                                     # negative strides: plain upload
-    # a caller that wants to write gets a plain upload afterwards -- never a stale device copy
+    # the returned arrays cannot be written (numpy refuses to make a view of foreign memory writable again), so the
+    # device copy can never go stale; a caller that wants to modify a result copies it, and the copy is uploaded
     coef2 = D.transform(P.patch(g1["img"]))
-    coef2.flags.writeable = True
-    coef2[0, 0, 0, 0, 0] += 1000.0
-    q2 = Q.quantize(coef2)
-    assert q2[0, 0, 0, 0, 0] != Q.quantize(g1["coef"])[0, 0, 0, 0, 0]
+    with pytest.raises(ValueError):
+        coef2[0, 0, 0, 0, 0] += 1000.0
+    with pytest.raises(ValueError):
+        coef2.flags.writeable = True
+    mine = coef2.copy()
+    mine[0, 0, 0, 0, 0] += 1000.0
+    assert _runtime._memo_get(mine, None) is None
+    assert Q.quantize(mine)[0, 0, 0, 0, 0] != Q.quantize(g1["coef"])[0, 0, 0, 0, 0]
     # switched off: writable arrays, no memo
     ivc.set_device_memo(False)
     try:
