@@ -48,6 +48,8 @@ struct MeArgs {
     int vec;                               // ... 16-byte staging loads are legal (alignment of base, strides, sr)
     unsigned m_pwl, m_q4, m_p4, m_ntpb, m_span;     // multiply-high reciprocals (host-computed)
     unsigned m_nbx[2], m_cww[2];                    // ... of nbx and 2*nbx for full / last-column tiles
+    int ipr[2];                                     // int kernels, float64 staging: 8-pixel items per window row (full / last-column tiles)
+    unsigned m_ipr[2];
     int64_t *mv;
     int *flag;                             // device flag (may be null)
     int run_if;                            // exact kernel: run only if *flag == run_if (when flag != null)
@@ -276,149 +278,250 @@ __device__ __forceinline__ void ldg16(const float *p, float (&v)[4]) {
     asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
 }
 
-// uint8 planes: a packed word IS four consecutive pixels -- one aligned 32-bit load (VEC: the window origin and W are
-// multiples of 4) or four byte loads; nothing to convert, nothing to check.
-template <bool VEC, int UNR, typename Dst>
-__device__ __forceinline__ void stage_batch_u8(const unsigned char *frame, int H, int W, int y0, int x0, int base, int total,
-                                               int wpr, FastDiv d_wpr, unsigned *smem, Dst dst) {
-    const int nthr = blockDim.x;
-    unsigned v[UNR];
-    int out[UNR];
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-        const int idx = base + u * nthr;
-        const int row = d_wpr.div(idx), w = idx - row * wpr;
-        const int gy = y0 + row, gx = x0 + 4 * w;
-        const bool rok = idx < total && (unsigned)gy < (unsigned)H;
-        const unsigned char *p = frame + (gy * W + gx);
-        out[u] = idx < total ? dst(row, w) : -1;
-        v[u] = 0u;
-        if (VEC) {
-            if (rok && (unsigned)gx < (unsigned)W) v[u] = __ldg(reinterpret_cast<const unsigned *>(p));
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (rok && (unsigned)(gx + k) < (unsigned)W) v[u] |= (unsigned)__ldg(p + k) << (8 * k);
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u)
-        if (out[u] >= 0) smem[out[u]] = v[u];
+// ---- staging: frames -> packed bytes in shared memory ------------------------------------------------------------
+// The words of a tile form ONE list: the search window of the reference frame first (word idx < n_ref covers pixels
+// (ry0 + idx / pwl, rx0 + 4 (idx % pwl) .. +3), zero where that leaves the frame, stored at s_b[row * pw + w]), then the
+// current blocks (stored block by block in s_cur).  A thread takes UNR words per batch and issues all their loads
+// before the first conversion, so the window AND the blocks are in flight together and a tile waits for memory once
+// or twice, not once per array and remainder (what is left after the full batches goes into ONE guarded batch of the
+// smallest sufficient size).  VEC: origins, W and the frame bases are multiples of 16 bytes (uint8 planes: 4), so
+// 16-byte groups are loaded whole and never straddle a frame edge.
+struct StageGeom {
+    int H, W;
+    int ry0, rx0, n_ref, pwl, pw;          // reference window: origin, words, words per staged row, words per smem row
+    int cy0, cx0, cww, tbx;                // current blocks: origin, words per row, blocks per tile row (smem slots)
+    unsigned m_pwl, m_cww;
+    int total;
+};
+
+struct StageItem {
+    int gy, gx, out;                       // pixel position in the frame, shared-memory word index (< 0: nothing to do)
+    bool is_cur;
+};
+__device__ __forceinline__ StageItem stage_item(const StageGeom &g, int idx, int cur_off_words) {
+    StageItem it;
+    it.is_cur = idx >= g.n_ref;
+    const int j = it.is_cur ? idx - g.n_ref : idx;
+    const int wpr = it.is_cur ? g.cww : g.pwl;
+    const int row = FastDiv(it.is_cur ? g.m_cww : g.m_pwl).div(j), w = j - row * wpr;
+    it.gy = (it.is_cur ? g.cy0 : g.ry0) + row;
+    it.gx = (it.is_cur ? g.cx0 : g.rx0) + 4 * w;
+    const int o_ref = row * g.pw + w;
+    const int o_cur = cur_off_words + ((row >> 3) * g.tbx + (w >> 1)) * kCurPitch + (row & 7) * 2 + (w & 1);
+    it.out = idx < g.total ? (it.is_cur ? o_cur : o_ref) : -1;
+    return it;
 }
 
-// Stage `total` packed words: word idx covers pixels (y0 + idx / wpr, x0 + 4 * (idx % wpr) .. +3) of `frame`,
-// zero where that leaves the frame; dst(row, w) gives the shared-memory word index.  Loads of kStageUnroll
-// words are issued before the first conversion so that a thread keeps 16 pixel loads in flight.  VEC: x0, W
-// and the frame base are multiples of 16 bytes, so 16-byte groups are loaded whole (never straddle an edge).
-template <bool VEC, int UNR, typename T, typename Dst>
-__device__ __forceinline__ void stage_batch(const T *frame, int H, int W, int y0, int x0, int base, int total, int wpr,
-                                            FastDiv d_wpr, U8Check &chk, unsigned *smem, Dst dst) {
+// s_b and s_cur are addressed through one base (s_b) and the word offset of s_cur from it
+template <bool VEC, int UNR, typename T>
+__device__ __forceinline__ void stage_batch(const T *ref, const T *cur, const StageGeom &g, int base, U8Check &chk,
+                                            unsigned *s_b, int cur_off_words) {
     constexpr int V = 16 / (int)sizeof(T);                                    // elements per 16-byte group
     const int nthr = blockDim.x;
     T v[UNR][4];
     int out[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
-        const int idx = base + u * nthr;
-        const int row = d_wpr.div(idx), w = idx - row * wpr;
-        const int gy = y0 + row, gx = x0 + 4 * w;
-        const bool rok = idx < total && (unsigned)gy < (unsigned)H;
-        const T *p = frame + (gy * W + gx);                                   // H * W < 2^31 (checked by the launcher)
-        out[u] = idx < total ? dst(row, w) : -1;
+        const StageItem it = stage_item(g, base + u * nthr, cur_off_words);
+        out[u] = it.out;
+        const bool rok = it.out >= 0 && (unsigned)it.gy < (unsigned)g.H;
+        const T *p = (it.is_cur ? cur : ref) + (it.gy * g.W + it.gx);         // H * W < 2^31 (checked by the launcher)
         if (VEC) {
 #pragma unroll
             for (int k = 0; k < 4; k += V) {
                 T t[V];
 #pragma unroll
                 for (int j = 0; j < V; ++j) t[j] = (T)0;
-                if (rok && (unsigned)(gx + k) < (unsigned)W) ldg16(p + k, t);
+                if (rok && (unsigned)(it.gx + k) < (unsigned)g.W) ldg16(p + k, t);
 #pragma unroll
                 for (int j = 0; j < V; ++j) v[u][k + j] = t[j];
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[u][k] = (rok && (unsigned)(gx + k) < (unsigned)W) ? __ldg(p + k) : (T)0;
+            for (int k = 0; k < 4; ++k) v[u][k] = (rok && (unsigned)(it.gx + k) < (unsigned)g.W) ? __ldg(p + k) : (T)0;
         }
     }
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
         const unsigned b0 = to_u8(v[u][0], chk), b1 = to_u8(v[u][1], chk), b2 = to_u8(v[u][2], chk), b3 = to_u8(v[u][3], chk);
-        if (out[u] >= 0) smem[out[u]] = pack_bytes(b0, b1, b2, b3);
+        if (out[u] >= 0) s_b[out[u]] = pack_bytes(b0, b1, b2, b3);
+    }
+}
+// uint8 planes: a packed word IS four consecutive pixels -- one aligned 32-bit load (VEC) or four byte loads;
+// nothing to convert, nothing to check.
+template <bool VEC, int UNR>
+__device__ __forceinline__ void stage_batch(const unsigned char *ref, const unsigned char *cur, const StageGeom &g, int base,
+                                            U8Check &, unsigned *s_b, int cur_off_words) {
+    const int nthr = blockDim.x;
+    unsigned v[UNR];
+    int out[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+        const StageItem it = stage_item(g, base + u * nthr, cur_off_words);
+        out[u] = it.out;
+        const bool rok = it.out >= 0 && (unsigned)it.gy < (unsigned)g.H;
+        const unsigned char *p = (it.is_cur ? cur : ref) + (it.gy * g.W + it.gx);
+        v[u] = 0u;
+        if (VEC) {
+            if (rok && (unsigned)it.gx < (unsigned)g.W) v[u] = __ldg(reinterpret_cast<const unsigned *>(p));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (rok && (unsigned)(it.gx + k) < (unsigned)g.W) v[u] |= (unsigned)__ldg(p + k) << (8 * k);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+        if (out[u] >= 0) s_b[out[u]] = v[u];
+}
+
+template <bool VEC, int UNR, typename T>
+__device__ __forceinline__ void stage_tile(const T *ref, const T *cur, const StageGeom &g, U8Check &chk, unsigned *s_b,
+                                           int cur_off_words) {
+    const int nthr = blockDim.x, tid = threadIdx.x;
+    int done = 0;
+    for (; done + UNR * nthr <= g.total; done += UNR * nthr) stage_batch<VEC, UNR>(ref, cur, g, done + tid, chk, s_b, cur_off_words);
+    const int rem = g.total - done;                                           // < UNR * nthr: one guarded batch
+    if (rem <= 0) return;
+    if (rem <= nthr) stage_batch<VEC, 1>(ref, cur, g, done + tid, chk, s_b, cur_off_words);
+    else if (UNR >= 2 && rem <= 2 * nthr) stage_batch<VEC, (UNR >= 2 ? 2 : 1)>(ref, cur, g, done + tid, chk, s_b, cur_off_words);
+    else if (UNR >= 4 && rem <= 4 * nthr) stage_batch<VEC, (UNR >= 4 ? 4 : 1)>(ref, cur, g, done + tid, chk, s_b, cur_off_words);
+    else stage_batch<VEC, UNR>(ref, cur, g, done + tid, chk, s_b, cur_off_words);
+}
+
+// float64 frames with 16-byte aligned rows (the codecs' case): the lean staging path.  An ITEM is eight consecutive
+// pixels of one frame row -- four 16-byte loads from one address, two packed words, one 8-byte store: a row of a
+// current block, or an 8-pixel column group of a window row.  Everything about an item but its pixels is computed
+// once per eight pixels; the validity tests ride on the FP64 pipe, which the search itself leaves idle (five FP64
+// operations per pixel: v + 2^52, the exactness probe (v + 2^52) - 2^52 != v, 0 <= v, v <= 255), so the integer pipe
+// sees about two instructions per pixel.  EDGE: the window leaves the frame somewhere -- every 16-byte group is
+// tested (groups never straddle an edge: origins and W are even) and zero-filled; CHECK: validate the values.
+template <bool CHECK>
+__device__ __forceinline__ unsigned to_u8_fp(double v, bool &bad) {
+    const double s = __dadd_rn(v, 4503599627370496.0);                        // 2^52: rint(v) lands in the low mantissa word
+    if (CHECK) bad |= (__dsub_rn(s, 4503599627370496.0) != v) | !(v >= 0.0) | !(v <= 255.0);
+    return (unsigned)__double2loint(s);
+}
+
+// One list of items (rows x per_row, eight pixels each) of one frame: thread t takes items t, t + nthr, ... and walks
+// (row, c) incrementally -- no division per item; the loads of item k + 1 are issued before item k is converted.
+// dst32(row, c) gives the 32-bit shared-memory address of the item's two packed words.
+template <bool EDGE, bool CHECK, typename Dst>
+__device__ __forceinline__ void stage_item_list(const double *frame, int H, int W, int y0, int x0, int rows, int per_row,
+                                                FastDiv d_per_row, bool &bad, Dst dst32) {
+    const int nthr = blockDim.x;
+    const int dr = d_per_row.div(nthr), dc = nthr - dr * per_row;             // what advancing by nthr items does to (row, c)
+    int row = d_per_row.div((int)threadIdx.x), c = (int)threadIdx.x - row * per_row;
+    const auto load = [&](int r, int cc, double (&v)[8]) {
+        const int gy = y0 + r, gx = x0 + 8 * cc;
+        const double *p = frame + (gy * W + gx);                               // H * W < 2^31 (checked by the launcher)
+        const bool rok = !EDGE || (unsigned)gy < (unsigned)H;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double t[2] = {0.0, 0.0};
+            if (rok && (!EDGE || (unsigned)(gx + 2 * k) < (unsigned)W)) ldg16(p + 2 * k, t);
+            v[2 * k] = t[0];
+            v[2 * k + 1] = t[1];
+        }
+    };
+    const auto convert_store = [&](int r, int cc, const double (&v)[8]) {
+        const unsigned w0 = pack_bytes(to_u8_fp<CHECK>(v[0], bad), to_u8_fp<CHECK>(v[1], bad), to_u8_fp<CHECK>(v[2], bad), to_u8_fp<CHECK>(v[3], bad));
+        const unsigned w1 = pack_bytes(to_u8_fp<CHECK>(v[4], bad), to_u8_fp<CHECK>(v[5], bad), to_u8_fp<CHECK>(v[6], bad), to_u8_fp<CHECK>(v[7], bad));
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(dst32(r, cc)), "r"(w0), "r"(w1) : "memory");
+    };
+    const auto advance = [&](int &r, int &cc) {
+        r += dr;
+        cc += dc;
+        if (cc >= per_row) { cc -= per_row; ++r; }
+    };
+    double va[8], vb[8];
+    if (row >= rows) return;
+    load(row, c, va);
+    for (;;) {
+        int r2 = row, c2 = c;
+        advance(r2, c2);
+        const bool have_b = r2 < rows;
+        if (have_b) load(r2, c2, vb);
+        convert_store(row, c, va);
+        if (!have_b) break;
+        row = r2; c = c2;
+        advance(row, c);
+        const bool have_a = row < rows;
+        if (have_a) load(row, c, va);
+        convert_store(r2, c2, vb);
+        if (!have_a) break;
     }
 }
 
-// Stage `total` packed words: word idx covers pixels (y0 + idx / wpr, x0 + 4 * (idx % wpr) .. +3) of `frame`,
-// zero where that leaves the frame; dst(row, w) gives the shared-memory word index.  Batches of
-// kStageUnroll words per thread issue all their loads before the first conversion (16 pixel loads in flight
-// per thread); what is left after the full batches goes in batches of one.  VEC: x0, W and the frame base
-// are multiples of 16 bytes, so 16-byte groups are loaded whole (they never straddle a frame edge).
-template <bool VEC, typename T, typename Dst>
-__device__ __forceinline__ void stage_words(const T *frame, int H, int W, int y0, int x0, int total, int wpr,
-                                            FastDiv d_wpr, U8Check &chk, unsigned *smem, Dst dst) {
-    const int nthr = blockDim.x;
-    int base = threadIdx.x;
-    for (; base - (int)threadIdx.x + kStageUnroll * nthr <= total; base += kStageUnroll * nthr)
-        stage_batch<VEC, kStageUnroll>(frame, H, W, y0, x0, base, total, wpr, d_wpr, chk, smem, dst);
-    for (; base < total; base += nthr)
-        stage_batch<VEC, 1>(frame, H, W, y0, x0, base, total, wpr, d_wpr, chk, smem, dst);
-}
-template <bool VEC, typename Dst>
-__device__ __forceinline__ void stage_words(const unsigned char *frame, int H, int W, int y0, int x0, int total, int wpr,
-                                            FastDiv d_wpr, U8Check &, unsigned *smem, Dst dst) {
-    const int nthr = blockDim.x;
-    int base = threadIdx.x;
-    for (; base - (int)threadIdx.x + 2 * kStageUnroll * nthr <= total; base += 2 * kStageUnroll * nthr)
-        stage_batch_u8<VEC, 2 * kStageUnroll>(frame, H, W, y0, x0, base, total, wpr, d_wpr, smem, dst);
-    for (; base < total; base += nthr)
-        stage_batch_u8<VEC, 1>(frame, H, W, y0, x0, base, total, wpr, d_wpr, smem, dst);
+template <bool EDGE, bool CHECK>
+__device__ __forceinline__ bool stage_items_f64(const double *ref, const double *cur, const MeArgs &a, const MeTile &tl, int R,
+                                                int pw, unsigned *s_b, unsigned *s_cur) {
+    const int H = (int)a.H, W = (int)a.W, sr = a.sr;
+    const int last_col = tl.nbx != a.tbx;
+    bool bad = false;
+    const uint32_t b32 = (uint32_t)__cvta_generic_to_shared(s_b), c32 = (uint32_t)__cvta_generic_to_shared(s_cur);
+    const int tbx = a.tbx;
+    // search window: rows x ipr items, stored row by row in s_b
+    stage_item_list<EDGE, CHECK>(ref, H, W, 8 * tl.by0 - sr, 8 * tl.bx0 - sr, min(R, 8 * tl.nby + 2 * sr), a.ipr[last_col],
+                                 FastDiv(a.m_ipr[last_col]), bad,
+                                 [&](int r, int c) { return b32 + (uint32_t)(r * pw + 2 * c) * 4u; });
+    // current blocks: 8 nby rows x nbx items (an item is one row of one block), stored block by block; never outside the frame
+    stage_item_list<false, CHECK>(cur, H, W, 8 * tl.by0, 8 * tl.bx0, 8 * tl.nby, tl.nbx, FastDiv(a.m_nbx[last_col]), bad,
+                                  [&](int r, int c) { return c32 + (uint32_t)(((r >> 3) * tbx + c) * kCurPitch + (r & 7) * 2) * 4u; });
+    return bad;
 }
 
-// PC: compile-time U / HS pitch (0 = take it from the arguments).  With a constant pitch every row offset of
-// the unrolled loops is an immediate, which keeps address IMADs off the pipe the dp4a instructions need.
-template <typename T, int G, int PC>
-__global__ void __launch_bounds__(PC ? kMeIntMaxThreads : kMeThreads, PC ? 2 : 3) k_me_int(const MeArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned *s_u = reinterpret_cast<unsigned *>(smem_raw);                   // [R][P4]
-    unsigned *s_hs = reinterpret_cast<unsigned *>(smem_raw + a.hs_off);       // [8*nseg+7][P4]
-    unsigned *s_b = reinterpret_cast<unsigned *>(smem_raw + a.b_off);         // [R][pw]
-    unsigned *s_cur = reinterpret_cast<unsigned *>(smem_raw + a.cur_off);     // [tby*tbx][kCurPitch]
-    __shared__ unsigned long long s_best[64];
-    __shared__ unsigned s_c2[64];
-    __shared__ int s_bad;
-    const MeTile tl = me_tile(a);
+// Phases A-C of the integer kernels: stage window + current blocks as packed bytes, build the unaligned-word view U,
+// the per-position sums of squares S (x16) and the per-block sum(c^2) (x16).  PC: compile-time U / HS pitch (0 = take
+// it from the arguments).  Returns false when the frames are not integer-valued (the device flag has been raised and
+// the CTA must leave the vectors to k_me_exact).  Ends with a CTA-wide barrier.
+template <typename T, int PC, int UNR, int KEYSHIFT = 4, bool BAKEX = false>
+__device__ __forceinline__ bool me_int_prepare(const MeArgs &a, const MeTile &tl, unsigned *s_u, unsigned *s_hs, unsigned *s_b,
+                                               unsigned *s_cur, unsigned *s_c2) {
     const T *ref = (const T *)a.ref + tl.frame * a.ref_fs;
     const T *cur = (const T *)a.cur + tl.frame * a.cur_fs;
-    const int sr = a.sr, span = a.span, P4 = PC ? PC : a.P, pw = PC ? PC / 4 + 2 : a.pw, R = a.R;
+    const int sr = a.sr, P4 = PC ? PC : a.P, pw = PC ? PC / 4 + 2 : a.pw, R = a.R;
     const int H = (int)a.H, W = (int)a.W;
     const int nblk = tl.nby * tl.nbx;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int last_col = tl.nbx != a.tbx;
     const FastDiv d_nbx(a.m_nbx[last_col]);
 
-    if (tid < 64) s_best[tid] = ~0ull;
-    if (tid == 0) s_bad = 0;
-
-    // ---- phase A: float frames -> packed bytes (window with halo, current blocks).  Rows / words past
-    //      the part of the window this tile can use stay unwritten: only discarded candidates see them ----
+    // ---- phase A: frames -> packed bytes (window with halo, current blocks).  Rows / words past the part
+    //      of the window this tile can use stay unwritten: only discarded candidates see them ----
+    int bad = 0;
     {
         U8Check chk;
-        const int rows = min(R, 8 * tl.nby + 2 * sr);
-        const int cww = 2 * tl.nbx;                                           // words per current row
-        auto dst_ref = [&](int row, int w) { return row * pw + w; };
-        auto dst_cur = [&](int row, int w) { return ((row >> 3) * a.tbx + (w >> 1)) * kCurPitch + (row & 7) * 2 + (w & 1); };
-        if (a.vec) {
-            stage_words<true>(ref, H, W, 8 * tl.by0 - sr, 8 * tl.bx0 - sr, rows * a.pwl, a.pwl, FastDiv(a.m_pwl), chk, s_b, dst_ref);
-            stage_words<true>(cur, H, W, 8 * tl.by0, 8 * tl.bx0, 8 * tl.nby * cww, cww, FastDiv(a.m_cww[last_col]), chk, s_cur, dst_cur);
-        } else {
-            stage_words<false>(ref, H, W, 8 * tl.by0 - sr, 8 * tl.bx0 - sr, rows * a.pwl, a.pwl, FastDiv(a.m_pwl), chk, s_b, dst_ref);
-            stage_words<false>(cur, H, W, 8 * tl.by0, 8 * tl.bx0, 8 * tl.nby * cww, cww, FastDiv(a.m_cww[last_col]), chk, s_cur, dst_cur);
+        StageGeom g;
+        g.H = H; g.W = W;
+        g.ry0 = 8 * tl.by0 - sr; g.rx0 = 8 * tl.bx0 - sr;
+        g.pwl = a.pwl; g.pw = pw; g.m_pwl = a.m_pwl;
+        g.n_ref = min(R, 8 * tl.nby + 2 * sr) * a.pwl;
+        g.cy0 = 8 * tl.by0; g.cx0 = 8 * tl.bx0;
+        g.cww = 2 * tl.nbx; g.tbx = a.tbx; g.m_cww = a.m_cww[last_col];
+        g.total = g.n_ref + 8 * tl.nby * g.cww;
+        const int cur_off_words = (int)(s_cur - s_b);
+        bool fast = false;
+        if (sizeof(T) == 8) {                                                 // float64 frames, 16-byte aligned rows: the lean path
+            fast = a.vec && (sr & 1) == 0 && (pw & 1) == 0;                   // 8-byte stores into s_b rows
+            if (fast) {
+                const bool edge = g.ry0 < 0 || g.rx0 < 0 || g.ry0 + R > H || g.rx0 + 8 * a.ipr[last_col] > W;
+                const double *r64 = (const double *)ref, *c64 = (const double *)cur;
+                bool b;
+                if (edge) b = a.check ? stage_items_f64<true, true>(r64, c64, a, tl, R, pw, s_b, s_cur) : stage_items_f64<true, false>(r64, c64, a, tl, R, pw, s_b, s_cur);
+                else b = a.check ? stage_items_f64<false, true>(r64, c64, a, tl, R, pw, s_b, s_cur) : stage_items_f64<false, false>(r64, c64, a, tl, R, pw, s_b, s_cur);
+                bad = b;
+            }
         }
-        if (a.check && __any_sync(0xffffffffu, chk.bad()) && (tid & 31) == 0) s_bad = 1;
+        if (!fast) {
+            if (a.vec) stage_tile<true, UNR>(ref, cur, g, chk, s_b, cur_off_words);
+            else stage_tile<false, UNR>(ref, cur, g, chk, s_b, cur_off_words);
+        }
+        bad = bad | (a.check && chk.bad());
     }
-    __syncthreads();
-    if (a.check && s_bad) {                                                   // not an integer frame: leave it to k_me_exact
+    if (__syncthreads_or(bad)) {                                              // not an integer frame: leave it to k_me_exact
         if (tid == 0) atomicOr(a.flag, 1);
-        return;
+        return false;
     }
 
     // ---- phase B: unaligned-word view U and horizontal sums of squares H; sum(c^2) per block ----
@@ -448,7 +551,7 @@ __global__ void __launch_bounds__(PC ? kMeIntMaxThreads : kMeThreads, PC ? 2 : 3
             unsigned c2 = 0;
 #pragma unroll
             for (int i = 0; i < 16; ++i) c2 = __dp4a(cb[i], cb[i], c2);
-            s_c2[tid] = c2 << 4;
+            s_c2[tid] = c2 << KEYSHIFT;
         }
     }
     __syncthreads();
@@ -463,23 +566,46 @@ __global__ void __launch_bounds__(PC ? kMeIntMaxThreads : kMeThreads, PC ? 2 : 3
             const bool active = item < total;
             const int seg = active ? FastDiv(a.m_p4).div(item) : 0;
             unsigned *hp = s_hs + item + 7 * seg * P4;                        // == (8 * seg) * P4 + x
-            unsigned s[8];
+            unsigned sv[8];
             if (active) {
                 unsigned h[15];
 #pragma unroll
                 for (int i = 0; i < 15; ++i) h[i] = hp[i * P4];
-                s[0] = ((h[0] + h[1]) + (h[2] + h[3])) + ((h[4] + h[5]) + (h[6] + h[7]));
+                sv[0] = ((h[0] + h[1]) + (h[2] + h[3])) + ((h[4] + h[5]) + (h[6] + h[7]));
 #pragma unroll
-                for (int j = 1; j < 8; ++j) s[j] = s[j - 1] + h[j + 7] - h[j - 1];
+                for (int j = 1; j < 8; ++j) sv[j] = sv[j - 1] + h[j + 7] - h[j - 1];
             }
             __syncthreads();
             if (active) {
+                const unsigned xcol = BAKEX ? (unsigned)(item - seg * P4) : 0u;     // BAKEX: the column rides in the free low bits
 #pragma unroll
-                for (int j = 0; j < 8; ++j) hp[j * P4] = s[j] << 4;           // S * 16: room for the candidate number
+                for (int j = 0; j < 8; ++j) hp[j * P4] = (sv[j] << KEYSHIFT) + xcol; // S * 2^KEYSHIFT: room for a candidate code
             }
         }
     }
     __syncthreads();
+    return true;
+}
+
+template <typename T, int G, int PC>
+__global__ void __launch_bounds__(PC ? kMeIntMaxThreads : kMeThreads, PC ? 2 : 3) k_me_int(const MeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned *s_u = reinterpret_cast<unsigned *>(smem_raw);                   // [R][P4]
+    unsigned *s_hs = reinterpret_cast<unsigned *>(smem_raw + a.hs_off);       // [8*nseg+7][P4]
+    unsigned *s_b = reinterpret_cast<unsigned *>(smem_raw + a.b_off);         // [R][pw]
+    unsigned *s_cur = reinterpret_cast<unsigned *>(smem_raw + a.cur_off);     // [tby*tbx][kCurPitch]
+    __shared__ unsigned long long s_best[64];
+    __shared__ unsigned s_c2[64];
+    const MeTile tl = me_tile(a);
+    const int sr = a.sr, span = a.span, P4 = PC ? PC : a.P;
+    const int H = (int)a.H, W = (int)a.W;
+    const int nblk = tl.nby * tl.nbx;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int last_col = tl.nbx != a.tbx;
+    const FastDiv d_nbx(a.m_nbx[last_col]);
+
+    if (tid < 64) s_best[tid] = ~0ull;
+    if (!me_int_prepare<T, PC, kStageUnroll>(a, tl, s_u, s_hs, s_b, s_cur, s_c2)) return;
 
     // ---- main loop ------------------------------------------------------------------------------
     const bool small = span * span <= 512;                                    // ssd < 2^22, index < 2^9: key fits 32 bits
@@ -555,6 +681,156 @@ __global__ void __launch_bounds__(PC ? kMeIntMaxThreads : kMeThreads, PC ? 2 : 3
         const int blk = tid, brow = d_nbx.div(blk), b = blk - brow * tl.nbx;
         const int64_t idx = small ? (int64_t)(s_best32[blk] & 511u) : (int64_t)(s_best[blk] & 0xffffffffull);
         a.mv[(tl.frame * a.Hp + tl.by0 + brow) * (int64_t)a.Wp + tl.bx0 + b] = idx;
+    }
+}
+
+// ================================================================================================
+// integer kernel, +-16, cross term on the tensor cores (mma.sync.m16n8k32.u8)
+// ================================================================================================
+// The cross term X[dy][dx] = sum_{i,j} c[i][j] r[y+dy+i][x+dx+j] of ONE block is a small GEMM once the vertical
+// shift is folded into a Toeplitz operand:  with t a window row and j a block column,
+//     A[m][(t, j)] = c[t - m][j]   (zero unless 0 <= t - m < 8)        m = 16 vertical shifts of an M-tile
+//     B[(t, j)][n] = r[y0 + t][x0 + n + j]                             n = 8 horizontal shifts of an N-tile
+//     C[m][n]      = sum_t sum_j c[t - m][j] r[y0 + t][x0 + n + j] = X at (dy, dx) = (y0 + m, x0 + n).
+// K runs over 24 window rows x 8 columns = six k-steps of 32; a k-step's B fragment is exactly two words of the
+// unaligned-word view U (bytes x..x+3 of a window row, any x), and its A fragment four words of the block stored
+// with 15 zero rows above and below -- no operand is ever materialised.  A fragments do not depend on the M-tile,
+// and the B fragment of (M-tile mt, k-step ks) is that of 4-row group 4 mt + ks, so a warp walks the ten row
+// groups of its block's 40-row window once: 24 + 100 shared-memory loads and 70 mma per block (M-tiles dy -16..-1,
+// 0..15 and the single row +16, which needs two k-steps only; N-tiles dx -16..23, the last one for +16 alone).
+// 35 % of K and 66 % of M x N are useful, which still is 2.6 times the useful multiply-adds per clock of dp4a
+// (mma.sync u8: 1935 MAC/clk/SM measured, dp4a 256).  sum(r^2), sum(c^2) and the staging are the phases the dp4a
+// kernel uses (me_int_prepare); a warp owns its block's whole search, so the argmin needs no atomics:
+// per-thread strict minimum in ascending index order, then two warp reductions (ssd, then index among equals)
+// = the reference's first strict minimum in (dy, dx) raster order (motion.py:35-51).
+constexpr int kMmaSr = 16, kMmaSpan = 33;
+constexpr int kMmaPitch = 112;       // U / HS pitch in words for the 4 x 8-block tile: 96 used; == 16 (mod 32), so the two
+                                     // window rows a B fragment touches fall on disjoint banks
+constexpr int kMmaTby = 4, kMmaTbx = 8;
+constexpr int kCpPitch = 80;         // words per zero-padded current block: 39 rows (i = -15 .. 23) x 2 words + 2
+
+__device__ __forceinline__ void mma_u8(int (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kMeThreads, 2) k_me_mma16(const MeArgs a) {
+    constexpr int P4 = kMmaPitch;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned *s_u = reinterpret_cast<unsigned *>(smem_raw);                   // [64][P4]
+    unsigned *s_hs = reinterpret_cast<unsigned *>(smem_raw + a.hs_off);       // [71][P4]
+    unsigned *s_b = reinterpret_cast<unsigned *>(smem_raw + a.b_off);         // [64][pw]
+    unsigned *s_cur = reinterpret_cast<unsigned *>(smem_raw + a.cur_off);     // [32][kCurPitch]
+    unsigned *s_cp = reinterpret_cast<unsigned *>(smem_raw + a.part_off);     // [32][kCpPitch]
+    __shared__ unsigned s_c2[64];
+    const MeTile tl = me_tile(a);
+    const int tid = threadIdx.x;
+    // S is stored as 128 S + x (x = window column < 112): a candidate's key 128 ssd + x orders the candidates of one
+    // window row by (ssd, dx) with nothing but a multiply-add and a minimum per candidate
+    if (!me_int_prepare<T, P4, 4, 7, true>(a, tl, s_u, s_hs, s_b, s_cur, s_c2)) return;
+
+    // current blocks with 15 zero rows above and 16 below: row r of a slot holds block row r - 15
+    for (int idx = tid; idx < kMmaTby * kMmaTbx * kCpPitch; idx += kMeThreads) {
+        const int slot = idx / kCpPitch, w = idx - slot * kCpPitch;
+        const int i = (w >> 1) - 15;
+        s_cp[idx] = ((unsigned)i < 8u) ? s_cur[slot * kCurPitch + i * 2 + (w & 1)] : 0u;
+    }
+    __syncthreads();
+
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tq = lane & 3, tlo = tq >> 1, h = tq & 1;
+    const int H = (int)a.H, W = (int)a.W;
+    const int nblk = tl.nby * tl.nbx;
+    const FastDiv d_nbx(a.m_nbx[tl.nbx != a.tbx]);
+    for (int blk = warp; blk < nblk; blk += kMeWarps) {
+        const int brow = d_nbx.div(blk), b = blk - brow * tl.nbx;
+        const int slot = brow * kMmaTbx + b;
+        // ---- A fragments: rows g / g + 8 of the Toeplitz operand, k-steps 0..5 ----
+        const unsigned *cp = s_cp + slot * kCpPitch + ((tlo - g + 15) * 2 + h);
+        unsigned af[6][4];
+#pragma unroll
+        for (int ks = 0; ks < 6; ++ks) {
+            af[ks][0] = cp[(4 * ks) * 2];
+            af[ks][1] = cp[(4 * ks - 8) * 2];
+            af[ks][2] = cp[(4 * ks + 2) * 2];
+            af[ks][3] = cp[(4 * ks + 2 - 8) * 2];
+        }
+        int acc[3][5][4];
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 5; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0;
+        const unsigned *ub = s_u + (8 * brow + tlo) * P4 + 8 * b + g + 4 * h;
+#pragma unroll
+        for (int rg = 0; rg < 10; ++rg) {
+            unsigned b0[5], b1[5];
+#pragma unroll
+            for (int nt = 0; nt < 5; ++nt) {
+                b0[nt] = ub[(4 * rg) * P4 + 8 * nt];
+                b1[nt] = ub[(4 * rg + 2) * P4 + 8 * nt];
+            }
+#pragma unroll
+            for (int mt = 0; mt < 3; ++mt) {
+                const int ks = rg - 4 * mt;
+                if (ks >= 0 && ks < (mt == 2 ? 2 : 6)) {
+#pragma unroll
+                    for (int nt = 0; nt < 5; ++nt) mma_u8(acc[mt][nt], af[ks], b0[nt], b1[nt]);
+                }
+            }
+        }
+        // ---- argmin.  key = 128 (S - 2 X) + x per candidate (c2 is common to the block and joins at the end);
+        //      rows ascend within a thread, so a later row replaces the best only on a strictly smaller ssd ----
+        const int gy0 = 8 * (tl.by0 + brow) - kMmaSr, gx0 = 8 * (tl.bx0 + b) - kMmaSr;     // frame position of candidate (0, 0)
+        const bool interior = gy0 >= 0 && gy0 + 2 * kMmaSr + 8 <= H && gx0 >= 0 && gx0 + 2 * kMmaSr + 8 <= W;   // warp-uniform
+        unsigned best = 0xffffffffu, bidx = 0xffffffffu;                  // best = 128 (S - 2X) of the winner, bidx its index
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                if (mt == 2 && hf == 1) continue;
+                const int dyi = 16 * mt + 8 * hf + g;
+                const unsigned *sp = s_hs + (8 * brow + dyi) * P4 + 8 * b + 2 * tq;
+                int rk = 0x7fffffff;                                      // min over the row's candidates of 128 (S - 2X) + x (signed: S < 2X happens)
+                if (interior) {
+                    if (mt < 2 || g == 0) {
+#pragma unroll
+                        for (int nt = 0; nt < 4; ++nt) {
+                            const uint2 sv = *reinterpret_cast<const uint2 *>(sp + 8 * nt);
+                            rk = min(rk, (int)sv.x - (acc[mt][nt][2 * hf] << 8));
+                            rk = min(rk, (int)sv.y - (acc[mt][nt][2 * hf + 1] << 8));
+                        }
+                        const int k32 = (int)sp[32] - (acc[mt][4][2 * hf] << 8);                 // dx = +16: lanes tq == 0 only
+                        rk = min(rk, tq == 0 ? k32 : 0x7fffffff);
+                    }
+                } else {
+                    const bool row_ok = dyi < kMmaSpan && gy0 + dyi >= 0 && gy0 + dyi + 8 <= H;
+#pragma unroll
+                    for (int nt = 0; nt < 5; ++nt) {
+                        uint2 sv = make_uint2(0u, 0u);
+                        if (row_ok) sv = *reinterpret_cast<const uint2 *>(sp + 8 * nt);
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int sx = 8 * nt + 2 * tq + e;
+                            const bool ok = row_ok && sx < kMmaSpan && gx0 + sx >= 0 && gx0 + sx + 8 <= W;
+                            const int key = (int)(e ? sv.y : sv.x) - (acc[mt][nt][2 * hf + e] << 8);
+                            if (ok) rk = min(rk, key);
+                        }
+                    }
+                }
+                // 128 c2 joins here: ssd = c2 + S - 2X >= 0, so the full key is a plain unsigned number again
+                if (rk != 0x7fffffff) {
+                    const unsigned full = (unsigned)rk + s_c2[blk];
+                    const unsigned ssd7 = full & ~127u;
+                    if (ssd7 < best) { best = ssd7; bidx = (unsigned)(dyi * kMmaSpan) + ((full & 127u) - (unsigned)(8 * b)); }
+                }
+            }
+        const unsigned m = __reduce_min_sync(0xffffffffu, best);
+        const unsigned mi = __reduce_min_sync(0xffffffffu, best == m ? bidx : 0xffffffffu);
+        if (lane == 0) a.mv[(tl.frame * a.Hp + tl.by0 + brow) * (int64_t)a.Wp + tl.bx0 + b] = (int64_t)mi;
     }
 }
 
@@ -726,6 +1002,11 @@ cudaError_t launch_me_exact(int device, cudaStream_t st, const void *ref, const 
     return me_launch_chunks(k_me_exact<double>, a, 8, smem, st);
 }
 
+static bool me_mma_enabled() {       // A/B switch for profiling: IVC_ME_MMA=0 selects the dp4a kernel at +-16
+    const char *e = getenv("IVC_ME_MMA");
+    return !(e && e[0] == '0');
+}
+
 // integer kernel: candidates per task for a search span (least padding of the last dy-group, then larger)
 static int me_int_group(int span) {
     static const int gs[] = {11, 9, 5, 3};
@@ -738,7 +1019,7 @@ static int me_int_group(int span) {
 }
 
 static size_t me_int_geometry(MeArgs &a, int G, int pitch, int64_t n_frames, int64_t H, int64_t W, int sr, size_t budget,
-                              int64_t min_ctas) {
+                              int64_t min_ctas, int force_tby = 0, int force_tbx = 0) {
     a.Hp = (int)(H / 8); a.Wp = (int)(W / 8); a.sr = sr; a.span = 2 * sr + 1;
     a.ngrp = (a.span + G - 1) / G;
     a.ntpb = a.ngrp * a.span;
@@ -746,8 +1027,9 @@ static size_t me_int_geometry(MeArgs &a, int G, int pitch, int64_t n_frames, int
     size_t smem = 0;
     for (auto &s : shapes) {
         a.tby = s[0]; a.tbx = s[1];
+        if (force_tby) { a.tby = force_tby; a.tbx = force_tbx; }
         const int64_t ctas = n_frames * ((a.Hp + a.tby - 1) / a.tby) * (int64_t)((a.Wp + a.tbx - 1) / a.tbx);
-        if (ctas < min_ctas && !(s[0] == 1 && s[1] == 1) && s[0] * s[1] > 8) continue;
+        if (!force_tby && ctas < min_ctas && !(s[0] == 1 && s[1] == 1) && s[0] * s[1] > 8) continue;
         a.R = 8 * (a.tby - 1) + a.ngrp * G + 7;                    // covers the last (padded) dy-group
         a.Wc = 8 * a.tbx + 2 * sr;
         a.P = pitch ? pitch : (a.Wc + 3) & ~3;                     // U / HS pitch in words (one per byte column)
@@ -758,7 +1040,7 @@ static size_t me_int_geometry(MeArgs &a, int G, int pitch, int64_t n_frames, int
         a.b_off = a.hs_off + (8 * a.nseg + 7) * a.P * 4;
         a.cur_off = (a.b_off + a.R * a.pw * 4 + 15) & ~15;
         smem = (size_t)a.cur_off + (size_t)a.tby * a.tbx * kCurPitch * 4;
-        if (smem <= budget) break;
+        if (smem <= budget || force_tby) break;
     }
     a.tiles_y = (a.Hp + a.tby - 1) / a.tby;
     a.tiles_x = (a.Wp + a.tbx - 1) / a.tbx;
@@ -767,6 +1049,8 @@ static size_t me_int_geometry(MeArgs &a, int G, int pitch, int64_t n_frames, int
     a.m_ntpb = fastdiv_magic(a.ntpb); a.m_span = fastdiv_magic(a.span);
     a.m_nbx[0] = fastdiv_magic(a.tbx); a.m_nbx[1] = fastdiv_magic(last_nbx);
     a.m_cww[0] = fastdiv_magic(2 * a.tbx); a.m_cww[1] = fastdiv_magic(2 * last_nbx);
+    a.ipr[0] = (8 * a.tbx + 2 * sr + 7) / 8; a.ipr[1] = (8 * last_nbx + 2 * sr + 7) / 8;
+    a.m_ipr[0] = fastdiv_magic(a.ipr[0]); a.m_ipr[1] = fastdiv_magic(a.ipr[1]);
     return smem;
 }
 
@@ -778,6 +1062,24 @@ cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const vo
     MeArgs a;
     a.ref = ref; a.cur = cur; a.n = n; a.H = H; a.W = W; a.ref_fs = ref_fs; a.cur_fs = cur_fs; a.mv = mv;
     a.flag = flag; a.run_if = 0; a.check = check;
+    if (sr == kMmaSr && me_mma_enabled()) {
+        // +-16: the cross term on the tensor cores (k_me_mma16); same staging / sum-of-squares phases
+        const size_t sm = me_int_geometry(a, 11, kMmaPitch, n, H, W, sr, 227 * 1024, 0, kMmaTby, kMmaTbx);
+        a.part_off = (int)((sm + 15) & ~(size_t)15);
+        const size_t smem_mma = (size_t)a.part_off + (size_t)kMmaTby * kMmaTbx * kCpPitch * 4;
+        if (H * W >= 2147483647LL || smem_mma > 113 * 1024) return cudaErrorInvalidValue;
+        const int el = u8 ? 1 : f32 ? 4 : 8;
+        if (u8)
+            a.vec = sr % 4 == 0 && ((uintptr_t)ref & 3) == 0 && ((uintptr_t)cur & 3) == 0 && ref_fs % 4 == 0 && cur_fs % 4 == 0;
+        else
+            a.vec = sr % (16 / el) == 0 && ((uintptr_t)ref & 15) == 0 && ((uintptr_t)cur & 15) == 0 &&
+                    (ref_fs * el) % 16 == 0 && (cur_fs * el) % 16 == 0;
+        cudaError_t e0;
+        if (check && (e0 = cudaMemsetAsync(flag, 0, sizeof(int), st)) != cudaSuccess) return e0;
+        return u8 ? me_launch_chunks(k_me_mma16<unsigned char>, a, 1, smem_mma, st, kMeThreads)
+             : f32 ? me_launch_chunks(k_me_mma16<float>, a, 4, smem_mma, st, kMeThreads)
+                   : me_launch_chunks(k_me_mma16<double>, a, 8, smem_mma, st, kMeThreads);
+    }
     const int G = me_int_group(2 * sr + 1);
     // common cases get a compile-time pitch: 16-block-wide tiles at +-4 (136) and up to +-16 (160)
     const int pitch = (G == 9 && sr <= 4) ? 136 : (G == 9 && sr <= 8) ? 144 : (G == 11 && sr <= 16) ? 160 : 0;

@@ -8,7 +8,17 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ivclab_b200 as ivc  # noqa: E402
-from bench_configs import luma_seq, timed  # noqa: E402
+import bench_configs as BC  # noqa: E402
+
+DEV = torch.device("cuda", 0)
+
+
+def luma_seq(T, H, W, seed, shift=3):
+    return BC.luma_seq(torch, DEV, T, H, W, seed, shift)
+
+
+def timed(fn, reps, warm=3):
+    return BC.Ctx(torch, None, DEV, 0, 1, 6542.1).timed(fn, reps, warm)
 
 
 def main():
@@ -46,11 +56,23 @@ def main():
         t = timed(lambda: pc.estimate(s[:-1], s[1:]), 5)
         print(f"1080p x32 sr={sr} int: {t:.3f} ms  {32 * 1080 * 1920 / t / 1e3:.0f} Mpixel/s")
     del s
-    s4 = luma_seq(5, 2160, 3840, 4000, shift=12)
-    for mode in ("int", "exact"):
-        pc = ivc.PFrameBlockCoder(1.0, 16, me_mode=mode)
-        t = timed(lambda: pc.estimate(s4[:-1], s4[1:]), 3, warm=1)
-        print(f"4K x4 sr=16 {mode}: {t / 4:.3f} ms/frame  {4 * 2160 * 3840 / t / 1e3:.0f} Mpixel/s")
+    s4 = luma_seq(9, 2160, 3840, 4000, shift=12)
+    res = {}
+    for mma in ("1", "0"):                                  # tensor-core cross term vs the dp4a kernel (A/B switch)
+        os.environ["IVC_ME_MMA"] = mma
+        pc = ivc.PFrameBlockCoder(1.0, 16, me_mode="int")
+        res[mma] = pc.estimate(s4[:-1], s4[1:])
+        t = timed(lambda: pc.estimate(s4[:-1], s4[1:]), 5, warm=2)
+        print(f"4K x8 sr=16 int IVC_ME_MMA={mma}: {t / 8:.4f} ms/frame  {8 * 2160 * 3840 / t / 1e3:.0f} Mpixel/s")
+        s8 = s4.to(torch.uint8)
+        t = timed(lambda: pc.estimate(s8[:-1], s8[1:]), 5, warm=2)
+        print(f"4K x8 sr=16 uint8 planes IVC_ME_MMA={mma}: {t / 8:.4f} ms/frame")
+    print("mma == dp4a vectors:", bool(torch.equal(res["1"], res["0"])))
+    os.environ.pop("IVC_ME_MMA")
+    if "--exact" in sys.argv:
+        pc = ivc.PFrameBlockCoder(1.0, 16, me_mode="exact")
+        t = timed(lambda: pc.estimate(s4[:2], s4[1:3]), 2, warm=1)
+        print(f"4K x2 sr=16 exact: {t / 2:.3f} ms/frame; == int: {bool(torch.equal(pc.estimate(s4[:2], s4[1:3]), res['1'][:2]))}")
 
 
 if __name__ == "__main__":
