@@ -13,7 +13,7 @@ from typing import Callable, List, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "shard_round_robin", "run_sharded", "gather_in_order", "gather_rows"]
+__all__ = ["shard_range", "shard_round_robin", "run_sharded", "gather_in_order", "gather_rows", "SharedPinned"]
 
 
 def shard_range(n_units: int, rank: int, world: int) -> Tuple[int, int]:
@@ -102,3 +102,83 @@ def gather_rows(local: torch.Tensor, n_units: int, dst: int = 0, axis: int = 0, 
         out.copy_(full, non_blocking=False)
         return out
     return full
+
+
+class SharedPinned:
+    """A host array in POSIX shared memory that every rank of a one-node run maps and page-locks: each rank's
+    device-to-host copies of ITS units land directly in the array rank ``dst`` reads -- the "host gather of bitstream
+    symbols and PSNR" of the path with no collective and no second copy (one process per GPU, one node).
+
+    Collective constructor: every rank calls ``SharedPinned(shape, dtype, tag)``; rank ``dst`` creates the segment
+    under ``/dev/shm``, the others attach after a barrier.  ``.tensor`` is a CPU tensor over the segment (pinned via
+    ``cudaHostRegister`` when a CUDA device is in use; plain shared memory otherwise, e.g. in the gloo tests).
+    ``close()`` (collective) unmaps and removes it.  Without a process group it is a private pinned buffer."""
+
+    def __init__(self, shape, dtype, tag: str, dst: int = 0, register: bool = True):
+        import mmap
+        import os
+        on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self._rank = dist.get_rank() if on else 0
+        self._dst, self._on = dst, on
+        self._registered = False
+        nbytes = int(torch.tensor([], dtype=dtype).element_size())
+        for d in shape:
+            nbytes *= int(d)
+        self._nbytes = max(nbytes, 1)
+        name = [f"ivcb200_{os.getpid()}_{tag}"]
+        if on:
+            dist.broadcast_object_list(name, src=dst)
+        self._path = os.path.join("/dev/shm", name[0])
+        # no step raises before both barriers have been passed: a rank that fails must not leave the others waiting
+        err, fd, self._map, self.tensor = None, -1, None, None
+        try:
+            if self._rank == dst:
+                fd = os.open(self._path, os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
+                os.ftruncate(fd, self._nbytes)
+        except Exception as e:
+            err = e
+        if on:
+            dist.barrier()
+        try:
+            if err is None:
+                if self._rank != dst:
+                    fd = os.open(self._path, os.O_RDWR)
+                self._map = mmap.mmap(fd, self._nbytes)
+                os.close(fd)
+                esz = torch.tensor([], dtype=dtype).element_size()
+                self.tensor = torch.frombuffer(self._map, dtype=dtype, count=nbytes // esz).reshape(tuple(shape))
+                if register and torch.cuda.is_available():
+                    rc = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), self._nbytes, 0)
+                    if int(rc) != 0:
+                        raise RuntimeError(f"cudaHostRegister failed on the shared segment: {rc}")
+                    self._registered = True
+        except Exception as e:
+            err = e
+        if on:
+            dist.barrier()
+        if err is not None:
+            if self._rank == dst:
+                try:
+                    os.unlink(self._path)
+                except OSError:
+                    pass
+            raise err
+
+    def close(self):
+        import os
+        if self._on:
+            dist.barrier()
+        if self._registered:
+            torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
+            self._registered = False
+        self.tensor = None
+        try:
+            if self._map is not None:
+                self._map.close()
+        except BufferError:
+            pass                                  # a caller still holds a view; the mapping goes with the process
+        if self._rank == self._dst:
+            try:
+                os.unlink(self._path)
+            except FileNotFoundError:
+                pass

@@ -62,10 +62,10 @@ class RateDistortionSweep:
         return sse, hist, outside
 
     # ---- the host-fed pipeline ------------------------------------------------------------------------------
-    def _buffers(self, F, H, W):
+    def _buffers(self, F, H, W, need_host=True):
         Q = len(self.coders)
         key = (F, H, W, Q, self.nb)
-        if self._host is None or self._host[0] != key:
+        if need_host and (self._host is None or self._host[0] != key):
             pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
             self._host = (key, {"sse": pin((Q, F), torch.float64), "hist": pin((Q, F, self.nb), torch.int32),
                                 "outside": pin((Q, F), torch.int32)})
@@ -73,16 +73,20 @@ class RateDistortionSweep:
         if self._slots is None or self._slots[0] != skey:
             self._slots = (skey, [torch.empty((self.chunk, H, W, 3), dtype=torch.uint8, device=self.device)
                                   for _ in range(self.nslots)])
-        return self._host[1], self._slots[1]
+        return (self._host[1] if need_host else None), self._slots[1]
 
-    def run(self, rgb, to_host=True):
+    def run(self, rgb, to_host=True, out=None, out_at=0):
         """rgb [F,H,W,3] uint8, a pinned host tensor (numpy arrays are accepted and pinned once; H a multiple of 8,
         W of 16).  Returns host arrays -- views of this object's pinned buffers, valid until the next ``run`` --
         ``sse`` [Q,F] float64 (``psnr = 10 log10(255^2 / (sse / (H W 3)))``), ``hist`` [Q,F,bins] int32 with
         ``hist[q,f,k]`` = number of symbols equal to ``hist_lo + k``, ``outside`` [Q,F] (symbols outside the
         histogram's range; 0 for 8-bit frames with the default range), plus ``h2d_bytes`` / ``d2h_bytes``.
         ``to_host=False`` leaves the three results on the device (CUDA tensors, complete when the compute stream
-        ``self._s_cmp`` is): the form a multi-GPU run hands to ``shard.gather_rows``."""
+        ``self._s_cmp`` is): the form a multi-GPU run hands to ``shard.gather_rows``.  ``out`` (a dict of pinned host
+        tensors ``sse`` [Q,Ftot], ``hist`` [Q,Ftot,bins], ``outside`` [Q,Ftot]) with ``out_at``: the results of frame f
+        are downloaded to column ``out_at + f`` of those tensors instead of this object's own buffers -- with
+        ``shard.SharedPinned`` buffers every rank of a sharded run writes its frame range straight into the array
+        rank 0 reads (the host gather without a collective)."""
         if isinstance(rgb, np.ndarray):
             rgb = torch.from_numpy(rgb)
         if rgb.dtype != torch.uint8 or rgb.ndim != 4 or rgb.shape[-1] != 3 or rgb.shape[1] % 8 or rgb.shape[2] % 16:
@@ -90,7 +94,9 @@ class RateDistortionSweep:
         if not rgb.is_pinned():
             rgb = rgb.pin_memory()
         F, H, W, _ = rgb.shape
-        hb, slots = self._buffers(F, H, W)
+        hb, slots = self._buffers(F, H, W, need_host=out is None and to_host)
+        if out is not None:
+            hb, to_host = out, True
         Q, C, S = len(self.coders), self.chunk, self.nslots
         bounds = [(lo, min(lo + C, F)) for lo in range(0, F, C)]
         n = len(bounds)
@@ -128,10 +134,11 @@ class RateDistortionSweep:
                 self._s_out.wait_event(ev_cmp[k])
                 for t in (sse, hist, outside):
                     t.record_stream(self._s_out)
-                for qi in range(Q):                                        # [qi, lo:hi] is contiguous on both sides
-                    hb["hist"][qi, lo:hi].copy_(hist[qi], non_blocking=True)
-                    hb["sse"][qi, lo:hi].copy_(sse[qi], non_blocking=True)
-                    hb["outside"][qi, lo:hi].copy_(outside[qi], non_blocking=True)
+                a, b = out_at + lo, out_at + hi
+                for qi in range(Q):                                        # [qi, a:b] is contiguous on both sides
+                    hb["hist"][qi, a:b].copy_(hist[qi], non_blocking=True)
+                    hb["sse"][qi, a:b].copy_(sse[qi], non_blocking=True)
+                    hb["outside"][qi, a:b].copy_(outside[qi], non_blocking=True)
 
         for k in range(min(S - 1, n)):
             upload(k)
@@ -149,9 +156,10 @@ class RateDistortionSweep:
         if n:
             download(n - 1)
         self._s_out.synchronize()
-        return {"sse": hb["sse"].numpy(), "hist": hb["hist"].numpy(), "outside": hb["outside"].numpy(),
+        view = (lambda t: t[:, out_at:out_at + F].numpy()) if out is not None else (lambda t: t.numpy())
+        return {"sse": view(hb["sse"]), "hist": view(hb["hist"]), "outside": view(hb["outside"]),
                 "qscales": self.qscales, "hist_lo": self.lo, "h2d_bytes": rgb.numel(),
-                "d2h_bytes": hb["sse"].numel() * 8 + hb["hist"].numel() * 4 + hb["outside"].numel() * 4}
+                "d2h_bytes": Q * F * (8 + 4 * self.nb + 4)}
 
     # ---- what the sweep's consumers compute from the results (host, numpy) -------------------------------------
     @staticmethod

@@ -304,6 +304,19 @@ def test_rate_distortion_sweep_vs_reference_statement():
     dev = sw.run(rgb, to_host=False)                                               # results left on the device
     torch.cuda.synchronize()
     assert np.array_equal(dev["hist"].cpu().numpy(), out["hist"]) and np.array_equal(dev["sse"].cpu().numpy(), out["sse"])
+    # results downloaded straight into caller-owned (shared, page-locked) arrays at a column offset: the multi-GPU host gather
+    from ivclab_b200.shard import SharedPinned
+    keep = {k: out[k].copy() for k in ("sse", "hist", "outside")}
+    sh = {"sse": SharedPinned((3, F + 3), torch.float64, "sse"), "hist": SharedPinned((3, F + 3, 8192), torch.int32, "hist"),
+          "outside": SharedPinned((3, F + 3), torch.int32, "outside")}
+    assert all(v.tensor.is_pinned() for v in sh.values())
+    got = sw.run(rgb, out={k: v.tensor for k, v in sh.items()}, out_at=2)
+    for k in keep:
+        assert np.array_equal(got[k], keep[k]) and np.array_equal(sh[k].tensor[:, 2:2 + F].numpy(), keep[k]), k
+    del got
+    for v in sh.values():
+        v.close()
+    out = keep
     bits = sw.entropy_bits(out["hist"])
     assert bits.shape == (3, F) and np.all(bits[0] > bits[1])                      # finer quantisation costs more bits
     with pytest.raises(ValueError):

@@ -129,3 +129,40 @@ def test_gather_rows_single_process():
     assert gather_rows(x, 4, axis=1) is x
     with pytest.raises(ValueError):
         gather_rows(x, 5, axis=1)
+
+
+def _shared_worker(rank, world, port, q):
+    from ivclab_b200.shard import SharedPinned
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = 7
+        lo, hi = shard_range(n, rank, world)
+        sp = SharedPinned((2, n, 3), torch.int32, "test", register=False)     # CPU test: shared, not page-locked
+        # every rank writes its own unit range (on a GPU box: the destination of its device-to-host copies)
+        sp.tensor[:, lo:hi] = torch.arange(lo, hi, dtype=torch.int32)[None, :, None] * 10 + rank
+        dist.barrier()                                                       # the whole "gather"
+        if rank == 0:
+            q.put(sp.tensor.clone().tolist())
+        path = sp._path
+        sp.close()
+        if rank == 0:
+            assert not os.path.exists(path)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_shared_pinned_host_gather():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shared_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = [[[10 * u + (0 if u < 4 else 1)] * 3 for u in range(7)]] * 2
+    assert got == want
