@@ -8,8 +8,9 @@ frames (cfg3 shape for the intra half, cfg4/cfg5-style frame pairs for the inter
 
     K1  intra forward   YCbCr f64 HWC -> DCT -> quantize -> zig-zag        (ivc_intra_forward)
     K2  intra inverse   scan indices -> dequantize -> IDCT -> HWC f64      (ivc_intra_inverse)
-    K3  motion search   luma(t) vs luma(t-1), +-4 full search, auto kernel  (ivc_me_full_search)
-    K1p P-frame forward MC + residual + DCT + quantize + zig-zag           (ivc_pframe_forward)
+    K3+K1p  motion search luma(t) vs luma(t-1), +-4 full search, THEN MC + residual + DCT + quantize + zig-zag of the
+            same blocks, in one call (ivc_pframe_search_forward: one fused kernel on integer-valued frames -- it reads
+            the two frames once; `--unfused` runs ivc_me_full_search + ivc_pframe_forward as two phases instead)
     K2p P-frame inverse dequantize + IDCT + prediction add                 (ivc_pframe_inverse)
 
 `value` = F*H*W pixels / step time: every pixel is intra-coded AND inter-coded once per step.
@@ -56,6 +57,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the host-fed legs (e2e keys become null)")
     ap.add_argument("--me-mode", default="auto", choices=["auto", "exact", "int"])
+    ap.add_argument("--unfused", action="store_true", help="time the search and the P-frame forward as two calls / kernels (round-1 step)")
     ap.add_argument("--configs", default="all",
                     help="which of BASELINE.json's five configurations to measure as named into the `configs` key: "
                          "'all', 'none', or a comma list such as cfg3,cfg4 (bench_configs.py)")
@@ -231,7 +233,10 @@ def run_b200(args):
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
     stream = torch.cuda.current_stream(device)
     sp = stream.cuda_stream
-    launches_per_step = {"auto": 6, "exact": 5, "int": 5}[args.me_mode]
+    # K1, K2, K2p + the search and P-frame forward: fused = 1 kernel (+ the exact search and the stand-alone forward in auto
+    # mode, enqueued behind it, which exit at once on integer frames); unfused = search (2 in auto mode) + forward
+    fused = not args.unfused and args.me_mode != "exact"
+    launches_per_step = 3 + ({"auto": 3, "int": 1}[args.me_mode] if fused else {"auto": 3, "exact": 2, "int": 2}[args.me_mode])
 
     def k1():
         _lib.check(L.ivc_intra_forward(local, sp, ycbcr.data_ptr(), _lib.F64, Fr, H, W, 3, H * W * 3, dtab.data_ptr(),
@@ -253,7 +258,15 @@ def run_b200(args):
         _lib.check(L.ivc_pframe_inverse(local, sp, zz_p.data_ptr(), 3, None, ref.data_ptr(), mv.data_ptr(), _lib.F64,
                                         Fr, H, W, SR, dtab.data_ptr(), tcode, rec_p.data_ptr()), "k2p")
 
-    phases = [("intra_fwd", k1), ("intra_inv", k2), ("me", k3), ("pframe_fwd", k1p), ("pframe_inv", k2p)]
+    def k3k1p():
+        _lib.check(L.ivc_pframe_search_forward(local, sp, luma.data_ptr(), ref.data_ptr(), _lib.F64, Fr, H, W, SR, me_mode,
+                                               dtab.data_ptr(), tcode, 3, mv.data_ptr(), zz_p.data_ptr(), ws.data_ptr(), ws_bytes),
+                   "k3+k1p")
+
+    if fused:
+        phases = [("intra_fwd", k1), ("intra_inv", k2), ("me_pframe_fwd", k3k1p), ("pframe_inv", k2p)]
+    else:
+        phases = [("intra_fwd", k1), ("intra_inv", k2), ("me", k3), ("pframe_fwd", k1p), ("pframe_inv", k2p)]
 
     def step(evs=None):
         for i, (_, fn) in enumerate(phases):
@@ -301,6 +314,17 @@ def run_b200(args):
                 for i, (name, _) in enumerate(phases)}
     px = Fr * H * W
     value = world * px / (ms_step * 1e-3) / 1e6
+    if fused:                                          # the two halves of the fused phase alone, outside the step (reported, not summed)
+        for name, fn in (("me", k3), ("pframe_fwd", k1p)):
+            for _ in range(3):
+                fn()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record(stream)
+            for _ in range(K):
+                fn()
+            b_.record(stream)
+            torch.cuda.synchronize()
+            phase_ms[name] = a_.elapsed_time(b_) / K
 
     e2e_ms = serial_ms = raw_ms = e2e_val = raw_val = None
     h2d = d2h = raw_h2d = raw_d2h = None
@@ -469,13 +493,17 @@ def run_b200(args):
         which = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         # algorithmic bytes per pixel of each phase: K1 8 in + 4 out per sample x 3 channels,
         # K2 the same, ME two float64 frame reads, K1p cur 8 + gathered prediction 8 + 3 x 4 out, K2p 4 in + 8 + 8
-        algo = {"intra_fwd": px * 36, "intra_inv": px * 36, "me": px * 16, "pframe_fwd": px * 28, "pframe_inv": px * 20}
+        # fused search + forward: the two frames once (16) + 3 x 4 out + the vectors
+        algo = {"intra_fwd": px * 36, "intra_inv": px * 36, "me": px * 16, "pframe_fwd": px * 28, "pframe_inv": px * 20,
+                "me_pframe_fwd": px * 28 + px // 8}
+        in_step = [n for n, _ in phases]
         kname = {"intra_fwd": "k_forward_c3_tma (K1: DCT + quantise + zig-zag, 3-channel intra)",
                  "intra_inv": "k_inverse_c3_tma<0,0> (K2: un-zig-zag + dequantise + IDCT, 3-channel intra)",
                  "me": "k_me_int (K3: +-4 full search, packed-integer kernel)",
                  "pframe_fwd": "k_pframe_forward_tm (K1p: MC + residual + DCT + quantise + zig-zag)",
-                 "pframe_inv": "k_pframe_inverse_tm (K2p: dequantise + IDCT + prediction add)"}
-        hbm_phases = [k for k in algo if k != "me"]                  # the search is bound by the integer pipe, not by HBM
+                 "pframe_inv": "k_pframe_inverse_tm (K2p: dequantise + IDCT + prediction add)",
+                 "me_pframe_fwd": "k_me_int<double,9,136,PF> (K3+K1p: +-4 full search, then MC + residual + DCT + quantise + zig-zag from the staged bytes)"}
+        hbm_phases = [k for k in in_step if k not in ("me", "me_pframe_fwd")]   # the search is bound by the integer pipe, not by HBM
         dom = max(hbm_phases, key=lambda k: phase_ms[k])             # the TIME-DOMINANT HBM-bound kernel of the step
         dom_gbs = algo[dom] / (phase_ms[dom] * 1e-3) / 1e9
         traffic = traffic_src = None
@@ -486,7 +514,7 @@ def run_b200(args):
             traffic_src = f"constant from {kt['source']} (one ncu --set full capture, scaled to {Fr} frames); NOT measured by this run"
         except Exception:
             pass
-        step_bytes = sum(algo.values())
+        step_bytes = sum(algo[k] for k in in_step)
         sm_hz = (clk.get("sm_mhz") or 1965.0) * 1e6 if clk else 1965.0e6
         sms = torch.cuda.get_device_properties(device).multi_processor_count
         import bench_configs as BC
@@ -531,9 +559,12 @@ def run_b200(args):
                                 "peak_source": f"{BC.IDP_LANES_PER_CLK_SM} dp4a lanes/clk/SM (measured, profiles/r1h_ubench_int.txt) x {sms} SMs x "
                                                f"{sm_hz / 1e6:.0f} MHz (SM clock sampled during the timed region)"}},
             "phases_ms": {k: round(v, 4) for k, v in phase_ms.items()},
+            "phases_in_step": in_step,
+            "phases_note": "phases_in_step are timed inside the step and add up to ms_per_step; any other entry of phases_ms is that "
+                           "kernel alone, timed after the step (the two halves of the fused search + forward phase)",
             "phases_mpixel_s": {k: round(px / (v * 1e-3) / 1e6, 1) for k, v in phase_ms.items()},
-            "phases_hbm_frac": {k: round(algo[k] / (phase_ms[k] * 1e-3) / 1e9 / peak, 4) for k in algo},
-            "me_mode": args.me_mode,
+            "phases_hbm_frac": {k: round(algo[k] / (phase_ms[k] * 1e-3) / 1e9 / peak, 4) for k in phase_ms},
+            "me_mode": args.me_mode, "fused_search_forward": fused,
         }
         if cfgs is not None:
             cfgs["clocks"] = cfg_clk

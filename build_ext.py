@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 OUT = os.path.join(OUT_DIR, "libivcb200.so")
 SOURCES = ["ivc_abi.cu", "ivc_transform.cu", "ivc_motion.cu", "ivc_metrics.cu", "ivc_zerorun.cu", "ivc_color.cu"]
-HEADERS = ["ivc_dct.cuh", "ivc_common.cuh", "ivc_color.cuh", os.path.join("..", "..", "include", "ivclab_b200.h")]
+HEADERS = ["ivc_dct.cuh", "ivc_common.cuh", "ivc_color.cuh", "ivc_tile.cuh", os.path.join("..", "..", "include", "ivclab_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define IVC_ABI_VERSION 4
+#define IVC_ABI_VERSION 5
 
 /* element types */
 #define IVC_U8   0
@@ -188,6 +188,20 @@ int ivc_pframe_forward_ch(int device, void *stream,
                           int64_t n_frames, int64_t H, int64_t W, int search_range,
                           const void *table, int table_dtype,
                           void *pred_out, int out_channels, int32_t *zz_out);
+
+/* ---- a13 + a15 fused: search AND P-frame encoder half in one call (videocodec.py:52 + :68-71 + intracodec.py:66-75) --
+ * mv = compute_motion_vector(ref, cur); zz = flatten(quantize(dct(patch(cur - MC(ref, mv))))) with out_channels (3 or 2,
+ * see ivc_pframe_forward_ch) scan blocks per image block.  cur/ref [n_frames,H,W] F64; mode as ivc_me_full_search.
+ * For +-4 searches of integer-valued frames ONE kernel does both: its tiles code their blocks from the bytes the search
+ * staged, so the frames are read once (16 B/pixel instead of 16 + 16).  In IVC_ME_AUTO mode that kernel validates the
+ * frames and otherwise leaves everything to the exact search and the stand-alone forward kernel, which are enqueued
+ * behind it and run only if it raised the device flag (workspace as for ivc_me_full_search).  Other search ranges,
+ * IVC_ME_EXACT: the two stand-alone kernels.  Results are identical in every case. */
+int ivc_pframe_search_forward(int device, void *stream,
+                              const void *cur, const void *ref, int dtype,
+                              int64_t n_frames, int64_t H, int64_t W, int search_range, int mode,
+                              const void *table, int table_dtype, int out_channels,
+                              int64_t *mv_out, int32_t *zz_out, void *workspace, int64_t workspace_bytes);
 
 /* ---- a15 fused: P-frame decoder half (intracodec.py:115-124 + videocodec.py:74) --------------
  * recon = pred + idct(dequantize(unflatten(zz[..., 0, :])))[channel 0]  (luminance table).

@@ -173,6 +173,38 @@ class PFrameBlockCoder:
         _lib.check(st, "ivc_me_full_search")
         return to_host(mv if batched else mv[0], was_np)
 
+    def estimate_forward(self, ref, cur, channels=3):
+        """Search and encoder half in one call: ``mv = estimate(ref, cur)`` and ``zz = forward(cur, ref, mv)``
+        (videocodec.py:52 + :68-71) -> ``(mv [(N,) Hp, Wp, 1] int64, zz [(N,) Hp, Wp, channels, 64] int32)``.
+        For +-4 searches of integer-valued float64 frames a single kernel does both -- its tiles code their blocks
+        from the bytes the search staged, so the frames are read once; every other case (other search ranges,
+        non-integer frames -- detected on the device in ``me_mode='auto'`` --, ``me_mode='exact'``) runs the two
+        stand-alone kernels.  Same results either way."""
+        r, was_np = to_device(ref)
+        c, _ = to_device(cur, r.device)
+        batched = r.ndim == 3
+        r = aligned16(r.to(torch.float64))
+        c = aligned16(c.to(torch.float64))
+        rv, cv = (r, c) if batched else (r[None], c[None])
+        N, H, W = rv.shape
+        if H % 8 or W % 8:
+            raise IndexError(f"frame sides ({H}, {W}) must be multiples of the 8x8 block size")
+        if channels not in (2, 3):
+            raise ValueError("channels must be 3 (the reference's layout) or 2 (channels 0 and 1)")
+        _, dtab = self.quant._table_on(r.device)
+        mv = torch.empty((N, H // 8, W // 8, 1), dtype=torch.int64, device=r.device)
+        zz = torch.empty((N, H // 8, W // 8, channels, 64), dtype=torch.int32, device=r.device)
+        mode = {"auto": _lib.ME_AUTO, "exact": _lib.ME_EXACT, "int": _lib.ME_INT}[self.motion_comp.me_mode]
+        ws_bytes = _lib.lib.ivc_me_workspace_bytes(N, H, W)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=r.device)
+        st = _lib.lib.ivc_pframe_search_forward(dev_index(rv), stream_ptr(rv.device), cv.data_ptr(), rv.data_ptr(), _lib.F64,
+                                                N, H, W, int(self.search_range), mode, dtab.data_ptr(), code(dtab.dtype),
+                                                channels, mv.data_ptr(), zz.data_ptr(), ws.data_ptr(), ws_bytes)
+        _lib.check(st, "ivc_pframe_search_forward")
+        if not batched:
+            mv, zz = mv[0], zz[0]
+        return to_host(mv, was_np), to_host(zz, was_np)
+
     def forward(self, cur, ref, mv, return_prediction=False, channels=3):
         """residual = cur - MC(ref, mv); -> scan indices ``[(N,) Hp, Wp, 3, 64]`` (and the prediction).
         ``channels=2`` stores channels 0 and 1 only (``[(N,) Hp, Wp, 2, 64]``): numpy broadcasting quantises the one

@@ -289,6 +289,42 @@ int ivc_pframe_forward_ch(int device, void *stream, const void *cur, const void 
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
 
+int ivc_pframe_search_forward(int device, void *stream, const void *cur, const void *ref, int dtype, int64_t n_frames,
+                              int64_t H, int64_t W, int search_range, int mode, const void *table, int table_dtype,
+                              int out_channels, int64_t *mv_out, int32_t *zz_out, void *workspace, int64_t workspace_bytes) {
+    if (n_frames < 0 || H < 0 || W < 0 || search_range < 0 || search_range > 64) return IVC_ERR_ARG;
+    if (out_channels != 2 && out_channels != 3) return IVC_ERR_ARG;
+    if (mode != IVC_ME_AUTO && mode != IVC_ME_EXACT && mode != IVC_ME_INT) return IVC_ERR_ARG;
+    if (dtype != IVC_F64 || !is_float(table_dtype)) return IVC_ERR_DTYPE;
+    if ((H & 7) || (W & 7)) return IVC_ERR_SHAPE;
+    if (n_frames * H * W == 0) return IVC_OK;
+    if (!cur || !ref || !table || !mv_out || !zz_out) return IVC_ERR_ARG;
+    if (!aligned16(cur) || !aligned16(zz_out)) return IVC_ERR_ARG;
+    if (mode == IVC_ME_AUTO && (!workspace || workspace_bytes < ivc_me_workspace_bytes(n_frames, H, W))) return IVC_ERR_WORKSPACE;
+    IVC_ENTER(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    if (mode != IVC_ME_EXACT && ivc::me_pf_fusable(dtype, search_range)) {
+        // one kernel searches and codes; in AUTO mode it leaves non-integer frames to the two stand-alone kernels, which
+        // run only if it raised the flag (no host round trip)
+        int *flag = mode == IVC_ME_AUTO ? (int *)workspace : nullptr;
+        e = ivc::launch_me_int(device, st, ref, cur, dtype, n_frames, H, W, H * W, H * W, search_range, mv_out, flag,
+                               mode == IVC_ME_AUTO ? 1 : 0, table, table_dtype, zz_out, out_channels);
+        if (e != cudaSuccess) return cuda_fail(e);
+        if (mode == IVC_ME_INT) return IVC_OK;
+        e = ivc::launch_me_exact(device, st, ref, cur, false, n_frames, H, W, H * W, H * W, search_range, mv_out, flag, 1);
+        if (e != cudaSuccess) return cuda_fail(e);
+        e = ivc::launch_forward(device, st, cur, n_frames, H, W, 1, H * W, table, table_dtype, zz_out, ref, mv_out,
+                                search_range, nullptr, true, out_channels, flag);
+        return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+    }
+    int rc = ivc_me_full_search(device, stream, ref, cur, dtype, n_frames, H, W, H * W, H * W, search_range, mode, mv_out,
+                                workspace, workspace_bytes);
+    if (rc != IVC_OK) return rc;
+    return ivc_pframe_forward_ch(device, stream, cur, ref, mv_out, dtype, n_frames, H, W, search_range, table, table_dtype,
+                                 nullptr, out_channels, zz_out);
+}
+
 int ivc_pframe_inverse(int device, void *stream, const int32_t *zz, int64_t Czz, const void *pred, const void *ref,
                        const int64_t *mv, int dtype, int64_t n_frames, int64_t H, int64_t W, int search_range,
                        const void *table, int table_dtype, void *recon_out) {

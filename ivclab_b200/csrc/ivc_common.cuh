@@ -9,7 +9,8 @@ namespace ivc {
 // launchers implemented in ivc_transform.cu
 cudaError_t launch_forward(int device, cudaStream_t st, const void *img, int64_t n, int64_t H, int64_t W, int C,
                            int64_t frame_stride, const void *table, int table_dtype, int32_t *out,
-                           const void *ref, const int64_t *mv, int sr, void *pred_out, bool pframe, int out_channels = 3);
+                           const void *ref, const int64_t *mv, int sr, void *pred_out, bool pframe, int out_channels = 3,
+                           const int *run_flag = nullptr);       // P-frame kernels: run only if *run_flag != 0 (null: always)
 cudaError_t launch_inverse(int device, cudaStream_t st, const int32_t *zz, int64_t n, int64_t Hp, int64_t Wp, int Czz,
                            const void *table, int table_dtype, void *out, int mode,
                            const void *pred, const void *ref, const int64_t *mv, int sr);
@@ -28,9 +29,13 @@ cudaError_t launch_zigzag(int device, cudaStream_t st, bool inverse, const void 
 cudaError_t launch_me_exact(int device, cudaStream_t st, const void *ref, const void *cur, bool f32, int64_t n,
                             int64_t H, int64_t W, int64_t ref_fs, int64_t cur_fs, int sr, int64_t *mv,
                             int *flag, int run_if);
+// pf_zz != nullptr: the fused kernel -- after the search every tile codes its blocks (MC + residual + DCT + quantise +
+// zig-zag, pf_och scan channels per block) from the staged bytes; only where me_pf_fusable(dtype, sr)
 cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const void *cur, int dtype, int64_t n,
                           int64_t H, int64_t W, int64_t ref_fs, int64_t cur_fs, int sr, int64_t *mv, int *flag,
-                          int check);
+                          int check, const void *pf_table = nullptr, int pf_table_dtype = 0, int32_t *pf_zz = nullptr,
+                          int pf_och = 3);
+bool me_pf_fusable(int dtype, int sr);
 cudaError_t launch_me_wrap(int device, cudaStream_t st, const void *ref, const void *cur, int dtype, int64_t n, int64_t H,
                            int64_t W, int64_t ref_fs, int64_t cur_fs, int sr, int64_t *mv);
 cudaError_t launch_mc(int device, cudaStream_t st, const void *ref, int elem_size, int64_t n, int64_t H, int64_t W,

@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include "ivc_dct.cuh"
 #include "ivc_common.cuh"
+#include "ivc_tile.cuh"
 
 namespace ivc {
 
@@ -54,6 +55,11 @@ struct MeArgs {
     int *flag;                             // device flag (may be null)
     int run_if;                            // exact kernel: run only if *flag == run_if (when flag != null)
     int check;                             // int kernel: 1 = validate integer-valuedness and raise the flag
+    // fused search + P-frame forward (k_me_int<.., PF = true>): quantiser table, scan-index output, channels stored per block
+    const void *table;
+    int table_dtype;
+    int32_t *zz;
+    int och;
 };
 
 template <typename T> struct Inf;
@@ -587,8 +593,112 @@ __device__ __forceinline__ bool me_int_prepare(const MeArgs &a, const MeTile &tl
     return true;
 }
 
-template <typename T, int G, int PC>
-__global__ void __launch_bounds__(PC ? kMeIntMaxThreads : kMeThreads, PC ? 2 : 3) k_me_int(const MeArgs a) {
+// ---- fused P-frame forward for one group of up to eight horizontally adjacent blocks of an integer-search tile ----
+// What k_pframe_forward_tm does per tile (ivc_transform.cu: residual -> DCT rows -> transpose -> DCT columns ->
+// quantise against [lum, chrom, chrom] -> zig-zag -> 768-byte bulk stores), fed from the tile's BYTES instead of
+// float64 planes: on integer-valued frames the staged bytes ARE the pixel values, so residual = (double)(c - p) is
+// the reference's `y_channel - prediction` bit for bit (videocodec.py:71) and everything after it is the same rounded
+// arithmetic as the stand-alone kernel.  Lane (r, u) owns pixel row r of blocks u and u + 4 of the group in the
+// row pass and column r in the column pass.  work_b: 4352 bytes of warp-private shared memory (the search's U / S
+// tables are dead by now and lend their space).
+constexpr int kMePfThreads = 288, kMePfCtas = 3;                              // the fused kernel's launch shape (+-4: 576 tasks = two rounds of 288)
+constexpr int kPfWork = 4 * kP3TU * 8;                                        // 4352: transposition buffer >= scan staging (3264)
+template <int PC>
+__device__ __forceinline__ void pf_forward_group(const MeArgs &a, const MeTile &tl, int brow, int b0, int nb, const unsigned *s_b,
+                                                 const unsigned *s_cur, const unsigned *s_best32, unsigned char *work_b,
+                                                 const double *s_rt, const double *s_t, bool chroma_twice) {
+    constexpr int pw = PC / 4 + 2;
+    const int lane = threadIdx.x & 31, r = lane & 7, u = lane >> 3;
+    const uint32_t work_s = smem_u32(work_b);
+    double x[2][8];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        const int bi = u + 4 * m, b = b0 + bi;
+        if (bi < nb) {
+            const unsigned *cb = s_cur + (brow * a.tbx + b) * kCurPitch + 2 * r;
+            const unsigned c0 = cb[0], c1 = cb[1];
+            const int idx = (int)(s_best32[brow * tl.nbx + b] & 511u);         // the block's vector (motion.py:55)
+            const int dyi = FastDiv(a.m_span).div(idx), dxi = idx - dyi * a.span;
+            const int xx = 8 * b + dxi;
+            const unsigned *wp = s_b + (8 * brow + dyi + r) * pw + (xx >> 2);
+            const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2];
+            const int sh = (xx & 3) * 8;
+            const unsigned p0 = __funnelshift_r(w0, w1, sh), p1 = __funnelshift_r(w1, w2, sh);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                x[m][k] = i32_to_f64((int)((c0 >> (8 * k)) & 255u) - (int)((p0 >> (8 * k)) & 255u));
+                x[m][4 + k] = i32_to_f64((int)((c1 >> (8 * k)) & 255u) - (int)((p1 >> (8 * k)) & 255u));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[m][k] = 0.0;
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m) dct2_8(x[m]);
+    bulk_wait_read0();                                  // an earlier group's stores have drained WORK
+    __syncwarp();
+    {
+        unsigned char *t_wr = work_b + u * (kP3TU * 8) + (r & 1) * 8;
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<double *>(t_wr + ((((r >> 1) ^ (j >> 1)) << 1) * 8) + (m * 8 + j) * 64) = x[m][j];
+    }
+    __syncwarp();
+    {
+        const unsigned char *t_rd = work_b + u * (kP3TU * 8) + r * 64;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double2 v = *reinterpret_cast<const double2 *>(t_rd + ((k ^ (r >> 1)) << 4) + m * 512);
+                x[m][2 * k] = v.x;
+                x[m][2 * k + 1] = v.y;
+            }
+            dct2_8(x[m]);
+        }
+    }
+    __syncwarp();
+    // numpy broadcasting: the single luma channel is quantised with all three tables (patchquant.py:59)
+    const int nch = (chroma_twice || a.och == 2) ? 2 : 3;
+    const double *rt_l = s_rt + r, *t_l = s_t + r;
+    unsigned zzo[2];                                    // scan positions of raster (v, r), v = 0..7, one byte each
+    zzo[0] = ZZ_ORDER[r] | (ZZ_ORDER[8 + r] << 8) | (ZZ_ORDER[16 + r] << 16) | (ZZ_ORDER[24 + r] << 24);
+    zzo[1] = ZZ_ORDER[32 + r] | (ZZ_ORDER[40 + r] << 8) | (ZZ_ORDER[48 + r] << 16) | (ZZ_ORDER[56 + r] << 24);
+    unsigned char *stage = work_b + u * (kStageUF * 4);
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        if (m == 1) { bulk_wait_read0(); __syncwarp(); }     // round 0's stores have drained the staging area
+        for (int ch = 0; ch < nch; ++ch) {
+            QuantGuard qg;
+            int qv[8];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) qv[v] = qg.q(x[m][v], rt_l[ch * 64 + v * 8]);
+            if (__builtin_expect(qg.risky(), 0)) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v) qv[v] = quantize_exact_f64(x[m][v], t_l[ch * 64 + v * 8]);
+            }
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                const unsigned pos = (zzo[v >> 2] >> (8 * (v & 3))) & 255u;
+                *reinterpret_cast<int *>(stage + pos * 4 + ch * 256) = qv[v];
+                if (ch == 1 && nch == 2) *reinterpret_cast<int *>(stage + pos * 4 + 512) = qv[v];   // channel 2 repeats channel 1
+            }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane < 4 && lane + 4 * m < nb)                // lane u stores the och scan blocks of image block u + 4m
+            bulk_s2g(a.zz + ((tl.frame * a.Hp + tl.by0 + brow) * (int64_t)a.Wp + tl.bx0 + b0 + lane + 4 * m) * (64 * a.och),
+                     work_s + lane * (kStageUF * 4), 256u * (uint32_t)a.och);
+        bulk_commit();                                    // every lane commits (possibly empty) groups: counts stay in step
+    }
+}
+
+// PF: after the search, code the tile's blocks (MC + residual + DCT + quantise + zig-zag) from the staged bytes
+template <typename T, int G, int PC, bool PF = false>
+__global__ void __launch_bounds__(PF ? kMePfThreads : (PC ? kMeIntMaxThreads : kMeThreads), PF ? kMePfCtas : (PC ? 2 : 3)) k_me_int(const MeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned *s_u = reinterpret_cast<unsigned *>(smem_raw);                   // [R][P4]
     unsigned *s_hs = reinterpret_cast<unsigned *>(smem_raw + a.hs_off);       // [8*nseg+7][P4]
@@ -605,6 +715,20 @@ __global__ void __launch_bounds__(PC ? kMeIntMaxThreads : kMeThreads, PC ? 2 : 3
     const FastDiv d_nbx(a.m_nbx[last_col]);
 
     if (tid < 64) s_best[tid] = ~0ull;
+    __shared__ double s_qt[PF ? 384 : 1];                                     // PF: fl(1/t) [192] and t [192] of the three tables
+    bool chroma_twice = false;
+    if (PF) {
+        if (tid < 192) {
+            const double t = load_table_elem(a.table, a.table_dtype, tid);
+            s_qt[192 + tid] = t;
+            s_qt[tid] = __drcp_rn(t);
+        }
+        bool same = true;                                                     // [lum, chrom, chrom]: the third copy IS the second
+        if (tid < 64)
+            same = __double_as_longlong(load_table_elem(a.table, a.table_dtype, 64 + tid)) ==
+                   __double_as_longlong(load_table_elem(a.table, a.table_dtype, 128 + tid));
+        chroma_twice = __syncthreads_and(same) != 0;
+    }
     if (!me_int_prepare<T, PC, kStageUnroll>(a, tl, s_u, s_hs, s_b, s_cur, s_c2)) return;
 
     // ---- main loop ------------------------------------------------------------------------------
@@ -681,6 +805,17 @@ __global__ void __launch_bounds__(PC ? kMeIntMaxThreads : kMeThreads, PC ? 2 : 3
         const int blk = tid, brow = d_nbx.div(blk), b = blk - brow * tl.nbx;
         const int64_t idx = small ? (int64_t)(s_best32[blk] & 511u) : (int64_t)(s_best[blk] & 0xffffffffull);
         a.mv[(tl.frame * a.Hp + tl.by0 + brow) * (int64_t)a.Wp + tl.bx0 + b] = idx;
+    }
+    if (PF) {
+        // U and S are dead (every warp is past the barrier above): their space holds one WORK buffer per warp
+        const int warp = tid >> 5, nwarps = nthr >> 5;
+        const int gpr = (tl.nbx + 7) >> 3, ngroups = tl.nby * gpr;            // groups of eight blocks per block row
+        unsigned char *work_b = smem_raw + warp * kPfWork;
+        for (int grp = warp; grp < ngroups; grp += nwarps) {
+            const int brow = grp / gpr, b0 = 8 * (grp - brow * gpr);
+            pf_forward_group<PC>(a, tl, brow, b0, min(8, tl.nbx - b0), s_b, s_cur, s_best32, work_b, s_qt, s_qt + 192, chroma_twice);
+        }
+        bulk_wait_all0();
     }
 }
 
@@ -1054,12 +1189,15 @@ static size_t me_int_geometry(MeArgs &a, int G, int pitch, int64_t n_frames, int
     return smem;
 }
 
+bool me_pf_fusable(int dtype, int sr) { return sr == 4 && (dtype == IVC_F64 || dtype == IVC_U8); }
+
 cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const void *cur, int dtype, int64_t n,
                           int64_t H, int64_t W, int64_t ref_fs, int64_t cur_fs, int sr, int64_t *mv, int *flag,
-                          int check) {
+                          int check, const void *pf_table, int pf_table_dtype, int32_t *pf_zz, int pf_och) {
     const bool f32 = dtype == IVC_F32, u8 = dtype == IVC_U8;
     if (u8) check = 0;                                                        // uint8 planes are integer-valued by construction
     MeArgs a;
+    a.table = pf_table; a.table_dtype = pf_table_dtype; a.zz = pf_zz; a.och = pf_och;
     a.ref = ref; a.cur = cur; a.n = n; a.H = H; a.W = W; a.ref_fs = ref_fs; a.cur_fs = cur_fs; a.mv = mv;
     a.flag = flag; a.run_if = 0; a.check = check;
     if (sr == kMmaSr && me_mma_enabled()) {
@@ -1105,6 +1243,13 @@ cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const vo
             const double waste = (double)((tasks + t - 1) / t) * t / tasks;
             if (waste < best - 1e-9) { best = waste; threads = t; }
         }
+    }
+    if (pf_zz) {                                                               // fused search + P-frame forward: +-4, tile 4 x 16
+        if (!me_pf_fusable(dtype, sr) || G != 9 || pitch != 136) return cudaErrorInvalidValue;
+        const int groups = a.tby * ((a.tbx + 7) / 8);                          // one warp-private WORK buffer per group, in U + S
+        if (groups > kMePfThreads / 32 || (size_t)groups * kPfWork > (size_t)a.b_off) return cudaErrorInvalidValue;
+        return u8 ? me_launch_chunks(k_me_int<unsigned char, 9, 136, true>, a, 1, smem, st, kMePfThreads)
+                  : me_launch_chunks(k_me_int<double, 9, 136, true>, a, 8, smem, st, kMePfThreads);
     }
 #define IVC_ME_INT_CASE(GG, PP)                                                                  \
     if (G == GG && pitch == PP)                                                                  \

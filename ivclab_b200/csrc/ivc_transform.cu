@@ -22,6 +22,7 @@
 #include "ivc_dct.cuh"
 #include "ivc_color.cuh"
 #include "ivc_common.cuh"
+#include "ivc_tile.cuh"
 
 namespace ivc {
 
@@ -34,8 +35,6 @@ constexpr int kRowPitch = 98;        // 96 doubles of tile row + 2 pad: 784 B ==
 constexpr int kTJ = 10;              // transposition buffer: T[u][m*8+j][r], 80-byte rows
 constexpr int kTU = 248;             // 24 rows * 10 + 8 pad: u-planes land 64 B apart (mod 128)
 constexpr int kStageU = 200;         // int32 staging: 3 chunks * 64 ints + 8 pad per u
-constexpr int kStageUF = 204;        // ... of the TMA forward kernels: +12 puts the zig-zag SCATTER of a warp on 16 instead of 20
-                                     // bank wavefronts per 8 stores (the inverse kernels' GATHER is best at +8)
 
 static_assert(8 * kRowPitch * 8 <= kWarpBufBytes, "row tile must fit");
 static_assert(4 * kTU * 8 <= kWarpBufBytes, "transposition buffer must fit");
@@ -76,13 +75,6 @@ __device__ __forceinline__ void stg_stream(int4 *p, int4 v) {
                  : "memory");
 }
 
-// quantiser tables in shared memory, one copy per CTA:
-//   fwd: rt[ch*64+k] = fl(1/t), t[ch*64+k]                    (raster k = 8v + j)
-//   inv: tT[ch*64 + j*8 + r] = t[ch][8r + j]                  (transposed so lanes r are contiguous)
-__device__ __forceinline__ double load_table_elem(const void *table, int table_dtype, int i) {
-    return table_dtype == IVC_F32 ? (double)((const float *)table)[i] : ((const double *)table)[i];
-}
-
 // decode a motion-vector index (motion.py:83-84) and test the source window (motion.py:90-92)
 __device__ __forceinline__ void mv_decode(int64_t idx, int sr, int &dy, int &dx) {
     const unsigned span = 2u * (unsigned)sr + 1u;
@@ -117,10 +109,12 @@ struct FwdArgs {
     int sr;
     double *pred_out;                // may be null
     int och;                         // P-frame: scan channels stored per block (3 = the reference's broadcast; 2 = tables 0 and 1 only)
+    const int *run_flag;             // P-frame: when not null the kernel runs only if *run_flag != 0 (fallback after the fused search)
 };
 
 template <int C, bool PFRAME>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward(const FwdArgs a) {
+    if (PFRAME && a.run_flag && *a.run_flag == 0) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_rt = reinterpret_cast<double *>(smem_raw);            // [3*64]
     double *s_t = s_rt + 192;                                        // [3*64]
@@ -492,34 +486,6 @@ constexpr int kTU2 = 200;                        // doubles per u-plane: 24 rows
 static_assert(kWarpBuf2 % 128 == 0, "per-warp buffers stay 128-byte aligned");
 static_assert(8 * kRowPitch * 8 <= kWorkBytes, "the output row tile reuses WORK");
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (uint32_t spin = 0; !done; ++spin) {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (spin > (1u << 24)) __trap();          // a lost copy must not hang the GPU
-    }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
 // tile iterator: (frame, block row, tile column) advanced by a fixed stride without divisions
 struct TileIter {
     int tx, by, dtx, dby;
@@ -543,21 +509,6 @@ struct TileIter {
         by -= c ? g.Hp : 0;
         frame += dframe + c;
     }
-};
-
-// branch-free quantiser: always produces the fast-path integer and folds "this sample needs the
-// exact division" into two running values (see quantize_f64 in ivc_dct.cuh for the argument).
-struct QuantGuard {
-    int mx = 0;                      // max of |y| high words
-    unsigned nz = 0xffffffffu;       // min of (frac16 ^ 0x8000): 0 <=> some sample sits exactly on a half
-    __device__ __forceinline__ int q(double x, double rt) {
-        const double y = __dmul_rn(x, rt);
-        const int lo = __double2loint(__dadd_rn(y, 103079215104.0));         // 1.5 * 2^36
-        mx = max(mx, __double2hiint(y) & 0x7fffffff);
-        nz = min(nz, (unsigned)((lo & 0xFFFF) ^ 0x8000));
-        return (lo + 0x8000) >> 16;
-    }
-    __device__ __forceinline__ bool risky() const { return (mx >= 0x40DFFFC0) | (nz == 0u); }   // |y| >= 2^15 - 1 (the rounding add would wrap at 32767.5), NaN, tie
 };
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_c3_tma(const FwdArgs a) {
@@ -1096,6 +1047,7 @@ struct PredGather {
 };
 
 __global__ void __launch_bounds__(kPfWarps * 32, 1) k_pframe_forward_tma(const FwdArgs a) {
+    if (a.run_flag && *a.run_flag == 0) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_rt = reinterpret_cast<double *>(smem_raw);                       // [192]
     double *s_t = s_rt + 192;                                                   // [192]
@@ -1434,7 +1386,6 @@ constexpr int kP3Pitch = 528;                         // bytes per IN row: 8 blo
 constexpr int kP3Box = 640;                           // one 10 x 8 box of doubles (80-byte rows)
 constexpr int kP3Pred = kP3Blocks * kP3Box;           // 5120: block-major boxes
 constexpr int kP3In = 8 * kP3Pitch;                   // 4224
-constexpr int kP3TU = 136;                            // doubles per u-plane: 16 rows * 8 + 8 skew (64 B)
 constexpr int kP3Trans = 4 * kP3TU * 8;               // 4352
 constexpr int kP3Region = 4 * kStageUF * 4;           // 3264: one round of scan staging (4 blocks x 3 tables)
 constexpr int kP3Header = 3584;                       // tables + barriers (a multiple of 128)
@@ -1490,6 +1441,7 @@ __device__ __forceinline__ void p3_gather(const CUtensorMap *tm, uint32_t pred_s
 
 template <int WARPS, int CTAS>
 __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pframe_forward_tm(const FwdArgs a, const __grid_constant__ CUtensorMap tm_ref) {
+    if (a.run_flag && *a.run_flag == 0) return;
     constexpr int kBuf = kP3FwdBuf;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_rt = reinterpret_cast<double *>(smem_raw);                       // [192]
@@ -2016,9 +1968,11 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
 
 cudaError_t launch_forward(int device, cudaStream_t st, const void *img, int64_t n, int64_t H, int64_t W, int C,
                            int64_t frame_stride, const void *table, int table_dtype, int32_t *out,
-                           const void *ref, const int64_t *mv, int sr, void *pred_out, bool pframe, int out_channels) {
+                           const void *ref, const int64_t *mv, int sr, void *pred_out, bool pframe, int out_channels,
+                           const int *run_flag) {
     FwdArgs a;
     a.och = pframe ? out_channels : 3;
+    a.run_flag = pframe ? run_flag : nullptr;
     a.g = make_geom(n, H, W, C, C == 3 ? 4 : 12);
     a.img = (const double *)img; a.frame_stride = frame_stride; a.table = table; a.table_dtype = table_dtype;
     a.out = out; a.ref = (const double *)ref; a.mv = mv; a.sr = sr; a.pred_out = (double *)pred_out;
@@ -2058,7 +2012,7 @@ cudaError_t launch_forward_rgb8(int device, cudaStream_t st, const void *rgb, in
     FwdArgs a;
     a.g = make_geom(n, H, W, 3, 4);
     a.img = (const double *)rgb; a.frame_stride = frame_stride_bytes; a.table = table; a.table_dtype = table_dtype;
-    a.out = out; a.ref = nullptr; a.mv = nullptr; a.sr = 0; a.pred_out = nullptr; a.och = 3;
+    a.out = out; a.ref = nullptr; a.mv = nullptr; a.sr = 0; a.pred_out = nullptr; a.och = 3; a.run_flag = nullptr;
     if (a.g.total_tiles == 0) return cudaSuccess;
     const size_t smem = 3200 + (size_t)kWarpsPerCta * kRgbBuf;
     cudaError_t e;

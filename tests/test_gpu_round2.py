@@ -414,3 +414,61 @@ def test_abi_call_leaves_current_device_alone():
     ivc.IntraBlockCoder(1.0).forward(x)
     assert torch.cuda.current_device() == 0
     assert torch.zeros(1, device="cuda").device.index == 0
+
+
+# ---------------------------------------------------------------- fused search + P-frame forward
+@pytest.mark.parametrize("mode", ["auto", "int", "exact"])
+def test_fused_search_forward_equals_the_two_kernels(mode):
+    """ivc_pframe_search_forward: one kernel (integer frames, +-4) or the stand-alone pair -- identical vectors and
+    indices, every tile shape (small frames get small tiles), ragged edges, batches, 2- and 3-channel output."""
+    for (n, H, W, seed) in ((1, 8, 8, 1), (1, 48, 64, 2), (3, 72, 136, 3), (2, 144, 176, 4), (1, 264, 1032, 5), (5, 200, 328, 6)):
+        seq = O.moving_sequence(300 + seed, n + 1, H, W)
+        ref, cur = seq[:-1], seq[1:]
+        pc = ivc.PFrameBlockCoder(0.4, 4, me_mode=mode)
+        mv_want = pc.estimate(ref, cur)
+        for ch in (3, 2):
+            mv, zz = pc.estimate_forward(ref, cur, channels=ch)
+            assert np.array_equal(mv, mv_want), (n, H, W, ch)
+            assert np.array_equal(zz, pc.forward(cur, ref, mv_want, channels=ch)), (n, H, W, ch)
+        tab = O.quant_table(0.4)
+        for i in range(n):                                                     # and against the oracle
+            assert np.array_equal(mv[i], O.me_full_search(ref[i], cur[i], 4))
+            _, zo = O.pframe_forward(cur[i], ref[i], mv[i], 4, tab)
+            assert np.array_equal(zz[i], zo[:, :, :2])
+    # non-integer frames: 'auto' falls back on the device (the fused kernel raises the flag, the pair runs)
+    if mode != "int":
+        rng = np.random.default_rng(9)
+        seq = O.moving_sequence(77, 3, 72, 136) + rng.normal(0, 0.3, (3, 72, 136))
+        pc = ivc.PFrameBlockCoder(1.0, 4, me_mode=mode)
+        mv, zz = pc.estimate_forward(seq[:-1], seq[1:])
+        for i in range(2):
+            assert np.array_equal(mv[i], O.me_full_search(seq[i], seq[i + 1], 4))
+            assert np.array_equal(zz[i], O.pframe_forward(seq[i + 1], seq[i], mv[i], 4, O.quant_table(1.0))[1])
+    # other search ranges take the pair; flat frames (all ties) and frame edges
+    for sr in (2, 7, 16):
+        seq = O.moving_sequence(80 + sr, 2, 64, 96)
+        pc = ivc.PFrameBlockCoder(1.0, sr, me_mode=mode)
+        mv, zz = pc.estimate_forward(seq[0], seq[1])
+        assert np.array_equal(mv, O.me_full_search(seq[0], seq[1], sr))
+        assert np.array_equal(zz, O.pframe_forward(seq[1], seq[0], mv, sr, O.quant_table(1.0))[1])
+    flat = np.full((2, 40, 56), 255.0)
+    mv, zz = ivc.PFrameBlockCoder(1.0, 4, me_mode=mode).estimate_forward(flat[0], flat[1])
+    assert np.array_equal(mv, O.me_full_search(flat[0], flat[1], 4)) and not zz.any()
+
+
+def test_fused_search_forward_1080p_batch_custom_tables():
+    """full-size frames through the fused kernel, float64 quantisation table (np.float64 scale) and distinct chrominance
+    tables (no channel-2 shortcut)"""
+    seq = O.moving_sequence(5000, 3, 1080, 1920)
+    d = torch.from_numpy(seq).cuda()
+    for kw in ({"quantization_scale": np.float64(0.4)}, {"quantization_scale": 1.0, "chrominance": np.arange(1, 65, dtype=np.float32).reshape(8, 8)}):
+        pc = ivc.PFrameBlockCoder(search_range=4, **kw)
+        mv, zz = pc.estimate_forward(d[:-1], d[1:])
+        mv2 = pc.estimate(d[:-1], d[1:])
+        assert torch.equal(mv, mv2) and torch.equal(zz, pc.forward(d[1:], d[:-1], mv2))
+    tab = O.quant_table(1.0)
+    mv, zz = ivc.PFrameBlockCoder(1.0, 4).estimate_forward(d[:1], d[1:2])
+    mvo = CO.me_full_search(seq[0], seq[1], 4, threads=8)
+    assert np.array_equal(mv[0].cpu().numpy(), mvo)
+    pred = CO.mc_reconstruct(seq[0][..., None], mvo, 4)[..., 0]
+    assert np.array_equal(zz[0].cpu().numpy(), CO.intra_forward(seq[1] - pred, tab, threads=8))

@@ -48,6 +48,12 @@ def main():
         pc = ivc.PFrameBlockCoder(1.0, 4, me_mode=mode)
         t = timed(lambda: pc.estimate(s[:-1], s[1:]), 10)
         print(f"1080p x32 sr=4 {mode}: {t:.3f} ms  {32 * 1080 * 1920 / t / 1e3:.0f} Mpixel/s")
+    for mode in ("int", "auto"):                                   # search + P-frame forward: two kernels vs the fused one
+        pc = ivc.PFrameBlockCoder(1.0, 4, me_mode=mode)
+        t2 = timed(lambda: pc.forward(s[1:], s[:-1], pc.estimate(s[:-1], s[1:])), 10)
+        t1 = timed(lambda: pc.estimate_forward(s[:-1], s[1:]), 10)
+        t1c = timed(lambda: pc.estimate_forward(s[:-1], s[1:], channels=2), 10)
+        print(f"1080p x32 sr=4 {mode}: estimate + forward {t2:.3f} ms, fused {t1:.3f} ms, fused 2-channel {t1c:.3f} ms")
     pc = ivc.PFrameBlockCoder(1.0, 4, me_mode="auto")
     t = timed(lambda: pc.estimate(s[:1], s[1:2]), 20)
     print(f"1080p x1 sr=4 auto: {t * 1e3:.1f} us")
