@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define IVC_ABI_VERSION 5
+#define IVC_ABI_VERSION 6
 
 /* element types */
 #define IVC_U8   0
@@ -196,12 +196,25 @@ int ivc_pframe_forward_ch(int device, void *stream,
  * staged, so the frames are read once (16 B/pixel instead of 16 + 16).  In IVC_ME_AUTO mode that kernel validates the
  * frames and otherwise leaves everything to the exact search and the stand-alone forward kernel, which are enqueued
  * behind it and run only if it raised the device flag (workspace as for ivc_me_full_search).  Other search ranges,
- * IVC_ME_EXACT: the two stand-alone kernels.  Results are identical in every case. */
+ * IVC_ME_EXACT: the two stand-alone kernels.  Results are identical in every case.
+ * dtype IVC_U8: cur/ref are uint8 PLANES holding the frames' values (no alignment requirement, no workspace); served by
+ * the fused kernel only, i.e. for search_range 4 -- IVC_ERR_DTYPE otherwise. */
 int ivc_pframe_search_forward(int device, void *stream,
                               const void *cur, const void *ref, int dtype,
                               int64_t n_frames, int64_t H, int64_t W, int search_range, int mode,
                               const void *table, int table_dtype, int out_channels,
                               int64_t *mv_out, int32_t *zz_out, void *workspace, int64_t workspace_bytes);
+
+/* The same, and the zero-run coder's count pass with it: counts_out[b] (int32) = the symbols ZeroRunCoder.encode emits for
+ * scan block b of zz_out (in its (h w c) order), masks_out[b] (uint64) = the block's non-zero mask -- exactly what
+ * ivc_zerorun_count_masks would compute from zz_out, taken while the block is still in shared memory, so a pipeline goes
+ * straight on to ivc_zerorun_offsets / ivc_zerorun_write_masks without re-reading the indices. */
+int ivc_pframe_search_forward_zr(int device, void *stream,
+                                 const void *cur, const void *ref, int dtype,
+                                 int64_t n_frames, int64_t H, int64_t W, int search_range, int mode,
+                                 const void *table, int table_dtype, int out_channels,
+                                 int64_t *mv_out, int32_t *zz_out, void *workspace, int64_t workspace_bytes,
+                                 int32_t *counts_out, uint64_t *masks_out);
 
 /* ---- a15 fused: P-frame decoder half (intracodec.py:115-124 + videocodec.py:74) --------------
  * recon = pred + idct(dequantize(unflatten(zz[..., 0, :])))[channel 0]  (luminance table).
@@ -319,6 +332,11 @@ int ivc_rgb8_to_luma8(int device, void *stream, const void *rgb, int64_t npixels
 int ivc_intra_forward_rgb8(int device, void *stream,
                            const void *rgb, int64_t n_frames, int64_t H, int64_t W, int64_t frame_stride_bytes,
                            const void *table, int table_dtype, int32_t *out);
+/* ... with the zero-run coder's count pass folded in (see ivc_pframe_search_forward_zr): counts_out / masks_out have
+ * n_frames * (H/8) * (W/8) * 3 entries. */
+int ivc_intra_forward_rgb8_zr(int device, void *stream, const void *rgb, int64_t n_frames, int64_t H, int64_t W,
+                              int64_t frame_stride_bytes, const void *table, int table_dtype, int32_t *out,
+                              int32_t *counts_out, uint64_t *masks_out);
 
 #ifdef __cplusplus
 }

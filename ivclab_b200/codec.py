@@ -46,10 +46,13 @@ class IntraBlockCoder:
         _lib.check(st, "ivc_intra_forward")
         return to_host(out if batched else out[0], was_np)
 
-    def forward_rgb(self, rgb):
+    def forward_rgb(self, rgb, zr=False):
         """uint8 RGB ``[H, W, 3]`` / ``[N, H, W, 3]`` -> the scan indices of ``forward(rgb2ycbcr(rgb))``
         (intracodec.py:45 + :66-75) in one kernel that reads 3 bytes per pixel.  Frames whose width is
-        not a multiple of 16 take the two-kernel route (colour kernel, then ``forward``)."""
+        not a multiple of 16 take the two-kernel route (colour kernel, then ``forward``).
+        ``zr=True`` (CUDA tensors, W % 16 == 0): returns ``(zz, counts, masks)`` -- per scan block the number of
+        symbols ``ZeroRunCoder.encode`` emits for it and its 64-bit non-zero mask, taken while the block is still in
+        shared memory; ``ZeroRunCoder.encode_begin(zz, counts=counts, masks=masks)`` then skips its count pass."""
         t, was_np = to_device(rgb)
         batched = t.ndim == 4
         if t.ndim not in (3, 4) or t.shape[-1] != 3:
@@ -57,12 +60,25 @@ class IntraBlockCoder:
         v = t if batched else t[None]
         N, H, W, _ = v.shape
         if v.dtype != torch.uint8 or W % 16:
+            if zr:
+                raise ValueError("zr=True needs uint8 frames whose width is a multiple of 16")
             from .signal.color import rgb2ycbcr
             out = self.forward(rgb2ycbcr(v))
             return to_host(out if batched else out[0], was_np)
         v = aligned16(v)
         _, dtab = self.quant._table_on(v.device)
         out = torch.empty((N, H // 8, W // 8, 3, 64), dtype=torch.int32, device=v.device)
+        if zr:
+            if was_np:
+                raise ValueError("zr=True is the device-resident pipeline's form: pass CUDA tensors")
+            nsb = out.numel() // 64
+            counts = torch.empty(nsb, dtype=torch.int32, device=v.device)
+            masks = torch.empty(nsb, dtype=torch.int64, device=v.device)
+            st = _lib.lib.ivc_intra_forward_rgb8_zr(dev_index(v), stream_ptr(v.device), v.data_ptr(), N, H, W, H * W * 3,
+                                                    dtab.data_ptr(), code(dtab.dtype), out.data_ptr(), counts.data_ptr(),
+                                                    masks.data_ptr())
+            _lib.check(st, "ivc_intra_forward_rgb8_zr")
+            return (out if batched else out[0]), counts, masks
         st = _lib.lib.ivc_intra_forward_rgb8(dev_index(v), stream_ptr(v.device), v.data_ptr(), N, H, W, H * W * 3,
                                              dtab.data_ptr(), code(dtab.dtype), out.data_ptr())
         _lib.check(st, "ivc_intra_forward_rgb8")
@@ -173,18 +189,25 @@ class PFrameBlockCoder:
         _lib.check(st, "ivc_me_full_search")
         return to_host(mv if batched else mv[0], was_np)
 
-    def estimate_forward(self, ref, cur, channels=3):
+    def estimate_forward(self, ref, cur, channels=3, zr=False):
         """Search and encoder half in one call: ``mv = estimate(ref, cur)`` and ``zz = forward(cur, ref, mv)``
         (videocodec.py:52 + :68-71) -> ``(mv [(N,) Hp, Wp, 1] int64, zz [(N,) Hp, Wp, channels, 64] int32)``.
         For +-4 searches of integer-valued float64 frames a single kernel does both -- its tiles code their blocks
         from the bytes the search staged, so the frames are read once; every other case (other search ranges,
         non-integer frames -- detected on the device in ``me_mode='auto'`` --, ``me_mode='exact'``) runs the two
-        stand-alone kernels.  Same results either way."""
+        stand-alone kernels.  Same results either way.  uint8 planes (the frames' values) are taken as they are when the
+        fused kernel applies.  ``zr=True`` (CUDA tensors): returns ``(mv, zz, counts, masks)`` with the zero-run coder's
+        per-block symbol counts and non-zero masks (see :meth:`IntraBlockCoder.forward_rgb`)."""
         r, was_np = to_device(ref)
         c, _ = to_device(cur, r.device)
         batched = r.ndim == 3
-        r = aligned16(r.to(torch.float64))
-        c = aligned16(c.to(torch.float64))
+        # uint8 planes (the frames' values) stay bytes where the fused kernel can take them: nothing is converted
+        u8 = r.dtype == torch.uint8 and c.dtype == torch.uint8 and int(self.search_range) == 4 and self.motion_comp.me_mode != "exact"
+        if u8:
+            r, c = r.contiguous(), c.contiguous()
+        else:
+            r = aligned16(r.to(torch.float64))
+            c = aligned16(c.to(torch.float64))
         rv, cv = (r, c) if batched else (r[None], c[None])
         N, H, W = rv.shape
         if H % 8 or W % 8:
@@ -197,9 +220,18 @@ class PFrameBlockCoder:
         mode = {"auto": _lib.ME_AUTO, "exact": _lib.ME_EXACT, "int": _lib.ME_INT}[self.motion_comp.me_mode]
         ws_bytes = _lib.lib.ivc_me_workspace_bytes(N, H, W)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=r.device)
-        st = _lib.lib.ivc_pframe_search_forward(dev_index(rv), stream_ptr(rv.device), cv.data_ptr(), rv.data_ptr(), _lib.F64,
-                                                N, H, W, int(self.search_range), mode, dtab.data_ptr(), code(dtab.dtype),
-                                                channels, mv.data_ptr(), zz.data_ptr(), ws.data_ptr(), ws_bytes)
+        args = (dev_index(rv), stream_ptr(rv.device), cv.data_ptr(), rv.data_ptr(), _lib.U8 if u8 else _lib.F64, N, H, W,
+                int(self.search_range), mode, dtab.data_ptr(), code(dtab.dtype), channels, mv.data_ptr(), zz.data_ptr(),
+                ws.data_ptr(), ws_bytes)
+        if zr:
+            if was_np:
+                raise ValueError("zr=True is the device-resident pipeline's form: pass CUDA tensors")
+            nsb = zz.numel() // 64
+            counts = torch.empty(nsb, dtype=torch.int32, device=r.device)
+            masks = torch.empty(nsb, dtype=torch.int64, device=r.device)
+            _lib.check(_lib.lib.ivc_pframe_search_forward_zr(*args, counts.data_ptr(), masks.data_ptr()), "ivc_pframe_search_forward_zr")
+            return (mv, zz, counts, masks) if batched else (mv[0], zz[0], counts, masks)
+        st = _lib.lib.ivc_pframe_search_forward(*args)
         _lib.check(st, "ivc_pframe_search_forward")
         if not batched:
             mv, zz = mv[0], zz[0]

@@ -289,40 +289,79 @@ int ivc_pframe_forward_ch(int device, void *stream, const void *cur, const void 
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
 
+static int search_forward_impl(int device, void *stream, const void *cur, const void *ref, int dtype, int64_t n_frames,
+                               int64_t H, int64_t W, int search_range, int mode, const void *table, int table_dtype,
+                               int out_channels, int64_t *mv_out, int32_t *zz_out, void *workspace, int64_t workspace_bytes,
+                               int32_t *zr_counts, uint64_t *zr_masks);
+
 int ivc_pframe_search_forward(int device, void *stream, const void *cur, const void *ref, int dtype, int64_t n_frames,
                               int64_t H, int64_t W, int search_range, int mode, const void *table, int table_dtype,
                               int out_channels, int64_t *mv_out, int32_t *zz_out, void *workspace, int64_t workspace_bytes) {
+    return search_forward_impl(device, stream, cur, ref, dtype, n_frames, H, W, search_range, mode, table, table_dtype,
+                               out_channels, mv_out, zz_out, workspace, workspace_bytes, nullptr, nullptr);
+}
+
+int ivc_pframe_search_forward_zr(int device, void *stream, const void *cur, const void *ref, int dtype, int64_t n_frames,
+                                 int64_t H, int64_t W, int search_range, int mode, const void *table, int table_dtype,
+                                 int out_channels, int64_t *mv_out, int32_t *zz_out, void *workspace, int64_t workspace_bytes,
+                                 int32_t *counts_out, uint64_t *masks_out) {
+    if (!counts_out || !masks_out) return IVC_ERR_ARG;
+    return search_forward_impl(device, stream, cur, ref, dtype, n_frames, H, W, search_range, mode, table, table_dtype,
+                               out_channels, mv_out, zz_out, workspace, workspace_bytes, counts_out, masks_out);
+}
+
+static int search_forward_impl(int device, void *stream, const void *cur, const void *ref, int dtype, int64_t n_frames,
+                               int64_t H, int64_t W, int search_range, int mode, const void *table, int table_dtype,
+                               int out_channels, int64_t *mv_out, int32_t *zz_out, void *workspace, int64_t workspace_bytes,
+                               int32_t *zr_counts, uint64_t *zr_masks) {
     if (n_frames < 0 || H < 0 || W < 0 || search_range < 0 || search_range > 64) return IVC_ERR_ARG;
     if (out_channels != 2 && out_channels != 3) return IVC_ERR_ARG;
     if (mode != IVC_ME_AUTO && mode != IVC_ME_EXACT && mode != IVC_ME_INT) return IVC_ERR_ARG;
-    if (dtype != IVC_F64 || !is_float(table_dtype)) return IVC_ERR_DTYPE;
+    if ((dtype != IVC_F64 && dtype != IVC_U8) || !is_float(table_dtype)) return IVC_ERR_DTYPE;
+    // uint8 PLANES (the frames' values, as in ivc_me_full_search): always integer-valued, so there is nothing to fall
+    // back to -- and nothing to fall back ON: only the fused kernel reads them
+    if (dtype == IVC_U8 && !ivc::me_pf_fusable(dtype, search_range)) return IVC_ERR_DTYPE;
     if ((H & 7) || (W & 7)) return IVC_ERR_SHAPE;
     if (n_frames * H * W == 0) return IVC_OK;
     if (!cur || !ref || !table || !mv_out || !zz_out) return IVC_ERR_ARG;
-    if (!aligned16(cur) || !aligned16(zz_out)) return IVC_ERR_ARG;
-    if (mode == IVC_ME_AUTO && (!workspace || workspace_bytes < ivc_me_workspace_bytes(n_frames, H, W))) return IVC_ERR_WORKSPACE;
+    if ((dtype == IVC_F64 && !aligned16(cur)) || !aligned16(zz_out)) return IVC_ERR_ARG;
+    if (dtype == IVC_F64 && mode == IVC_ME_AUTO && (!workspace || workspace_bytes < ivc_me_workspace_bytes(n_frames, H, W)))
+        return IVC_ERR_WORKSPACE;
     IVC_ENTER(device);
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
+    const int64_t n_scan = n_frames * (H / 8) * (W / 8) * out_channels;           // scan blocks of zz_out
+    if (dtype == IVC_U8) {
+        e = ivc::launch_me_int(device, st, ref, cur, dtype, n_frames, H, W, H * W, H * W, search_range, mv_out, nullptr, 0,
+                               table, table_dtype, zz_out, out_channels, zr_counts, zr_masks);
+        return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+    }
     if (mode != IVC_ME_EXACT && ivc::me_pf_fusable(dtype, search_range)) {
         // one kernel searches and codes; in AUTO mode it leaves non-integer frames to the two stand-alone kernels, which
         // run only if it raised the flag (no host round trip)
         int *flag = mode == IVC_ME_AUTO ? (int *)workspace : nullptr;
         e = ivc::launch_me_int(device, st, ref, cur, dtype, n_frames, H, W, H * W, H * W, search_range, mv_out, flag,
-                               mode == IVC_ME_AUTO ? 1 : 0, table, table_dtype, zz_out, out_channels);
+                               mode == IVC_ME_AUTO ? 1 : 0, table, table_dtype, zz_out, out_channels, zr_counts, zr_masks);
         if (e != cudaSuccess) return cuda_fail(e);
         if (mode == IVC_ME_INT) return IVC_OK;
         e = ivc::launch_me_exact(device, st, ref, cur, false, n_frames, H, W, H * W, H * W, search_range, mv_out, flag, 1);
         if (e != cudaSuccess) return cuda_fail(e);
+        bool zr_done = false;
         e = ivc::launch_forward(device, st, cur, n_frames, H, W, 1, H * W, table, table_dtype, zz_out, ref, mv_out,
-                                search_range, nullptr, true, out_channels, flag);
+                                search_range, nullptr, true, out_channels, flag, zr_counts, zr_masks, &zr_done);
+        if (e == cudaSuccess && zr_counts && !zr_done)                           // the kernel variant that ran cannot emit them
+            e = ivc::launch_zr_count(device, st, zz_out, n_scan, zr_counts, zr_masks, flag);
         return e == cudaSuccess ? IVC_OK : cuda_fail(e);
     }
     int rc = ivc_me_full_search(device, stream, ref, cur, dtype, n_frames, H, W, H * W, H * W, search_range, mode, mv_out,
                                 workspace, workspace_bytes);
     if (rc != IVC_OK) return rc;
-    return ivc_pframe_forward_ch(device, stream, cur, ref, mv_out, dtype, n_frames, H, W, search_range, table, table_dtype,
-                                 nullptr, out_channels, zz_out);
+    if (!aligned16(cur)) return IVC_ERR_ARG;
+    bool zr_done = false;
+    e = ivc::launch_forward(device, st, cur, n_frames, H, W, 1, H * W, table, table_dtype, zz_out, ref, mv_out, search_range,
+                            nullptr, true, out_channels, nullptr, zr_counts, zr_masks, &zr_done);
+    if (e == cudaSuccess && zr_counts && !zr_done) e = ivc::launch_zr_count(device, st, zz_out, n_scan, zr_counts, zr_masks);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
 
 int ivc_pframe_inverse(int device, void *stream, const int32_t *zz, int64_t Czz, const void *pred, const void *ref,
@@ -541,6 +580,21 @@ int ivc_intra_forward_rgb8(int device, void *stream, const void *rgb, int64_t n_
     IVC_ENTER(device);
     cudaError_t e = ivc::launch_forward_rgb8(device, (cudaStream_t)stream, rgb, n_frames, H, W, frame_stride_bytes, table,
                                              table_dtype, out);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
+int ivc_intra_forward_rgb8_zr(int device, void *stream, const void *rgb, int64_t n_frames, int64_t H, int64_t W,
+                              int64_t frame_stride_bytes, const void *table, int table_dtype, int32_t *out,
+                              int32_t *counts_out, uint64_t *masks_out) {
+    if (n_frames < 0 || H < 0 || W < 0 || frame_stride_bytes < 0) return IVC_ERR_ARG;
+    if (!is_float(table_dtype)) return IVC_ERR_DTYPE;
+    if ((H & 7) || (W & 15)) return IVC_ERR_SHAPE;
+    if (n_frames * H * W == 0) return IVC_OK;
+    if (!rgb || !table || !out || !counts_out || !masks_out) return IVC_ERR_ARG;
+    if (!aligned16(rgb) || !aligned16(out) || (frame_stride_bytes & 15)) return IVC_ERR_ARG;
+    IVC_ENTER(device);
+    cudaError_t e = ivc::launch_forward_rgb8(device, (cudaStream_t)stream, rgb, n_frames, H, W, frame_stride_bytes, table,
+                                             table_dtype, out, counts_out, masks_out);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
 

@@ -10,7 +10,10 @@ namespace ivc {
 cudaError_t launch_forward(int device, cudaStream_t st, const void *img, int64_t n, int64_t H, int64_t W, int C,
                            int64_t frame_stride, const void *table, int table_dtype, int32_t *out,
                            const void *ref, const int64_t *mv, int sr, void *pred_out, bool pframe, int out_channels = 3,
-                           const int *run_flag = nullptr);       // P-frame kernels: run only if *run_flag != 0 (null: always)
+                           const int *run_flag = nullptr,        // P-frame kernels: run only if *run_flag != 0 (null: always)
+                           int32_t *zr_counts = nullptr, uint64_t *zr_masks = nullptr, bool *zr_done = nullptr);
+                           // zr_*: per scan block the zero-run symbol count and non-zero mask, when the kernel variant that runs
+                           // can emit them (*zr_done says whether it did)
 cudaError_t launch_inverse(int device, cudaStream_t st, const int32_t *zz, int64_t n, int64_t Hp, int64_t Wp, int Czz,
                            const void *table, int table_dtype, void *out, int mode,
                            const void *pred, const void *ref, const int64_t *mv, int sr);
@@ -34,7 +37,7 @@ cudaError_t launch_me_exact(int device, cudaStream_t st, const void *ref, const 
 cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const void *cur, int dtype, int64_t n,
                           int64_t H, int64_t W, int64_t ref_fs, int64_t cur_fs, int sr, int64_t *mv, int *flag,
                           int check, const void *pf_table = nullptr, int pf_table_dtype = 0, int32_t *pf_zz = nullptr,
-                          int pf_och = 3);
+                          int pf_och = 3, int32_t *zr_counts = nullptr, uint64_t *zr_masks = nullptr);
 bool me_pf_fusable(int dtype, int sr);
 cudaError_t launch_me_wrap(int device, cudaStream_t st, const void *ref, const void *cur, int dtype, int64_t n, int64_t H,
                            int64_t W, int64_t ref_fs, int64_t cur_fs, int sr, int64_t *mv);
@@ -48,7 +51,7 @@ cudaError_t launch_sse(int device, cudaStream_t st, const void *a, int a_dtype, 
 
 // implemented in ivc_zerorun.cu
 cudaError_t launch_zr_count(int device, cudaStream_t st, const int32_t *zz, int64_t nblocks, int32_t *counts,
-                            uint64_t *masks);
+                            uint64_t *masks, const int *run_flag = nullptr);     // run_flag: run only if *run_flag != 0
 cudaError_t launch_zr_write(int device, cudaStream_t st, const int32_t *zz, int64_t nblocks, int32_t eob,
                             const int64_t *offsets, const uint64_t *masks, void *out, int out_elem_size,
                             int64_t total_symbols);
@@ -76,6 +79,7 @@ cudaError_t launch_minmax(int device, cudaStream_t st, const void *x, int dtype,
 cudaError_t launch_color(int device, cudaStream_t st, bool to_rgb, const void *in, int in_dtype, int64_t npix, double *out);
 cudaError_t launch_rgb8_luma8(int device, cudaStream_t st, const void *rgb, int64_t npix, void *out, void *out64);
 cudaError_t launch_forward_rgb8(int device, cudaStream_t st, const void *rgb, int64_t n, int64_t H, int64_t W,
-                                int64_t frame_stride_bytes, const void *table, int table_dtype, int32_t *out);
+                                int64_t frame_stride_bytes, const void *table, int table_dtype, int32_t *out,
+                                int32_t *zr_counts = nullptr, uint64_t *zr_masks = nullptr);
 
 }  // namespace ivc

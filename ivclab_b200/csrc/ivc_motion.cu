@@ -60,6 +60,8 @@ struct MeArgs {
     int table_dtype;
     int32_t *zz;
     int och;
+    int32_t *zr_counts;                    // optional: zero-run symbol count and non-zero mask per scan block (see ivc_tile.cuh)
+    unsigned long long *zr_masks;
 };
 
 template <typename T> struct Inf;
@@ -693,6 +695,16 @@ __device__ __forceinline__ void pf_forward_group(const MeArgs &a, const MeTile &
             bulk_s2g(a.zz + ((tl.frame * a.Hp + tl.by0 + brow) * (int64_t)a.Wp + tl.bx0 + b0 + lane + 4 * m) * (64 * a.och),
                      work_s + lane * (kStageUF * 4), 256u * (uint32_t)a.och);
         bulk_commit();                                    // every lane commits (possibly empty) groups: counts stay in step
+        if (a.zr_masks) {                                 // scan block j = 3 u + ch of this round (ch < och are stored)
+            unsigned long long mk;
+            zr_masks_from_staging<12>(work_b, [](int j) { return (j / 3) * (kStageUF * 4) + (j % 3) * 256; }, lane, mk);
+            const int u_ = lane / 3, ch_ = lane - 3 * u_;
+            if (lane < 12 && u_ + 4 * m < nb && ch_ < a.och) {
+                const int64_t sblk = ((tl.frame * a.Hp + tl.by0 + brow) * (int64_t)a.Wp + tl.bx0 + b0 + u_ + 4 * m) * a.och + ch_;
+                a.zr_masks[sblk] = mk;
+                a.zr_counts[sblk] = zr_block_count(mk);
+            }
+        }
     }
 }
 
@@ -1193,11 +1205,13 @@ bool me_pf_fusable(int dtype, int sr) { return sr == 4 && (dtype == IVC_F64 || d
 
 cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const void *cur, int dtype, int64_t n,
                           int64_t H, int64_t W, int64_t ref_fs, int64_t cur_fs, int sr, int64_t *mv, int *flag,
-                          int check, const void *pf_table, int pf_table_dtype, int32_t *pf_zz, int pf_och) {
+                          int check, const void *pf_table, int pf_table_dtype, int32_t *pf_zz, int pf_och,
+                          int32_t *zr_counts, uint64_t *zr_masks) {
     const bool f32 = dtype == IVC_F32, u8 = dtype == IVC_U8;
     if (u8) check = 0;                                                        // uint8 planes are integer-valued by construction
     MeArgs a;
     a.table = pf_table; a.table_dtype = pf_table_dtype; a.zz = pf_zz; a.och = pf_och;
+    a.zr_counts = zr_counts; a.zr_masks = (unsigned long long *)zr_masks;
     a.ref = ref; a.cur = cur; a.n = n; a.H = H; a.W = W; a.ref_fs = ref_fs; a.cur_fs = cur_fs; a.mv = mv;
     a.flag = flag; a.run_if = 0; a.check = check;
     if (sr == kMmaSr && me_mma_enabled()) {

@@ -62,4 +62,27 @@ struct QuantGuard {
     __device__ __forceinline__ bool risky() const { return (mx >= 0x40DFFFC0) | (nz == 0u); }   // |y| >= 2^15 - 1 (the rounding add would wrap at 32767.5), NaN, tie
 };
 
+// ---- zero-run coder arithmetic on a block's 64-bit "non-zero" mask (ivclab/entropy/zerorun.py:10-43) ----
+// S = the zero positions below the highest set bit that start a run; a block emits popc(m) + 2 popc(S) + 1 symbols.
+__device__ __forceinline__ unsigned long long zr_run_starts(unsigned long long m) {
+    const unsigned long long below_top = (2ull << (63 - __clzll((long long)m))) - 1ull;        // m != 0
+    return ~m & ((m << 1) | 1ull) & below_top;
+}
+__device__ __forceinline__ int zr_block_count(unsigned long long m) {
+    return m ? 1 + __popcll(m) + 2 * __popcll(zr_run_starts(m)) : 1;
+}
+// The masks and symbol counts of NB scan blocks that sit, 64 int32 each, in a warp's staging area (block j at
+// stage + off(j) bytes): two ballots per block, lane j keeps block j.  What the zero-run coder's count pass would
+// compute by re-reading the indices from HBM -- here they are still in shared memory.
+template <int NB, typename Off>
+__device__ __forceinline__ void zr_masks_from_staging(const unsigned char *stage, Off off, int lane, unsigned long long &mask_out) {
+    mask_out = 0ull;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        const int *sb = reinterpret_cast<const int *>(stage + off(j));
+        const unsigned lo = __ballot_sync(0xffffffffu, sb[lane] != 0), hi = __ballot_sync(0xffffffffu, sb[32 + lane] != 0);
+        if (lane == j) mask_out = (unsigned long long)lo | ((unsigned long long)hi << 32);
+    }
+}
+
 }  // namespace ivc

@@ -110,6 +110,8 @@ struct FwdArgs {
     double *pred_out;                // may be null
     int och;                         // P-frame: scan channels stored per block (3 = the reference's broadcast; 2 = tables 0 and 1 only)
     const int *run_flag;             // P-frame: when not null the kernel runs only if *run_flag != 0 (fallback after the fused search)
+    int32_t *zr_counts;              // optional (TMA forward kernels): per scan block, the symbols ZeroRunCoder.encode emits for it ...
+    unsigned long long *zr_masks;    // ... and its 64-bit non-zero mask: the zero-run coder's count pass, done while the block is in smem
 };
 
 template <int C, bool PFRAME>
@@ -640,6 +642,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_c3_tma(const F
                 bulk_s2g(outf, work_s + lane * (kStageUF * 4), 768u);
                 bulk_commit();
             }
+            if (a.zr_masks) {                             // scan block j = 3 u + m of the tile, in (h w c) order
+                unsigned long long mk;
+                zr_masks_from_staging<12>(work_b, [](int j) { return (j / 3) * (kStageUF * 4) + (j % 3) * 256; }, lane, mk);
+                if (lane < 3 * nb) {
+                    const int64_t sblk = ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0) * 3 + lane;
+                    a.zr_masks[sblk] = mk;
+                    a.zr_counts[sblk] = zr_block_count(mk);
+                }
+            }
         }
         cur = nxt;
     }
@@ -785,6 +796,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_rgb8_tma(const
                 int32_t *outf = a.out + ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0 + lane) * 192;
                 bulk_s2g(outf, work_s + lane * (kStageUF * 4), 768u);
                 bulk_commit();
+            }
+            if (a.zr_masks) {                             // scan block j = 3 u + m of the tile, in (h w c) order
+                unsigned long long mk;
+                zr_masks_from_staging<12>(work_b, [](int j) { return (j / 3) * (kStageUF * 4) + (j % 3) * 256; }, lane, mk);
+                if (lane < 3 * nb) {
+                    const int64_t sblk = ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0) * 3 + lane;
+                    a.zr_masks[sblk] = mk;
+                    a.zr_counts[sblk] = zr_block_count(mk);
+                }
             }
         }
         cur = nxt;
@@ -1602,6 +1622,16 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k_pframe_forward_tm(const Fw
                 bulk_s2g(a.out + ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0 + lane + 4 * m) * (64 * a.och),
                          work_s + lane * (kStageUF * 4), 256u * (uint32_t)a.och);
             bulk_commit();                                // every lane commits (possibly empty) groups: counts stay in step
+            if (a.zr_masks) {                             // scan block j = 3 u + ch of this round (ch < och are stored)
+                unsigned long long mk;
+                zr_masks_from_staging<12>(work_b, [](int j) { return (j / 3) * (kStageUF * 4) + (j % 3) * 256; }, lane, mk);
+                const int u_ = lane / 3, ch_ = lane - 3 * u_;
+                if (lane < 12 && u_ + 4 * m < nb && ch_ < a.och) {
+                    const int64_t sblk = ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0 + u_ + 4 * m) * a.och + ch_;
+                    a.zr_masks[sblk] = mk;
+                    a.zr_counts[sblk] = zr_block_count(mk);
+                }
+            }
         }
         cur = nxt;
         nxt = nx2;
@@ -1969,10 +1999,12 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
 cudaError_t launch_forward(int device, cudaStream_t st, const void *img, int64_t n, int64_t H, int64_t W, int C,
                            int64_t frame_stride, const void *table, int table_dtype, int32_t *out,
                            const void *ref, const int64_t *mv, int sr, void *pred_out, bool pframe, int out_channels,
-                           const int *run_flag) {
+                           const int *run_flag, int32_t *zr_counts, uint64_t *zr_masks, bool *zr_done) {
     FwdArgs a;
     a.och = pframe ? out_channels : 3;
     a.run_flag = pframe ? run_flag : nullptr;
+    a.zr_counts = nullptr; a.zr_masks = nullptr;                  // only the tensor-map P-frame kernel emits them
+    if (zr_done) *zr_done = false;
     a.g = make_geom(n, H, W, C, C == 3 ? 4 : 12);
     a.img = (const double *)img; a.frame_stride = frame_stride; a.table = table; a.table_dtype = table_dtype;
     a.out = out; a.ref = (const double *)ref; a.mv = mv; a.sr = sr; a.pred_out = (double *)pred_out;
@@ -1983,6 +2015,10 @@ cudaError_t launch_forward(int device, cudaStream_t st, const void *img, int64_t
     CUtensorMap tm_ref;
     if (pframe && !use_v1() && pframe_v3() && make_plane_map(&tm_ref, ref, n, H, W, H * W, 10)) {
         a.g = make_geom(n, H, W, 1, kP3Blocks);
+        if (zr_counts && zr_masks) {
+            a.zr_counts = zr_counts; a.zr_masks = (unsigned long long *)zr_masks;
+            if (zr_done) *zr_done = true;
+        }
         const size_t smem3 = kP3Header + (size_t)8 * kP3FwdBuf;
         if ((e = set_smem(k_pframe_forward_tm<8, 2>, smem3)) != cudaSuccess) return e;
         k_pframe_forward_tm<8, 2><<<grid_for(a.g.total_tiles, 8, device, 2), 8 * 32, smem3, st>>>(a, tm_ref);
@@ -2008,8 +2044,10 @@ cudaError_t launch_forward(int device, cudaStream_t st, const void *img, int64_t
 }
 
 cudaError_t launch_forward_rgb8(int device, cudaStream_t st, const void *rgb, int64_t n, int64_t H, int64_t W,
-                                int64_t frame_stride_bytes, const void *table, int table_dtype, int32_t *out) {
+                                int64_t frame_stride_bytes, const void *table, int table_dtype, int32_t *out,
+                                int32_t *zr_counts, uint64_t *zr_masks) {
     FwdArgs a;
+    a.zr_counts = zr_counts; a.zr_masks = (unsigned long long *)zr_masks;
     a.g = make_geom(n, H, W, 3, 4);
     a.img = (const double *)rgb; a.frame_stride = frame_stride_bytes; a.table = table; a.table_dtype = table_dtype;
     a.out = out; a.ref = nullptr; a.mv = nullptr; a.sr = 0; a.pred_out = nullptr; a.och = 3; a.run_flag = nullptr;

@@ -18,21 +18,20 @@
 // output counts, a warp scan, a scatter into a zeroed 64-entry row.  Streams the reference would reject
 // (or a zero run length) raise a flag instead of producing blocks.
 #include "ivc_common.cuh"
+#include "ivc_tile.cuh"
 
 namespace ivc {
 
 constexpr int kZrWarps = 8;
 constexpr int kZrBatch = 8;        // blocks whose loads are in flight per warp
 
-__device__ __forceinline__ unsigned long long zr_run_starts(unsigned long long m) {
-    const unsigned long long below_top = (2ull << (63 - __clzll((long long)m))) - 1ull;        // m != 0
-    return ~m & ((m << 1) | 1ull) & below_top;
-}
 
 // counts[b] = symbols of block b; masks[b] (optional) = its 64-bit non-zero mask, which lets the write pass skip
 // the parts of a block that hold no symbol (most of it, for typical quantised blocks)
 __global__ void __launch_bounds__(kZrWarps * 32) k_zr_count(const int32_t *__restrict__ zz, int64_t nblocks,
-                                                            int32_t *__restrict__ counts, unsigned long long *__restrict__ masks) {
+                                                            int32_t *__restrict__ counts, unsigned long long *__restrict__ masks,
+                                                            const int *run_flag) {
+    if (run_flag && *run_flag == 0) return;
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * kZrWarps + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * kZrWarps;
     for (int64_t blk0 = warp * 32; blk0 < nblocks; blk0 += nw * 32) {                 // 32 blocks per warp and round
@@ -412,10 +411,10 @@ static int zr_grid(int device, int64_t units, int per_cta) {
 }
 
 cudaError_t launch_zr_count(int device, cudaStream_t st, const int32_t *zz, int64_t nblocks, int32_t *counts,
-                            uint64_t *masks) {
+                            uint64_t *masks, const int *run_flag) {
     if (nblocks == 0) return cudaSuccess;
     k_zr_count<<<zr_grid(device, nblocks, 32 * kZrWarps), kZrWarps * 32, 0, st>>>(zz, nblocks, counts,
-                                                                                  (unsigned long long *)masks);
+                                                                                  (unsigned long long *)masks, run_flag);
     return cudaGetLastError();
 }
 

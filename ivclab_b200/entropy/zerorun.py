@@ -32,21 +32,28 @@ class ZeroRunCoder:
             raise ValueError(f"expected [h, w, c, 64] (or [n, h, w, c, 64]) scan blocks, got shape {tuple(t.shape)}")
         return aligned16(t.to(torch.int32)), was_np
 
-    def encode_begin(self, flat_patch_img, total_host=None, record=True) -> _PendingEncode:
+    def encode_begin(self, flat_patch_img, total_host=None, record=True, counts=None, masks=None) -> _PendingEncode:
         """First half of :meth:`encode` without a host synchronisation: counts the symbols of every block,
         scans them and starts an asynchronous copy of the stream length into pinned host memory.  Lets a
         pipeline enqueue further work before :meth:`encode_finish` waits for that one number.
         ``total_host``: a caller-owned pinned int64[1] to receive the length (nothing is allocated on the host
         then -- required inside CUDA-graph capture); ``record=False`` leaves the synchronisation to the caller
-        (who must have waited for this call's work before calling :meth:`encode_finish`)."""
+        (who must have waited for this call's work before calling :meth:`encode_finish`).  ``counts`` / ``masks``: the
+        per-block symbol counts (int32) and non-zero masks (int64) when the kernel that produced the blocks has
+        already emitted them (``forward_rgb(zr=True)``, ``estimate_forward(zr=True)``): the count pass is skipped."""
         t, _ = self._check(flat_patch_img)
         p = _PendingEncode()
         p.blocks, p.nblk, p.stream = t, t.numel() // 64, torch.cuda.current_stream(t.device)
         dev, sp = dev_index(t), stream_ptr(t.device)
-        counts = torch.empty(p.nblk, dtype=torch.int32, device=t.device)
-        p.masks = torch.empty(p.nblk, dtype=torch.int64, device=t.device)      # 64-bit non-zero masks, count pass -> write pass
-        _lib.check(_lib.lib.ivc_zerorun_count_masks(dev, sp, t.data_ptr(), p.nblk, counts.data_ptr(), p.masks.data_ptr()),
-                   "ivc_zerorun_count_masks")
+        if counts is not None and masks is not None:
+            if counts.numel() != p.nblk or masks.numel() != p.nblk or counts.dtype != torch.int32 or masks.dtype != torch.int64:
+                raise ValueError("counts (int32) and masks (int64) must hold one entry per scan block")
+            p.masks = masks
+        else:
+            counts = torch.empty(p.nblk, dtype=torch.int32, device=t.device)
+            p.masks = torch.empty(p.nblk, dtype=torch.int64, device=t.device)  # 64-bit non-zero masks, count pass -> write pass
+            _lib.check(_lib.lib.ivc_zerorun_count_masks(dev, sp, t.data_ptr(), p.nblk, counts.data_ptr(), p.masks.data_ptr()),
+                       "ivc_zerorun_count_masks")
         p.offsets = torch.empty(p.nblk, dtype=torch.int64, device=t.device)
         p.total_host = total_host if total_host is not None else torch.zeros(1, dtype=torch.int64).pin_memory()
         if p.nblk:              # one scan kernel; it posts the stream length into the mapped pinned word itself

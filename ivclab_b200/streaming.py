@@ -62,6 +62,8 @@ class StreamedCoder:
         if mv_dtype not in (torch.int16, torch.int32, torch.int64) or (mv_dtype == torch.int16 and span2 > 32767):
             raise ValueError("mv_dtype must be 'auto', torch.int64, torch.int32, or torch.int16 with (2 sr + 1)^2 <= 32767")
         self.mv_dtype = mv_dtype
+        import os
+        self.fused_count = os.environ.get("IVC_STREAM_FUSED_COUNT", "1") != "0"    # A/B switch: zero-run counts from the forward kernels
         # Symbol streams are the bulk of the download.  The inputs are 8-bit images, so every DCT coefficient is
         # bounded by 8 * 255 and every quantised value by 2040 / min(table): when that (and the EOB marker) fits 16
         # bits, "auto" sends int16 symbols -- a lossless transfer format, half the bytes; torch.int32 forces the
@@ -142,12 +144,25 @@ class StreamedCoder:
         else:
             r8, c8 = s.ref[:n], s.cur[:n]
             d_cur, d_ref = c8.double(), r8.double()
-        zz = self.intra.forward_rgb(d_rgb)
-        pend_i = self.zr.encode_begin(zz, total_host=s.totals[0:1], record=False)
+        # the forward kernels hand the zero-run coder its per-block symbol counts and non-zero masks (taken from their
+        # staging buffers): no pass re-reads the indices from HBM to count
+        if self.fused_count:
+            zz, cnt_i, msk_i = self.intra.forward_rgb(d_rgb, zr=True)
+        else:
+            zz, cnt_i, msk_i = self.intra.forward_rgb(d_rgb), None, None
+        pend_i = self.zr.encode_begin(zz, total_host=s.totals[0:1], record=False, counts=cnt_i, masks=msk_i)
         sse_i = self.intra.inverse_with_distortion(zz, d_rgb, space="ycbcr")   # decode + error in one kernel, nothing stored
-        mv = self.pframe.estimate(r8, c8)              # the search reads the uint8 planes as they arrived
-        zzp = self.pframe.forward(d_cur, d_ref, mv, channels=self.inter_channels)
-        pend_p = self.zr.encode_begin(zzp, total_host=s.totals[1:2], record=False)
+        if int(self.pframe.search_range) == 4 and self.pframe.motion_comp.me_mode != "exact":
+            # one kernel: the search reads the uint8 planes as they arrived and codes its tiles' blocks from the same bytes
+            if self.fused_count:
+                mv, zzp, cnt_p, msk_p = self.pframe.estimate_forward(r8, c8, channels=self.inter_channels, zr=True)
+            else:
+                (mv, zzp), cnt_p, msk_p = self.pframe.estimate_forward(r8, c8, channels=self.inter_channels), None, None
+        else:
+            mv = self.pframe.estimate(r8, c8)
+            zzp = self.pframe.forward(d_cur, d_ref, mv, channels=self.inter_channels)
+            cnt_p = msk_p = None
+        pend_p = self.zr.encode_begin(zzp, total_host=s.totals[1:2], record=False, counts=cnt_p, masks=msk_p)
         recp = self.pframe.inverse(zzp, ref=d_ref, mv=mv)
         sse_p = frame_sse(d_cur, recp)
         if self.mv_dtype != torch.int64:

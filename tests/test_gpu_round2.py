@@ -451,6 +451,18 @@ def test_fused_search_forward_equals_the_two_kernels(mode):
         mv, zz = pc.estimate_forward(seq[0], seq[1])
         assert np.array_equal(mv, O.me_full_search(seq[0], seq[1], sr))
         assert np.array_equal(zz, O.pframe_forward(seq[1], seq[0], mv, sr, O.quant_table(1.0))[1])
+    if mode != "exact":                                                        # uint8 planes: the fused kernel on the bytes as they are
+        seq = O.moving_sequence(91, 3, 72, 136)
+        s8 = torch.from_numpy(seq.astype(np.uint8)).cuda()
+        pc = ivc.PFrameBlockCoder(0.4, 4, me_mode=mode)
+        mv, zz = pc.estimate_forward(s8[:-1], s8[1:], channels=2)
+        for i in range(2):
+            assert np.array_equal(mv[i].cpu().numpy(), O.me_full_search(seq[i], seq[i + 1], 4))
+            assert np.array_equal(zz[i].cpu().numpy(), O.pframe_forward(seq[i + 1], seq[i], mv[i].cpu().numpy(), 4, O.quant_table(0.4))[1][:, :, :2])
+        odd = torch.empty(s8.numel() + 1, dtype=torch.uint8, device="cuda")[1:].view(s8.shape)     # unaligned planes: scalar staging
+        odd.copy_(s8)
+        mv2, zz2 = pc.estimate_forward(odd[:-1], odd[1:], channels=2)
+        assert torch.equal(mv2, mv) and torch.equal(zz2, zz)
     flat = np.full((2, 40, 56), 255.0)
     mv, zz = ivc.PFrameBlockCoder(1.0, 4, me_mode=mode).estimate_forward(flat[0], flat[1])
     assert np.array_equal(mv, O.me_full_search(flat[0], flat[1], 4)) and not zz.any()
@@ -472,3 +484,48 @@ def test_fused_search_forward_1080p_batch_custom_tables():
     assert np.array_equal(mv[0].cpu().numpy(), mvo)
     pred = CO.mc_reconstruct(seq[0][..., None], mvo, 4)[..., 0]
     assert np.array_equal(zz[0].cpu().numpy(), CO.intra_forward(seq[1] - pred, tab, threads=8))
+
+
+def test_forward_kernels_emit_zero_run_counts_and_masks():
+    """forward_rgb(zr=True) / estimate_forward(zr=True): the counts and masks of the zero-run coder's count pass, taken in
+    the forward kernels -- equal to the stand-alone pass, and the symbol streams built from them equal the oracle's."""
+    from ivclab_b200 import _lib as L
+    zr = ivc.ZeroRunCoder()
+
+    def count_pass(zz):
+        n = zz.numel() // 64
+        c = torch.empty(n, dtype=torch.int32, device="cuda")
+        m = torch.empty(n, dtype=torch.int64, device="cuda")
+        L.check(L.lib.ivc_zerorun_count_masks(0, torch.cuda.current_stream().cuda_stream, zz.data_ptr(), n, c.data_ptr(), m.data_ptr()), "count")
+        return c, m
+    for (n, H, W) in ((1, 8, 16), (2, 64, 96), (3, 72, 144), (1, 136, 272)):       # ragged tiles incl. a single block row
+        rgb = torch.from_numpy(np.stack([O.smooth_noise_rgb(400 + i, H, W) for i in range(n)])).cuda()
+        for q in (0.07, 1.0, 4.5):
+            coder = ivc.IntraBlockCoder(q)
+            zz, c, m = coder.forward_rgb(rgb, zr=True)
+            assert torch.equal(zz, coder.forward_rgb(rgb))
+            c2, m2 = count_pass(zz)
+            assert torch.equal(c, c2) and torch.equal(m, m2), (n, H, W, q)
+            sym = zr.encode_finish(zr.encode_begin(zz, counts=c, masks=m))
+            want = np.concatenate([O.zerorun_encode_fast(z) for z in zz.cpu().numpy()])
+            assert np.array_equal(sym.cpu().numpy(), want)
+        seq = O.moving_sequence(500 + H, n + 1, H, W)
+        for dt in (torch.float64, torch.uint8):
+            d = torch.from_numpy(seq).cuda().to(dt)
+            for ch in (2, 3):
+                for sr in (4, 2):                                                  # fused kernel / the stand-alone pair
+                    if dt == torch.uint8 and sr != 4:
+                        continue
+                    pc = ivc.PFrameBlockCoder(0.4, sr)
+                    mv, zz, c, m = pc.estimate_forward(d[:-1], d[1:], channels=ch, zr=True)
+                    mv2, zz2 = pc.estimate_forward(d[:-1], d[1:], channels=ch)
+                    assert torch.equal(mv, mv2) and torch.equal(zz, zz2)
+                    c2, m2 = count_pass(zz)
+                    assert torch.equal(c, c2) and torch.equal(m, m2), (n, H, W, dt, ch, sr)
+    # non-integer frames in auto mode: the gated fallback fills counts / masks as well
+    seq = torch.from_numpy(O.moving_sequence(9, 3, 72, 136) + 0.25).cuda()
+    mv, zz, c, m = ivc.PFrameBlockCoder(1.0, 4).estimate_forward(seq[:-1], seq[1:], zr=True)
+    c2, m2 = count_pass(zz)
+    assert torch.equal(c, c2) and torch.equal(m, m2)
+    with pytest.raises(ValueError):
+        ivc.IntraBlockCoder(1.0).forward_rgb(rgb.cpu().numpy(), zr=True)

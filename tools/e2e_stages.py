@@ -9,7 +9,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ivclab_b200 as ivc  # noqa: E402
 from ivclab_b200.signal.color import rgb2ycbcr  # noqa: E402
 from ivclab_b200.utils.metrics import frame_sse  # noqa: E402
-from bench_configs import luma_seq, timed  # noqa: E402
+import bench_configs as BC  # noqa: E402
+
+DEV = torch.device("cuda", 0)
+luma_seq = lambda T, H, W, seed: BC.luma_seq(torch, DEV, T, H, W, seed)
+timed = lambda fn, reps: BC.Ctx(torch, None, DEV, 0, 1, 6542.1).timed(fn, reps, 3)
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 g = torch.Generator(device="cuda").manual_seed(0)
@@ -23,7 +27,7 @@ zz = intra.forward_rgb(rgb)
 rec = intra.inverse(zz)
 ycc = rgb2ycbcr(rgb)
 mv = pf.estimate(ref, cur)
-zzp = pf.forward(cur, ref, mv)
+zzp = pf.forward(cur, ref, mv, channels=2)
 recp = pf.inverse(zzp, ref=ref, mv=mv)
 luma8 = torch.empty((n + 1, 1080, 1920), dtype=torch.uint8, device="cuda")
 rgb1 = torch.cat([rgb[-1:], rgb]).contiguous()
@@ -33,8 +37,9 @@ stages = {                                               # the stages of Streame
     "forward_rgb": lambda: intra.forward_rgb(rgb),
     "zr intra (count+scan+write)": lambda: zr.encode(zz),
     "decode + distortion (K2d)": lambda: intra.inverse_with_distortion(zz, rgb, space="ycbcr"),
-    "ME on uint8 planes": lambda: pf.estimate(ref8, cur8),
-    "pframe fwd": lambda: pf.forward(cur, ref, mv),
+    "search + pframe fwd, fused, uint8 planes": lambda: pf.estimate_forward(ref8, cur8, channels=2),
+    "(ME on uint8 planes alone)": lambda: pf.estimate(ref8, cur8),
+    "(pframe fwd alone, 2 channels)": lambda: pf.forward(cur, ref, mv, channels=2),
     "zr inter (count+scan+write)": lambda: zr.encode(zzp),
     "pframe inv": lambda: pf.inverse(zzp, ref=ref, mv=mv),
     "sse inter": lambda: frame_sse(cur, recp),
@@ -42,6 +47,7 @@ stages = {                                               # the stages of Streame
 tot = 0.0
 for name, fn in stages.items():
     t = timed(fn, 20)
-    tot += t
+    if not name.startswith("("):
+        tot += t
     print(f"{name:32s} {t * 1e3 / n:8.1f} us/frame")
 print(f"{'total':32s} {tot * 1e3 / n:8.1f} us/frame  -> {tot / n * 32:.2f} ms per 32 frames;  symbols/frame intra {zr.encode(zz).numel() / n:.0f} inter {zr.encode(zzp).numel() / n:.0f}")
