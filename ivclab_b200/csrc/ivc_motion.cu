@@ -22,6 +22,7 @@
 // all blocks of the tile are flattened over the CTA's threads; the per-block argmin is a shared-memory atomicMin
 // on the packed key (ssd, index).  ivc_me_full_search(IVC_ME_AUTO) launches k_me_int and then k_me_exact, which
 // exits immediately unless the flag was raised -- no host round trip, no workspace beyond the 4-byte flag.
+#include <cstdio>
 #include <cstdlib>
 #include "ivc_dct.cuh"
 #include "ivc_common.cuh"
@@ -1235,7 +1236,10 @@ cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const vo
     const int G = me_int_group(2 * sr + 1);
     // common cases get a compile-time pitch: 16-block-wide tiles at +-4 (136) and up to +-16 (160)
     const int pitch = (G == 9 && sr <= 4) ? 136 : (G == 9 && sr <= 8) ? 144 : (G == 11 && sr <= 16) ? 160 : 0;
-    const size_t smem = me_int_geometry(a, G, pitch, n, H, W, sr, 200 * 1024, 4 * 3 * (int64_t)sm_count(device));
+    int f_tby = 0, f_tbx = 0, f_thr = 0;                                       // developer overrides: IVC_ME_TILE="tby,tbx", IVC_ME_THREADS
+    if (const char *e = getenv("IVC_ME_TILE")) sscanf(e, "%d,%d", &f_tby, &f_tbx);
+    if (const char *e = getenv("IVC_ME_THREADS")) f_thr = atoi(e);
+    const size_t smem = me_int_geometry(a, G, pitch, n, H, W, sr, 200 * 1024, 4 * 3 * (int64_t)sm_count(device), f_tby, f_tbx);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     if (H * W >= 2147483647LL) return cudaErrorInvalidValue;                  // 32-bit pixel coordinates inside a frame
     const int elem = u8 ? 1 : f32 ? 4 : 8;
@@ -1258,12 +1262,14 @@ cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const vo
             if (waste < best - 1e-9) { best = waste; threads = t; }
         }
     }
+    if (f_thr) threads = f_thr;
     if (pf_zz) {                                                               // fused search + P-frame forward: +-4, tile 4 x 16
         if (!me_pf_fusable(dtype, sr) || G != 9 || pitch != 136) return cudaErrorInvalidValue;
         const int groups = a.tby * ((a.tbx + 7) / 8);                          // one warp-private WORK buffer per group, in U + S
-        if (groups > kMePfThreads / 32 || (size_t)groups * kPfWork > (size_t)a.b_off) return cudaErrorInvalidValue;
-        return u8 ? me_launch_chunks(k_me_int<unsigned char, 9, 136, true>, a, 1, smem, st, kMePfThreads)
-                  : me_launch_chunks(k_me_int<double, 9, 136, true>, a, 8, smem, st, kMePfThreads);
+        if (groups > (f_thr ? f_thr : kMePfThreads) / 32 || (size_t)groups * kPfWork > (size_t)a.b_off) return cudaErrorInvalidValue;
+        const int pf_thr = f_thr ? f_thr : kMePfThreads;
+        return u8 ? me_launch_chunks(k_me_int<unsigned char, 9, 136, true>, a, 1, smem, st, pf_thr)
+                  : me_launch_chunks(k_me_int<double, 9, 136, true>, a, 8, smem, st, pf_thr);
     }
 #define IVC_ME_INT_CASE(GG, PP)                                                                  \
     if (G == GG && pitch == PP)                                                                  \
