@@ -28,6 +28,7 @@ if ROOT not in sys.path:
 QS = [0.07, 0.2, 0.4, 0.8, 1.0, 1.5, 2, 3, 4, 4.5]          # exercises/ch4/ex1.py:385
 IDP_LANES_PER_CLK_SM = 64                                   # measured: tools/ubench_int.cu, profiles/r1h_ubench_int.txt
 FP64_LANES_PER_CLK_SM = 64
+MMA_U8_MAC_PER_CLK_SM = 1935                                # mma.sync.m16n8k32.u8, measured (same file)
 
 
 def candidates(H, W, sr):
@@ -295,11 +296,14 @@ def cfg4(cx, ivc, n_seq=8, T=120, exact_pairs=4):
                        f"against the previous original frame, sequence s on rank s mod {cx.world} (strong scaling)",
            "ms": round(ms, 3), "frame_pairs": pairs, "mpixel_s": round(pairs * H * W / ms / 1e3, 1),
            "ms_per_frame_per_gpu": round(per_frame, 4) if per_frame else None,
-           "kernel": "k_me_int<double,11,160> (auto mode: integer-valued frames)",
-           "bound": "IDP (dp4a) pipe",
-           "idp_lanes_per_s": round(lanes / (per_frame * 1e-3), 0) if per_frame else None,
-           "idp_pipe_frac": round(lanes / (per_frame * 1e-3) / pipe, 4) if per_frame else None,
-           "idp_pipe_peak": f"{IDP_LANES_PER_CLK_SM} lanes/clk/SM x {cx.sms} SMs x {cx.sm_hz / 1e6:.0f} MHz (measured issue rate, profiles/r1h_ubench_int.txt)",
+           "kernel": "k_me_mma16<double> (auto mode: integer-valued frames; cross term on mma.sync.m16n8k32.u8; IVC_ME_MMA=0 selects "
+                     "the dp4a kernel k_me_int<double,11,160>)",
+           "bound": "tensor pipe + shared-memory wavefronts + staging phases (profiles/README.md)",
+           # 70 IMMA.16832 per block (4096 MAC each) against the measured mma.sync u8 rate; useful = 64 MAC per candidate
+           "tensor_pipe_frac": round((H // 8) * (W // 8) * 70 * 4096 / (per_frame * 1e-3) / (MMA_U8_MAC_PER_CLK_SM * cx.sms * cx.sm_hz), 4) if per_frame else None,
+           "tensor_pipe_peak": f"{MMA_U8_MAC_PER_CLK_SM} MAC/clk/SM (mma.sync u8, measured: profiles/r1h_ubench_int.txt) x {cx.sms} SMs x {cx.sm_hz / 1e6:.0f} MHz",
+           "useful_mac_per_s": round(cand * 64 / (per_frame * 1e-3), 0) if per_frame else None,
+           "dp4a_equivalent_idp_pipe_frac": round(lanes / (per_frame * 1e-3) / pipe, 4) if per_frame else None,
            "hbm_frac": round((2 * 8 * H * W + 8 * (H // 8) * (W // 8)) / (per_frame * 1e-3) / 1e9 / cx.peak, 4) if per_frame else None,
            "candidates_per_frame": cand}
     if ms_exact is not None:
