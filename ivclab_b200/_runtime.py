@@ -83,6 +83,48 @@ def _memo_get(a: np.ndarray, device):
     return torch.as_strided(t.reshape(-1), a.shape, tuple(s // a.itemsize for s in a.strides), off // a.itemsize)
 
 
+_stage = {"buf": None, "event": None}          # one cached pinned staging buffer for numpy uploads (grown on demand)
+
+
+def _pinned_upload(flat: np.ndarray, device) -> torch.Tensor:
+    """contiguous 1-D numpy array -> device tensor through a reused page-locked staging buffer: one host memcpy and
+    one DMA at the link's rate instead of the driver's chunked pageable copy."""
+    n = flat.nbytes
+    st = _stage
+    if st["event"] is not None:
+        st["event"].synchronize()                  # the previous upload has left the staging buffer
+    if st["buf"] is None or st["buf"].numel() < n:
+        st["buf"] = torch.empty(max(n, 1 << 20), dtype=torch.uint8, pin_memory=True)
+    host = st["buf"][:n]
+    np.copyto(host.numpy(), flat.view(np.uint8).reshape(-1))     # (four copying threads measured slower: 1.17 vs 0.95 ms per 9.4 MB)
+    dev = torch.empty(n, dtype=torch.uint8, device=device or "cuda")
+    dev.copy_(host, non_blocking=True)
+    st["event"] = torch.cuda.Event()
+    st["event"].record(torch.cuda.current_stream(dev.device))
+    return dev
+
+
+def _upload_via_base(a: np.ndarray, device):
+    """numpy array -> device tensor with the same shape / strides.  A strided VIEW of a contiguous array (what
+    ``Patcher.patch`` / ``einops.rearrange`` hand to the first method of a chain, shape.py:54) is uploaded as its
+    contiguous base and re-viewed on the device: no strided gather on the host.  Returns None when that does not apply
+    (the caller falls back to the plain copy)."""
+    if a.size == 0 or a.dtype.type not in _NP_OK or a.dtype == np.bool_ or a.dtype == np.float16 or a.dtype == np.int8 or a.dtype == np.int16:
+        return None
+    root = a
+    while isinstance(root.base, np.ndarray):
+        root = root.base
+    if not root.flags.c_contiguous or root.dtype != a.dtype or root.nbytes > 4 * a.nbytes + (1 << 16) or root.nbytes < (1 << 18):
+        return None
+    if any(s < 0 or s % a.itemsize for s in a.strides):
+        return None
+    off = a.__array_interface__["data"][0] - root.__array_interface__["data"][0]
+    if off < 0 or off % a.itemsize:
+        return None
+    dev = _pinned_upload(root.reshape(-1), device).view(torch.from_numpy(np.empty(0, dtype=a.dtype)).dtype)
+    return torch.as_strided(dev, a.shape, tuple(s // a.itemsize for s in a.strides), off // a.itemsize)
+
+
 def to_device(x, device=None):
     """-> (cuda tensor, was_numpy).  numpy arrays (incl. strided views such as
     Patcher.patch output) are copied H2D keeping their strides; cuda tensors pass through.  Arrays that this
@@ -97,6 +139,9 @@ def to_device(x, device=None):
         t = _memo_get(a, device)
         if t is not None:
             return t, True
+    t = _upload_via_base(a, device)
+    if t is not None:
+        return t, True
     if a.dtype.type not in _NP_OK:
         a = a.astype(np.float64)
     if any(s < 0 for s in a.strides):

@@ -8,24 +8,24 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ivclab_b200 as ivc  # noqa: E402
-from bench_configs import luma_seq  # noqa: E402
+import bench_configs as BC  # noqa: E402
 
 F, chunk = int(sys.argv[1]), int(sys.argv[2])
 g = torch.Generator(device="cuda").manual_seed(0)
 rgb = (torch.nn.functional.avg_pool2d(torch.rand((F, 3, 1080, 1920), generator=g, device="cuda") * 255, 5, 1, 2)
        .permute(0, 2, 3, 1).contiguous().to(torch.uint8).cpu().pin_memory())
-s = luma_seq(F + 1, 1080, 1920, 5000).to(torch.uint8).cpu()
-ref, cur = s[:-1].contiguous().pin_memory(), s[1:].contiguous().pin_memory()
-sc = ivc.StreamedCoder(1.0, 4, chunk_frames=chunk, ramp=tuple(int(v) for v in os.environ.get('RAMP', '').split(',') if v))
-SEQ = bool(int(os.environ.get('SEQ', '1')))
+first = rgb[-1].clone().pin_memory()
+sc = ivc.StreamedCoder(1.0, 4, chunk_frames=chunk, ramp=tuple(int(v) for v in os.environ.get('RAMP', '').split(',') if v),
+                       slots=int(os.environ.get('SLOTS', '3')))
+run = lambda: sc.run(rgb, first_ref=first)                  # the bench's e2e form: RGB only, luma derived on the device
 for _ in range(3):
-    sc.run(rgb, cur, first_ref=ref[0]) if SEQ else sc.run(rgb, cur, ref)
+    run()
 torch.cuda.synchronize()
 sc.trace = []
 origin = torch.cuda.Event(enable_timing=True)
 origin.record()
 t0 = time.perf_counter()
-sc.run(rgb, cur, first_ref=ref[0]) if SEQ else sc.run(rgb, cur, ref)
+run()
 t1 = time.perf_counter()
 torch.cuda.synchronize()
 print(f"run: {(t1 - t0) * 1e3:.3f} ms host wall")
