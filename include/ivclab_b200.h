@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define IVC_ABI_VERSION 6
+#define IVC_ABI_VERSION 7
 
 /* element types */
 #define IVC_U8   0
@@ -215,6 +215,20 @@ int ivc_pframe_search_forward_zr(int device, void *stream,
                                  const void *table, int table_dtype, int out_channels,
                                  int64_t *mv_out, int32_t *zz_out, void *workspace, int64_t workspace_bytes,
                                  int32_t *counts_out, uint64_t *masks_out);
+
+/* ---- a13 + a15 + a15: one whole closed-loop P-frame step in ONE kernel (exercises/ch4/E4-1.py:257-306) --------------
+ * mv = compute_motion_vector(ref, cur) with the order-exact search (ref is a reconstruction: not integer-valued);
+ * zz = flatten(quantize(dct(patch(cur - MC(ref, mv))))) (out_channels scan blocks per image block);
+ * recon = MC(ref, mv) + idct(dequantize(unflatten(zz[..., 0, :]))) with the luminance table, i.e. the decoder's next
+ * reference for decode = "luma" (channel 0 of every block -- the reference's own `symbols2image` with a 2-D shape reads
+ * other blocks, SURVEY.md section 0 item 10, and needs the three stand-alone kernels).  Per block the three stages need
+ * only the block, its window and its vector, so the warp that finds the vector codes and reconstructs the block from
+ * shared memory: the frame pair is read once.  cur/ref/recon_out [n_frames,H,W] F64, n_frames <= 65535. */
+int ivc_pframe_step(int device, void *stream,
+                    const void *cur, const void *ref, int dtype,
+                    int64_t n_frames, int64_t H, int64_t W, int search_range,
+                    const void *table, int table_dtype, int out_channels,
+                    int64_t *mv_out, int32_t *zz_out, void *recon_out);
 
 /* ---- a15 fused: P-frame decoder half (intracodec.py:115-124 + videocodec.py:74) --------------
  * recon = pred + idct(dequantize(unflatten(zz[..., 0, :])))[channel 0]  (luminance table).

@@ -364,6 +364,21 @@ static int search_forward_impl(int device, void *stream, const void *cur, const 
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
 
+int ivc_pframe_step(int device, void *stream, const void *cur, const void *ref, int dtype, int64_t n_frames, int64_t H,
+                    int64_t W, int search_range, const void *table, int table_dtype, int out_channels, int64_t *mv_out,
+                    int32_t *zz_out, void *recon_out) {
+    if (n_frames < 0 || n_frames > 65535 || H < 0 || W < 0 || search_range < 0 || search_range > 64) return IVC_ERR_ARG;
+    if (out_channels != 2 && out_channels != 3) return IVC_ERR_ARG;
+    if (dtype != IVC_F64 || !is_float(table_dtype)) return IVC_ERR_DTYPE;
+    if ((H & 7) || (W & 7)) return IVC_ERR_SHAPE;
+    if (n_frames * H * W == 0) return IVC_OK;
+    if (!cur || !ref || !table || !mv_out || !zz_out || !recon_out || !aligned16(zz_out)) return IVC_ERR_ARG;
+    IVC_ENTER(device);
+    cudaError_t e = ivc::launch_pframe_step(device, (cudaStream_t)stream, ref, cur, n_frames, H, W, search_range, table,
+                                            table_dtype, out_channels, mv_out, zz_out, (double *)recon_out);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
 int ivc_pframe_inverse(int device, void *stream, const int32_t *zz, int64_t Czz, const void *pred, const void *ref,
                        const int64_t *mv, int dtype, int64_t n_frames, int64_t H, int64_t W, int search_range,
                        const void *table, int table_dtype, void *recon_out) {

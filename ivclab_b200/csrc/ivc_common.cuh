@@ -39,6 +39,9 @@ cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const vo
                           int check, const void *pf_table = nullptr, int pf_table_dtype = 0, int32_t *pf_zz = nullptr,
                           int pf_och = 3, int32_t *zr_counts = nullptr, uint64_t *zr_masks = nullptr);
 bool me_pf_fusable(int dtype, int sr);
+cudaError_t launch_pframe_step(int device, cudaStream_t st, const void *ref, const void *cur, int64_t n, int64_t H, int64_t W,
+                               int sr, const void *table, int table_dtype, int out_channels, int64_t *mv, int32_t *zz,
+                               double *recon);
 cudaError_t launch_me_wrap(int device, cudaStream_t st, const void *ref, const void *cur, int dtype, int64_t n, int64_t H,
                            int64_t W, int64_t ref_fs, int64_t cur_fs, int sr, int64_t *mv);
 cudaError_t launch_mc(int device, cudaStream_t st, const void *ref, int elem_size, int64_t n, int64_t H, int64_t W,

@@ -61,6 +61,8 @@ struct MeArgs {
     int table_dtype;
     int32_t *zz;
     int och;
+    double *recon;                         // fused closed-loop step (k_me_exact<double, STEP>): the decoder's reconstruction of the frame
+    int work_off;                          // ... byte offset of the warps' WORK buffers in dynamic shared memory
     int32_t *zr_counts;                    // optional: zero-run symbol count and non-zero mask per scan block (see ivc_tile.cuh)
     unsigned long long *zr_masks;
 };
@@ -101,12 +103,192 @@ __device__ __forceinline__ MeTile me_tile(const MeArgs &a) {
 }
 
 // ================================================================================================
+// fused closed-loop step: what follows the exact search for the warp's own blocks
+// ================================================================================================
+// One P-frame of the closed loop is search -> MC + residual + DCT + quantise + zig-zag -> dequantise + IDCT +
+// prediction add (exercises/ch4/E4-1.py:257-306; videocodec.py:52-75), and per block it needs nothing but the block, its
+// search window and its vector -- all of which the exact search kernel holds in shared memory.  With decode = "luma"
+// (channel 0 of every block) nothing crosses a tile, so the warp that found a block's vector codes and reconstructs it on
+// the spot: the frame pair is read once, one launch per frame instead of three, and no kernel ramps up or drains between
+// the phases.  Arithmetic and operation order are those of k_pframe_forward_tm / k_pframe_inverse_tm (ivc_transform.cu):
+// lane (r, u) owns pixel row r of blocks u and u + 4 of the group in the row passes and column r in the column passes.
+constexpr int kStepWork = 4 * kP3TU * 8;                                      // 4352 B per warp: transposition buffer / scan staging
+constexpr int kStepCurPitch = 66;                                             // == kExactCurPitch (defined below)
+
+__device__ __forceinline__ void pstep_group(const MeArgs &a, const MeTile &tl, const double *s_win, const double *s_cur,
+                                            const int *s_pidx, int blk_first, int nb, FastDiv d_nbx, unsigned char *work_b,
+                                            const double *s_rt, const double *s_t, const double *s_tT, bool chroma_twice) {
+    const int lane = threadIdx.x & 31, r = lane & 7, u = lane >> 3;
+    const uint32_t work_s = smem_u32(work_b);
+    const FastDiv d_span(a.m_span);
+    const int mc = nb > 4 ? 2 : 1;                      // a group of at most four blocks leaves the m = 1 half empty: skip its arithmetic (warp-uniform)
+    double x[2][8];
+    int wrow[2], wcol[2], gby[2], gbx[2];                                     // window position of the prediction, block coordinates
+    bool valid[2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        const int bi = u + 4 * m;
+        valid[m] = bi < nb;
+        if (m >= mc) continue;
+        const int blk = blk_first + (valid[m] ? bi : 0);
+        const int brow = d_nbx.div(blk), b = blk - brow * tl.nbx;
+        const int idx = s_pidx[blk * 32];                                     // the block's vector (lane 0's slot after the argmin)
+        const int dyi = d_span.div(idx), dxi = idx - dyi * a.span;
+        wrow[m] = 8 * brow + dyi;
+        wcol[m] = 8 * b + dxi;
+        gby[m] = tl.by0 + brow;
+        gbx[m] = tl.bx0 + b;
+        const double *cb = s_cur + (brow * a.tbx + b) * kStepCurPitch + r * 8;
+        const double *wp = s_win + (wrow[m] + r) * a.P + wcol[m];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[m][k] = valid[m] ? __dsub_rn(cb[k], wp[k]) : 0.0;   // residual = cur - prediction (videocodec.py:71)
+    }
+    // ---- forward: rows, transpose, columns ----
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+        if (m < mc) dct2_8(x[m]);
+    bulk_wait_read0();                                  // an earlier group's stores have drained WORK
+    __syncwarp();
+    unsigned char *t_base = work_b + u * (kP3TU * 8);
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+        if (m < mc) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<double *>(t_base + ((((r >> 1) ^ (j >> 1)) << 1) + (r & 1)) * 8 + (m * 8 + j) * 64) = x[m][j];
+        }
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        if (m >= mc) continue;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double2 v = *reinterpret_cast<const double2 *>(t_base + r * 64 + ((k ^ (r >> 1)) << 4) + m * 512);
+            x[m][2 * k] = v.x;
+            x[m][2 * k + 1] = v.y;
+        }
+        dct2_8(x[m]);
+    }
+    __syncwarp();
+    // ---- quantise against [lum, chrom, chrom] (patchquant.py:59), zig-zag, store; keep channel 0 for the decoder ----
+    const int nch = (chroma_twice || a.och == 2) ? 2 : 3;
+    const double *rt_l = s_rt + r, *t_l = s_t + r;
+    unsigned char *stage = work_b + u * (kStageUF * 4);
+    int q0[2][8];                                       // channel 0 of row r (columns j): the decoder's input
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        if (m >= mc) continue;
+        if (m == 1) { bulk_wait_read0(); __syncwarp(); }     // round 0's stores have drained the staging area
+        for (int ch = 0; ch < nch; ++ch) {
+            QuantGuard qg;
+            int qv[8];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) qv[v] = qg.q(x[m][v], rt_l[ch * 64 + v * 8]);
+            if (__builtin_expect(qg.risky(), 0)) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v) qv[v] = quantize_exact_f64(x[m][v], t_l[ch * 64 + v * 8]);
+            }
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                const int pos = ZZ_ORDER[v * 8 + r];
+                *reinterpret_cast<int *>(stage + pos * 4 + ch * 256) = qv[v];
+                if (ch == 1 && nch == 2) *reinterpret_cast<int *>(stage + pos * 4 + 512) = qv[v];   // channel 2 repeats channel 1
+            }
+        }
+        fence_proxy_async();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q0[m][j] = *reinterpret_cast<const int *>(stage + ZZ_ORDER[r * 8 + j] * 4);   // coefficient (r, j)
+        {
+            const int bi = lane + 4 * m;                  // lane u (< 4) stores the och scan blocks of the group's block u + 4m
+            if (lane < 4 && bi < nb) {
+                const int blk = blk_first + bi, brow = d_nbx.div(blk), b = blk - brow * tl.nbx;
+                bulk_s2g(a.zz + ((tl.frame * a.Hp + tl.by0 + brow) * (int64_t)a.Wp + tl.bx0 + b) * (64 * a.och),
+                         work_s + lane * (kStageUF * 4), 256u * (uint32_t)a.och);
+            }
+        }
+        bulk_commit();                                    // every lane commits (possibly empty) groups: counts stay in step
+    }
+    // ---- decoder: dequantise with the luminance table, IDCT rows then columns, + prediction (videocodec.py:74) ----
+    {
+        int mx = 0;
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+            if (m < mc) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const double pr = __dmul_rn(i32_to_f64(q0[m][j]), s_tT[j * 8 + r]);     // s_tT[j*8 + r] = lum[r][j]
+                    mx = max(mx, __double2hiint(pr) & 0x7fffffff);
+                    x[m][j] = trunc_f64_small(pr);
+                }
+            }
+        if (__builtin_expect(mx >= 0x41E00000, 0)) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+                if (m < mc) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) x[m][j] = dequantize_f64(q0[m][j], s_tT[j * 8 + r]);
+                }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+        if (m < mc) dct3_8(x[m]);
+    bulk_wait_read0();                                  // the scan stores have read the staging area: WORK is free again
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+        if (m < mc) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<double *>(t_base + ((((r >> 1) ^ (j >> 1)) << 1) + (r & 1)) * 8 + (m * 8 + j) * 64) = x[m][j];
+        }
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        if (m >= mc) continue;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double2 v = *reinterpret_cast<const double2 *>(t_base + r * 64 + ((k ^ (r >> 1)) << 4) + m * 512);
+            x[m][2 * k] = v.x;
+            x[m][2 * k + 1] = v.y;
+        }
+        dct3_8(x[m]);
+    }
+    __syncwarp();                                       // WORK may be rewritten by the next group from here on
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        if (!valid[m]) continue;
+        const double *wp = s_win + wrow[m] * a.P + wcol[m] + r;                // column r of the prediction
+        double *out = a.recon + tl.frame * (a.H * a.W) + ((int64_t)gby[m] * 8) * a.W + gbx[m] * 8 + r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[i * a.W] = __dadd_rn(wp[i * a.P], x[m][i]);   // recon = prediction + recon_residual
+    }
+}
+
+// ================================================================================================
 // exact float kernel
 // ================================================================================================
-template <typename T>
+template <typename T, bool STEP = false>
 __global__ void __launch_bounds__(kMeThreads, 2) k_me_exact(const MeArgs a) {
     if (a.flag && *a.flag != a.run_if) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double s_qt[STEP ? 448 : 1];              // STEP: fl(1/t) [192], t [192], luminance table transposed [64]
+    bool chroma_twice = false;
+    if (STEP) {
+        const int t_ = threadIdx.x;
+        if (t_ < 192) {
+            const double t = load_table_elem(a.table, a.table_dtype, t_);
+            s_qt[192 + t_] = t;
+            s_qt[t_] = __drcp_rn(t);
+            if (t_ < 64) s_qt[384 + (t_ & 7) * 8 + (t_ >> 3)] = t;
+        }
+        bool same = true;
+        if (t_ < 64)
+            same = __double_as_longlong(load_table_elem(a.table, a.table_dtype, 64 + t_)) ==
+                   __double_as_longlong(load_table_elem(a.table, a.table_dtype, 128 + t_));
+        chroma_twice = __syncthreads_and(same) != 0;
+    }
     T *s_win = reinterpret_cast<T *>(smem_raw);                         // [R][P]
     T *s_cur = reinterpret_cast<T *>(smem_raw + a.cur_off);             // [tby*tbx][kExactCurPitch]
     using R_ = Rn<T>;
@@ -227,7 +409,18 @@ __global__ void __launch_bounds__(kMeThreads, 2) k_me_exact(const MeArgs a) {
             const int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
             if (os < best || (os == best && oi < bidx && os != Inf<T>::v())) { best = os; bidx = oi; }
         }
-        if (lane == 0) a.mv[(tl.frame * a.Hp + tl.by0 + brow) * (int64_t)a.Wp + tl.bx0 + b] = bidx;
+        if (lane == 0) {
+            a.mv[(tl.frame * a.Hp + tl.by0 + brow) * (int64_t)a.Wp + tl.bx0 + b] = bidx;
+            if (STEP) s_pidx[blk * 32] = bidx;
+        }
+    }
+    if constexpr (STEP && sizeof(T) == 8) {
+        __syncwarp();
+        unsigned char *work_b = smem_raw + a.work_off + warp * kStepWork;
+        for (int k0 = 0; k0 < nb_w; k0 += 8)
+            pstep_group(a, tl, reinterpret_cast<const double *>(s_win), reinterpret_cast<const double *>(s_cur), s_pidx, blk0 + k0,
+                        min(8, nb_w - k0), d_nbx, work_b, s_qt, s_qt + 192, s_qt + 384, chroma_twice);
+        bulk_wait_all0();
     }
 }
 
@@ -1089,7 +1282,7 @@ __global__ void __launch_bounds__(256) k_mc(const McArgs a) {
 
 // choose the CTA tile (at most 64 blocks) and the shared-memory layout
 static size_t me_geometry(MeArgs &a, int64_t n_frames, int64_t H, int64_t W, int sr, int elem, int pitch_quantum,
-                          int pitch_skew, size_t budget, int64_t min_ctas) {
+                          int pitch_skew, size_t budget, int64_t min_ctas, int extra_per_warp = 0) {
     a.Hp = (int)(H / 8); a.Wp = (int)(W / 8); a.sr = sr; a.span = 2 * sr + 1;
     a.ngrp = (a.span + kMeG - 1) / kMeG;
     a.ntpb = a.ngrp * a.span;
@@ -1109,6 +1302,8 @@ static size_t me_geometry(MeArgs &a, int64_t n_frames, int64_t H, int64_t W, int
         a.npieces = 32;                                            // one (ssd, index) slot per block and lane
         a.part_off = (int)(((size_t)a.cur_off + (size_t)a.tby * a.tbx * kExactCurPitch * elem + 15) & ~(size_t)15);
         smem = (size_t)a.part_off + (size_t)64 * 32 * (elem + 4);
+        a.work_off = (int)((smem + 127) & ~(size_t)127);
+        if (extra_per_warp) smem = (size_t)a.work_off + (size_t)kMeWarps * extra_per_warp;
         if (smem <= budget) break;
     }
     a.tiles_y = (a.Hp + a.tby - 1) / a.tby;
@@ -1135,6 +1330,20 @@ static cudaError_t me_launch_chunks(K kernel, MeArgs a, int elem, size_t smem, c
         a.mv += 65535 * (int64_t)a.Hp * a.Wp;
     }
     return cudaGetLastError();
+}
+
+// The fused closed-loop step (decode = "luma"): exact search, then the warp codes and reconstructs its own blocks.
+cudaError_t launch_pframe_step(int device, cudaStream_t st, const void *ref, const void *cur, int64_t n, int64_t H, int64_t W,
+                               int sr, const void *table, int table_dtype, int out_channels, int64_t *mv, int32_t *zz,
+                               double *recon) {
+    MeArgs a;
+    a.ref = ref; a.cur = cur; a.n = n; a.H = H; a.W = W; a.ref_fs = H * W; a.cur_fs = H * W; a.mv = mv;
+    a.flag = nullptr; a.run_if = 0; a.check = 0;
+    a.table = table; a.table_dtype = table_dtype; a.zz = zz; a.och = out_channels; a.recon = recon;
+    a.zr_counts = nullptr; a.zr_masks = nullptr;
+    const size_t smem = me_geometry(a, n, H, W, sr, 8, 32, 3, 113 * 1024, 2 * 2 * (int64_t)sm_count(device), kStepWork);
+    if (smem > 227 * 1024 || n > 65535) return cudaErrorInvalidValue;          // one launch: y = frame
+    return me_launch_chunks(k_me_exact<double, true>, a, 8, smem, st);
 }
 
 cudaError_t launch_me_exact(int device, cudaStream_t st, const void *ref, const void *cur, bool f32, int64_t n,

@@ -33,6 +33,10 @@ class ClosedLoopLumaCoder:
         self.me_mode = {"auto": _lib.ME_AUTO, "exact": _lib.ME_EXACT, "int": _lib.ME_INT}[me_mode]
         self.use_graph = use_graph
         self._graphs = {}
+        # decode == "luma" needs nothing across tiles: one fused kernel per P-frame (the reference frames of a closed loop
+        # are reconstructions, so the search is the order-exact one whatever me_mode says -- the vectors are the same)
+        import os
+        self.fused_step = decode == "luma" and os.environ.get("IVC_CLOSED_LOOP_FUSED", "1") != "0"
 
     # S sequences in lockstep, time-major [T,S,H,W] float64 on the device: every launch codes frame t of all S
     def _enqueue(self, frames, zz, mv, recon, ws, zero, dtab, tcode):
@@ -60,6 +64,10 @@ class ClosedLoopLumaCoder:
         for t in range(1, T):
             cur, ref, out = fp + t * fsz, rp + (t - 1) * fsz, rp + t * fsz
             z, m = zp + t * zsz, mp + (t - 1) * msz
+            if self.fused_step:                   # decode == "luma": search, encoder half and decoder half in ONE kernel
+                chk(L.ivc_pframe_step(dev, sp, cur, ref, _lib.F64, S, H, W, self.search_range, dtab, tcode, 3, m, z, out),
+                    "ivc_pframe_step")
+                continue
             chk(L.ivc_me_full_search(dev, sp, ref, cur, _lib.F64, S, H, W, H * W, H * W, self.search_range,
                                      self.me_mode, m, ws.data_ptr(), ws.numel()), "ivc_me_full_search")
             chk(L.ivc_pframe_forward(dev, sp, cur, ref, m, _lib.F64, S, H, W, self.search_range, dtab, tcode, None, z),

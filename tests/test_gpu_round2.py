@@ -529,3 +529,38 @@ def test_forward_kernels_emit_zero_run_counts_and_masks():
     assert torch.equal(c, c2) and torch.equal(m, m2)
     with pytest.raises(ValueError):
         ivc.IntraBlockCoder(1.0).forward_rgb(rgb.cpu().numpy(), zr=True)
+
+
+# ---------------------------------------------------------------- fused closed-loop step (search + encoder + decoder half)
+def test_closed_loop_fused_step_equals_three_kernels_and_oracle(monkeypatch):
+    """decode='luma': one kernel per P-frame (ivc_pframe_step).  Same scan indices, vectors and reconstructions as the
+    three stand-alone kernels and as the oracle's closed loop -- ragged tiles, tiny frames, lockstep batches, +-2 / +-7."""
+    from oracle import closed_loop as CL
+    g8 = load_golden("g8_closed_loop.npz")
+    fused = ivc.ClosedLoopLumaCoder(float(g8["qscale"]), int(g8["sr"]), decode="luma")
+    assert fused.fused_step
+    got = fused.code_sequence(g8["frames"])
+    assert np.array_equal(got["zz"], g8["zz_luma"]) and np.array_equal(got["mv"], g8["mv_luma"]) and np.array_equal(got["recon"], g8["recon_luma"])
+    monkeypatch.setenv("IVC_CLOSED_LOOP_FUSED", "0")
+    plain = ivc.ClosedLoopLumaCoder(0.4, 4, decode="luma")
+    assert not plain.fused_step
+    monkeypatch.delenv("IVC_CLOSED_LOOP_FUSED")
+    for (T, H, W, sr, q) in ((3, 8, 8, 4, 1.0), (4, 40, 56, 4, 0.4), (3, 72, 136, 2, 0.4), (3, 144, 176, 7, 1.0), (3, 264, 520, 4, 0.07)):
+        seq = O.moving_sequence(700 + H, T, H, W)
+        a = ivc.ClosedLoopLumaCoder(q, sr, decode="luma").code_sequence(seq)
+        monkeypatch.setenv("IVC_CLOSED_LOOP_FUSED", "0")
+        b = ivc.ClosedLoopLumaCoder(q, sr, decode="luma").code_sequence(seq)
+        monkeypatch.delenv("IVC_CLOSED_LOOP_FUSED")
+        for k in ("zz", "mv", "recon"):
+            assert np.array_equal(a[k], b[k]), (T, H, W, sr, q, k)
+        if H <= 144:
+            o = CL.code_sequence(seq, q, sr, "luma")
+            for k in ("zz", "mv", "recon"):
+                assert np.array_equal(a[k], o[k]), (T, H, W, sr, q, k)
+    seqs = np.stack([O.moving_sequence(800 + i, 4, 48, 64) for i in range(3)])          # three sequences in lockstep
+    lock = ivc.ClosedLoopLumaCoder(0.4, 4, decode="luma", use_graph=True).code_sequences(seqs)
+    for i in range(3):
+        one = ivc.ClosedLoopLumaCoder(0.4, 4, decode="luma").code_sequence(seqs[i])
+        for k in ("zz", "mv", "recon"):
+            assert np.array_equal(lock[k][i], one[k]), (i, k)
+    assert not ivc.ClosedLoopLumaCoder(0.4, 4, decode="faithful").fused_step                # the reference's scrambled decode crosses tiles
