@@ -61,6 +61,7 @@ struct MeArgs {
     int table_dtype;
     int32_t *zz;
     int och;
+    int win32_off, cur32_off, acand_off, acand_pitch;   // k_me_exact2: float copies of window / blocks, per-warp candidate scores
     double *recon;                         // fused closed-loop step (k_me_exact<double, STEP>): the decoder's reconstruction of the frame
     int work_off;                          // ... byte offset of the warps' WORK buffers in dynamic shared memory
     int32_t *zr_counts;                    // optional: zero-run symbol count and non-zero mask per scan block (see ivc_tile.cuh)
@@ -115,8 +116,11 @@ __device__ __forceinline__ MeTile me_tile(const MeArgs &a) {
 constexpr int kStepWork = 4 * kP3TU * 8;                                      // 4352 B per warp: transposition buffer / scan staging
 constexpr int kStepCurPitch = 66;                                             // == kExactCurPitch (defined below)
 
+// mvs[i * mv_stride] = vector of block blk_first + i; TUB = bytes per u-plane of the transposition buffer (1088 for groups
+// of up to eight blocks, 576 when the caller never passes more than four: WORK is then 3264 bytes)
+template <int TUB>
 __device__ __forceinline__ void pstep_group(const MeArgs &a, const MeTile &tl, const double *s_win, const double *s_cur,
-                                            const int *s_pidx, int blk_first, int nb, FastDiv d_nbx, unsigned char *work_b,
+                                            const int *mvs, int mv_stride, int blk_first, int nb, FastDiv d_nbx, unsigned char *work_b,
                                             const double *s_rt, const double *s_t, const double *s_tT, bool chroma_twice) {
     const int lane = threadIdx.x & 31, r = lane & 7, u = lane >> 3;
     const uint32_t work_s = smem_u32(work_b);
@@ -132,7 +136,7 @@ __device__ __forceinline__ void pstep_group(const MeArgs &a, const MeTile &tl, c
         if (m >= mc) continue;
         const int blk = blk_first + (valid[m] ? bi : 0);
         const int brow = d_nbx.div(blk), b = blk - brow * tl.nbx;
-        const int idx = s_pidx[blk * 32];                                     // the block's vector (lane 0's slot after the argmin)
+        const int idx = mvs[(valid[m] ? bi : 0) * mv_stride];                 // the block's vector
         const int dyi = d_span.div(idx), dxi = idx - dyi * a.span;
         wrow[m] = 8 * brow + dyi;
         wcol[m] = 8 * b + dxi;
@@ -149,7 +153,7 @@ __device__ __forceinline__ void pstep_group(const MeArgs &a, const MeTile &tl, c
         if (m < mc) dct2_8(x[m]);
     bulk_wait_read0();                                  // an earlier group's stores have drained WORK
     __syncwarp();
-    unsigned char *t_base = work_b + u * (kP3TU * 8);
+    unsigned char *t_base = work_b + u * TUB;
 #pragma unroll
     for (int m = 0; m < 2; ++m)
         if (m < mc) {
@@ -418,8 +422,241 @@ __global__ void __launch_bounds__(kMeThreads, 2) k_me_exact(const MeArgs a) {
         __syncwarp();
         unsigned char *work_b = smem_raw + a.work_off + warp * kStepWork;
         for (int k0 = 0; k0 < nb_w; k0 += 8)
-            pstep_group(a, tl, reinterpret_cast<const double *>(s_win), reinterpret_cast<const double *>(s_cur), s_pidx, blk0 + k0,
-                        min(8, nb_w - k0), d_nbx, work_b, s_qt, s_qt + 192, s_qt + 384, chroma_twice);
+            pstep_group<kP3TU * 8>(a, tl, reinterpret_cast<const double *>(s_win), reinterpret_cast<const double *>(s_cur),
+                                   s_pidx + (blk0 + k0) * 32, 32, blk0 + k0, min(8, nb_w - k0), d_nbx, work_b, s_qt, s_qt + 192,
+                                   s_qt + 384, chroma_twice);
+        bulk_wait_all0();
+    }
+}
+
+// ================================================================================================
+// exact search, second generation (float64 frames): float32 prefilter, exact evaluation of the survivors
+// ================================================================================================
+// The vector of a block is the FIRST strict minimum of the exactly rounded SSDs (motion.py:35-51) -- but almost every
+// candidate loses by a margin no rounding can bridge.  A float32 pass scores all candidates (one subtract and one fused
+// multiply-add per pixel on the FP32 pipe, a third of the issue cost of the three rounded FP64 operations), with a
+// rigorous bound on its error: for |values| <= M, |A - S| <= 1031 u M^2 + 64 u A with u = 2^-24 (conversion of both
+// operands, the rounded difference, its square, the accumulation); the kernel uses twice that.  A candidate can only win
+// or tie if A - eps(A) <= min over candidates of (A + eps(A)); typically one or two survive.  The survivors -- all
+// in-frame candidates if the tile holds NaN / Inf / absurd magnitudes -- are evaluated exactly, in numpy's own order, eight
+// lanes per candidate: lane j is numpy's column accumulator j (rows in order), three shuffles are its pairwise tree.
+// Ascending candidate order and a strict "<" reproduce the reference loop.  With STEP the warp then codes and
+// reconstructs its blocks (see pstep_group).
+constexpr int kX2CurPitch32 = 68;                                             // floats per block copy: 64 + 4 (rows stay 16-byte aligned)
+constexpr int kX2Work = 4 * kStageUF * 4;                                     // 3264 B per warp: groups of four blocks
+constexpr int kX2MaxCand = 33 * 33;
+
+// CSPAN / CP: compile-time search span and window pitch (0 = take them from the arguments): with constants every row
+// offset of the unrolled loops is an immediate and the index divisions are multiply-shifts
+template <bool STEP, int CSPAN = 0, int CP = 0>
+__global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exact2(const MeArgs a) {
+    if (a.flag && *a.flag != a.run_if) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double s_qt[STEP ? 448 : 1];              // STEP: fl(1/t) [192], t [192], luminance table transposed [64]
+    __shared__ double s_red[kMeWarps];
+    __shared__ int s_mvw[kMeWarps][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    bool chroma_twice = false;
+    if (STEP) {
+        if (tid < 192) {
+            const double t = load_table_elem(a.table, a.table_dtype, tid);
+            s_qt[192 + tid] = t;
+            s_qt[tid] = __drcp_rn(t);
+            if (tid < 64) s_qt[384 + (tid & 7) * 8 + (tid >> 3)] = t;
+        }
+        bool same = true;
+        if (tid < 64)
+            same = __double_as_longlong(load_table_elem(a.table, a.table_dtype, 64 + tid)) ==
+                   __double_as_longlong(load_table_elem(a.table, a.table_dtype, 128 + tid));
+        chroma_twice = __syncthreads_and(same) != 0;
+    }
+    double *s_win = reinterpret_cast<double *>(smem_raw);                     // [R][P]
+    double *s_cur = reinterpret_cast<double *>(smem_raw + a.cur_off);         // [tby*tbx][kExactCurPitch]
+    float *s_win32 = reinterpret_cast<float *>(smem_raw + a.win32_off);       // [R][P]
+    float *s_cur32 = reinterpret_cast<float *>(smem_raw + a.cur32_off);       // [tby*tbx][kX2CurPitch32]
+    float *s_A = reinterpret_cast<float *>(smem_raw + a.acand_off) + warp * a.acand_pitch;   // this warp's candidate scores
+    using R_ = Rn<double>;
+    const MeTile tl = me_tile(a);
+    const double *ref = (const double *)a.ref + tl.frame * a.ref_fs;
+    const double *cur = (const double *)a.cur + tl.frame * a.cur_fs;
+    const int sr = a.sr, span = CSPAN ? CSPAN : a.span, P = CP ? CP : a.P, ncand = span * span;
+    const int ntpb = CSPAN ? ((CSPAN + kMeG - 1) / kMeG) * CSPAN : a.ntpb;
+    const auto div_span = [&](int x) { return CSPAN ? x / (CSPAN ? CSPAN : 1) : FastDiv(a.m_span).div(x); };
+
+    // ---- stage window and current blocks (float64, zero outside the frame), all copies in flight at once ----
+    const int rows_used = 8 * tl.nby + 2 * sr;
+    const uint32_t win_s = (uint32_t)__cvta_generic_to_shared(s_win), cur_s = (uint32_t)__cvta_generic_to_shared(s_cur);
+    for (int row = warp; row < a.R; row += kMeWarps) {
+        const int64_t gy = (int64_t)8 * tl.by0 - sr + row;
+        const bool row_ok = row < rows_used && gy >= 0 && gy < a.H;
+        const double *rp = ref + (row_ok ? gy : 0) * a.W;
+        for (int col = lane; col < a.Wc; col += 32) {
+            const int64_t gx = (int64_t)8 * tl.bx0 - sr + col;
+            const bool ok = row_ok && gx >= 0 && gx < a.W;
+            cp_async_zfill<8>(win_s + (uint32_t)(row * P + col) * 8u, ok ? rp + gx : ref, ok);
+        }
+    }
+    const int cw = 8 * tl.nbx;
+    for (int row = warp; row < 8 * tl.nby; row += kMeWarps) {
+        const double *cp = cur + ((int64_t)8 * tl.by0 + row) * a.W + 8 * tl.bx0;
+        for (int col = lane; col < cw; col += 32)
+            cp_async_zfill<8>(cur_s + (uint32_t)(((row >> 3) * a.tbx + (col >> 3)) * kExactCurPitch + (row & 7) * 8 + (col & 7)) * 8u, cp + col, true);
+    }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    // ---- float copies, and M = max |value| of the tile (NaN shows up as "not below infinity") ----
+    double mabs = 0.0;
+    bool wild = false;
+    for (int row = warp; row < a.R; row += kMeWarps)
+        for (int col = lane; col < a.Wc; col += 32) {
+            const double v = s_win[row * P + col];
+            s_win32[row * P + col] = (float)v;
+            mabs = fmax(mabs, fabs(v));
+            wild |= !(fabs(v) < 1e15);
+        }
+    for (int row = warp; row < 8 * tl.nby; row += kMeWarps)
+        for (int col = lane; col < cw; col += 32) {
+            const int o = (row >> 3) * a.tbx + (col >> 3), e = (row & 7) * 8 + (col & 7);
+            const double v = s_cur[o * kExactCurPitch + e];
+            s_cur32[o * kX2CurPitch32 + e] = (float)v;
+            mabs = fmax(mabs, fabs(v));
+            wild |= !(fabs(v) < 1e15);
+        }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mabs = fmax(mabs, __shfl_xor_sync(0xffffffffu, mabs, off));
+    if (lane == 0) s_red[warp] = mabs;
+    const bool any_wild = __syncthreads_or(wild) != 0;
+    mabs = s_red[0];
+#pragma unroll
+    for (int w = 1; w < kMeWarps; ++w) mabs = fmax(mabs, s_red[w]);
+    const bool fallback = any_wild || mabs < 1e-12;          // no usable error bound: every in-frame candidate is a survivor
+    // eps(A) = e0 + ek * A, twice the proven bound (1031 u M^2 + 64 u A, u = 2^-24), evaluated a little upwards
+    const float e0 = (float)(mabs * mabs * (2200.0 / 16777216.0) * 1.001), ek = 160.0f / 16777216.0f;
+
+    const int center = sr * span + sr;
+    const int nblk = tl.nby * tl.nbx;
+    const int per_w = (nblk + kMeWarps - 1) / kMeWarps, blk0 = warp * per_w;        // blocks blk0 .. blk0+nb_w-1 (per_w <= 8)
+    const int nb_w = max(0, min(per_w, nblk - blk0));
+    const FastDiv d_nbx(a.m_nbx[tl.nbx != a.tbx]);
+    const int g8 = lane >> 3, j8 = lane & 7;
+    const float FINF = __int_as_float(0x7f800000);
+    const double DINF = Inf<double>::v();
+
+    for (int k = 0; k < nb_w; ++k) {
+        const int blk = blk0 + k, brow = d_nbx.div(blk), b = blk - brow * tl.nbx;
+        const int slot = brow * a.tbx + b;
+        const int gy0 = 8 * (tl.by0 + brow) - sr, gx0 = 8 * (tl.bx0 + b) - sr;       // frame position of candidate (0, 0)
+        float thr = FINF;
+        if (!fallback) {
+            // ---- float32 scores: a task = three vertically adjacent candidates sharing their window rows ----
+            const float *cb32 = s_cur32 + slot * kX2CurPitch32;
+            for (int tt = lane; tt < ntpb; tt += 32) {
+                const int g = div_span(tt), dxi = tt - g * span, dy0 = g * kMeG;
+                const int gx = gx0 + dxi;
+                const bool x_ok = gx >= 0 && gx + 8 <= a.W;
+                float acc[kMeG][2];
+#pragma unroll
+                for (int gg = 0; gg < kMeG; ++gg) acc[gg][0] = acc[gg][1] = 0.0f;
+                const float *wp = s_win32 + (8 * brow + dy0) * P + 8 * b + dxi;
+                float crow[3][8];
+#pragma unroll
+                for (int rr = 0; rr < kMeG + 7; ++rr) {
+                    if (rr < 8) {
+                        const float4 c0 = *reinterpret_cast<const float4 *>(cb32 + rr * 8), c1 = *reinterpret_cast<const float4 *>(cb32 + rr * 8 + 4);
+                        float *cr = crow[rr % 3];
+                        cr[0] = c0.x; cr[1] = c0.y; cr[2] = c0.z; cr[3] = c0.w; cr[4] = c1.x; cr[5] = c1.y; cr[6] = c1.z; cr[7] = c1.w;
+                    }
+                    float rv[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) rv[j] = wp[rr * P + j];
+#pragma unroll
+                    for (int gg = 0; gg < kMeG; ++gg) {
+                        const int i = rr - gg;                                 // row of the block for candidate gg
+                        if (i >= 0 && i < 8) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float d = __fsub_rn(crow[i % 3][j], rv[j]);
+                                acc[gg][j & 1] = __fmaf_rn(d, d, acc[gg][j & 1]);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int gg = 0; gg < kMeG; ++gg) {
+                    const int dyi = dy0 + gg, gy = gy0 + dyi;
+                    if (dyi < span) {
+                        const bool ok = x_ok && gy >= 0 && gy + 8 <= a.H;             // motion.py:41-43
+                        const float sc = __fadd_rn(acc[gg][0], acc[gg][1]);
+                        s_A[dyi * span + dxi] = ok ? sc : -1.0f;                      // scores are >= 0: -1 marks "outside the frame"
+                        if (ok) thr = fminf(thr, __fmaf_rn(ek, sc, sc) + e0);
+                    }
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) thr = fminf(thr, __shfl_xor_sync(0xffffffffu, thr, off));
+            __syncwarp();
+        }
+        // ---- survivors, in ascending candidate order, four at a time: exact SSD in numpy's order ----
+        double best = DINF;
+        int bidx = center;
+        const double *cb = s_cur + slot * kExactCurPitch + j8;                        // column j8 of the block
+        for (int base = 0; base < ncand; base += 32) {
+            const int c = base + lane;
+            bool surv = false;
+            if (c < ncand) {
+                if (fallback) {
+                    const int dyi = div_span(c), dxi = c - dyi * span;
+                    surv = gy0 + dyi >= 0 && gy0 + dyi + 8 <= a.H && gx0 + dxi >= 0 && gx0 + dxi + 8 <= a.W;
+                } else {
+                    const float sc = s_A[c];
+                    surv = sc >= 0.0f && (sc - (__fmaf_rn(ek, sc, e0))) <= thr;
+                }
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, surv);
+            while (mask) {
+                int mine = -1;                                                    // the candidate of this lane's group of eight
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (mask) {
+                        const int bit = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        if (g == g8) mine = base + bit;
+                    }
+                }
+                double acc = DINF;
+                if (mine >= 0) {
+                    const int dyi = div_span(mine), dxi = mine - dyi * span;
+                    const double *wp = s_win + (8 * brow + dyi) * P + 8 * b + dxi + j8;
+                    acc = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {                                 // r[j] += d**2, rows in order
+                        const double d = R_::sub(cb[i * 8], wp[i * P]);
+                        acc = R_::add(acc, R_::mul(d, d));
+                    }
+                }
+                acc = R_::add(acc, __shfl_xor_sync(0xffffffffu, acc, 1));        // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7))
+                acc = R_::add(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
+                acc = R_::add(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const double sg = __shfl_sync(0xffffffffu, acc, 8 * g);
+                    const int ig = __shfl_sync(0xffffffffu, mine, 8 * g);
+                    if (ig >= 0 && sg < best) { best = sg; bidx = ig; }           // ascending order: strict < (motion.py:48)
+                }
+            }
+        }
+        if (lane == 0) {
+            a.mv[(tl.frame * a.Hp + tl.by0 + brow) * (int64_t)a.Wp + tl.bx0 + b] = bidx;
+            s_mvw[warp][k] = bidx;
+        }
+        __syncwarp();
+    }
+    if constexpr (STEP) {
+        unsigned char *work_b = smem_raw + a.work_off + warp * kX2Work;
+        for (int k0 = 0; k0 < nb_w; k0 += 4)
+            pstep_group<576>(a, tl, s_win, s_cur, &s_mvw[warp][k0], 1, blk0 + k0, min(4, nb_w - k0), d_nbx, work_b, s_qt, s_qt + 192,
+                             s_qt + 384, chroma_twice);
         bulk_wait_all0();
     }
 }
@@ -1332,6 +1569,45 @@ static cudaError_t me_launch_chunks(K kernel, MeArgs a, int elem, size_t smem, c
     return cudaGetLastError();
 }
 
+// shared-memory layout of k_me_exact2 on top of me_geometry's (window + blocks in float64): float copies, per-warp
+// candidate scores, and -- for the fused step -- one WORK buffer per warp
+static size_t me_geometry2(MeArgs &a, int64_t n_frames, int64_t H, int64_t W, int sr, size_t budget, int64_t min_ctas, bool step) {
+    a.Hp = (int)(H / 8); a.Wp = (int)(W / 8); a.sr = sr; a.span = 2 * sr + 1;
+    a.ngrp = (a.span + kMeG - 1) / kMeG;
+    a.ntpb = a.ngrp * a.span;
+    static const int shapes[][2] = {{4, 16}, {2, 16}, {2, 8}, {1, 8}, {1, 4}, {1, 2}, {1, 1}};
+    size_t smem = 0;
+    if (const char *env = getenv("IVC_ME_MIN_CTAS")) min_ctas = atoll(env);          // developer override
+    for (auto &s : shapes) {
+        a.tby = s[0]; a.tbx = s[1];
+        const int64_t ctas = n_frames * ((a.Hp + a.tby - 1) / a.tby) * (int64_t)((a.Wp + a.tbx - 1) / a.tbx);
+        if (ctas < min_ctas && !(s[0] == 1 && s[1] == 1) && s[0] * s[1] > 8) continue;
+        a.R = 8 * (a.tby - 1) + a.ngrp * kMeG + 7;                 // >= 8*tby + 2*sr, covers the last dy-group
+        a.Wc = 8 * a.tbx + 2 * sr;
+        a.P = ((a.Wc + 31) / 32) * 32 + 3;                         // == 3 (mod 32): the dy-groups of a warp on disjoint banks
+        const size_t win = (size_t)a.R * a.P, blocks = (size_t)a.tby * a.tbx;
+        a.cur_off = (int)((win * 8 + 15) & ~(size_t)15);
+        a.win32_off = (int)((a.cur_off + blocks * kExactCurPitch * 8 + 15) & ~(size_t)15);
+        a.cur32_off = (int)((a.win32_off + win * 4 + 15) & ~(size_t)15);
+        a.acand_off = (int)((a.cur32_off + blocks * kX2CurPitch32 * 4 + 15) & ~(size_t)15);
+        a.acand_pitch = (a.span * a.span + 3) & ~3;
+        smem = (size_t)a.acand_off + (size_t)kMeWarps * a.acand_pitch * 4;
+        a.work_off = (int)((smem + 127) & ~(size_t)127);
+        if (step) smem = (size_t)a.work_off + (size_t)kMeWarps * kX2Work;
+        if (smem <= budget) break;
+    }
+    a.tiles_y = (a.Hp + a.tby - 1) / a.tby;
+    a.tiles_x = (a.Wp + a.tbx - 1) / a.tbx;
+    a.m_ntpb = fastdiv_magic(a.ntpb); a.m_span = fastdiv_magic(a.span);
+    a.m_nbx[0] = fastdiv_magic(a.tbx); a.m_nbx[1] = fastdiv_magic(a.Wp - (a.tiles_x - 1) * a.tbx);
+    return smem;
+}
+
+static bool me_exact_v1() {          // A/B switch: IVC_ME_EXACT_V1=1 selects the first-generation exact kernel (every candidate in FP64)
+    const char *e = getenv("IVC_ME_EXACT_V1");
+    return e && e[0] == '1';
+}
+
 // The fused closed-loop step (decode = "luma"): exact search, then the warp codes and reconstructs its own blocks.
 cudaError_t launch_pframe_step(int device, cudaStream_t st, const void *ref, const void *cur, int64_t n, int64_t H, int64_t W,
                                int sr, const void *table, int table_dtype, int out_channels, int64_t *mv, int32_t *zz,
@@ -1341,8 +1617,15 @@ cudaError_t launch_pframe_step(int device, cudaStream_t st, const void *ref, con
     a.flag = nullptr; a.run_if = 0; a.check = 0;
     a.table = table; a.table_dtype = table_dtype; a.zz = zz; a.och = out_channels; a.recon = recon;
     a.zr_counts = nullptr; a.zr_masks = nullptr;
+    if (n > 65535) return cudaErrorInvalidValue;                               // one launch: y = frame
+    if (2 * sr + 1 <= 33 && !me_exact_v1()) {
+        const size_t smem2 = me_geometry2(a, n, H, W, sr, 113 * 1024, 2 * 2 * (int64_t)sm_count(device), true);
+        if (smem2 <= 227 * 1024)
+            return (a.span == 9 && a.P == 163) ? me_launch_chunks(k_me_exact2<true, 9, 163>, a, 8, smem2, st)
+                                              : me_launch_chunks(k_me_exact2<true>, a, 8, smem2, st);
+    }
     const size_t smem = me_geometry(a, n, H, W, sr, 8, 32, 3, 113 * 1024, 2 * 2 * (int64_t)sm_count(device), kStepWork);
-    if (smem > 227 * 1024 || n > 65535) return cudaErrorInvalidValue;          // one launch: y = frame
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
     return me_launch_chunks(k_me_exact<double, true>, a, 8, smem, st);
 }
 
@@ -1352,6 +1635,12 @@ cudaError_t launch_me_exact(int device, cudaStream_t st, const void *ref, const 
     MeArgs a;
     a.ref = ref; a.cur = cur; a.n = n; a.H = H; a.W = W; a.ref_fs = ref_fs; a.cur_fs = cur_fs; a.mv = mv;
     a.flag = flag; a.run_if = run_if; a.check = 0;
+    if (!f32 && 2 * sr + 1 <= 33 && !me_exact_v1()) {                       // float64 frames: prefilter + exact survivors
+        const size_t smem2 = me_geometry2(a, n, H, W, sr, 113 * 1024, 2 * 2 * (int64_t)sm_count(device), false);
+        if (smem2 <= 227 * 1024)
+            return (a.span == 9 && a.P == 163) ? me_launch_chunks(k_me_exact2<false, 9, 163>, a, 8, smem2, st)
+                                              : me_launch_chunks(k_me_exact2<false>, a, 8, smem2, st);
+    }
     const size_t smem = me_geometry(a, n, H, W, sr, f32 ? 4 : 8, 32, 3, 113 * 1024, 2 * 2 * (int64_t)sm_count(device));
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     (void)device;
