@@ -564,3 +564,41 @@ def test_closed_loop_fused_step_equals_three_kernels_and_oracle(monkeypatch):
         for k in ("zz", "mv", "recon"):
             assert np.array_equal(lock[k][i], one[k]), (i, k)
     assert not ivc.ClosedLoopLumaCoder(0.4, 4, decode="faithful").fused_step                # the reference's scrambled decode crosses tiles
+
+
+# ---------------------------------------------------------------- exact search with the float32 prefilter: adversarial inputs
+def test_exact_search_prefilter_adversarial_magnitudes_and_ties():
+    """k_me_exact2 keeps a candidate unless float32 PROVES it loses; the vectors must equal the oracle's on inputs built to
+    sit inside, at and beyond the error bound: candidates that differ by far less than float32 resolves, huge / tiny /
+    negative magnitudes, NaN and Inf (no bound: every candidate is evaluated exactly), flat frames (all ties)."""
+    rng = np.random.default_rng(42)
+    base = O.moving_sequence(900, 2, 72, 136)
+    mc = ivc.MotionCompensator(4, me_mode="exact")
+
+    def check(ref, cur, sr=4, tag=""):
+        got = ivc.MotionCompensator(sr, me_mode="exact").compute_motion_vector(ref, cur)
+        assert np.array_equal(got, CO.me_full_search(ref, cur, sr, threads=8)), tag
+    check(base[0] + 0.25, base[1], tag="plain")
+    # periodic texture: many candidates with SSDs that agree to ~1e-9 relative (float32 cannot tell them apart)
+    yy, xx = np.mgrid[0:72, 0:136]
+    per = 128 + 100 * np.sin(2 * np.pi * xx / 4) * np.sin(2 * np.pi * yy / 4)
+    check(per + 1e-7 * rng.normal(size=per.shape), per + 1e-7 * rng.normal(size=per.shape), tag="periodic 1e-7")
+    check(per + 1e-11 * rng.normal(size=per.shape), per, tag="periodic 1e-11")
+    check(per, per, tag="periodic exact ties")
+    for scale in (1e-9, 1e-3, 1e3, 1e6, 3e14, 5e15, 1e30, 1e200):                   # 5e15 and beyond: no bound -> exact for all
+        check((base[0] + 0.25) * scale, base[1] * scale, tag=f"scale {scale}")
+    check(base[0] - 1000.0, base[1] - 1000.0 + 0.5, tag="negative offset")
+    check(np.zeros((40, 56)), np.zeros((40, 56)), tag="zeros")
+    check(np.full((40, 56), 1e-300), np.full((40, 56), 3e-300), tag="denormal-ish")
+    for bad in (np.nan, np.inf, -np.inf):
+        r, c = base[0] + 0.25, base[1].copy()
+        r[10, 20] = bad
+        c[50, 100] = bad
+        check(r, c, tag=f"{bad} pixels")
+    r = base[0] + 0.25
+    r[::7, ::5] = 4e14                                                           # a few huge pixels next to ordinary ones
+    check(r, base[1], tag="mixed magnitudes")
+    for sr in (1, 2, 7, 16):
+        check(base[0] + rng.normal(0, 0.3, base[0].shape), base[1], sr=sr, tag=f"sr {sr}")
+    big = O.moving_sequence(901, 2, 264, 520)
+    check(big[0] + rng.normal(0, 0.3, big[0].shape), big[1], tag="larger frame")
