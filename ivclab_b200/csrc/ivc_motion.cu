@@ -24,6 +24,7 @@
 // exits immediately unless the flag was raised -- no host round trip, no workspace beyond the 4-byte flag.
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 #include "ivc_dct.cuh"
 #include "ivc_common.cuh"
 #include "ivc_tile.cuh"
@@ -61,7 +62,7 @@ struct MeArgs {
     int table_dtype;
     int32_t *zz;
     int och;
-    int win32_off, cur32_off, acand_off, acand_pitch;   // k_me_exact2: float copies of window / blocks, per-warp candidate scores
+    int win32_off, cur32_off, acand_off, acand_pitch;   // k_me_exact2: unaligned-word view (packed rows at b_off), quantised blocks, per-warp candidate scores
     double *recon;                         // fused closed-loop step (k_me_exact<double, STEP>): the decoder's reconstruction of the frame
     int work_off;                          // ... byte offset of the warps' WORK buffers in dynamic shared memory
     int32_t *zr_counts;                    // optional: zero-run symbol count and non-zero mask per scan block (see ivc_tile.cuh)
@@ -430,21 +431,44 @@ __global__ void __launch_bounds__(kMeThreads, 2) k_me_exact(const MeArgs a) {
 }
 
 // ================================================================================================
-// exact search, second generation (float64 frames): float32 prefilter, exact evaluation of the survivors
+// exact search, second generation (float64 frames): 8-bit prefilter, exact evaluation of the survivors
 // ================================================================================================
 // The vector of a block is the FIRST strict minimum of the exactly rounded SSDs (motion.py:35-51) -- but almost every
-// candidate loses by a margin no rounding can bridge.  A float32 pass scores all candidates (one subtract and one fused
-// multiply-add per pixel on the FP32 pipe, a third of the issue cost of the three rounded FP64 operations), with a
-// rigorous bound on its error: for |values| <= M, |A - S| <= 1031 u M^2 + 64 u A with u = 2^-24 (conversion of both
-// operands, the rounded difference, its square, the accumulation); the kernel uses twice that.  A candidate can only win
-// or tie if A - eps(A) <= min over candidates of (A + eps(A)); typically one or two survive.  The survivors -- all
-// in-frame candidates if the tile holds NaN / Inf / absurd magnitudes -- are evaluated exactly, in numpy's own order, eight
-// lanes per candidate: lane j is numpy's column accumulator j (rows in order), three shuffles are its pairwise tree.
-// Ascending candidate order and a strict "<" reproduce the reference loop.  With STEP the warp then codes and
-// reconstructs its blocks (see pstep_group).
-constexpr int kX2CurPitch32 = 68;                                             // floats per block copy: 64 + 4 (rows stay 16-byte aligned)
+// candidate loses by a margin no rounding can bridge.  The tile is quantised to bytes with ITS OWN affine map
+// v' = (v - lo) / q (1 / q an integer whenever the tile spans 1 .. 255, so integer-valued frames are quantised exactly),
+// delta = the largest rounding error actually made on the window plus the largest on the blocks; the packed-byte
+// machinery of the integer search (unaligned-word view, vabsdiff4 + dp4a: two instructions per four pixels) scores
+// every candidate with S~ = sum of squared byte differences, and in quantised units
+//     |S' - S~| <= 2 delta sum|d~| + 64 delta^2 <= 16 delta sqrt(S~) + 64 delta^2 =: eps(S~)       (Cauchy-Schwarz)
+// where S' = S / q^2 is the real SSD.  A candidate can only win or tie if S~ - eps(S~) <= min (S~ + eps(S~)); typically
+// one or two survive (on integer-valued frames delta = 0 and only exact ties do).  The survivors -- all in-frame
+// candidates if the tile holds NaN / Inf or is flat -- are evaluated exactly, in numpy's own order, eight lanes per
+// candidate: lane j is numpy's column accumulator j (rows in order), three shuffles are its pairwise tree.  Ascending
+// candidate order and a strict "<" reproduce the reference loop.  With STEP the warp then codes and reconstructs its
+// blocks (see pstep_group).
+constexpr int kCurPitch = 18;      // words per current block in shared memory (16 + 2: blocks on distinct banks)
 constexpr int kX2Work = 4 * kStageUF * 4;                                     // 3264 B per warp: groups of four blocks
-constexpr int kX2MaxCand = 33 * 33;
+
+// four values -> one word of bytes under the map x = (v - lo) * inv_q (GEN) or the identity; flags |= 1 if a value leaves
+// [0, 255] (NaN and Inf do), |= nonint_bit if a value is not an integer after the map; nmin / nmax track the bytes
+template <bool GEN>
+__device__ __forceinline__ unsigned x2_quant4(const double *p, int cnt, double lo, double inv_q, unsigned &flags, unsigned nonint_bit,
+                                              unsigned &nmin, unsigned &nmax) {
+    unsigned w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < cnt) {
+            const double x = GEN ? __dmul_rn(__dsub_rn(p[k], lo), inv_q) : p[k];
+            const double sft = __dadd_rn(x, 4503599627370496.0);              // 2^52: rint(x) in the low mantissa word
+            const unsigned n = (unsigned)__double2loint(sft);
+            if (__double2hiint(sft) != 0x43300000 || n > 255u) flags |= 1u;
+            if (__dadd_rn(sft, -4503599627370496.0) != x) flags |= nonint_bit;
+            nmin = min(nmin, n); nmax = max(nmax, n);
+            w |= (n & 255u) << (8 * k);
+        }
+    }
+    return w;
+}
 
 // CSPAN / CP: compile-time search span and window pitch (0 = take them from the arguments): with constants every row
 // offset of the unrolled loops is an immediate and the index divisions are multiply-shifts
@@ -453,7 +477,7 @@ __global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exa
     if (a.flag && *a.flag != a.run_if) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double s_qt[STEP ? 448 : 1];              // STEP: fl(1/t) [192], t [192], luminance table transposed [64]
-    __shared__ double s_red[kMeWarps];
+    __shared__ unsigned s_redi[3][kMeWarps];
     __shared__ int s_mvw[kMeWarps][8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     bool chroma_twice = false;
@@ -472,8 +496,9 @@ __global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exa
     }
     double *s_win = reinterpret_cast<double *>(smem_raw);                     // [R][P]
     double *s_cur = reinterpret_cast<double *>(smem_raw + a.cur_off);         // [tby*tbx][kExactCurPitch]
-    float *s_win32 = reinterpret_cast<float *>(smem_raw + a.win32_off);       // [R][P]
-    float *s_cur32 = reinterpret_cast<float *>(smem_raw + a.cur32_off);       // [tby*tbx][kX2CurPitch32]
+    unsigned *s_u = reinterpret_cast<unsigned *>(smem_raw + a.win32_off);     // [R][PU]  unaligned-word view of the quantised window
+    unsigned *s_b8 = reinterpret_cast<unsigned *>(smem_raw + a.b_off);        // [R][PW]  packed quantised window
+    unsigned *s_c8 = reinterpret_cast<unsigned *>(smem_raw + a.cur32_off);    // [tby*tbx][kCurPitch] quantised blocks
     float *s_A = reinterpret_cast<float *>(smem_raw + a.acand_off) + warp * a.acand_pitch;   // this warp's candidate scores
     using R_ = Rn<double>;
     const MeTile tl = me_tile(a);
@@ -505,34 +530,97 @@ __global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exa
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
-    // ---- float copies, and M = max |value| of the tile (NaN shows up as "not below infinity") ----
-    double mabs = 0.0;
-    bool wild = false;
-    for (int row = warp; row < a.R; row += kMeWarps)
-        for (int col = lane; col < a.Wc; col += 32) {
-            const double v = s_win[row * P + col];
-            s_win32[row * P + col] = (float)v;
-            mabs = fmax(mabs, fabs(v));
-            wild |= !(fabs(v) < 1e15);
+    // ---- quantise.  First guess: the identity map (lo = 0, q = 1) -- right for anything that looks like an 8-bit frame ----
+    const int PW = a.pw, PU = a.pwl;                                          // words per packed row / per row of the unaligned view
+    const int wpr = (a.Wc + 3) >> 2, cwpr = 2 * tl.nbx;                       // words per window row / per row of blocks
+    const FastDiv d_wpr(a.m_pwl);
+    const int nblk_all = tl.nby * tl.nbx;
+    const auto quant_tile = [&](auto gen_tag, double lo, double inv_q, unsigned &flags, unsigned &nmin, unsigned &nmax) {
+        constexpr bool GEN = decltype(gen_tag)::value;
+        for (int idx = tid; idx < a.R * wpr; idx += kMeThreads) {
+            const int row = d_wpr.div(idx), w = idx - row * wpr;
+            s_b8[row * PW + w] = x2_quant4<GEN>(s_win + row * P + 4 * w, a.Wc - 4 * w, lo, inv_q, flags, 2u, nmin, nmax);
         }
-    for (int row = warp; row < 8 * tl.nby; row += kMeWarps)
-        for (int col = lane; col < cw; col += 32) {
-            const int o = (row >> 3) * a.tbx + (col >> 3), e = (row & 7) * 8 + (col & 7);
-            const double v = s_cur[o * kExactCurPitch + e];
-            s_cur32[o * kX2CurPitch32 + e] = (float)v;
-            mabs = fmax(mabs, fabs(v));
-            wild |= !(fabs(v) < 1e15);
+        for (int idx = tid; idx < 8 * tl.nby * cwpr; idx += kMeThreads) {
+            const int row = idx / cwpr, w = idx - row * cwpr, o = (row >> 3) * a.tbx + (w >> 1);
+            s_c8[o * kCurPitch + (row & 7) * 2 + (w & 1)] =
+                x2_quant4<GEN>(s_cur + o * kExactCurPitch + (row & 7) * 8 + (w & 1) * 4, 4, lo, inv_q, flags, 4u, nmin, nmax);
         }
+        for (int idx = tid; idx < a.R * 2; idx += kMeThreads) s_b8[(idx >> 1) * PW + wpr + (idx & 1)] = 0u;   // the spare words
+    };
+    // flags: 1 = a value left [0, 255] (or is NaN / Inf), 2 / 4 = the window / the blocks hold a non-integer (after the map)
+    const auto tile_reduce = [&](unsigned &flags, unsigned &nmin, unsigned &nmax) {
+        flags = __reduce_or_sync(0xffffffffu, flags);
+        nmin = __reduce_min_sync(0xffffffffu, nmin);
+        nmax = __reduce_max_sync(0xffffffffu, nmax);
+        if (lane == 0) { s_redi[0][warp] = flags; s_redi[1][warp] = nmin; s_redi[2][warp] = nmax; }
+        __syncthreads();
+        flags = 0u; nmin = 0xffffffffu; nmax = 0u;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) mabs = fmax(mabs, __shfl_xor_sync(0xffffffffu, mabs, off));
-    if (lane == 0) s_red[warp] = mabs;
-    const bool any_wild = __syncthreads_or(wild) != 0;
-    mabs = s_red[0];
-#pragma unroll
-    for (int w = 1; w < kMeWarps; ++w) mabs = fmax(mabs, s_red[w]);
-    const bool fallback = any_wild || mabs < 1e-12;          // no usable error bound: every in-frame candidate is a survivor
-    // eps(A) = e0 + ek * A, twice the proven bound (1031 u M^2 + 64 u A, u = 2^-24), evaluated a little upwards
-    const float e0 = (float)(mabs * mabs * (2200.0 / 16777216.0) * 1.001), ek = 160.0f / 16777216.0f;
+        for (int w = 0; w < kMeWarps; ++w) { flags |= s_redi[0][w]; nmin = min(nmin, s_redi[1][w]); nmax = max(nmax, s_redi[2][w]); }
+        __syncthreads();                                                      // s_redi is written again below
+    };
+    unsigned flags = 0u, nmin = 0xffffffffu, nmax = 0u;
+    quant_tile(std::false_type{}, 0.0, 1.0, flags, nmin, nmax);
+    tile_reduce(flags, nmin, nmax);
+    bool fallback = false;
+    // the guess is kept unless it failed or resolves the tile poorly (non-integer content on fewer than 48 levels)
+    if ((flags & 1u) || ((flags & 6u) && nmax - nmin < 48u)) {
+        // ---- the tile's own range, from the high words of the doubles (order-preserving integer keys), one step outwards ----
+        int kmin = 0x7fffffff, kmax = (int)0x80000000;
+        const auto track = [&](const double *p) {
+            const int hi = __double2hiint(*p), key = hi ^ ((hi >> 31) & 0x7fffffff);
+            kmin = min(kmin, key); kmax = max(kmax, key);
+        };
+        for (int idx = tid; idx < a.R * a.Wc; idx += kMeThreads) {
+            const int row = FastDiv(a.m_p4).div(idx);
+            track(s_win + row * P + (idx - row * a.Wc));
+        }
+        for (int idx = tid; idx < 64 * nblk_all; idx += kMeThreads) {
+            const int o = idx >> 6, brow_ = o / tl.nbx;
+            track(s_cur + (brow_ * a.tbx + (o - brow_ * tl.nbx)) * kExactCurPitch + (idx & 63));
+        }
+        unsigned ukmin = (unsigned)kmin ^ 0x80000000u, ukmax = (unsigned)kmax ^ 0x80000000u, dummy = 0u;   // biased: unsigned order
+        tile_reduce(dummy, ukmin, ukmax);
+        const auto decode = [](unsigned ukey, int step) {
+            const long long k = (long long)(int)(ukey ^ 0x80000000u) + step;
+            const int key = (int)max(min(k, 0x7fffffffLL), -0x7fffffffLL - 1);
+            return __hiloint2double(key ^ ((key >> 31) & 0x7fffffff), 0);
+        };
+        const double vmin = decode(ukmin, -1), vmax = decode(ukmax, 1);       // vmin <= every value <= vmax
+        const bool wild = !(fabs(vmin) < 1e300) || !(fabs(vmax) < 1e300);     // NaN / Inf (or next to the end of the range)
+        // an INTEGER scale while the tile spans 1 .. 255: integer-valued frames are then quantised exactly
+        const double lo = (vmax - floor(vmin) >= 1.0) ? floor(vmin) : vmin, range = vmax - lo;
+        const double inv_q = (range >= 1.0 && range <= 255.0) ? floor(255.0 / range) : 255.0 / (range * (1.0 + 1e-12));
+        fallback = wild || !(range > 0.0) || !(range < 1e290);                // no usable bound: every in-frame candidate survives
+        if (!fallback) {
+            flags = 0u; nmin = 0xffffffffu; nmax = 0u;
+            quant_tile(std::true_type{}, lo, inv_q, flags, nmin, nmax);
+            tile_reduce(flags, nmin, nmax);
+            fallback = (flags & 1u) != 0u;                                    // cannot happen; if it does the bound is void
+        }
+    }
+    // the unaligned-word view: U[y][x] = bytes x .. x+3 of window row y
+    if (!fallback) {
+        const int q4 = PU >> 2;
+        const FastDiv d_q4(a.m_q4);
+        for (int idx = tid; idx < a.R * q4; idx += kMeThreads) {
+            const int row = d_q4.div(idx), w = idx - row * q4;
+            const unsigned *bp = s_b8 + row * PW + w;                         // PW >= q4 + 2: no guards
+            const unsigned w0 = bp[0], w1 = bp[1];
+            uint4 u;
+            u.x = w0;
+            u.y = __funnelshift_r(w0, w1, 8);
+            u.z = __funnelshift_r(w0, w1, 16);
+            u.w = __funnelshift_r(w0, w1, 24);
+            *reinterpret_cast<uint4 *>(s_u + row * PU + 4 * w) = u;
+        }
+    }
+    __syncthreads();
+    // delta: 0 if both sides are integers after the map, else 1/2 per rounded side (plus the rounding of the map itself)
+    const float delta = ((flags & 2u) ? 0.5f : 0.0f) + ((flags & 4u) ? 0.5f : 0.0f) + ((flags & 6u) ? 1e-6f : 0.0f);
+    // eps(S~) = 16 delta sqrt(S~) + 64 delta^2, a little upwards (the float evaluation and numpy's own rounding of S)
+    const float e16 = 16.0f * delta * 1.001f, e64 = 64.0f * delta * delta * 1.001f + 1e-3f;
 
     const int center = sr * span + sr;
     const int nblk = tl.nby * tl.nbx;
@@ -549,36 +637,29 @@ __global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exa
         const int gy0 = 8 * (tl.by0 + brow) - sr, gx0 = 8 * (tl.bx0 + b) - sr;       // frame position of candidate (0, 0)
         float thr = FINF;
         if (!fallback) {
-            // ---- float32 scores: a task = three vertically adjacent candidates sharing their window rows ----
-            const float *cb32 = s_cur32 + slot * kX2CurPitch32;
+            // ---- byte scores: a task = three vertically adjacent candidates sharing their window rows in registers ----
+            const uint2 *cb8 = reinterpret_cast<const uint2 *>(s_c8 + slot * kCurPitch);
             for (int tt = lane; tt < ntpb; tt += 32) {
                 const int g = div_span(tt), dxi = tt - g * span, dy0 = g * kMeG;
                 const int gx = gx0 + dxi;
                 const bool x_ok = gx >= 0 && gx + 8 <= a.W;
-                float acc[kMeG][2];
+                uint2 c[8];
 #pragma unroll
-                for (int gg = 0; gg < kMeG; ++gg) acc[gg][0] = acc[gg][1] = 0.0f;
-                const float *wp = s_win32 + (8 * brow + dy0) * P + 8 * b + dxi;
-                float crow[3][8];
+                for (int i = 0; i < 8; ++i) c[i] = cb8[i];
+                unsigned acc[kMeG];
+#pragma unroll
+                for (int gg = 0; gg < kMeG; ++gg) acc[gg] = 0u;
+                const unsigned *up = s_u + (8 * brow + dy0) * PU + 8 * b + dxi;
 #pragma unroll
                 for (int rr = 0; rr < kMeG + 7; ++rr) {
-                    if (rr < 8) {
-                        const float4 c0 = *reinterpret_cast<const float4 *>(cb32 + rr * 8), c1 = *reinterpret_cast<const float4 *>(cb32 + rr * 8 + 4);
-                        float *cr = crow[rr % 3];
-                        cr[0] = c0.x; cr[1] = c0.y; cr[2] = c0.z; cr[3] = c0.w; cr[4] = c1.x; cr[5] = c1.y; cr[6] = c1.z; cr[7] = c1.w;
-                    }
-                    float rv[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) rv[j] = wp[rr * P + j];
+                    const unsigned r0 = up[rr * PU], r1 = up[rr * PU + 4];
 #pragma unroll
                     for (int gg = 0; gg < kMeG; ++gg) {
                         const int i = rr - gg;                                 // row of the block for candidate gg
                         if (i >= 0 && i < 8) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float d = __fsub_rn(crow[i % 3][j], rv[j]);
-                                acc[gg][j & 1] = __fmaf_rn(d, d, acc[gg][j & 1]);
-                            }
+                            const unsigned d0 = __vabsdiffu4(c[i].x, r0), d1 = __vabsdiffu4(c[i].y, r1);
+                            acc[gg] = __dp4a(d0, d0, acc[gg]);
+                            acc[gg] = __dp4a(d1, d1, acc[gg]);
                         }
                     }
                 }
@@ -587,9 +668,9 @@ __global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exa
                     const int dyi = dy0 + gg, gy = gy0 + dyi;
                     if (dyi < span) {
                         const bool ok = x_ok && gy >= 0 && gy + 8 <= a.H;             // motion.py:41-43
-                        const float sc = __fadd_rn(acc[gg][0], acc[gg][1]);
+                        const float sc = (float)acc[gg];                              // < 2^23: exact
                         s_A[dyi * span + dxi] = ok ? sc : -1.0f;                      // scores are >= 0: -1 marks "outside the frame"
-                        if (ok) thr = fminf(thr, __fmaf_rn(ek, sc, sc) + e0);
+                        if (ok) thr = fminf(thr, sc + (__fmaf_rn(e16, __fsqrt_ru(sc), e64)));
                     }
                 }
             }
@@ -610,7 +691,7 @@ __global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exa
                     surv = gy0 + dyi >= 0 && gy0 + dyi + 8 <= a.H && gx0 + dxi >= 0 && gx0 + dxi + 8 <= a.W;
                 } else {
                     const float sc = s_A[c];
-                    surv = sc >= 0.0f && (sc - (__fmaf_rn(ek, sc, e0))) <= thr;
+                    surv = sc >= 0.0f && (sc - __fmaf_rn(e16, __fsqrt_ru(sc), e64)) <= thr;
                 }
             }
             unsigned mask = __ballot_sync(0xffffffffu, surv);
@@ -706,7 +787,6 @@ __device__ __forceinline__ unsigned pack_bytes(unsigned b0, unsigned b1, unsigne
 }
 
 constexpr int kMeIntMaxThreads = 512;   // integer kernel, constant-pitch variants: 256..512 threads per CTA (chosen by the launcher), <= 64 registers
-constexpr int kCurPitch = 18;      // words per current block in shared memory (16 + 2: blocks on distinct banks)
 constexpr int kStageUnroll = 4;    // packed words (16 pixel loads) in flight per thread while staging
 
 // 16-byte read-only loads (two doubles / four floats)
@@ -1587,9 +1667,13 @@ static size_t me_geometry2(MeArgs &a, int64_t n_frames, int64_t H, int64_t W, in
         a.P = ((a.Wc + 31) / 32) * 32 + 3;                         // == 3 (mod 32): the dy-groups of a warp on disjoint banks
         const size_t win = (size_t)a.R * a.P, blocks = (size_t)a.tby * a.tbx;
         a.cur_off = (int)((win * 8 + 15) & ~(size_t)15);
-        a.win32_off = (int)((a.cur_off + blocks * kExactCurPitch * 8 + 15) & ~(size_t)15);
-        a.cur32_off = (int)((a.win32_off + win * 4 + 15) & ~(size_t)15);
-        a.acand_off = (int)((a.cur32_off + blocks * kX2CurPitch32 * 4 + 15) & ~(size_t)15);
+        a.pwl = ((a.Wc + 3 - 4 + 31) / 32) * 32 + 4;               // PU: words per row of the unaligned view, == 4 (mod 32): the dy-groups of a warp on disjoint banks
+        a.pw = a.pwl / 4 + 2;                                      // PW: packed words per row, two spare words at the end
+        a.m_q4 = fastdiv_magic(a.pwl / 4); a.m_pwl = fastdiv_magic((a.Wc + 3) / 4); a.m_p4 = fastdiv_magic(a.Wc);
+        a.win32_off = (int)((a.cur_off + blocks * kExactCurPitch * 8 + 15) & ~(size_t)15);       // U view
+        a.b_off = (int)((a.win32_off + (size_t)a.R * a.pwl * 4 + 15) & ~(size_t)15);             // packed window
+        a.cur32_off = (int)((a.b_off + (size_t)a.R * a.pw * 4 + 15) & ~(size_t)15);              // quantised blocks
+        a.acand_off = (int)((a.cur32_off + blocks * kCurPitch * 4 + 15) & ~(size_t)15);
         a.acand_pitch = (a.span * a.span + 3) & ~3;
         smem = (size_t)a.acand_off + (size_t)kMeWarps * a.acand_pitch * 4;
         a.work_off = (int)((smem + 127) & ~(size_t)127);
