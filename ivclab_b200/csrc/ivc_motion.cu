@@ -76,7 +76,8 @@ template <> struct Inf<float> { static __device__ __forceinline__ float v() { re
 template <int BYTES>
 __device__ __forceinline__ void cp_async_zfill(uint32_t dst, const void *src, bool valid) {
     const uint32_t n = valid ? BYTES : 0;
-    if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+    else if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
     else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
 }
 
@@ -434,9 +435,10 @@ __global__ void __launch_bounds__(kMeThreads, 2) k_me_exact(const MeArgs a) {
 // exact search, second generation (float64 frames): 8-bit prefilter, exact evaluation of the survivors
 // ================================================================================================
 // The vector of a block is the FIRST strict minimum of the exactly rounded SSDs (motion.py:35-51) -- but almost every
-// candidate loses by a margin no rounding can bridge.  The tile is quantised to bytes with ITS OWN affine map
-// v' = (v - lo) / q (1 / q an integer whenever the tile spans 1 .. 255, so integer-valued frames are quantised exactly),
-// delta = the largest rounding error actually made on the window plus the largest on the blocks; the packed-byte
+// candidate loses by a margin no rounding can bridge.  The tile is quantised to bytes with an affine map
+// v' = (v - lo) / q -- a fixed first guess that holds an 8-bit frame and its reconstruction's overshoot; if a value leaves
+// it, or the tile spans too few levels, the tile's OWN range (1 / q an integer whenever it spans 1 .. 255, so integer-valued
+// frames are quantised exactly) -- delta = 1/2 for each side that was rounded at all; the packed-byte
 // machinery of the integer search (unaligned-word view, vabsdiff4 + dp4a: two instructions per four pixels) scores
 // every candidate with S~ = sum of squared byte differences, and in quantised units
 //     |S' - S~| <= 2 delta sum|d~| + 64 delta^2 <= 16 delta sqrt(S~) + 64 delta^2 =: eps(S~)       (Cauchy-Schwarz)
@@ -447,23 +449,34 @@ __global__ void __launch_bounds__(kMeThreads, 2) k_me_exact(const MeArgs a) {
 // candidate order and a strict "<" reproduce the reference loop.  With STEP the warp then codes and reconstructs its
 // blocks (see pstep_group).
 constexpr int kCurPitch = 18;      // words per current block in shared memory (16 + 2: blocks on distinct banks)
+constexpr double kX2GuessLo = -64.0, kX2GuessInvQ = 255.0 / 384.0;                 // 85 / 128: exact
 constexpr int kX2Work = 4 * kStageUF * 4;                                     // 3264 B per warp: groups of four blocks
 
-// four values -> one word of bytes under the map x = (v - lo) * inv_q (GEN) or the identity; flags |= 1 if a value leaves
-// [0, 255] (NaN and Inf do), |= nonint_bit if a value is not an integer after the map; nmin / nmax track the bytes
-template <bool GEN>
-__device__ __forceinline__ unsigned x2_quant4(const double *p, int cnt, double lo, double inv_q, unsigned &flags, unsigned nonint_bit,
-                                              unsigned &nmin, unsigned &nmax) {
+// four values -> one word of bytes under the map x = (v - lo) * inv_q.  Everything the tile needs to know about the values
+// is OR-ed / min-maxed into the accumulators and looked at once per tile:
+//   bad     != 0  <=> some x left [0, 255] (NaN and Inf do)
+//   nonint  != 0  <=> some x is not an integer (-0.0 counts as one)
+//   kmin, kmax    (KEYS) order-preserving integer keys of the high words of the VALUES: the tile's range
+struct X2Acc {
+    unsigned bad = 0u, nonint = 0u;
+    int kmin = 0x7fffffff, kmax = (int)0x80000000;
+};
+template <bool KEYS>
+__device__ __forceinline__ unsigned x2_quant4(const double *p, int cnt, double lo, double inv_q, X2Acc &acc) {
     unsigned w = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         if (k < cnt) {
-            const double x = GEN ? __dmul_rn(__dsub_rn(p[k], lo), inv_q) : p[k];
+            const double v = p[k], x = __dmul_rn(__dsub_rn(v, lo), inv_q);
             const double sft = __dadd_rn(x, 4503599627370496.0);              // 2^52: rint(x) in the low mantissa word
+            const double back = __dadd_rn(sft, -4503599627370496.0);
             const unsigned n = (unsigned)__double2loint(sft);
-            if (__double2hiint(sft) != 0x43300000 || n > 255u) flags |= 1u;
-            if (__dadd_rn(sft, -4503599627370496.0) != x) flags |= nonint_bit;
-            nmin = min(nmin, n); nmax = max(nmax, n);
+            acc.bad |= ((unsigned)__double2hiint(sft) ^ 0x43300000u) | (n >> 8);
+            acc.nonint |= ((unsigned)__double2hiint(back) ^ (unsigned)__double2hiint(x)) | ((unsigned)__double2loint(back) ^ (unsigned)__double2loint(x));
+            if (KEYS) {
+                const int hi = __double2hiint(v), key = hi ^ ((hi >> 31) & 0x7fffffff);
+                acc.kmin = min(acc.kmin, key); acc.kmax = max(acc.kmax, key);
+            }
             w |= (n & 255u) << (8 * k);
         }
     }
@@ -478,6 +491,7 @@ __global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exa
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double s_qt[STEP ? 448 : 1];              // STEP: fl(1/t) [192], t [192], luminance table transposed [64]
     __shared__ unsigned s_redi[3][kMeWarps];
+    __shared__ __align__(8) unsigned long long s_bar;
     __shared__ int s_mvw[kMeWarps][8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     bool chroma_twice = false;
@@ -509,94 +523,105 @@ __global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exa
     const auto div_span = [&](int x) { return CSPAN ? x / (CSPAN ? CSPAN : 1) : FastDiv(a.m_span).div(x); };
 
     // ---- stage window and current blocks (float64, zero outside the frame), all copies in flight at once ----
+    // A tile whose window lies inside the frame takes one bulk copy per window row (lanes of warp 0) and 16-byte copies for
+    // the blocks; at the frame's edge (or with an odd range / width) every element is copied -- or zero-filled -- alone.
     const int rows_used = 8 * tl.nby + 2 * sr;
     const uint32_t win_s = (uint32_t)__cvta_generic_to_shared(s_win), cur_s = (uint32_t)__cvta_generic_to_shared(s_cur);
-    for (int row = warp; row < a.R; row += kMeWarps) {
-        const int64_t gy = (int64_t)8 * tl.by0 - sr + row;
-        const bool row_ok = row < rows_used && gy >= 0 && gy < a.H;
-        const double *rp = ref + (row_ok ? gy : 0) * a.W;
-        for (int col = lane; col < a.Wc; col += 32) {
-            const int64_t gx = (int64_t)8 * tl.bx0 - sr + col;
-            const bool ok = row_ok && gx >= 0 && gx < a.W;
-            cp_async_zfill<8>(win_s + (uint32_t)(row * P + col) * 8u, ok ? rp + gx : ref, ok);
+    const int64_t wy0 = (int64_t)8 * tl.by0 - sr, wx0 = (int64_t)8 * tl.bx0 - sr;
+    const int cw = 8 * tl.nbx;
+    const bool pairs = (((sr | a.W) & 1) == 0) && (((reinterpret_cast<uintptr_t>(ref) | reinterpret_cast<uintptr_t>(cur)) & 15) == 0);
+    const bool interior = pairs && wy0 >= 0 && wy0 + a.R <= a.H && wx0 >= 0 && wx0 + a.Wc <= a.W;
+    const uint32_t bar = smem_u32(&s_bar);
+    if (interior) {
+        if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+        __syncthreads();
+        if (warp == 0) {
+            if (lane == 0) mbar_expect_tx(bar, (uint32_t)(a.R * a.Wc * 8));
+            __syncwarp();
+            for (int row = lane; row < a.R; row += 32)
+                bulk_g2s(win_s + (uint32_t)(row * P) * 8u, ref + (wy0 + row) * a.W + wx0, (uint32_t)(a.Wc * 8), bar);
+        }
+    } else {
+        for (int row = warp; row < a.R; row += kMeWarps) {
+            const int64_t gy = wy0 + row;
+            const bool row_ok = row < rows_used && gy >= 0 && gy < a.H;
+            const double *rp = ref + (row_ok ? gy : 0) * a.W;
+            for (int col = lane; col < a.Wc; col += 32) {
+                const int64_t gx = wx0 + col;
+                const bool ok = row_ok && gx >= 0 && gx < a.W;
+                cp_async_zfill<8>(win_s + (uint32_t)(row * P + col) * 8u, ok ? rp + gx : ref, ok);
+            }
         }
     }
-    const int cw = 8 * tl.nbx;
-    for (int row = warp; row < 8 * tl.nby; row += kMeWarps) {
-        const double *cp = cur + ((int64_t)8 * tl.by0 + row) * a.W + 8 * tl.bx0;
-        for (int col = lane; col < cw; col += 32)
-            cp_async_zfill<8>(cur_s + (uint32_t)(((row >> 3) * a.tbx + (col >> 3)) * kExactCurPitch + (row & 7) * 8 + (col & 7)) * 8u, cp + col, true);
+    if (pairs) {
+        const int hw = cw >> 1;                                               // 16-byte pairs per row of blocks
+        for (int idx = tid; idx < 8 * tl.nby * hw; idx += kMeThreads) {
+            const int row = idx / hw, col = 2 * (idx - row * hw);
+            cp_async_zfill<16>(cur_s + (uint32_t)(((row >> 3) * a.tbx + (col >> 3)) * kExactCurPitch + (row & 7) * 8 + (col & 7)) * 8u,
+                               cur + ((int64_t)8 * tl.by0 + row) * a.W + 8 * tl.bx0 + col, true);
+        }
+    } else {
+        for (int row = warp; row < 8 * tl.nby; row += kMeWarps) {
+            const double *cp = cur + ((int64_t)8 * tl.by0 + row) * a.W + 8 * tl.bx0;
+            for (int col = lane; col < cw; col += 32)
+                cp_async_zfill<8>(cur_s + (uint32_t)(((row >> 3) * a.tbx + (col >> 3)) * kExactCurPitch + (row & 7) * 8 + (col & 7)) * 8u, cp + col, true);
+        }
     }
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    if (interior) mbar_wait(bar, 0);
     __syncthreads();
 
-    // ---- quantise.  First guess: the identity map (lo = 0, q = 1) -- right for anything that looks like an 8-bit frame ----
+    // ---- quantise.  First guess: [-64, 320) on 255 levels -- an 8-bit frame or its reconstruction, which overshoots [0, 255]
+    // wherever the content is saturated (on the bench sequences 97 % of the tiles hold such a value) ----
     const int PW = a.pw, PU = a.pwl;                                          // words per packed row / per row of the unaligned view
     const int wpr = (a.Wc + 3) >> 2, cwpr = 2 * tl.nbx;                       // words per window row / per row of blocks
     const FastDiv d_wpr(a.m_pwl);
-    const int nblk_all = tl.nby * tl.nbx;
-    const auto quant_tile = [&](auto gen_tag, double lo, double inv_q, unsigned &flags, unsigned &nmin, unsigned &nmax) {
-        constexpr bool GEN = decltype(gen_tag)::value;
+    // flags after a pass: 1 = a value left [0, 255] (or is NaN / Inf), 2 / 4 = the window / the blocks hold a non-integer
+    const auto quant_tile = [&](auto keys_tag, double lo, double inv_q, unsigned &flags, int &kmin, int &kmax) {
+        constexpr bool KEYS = decltype(keys_tag)::value;
+        X2Acc aw, ac;
         for (int idx = tid; idx < a.R * wpr; idx += kMeThreads) {
             const int row = d_wpr.div(idx), w = idx - row * wpr;
-            s_b8[row * PW + w] = x2_quant4<GEN>(s_win + row * P + 4 * w, a.Wc - 4 * w, lo, inv_q, flags, 2u, nmin, nmax);
+            s_b8[row * PW + w] = x2_quant4<KEYS>(s_win + row * P + 4 * w, a.Wc - 4 * w, lo, inv_q, aw);
         }
         for (int idx = tid; idx < 8 * tl.nby * cwpr; idx += kMeThreads) {
             const int row = idx / cwpr, w = idx - row * cwpr, o = (row >> 3) * a.tbx + (w >> 1);
             s_c8[o * kCurPitch + (row & 7) * 2 + (w & 1)] =
-                x2_quant4<GEN>(s_cur + o * kExactCurPitch + (row & 7) * 8 + (w & 1) * 4, 4, lo, inv_q, flags, 4u, nmin, nmax);
+                x2_quant4<KEYS>(s_cur + o * kExactCurPitch + (row & 7) * 8 + (w & 1) * 4, 4, lo, inv_q, ac);
         }
         for (int idx = tid; idx < a.R * 2; idx += kMeThreads) s_b8[(idx >> 1) * PW + wpr + (idx & 1)] = 0u;   // the spare words
-    };
-    // flags: 1 = a value left [0, 255] (or is NaN / Inf), 2 / 4 = the window / the blocks hold a non-integer (after the map)
-    const auto tile_reduce = [&](unsigned &flags, unsigned &nmin, unsigned &nmax) {
+        flags = ((aw.bad | ac.bad) ? 1u : 0u) | (aw.nonint ? 2u : 0u) | (ac.nonint ? 4u : 0u);
         flags = __reduce_or_sync(0xffffffffu, flags);
-        nmin = __reduce_min_sync(0xffffffffu, nmin);
-        nmax = __reduce_max_sync(0xffffffffu, nmax);
-        if (lane == 0) { s_redi[0][warp] = flags; s_redi[1][warp] = nmin; s_redi[2][warp] = nmax; }
+        unsigned umin = (unsigned)min(aw.kmin, ac.kmin) ^ 0x80000000u, umax = (unsigned)max(aw.kmax, ac.kmax) ^ 0x80000000u;
+        if (KEYS) { umin = __reduce_min_sync(0xffffffffu, umin); umax = __reduce_max_sync(0xffffffffu, umax); }
+        if (lane == 0) { s_redi[0][warp] = flags; s_redi[1][warp] = umin; s_redi[2][warp] = umax; }
         __syncthreads();
-        flags = 0u; nmin = 0xffffffffu; nmax = 0u;
+        flags = 0u; umin = 0xffffffffu; umax = 0u;
 #pragma unroll
-        for (int w = 0; w < kMeWarps; ++w) { flags |= s_redi[0][w]; nmin = min(nmin, s_redi[1][w]); nmax = max(nmax, s_redi[2][w]); }
-        __syncthreads();                                                      // s_redi is written again below
+        for (int w = 0; w < kMeWarps; ++w) { flags |= s_redi[0][w]; umin = min(umin, s_redi[1][w]); umax = max(umax, s_redi[2][w]); }
+        kmin = (int)(umin ^ 0x80000000u); kmax = (int)(umax ^ 0x80000000u);
     };
-    unsigned flags = 0u, nmin = 0xffffffffu, nmax = 0u;
-    quant_tile(std::false_type{}, 0.0, 1.0, flags, nmin, nmax);
-    tile_reduce(flags, nmin, nmax);
+    unsigned flags;
+    int kmin, kmax;
+    quant_tile(std::true_type{}, kX2GuessLo, kX2GuessInvQ, flags, kmin, kmax);
+    // the tile's range from the keys, one step outwards: vmin <= every value <= vmax
+    const auto decode = [](int key0, int step) {
+        const long long k = (long long)key0 + step;
+        const int key = (int)max(min(k, 0x7fffffffLL), -0x7fffffffLL - 1);
+        return __hiloint2double(key ^ ((key >> 31) & 0x7fffffff), 0);
+    };
+    const double vmin = decode(kmin, -1), vmax = decode(kmax, 1);
     bool fallback = false;
     // the guess is kept unless it failed or resolves the tile poorly (non-integer content on fewer than 48 levels)
-    if ((flags & 1u) || ((flags & 6u) && nmax - nmin < 48u)) {
-        // ---- the tile's own range, from the high words of the doubles (order-preserving integer keys), one step outwards ----
-        int kmin = 0x7fffffff, kmax = (int)0x80000000;
-        const auto track = [&](const double *p) {
-            const int hi = __double2hiint(*p), key = hi ^ ((hi >> 31) & 0x7fffffff);
-            kmin = min(kmin, key); kmax = max(kmax, key);
-        };
-        for (int idx = tid; idx < a.R * a.Wc; idx += kMeThreads) {
-            const int row = FastDiv(a.m_p4).div(idx);
-            track(s_win + row * P + (idx - row * a.Wc));
-        }
-        for (int idx = tid; idx < 64 * nblk_all; idx += kMeThreads) {
-            const int o = idx >> 6, brow_ = o / tl.nbx;
-            track(s_cur + (brow_ * a.tbx + (o - brow_ * tl.nbx)) * kExactCurPitch + (idx & 63));
-        }
-        unsigned ukmin = (unsigned)kmin ^ 0x80000000u, ukmax = (unsigned)kmax ^ 0x80000000u, dummy = 0u;   // biased: unsigned order
-        tile_reduce(dummy, ukmin, ukmax);
-        const auto decode = [](unsigned ukey, int step) {
-            const long long k = (long long)(int)(ukey ^ 0x80000000u) + step;
-            const int key = (int)max(min(k, 0x7fffffffLL), -0x7fffffffLL - 1);
-            return __hiloint2double(key ^ ((key >> 31) & 0x7fffffff), 0);
-        };
-        const double vmin = decode(ukmin, -1), vmax = decode(ukmax, 1);       // vmin <= every value <= vmax
+    if ((flags & 1u) || ((flags & 6u) && vmax - vmin < 48.0)) {
         const bool wild = !(fabs(vmin) < 1e300) || !(fabs(vmax) < 1e300);     // NaN / Inf (or next to the end of the range)
         // an INTEGER scale while the tile spans 1 .. 255: integer-valued frames are then quantised exactly
         const double lo = (vmax - floor(vmin) >= 1.0) ? floor(vmin) : vmin, range = vmax - lo;
         const double inv_q = (range >= 1.0 && range <= 255.0) ? floor(255.0 / range) : 255.0 / (range * (1.0 + 1e-12));
         fallback = wild || !(range > 0.0) || !(range < 1e290);                // no usable bound: every in-frame candidate survives
+        __syncthreads();                                                      // s_redi is written again
         if (!fallback) {
-            flags = 0u; nmin = 0xffffffffu; nmax = 0u;
-            quant_tile(std::true_type{}, lo, inv_q, flags, nmin, nmax);
-            tile_reduce(flags, nmin, nmax);
+            quant_tile(std::false_type{}, lo, inv_q, flags, kmin, kmax);
             fallback = (flags & 1u) != 0u;                                    // cannot happen; if it does the bound is void
         }
     }
@@ -1664,7 +1689,7 @@ static size_t me_geometry2(MeArgs &a, int64_t n_frames, int64_t H, int64_t W, in
         if (ctas < min_ctas && !(s[0] == 1 && s[1] == 1) && s[0] * s[1] > 8) continue;
         a.R = 8 * (a.tby - 1) + a.ngrp * kMeG + 7;                 // >= 8*tby + 2*sr, covers the last dy-group
         a.Wc = 8 * a.tbx + 2 * sr;
-        a.P = ((a.Wc + 31) / 32) * 32 + 3;                         // == 3 (mod 32): the dy-groups of a warp on disjoint banks
+        a.P = ((a.Wc + 31) / 32) * 32 + 4;                         // even: rows start 16-byte aligned (bulk copies)
         const size_t win = (size_t)a.R * a.P, blocks = (size_t)a.tby * a.tbx;
         a.cur_off = (int)((win * 8 + 15) & ~(size_t)15);
         a.pwl = ((a.Wc + 3 - 4 + 31) / 32) * 32 + 4;               // PU: words per row of the unaligned view, == 4 (mod 32): the dy-groups of a warp on disjoint banks
@@ -1705,7 +1730,7 @@ cudaError_t launch_pframe_step(int device, cudaStream_t st, const void *ref, con
     if (2 * sr + 1 <= 33 && !me_exact_v1()) {
         const size_t smem2 = me_geometry2(a, n, H, W, sr, 113 * 1024, 2 * 2 * (int64_t)sm_count(device), true);
         if (smem2 <= 227 * 1024)
-            return (a.span == 9 && a.P == 163) ? me_launch_chunks(k_me_exact2<true, 9, 163>, a, 8, smem2, st)
+            return (a.span == 9 && a.P == 164) ? me_launch_chunks(k_me_exact2<true, 9, 164>, a, 8, smem2, st)
                                               : me_launch_chunks(k_me_exact2<true>, a, 8, smem2, st);
     }
     const size_t smem = me_geometry(a, n, H, W, sr, 8, 32, 3, 113 * 1024, 2 * 2 * (int64_t)sm_count(device), kStepWork);
@@ -1722,7 +1747,7 @@ cudaError_t launch_me_exact(int device, cudaStream_t st, const void *ref, const 
     if (!f32 && 2 * sr + 1 <= 33 && !me_exact_v1()) {                       // float64 frames: prefilter + exact survivors
         const size_t smem2 = me_geometry2(a, n, H, W, sr, 113 * 1024, 2 * 2 * (int64_t)sm_count(device), false);
         if (smem2 <= 227 * 1024)
-            return (a.span == 9 && a.P == 163) ? me_launch_chunks(k_me_exact2<false, 9, 163>, a, 8, smem2, st)
+            return (a.span == 9 && a.P == 164) ? me_launch_chunks(k_me_exact2<false, 9, 164>, a, 8, smem2, st)
                                               : me_launch_chunks(k_me_exact2<false>, a, 8, smem2, st);
     }
     const size_t smem = me_geometry(a, n, H, W, sr, f32 ? 4 : 8, 32, 3, 113 * 1024, 2 * 2 * (int64_t)sm_count(device));
