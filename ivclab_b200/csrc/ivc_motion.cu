@@ -656,10 +656,8 @@ __global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exa
     const float FINF = __int_as_float(0x7f800000);
     const double DINF = Inf<double>::v();
 
-    for (int k = 0; k < nb_w; ++k) {
-        const int blk = blk0 + k, brow = d_nbx.div(blk), b = blk - brow * tl.nbx;
-        const int slot = brow * a.tbx + b;
-        const int gy0 = 8 * (tl.by0 + brow) - sr, gx0 = 8 * (tl.bx0 + b) - sr;       // frame position of candidate (0, 0)
+    // byte scores of one block into this warp's s_A (-1 = outside the frame); returns min (S~ + eps(S~)) over its candidates
+    const auto score_block = [&](int brow, int b, int slot, int gy0, int gx0) {
         float thr = FINF;
         if (!fallback) {
             // ---- byte scores: a task = three vertically adjacent candidates sharing their window rows in registers ----
@@ -703,37 +701,52 @@ __global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exa
             for (int off = 16; off > 0; off >>= 1) thr = fminf(thr, __shfl_xor_sync(0xffffffffu, thr, off));
             __syncwarp();
         }
-        // ---- survivors, in ascending candidate order, four at a time: exact SSD in numpy's order ----
-        double best = DINF;
-        int bidx = center;
-        const double *cb = s_cur + slot * kExactCurPitch + j8;                        // column j8 of the block
-        for (int base = 0; base < ncand; base += 32) {
-            const int c = base + lane;
-            bool surv = false;
-            if (c < ncand) {
-                if (fallback) {
-                    const int dyi = div_span(c), dxi = c - dyi * span;
-                    surv = gy0 + dyi >= 0 && gy0 + dyi + 8 <= a.H && gx0 + dxi >= 0 && gx0 + dxi + 8 <= a.W;
-                } else {
-                    const float sc = s_A[c];
-                    surv = sc >= 0.0f && (sc - __fmaf_rn(e16, __fsqrt_ru(sc), e64)) <= thr;
-                }
-            }
-            unsigned mask = __ballot_sync(0xffffffffu, surv);
-            while (mask) {
-                int mine = -1;                                                    // the candidate of this lane's group of eight
+        return thr;
+    };
+    if constexpr (CSPAN == 9) {
+        // ---- 81 candidates: four blocks at a time.  Their survivors are three ballot words each; then the warp's four groups
+        // of eight lanes walk one block's list each -- typically a single exact evaluation for all four blocks together ----
+        for (int k0 = 0; k0 < nb_w; k0 += 4) {
+            unsigned m0 = 0u, m1 = 0u, m2 = 0u;                                   // this lane group's block: candidates still to evaluate
+            for (int q = 0; q < 4 && k0 + q < nb_w; ++q) {
+                const int blk = blk0 + k0 + q, brow = d_nbx.div(blk), b = blk - brow * tl.nbx;
+                const int gy0 = 8 * (tl.by0 + brow) - sr, gx0 = 8 * (tl.bx0 + b) - sr;
+                const float thr = fallback ? FINF : score_block(brow, b, brow * a.tbx + b, gy0, gx0);
+                unsigned w[3];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    if (mask) {
-                        const int bit = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        if (g == g8) mine = base + bit;
+                for (int j = 0; j < 3; ++j) {
+                    const int c = 32 * j + lane;
+                    bool surv = false;
+                    if (c < 81) {
+                        if (fallback) {
+                            const int dyi = c / 9, dxi = c - dyi * 9;
+                            surv = gy0 + dyi >= 0 && gy0 + dyi + 8 <= a.H && gx0 + dxi >= 0 && gx0 + dxi + 8 <= a.W;
+                        } else {
+                            const float sc = s_A[c];
+                            surv = sc >= 0.0f && (sc - __fmaf_rn(e16, __fsqrt_ru(sc), e64)) <= thr;
+                        }
                     }
+                    w[j] = __ballot_sync(0xffffffffu, surv);
                 }
+                if (g8 == q) { m0 = w[0]; m1 = w[1]; m2 = w[2]; }
+                __syncwarp();                                                     // s_A is rewritten for the next block
+            }
+            const int kq = k0 + g8;
+            const bool have = kq < nb_w;
+            const int blk = blk0 + (have ? kq : 0), brow = d_nbx.div(blk), b = blk - brow * tl.nbx;
+            const double *cb = s_cur + (brow * a.tbx + b) * kExactCurPitch + j8;  // column j8 of the block
+            const double *wb = s_win + (8 * brow) * P + 8 * b + j8;
+            double best = DINF;
+            int bidx = center;
+            while (__any_sync(0xffffffffu, (m0 | m1 | m2) != 0u)) {
+                int mine = -1;                                                    // ascending order: lowest candidate first
+                if (m0) { mine = __ffs(m0) - 1; m0 &= m0 - 1; }
+                else if (m1) { mine = 31 + __ffs(m1); m1 &= m1 - 1; }
+                else if (m2) { mine = 63 + __ffs(m2); m2 &= m2 - 1; }
                 double acc = DINF;
                 if (mine >= 0) {
-                    const int dyi = div_span(mine), dxi = mine - dyi * span;
-                    const double *wp = s_win + (8 * brow + dyi) * P + 8 * b + dxi + j8;
+                    const int dyi = mine / 9, dxi = mine - dyi * 9;
+                    const double *wp = wb + dyi * P + dxi;
                     acc = 0.0;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {                                 // r[j] += d**2, rows in order
@@ -744,19 +757,75 @@ __global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exa
                 acc = R_::add(acc, __shfl_xor_sync(0xffffffffu, acc, 1));        // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7))
                 acc = R_::add(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
                 acc = R_::add(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const double sg = __shfl_sync(0xffffffffu, acc, 8 * g);
-                    const int ig = __shfl_sync(0xffffffffu, mine, 8 * g);
-                    if (ig >= 0 && sg < best) { best = sg; bidx = ig; }           // ascending order: strict < (motion.py:48)
+                if (mine >= 0 && acc < best) { best = acc; bidx = mine; }        // strict < (motion.py:48)
+            }
+            if (have && j8 == 0) {
+                a.mv[(tl.frame * a.Hp + tl.by0 + brow) * (int64_t)a.Wp + tl.bx0 + b] = bidx;
+                s_mvw[warp][kq] = bidx;
+            }
+            __syncwarp();
+        }
+    } else {
+        for (int k = 0; k < nb_w; ++k) {
+            const int blk = blk0 + k, brow = d_nbx.div(blk), b = blk - brow * tl.nbx;
+            const int slot = brow * a.tbx + b;
+            const int gy0 = 8 * (tl.by0 + brow) - sr, gx0 = 8 * (tl.bx0 + b) - sr;       // frame position of candidate (0, 0)
+            const float thr = fallback ? FINF : score_block(brow, b, slot, gy0, gx0);
+            // ---- survivors, in ascending candidate order, four at a time: exact SSD in numpy's order ----
+            double best = DINF;
+            int bidx = center;
+            const double *cb = s_cur + slot * kExactCurPitch + j8;                        // column j8 of the block
+            for (int base = 0; base < ncand; base += 32) {
+                const int c = base + lane;
+                bool surv = false;
+                if (c < ncand) {
+                    if (fallback) {
+                        const int dyi = div_span(c), dxi = c - dyi * span;
+                        surv = gy0 + dyi >= 0 && gy0 + dyi + 8 <= a.H && gx0 + dxi >= 0 && gx0 + dxi + 8 <= a.W;
+                    } else {
+                        const float sc = s_A[c];
+                        surv = sc >= 0.0f && (sc - __fmaf_rn(e16, __fsqrt_ru(sc), e64)) <= thr;
+                    }
+                }
+                unsigned mask = __ballot_sync(0xffffffffu, surv);
+                while (mask) {
+                    int mine = -1;                                                    // the candidate of this lane's group of eight
+    #pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (mask) {
+                            const int bit = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            if (g == g8) mine = base + bit;
+                        }
+                    }
+                    double acc = DINF;
+                    if (mine >= 0) {
+                        const int dyi = div_span(mine), dxi = mine - dyi * span;
+                        const double *wp = s_win + (8 * brow + dyi) * P + 8 * b + dxi + j8;
+                        acc = 0.0;
+    #pragma unroll
+                        for (int i = 0; i < 8; ++i) {                                 // r[j] += d**2, rows in order
+                            const double d = R_::sub(cb[i * 8], wp[i * P]);
+                            acc = R_::add(acc, R_::mul(d, d));
+                        }
+                    }
+                    acc = R_::add(acc, __shfl_xor_sync(0xffffffffu, acc, 1));        // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7))
+                    acc = R_::add(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
+                    acc = R_::add(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
+    #pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const double sg = __shfl_sync(0xffffffffu, acc, 8 * g);
+                        const int ig = __shfl_sync(0xffffffffu, mine, 8 * g);
+                        if (ig >= 0 && sg < best) { best = sg; bidx = ig; }           // ascending order: strict < (motion.py:48)
+                    }
                 }
             }
+            if (lane == 0) {
+                a.mv[(tl.frame * a.Hp + tl.by0 + brow) * (int64_t)a.Wp + tl.bx0 + b] = bidx;
+                s_mvw[warp][k] = bidx;
+            }
+            __syncwarp();
         }
-        if (lane == 0) {
-            a.mv[(tl.frame * a.Hp + tl.by0 + brow) * (int64_t)a.Wp + tl.bx0 + b] = bidx;
-            s_mvw[warp][k] = bidx;
-        }
-        __syncwarp();
     }
     if constexpr (STEP) {
         unsigned char *work_b = smem_raw + a.work_off + warp * kX2Work;
