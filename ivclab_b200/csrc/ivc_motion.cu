@@ -452,6 +452,12 @@ constexpr int kCurPitch = 18;      // words per current block in shared memory (
 constexpr double kX2GuessLo = -64.0, kX2GuessInvQ = 255.0 / 384.0;                 // 85 / 128: exact
 constexpr int kX2Work = 4 * kStageUF * 4;                                     // 3264 B per warp: groups of four blocks
 
+__device__ __forceinline__ float sqrt_approx(float x) {          // MUFU.SQRT: relative error ~2^-22, sqrt(0) = 0
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // four values -> one word of bytes under the map x = (v - lo) * inv_q.  Everything the tile needs to know about the values
 // is OR-ed / min-maxed into the accumulators and looked at once per tile:
 //   bad     != 0  <=> some x left [0, 255] (NaN and Inf do)
@@ -513,7 +519,7 @@ __global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exa
     unsigned *s_u = reinterpret_cast<unsigned *>(smem_raw + a.win32_off);     // [R][PU]  unaligned-word view of the quantised window
     unsigned *s_b8 = reinterpret_cast<unsigned *>(smem_raw + a.b_off);        // [R][PW]  packed quantised window
     unsigned *s_c8 = reinterpret_cast<unsigned *>(smem_raw + a.cur32_off);    // [tby*tbx][kCurPitch] quantised blocks
-    float *s_A = reinterpret_cast<float *>(smem_raw + a.acand_off) + warp * a.acand_pitch;   // this warp's candidate scores
+    unsigned *s_A = reinterpret_cast<unsigned *>(smem_raw + a.acand_off) + warp * a.acand_pitch;   // this warp's candidate scores
     using R_ = Rn<double>;
     const MeTile tl = me_tile(a);
     const double *ref = (const double *)a.ref + tl.frame * a.ref_fs;
@@ -521,6 +527,7 @@ __global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exa
     const int sr = a.sr, span = CSPAN ? CSPAN : a.span, P = CP ? CP : a.P, ncand = span * span;
     const int ntpb = CSPAN ? ((CSPAN + kMeG - 1) / kMeG) * CSPAN : a.ntpb;
     const auto div_span = [&](int x) { return CSPAN ? x / (CSPAN ? CSPAN : 1) : FastDiv(a.m_span).div(x); };
+    const FastDiv d_nbx(a.m_nbx[tl.nbx != a.tbx]);
 
     // ---- stage window and current blocks (float64, zero outside the frame), all copies in flight at once ----
     // A tile whose window lies inside the frame takes one bulk copy per window row (lanes of warp 0) and 16-byte copies for
@@ -556,7 +563,7 @@ __global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exa
     if (pairs) {
         const int hw = cw >> 1;                                               // 16-byte pairs per row of blocks
         for (int idx = tid; idx < 8 * tl.nby * hw; idx += kMeThreads) {
-            const int row = idx / hw, col = 2 * (idx - row * hw);
+            const int row = d_nbx.div(idx >> 2), col = 2 * (idx - row * hw);          // hw = 4 nbx
             cp_async_zfill<16>(cur_s + (uint32_t)(((row >> 3) * a.tbx + (col >> 3)) * kExactCurPitch + (row & 7) * 8 + (col & 7)) * 8u,
                                cur + ((int64_t)8 * tl.by0 + row) * a.W + 8 * tl.bx0 + col, true);
         }
@@ -585,7 +592,7 @@ __global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exa
             s_b8[row * PW + w] = x2_quant4<KEYS>(s_win + row * P + 4 * w, a.Wc - 4 * w, lo, inv_q, aw);
         }
         for (int idx = tid; idx < 8 * tl.nby * cwpr; idx += kMeThreads) {
-            const int row = idx / cwpr, w = idx - row * cwpr, o = (row >> 3) * a.tbx + (w >> 1);
+            const int row = d_nbx.div(idx >> 1), w = idx - row * cwpr, o = (row >> 3) * a.tbx + (w >> 1);   // cwpr = 2 nbx
             s_c8[o * kCurPitch + (row & 7) * 2 + (w & 1)] =
                 x2_quant4<KEYS>(s_cur + o * kExactCurPitch + (row & 7) * 8 + (w & 1) * 4, 4, lo, inv_q, ac);
         }
@@ -651,15 +658,13 @@ __global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exa
     const int nblk = tl.nby * tl.nbx;
     const int per_w = (nblk + kMeWarps - 1) / kMeWarps, blk0 = warp * per_w;        // blocks blk0 .. blk0+nb_w-1 (per_w <= 8)
     const int nb_w = max(0, min(per_w, nblk - blk0));
-    const FastDiv d_nbx(a.m_nbx[tl.nbx != a.tbx]);
     const int g8 = lane >> 3, j8 = lane & 7;
-    const float FINF = __int_as_float(0x7f800000);
     const double DINF = Inf<double>::v();
 
-    // byte scores of one block into this warp's s_A (-1 = outside the frame); returns min (S~ + eps(S~)) over its candidates
+    // byte scores of one block into this warp's s_A; returns the largest score that can still win or tie
     const auto score_block = [&](int brow, int b, int slot, int gy0, int gx0) {
-        float thr = FINF;
-        if (!fallback) {
+        unsigned smin = 0xffffffffu;
+        {
             // ---- byte scores: a task = three vertically adjacent candidates sharing their window rows in registers ----
             const uint2 *cb8 = reinterpret_cast<const uint2 *>(s_c8 + slot * kCurPitch);
             for (int tt = lane; tt < ntpb; tt += 32) {
@@ -691,17 +696,20 @@ __global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exa
                     const int dyi = dy0 + gg, gy = gy0 + dyi;
                     if (dyi < span) {
                         const bool ok = x_ok && gy >= 0 && gy + 8 <= a.H;             // motion.py:41-43
-                        const float sc = (float)acc[gg];                              // < 2^23: exact
-                        s_A[dyi * span + dxi] = ok ? sc : -1.0f;                      // scores are >= 0: -1 marks "outside the frame"
-                        if (ok) thr = fminf(thr, sc + (__fmaf_rn(e16, __fsqrt_ru(sc), e64)));
+                        const unsigned sc = ok ? acc[gg] : 0xffffffffu;               // all ones marks "outside the frame"
+                        s_A[dyi * span + dxi] = sc;
+                        smin = min(smin, sc);
                     }
                 }
             }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) thr = fminf(thr, __shfl_xor_sync(0xffffffffu, thr, off));
+            smin = __reduce_min_sync(0xffffffffu, smin);
             __syncwarp();
         }
-        return thr;
+        // S~ - eps(S~) <= min (S~ + eps(S~)) = smin + eps(smin) (eps grows with S~)  <=>  S~ <= lim, the root of a quadratic
+        // in sqrt(S~), taken a little upwards; below 64 delta^2, where S~ - eps(S~) falls, every candidate passes anyway
+        const float fmin_ = (float)smin, thr = fmin_ + __fmaf_rn(e16, sqrt_approx(fmin_), e64);
+        const float rt = 0.5f * (e16 + sqrt_approx(__fmaf_rn(e16, e16, 4.0f * (thr + e64)))) * 1.00001f;
+        return (unsigned)fminf(__fmaf_rn(rt, rt, 1.0f), 4.0e9f);
     };
     if constexpr (CSPAN == 9) {
         // ---- 81 candidates: four blocks at a time.  Their survivors are three ballot words each; then the warp's four groups
@@ -711,7 +719,7 @@ __global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exa
             for (int q = 0; q < 4 && k0 + q < nb_w; ++q) {
                 const int blk = blk0 + k0 + q, brow = d_nbx.div(blk), b = blk - brow * tl.nbx;
                 const int gy0 = 8 * (tl.by0 + brow) - sr, gx0 = 8 * (tl.bx0 + b) - sr;
-                const float thr = fallback ? FINF : score_block(brow, b, brow * a.tbx + b, gy0, gx0);
+                const unsigned lim = fallback ? 0u : score_block(brow, b, brow * a.tbx + b, gy0, gx0);
                 unsigned w[3];
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
@@ -722,8 +730,7 @@ __global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exa
                             const int dyi = c / 9, dxi = c - dyi * 9;
                             surv = gy0 + dyi >= 0 && gy0 + dyi + 8 <= a.H && gx0 + dxi >= 0 && gx0 + dxi + 8 <= a.W;
                         } else {
-                            const float sc = s_A[c];
-                            surv = sc >= 0.0f && (sc - __fmaf_rn(e16, __fsqrt_ru(sc), e64)) <= thr;
+                            surv = s_A[c] <= lim;
                         }
                     }
                     w[j] = __ballot_sync(0xffffffffu, surv);
@@ -770,7 +777,7 @@ __global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exa
             const int blk = blk0 + k, brow = d_nbx.div(blk), b = blk - brow * tl.nbx;
             const int slot = brow * a.tbx + b;
             const int gy0 = 8 * (tl.by0 + brow) - sr, gx0 = 8 * (tl.bx0 + b) - sr;       // frame position of candidate (0, 0)
-            const float thr = fallback ? FINF : score_block(brow, b, slot, gy0, gx0);
+            const unsigned lim = fallback ? 0u : score_block(brow, b, slot, gy0, gx0);
             // ---- survivors, in ascending candidate order, four at a time: exact SSD in numpy's order ----
             double best = DINF;
             int bidx = center;
@@ -783,8 +790,7 @@ __global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exa
                         const int dyi = div_span(c), dxi = c - dyi * span;
                         surv = gy0 + dyi >= 0 && gy0 + dyi + 8 <= a.H && gx0 + dxi >= 0 && gx0 + dxi + 8 <= a.W;
                     } else {
-                        const float sc = s_A[c];
-                        surv = sc >= 0.0f && (sc - __fmaf_rn(e16, __fsqrt_ru(sc), e64)) <= thr;
+                        surv = s_A[c] <= lim;
                     }
                 }
                 unsigned mask = __ballot_sync(0xffffffffu, surv);
