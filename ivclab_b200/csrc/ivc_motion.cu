@@ -23,6 +23,7 @@
 // on the packed key (ssd, index).  ivc_me_full_search(IVC_ME_AUTO) launches k_me_int and then k_me_exact, which
 // exits immediately unless the flag was raised -- no host round trip, no workspace beyond the 4-byte flag.
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 #include "ivc_dct.cuh"
@@ -492,7 +493,7 @@ __device__ __forceinline__ unsigned x2_quant4(const double *p, int cnt, double l
 // CSPAN / CP: compile-time search span and window pitch (0 = take them from the arguments): with constants every row
 // offset of the unrolled loops is an immediate and the index divisions are multiply-shifts
 template <bool STEP, int CSPAN = 0, int CP = 0>
-__global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exact2(const MeArgs a) {
+__global__ void __launch_bounds__(kMeThreads, CSPAN ? 3 : 2) k_me_exact2(const MeArgs a) {
     if (a.flag && *a.flag != a.run_if) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double s_qt[STEP ? 448 : 1];              // STEP: fl(1/t) [192], t [192], luminance table transposed [64]
@@ -834,6 +835,7 @@ __global__ void __launch_bounds__(kMeThreads, (CSPAN && !STEP) ? 3 : 2) k_me_exa
         }
     }
     if constexpr (STEP) {
+        __syncthreads();                                  // the WORK buffers lie over the search's tables (U view, bytes, scores)
         unsigned char *work_b = smem_raw + a.work_off + warp * kX2Work;
         for (int k0 = 0; k0 < nb_w; k0 += 4)
             pstep_group<576>(a, tl, s_win, s_cur, &s_mvw[warp][k0], 1, blk0 + k0, min(4, nb_w - k0), d_nbx, work_b, s_qt, s_qt + 192,
@@ -1764,7 +1766,7 @@ static size_t me_geometry2(MeArgs &a, int64_t n_frames, int64_t H, int64_t W, in
         if (ctas < min_ctas && !(s[0] == 1 && s[1] == 1) && s[0] * s[1] > 8) continue;
         a.R = 8 * (a.tby - 1) + a.ngrp * kMeG + 7;                 // >= 8*tby + 2*sr, covers the last dy-group
         a.Wc = 8 * a.tbx + 2 * sr;
-        a.P = ((a.Wc + 31) / 32) * 32 + 4;                         // even: rows start 16-byte aligned (bulk copies)
+        a.P = a.Wc + 2;                                            // even: rows start 16-byte aligned (bulk copies); 138 for 16 blocks at +-4
         const size_t win = (size_t)a.R * a.P, blocks = (size_t)a.tby * a.tbx;
         a.cur_off = (int)((win * 8 + 15) & ~(size_t)15);
         a.pwl = ((a.Wc + 3 - 4 + 31) / 32) * 32 + 4;               // PU: words per row of the unaligned view, == 4 (mod 32): the dy-groups of a warp on disjoint banks
@@ -1776,8 +1778,8 @@ static size_t me_geometry2(MeArgs &a, int64_t n_frames, int64_t H, int64_t W, in
         a.acand_off = (int)((a.cur32_off + blocks * kCurPitch * 4 + 15) & ~(size_t)15);
         a.acand_pitch = (a.span * a.span + 3) & ~3;
         smem = (size_t)a.acand_off + (size_t)kMeWarps * a.acand_pitch * 4;
-        a.work_off = (int)((smem + 127) & ~(size_t)127);
-        if (step) smem = (size_t)a.work_off + (size_t)kMeWarps * kX2Work;
+        a.work_off = (int)(((size_t)a.win32_off + 127) & ~(size_t)127);          // over the search's tables: dead when the step starts
+        if (step) smem = std::max(smem, (size_t)a.work_off + (size_t)kMeWarps * kX2Work);
         if (smem <= budget) break;
     }
     a.tiles_y = (a.Hp + a.tby - 1) / a.tby;
@@ -1803,9 +1805,9 @@ cudaError_t launch_pframe_step(int device, cudaStream_t st, const void *ref, con
     a.zr_counts = nullptr; a.zr_masks = nullptr;
     if (n > 65535) return cudaErrorInvalidValue;                               // one launch: y = frame
     if (2 * sr + 1 <= 33 && !me_exact_v1()) {
-        const size_t smem2 = me_geometry2(a, n, H, W, sr, 113 * 1024, 2 * 2 * (int64_t)sm_count(device), true);
+        const size_t smem2 = me_geometry2(a, n, H, W, sr, (sr == 4 ? 73 : 113) * 1024, 2 * 2 * (int64_t)sm_count(device), true);     // +-4: three CTAs per SM
         if (smem2 <= 227 * 1024)
-            return (a.span == 9 && a.P == 164) ? me_launch_chunks(k_me_exact2<true, 9, 164>, a, 8, smem2, st)
+            return (a.span == 9 && a.P == 138) ? me_launch_chunks(k_me_exact2<true, 9, 138>, a, 8, smem2, st)
                                               : me_launch_chunks(k_me_exact2<true>, a, 8, smem2, st);
     }
     const size_t smem = me_geometry(a, n, H, W, sr, 8, 32, 3, 113 * 1024, 2 * 2 * (int64_t)sm_count(device), kStepWork);
@@ -1820,9 +1822,9 @@ cudaError_t launch_me_exact(int device, cudaStream_t st, const void *ref, const 
     a.ref = ref; a.cur = cur; a.n = n; a.H = H; a.W = W; a.ref_fs = ref_fs; a.cur_fs = cur_fs; a.mv = mv;
     a.flag = flag; a.run_if = run_if; a.check = 0;
     if (!f32 && 2 * sr + 1 <= 33 && !me_exact_v1()) {                       // float64 frames: prefilter + exact survivors
-        const size_t smem2 = me_geometry2(a, n, H, W, sr, 113 * 1024, 2 * 2 * (int64_t)sm_count(device), false);
+        const size_t smem2 = me_geometry2(a, n, H, W, sr, (sr == 4 ? 73 : 113) * 1024, 2 * 2 * (int64_t)sm_count(device), false);
         if (smem2 <= 227 * 1024)
-            return (a.span == 9 && a.P == 164) ? me_launch_chunks(k_me_exact2<false, 9, 164>, a, 8, smem2, st)
+            return (a.span == 9 && a.P == 138) ? me_launch_chunks(k_me_exact2<false, 9, 138>, a, 8, smem2, st)
                                               : me_launch_chunks(k_me_exact2<false>, a, 8, smem2, st);
     }
     const size_t smem = me_geometry(a, n, H, W, sr, f32 ? 4 : 8, 32, 3, 113 * 1024, 2 * 2 * (int64_t)sm_count(device));
