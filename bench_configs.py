@@ -137,7 +137,7 @@ def cfg1(cx, ivc):
 # ---- cfg2: ch4 codec on a QCIF 21-frame luma sequence -----------------------------------------------------------
 def cfg2(cx, ivc):
     seq = luma_seq(cx.torch, cx.device, 21, 144, 176, 2)
-    out = {"workload": "QCIF 176x144, 21 luma frames, closed loop: +-4 full search (exact FP64 kernel), MC, residual DCT/quant, reconstruction"}
+    out = {"workload": "QCIF 176x144, 21 luma frames, closed loop: +-4 order-exact full search, MC, residual DCT/quant, reconstruction (one fused kernel per frame)"}
     for graph in (False, True):
         cl = ivc.ClosedLoopLumaCoder(1.0, 4, decode="luma", me_mode="exact", use_graph=graph)
         t = cx.timed(lambda: cl.code_sequence(seq), 20, warm=3)
@@ -307,8 +307,10 @@ def cfg4(cx, ivc, n_seq=8, T=120, exact_pairs=4):
            "hbm_frac": round((2 * 8 * H * W + 8 * (H // 8) * (W // 8)) / (per_frame * 1e-3) / 1e9 / cx.peak, 4) if per_frame else None,
            "candidates_per_frame": cand}
     if ms_exact is not None:
-        res["exact_fp64_kernel"] = {"ms_per_frame": round(ms_exact, 4), "mpixel_s": round(H * W / ms_exact / 1e3, 1),
-                                    "fp64_pipe_frac": round(cand * 192 / (ms_exact * 1e-3) / (FP64_LANES_PER_CLK_SM * cx.sms * cx.sm_hz), 4),
+        res["exact_fp64_kernel"] = {"kernel": "k_me_exact2 (byte prefilter, order-exact FP64 evaluation of the survivors)",
+                                    "ms_per_frame": round(ms_exact, 4), "mpixel_s": round(H * W / ms_exact / 1e3, 1),
+                                    "replay_equivalent_fp64_pipe_frac": round(cand * 192 / (ms_exact * 1e-3) / (FP64_LANES_PER_CLK_SM * cx.sms * cx.sm_hz), 4),
+                                    "note": "the fraction is what evaluating EVERY candidate in FP64 at this speed would need; the kernel evaluates about one per block",
                                     "vectors_equal_integer_kernel": checked}
     torch.cuda.empty_cache()
     return res
@@ -320,7 +322,7 @@ def cfg5(cx, ivc, T=300):
     H, W = 1080, 1920
     s5 = luma_seq(torch, cx.device, T, H, W, 5000)
     res = {"workload": f"{T} synthetic 1920x1080 luma frames, closed loop (frame t is predicted from the decoder's reconstruction "
-                       "of t-1): +-4 exact FP64 search, MC + residual DCT/quant, reconstruction; replicas only across GPUs",
+                       "of t-1): +-4 order-exact search, MC + residual DCT/quant, reconstruction in ONE kernel per frame (k_me_exact2<STEP>); replicas only across GPUs",
            "replicas": cx.world}
     for graph in (False, True):
         cl = ivc.ClosedLoopLumaCoder(1.0, 4, decode="luma", me_mode="exact", use_graph=graph)
@@ -332,8 +334,10 @@ def cfg5(cx, ivc, T=300):
     res["us_per_frame"] = best["us_per_frame"]
     res["mpixel_s"] = best["mpixel_s"]
     cand = candidates(H, W, 4)
-    res["fp64_pipe_frac"] = round(cand * 192 / (best["us_per_frame"] * 1e-6) / (FP64_LANES_PER_CLK_SM * cx.sms * cx.sm_hz), 4)
-    res["bound"] = "FP64 pipe of the order-exact search (3 x 64 rounded operations per candidate) on ONE frame: 32 400 blocks = a few waves"
+    res["hbm_frac"] = round((16 + 12 + 8) * H * W / (best["us_per_frame"] * 1e-6) / 1e9 / cx.peak, 4)     # two frames in, scan blocks + reconstruction out
+    res["replay_equivalent_fp64_pipe_frac"] = round(cand * 192 / (best["us_per_frame"] * 1e-6) / (FP64_LANES_PER_CLK_SM * cx.sms * cx.sm_hz), 4)
+    res["bound"] = ("latency of ONE frame: 1020 tiles of 32 blocks on 444 resident CTAs = 2.3 waves, issue slots about half busy "
+                    "(profiles/r2p_ncu_exact2.md); the prefilter leaves about one FP64 evaluation per block")
     del s5
     torch.cuda.empty_cache()
     return res

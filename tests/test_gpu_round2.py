@@ -602,3 +602,15 @@ def test_exact_search_prefilter_adversarial_magnitudes_and_ties():
         check(base[0] + rng.normal(0, 0.3, base[0].shape), base[1], sr=sr, tag=f"sr {sr}")
     big = O.moving_sequence(901, 2, 264, 520)
     check(big[0] + rng.normal(0, 0.3, big[0].shape), big[1], tag="larger frame")
+
+
+def test_exact_search_generations_agree_randomised():
+    """The prefilter + survivors kernel against the kernel that replays numpy on every candidate: 150 random cases over
+    shapes (8..240 x 8..320), ranges 1..16 and ten content classes (noise, integers, overshooting smooth scenes, low
+    contrast, piecewise constant, tiny range on a 1e6 offset, scaled negatives, periodic exact ties, NaN / Inf pixels,
+    static scene with an outlier) -- tools/exact_stress.py."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("exact_stress", os.path.join(ROOT, "tools", "exact_stress.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.run(seed=11, N=150, verbose=False) == []
