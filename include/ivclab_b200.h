@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define IVC_ABI_VERSION 7
+#define IVC_ABI_VERSION 8
 
 /* element types */
 #define IVC_U8   0
@@ -70,6 +70,17 @@ const char *ivc_last_cuda_error_string(void);
 int ivc_dct8x8(int device, void *stream, int inverse,
                const void *x, int x_dtype, int64_t n0, int64_t n1, int64_t C,
                const int64_t strides[5], void *out, int out_dtype);
+
+/* The same with scipy's other normalisations -- the reference forwards `self.norm` to scipy.fft.dct / idct
+ * (dct.py:9-10,24,26,42,44); nothing in ivclab uses one, the class accepts them.  norm: IVC_NORM_ORTHO, IVC_NORM_BACKWARD
+ * (scipy's None / "backward": unscaled forward transform, inverse / 16 per axis), IVC_NORM_FORWARD (forward / 16 per axis,
+ * unscaled inverse).  For length 8 ducc0's factor is a power of two in every mode, so the results stay bit-identical. */
+#define IVC_NORM_ORTHO 0
+#define IVC_NORM_BACKWARD 1
+#define IVC_NORM_FORWARD 2
+int ivc_dct8x8_norm(int device, void *stream, int inverse, int norm,
+                    const void *x, int x_dtype, int64_t n0, int64_t n1, int64_t C,
+                    const int64_t strides[5], void *out, int out_dtype);
 
 /* ---- a6: PatchQuant.quantize (patchquant.py:56-60) ------------------------------------------
  * out[n0,n1,Cout,8,8] = int32(rint(x / table[c])) with numpy broadcasting of C against 3

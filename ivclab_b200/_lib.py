@@ -14,8 +14,8 @@ LIB_PATH = os.path.join(_HERE, "_C", "libivcb200.so")
 
 # element type codes (include/ivclab_b200.h)
 U8, I32, F32, F64, I64, I16 = 0, 1, 2, 3, 4, 5
-ABI_VERSION = 7            # include/ivclab_b200.h IVC_ABI_VERSION (2: entry points added in round 1, zero-run write gained a length; 3: ivc_rgb8_to_luma8;
-                           # 4: ivc_pframe_forward_ch, ivc_zerorun_symbol_histogram; 5: ivc_pframe_search_forward; 6: the _zr variants; 7: ivc_pframe_step)
+ABI_VERSION = 8            # include/ivclab_b200.h IVC_ABI_VERSION (2: entry points added in round 1, zero-run write gained a length; 3: ivc_rgb8_to_luma8;
+                           # 4: ivc_pframe_forward_ch, ivc_zerorun_symbol_histogram; 5: ivc_pframe_search_forward; 6: the _zr variants; 7: ivc_pframe_step; 8: ivc_dct8x8_norm)
 ME_AUTO, ME_EXACT, ME_INT = 0, 1, 2
 SSE_RGB8_AS_YCBCR = 103
 DIST_RGB, DIST_YCBCR = 1, 2
@@ -32,6 +32,7 @@ SIGNATURES = {
     "ivc_last_cuda_error": (_i, []),
     "ivc_last_cuda_error_string": (C.c_char_p, []),
     "ivc_dct8x8": (_i, [_i, _p, _i, _p, _i, _i64, _i64, _i64, _s5, _p, _i]),
+    "ivc_dct8x8_norm": (_i, [_i, _p, _i, _i, _p, _i, _i64, _i64, _i64, _s5, _p, _i]),
     "ivc_quantize": (_i, [_i, _p, _p, _i, _i64, _i64, _i64, _s5, _p, _i, _i, _p]),
     "ivc_dequantize": (_i, [_i, _p, _p, _i, _i64, _i64, _i64, _s5, _p, _i, _i, _p]),
     "ivc_zigzag": (_i, [_i, _p, _i, _p, _i, _i64, _p]),

@@ -78,6 +78,12 @@ const char *ivc_last_cuda_error_string(void) { return cudaGetErrorString(g_last_
 
 int ivc_dct8x8(int device, void *stream, int inverse, const void *x, int x_dtype, int64_t n0, int64_t n1, int64_t C,
                const int64_t strides[5], void *out, int out_dtype) {
+    return ivc_dct8x8_norm(device, stream, inverse, IVC_NORM_ORTHO, x, x_dtype, n0, n1, C, strides, out, out_dtype);
+}
+
+int ivc_dct8x8_norm(int device, void *stream, int inverse, int norm, const void *x, int x_dtype, int64_t n0, int64_t n1,
+                    int64_t C, const int64_t strides[5], void *out, int out_dtype) {
+    if (norm != IVC_NORM_ORTHO && norm != IVC_NORM_BACKWARD && norm != IVC_NORM_FORWARD) return IVC_ERR_ARG;
     if (n0 < 0 || n1 < 0 || C < 0 || !strides) return IVC_ERR_ARG;
     if (n0 * n1 * C == 0) return IVC_OK;
     if (!x || !out) return IVC_ERR_ARG;
@@ -86,7 +92,7 @@ int ivc_dct8x8(int device, void *stream, int inverse, const void *x, int x_dtype
     if (out_dtype != want) return IVC_ERR_DTYPE;
     IVC_ENTER(device);
     cudaError_t e = ivc::launch_dct(device, (cudaStream_t)stream, inverse != 0, x, x_dtype, n0, n1, C, strides, out,
-                                    want == IVC_F32);
+                                    want == IVC_F32, norm);
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
 

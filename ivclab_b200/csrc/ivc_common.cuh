@@ -22,7 +22,7 @@ cudaError_t launch_inverse_sse(int device, cudaStream_t st, const int32_t *zz, i
                                const void *table, int table_dtype, void *out, const void *orig_rgb8,
                                int64_t orig_frame_stride, int sse_mode, double *partial, double *sse_out);
 cudaError_t launch_dct(int device, cudaStream_t st, bool inverse, const void *x, int x_dtype, int64_t n0, int64_t n1,
-                       int64_t C, const int64_t s[5], void *out, bool f32);
+                       int64_t C, const int64_t s[5], void *out, bool f32, int norm = 0);
 cudaError_t launch_quant(int device, cudaStream_t st, bool dequant, const void *x, int x_dtype, int64_t n0, int64_t n1,
                          int64_t C, const int64_t s[5], const void *table, int table_dtype, bool f32, int32_t *out);
 cudaError_t launch_zigzag(int device, cudaStream_t st, bool inverse, const void *x, int elem_size, int64_t nblocks,

@@ -54,8 +54,17 @@ template <typename T> struct Ducc {
     static __device__ __forceinline__ T sqrt2(T scale) { return (T)SQRT2 * scale; }
 };
 
-// ---- forward: orthonormal DCT-II of x[0..7], in place ------------------------------------------
-template <typename T>
+// scipy's `norm` (dct.py:24,26,42,44 forward it): ducc0 multiplies the FFT output by fct and, for "ortho", the DC term by
+// sqrt2 / 2 (type 2) or sqrt2 (type 3).  For length 8 fct is a power of two in all three modes -- forward transform: ortho
+// 1/4, backward 1, forward 1/16; the inverse takes the complementary factor -- so it folds into the constants exactly.
+enum { kNormOrtho = 0, kNormBackward = 1, kNormForward = 2 };
+template <typename T, int NORM, bool INVERSE>
+__device__ __forceinline__ T dct_fct() {
+    return NORM == kNormOrtho ? (T)0.25 : ((NORM == kNormForward) != INVERSE) ? (T)0.0625 : (T)1.0;
+}
+
+// ---- forward: DCT-II of x[0..7], in place (orthonormal unless NORM says otherwise) --------------
+template <typename T, int NORM = kNormOrtho>
 __device__ __forceinline__ void dct2_8(T (&x)[8]) {
     using R = Rn<T>;
     using K = Ducc<T>;
@@ -81,9 +90,9 @@ __device__ __forceinline__ void dct2_8(T (&x)[8]) {
         o[1] = R::add(p, h5); o[5] = R::sub(p, h5);
         o[7] = R::add(q, h6); o[3] = R::sub(q, h6);
     }
-    // o == (reference's FFT output) / 2.  fct = 0.25, final 0.5*(t1 +- t2): constants carry 0.25.
-    const T s = (T)0.25;
-    x[0] = R::mul(o[0], K::sqrt2(s));                 // * fct * (sqrt2*0.5) * 2
+    // o == (reference's FFT output) / 2.  ortho: fct = 0.25, final 0.5*(t1 +- t2): constants carry 0.25.
+    const T s = dct_fct<T, NORM, false>();
+    x[0] = R::mul(o[0], NORM == kNormOrtho ? K::sqrt2(s) : (T)2 * s);   // * fct * (sqrt2*0.5) * 2; without ortho an exact scaling
 #pragma unroll
     for (int k = 1; k <= 3; ++k) {
         const int kc = 8 - k;
@@ -93,17 +102,17 @@ __device__ __forceinline__ void dct2_8(T (&x)[8]) {
         x[k] = R::add(t1, t2);
         x[kc] = R::sub(t1, t2);
     }
-    x[4] = R::mul(o[4], K::tw(3, (T)0.5));
+    x[4] = R::mul(o[4], K::tw(3, (T)2 * s));
 }
 
-// ---- inverse: orthonormal DCT-III of X[0..7], in place -----------------------------------------
-template <typename T>
+// ---- inverse: DCT-III of X[0..7], in place ----------------------------------------------------
+template <typename T, int NORM = kNormOrtho>
 __device__ __forceinline__ void dct3_8(T (&X)[8]) {
     using R = Rn<T>;
     using K = Ducc<T>;
-    const T s = (T)0.25;                                // fct folded into the pre-step constants
+    const T s = dct_fct<T, NORM, true>();               // fct folded into the pre-step constants
     T c[8];
-    c[0] = R::mul(X[0], K::sqrt2(s));
+    c[0] = R::mul(X[0], NORM == kNormOrtho ? K::sqrt2(s) : s);
 #pragma unroll
     for (int k = 1; k <= 3; ++k) {
         const int kc = 8 - k;
@@ -112,7 +121,7 @@ __device__ __forceinline__ void dct3_8(T (&X)[8]) {
         c[k] = R::add(R::mul(twk, t2), R::mul(twc, t1));
         c[kc] = R::sub(R::mul(twk, t1), R::mul(twc, t2));
     }
-    c[4] = R::mul(X[4], K::tw(3, (T)0.5));              // * (2*tw3) * fct
+    c[4] = R::mul(X[4], K::tw(3, (T)2 * s));            // * (2*tw3) * fct
     // radf4 (ido=1, l1=2): k=0 works on c0,c2,c4,c6; k=1 on c1,c3,c5,c7
     T h[8];
     {

@@ -1809,7 +1809,7 @@ struct DctArgs {
 };
 
 // one warp = 4 blocks; lane (r,u) row pass, lane (j,u) column pass, T buffer [u][j][r] pitch 9
-template <typename T, bool INVERSE>
+template <typename T, bool INVERSE, int NORM = kNormOrtho>
 __global__ void __launch_bounds__(256) k_dct8x8(const DctArgs a) {
     __shared__ T s_T[8][4 * 8 * 9];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1838,14 +1838,14 @@ __global__ void __launch_bounds__(256) k_dct8x8(const DctArgs a) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) x[j] = (T)0;
         }
-        if (INVERSE) dct3_8(x); else dct2_8(x);
+        if (INVERSE) dct3_8<T, NORM>(x); else dct2_8<T, NORM>(x);
 #pragma unroll
         for (int j = 0; j < 8; ++j) tb[j * 9 + r] = x[j];
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] = tb[r * 9 + i];
         __syncwarp();
-        if (INVERSE) dct3_8(x); else dct2_8(x);
+        if (INVERSE) dct3_8<T, NORM>(x); else dct2_8<T, NORM>(x);
         if (valid) {
             T *o = (T *)a.out + blk * 64;
 #pragma unroll
@@ -2128,19 +2128,29 @@ cudaError_t launch_inverse_sse(int device, cudaStream_t st, const int32_t *zz, i
     return cudaGetLastError();
 }
 
+template <int NORM>
+static void launch_dct_norm(int grid, cudaStream_t st, bool inverse, bool f32, const DctArgs &a) {
+    if (f32) {
+        if (inverse) k_dct8x8<float, true, NORM><<<grid, 256, 0, st>>>(a);
+        else k_dct8x8<float, false, NORM><<<grid, 256, 0, st>>>(a);
+    } else {
+        if (inverse) k_dct8x8<double, true, NORM><<<grid, 256, 0, st>>>(a);
+        else k_dct8x8<double, false, NORM><<<grid, 256, 0, st>>>(a);
+    }
+}
+
 cudaError_t launch_dct(int device, cudaStream_t st, bool inverse, const void *x, int x_dtype, int64_t n0, int64_t n1,
-                       int64_t C, const int64_t s[5], void *out, bool f32) {
+                       int64_t C, const int64_t s[5], void *out, bool f32, int norm) {
     DctArgs a;
     a.x = x; a.x_dtype = x_dtype; a.nblocks = n0 * n1 * C; a.n1 = n1; a.C = C; a.out = out;
     for (int i = 0; i < 5; ++i) a.s[i] = s[i];
     if (a.nblocks == 0) return cudaSuccess;
     const int grid = grid_for((a.nblocks + 3) / 4, 8, device, 8);
-    if (f32) {
-        if (inverse) k_dct8x8<float, true><<<grid, 256, 0, st>>>(a);
-        else k_dct8x8<float, false><<<grid, 256, 0, st>>>(a);
-    } else {
-        if (inverse) k_dct8x8<double, true><<<grid, 256, 0, st>>>(a);
-        else k_dct8x8<double, false><<<grid, 256, 0, st>>>(a);
+    switch (norm) {
+        case kNormOrtho: launch_dct_norm<kNormOrtho>(grid, st, inverse, f32, a); break;
+        case kNormBackward: launch_dct_norm<kNormBackward>(grid, st, inverse, f32, a); break;
+        case kNormForward: launch_dct_norm<kNormForward>(grid, st, inverse, f32, a); break;
+        default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }

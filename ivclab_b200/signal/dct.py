@@ -10,7 +10,7 @@ __all__ = ["DiscreteCosineTransform"]
 
 
 class DiscreteCosineTransform:
-    """Forward / inverse orthonormal 8x8 DCT-II over the last two axes.
+    """Forward / inverse 8x8 DCT-II over the last two axes (orthonormal by default; `norm` as scipy spells it).
 
     Same constructor, methods and array conventions as the reference class
     (dct.py:9, :12-28, :30-46): input ``[..., 8, 8]`` (typically the strided
@@ -24,11 +24,16 @@ class DiscreteCosineTransform:
     def __init__(self, norm='ortho'):
         self.norm = norm
 
+    # scipy's spellings of `norm` (the reference forwards it, dct.py:24,26,42,44; ivclab itself only uses 'ortho',
+    # intracodec.py:25, tests/ch3.py:15) -> IVC_NORM_*
+    _NORMS = {'ortho': 0, None: 1, 'backward': 1, 'forward': 2}
+
     def _run(self, x, inverse: bool):
-        if self.norm != 'ortho':
-            # the reference forwards `norm` to scipy; only 'ortho' is used anywhere in ivclab
-            # (intracodec.py:25, tests/ch3.py:15) and only 'ortho' is implemented here.
-            raise NotImplementedError(f"norm={self.norm!r}: only norm='ortho' is implemented")
+        try:
+            norm = self._NORMS[self.norm]
+        except (KeyError, TypeError):
+            # what scipy raises, at the call (not in the constructor), for anything else
+            raise ValueError(f'Invalid norm value {self.norm!r}; should be "backward", "ortho" or "forward".') from None
         t, was_np = to_device(x)
         if t.ndim < 2 or t.shape[-1] != 8 or t.shape[-2] != 8:
             raise ValueError(f"expected [..., 8, 8] patches, got shape {tuple(t.shape)}")
@@ -42,9 +47,9 @@ class DiscreteCosineTransform:
         out_dtype = torch.float32 if v.dtype == torch.float32 else torch.float64
         out = torch.empty(v.shape, dtype=out_dtype, device=v.device)
         n0, n1, c = v.shape[:3]
-        st = _lib.lib.ivc_dct8x8(dev_index(v), stream_ptr(v.device), int(inverse), v.data_ptr(), code(v.dtype),
-                                 n0, n1, c, _lib.strides5(v.stride()), out.data_ptr(), code(out_dtype))
-        _lib.check(st, "ivc_dct8x8")
+        st = _lib.lib.ivc_dct8x8_norm(dev_index(v), stream_ptr(v.device), int(inverse), norm, v.data_ptr(), code(v.dtype),
+                                      n0, n1, c, _lib.strides5(v.stride()), out.data_ptr(), code(out_dtype))
+        _lib.check(st, "ivc_dct8x8_norm")
         return to_host(out.reshape(shape), was_np)
 
     def transform(self, patched_img):

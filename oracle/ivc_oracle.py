@@ -126,18 +126,31 @@ def _consts(T):
 # --------------------------------------------------------------------------
 # 2. 8-point DCT-II / DCT-III, op-for-op as ducc0 evaluates them
 # --------------------------------------------------------------------------
-def dct2_8(x: np.ndarray) -> np.ndarray:
-    """Orthonormal DCT-II along the last axis (length 8), bit-identical to
-    ``scipy.fft.dct(x, axis=-1, norm='ortho')`` (reference dct.py:24,26).
+_NORMS = ("ortho", "backward", "forward")
+
+
+def _norm_name(norm):
+    """scipy's spelling: None means 'backward' (the forward transform is unscaled)."""
+    norm = "backward" if norm is None else norm
+    if norm not in _NORMS:
+        raise ValueError(f'Invalid norm value {norm!r}; should be "backward", "ortho" or "forward".')
+    return norm
+
+
+def dct2_8(x: np.ndarray, norm="ortho") -> np.ndarray:
+    """DCT-II along the last axis (length 8), bit-identical to
+    ``scipy.fft.dct(x, axis=-1, norm=norm)`` (reference dct.py:24,26 forward ``self.norm``; 'ortho' everywhere in ivclab).
 
     float32 in -> float32 arithmetic; anything else -> float64.
     Every ``*2``/``*0.25``/``*0.5`` is an exact power-of-two scaling; all other
     operations are individually rounded (no FMA), in exactly this order.
+    ducc0's factor for length 8: ortho 1/sqrt(16), backward 1, forward 1/16 -- all powers of two.
     """
+    norm = _norm_name(norm)
     T = np.float32 if x.dtype == np.float32 else np.float64
     tw, wa0, wa1, sq2 = _consts(T)
     c = [x[..., i].astype(T) for i in range(8)]
-    two, half, fct = T(2), T(0.5), T(0.25)
+    two, half, fct = T(2), T(0.5), T({"ortho": 0.25, "backward": 1.0, "forward": 0.0625}[norm])
     # T_dcst23::exec, type 2 pre-processing
     c[0] = c[0] * two
     c[7] = c[7] * two
@@ -168,9 +181,9 @@ def dct2_8(x: np.ndarray) -> np.ndarray:
         o[k + 4] = tr2 - tr3
         o[k + 6] = tr1 + tr4
         o[k + 2] = tr1 - tr4
-    o = [v * fct for v in o]                       # fct = 1/sqrt(2*8) = 0.25
+    o = [v * fct for v in o]                       # ortho: fct = 1/sqrt(2*8) = 0.25
     r = [None] * 8
-    r[0] = o[0] * (sq2 * half)
+    r[0] = o[0] * (sq2 * half) if norm == "ortho" else o[0]
     for k, kc in ((1, 7), (2, 6), (3, 5)):
         t1 = tw[k - 1] * o[kc] + tw[kc - 1] * o[k]
         t2 = tw[k - 1] * o[k] - tw[kc - 1] * o[kc]
@@ -180,16 +193,18 @@ def dct2_8(x: np.ndarray) -> np.ndarray:
     return np.stack(r, axis=-1)
 
 
-def dct3_8(x: np.ndarray) -> np.ndarray:
-    """Orthonormal DCT-III (= inverse of DCT-II) along the last axis, length 8,
-    bit-identical to ``scipy.fft.idct(x, axis=-1, norm='ortho')`` (reference
-    dct.py:42,44)."""
+def dct3_8(x: np.ndarray, norm="ortho") -> np.ndarray:
+    """DCT-III (= inverse of DCT-II) along the last axis, length 8,
+    bit-identical to ``scipy.fft.idct(x, axis=-1, norm=norm)`` (reference
+    dct.py:42,44).  The inverse carries the factor the forward direction left out: backward 1/16, forward 1."""
+    norm = _norm_name(norm)
     T = np.float32 if x.dtype == np.float32 else np.float64
     tw, wa0, wa1, sq2 = _consts(T)
     c = [x[..., i].astype(T) for i in range(8)]
-    two, fct = T(2), T(0.25)
+    two, fct = T(2), T({"ortho": 0.25, "backward": 0.0625, "forward": 1.0}[norm])
     # T_dcst23::exec, type 3 pre-processing
-    c[0] = c[0] * sq2
+    if norm == "ortho":
+        c[0] = c[0] * sq2
     for k, kc in ((1, 7), (2, 6), (3, 5)):
         t1 = c[k] + c[kc]
         t2 = c[k] - c[kc]
@@ -230,15 +245,15 @@ def _apply_2d(fn, x):
     return np.ascontiguousarray(np.swapaxes(fn(np.swapaxes(t, -1, -2)), -1, -2))
 
 
-def dct8x8_forward(patches: np.ndarray) -> np.ndarray:
+def dct8x8_forward(patches: np.ndarray, norm="ortho") -> np.ndarray:
     """``DiscreteCosineTransform.transform`` (dct.py:12-28): DCT-II over axis -1
     then axis -2 of ``[..., 8, 8]``; f32->f32, everything else ->f64."""
-    return _apply_2d(dct2_8, np.asarray(patches))
+    return _apply_2d(lambda v: dct2_8(v, norm), np.asarray(patches))
 
 
-def dct8x8_inverse(patches: np.ndarray) -> np.ndarray:
+def dct8x8_inverse(patches: np.ndarray, norm="ortho") -> np.ndarray:
     """``DiscreteCosineTransform.inverse_transform`` (dct.py:30-46)."""
-    return _apply_2d(dct3_8, np.asarray(patches))
+    return _apply_2d(lambda v: dct3_8(v, norm), np.asarray(patches))
 
 
 # --------------------------------------------------------------------------

@@ -614,3 +614,34 @@ def test_exact_search_generations_agree_randomised():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.run(seed=11, N=150, verbose=False) == []
+
+
+def test_dct_other_norms_bit_identical_to_scipy():
+    """`DiscreteCosineTransform(norm=...)`: the reference hands `norm` to scipy.fft.dct / idct (dct.py:9-10,24,26,42,44);
+    None / 'backward' / 'forward' through ivc_dct8x8_norm against the oracle (pinned to scipy on the CPU suite) and against
+    scipy itself where it is importable -- float64, float32, int32 and uint8 inputs, a strided patch view, and scipy's
+    ValueError for anything else."""
+    rng = np.random.default_rng(21)
+    img = rng.uniform(-300, 300, size=(48, 64, 3))
+    view = ivc.Patcher().patch(img)                                            # the strided [Hp, Wp, C, 8, 8] view
+    cases = [view, rng.standard_normal((7, 5, 3, 8, 8)).astype(np.float32) * 100,
+             rng.integers(-500, 500, size=(4, 6, 1, 8, 8)).astype(np.int32), rng.integers(0, 256, size=(3, 8, 8)).astype(np.uint8)]
+    try:
+        from scipy.fft import dct, idct
+    except ImportError:                                                        # the oracle is the checker either way
+        dct = idct = None
+    for norm in (None, "backward", "forward", "ortho"):
+        t = ivc.DiscreteCosineTransform(norm=norm)
+        assert t.norm == norm
+        for x in cases:
+            f, b = t.transform(x), t.inverse_transform(x)
+            assert f.dtype == (np.float32 if x.dtype == np.float32 else np.float64) and f.flags.c_contiguous
+            assert np.array_equal(f, O.dct8x8_forward(np.ascontiguousarray(x), norm))
+            assert np.array_equal(b, O.dct8x8_inverse(np.ascontiguousarray(x), norm))
+            if dct is not None:
+                assert np.array_equal(f, dct(dct(x, axis=-1, norm=norm), axis=-2, norm=norm))
+                assert np.array_equal(b, idct(idct(x, axis=-1, norm=norm), axis=-2, norm=norm))
+        d = t.transform(torch.from_numpy(np.ascontiguousarray(view)).cuda())    # CUDA tensor in -> CUDA tensor out
+        assert d.is_cuda and np.array_equal(d.cpu().numpy(), O.dct8x8_forward(np.ascontiguousarray(view), norm))
+    with pytest.raises(ValueError):
+        ivc.DiscreteCosineTransform(norm="bogus").transform(view)

@@ -38,6 +38,23 @@ def test_oracle_dct_matches_scipy_here():
     assert np.array_equal(O.dct3_8(xi), idct(xi, axis=-1, norm="ortho"))
 
 
+def test_oracle_dct_other_norms_match_scipy_here():
+    """The reference forwards `norm` to scipy (dct.py:24,26,42,44): None / 'backward' / 'forward' as scipy computes them,
+    one axis and the 2-D composition the class applies."""
+    from scipy.fft import dct, idct
+    rng = np.random.default_rng(1)
+    for dt in (np.float64, np.float32):
+        for scale in (1.0, 300.0, 1e-4):
+            x = (rng.standard_normal((600, 8, 8)) * scale).astype(dt)
+            for norm in (None, "backward", "forward", "ortho"):
+                assert np.array_equal(O.dct2_8(x, norm), dct(x, axis=-1, norm=norm))
+                assert np.array_equal(O.dct3_8(x, norm), idct(x, axis=-1, norm=norm))
+                assert np.array_equal(O.dct8x8_forward(x, norm), dct(dct(x, axis=-1, norm=norm), axis=-2, norm=norm))
+                assert np.array_equal(O.dct8x8_inverse(x, norm), idct(idct(x, axis=-1, norm=norm), axis=-2, norm=norm))
+    with pytest.raises(ValueError):
+        O.dct2_8(np.zeros((1, 8)), "bogus")
+
+
 @pytest.mark.parametrize("qi", range(4))
 def test_oracle_intra_golden(g1, g2, qi):
     tab = O.quant_table(QSCALES[qi])
@@ -191,7 +208,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(raw, n), f"{n} declared in include/ivclab_b200.h but not exported"
     assert set(names) == set(_lib.SIGNATURES), "ctypes table and header disagree"
-    assert _lib.lib.ivc_abi_version() == _lib.ABI_VERSION == 7
+    assert _lib.lib.ivc_abi_version() == _lib.ABI_VERSION == 8
     assert b"sm_100a" in _lib.lib.ivc_build_info()
     assert _lib.lib.ivc_me_workspace_bytes(2, 16, 16) >= 4
     assert ivclab_b200.__version__
