@@ -502,19 +502,6 @@ __global__ void __launch_bounds__(kMeThreads, CSPAN ? 3 : 2) k_me_exact2(const M
     __shared__ int s_mvw[kMeWarps][8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     bool chroma_twice = false;
-    if (STEP) {
-        if (tid < 192) {
-            const double t = load_table_elem(a.table, a.table_dtype, tid);
-            s_qt[192 + tid] = t;
-            s_qt[tid] = __drcp_rn(t);
-            if (tid < 64) s_qt[384 + (tid & 7) * 8 + (tid >> 3)] = t;
-        }
-        bool same = true;
-        if (tid < 64)
-            same = __double_as_longlong(load_table_elem(a.table, a.table_dtype, 64 + tid)) ==
-                   __double_as_longlong(load_table_elem(a.table, a.table_dtype, 128 + tid));
-        chroma_twice = __syncthreads_and(same) != 0;
-    }
     double *s_win = reinterpret_cast<double *>(smem_raw);                     // [R][P]
     double *s_cur = reinterpret_cast<double *>(smem_raw + a.cur_off);         // [tby*tbx][kExactCurPitch]
     unsigned *s_u = reinterpret_cast<unsigned *>(smem_raw + a.win32_off);     // [R][PU]  unaligned-word view of the quantised window
@@ -575,7 +562,21 @@ __global__ void __launch_bounds__(kMeThreads, CSPAN ? 3 : 2) k_me_exact2(const M
                 cp_async_zfill<8>(cur_s + (uint32_t)(((row >> 3) * a.tbx + (col >> 3)) * kExactCurPitch + (row & 7) * 8 + (col & 7)) * 8u, cp + col, true);
         }
     }
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (STEP) {                                          // the tables, while the tile's copies are in flight
+        if (tid < 192) {
+            const double t = load_table_elem(a.table, a.table_dtype, tid);
+            s_qt[192 + tid] = t;
+            s_qt[tid] = __drcp_rn(t);
+            if (tid < 64) s_qt[384 + (tid & 7) * 8 + (tid >> 3)] = t;
+        }
+        bool same = true;
+        if (tid < 64)
+            same = __double_as_longlong(load_table_elem(a.table, a.table_dtype, 64 + tid)) ==
+                   __double_as_longlong(load_table_elem(a.table, a.table_dtype, 128 + tid));
+        chroma_twice = __syncthreads_and(same) != 0;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (interior) mbar_wait(bar, 0);
     __syncthreads();
 
