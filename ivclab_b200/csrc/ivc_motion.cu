@@ -13,7 +13,12 @@
 // fixed pairwise tree; motion.py:46 == np.sum of a contiguous 64-element array) with individually
 // rounded sub/mul/add, so motion vectors are bit-exact for arbitrary float frames.  The argmin is
 // lexicographic on (ssd, index) == the reference's "first strict minimum in (dy, dx) raster order"
-// (motion.py:35-51).
+// (motion.py:35-51).  It serves float32 frames (and IVC_ME_EXACT_V1=1).
+//
+// K3 exact, second generation (k_me_exact2, float64 frames): the same answer with about one such evaluation per block --
+// a byte prefilter (vabsdiff4 + dp4a on the tile quantised with its own affine map) and a rounding bound prove every
+// other candidate away; k_me_exact2<STEP> goes on to code and reconstruct the warp's blocks (the closed-loop P-frame in
+// one kernel, ivc_pframe_step).
 //
 // K3 integer (k_me_int<T,G,PC>): reads the float frames directly (or uint8 planes as they are), converts them to
 // packed uint8 while staging (raising a device flag if any value is not an integer in [0,255]) and evaluates
