@@ -233,10 +233,11 @@ def cfg3(cx, ivc, pool=1024, chunk=8):
            "frames": pool, "qscales": Q, "frames_per_rank": Fl,
            "resident": {"ms": round(ms_res, 3), "mpixel_s": round(pool * Q * px / ms_res / 1e3, 1),
                         "us_per_rd_point": round(ms_res * 1e3 / (Fl * Q), 2),
-                        # per RD point and pixel: RGB in 3 + indices out 12 (forward), indices in 12 (statistics),
-                        # indices in 12 + RGB in 3 (decode + distortion) = 42 bytes
-                        "hbm_frac": round(Fl * Q * px * 42 / (ms_res * 1e-3) / 1e9 / cx.peak, 4),
-                        "bound": "FP64 pipe / issue (forward from RGB: 21 rounded FP64 ops per sample, decoder + ycbcr2rgb + error: 27)"},
+                        # per RD point and pixel: RGB in 3 / Q + indices out 12 (forward, all scales in one kernel), indices
+                        # in 12 (statistics), indices in 12 + RGB in 3 (decode + distortion) = 39 bytes + 3 / Q
+                        "hbm_frac": round(Fl * px * (Q * 39 + 3) / (ms_res * 1e-3) / 1e9 / cx.peak, 4),
+                        "bound": "FP64 pipe / issue of the decoder (dequantise + IDCT + ycbcr2rgb + error: 27 rounded FP64 ops per sample); "
+                                 "colour transform + DCT run once per frame for all scales (ivc_intra_forward_rgb8_multi)"},
            "e2e": {"ms": round(ms_fed, 3), "mpixel_s": round(pool * Q * px / ms_fed / 1e3, 1),
                    "h2d_bytes": pool * px * 3, "d2h_bytes": Q * pool * (8 + 4 * NB + 4),
                    "gather_ms": round(ms_gather, 3), "gather": how + "; inside the timed region"}}

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define IVC_ABI_VERSION 8
+#define IVC_ABI_VERSION 9
 
 /* element types */
 #define IVC_U8   0
@@ -362,6 +362,17 @@ int ivc_intra_forward_rgb8(int device, void *stream,
 int ivc_intra_forward_rgb8_zr(int device, void *stream, const void *rgb, int64_t n_frames, int64_t H, int64_t W,
                               int64_t frame_stride_bytes, const void *table, int table_dtype, int32_t *out,
                               int32_t *counts_out, uint64_t *masks_out);
+
+/* The same transform quantised with n_tables tables at once: a rate-distortion sweep codes every frame at each of its
+ * scales (exercises/ch4/ex1.py:385-405: `for q in scales: IntraCodec(quantization_scale=q) ...` over the same images),
+ * and rgb2ycbcr + DCT do not depend on the scale.  tables: device [n_tables,3,8,8]; out: [n_tables, n_frames, Hp, Wp, 3, 64],
+ * out[t] identical to ivc_intra_forward_rgb8 with table t; counts_out / masks_out: both NULL, or [n_tables, n_frames*Hp*Wp*3]
+ * as in the _zr variant.  n_tables <= IVC_MAX_FORWARD_TABLES. */
+#define IVC_MAX_FORWARD_TABLES 16
+int ivc_intra_forward_rgb8_multi(int device, void *stream,
+                                 const void *rgb, int64_t n_frames, int64_t H, int64_t W, int64_t frame_stride_bytes,
+                                 const void *tables, int table_dtype, int n_tables, int32_t *out,
+                                 int32_t *counts_out, uint64_t *masks_out);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ reference codecs on top.  Everything executes in hand-written CUDA kernels behin
 extension has not been built, and calling it fails if no CUDA device is visible.
 """
 from . import _lib  # noqa: F401  (loads libivcb200.so or raises)
-from .codec import IntraBlockCoder, PFrameBlockCoder
+from .codec import IntraBlockCoder, PFrameBlockCoder, forward_rgb_multi
 from .entropy import ZeroRunCoder, stats_marg, symbol_histogram, symbol_minmax, zerorun_symbol_histogram
 from .image import IntraCodec
 from ._runtime import set_device_memo
@@ -28,6 +28,6 @@ from .video import ClosedLoopLumaCoder, MotionCompensator
 
 __version__ = "0.1.0"
 __all__ = ["DiscreteCosineTransform", "PatchQuant", "ZigZag", "Patcher", "MotionCompensator",
-           "IntraBlockCoder", "PFrameBlockCoder", "IntraCodec", "ClosedLoopLumaCoder", "ZeroRunCoder", "calc_mse", "calc_psnr",
+           "IntraBlockCoder", "PFrameBlockCoder", "forward_rgb_multi", "IntraCodec", "ClosedLoopLumaCoder", "ZeroRunCoder", "calc_mse", "calc_psnr",
            "frame_sse", "frame_sse_rgb8_vs_ycbcr", "rgb2ycbcr", "ycbcr2rgb", "luma8_from_rgb8", "StreamedCoder", "stats_marg", "symbol_minmax", "symbol_histogram", "zerorun_symbol_histogram",
            "install", "inject", "set_device_memo", "RateDistortionSweep"]

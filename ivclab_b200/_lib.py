@@ -14,8 +14,8 @@ LIB_PATH = os.path.join(_HERE, "_C", "libivcb200.so")
 
 # element type codes (include/ivclab_b200.h)
 U8, I32, F32, F64, I64, I16 = 0, 1, 2, 3, 4, 5
-ABI_VERSION = 8            # include/ivclab_b200.h IVC_ABI_VERSION (2: entry points added in round 1, zero-run write gained a length; 3: ivc_rgb8_to_luma8;
-                           # 4: ivc_pframe_forward_ch, ivc_zerorun_symbol_histogram; 5: ivc_pframe_search_forward; 6: the _zr variants; 7: ivc_pframe_step; 8: ivc_dct8x8_norm)
+ABI_VERSION = 9            # include/ivclab_b200.h IVC_ABI_VERSION (2: entry points added in round 1, zero-run write gained a length; 3: ivc_rgb8_to_luma8;
+                           # 4: ivc_pframe_forward_ch, ivc_zerorun_symbol_histogram; 5: ivc_pframe_search_forward; 6: the _zr variants; 7: ivc_pframe_step; 8: ivc_dct8x8_norm; 9: ivc_intra_forward_rgb8_multi)
 ME_AUTO, ME_EXACT, ME_INT = 0, 1, 2
 SSE_RGB8_AS_YCBCR = 103
 DIST_RGB, DIST_YCBCR = 1, 2
@@ -72,6 +72,7 @@ SIGNATURES = {
     "ivc_rgb8_to_luma8": (_i, [_i, _p, _p, _i64, _p, _p]),
     "ivc_intra_forward_rgb8": (_i, [_i, _p, _p, _i64, _i64, _i64, _i64, _p, _i, _p]),
     "ivc_intra_forward_rgb8_zr": (_i, [_i, _p, _p, _i64, _i64, _i64, _i64, _p, _i, _p, _p, _p]),
+    "ivc_intra_forward_rgb8_multi": (_i, [_i, _p, _p, _i64, _i64, _i64, _i64, _p, _i, _i, _p, _p, _p]),
 }
 
 

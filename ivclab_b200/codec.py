@@ -14,7 +14,7 @@ from ._runtime import aligned16, code, dev_index, stream_ptr, to_device, to_host
 from .quantization import PatchQuant
 from .video import MotionCompensator
 
-__all__ = ["IntraBlockCoder", "PFrameBlockCoder"]
+__all__ = ["IntraBlockCoder", "PFrameBlockCoder", "forward_rgb_multi"]
 
 
 class IntraBlockCoder:
@@ -148,6 +148,43 @@ class IntraBlockCoder:
         if not batched:
             sse, out = sse[0], (out[0] if out is not None else None)
         return (sse, out) if return_reconstruction else sse
+
+
+MAX_FORWARD_TABLES = 16                  # include/ivclab_b200.h IVC_MAX_FORWARD_TABLES
+
+
+def forward_rgb_multi(coders, rgb, zr=False):
+    """``[c.forward_rgb(rgb) for c in coders]`` as ONE kernel: the colour transform and the DCT of a frame do not depend on
+    the quantisation scale, so a rate-distortion sweep (exercises/ch4/ex1.py:385-405) transforms each frame once and
+    quantises it ``len(coders)`` times.  rgb: CUDA uint8 ``[N, H, W, 3]`` with ``W % 16 == 0``; returns int32
+    ``[Q, N, Hp, Wp, 3, 64]`` (``zr=True``: also counts ``[Q, N*Hp*Wp*3]`` int32 and masks int64, as ``forward_rgb``).
+    Coders whose tables differ in dtype (float32 for a Python-float scale, float64 for ``np.float64``) and lists longer
+    than ``MAX_FORWARD_TABLES`` are handled in groups."""
+    coders = list(coders)
+    if not isinstance(rgb, torch.Tensor) or not rgb.is_cuda or rgb.dtype != torch.uint8 or rgb.ndim != 4 or rgb.shape[-1] != 3:
+        raise ValueError("forward_rgb_multi takes a CUDA uint8 tensor [N, H, W, 3]")
+    N, H, W, _ = rgb.shape
+    if H % 8 or W % 16:
+        raise ValueError("forward_rgb_multi needs H % 8 == 0 and W % 16 == 0")
+    v = aligned16(rgb)
+    Q = len(coders)
+    out = torch.empty((Q, N, H // 8, W // 8, 3, 64), dtype=torch.int32, device=v.device)
+    nsb = N * (H // 8) * (W // 8) * 3
+    counts = torch.empty((Q, nsb), dtype=torch.int32, device=v.device) if zr else None
+    masks = torch.empty((Q, nsb), dtype=torch.int64, device=v.device) if zr else None
+    tabs = [c.quant._table_on(v.device)[1] for c in coders]
+    i = 0
+    while i < Q:
+        j = i + 1
+        while j < Q and j - i < MAX_FORWARD_TABLES and tabs[j].dtype == tabs[i].dtype:
+            j += 1
+        dtab = torch.stack(tabs[i:j]).contiguous()
+        st = _lib.lib.ivc_intra_forward_rgb8_multi(
+            dev_index(v), stream_ptr(v.device), v.data_ptr(), N, H, W, H * W * 3, dtab.data_ptr(), code(dtab.dtype), j - i,
+            out[i].data_ptr(), counts[i].data_ptr() if zr else None, masks[i].data_ptr() if zr else None)
+        _lib.check(st, "ivc_intra_forward_rgb8_multi")
+        i = j
+    return (out, counts, masks) if zr else out
 
 
 class PFrameBlockCoder:

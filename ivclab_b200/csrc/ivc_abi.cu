@@ -619,4 +619,20 @@ int ivc_intra_forward_rgb8_zr(int device, void *stream, const void *rgb, int64_t
     return e == cudaSuccess ? IVC_OK : cuda_fail(e);
 }
 
+int ivc_intra_forward_rgb8_multi(int device, void *stream, const void *rgb, int64_t n_frames, int64_t H, int64_t W,
+                                 int64_t frame_stride_bytes, const void *tables, int table_dtype, int n_tables, int32_t *out,
+                                 int32_t *counts_out, uint64_t *masks_out) {
+    if (n_frames < 0 || H < 0 || W < 0 || frame_stride_bytes < 0) return IVC_ERR_ARG;
+    if (n_tables < 1 || n_tables > IVC_MAX_FORWARD_TABLES) return IVC_ERR_ARG;
+    if (!is_float(table_dtype)) return IVC_ERR_DTYPE;
+    if ((H & 7) || (W & 15)) return IVC_ERR_SHAPE;
+    if (n_frames * H * W == 0) return IVC_OK;
+    if (!rgb || !tables || !out || (!counts_out != !masks_out)) return IVC_ERR_ARG;
+    if (!aligned16(rgb) || !aligned16(out) || (frame_stride_bytes & 15)) return IVC_ERR_ARG;
+    IVC_ENTER(device);
+    cudaError_t e = ivc::launch_forward_rgb8(device, (cudaStream_t)stream, rgb, n_frames, H, W, frame_stride_bytes, tables,
+                                             table_dtype, out, counts_out, masks_out, n_tables);
+    return e == cudaSuccess ? IVC_OK : cuda_fail(e);
+}
+
 }  // extern "C"

@@ -83,6 +83,6 @@ cudaError_t launch_color(int device, cudaStream_t st, bool to_rgb, const void *i
 cudaError_t launch_rgb8_luma8(int device, cudaStream_t st, const void *rgb, int64_t npix, void *out, void *out64);
 cudaError_t launch_forward_rgb8(int device, cudaStream_t st, const void *rgb, int64_t n, int64_t H, int64_t W,
                                 int64_t frame_stride_bytes, const void *table, int table_dtype, int32_t *out,
-                                int32_t *zr_counts = nullptr, uint64_t *zr_masks = nullptr);
+                                int32_t *zr_counts = nullptr, uint64_t *zr_masks = nullptr, int nq = 1);
 
 }  // namespace ivc

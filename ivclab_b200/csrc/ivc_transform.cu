@@ -112,6 +112,11 @@ struct FwdArgs {
     const int *run_flag;             // P-frame: when not null the kernel runs only if *run_flag != 0 (fallback after the fused search)
     int32_t *zr_counts;              // optional (TMA forward kernels): per scan block, the symbols ZeroRunCoder.encode emits for it ...
     unsigned long long *zr_masks;    // ... and its 64-bit non-zero mask: the zero-run coder's count pass, done while the block is in smem
+    // k_forward_rgb8_tma only: nq quantisation tables [nq][3][64] applied to ONE transform of the frames (a rate-distortion sweep
+    // codes the same frame at every scale: colour transform and DCT do not depend on the scale)
+    int nq = 1;
+    int64_t out_q_stride = 0;        // int32 elements between the outputs of successive tables
+    int64_t zr_q_stride = 0;         // scan blocks between the counts / masks of successive tables
 };
 
 template <int C, bool PFRAME>
@@ -661,22 +666,26 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_c3_tma(const F
 constexpr int kRgbPitch = 112;                       // 96 B of pixels + 16 B pad (bulk copies need 16-byte rows)
 constexpr int kRgbIn = 8 * kRgbPitch;                // 896
 constexpr int kRgbBuf = 7424;                        // kRgbIn + kWorkBytes rounded up to 128
+constexpr int kMaxForwardScales = 16;                // tables of one launch: 16 x 3 KB next to the warps' buffers keeps two CTAs per SM
 static_assert(kRgbIn + kWorkBytes <= kRgbBuf && kRgbBuf % 128 == 0, "layout");
 
+template <bool MULTI>                                // MULTI: a.nq tables (a runtime loop around the quantiser); else exactly one
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_rgb8_tma(const FwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *s_rt = reinterpret_cast<double *>(smem_raw);                       // [192]
-    double *s_t = s_rt + 192;                                                   // [192]
-    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem_raw + 3072);   // [8]
+    double *s_rt = reinterpret_cast<double *>(smem_raw);                       // [nq][fl(1/t) 192 | t 192]
+    const int nq = MULTI ? a.nq : 1;
+    const int tab_bytes = nq * 3072;
+    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem_raw + tab_bytes);   // [8]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char *in_b = smem_raw + 3200 + warp * kRgbBuf;          // 8 rows x 96 B of packed RGB, pitch 112 B
+    unsigned char *in_b = smem_raw + tab_bytes + 128 + warp * kRgbBuf;   // 8 rows x 96 B of packed RGB, pitch 112 B
     unsigned char *work_b = in_b + kRgbIn;
     const uint32_t bar = smem_u32(s_bar + warp), in_s = smem_u32(in_b), work_s = smem_u32(work_b);
 
-    for (int i = threadIdx.x; i < 192; i += blockDim.x) {
+    for (int i = threadIdx.x; i < 192 * nq; i += blockDim.x) {
+        const int q = i / 192, e = i - q * 192;
         const double t = load_table_elem(a.table, a.table_dtype, i);
-        s_t[i] = t;
-        s_rt[i] = __drcp_rn(t);
+        s_rt[q * 384 + 192 + e] = t;
+        s_rt[q * 384 + e] = __drcp_rn(t);
     }
     if (lane == 0) mbar_init(bar, 1);
     fence_mbar_init();
@@ -694,7 +703,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_rgb8_tma(const
     }
 #pragma unroll
     for (int v = 0; v < 8; ++v) zz_wr[v] = work_b + (u * kStageUF + ZZ_ORDER[v * 8 + r]) * 4;   // + m*256
-    const double *rt_l = s_rt + r, *t_l = s_t + r;
+    const double *rt_l0 = s_rt + r;
 
     const TileGeom &g = a.g;
     const int64_t row_elems = g.W * 3;                                   // BYTES per image row (uint8 RGB)
@@ -764,46 +773,50 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_forward_rgb8_tma(const
             dct2_8(x[m]);
         }
         __syncwarp();
-        QuantGuard qg;
-        {
-            double rtv[3][8];                           // loaded as one batch: the staging stores below would otherwise
-#pragma unroll                                          // serialise each (possibly aliasing) shared-memory load
-            for (int m = 0; m < 3; ++m)
-#pragma unroll
-                for (int v = 0; v < 8; ++v) rtv[m][v] = rt_l[m * 64 + v * 8];
-            int qv[3][8];
-#pragma unroll
-            for (int m = 0; m < 3; ++m)
-#pragma unroll
-                for (int v = 0; v < 8; ++v) qv[m][v] = qg.q(x[m][v], rtv[m][v]);
-#pragma unroll
-            for (int m = 0; m < 3; ++m)
-#pragma unroll
-                for (int v = 0; v < 8; ++v) *reinterpret_cast<int *>(zz_wr[v] + m * 256) = qv[m][v];
-        }
-        if (__builtin_expect(qg.risky(), 0)) {          // rare: redo this lane's 24 samples with the IEEE division
-#pragma unroll
-            for (int m = 0; m < 3; ++m)
-#pragma unroll
-                for (int v = 0; v < 8; ++v)
-                    *reinterpret_cast<int *>(zz_wr[v] + m * 256) = quantize_exact_f64(x[m][v], t_l[m * 64 + v * 8]);
-        }
-        fence_proxy_async();                            // make the staging visible to the bulk-copy unit
-        __syncwarp();
-        {
-            const int b0 = cur.tx * 4, nb = min(4, g.Wp - b0);
-            if (lane < nb) {                              // lane u stores the 3 scan blocks of image block u
-                int32_t *outf = a.out + ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0 + lane) * 192;
-                bulk_s2g(outf, work_s + lane * (kStageUF * 4), 768u);
-                bulk_commit();
+        for (int q = 0; q < nq; ++q) {                  // one transform, nq quantisations (nq = 1: the plain forward)
+            if (q) { bulk_wait_read0(); __syncwarp(); } // the previous scale's stores have drained the staging area
+            const double *rt_l = rt_l0 + q * 384, *t_l = rt_l + 192;
+            QuantGuard qg;
+            {
+                double rtv[3][8];                           // loaded as one batch: the staging stores below would otherwise
+    #pragma unroll                                          // serialise each (possibly aliasing) shared-memory load
+                for (int m = 0; m < 3; ++m)
+    #pragma unroll
+                    for (int v = 0; v < 8; ++v) rtv[m][v] = rt_l[m * 64 + v * 8];
+                int qv[3][8];
+    #pragma unroll
+                for (int m = 0; m < 3; ++m)
+    #pragma unroll
+                    for (int v = 0; v < 8; ++v) qv[m][v] = qg.q(x[m][v], rtv[m][v]);
+    #pragma unroll
+                for (int m = 0; m < 3; ++m)
+    #pragma unroll
+                    for (int v = 0; v < 8; ++v) *reinterpret_cast<int *>(zz_wr[v] + m * 256) = qv[m][v];
             }
-            if (a.zr_masks) {                             // scan block j = 3 u + m of the tile, in (h w c) order
-                unsigned long long mk;
-                zr_masks_from_staging<12>(work_b, [](int j) { return (j / 3) * (kStageUF * 4) + (j % 3) * 256; }, lane, mk);
-                if (lane < 3 * nb) {
-                    const int64_t sblk = ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0) * 3 + lane;
-                    a.zr_masks[sblk] = mk;
-                    a.zr_counts[sblk] = zr_block_count(mk);
+            if (__builtin_expect(qg.risky(), 0)) {          // rare: redo this lane's 24 samples with the IEEE division
+    #pragma unroll
+                for (int m = 0; m < 3; ++m)
+    #pragma unroll
+                    for (int v = 0; v < 8; ++v)
+                        *reinterpret_cast<int *>(zz_wr[v] + m * 256) = quantize_exact_f64(x[m][v], t_l[m * 64 + v * 8]);
+            }
+            fence_proxy_async();                            // make the staging visible to the bulk-copy unit
+            __syncwarp();
+            {
+                const int b0 = cur.tx * 4, nb = min(4, g.Wp - b0);
+                if (lane < nb) {                              // lane u stores the 3 scan blocks of image block u
+                    int32_t *outf = a.out + q * a.out_q_stride + ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0 + lane) * 192;
+                    bulk_s2g(outf, work_s + lane * (kStageUF * 4), 768u);
+                    bulk_commit();
+                }
+                if (a.zr_masks) {                             // scan block j = 3 u + m of the tile, in (h w c) order
+                    unsigned long long mk;
+                    zr_masks_from_staging<12>(work_b, [](int j) { return (j / 3) * (kStageUF * 4) + (j % 3) * 256; }, lane, mk);
+                    if (lane < 3 * nb) {
+                        const int64_t sblk = q * a.zr_q_stride + ((cur.frame * g.Hp + cur.by) * (int64_t)g.Wp + b0) * 3 + lane;
+                        a.zr_masks[sblk] = mk;
+                        a.zr_counts[sblk] = zr_block_count(mk);
+                    }
                 }
             }
         }
@@ -2045,17 +2058,25 @@ cudaError_t launch_forward(int device, cudaStream_t st, const void *img, int64_t
 
 cudaError_t launch_forward_rgb8(int device, cudaStream_t st, const void *rgb, int64_t n, int64_t H, int64_t W,
                                 int64_t frame_stride_bytes, const void *table, int table_dtype, int32_t *out,
-                                int32_t *zr_counts, uint64_t *zr_masks) {
+                                int32_t *zr_counts, uint64_t *zr_masks, int nq) {
+    if (nq < 1 || nq > kMaxForwardScales) return cudaErrorInvalidValue;
     FwdArgs a;
+    a.nq = nq; a.out_q_stride = n * (H / 8) * (W / 8) * 192; a.zr_q_stride = n * (H / 8) * (W / 8) * 3;
     a.zr_counts = zr_counts; a.zr_masks = (unsigned long long *)zr_masks;
     a.g = make_geom(n, H, W, 3, 4);
     a.img = (const double *)rgb; a.frame_stride = frame_stride_bytes; a.table = table; a.table_dtype = table_dtype;
     a.out = out; a.ref = nullptr; a.mv = nullptr; a.sr = 0; a.pred_out = nullptr; a.och = 3; a.run_flag = nullptr;
     if (a.g.total_tiles == 0) return cudaSuccess;
-    const size_t smem = 3200 + (size_t)kWarpsPerCta * kRgbBuf;
+    const size_t smem = (size_t)nq * 3072 + 128 + (size_t)kWarpsPerCta * kRgbBuf;      // <= 113 KB: two CTAs per SM
     cudaError_t e;
-    if ((e = set_smem(k_forward_rgb8_tma, smem)) != cudaSuccess) return e;
-    k_forward_rgb8_tma<<<grid_for(a.g.total_tiles, kWarpsPerCta, device, 2), kWarpsPerCta * 32, smem, st>>>(a);
+    const int grid = grid_for(a.g.total_tiles, kWarpsPerCta, device, 2);
+    if (nq == 1) {
+        if ((e = set_smem(k_forward_rgb8_tma<false>, smem)) != cudaSuccess) return e;
+        k_forward_rgb8_tma<false><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
+    } else {
+        if ((e = set_smem(k_forward_rgb8_tma<true>, (size_t)kMaxForwardScales * 3072 + 128 + (size_t)kWarpsPerCta * kRgbBuf)) != cudaSuccess) return e;   // a cap, not the launch size
+        k_forward_rgb8_tma<true><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
+    }
     return cudaGetLastError();
 }
 

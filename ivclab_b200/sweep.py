@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib  # noqa: F401
-from .codec import IntraBlockCoder
+from .codec import IntraBlockCoder, forward_rgb_multi
 
 __all__ = ["RateDistortionSweep"]
 
@@ -53,8 +53,9 @@ class RateDistortionSweep:
         else:
             sse, hist, outside = out
         sp = torch.cuda.current_stream(d_rgb.device).cuda_stream
+        zz_all = forward_rgb_multi(self.coders, d_rgb)                       # rgb2ycbcr + DCT ONCE, quantise + zig-zag per scale
         for qi, coder in enumerate(self.coders):
-            zz = coder.forward_rgb(d_rgb)                                    # rgb2ycbcr + DCT + quantise + zig-zag
+            zz = zz_all[qi]
             _lib.check(_lib.lib.ivc_zerorun_symbol_histogram(
                 d_rgb.device.index, sp, zz.data_ptr(), n, zz.numel() // 64 // n, self.eob, self.lo, self.nb,
                 hist[qi, at:at + n].data_ptr(), outside[qi, at:at + n].data_ptr()), "ivc_zerorun_symbol_histogram")

@@ -645,3 +645,25 @@ def test_dct_other_norms_bit_identical_to_scipy():
         assert d.is_cuda and np.array_equal(d.cpu().numpy(), O.dct8x8_forward(np.ascontiguousarray(view), norm))
     with pytest.raises(ValueError):
         ivc.DiscreteCosineTransform(norm="bogus").transform(view)
+
+
+def test_forward_rgb_multi_equals_per_scale_forward():
+    """One transform, many quantisations (the sweep's forward half): out[q] == IntraBlockCoder(q).forward_rgb(rgb) bit for
+    bit for the ten scales of exercises/ch4/ex1.py:385, float32 and float64 tables mixed, more than 16 scales (grouping),
+    with the zero-run counts / masks, on ragged tile counts (W = 16 * 7) and through the sweep itself."""
+    rng = np.random.default_rng(31)
+    rgb = torch.from_numpy(rng.integers(0, 256, size=(3, 40, 112, 3), dtype=np.uint8)).cuda()
+    scales = list(QS10) + [np.float64(0.4), np.float64(2.5)] + [0.1 * k for k in range(1, 8)]            # 19 tables, two dtypes
+    coders = [ivc.IntraBlockCoder(q) for q in scales]
+    zz, counts, masks = ivc.forward_rgb_multi(coders, rgb, zr=True)
+    assert zz.shape == (len(scales), 3, 5, 14, 3, 64)
+    for qi, c in enumerate(coders):
+        one, c1, m1 = c.forward_rgb(rgb, zr=True)
+        assert torch.equal(zz[qi], one) and torch.equal(counts[qi], c1) and torch.equal(masks[qi], m1)
+    assert torch.equal(ivc.forward_rgb_multi(coders[:3], rgb), zz[:3])
+    o = O.intra_forward(O.rgb2ycbcr(rgb[1].cpu().numpy()), coders[4].quant.get_quantization_table())    # the oracle on one frame
+    assert np.array_equal(zz[4, 1].cpu().numpy(), o)
+    with pytest.raises(ValueError):
+        ivc.forward_rgb_multi(coders, rgb[..., :100, :])
+    with pytest.raises(ValueError):
+        ivc.forward_rgb_multi(coders, rgb.cpu())
