@@ -53,9 +53,10 @@ class RateDistortionSweep:
         else:
             sse, hist, outside = out
         sp = torch.cuda.current_stream(d_rgb.device).cuda_stream
-        zz_all = forward_rgb_multi(self.coders, d_rgb)                       # rgb2ycbcr + DCT ONCE, quantise + zig-zag per scale
+        # rgb2ycbcr + DCT ONCE, quantise + zig-zag per scale (widths that are not a multiple of 16: one forward per scale)
+        zz_all = forward_rgb_multi(self.coders, d_rgb) if d_rgb.dtype == torch.uint8 and d_rgb.shape[2] % 16 == 0 else None
         for qi, coder in enumerate(self.coders):
-            zz = zz_all[qi]
+            zz = zz_all[qi] if zz_all is not None else coder.forward_rgb(d_rgb)
             _lib.check(_lib.lib.ivc_zerorun_symbol_histogram(
                 d_rgb.device.index, sp, zz.data_ptr(), n, zz.numel() // 64 // n, self.eob, self.lo, self.nb,
                 hist[qi, at:at + n].data_ptr(), outside[qi, at:at + n].data_ptr()), "ivc_zerorun_symbol_histogram")
