@@ -6,7 +6,6 @@ per direction.  Results are identical to calling the four drop-in classes one af
 written once.  All entry points accept a single image/frame or a batch (leading axis)."""
 from __future__ import annotations
 
-import numpy as np
 import torch
 
 from . import _lib

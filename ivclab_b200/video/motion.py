@@ -1,7 +1,6 @@
 """``ivclab.video.MotionCompensator`` on the B200 (reference: ivclab/video/motion.py:3-97)."""
 from __future__ import annotations
 
-import numpy as np
 import torch
 
 from .. import _lib

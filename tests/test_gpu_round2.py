@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLD, ROOT, load_golden
+from conftest import ROOT, load_golden
 
 pytestmark = pytest.mark.gpu
 

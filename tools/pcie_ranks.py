@@ -12,7 +12,6 @@ import json
 import os
 import subprocess
 import sys
-import time
 
 import torch
 import torch.distributed as dist
