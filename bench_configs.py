@@ -297,8 +297,8 @@ def cfg4(cx, ivc, n_seq=8, T=120, exact_pairs=4):
                        f"against the previous original frame, sequence s on rank s mod {cx.world} (strong scaling)",
            "ms": round(ms, 3), "frame_pairs": pairs, "mpixel_s": round(pairs * H * W / ms / 1e3, 1),
            "ms_per_frame_per_gpu": round(per_frame, 4) if per_frame else None,
-           "kernel": "k_me_mma16<double> (auto mode: integer-valued frames; cross term on mma.sync.m16n8k32.u8; IVC_ME_MMA=0 selects "
-                     "the dp4a kernel k_me_int<double,11,160>)",
+           "kernel": "k_f64_to_u8 (every frame of the sequence converted and validated once) + k_me_mma16<uint8> (cross term on "
+                     "mma.sync.m16n8k32.u8; IVC_ME_MMA=0 selects the dp4a kernel k_me_int<uint8,11,160>); both inside the timed region",
            "bound": "tensor pipe + shared-memory wavefronts + staging phases (profiles/README.md)",
            # 70 IMMA.16832 per block (4096 MAC each) against the measured mma.sync u8 rate; useful = 64 MAC per candidate
            "tensor_pipe_frac": round((H // 8) * (W // 8) * 70 * 4096 / (per_frame * 1e-3) / (MMA_U8_MAC_PER_CLK_SM * cx.sms * cx.sm_hz), 4) if per_frame else None,

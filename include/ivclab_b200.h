@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define IVC_ABI_VERSION 9
+#define IVC_ABI_VERSION 10
 
 /* element types */
 #define IVC_U8   0
@@ -155,8 +155,11 @@ int ivc_intra_inverse_sse(int device, void *stream,
  * mv_out: [n_frames, H/8, W/8, 1] int64, index = (dy+sr)*(2sr+1) + (dx+sr); first minimum in
  * (dy asc, dx asc) order over in-bounds candidates.
  * workspace: needed for IVC_ME_AUTO only (holds the device-side "not an integer frame" flag),
- * ivc_me_workspace_bytes() bytes; NULL otherwise. */
+ * ivc_me_workspace_bytes() bytes; NULL otherwise.  Optional: with ivc_me_workspace_bytes_planes() bytes (AUTO and INT modes,
+ * F64 frames, search_range >= 8) the frames are converted to uint8 planes -- and validated -- once, and the search reads the
+ * planes; two views of one contiguous sequence (cur = ref + one frame) are converted as n_frames + 1 planes.  Same vectors. */
 int64_t ivc_me_workspace_bytes(int64_t n_frames, int64_t H, int64_t W);
+int64_t ivc_me_workspace_bytes_planes(int64_t n_frames, int64_t H, int64_t W);
 int ivc_me_full_search(int device, void *stream,
                        const void *ref, const void *cur, int dtype,
                        int64_t n_frames, int64_t H, int64_t W,

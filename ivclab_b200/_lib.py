@@ -14,8 +14,8 @@ LIB_PATH = os.path.join(_HERE, "_C", "libivcb200.so")
 
 # element type codes (include/ivclab_b200.h)
 U8, I32, F32, F64, I64, I16 = 0, 1, 2, 3, 4, 5
-ABI_VERSION = 9            # include/ivclab_b200.h IVC_ABI_VERSION (2: entry points added in round 1, zero-run write gained a length; 3: ivc_rgb8_to_luma8;
-                           # 4: ivc_pframe_forward_ch, ivc_zerorun_symbol_histogram; 5: ivc_pframe_search_forward; 6: the _zr variants; 7: ivc_pframe_step; 8: ivc_dct8x8_norm; 9: ivc_intra_forward_rgb8_multi)
+ABI_VERSION = 10            # include/ivclab_b200.h IVC_ABI_VERSION (2: entry points added in round 1, zero-run write gained a length; 3: ivc_rgb8_to_luma8;
+                           # 4: ivc_pframe_forward_ch, ivc_zerorun_symbol_histogram; 5: ivc_pframe_search_forward; 6: the _zr variants; 7: ivc_pframe_step; 8: ivc_dct8x8_norm; 9: ivc_intra_forward_rgb8_multi; 10: ivc_me_workspace_bytes_planes)
 ME_AUTO, ME_EXACT, ME_INT = 0, 1, 2
 SSE_RGB8_AS_YCBCR = 103
 DIST_RGB, DIST_YCBCR = 1, 2
@@ -42,6 +42,7 @@ SIGNATURES = {
     "ivc_intra_inverse_sse_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "ivc_intra_inverse_sse": (_i, [_i, _p, _p, _i64, _i64, _i64, _p, _i, _p, _p, _i64, _i, _p, _i64, _p]),
     "ivc_me_workspace_bytes": (_i64, [_i64, _i64, _i64]),
+    "ivc_me_workspace_bytes_planes": (_i64, [_i64, _i64, _i64]),
     "ivc_me_full_search": (_i, [_i, _p, _p, _p, _i, _i64, _i64, _i64, _i64, _i64, _i, _i, _p, _p, _i64]),
     "ivc_me_full_search_intdtype": (_i, [_i, _p, _p, _p, _i, _i64, _i64, _i64, _i64, _i64, _i, _p]),
     "ivc_mc_reconstruct": (_i, [_i, _p, _p, _i, _i64, _i64, _i64, _i64, _p, _i, _p]),

@@ -217,7 +217,9 @@ class PFrameBlockCoder:
         mode = {"auto": _lib.ME_AUTO, "exact": _lib.ME_EXACT, "int": _lib.ME_INT}[self.motion_comp.me_mode]
         ws, ws_bytes = None, 0
         if mode != _lib.ME_EXACT:
-            ws_bytes = _lib.lib.ivc_me_workspace_bytes(N, H, W)
+            # wide searches of float64 frames: room for uint8 planes, so that the frames are converted once
+            planes = dt == torch.float64 and int(self.search_range) >= 8
+            ws_bytes = (_lib.lib.ivc_me_workspace_bytes_planes if planes else _lib.lib.ivc_me_workspace_bytes)(N, H, W)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=r.device)
         st = _lib.lib.ivc_me_full_search(dev_index(rv), stream_ptr(rv.device), rv.data_ptr(), cv.data_ptr(), code(dt),
                                          N, H, W, H * W, H * W, int(self.search_range), mode, mv.data_ptr(),

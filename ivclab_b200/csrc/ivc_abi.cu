@@ -208,6 +208,14 @@ int64_t ivc_me_workspace_bytes(int64_t n_frames, int64_t H, int64_t W) {
     return 256;                                // one device flag (kept 256-byte sized/aligned)
 }
 
+int64_t ivc_me_workspace_bytes_planes(int64_t n_frames, int64_t H, int64_t W) {
+    if (n_frames < 0 || H < 0 || W < 0) return -1;
+    return 256 + 2 * n_frames * H * W;         // the flag + a uint8 plane per reference and per current frame
+}
+
+// search ranges from which float64 frames are converted to uint8 planes first when the workspace has room for them
+static const int kMePlanesMinRange = 8;
+
 int ivc_me_full_search(int device, void *stream, const void *ref, const void *cur, int dtype, int64_t n_frames,
                        int64_t H, int64_t W, int64_t ref_frame_stride, int64_t cur_frame_stride, int search_range,
                        int mode, int64_t *mv_out, void *workspace, int64_t workspace_bytes) {
@@ -231,6 +239,30 @@ int ivc_me_full_search(int device, void *stream, const void *ref, const void *cu
     cudaStream_t st = (cudaStream_t)stream;
     const bool f32 = dtype == IVC_F32;
     cudaError_t e;
+    // A wide search reads every frame many times over (as a window with its halo and as blocks): with room in the workspace
+    // float64 frames are converted -- and, in AUTO mode, validated -- ONCE, and the search runs on the uint8 planes.
+    // Frames handed over as two views of one sequence (cur = ref + one frame) are converted once, not twice.
+    const int64_t plane = H * W;
+    const bool seq = cur_frame_stride == ref_frame_stride && ref_frame_stride == plane &&
+                     (const char *)cur == (const char *)ref + plane * 8;
+    if (dtype == IVC_F64 && mode != IVC_ME_EXACT && search_range >= kMePlanesMinRange && workspace &&
+        workspace_bytes >= 256 + (seq ? n_frames + 1 : 2 * n_frames) * plane && aligned16(ref) && aligned16(cur) &&
+        !(ref_frame_stride & 1) && !(cur_frame_stride & 1)) {
+        int *flag = mode == IVC_ME_AUTO ? (int *)workspace : nullptr;
+        unsigned char *planes = (unsigned char *)workspace + 256, *cur8 = planes + (seq ? plane : n_frames * plane);
+        if (flag && (e = cudaMemsetAsync(flag, 0, sizeof(int), st)) != cudaSuccess) return cuda_fail(e);
+        e = ivc::launch_f64_to_u8(device, st, ref, ref_frame_stride, seq ? n_frames + 1 : n_frames, plane, planes, flag);
+        if (e == cudaSuccess && !seq) e = ivc::launch_f64_to_u8(device, st, cur, cur_frame_stride, n_frames, plane, cur8, flag);
+        if (e == cudaSuccess)
+            e = ivc::launch_me_int(device, st, planes, cur8, IVC_U8, n_frames, H, W, plane, plane, search_range, mv_out, nullptr, 0);
+        if (e != cudaSuccess) return cuda_fail(e);
+        if (mode == IVC_ME_AUTO) {             // the exact kernel overwrites the vectors if a frame was not integer-valued
+            e = ivc::launch_me_exact(device, st, ref, cur, false, n_frames, H, W, ref_frame_stride, cur_frame_stride, search_range,
+                                     mv_out, flag, 1);
+            if (e != cudaSuccess) return cuda_fail(e);
+        }
+        return IVC_OK;
+    }
     if (mode != IVC_ME_EXACT) {
         // integer kernel: converts the frames to packed u8 while staging; in AUTO mode it validates them
         // and raises the device flag instead of producing vectors from a non-integer frame

@@ -34,6 +34,8 @@ cudaError_t launch_me_exact(int device, cudaStream_t st, const void *ref, const 
                             int *flag, int run_if);
 // pf_zz != nullptr: the fused kernel -- after the search every tile codes its blocks (MC + residual + DCT + quantise +
 // zig-zag, pf_och scan channels per block) from the staged bytes; only where me_pf_fusable(dtype, sr)
+cudaError_t launch_f64_to_u8(int device, cudaStream_t st, const void *src, int64_t frame_stride, int64_t n, int64_t plane,
+                             void *dst, int *flag);
 cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const void *cur, int dtype, int64_t n,
                           int64_t H, int64_t W, int64_t ref_fs, int64_t cur_fs, int sr, int64_t *mv, int *flag,
                           int check, const void *pf_table = nullptr, int pf_table_dtype = 0, int32_t *pf_zz = nullptr,

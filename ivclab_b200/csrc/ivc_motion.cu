@@ -1977,6 +1977,49 @@ cudaError_t launch_me_int(int device, cudaStream_t st, const void *ref, const vo
     return cudaErrorInvalidValue;
 }
 
+// ---- float64 frames -> uint8 planes, once per frame (the +-16 search reads every frame as a window AND as blocks, and the
+// conversion is a fifth of its time when done while staging); CHECK raises the flag on a value that is not an integer in
+// [0, 255], exactly like the staging of the integer kernels.  One thread = 8 pixels: four 16-byte loads, one 8-byte store.
+template <bool CHECK>
+__global__ void __launch_bounds__(256) k_f64_to_u8(const double *__restrict__ src, int64_t frame_stride, int64_t plane,
+                                                   unsigned char *__restrict__ dst, int *flag) {
+    const int64_t items = plane >> 3, f = blockIdx.y;
+    const double *sp = src + f * frame_stride;
+    unsigned char *dp = dst + f * plane;
+    bool bad = false;
+    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double t[2];
+            ldg16(sp + 8 * it + 2 * k, t);
+            v[2 * k] = t[0]; v[2 * k + 1] = t[1];
+        }
+        uint2 w;
+        w.x = pack_bytes(to_u8_fp<CHECK>(v[0], bad), to_u8_fp<CHECK>(v[1], bad), to_u8_fp<CHECK>(v[2], bad), to_u8_fp<CHECK>(v[3], bad));
+        w.y = pack_bytes(to_u8_fp<CHECK>(v[4], bad), to_u8_fp<CHECK>(v[5], bad), to_u8_fp<CHECK>(v[6], bad), to_u8_fp<CHECK>(v[7], bad));
+        *reinterpret_cast<uint2 *>(dp + 8 * it) = w;
+    }
+    if (CHECK && __syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
+// src: n frames of H*W float64 (16-byte aligned, frame_stride even, H*W a multiple of 8) -> dst [n][H*W] uint8
+cudaError_t launch_f64_to_u8(int device, cudaStream_t st, const void *src, int64_t frame_stride, int64_t n, int64_t plane,
+                             void *dst, int *flag) {
+    if (n == 0 || plane == 0) return cudaSuccess;
+    int64_t gx = (plane / 8 + 255) / 256;
+    const int64_t cap = (int64_t)sm_count(device) * 8;
+    if (gx > cap) gx = cap;
+    for (int64_t f0 = 0; f0 < n; f0 += 65535) {
+        const unsigned nf = (unsigned)(n - f0 < 65535 ? n - f0 : 65535);
+        const double *sp = (const double *)src + f0 * frame_stride;
+        unsigned char *dp = (unsigned char *)dst + f0 * plane;
+        if (flag) k_f64_to_u8<true><<<dim3((unsigned)gx, nf), 256, 0, st>>>(sp, frame_stride, plane, dp, flag);
+        else k_f64_to_u8<false><<<dim3((unsigned)gx, nf), 256, 0, st>>>(sp, frame_stride, plane, dp, nullptr);
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_mc(int device, cudaStream_t st, const void *ref, int elem_size, int64_t n, int64_t H, int64_t W,
                       int64_t C, const int64_t *mv, int sr, void *out) {
     McArgs a;

@@ -62,7 +62,8 @@ class MotionCompensator:
         mode = _MODES[self.me_mode]
         ws, ws_bytes = None, 0
         if mode != _lib.ME_EXACT:
-            ws_bytes = _lib.lib.ivc_me_workspace_bytes(1, H, W)
+            planes = dt == torch.float64 and int(self.search_range) >= 8      # wide search: convert the frames to bytes once
+            ws_bytes = (_lib.lib.ivc_me_workspace_bytes_planes if planes else _lib.lib.ivc_me_workspace_bytes)(1, H, W)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=ref.device)
         st = _lib.lib.ivc_me_full_search(dev_index(ref), stream_ptr(ref.device), ref.data_ptr(), cur.data_ptr(),
                                          code(dt), 1, H, W, H * W, H * W, int(self.search_range), mode,

@@ -667,3 +667,39 @@ def test_forward_rgb_multi_equals_per_scale_forward():
         ivc.forward_rgb_multi(coders, rgb[..., :100, :])
     with pytest.raises(ValueError):
         ivc.forward_rgb_multi(coders, rgb.cpu())
+
+
+def test_wide_search_through_uint8_planes():
+    """ivc_me_full_search with room for planes in the workspace (float64 frames, range >= 8): the frames are converted to
+    uint8 once and the search reads the planes -- same vectors as the search that converts while staging (minimal
+    workspace, through the raw ABI) and as the oracle; two views of one sequence and two separate tensors; AUTO mode with a
+    non-integer frame still ends in the exact kernel."""
+    from ivclab_b200 import _lib as L
+    from ivclab_b200._runtime import code, dev_index, stream_ptr
+    seq = torch.from_numpy(O.moving_sequence(123, 4, 72, 136)).cuda()              # integer-valued float64, ragged tiles
+    ref, cur = seq[:-1], seq[1:]                                                   # views of one sequence
+    N, H, W = ref.shape
+
+    def raw(r, c, sr, mode, ws_bytes):
+        mv = torch.empty((N, H // 8, W // 8, 1), dtype=torch.int64, device=r.device)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=r.device)
+        st = L.lib.ivc_me_full_search(dev_index(r), stream_ptr(r.device), r.data_ptr(), c.data_ptr(), code(torch.float64), N, H, W,
+                                      H * W, H * W, sr, mode, mv.data_ptr(), ws.data_ptr(), ws_bytes)
+        L.check(st, "ivc_me_full_search")
+        return mv
+    small, big = L.lib.ivc_me_workspace_bytes(N, H, W), L.lib.ivc_me_workspace_bytes_planes(N, H, W)
+    assert big == 256 + 2 * N * H * W
+    for sr in (8, 16):
+        want = np.stack([O.me_full_search(ref[i].cpu().numpy(), cur[i].cpu().numpy(), sr) for i in range(N)])
+        for mode in (L.ME_AUTO, L.ME_INT):
+            a = raw(ref, cur, sr, mode, small)                                      # converts while staging
+            b = raw(ref, cur, sr, mode, big)                                        # one sequence: N + 1 planes
+            c = raw(ref.clone(), cur.clone(), sr, mode, big)                        # two tensors: 2 N planes
+            assert torch.equal(a, b) and torch.equal(a, c)
+            assert np.array_equal(a.cpu().numpy().reshape(want.shape), want)
+        pc = ivc.PFrameBlockCoder(1.0, sr)                                          # the class asks for the planes itself
+        assert torch.equal(pc.estimate(ref, cur), a)
+    noisy = seq + 0.25 * torch.rand_like(seq)                                       # not integer-valued: AUTO falls back on the device
+    a = raw(noisy[:-1], noisy[1:], 8, L.ME_AUTO, big)
+    b = raw(noisy[:-1], noisy[1:], 8, L.ME_EXACT, small)
+    assert torch.equal(a, b)

@@ -208,7 +208,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(raw, n), f"{n} declared in include/ivclab_b200.h but not exported"
     assert set(names) == set(_lib.SIGNATURES), "ctypes table and header disagree"
-    assert _lib.lib.ivc_abi_version() == _lib.ABI_VERSION == 9
+    assert _lib.lib.ivc_abi_version() == _lib.ABI_VERSION == 10
     assert b"sm_100a" in _lib.lib.ivc_build_info()
     assert _lib.lib.ivc_me_workspace_bytes(2, 16, 16) >= 4
     assert ivclab_b200.__version__
