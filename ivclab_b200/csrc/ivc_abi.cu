@@ -246,7 +246,7 @@ int ivc_me_full_search(int device, void *stream, const void *ref, const void *cu
     const bool seq = cur_frame_stride == ref_frame_stride && ref_frame_stride == plane &&
                      (const char *)cur == (const char *)ref + plane * 8;
     if (dtype == IVC_F64 && mode != IVC_ME_EXACT && search_range >= kMePlanesMinRange && workspace &&
-        workspace_bytes >= 256 + (seq ? n_frames + 1 : 2 * n_frames) * plane && aligned16(ref) && aligned16(cur) &&
+        workspace_bytes >= 256 + (seq ? n_frames + 1 : 2 * n_frames) * plane && aligned16(workspace) && aligned16(ref) && aligned16(cur) &&
         !(ref_frame_stride & 1) && !(cur_frame_stride & 1)) {
         int *flag = mode == IVC_ME_AUTO ? (int *)workspace : nullptr;
         unsigned char *planes = (unsigned char *)workspace + 256, *cur8 = planes + (seq ? plane : n_frames * plane);
